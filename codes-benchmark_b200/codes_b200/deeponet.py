@@ -1,0 +1,181 @@
+"""MultiONet (DeepONet with per-quantity split scalar products).
+
+Mirror of codes/surrogates/DeepONet/deeponet.py: ``branch_net`` / ``trunk_net``
+parameter containers with state_dict keys ``{branch,trunk}_net.network.*``,
+flat-row loader (branch = x0 repeated T times, trunk = time grid tiled N times),
+fit loop.  Forward = two fused dense chains + one segmented-dot kernel instead of
+2 nn.Sequential calls + a Python loop of 3*Q tiny kernels (deeponet.py:245-253).
+"""
+from __future__ import annotations
+
+from typing import TypeVar
+
+import numpy as np
+import torch
+from torch import nn
+from torch.utils.data import DataLoader
+
+from . import ops
+from .abstract_surrogate import AbstractSurrogateModel
+from .configs import MultiONetBaseConfig
+from .fcnn import _cached_chain, criterion_kind
+from .loaders import RowBatchIterable, make_loader
+from .utils import time_execution
+
+
+class _OperatorSubNet(nn.Module):
+    def __init__(self, input_size: int, hidden_size: int, output_size: int, num_hidden_layers: int,
+                 activation: nn.Module | None = None):
+        super().__init__()
+        activation = activation if activation is not None else nn.ReLU()
+        layers = [nn.Linear(input_size, hidden_size), activation]
+        for _ in range(num_hidden_layers - 1):
+            layers += [nn.Linear(hidden_size, hidden_size), activation]
+        layers.append(nn.Linear(hidden_size, output_size))
+        self.network = nn.Sequential(*layers)
+        self._activation = [activation]
+
+    def chain(self):
+        return _cached_chain(self, self.network, self._activation[0], "identity")
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        w, b = ops.sequential_params(self.network)
+        return ops.run_chain(self.chain(), x, w, b)
+
+
+class BranchNet(_OperatorSubNet):
+    """deeponet.py:15-48"""
+
+
+class TrunkNet(_OperatorSubNet):
+    """deeponet.py:51-84"""
+
+
+class OperatorNetwork(AbstractSurrogateModel):
+    """Abstract operator network (deeponet.py:87-137)."""
+
+    def __init__(self, device=None, n_quantities: int = 29, n_timesteps: int = 100,
+                 training_id: str | None = None, config: dict | None = None):
+        super().__init__(device=device, n_quantities=n_quantities, n_timesteps=n_timesteps,
+                         training_id=training_id, config=config)
+
+    def post_init_check(self):
+        if not hasattr(self, "branch_net") or not hasattr(self, "trunk_net"):
+            raise NotImplementedError("Child classes must initialize a branch_net and trunk_net.")
+
+    def forward(self, branch_input, trunk_input):
+        raise NotImplementedError("Forward method must be implemented by subclasses.")
+
+    @staticmethod
+    def _calculate_split_sizes(total_neurons: int, num_splits: int) -> list[int]:
+        base, rem = divmod(total_neurons, num_splits)
+        return [base + (1 if i < rem else 0) for i in range(num_splits)]
+
+
+OperatorNetworkType = TypeVar("OperatorNetworkType", bound=OperatorNetwork)
+
+
+class MultiONet(OperatorNetwork):
+    def __init__(self, device: str | None = None, n_quantities: int = 29, n_timesteps: int = 100,
+                 n_parameters: int = 0, training_id: str | None = None, config: dict | None = None):
+        super().__init__(device=device, n_quantities=n_quantities, n_timesteps=n_timesteps,
+                         training_id=training_id, config=config)
+        self.config = MultiONetBaseConfig(**self.config)
+        self.device = device
+        self.n_parameters = n_parameters
+        self.N = n_quantities
+        self.outputs = n_quantities * self.config.output_factor
+        branch_in = n_quantities - (self.config.trunk_input_size - 1)
+        trunk_in = self.config.trunk_input_size
+        if self.config.params_branch:
+            branch_in += n_parameters
+        else:
+            trunk_in += n_parameters
+        self.branch_net = BranchNet(branch_in, self.config.hidden_size, self.outputs,
+                                    self.config.branch_hidden_layers, self.config.activation).to(device)
+        self.trunk_net = TrunkNet(trunk_in, self.config.hidden_size, self.outputs,
+                                  self.config.trunk_hidden_layers, self.config.activation).to(device)
+
+    def forward(self, inputs) -> tuple[torch.Tensor, torch.Tensor]:
+        """(branch_input, trunk_input, targets) -> (y (B,Q), targets)  (deeponet.py:226-253)."""
+        branch_input, trunk_input, targets = (
+            v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v for v in inputs)
+        fused = ops.try_fused_multionet(self, branch_input, trunk_input)
+        if fused is not None:
+            return fused, targets
+        b = self.branch_net(branch_input)
+        t = self.trunk_net(trunk_input)
+        return ops.deeponet_combine(b, t, self.N), targets
+
+    # ------------------------------------------------------------------ data
+    def create_dataloader(self, data: np.ndarray, timesteps: np.ndarray, batch_size: int, shuffle: bool,
+                          dataset_params: np.ndarray | None, params_in_branch: bool, num_workers: int = 0,
+                          pin_memory: bool = True):
+        """rows r = n*T + t (deeponet.py:354-402)."""
+        n, T, Q = data.shape
+        branch = np.repeat(data[:, 0, :], T, axis=0)
+        trunk = np.tile(np.asarray(timesteps).reshape(1, -1), (n, 1)).reshape(-1, 1)
+        if dataset_params is not None:
+            rep = np.repeat(dataset_params, T, axis=0)
+            if params_in_branch:
+                branch = np.concatenate([branch, rep], axis=1)
+            else:
+                trunk = np.concatenate([trunk, rep], axis=1)
+        tensors = [torch.from_numpy(np.ascontiguousarray(a)).float()
+                   for a in (branch, trunk, data.reshape(-1, Q))]
+        pin = pin_memory and self.device is not None and "cuda" in self.device and torch.cuda.is_available()
+        ds = RowBatchIterable(tensors, batch_size, shuffle, pin=pin)
+        return make_loader(ds, self.device, num_workers)
+
+    def prepare_data(self, dataset_train, dataset_test, dataset_val, timesteps, batch_size, shuffle=True,
+                     dummy_timesteps=True, dataset_train_params=None, dataset_test_params=None,
+                     dataset_val_params=None):
+        if dummy_timesteps:
+            timesteps = np.linspace(0, 1, dataset_train.shape[1])
+        assert timesteps.shape[0] == dataset_train.shape[1], \
+            "Number of timesteps in timesteps array and dataset must match."
+        nw = getattr(self.config, "num_workers", 0)
+        pb = self.config.params_branch
+        loaders = [self.create_dataloader(dataset_train, timesteps, batch_size, shuffle,
+                                          dataset_train_params, pb, nw)]
+        for d, p in ((dataset_test, dataset_test_params), (dataset_val, dataset_val_params)):
+            loaders.append(None if d is None else
+                           self.create_dataloader(d, timesteps, batch_size, False, p, pb, nw))
+        return tuple(loaders)
+
+    # ------------------------------------------------------------------ training
+    @time_execution
+    def fit(self, train_loader: DataLoader, test_loader: DataLoader, epochs: int, position: int = 0,
+            description: str = "Training DeepONet", multi_objective: bool = False) -> None:
+        """deeponet.py:255-312."""
+        self.n_train_samples = int(len(train_loader.dataset) / self.n_timesteps)
+        criterion = self.config.loss_function
+        optimizer, scheduler = self.setup_optimizer_and_scheduler(epochs)
+        n_log = (epochs + self.update_epochs - 1) // self.update_epochs
+        self.train_loss, self.test_loss, self.MAE = (np.zeros(n_log) for _ in range(3))
+        progress_bar = self.setup_progress_bar(epochs, position, description)
+        self.train()
+        optimizer.train()
+        self.setup_checkpoint()
+        epoch = -1
+        for epoch in progress_bar:
+            self.epoch(train_loader, criterion, optimizer)
+            scheduler.step()
+            self.validate(epoch=epoch, train_loader=train_loader, test_loader=test_loader,
+                          optimizer=optimizer, progress_bar=progress_bar, total_epochs=epochs,
+                          multi_objective=multi_objective)
+        progress_bar.close()
+        self.n_epochs = epoch + 1
+        self.get_checkpoint(test_loader, criterion)
+
+    def epoch(self, data_loader: DataLoader, criterion: nn.Module, optimizer: torch.optim.Optimizer):
+        kind = criterion_kind(criterion)
+        for branch_input, trunk_input, targets in data_loader:
+            optimizer.zero_grad()
+            outputs, targets = self((branch_input, trunk_input, targets))
+            loss = ops.pointwise_loss(outputs, targets, kind)
+            loss.backward()
+            optimizer.step()
+
+
+AbstractSurrogateModel.register(MultiONet)

@@ -1,0 +1,68 @@
+"""Batch iterables behind the ``DataLoader`` facade of the four surrogates.
+
+Same batch-tuple layout, batch order and RNG stream as the reference iterables
+  FCFlatBatchIterable   codes/surrogates/FCNN/fcnn.py:14-35
+  FlatBatchIterable     codes/surrogates/DeepONet/don_utils.py:59-87
+  FlatSeqBatchIterable  codes/surrogates/LatentNeuralODE/utilities.py:35-55
+(one ``torch.randperm(N)`` on the CPU default generator per epoch when shuffling,
+ceil(N / batch) batches, ``len()`` = number of batches), but the base tensors are
+pinned once and un-shuffled batches are zero-copy slices instead of fancy-index
+gathers, so the per-step H2D copy can run asynchronously.
+"""
+from __future__ import annotations
+
+import math
+from typing import Sequence
+
+import torch
+from torch.utils.data import DataLoader, IterableDataset
+
+
+def _maybe_pin(t: torch.Tensor | None, pin: bool):
+    if t is None or not pin:
+        return t
+    try:
+        return t.pin_memory()
+    except RuntimeError:  # no CUDA runtime available: keep pageable memory
+        return t
+
+
+class RowBatchIterable(IterableDataset):
+    """Batches over the first dimension of several aligned tensors.
+
+    ``tensors`` are sliced / gathered together; ``constants`` are yielded unchanged
+    with every batch at the given tuple positions (e.g. the time grid of the latent
+    models); ``None`` entries in ``tensors`` stay ``None``.
+    """
+
+    def __init__(self, tensors: Sequence[torch.Tensor | None], batch_size: int, shuffle: bool,
+                 layout: Sequence[tuple[str, int]] | None = None, constants: Sequence[torch.Tensor] = (),
+                 pin: bool = False):
+        self.tensors = [_maybe_pin(t, pin) for t in tensors]
+        self.constants = [_maybe_pin(c, pin) for c in constants]
+        # layout: output tuple description, ("t", i) -> batched tensor i, ("c", i) -> constant i
+        self.layout = list(layout) if layout is not None else [("t", i) for i in range(len(tensors))]
+        self.N = next(t for t in self.tensors if t is not None).size(0)
+        self.bs = int(batch_size)
+        self.shuffle = bool(shuffle)
+        self.pin = pin
+
+    def __len__(self) -> int:
+        return math.ceil(self.N / self.bs)
+
+    def __iter__(self):
+        perm = torch.randperm(self.N) if self.shuffle else None
+        for start in range(0, self.N, self.bs):
+            if perm is None:
+                batch = [None if t is None else t[start:start + self.bs] for t in self.tensors]
+            else:
+                idx = perm[start:start + self.bs]
+                batch = [None if t is None else t[idx] for t in self.tensors]
+            yield tuple(batch[i] if kind == "t" else self.constants[i] for kind, i in self.layout)
+
+
+def make_loader(dataset: IterableDataset, device: str | None, num_workers: int = 0) -> DataLoader:
+    """``DataLoader(batch_size=None)``: the dataset already yields whole batches."""
+    pin = device is not None and "cuda" in str(device) and torch.cuda.is_available()
+    return DataLoader(dataset, batch_size=None, num_workers=num_workers, pin_memory=pin,
+                      persistent_workers=False)

@@ -1,0 +1,420 @@
+"""Torch-facing wrappers of the C ABI: tensors in, tensors out, autograd wired.
+
+Everything here launches kernels from ``libcodes_b200.so`` on the current CUDA
+stream of the tensors' device.  torch is used for memory (allocation, autograd
+bookkeeping) only; there is no torch compute on these paths and no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+from ._lib import check, lib, make_desc, ptr_array
+
+# --------------------------------------------------------------------------- helpers
+_ACT_NAMES = {
+    nn.Identity: "identity", nn.ReLU: "relu", nn.LeakyReLU: "leakyrelu", nn.Tanh: "tanh",
+    nn.GELU: "gelu", nn.ELU: "elu", nn.SiLU: "silu", nn.Softplus: "softplus", nn.Mish: "mish",
+    nn.Sigmoid: "sigmoid", nn.PReLU: "prelu",
+}
+
+
+def activation_spec(module: nn.Module) -> tuple[str, float]:
+    """Map a torch activation module instance to (kernel activation name, parameter)."""
+    for cls, name in _ACT_NAMES.items():
+        if type(module) is cls:
+            break
+    else:
+        raise NotImplementedError(
+            f"activation {type(module).__name__} has no codes_b200 kernel "
+            f"(supported: {sorted(set(_ACT_NAMES.values()))})")
+    param = 0.01
+    if name == "leakyrelu":
+        param = float(module.negative_slope)
+    elif name == "gelu" and getattr(module, "approximate", "none") != "none":
+        raise NotImplementedError("GELU(approximate='tanh') is not supported")
+    elif name == "elu" and float(module.alpha) != 1.0:
+        raise NotImplementedError("ELU alpha != 1 is not supported")
+    elif name == "softplus" and (float(module.beta) != 1.0 or float(module.threshold) != 20.0):
+        raise NotImplementedError("Softplus beta/threshold other than defaults are not supported")
+    elif name == "prelu":
+        if module.weight.numel() != 1:
+            raise NotImplementedError("PReLU with per-channel slopes is not supported")
+        param = float(module.weight.detach().reshape(-1)[0])
+    return name, param
+
+
+def _stream(t: Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require_cuda(*tensors: Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "codes_b200 kernels need CUDA tensors (device 'cuda:N'); there is no CPU fallback")
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _p(t) -> C.c_void_p:
+    return C.c_void_p(None if t is None else t.data_ptr())
+
+
+# --------------------------------------------------------------------------- MLP chain
+class ChainSpec:
+    """Static description of an nn.Sequential of Linear(+activation) layers."""
+
+    def __init__(self, dims: Sequence[int], act: str, final_act: str = "identity", act_param: float = 0.01):
+        self.dims = [int(d) for d in dims]
+        self.act, self.final_act, self.act_param = act, final_act, float(act_param)
+        self.desc = make_desc(self.dims, act, final_act, act_param)
+
+    @property
+    def n_layers(self) -> int:
+        return len(self.dims) - 1
+
+    def macs_per_row(self) -> int:
+        return sum(a * b for a, b in zip(self.dims[:-1], self.dims[1:]))
+
+
+class _MlpChainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec: ChainSpec, x: Tensor, *params: Tensor):
+        n = spec.n_layers
+        weights, biases = params[:n], params[n:]
+        _require_cuda(x, *weights)
+        x2 = _f32c(x.reshape(-1, spec.dims[0]))
+        rows = x2.shape[0]
+        y = torch.empty((rows, spec.dims[-1]), device=x.device, dtype=torch.float32)
+        need_grad = any(ctx.needs_input_grad) and rows > 0
+        if rows == 0:
+            ctx.empty = True
+            return y.reshape(*x.shape[:-1], spec.dims[-1])
+        L = lib()
+        with torch.cuda.device(x.device):
+            saved = None
+            if need_grad:
+                nf = L.cb_mlp_saved_floats(C.byref(spec.desc), rows)
+                saved = torch.empty(max(int(nf), 1), device=x.device, dtype=torch.float32)
+            wsf = int(L.cb_mlp_workspace_floats(C.byref(spec.desc), rows, 0)) if (saved is None and n > 1) else 0
+            ws = torch.empty(max(wsf, 1), device=x.device, dtype=torch.float32)
+            wl = [_f32c(w) for w in weights]
+            bl = [None if b is None else _f32c(b) for b in biases]
+            check(L.cb_mlp_forward_f32(C.byref(spec.desc), ptr_array(wl), ptr_array(bl), _p(x2), rows,
+                                       _p(y), _p(saved), _p(ws), wsf, _stream(x)), "mlp_forward_f32")
+        if need_grad:
+            ctx.spec = spec
+            ctx.x_shape = x.shape
+            ctx.save_for_backward(x2, saved, *wl)
+            ctx.has_bias = [b is not None for b in biases]
+        return y.reshape(*x.shape[:-1], spec.dims[-1])
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        spec = ctx.spec
+        n = spec.n_layers
+        x2, saved, *wl = ctx.saved_tensors
+        rows = x2.shape[0]
+        dy2 = _f32c(dy.reshape(rows, spec.dims[-1]))
+        dev = x2.device
+        L = lib()
+        need_dx = ctx.needs_input_grad[1]
+        with torch.cuda.device(dev):
+            dW = [torch.empty_like(w) for w in wl]
+            db = [torch.empty(w.shape[0], device=dev, dtype=torch.float32) if hb else None
+                  for w, hb in zip(wl, ctx.has_bias)]
+            dx = torch.empty_like(x2) if need_dx else None
+            wsf = int(L.cb_mlp_workspace_floats(C.byref(spec.desc), rows, 1))
+            ws = torch.empty(wsf, device=dev, dtype=torch.float32)
+            check(L.cb_mlp_backward_f32(C.byref(spec.desc), ptr_array(wl), _p(x2), _p(saved), _p(dy2), rows,
+                                        ptr_array(dW), ptr_array(db), _p(dx), _p(ws), wsf, _stream(x2)),
+                  "mlp_backward_f32")
+        gx = dx.reshape(ctx.x_shape) if need_dx else None
+        return (None, gx, *dW, *db)
+
+
+def mlp_chain(spec: ChainSpec, x: Tensor, weights: Sequence[Tensor], biases: Sequence[Tensor | None]) -> Tensor:
+    """y = chain(x) on the last dimension of ``x`` (fp32 FFMA path, exact mode)."""
+    return _MlpChainFn.apply(spec, x, *weights, *biases)
+
+
+def sequential_params(seq: nn.Sequential):
+    """(weights, biases) of the nn.Linear members of an nn.Sequential, in order."""
+    lin = [m for m in seq if isinstance(m, nn.Linear)]
+    return [m.weight for m in lin], [m.bias for m in lin]
+
+
+def sequential_spec(seq: nn.Sequential, activation: nn.Module, final_act: str = "identity") -> ChainSpec:
+    lin = [m for m in seq if isinstance(m, nn.Linear)]
+    dims = [lin[0].in_features] + [m.out_features for m in lin]
+    name, param = activation_spec(activation)
+    return ChainSpec(dims, name, final_act, param)
+
+
+# --------------------------------------------------------------------------- MultiONet combine
+class _CombineFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, branch: Tensor, trunk: Tensor, n_quantities: int):
+        _require_cuda(branch, trunk)
+        b, t = _f32c(branch), _f32c(trunk)
+        rows, n_out = b.shape
+        y = torch.empty((rows, n_quantities), device=b.device, dtype=torch.float32)
+        with torch.cuda.device(b.device):
+            check(lib().cb_deeponet_combine_fwd(_p(b), _p(t), rows, n_out, n_quantities, _p(y), _stream(b)),
+                  "deeponet_combine_fwd")
+        ctx.save_for_backward(b, t)
+        ctx.q = n_quantities
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        b, t = ctx.saved_tensors
+        rows, n_out = b.shape
+        dy = _f32c(dy)
+        db, dt = torch.empty_like(b), torch.empty_like(t)
+        with torch.cuda.device(b.device):
+            check(lib().cb_deeponet_combine_bwd(_p(b), _p(t), _p(dy), rows, n_out, ctx.q, _p(db), _p(dt),
+                                                _stream(b)), "deeponet_combine_bwd")
+        return db, dt, None
+
+
+def deeponet_combine(branch: Tensor, trunk: Tensor, n_quantities: int) -> Tensor:
+    return _CombineFn.apply(branch, trunk, n_quantities)
+
+
+# --------------------------------------------------------------------------- LatentPoly polynomial
+class _PolyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coef: Tensor, z0: Tensor, t: Tensor):
+        _require_cuda(coef, z0, t)
+        coef, z0, t = _f32c(coef), _f32c(z0), _f32c(t)
+        B, Lat = z0.shape
+        deg = coef.shape[1]
+        T = t.shape[0]
+        z = torch.empty((B, T, Lat), device=z0.device, dtype=torch.float32)
+        with torch.cuda.device(z0.device):
+            check(lib().cb_poly_eval_fwd(_p(coef), _p(z0), _p(t), B, T, Lat, deg, _p(z), _stream(z0)),
+                  "poly_eval_fwd")
+        ctx.save_for_backward(t)
+        ctx.shape = (B, T, Lat, deg)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz: Tensor):
+        (t,) = ctx.saved_tensors
+        B, T, Lat, deg = ctx.shape
+        dz = _f32c(dz)
+        dev = dz.device
+        dz0 = torch.empty((B, Lat), device=dev, dtype=torch.float32)
+        dcoef = torch.empty((Lat, deg), device=dev, dtype=torch.float32)
+        wsf = 128 * T * Lat
+        ws = torch.empty(wsf, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(lib().cb_poly_eval_bwd(_p(dz), _p(t), B, T, Lat, deg, _p(dz0), _p(dcoef), _p(ws), wsf,
+                                         _stream(dz)), "poly_eval_bwd")
+        return dcoef, dz0, None
+
+
+def poly_eval(coef: Tensor, z0: Tensor, t: Tensor) -> Tensor:
+    """z[b,t,:] = z0[b,:] + sum_i coef[:,i-1] t^i."""
+    return _PolyFn.apply(coef, z0, t)
+
+
+# --------------------------------------------------------------------------- losses
+def _loss_ws(dev, n_floats: int) -> Tensor:
+    return torch.empty(max(n_floats, 1), device=dev, dtype=torch.float32)
+
+
+def _pointwise_loss_raw(pred: Tensor, target: Tensor, kind: str, scale: float, want_grad: bool):
+    _require_cuda(pred, target)
+    p, t = _f32c(pred), _f32c(target)
+    n = p.numel()
+    dev = p.device
+    loss = torch.empty((), device=dev, dtype=torch.float32)
+    dpred = torch.empty_like(p) if want_grad else None
+    wsf = 4096
+    ws = _loss_ws(dev, wsf)
+    with torch.cuda.device(dev):
+        check(lib().cb_pointwise_loss(_p(p), _p(t), n, _lib.LOSS_IDS[kind], scale, _p(loss), _p(dpred),
+                                      _p(ws), wsf, _stream(p)), "pointwise_loss")
+    return loss, dpred
+
+
+class _PointwiseLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred: Tensor, target: Tensor, kind: str, scale: float):
+        loss, dpred = _pointwise_loss_raw(pred, target, kind, scale, True)
+        ctx.save_for_backward(dpred)
+        ctx.shape = pred.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        (dpred,) = ctx.saved_tensors
+        return (dpred * g).reshape(ctx.shape), None, None, None
+
+
+def pointwise_loss(pred: Tensor, target: Tensor, kind: str = "mse", scale: float = 1.0) -> Tensor:
+    """scale * mean(crit(pred - target)); crit in {mse, smoothl1 (beta=1), l1}."""
+    if torch.is_grad_enabled() and pred.requires_grad:
+        return _PointwiseLossFn.apply(pred, target, kind, scale)
+    return _pointwise_loss_raw(pred.detach(), target.detach(), kind, scale, False)[0]
+
+
+def _latent_loss_raw(x_hat, x, n_timesteps_h, kind, w0, w2, w3, want_grad: bool):
+    _require_cuda(x_hat, x)
+    xh, xt = _f32c(x_hat), _f32c(x)
+    B, T, Q = xh.shape
+    dev = xh.device
+    loss = torch.empty((), device=dev, dtype=torch.float32)
+    dxh = torch.empty_like(xh) if want_grad else None
+    wsf = (B * Q + 31) // 32 + 8
+    ws = _loss_ws(dev, wsf)
+    with torch.cuda.device(dev):
+        check(lib().cb_latent_loss_fwd_bwd(_p(xh), _p(xt), B, T, Q, int(n_timesteps_h), _lib.LOSS_IDS[kind],
+                                           w0, w2, w3, _p(loss), _p(dxh), _p(ws), wsf, _stream(xh)),
+              "latent_loss_fwd_bwd")
+    return loss, dxh
+
+
+class _LatentLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_hat: Tensor, x: Tensor, n_timesteps_h: int, kind: str, w0: float, w2: float, w3: float):
+        loss, dxh = _latent_loss_raw(x_hat, x, n_timesteps_h, kind, w0, w2, w3, True)
+        ctx.save_for_backward(dxh)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        (dxh,) = ctx.saved_tensors
+        return dxh * g, None, None, None, None, None, None
+
+
+def latent_traj_loss(x_hat: Tensor, x: Tensor, n_timesteps_h: int, kind: str, w0: float, w2: float, w3: float):
+    """w0*crit(x_hat,x) + w2*MSE(D1) + w3*MSE(D2) with h = 1/n_timesteps_h (fused fwd+bwd)."""
+    if torch.is_grad_enabled() and x_hat.requires_grad:
+        return _LatentLossFn.apply(x_hat, x, n_timesteps_h, kind, float(w0), float(w2), float(w3))
+    return _latent_loss_raw(x_hat.detach(), x.detach(), n_timesteps_h, kind, float(w0), float(w2), float(w3),
+                            False)[0]
+
+
+# --------------------------------------------------------------------------- denormalise
+def denormalize(x: Tensor, mode: int, dmin: Tensor | None, dmax: Tensor | None, pow10: bool) -> Tensor:
+    _require_cuda(x)
+    x2 = _f32c(x)
+    q = x2.shape[-1]
+    rows = x2.numel() // q
+    out = torch.empty_like(x2)
+    with torch.cuda.device(x2.device):
+        check(lib().cb_denormalize(_p(x2), rows, q, mode, _p(dmin), _p(dmax), int(pow10), _p(out), _stream(x2)),
+              "denormalize")
+    return out
+
+
+# --------------------------------------------------------------------------- latent ODE solve
+def lnode_solve(spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor, tanh_reg: bool, reg_factor: float,
+                rtol: float, atol: float, max_steps: int = 100000, return_stats: bool = False):
+    """Adaptive Tsit5 solve of dz/dt = ODE-net(z); z0:(B,L) -> (B,T,L) fp32."""
+    _require_cuda(z0, t_eval)
+    z0c, tc = _f32c(z0), _f32c(t_eval)
+    B, Lat = z0c.shape
+    T = tc.shape[0]
+    d = _lib.LnodeDesc()
+    d.ode = spec.desc
+    d.tanh_reg = int(bool(tanh_reg))
+    d.reg_factor = float(reg_factor)
+    d.rtol, d.atol, d.max_steps = float(rtol), float(atol), int(max_steps)
+    dev = z0c.device
+    out = torch.empty((B, T, Lat), device=dev, dtype=torch.float32)
+    stats = torch.empty((B, 2), device=dev, dtype=torch.int32)
+    L = lib()
+    wsf = int(L.cb_lnode_workspace_floats(C.byref(d)))
+    if wsf < 0:
+        check(-1, "lnode_workspace_floats")
+    ws = torch.empty(wsf, device=dev, dtype=torch.float32)
+    wl = [_f32c(w.detach()) for w in weights]
+    bl = [_f32c(b.detach()) for b in biases]
+    with torch.cuda.device(dev):
+        check(L.cb_lnode_solve_fwd(C.byref(d), ptr_array(wl), ptr_array(bl), _p(z0c), _p(tc), B, T, _p(out),
+                                   _p(stats), _p(ws), wsf, _stream(z0c)), "lnode_solve_fwd")
+    return (out, stats) if return_stats else out
+
+
+# --------------------------------------------------------------------------- precision dispatch
+_PRECISION = {"mode": None}
+
+
+def precision_mode() -> str:
+    """'fp32' (FFMA, exact mode) or 'bf16' (tcgen05 tensor cores, fp32 accumulate).
+
+    Selected by ``set_precision`` or the ``CODES_B200_PRECISION`` environment variable;
+    the default is 'bf16' for inference-only dense chains and always 'fp32' for anything
+    that needs gradients or feeds the ODE step-size controller.
+    """
+    import os
+    if _PRECISION["mode"] is None:
+        _PRECISION["mode"] = os.environ.get("CODES_B200_PRECISION", "bf16").lower()
+    return _PRECISION["mode"]
+
+
+def set_precision(mode: str) -> None:
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION["mode"] = mode
+
+
+def run_chain(spec: ChainSpec, x: Tensor, weights, biases) -> Tensor:
+    """Dispatch a dense chain: tensor-core path for gradient-free calls in bf16 mode,
+    fp32 FFMA path otherwise."""
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in weights))
+    if not needs_grad and precision_mode() == "bf16":
+        from . import tc
+        if tc.supported(spec):
+            return tc.chain_forward(spec, x, weights, biases)
+    return mlp_chain(spec, x, weights, biases)
+
+
+def try_fused_multionet(model, branch_input: Tensor, trunk_input: Tensor):
+    """Fully fused tensor-core MultiONet forward (both chains + combine), or None when the
+    fp32 path must be used (gradients needed, fp32 mode, unsupported shape)."""
+    if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
+        return None
+    if precision_mode() != "bf16":
+        return None
+    from . import tc
+    if not hasattr(tc, "multionet_forward"):
+        return None
+    return tc.multionet_forward(model, branch_input, trunk_input)
+
+
+# --------------------------------------------------------------------------- latent ODE (autograd wrapper)
+class _LnodeSolveFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wrapper, spec: ChainSpec, z0: Tensor, t_eval: Tensor, reg_factor: Tensor, *params: Tensor):
+        n = spec.n_layers
+        weights, biases = params[:n], params[n:]
+        cfg = wrapper.config
+        out, stats = lnode_solve(spec, weights, biases, z0.detach(), t_eval, cfg.ode_tanh_reg,
+                                 float(reg_factor.detach()) if cfg.ode_tanh_reg else 1.0,
+                                 cfg.rtol, cfg.atol, return_stats=True)
+        wrapper.last_solver_stats = stats
+        return out
+
+    @staticmethod
+    def backward(ctx, dz: Tensor):
+        raise NotImplementedError(
+            "codes_b200: the backward sweep of the persistent latent-ODE integrator is not built yet "
+            "(LatentNeuralODE inference is supported; training lands next round)")
+
+
+def lnode_integrate(wrapper, spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor) -> Tensor:
+    return _LnodeSolveFn.apply(wrapper, spec, z0, t_eval, wrapper.ode.reg_factor, *weights, *biases)

@@ -1,0 +1,571 @@
+// HBM-bound kernels of the surrogate path: MultiONet combine, LatentPoly polynomial,
+// losses (+gradients), multi-tensor optimizers, denormalise.  All reductions are
+// two-pass with a fixed partition -> bitwise run-to-run deterministic
+// (the reference trains under torch.use_deterministic_algorithms, run_training.py:35).
+#include "cb_common.cuh"
+
+namespace cb {
+
+constexpr int kThreads = 256;
+
+static inline int grid_for(int64_t n, int per_thread = 4) {
+  int64_t blocks = (n + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum, result valid in thread 0 (fixed tree -> deterministic)
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float sm[32];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = (lane < (int)((blockDim.x + 31) >> 5)) ? sm[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+__global__ void final_sum_kernel(const float* __restrict__ part, int n, float scale,
+                                 float* __restrict__ out) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  s = block_sum(s);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+
+// --------------------------------------------------------------- MultiONet combine
+// one warp per row; segment q = columns [q*base + min(q,rem), +base + (q<rem))
+__global__ void combine_fwd_kernel(const float* __restrict__ br, const float* __restrict__ tr,
+                                   int64_t rows, int n_out, int Q, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int base = n_out / Q, rem = n_out % Q;
+  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows;
+       r += (int64_t)gridDim.x * wpb) {
+    const float* b = br + r * n_out;
+    const float* t = tr + r * n_out;
+    int start = 0;
+    for (int q = 0; q < Q; ++q) {
+      const int sz = base + (q < rem ? 1 : 0);
+      float s = 0.f;
+      for (int k = lane; k < sz; k += 32) s = fmaf(__ldg(b + start + k), __ldg(t + start + k), s);
+      s = warp_sum(s);
+      if (lane == 0) y[r * Q + q] = s;
+      start += sz;
+    }
+  }
+}
+
+__global__ void combine_bwd_kernel(const float* __restrict__ br, const float* __restrict__ tr,
+                                   const float* __restrict__ dy, int64_t rows, int n_out, int Q,
+                                   float* __restrict__ dbr, float* __restrict__ dtr) {
+  const int base = n_out / Q, rem = n_out % Q;
+  const int cut = rem * (base + 1);
+  const int64_t total = rows * n_out;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / n_out;
+    const int k = (int)(i - r * n_out);
+    const int q = (k < cut) ? k / (base + 1) : rem + (k - cut) / base;
+    const float g = __ldg(dy + r * Q + q);
+    dbr[i] = g * __ldg(tr + i);
+    dtr[i] = g * __ldg(br + i);
+  }
+}
+
+// --------------------------------------------------------------- LatentPoly
+__global__ void poly_fwd_kernel(const float* __restrict__ C, const float* __restrict__ z0,
+                                const float* __restrict__ t, int64_t B, int T, int L, int deg,
+                                float* __restrict__ z) {
+  const int64_t total = B * T * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int l = (int)(i % L);
+    const int64_t bt = i / L;
+    const int ti = (int)(bt % T);
+    const int64_t b = bt / T;
+    const float tv = __ldg(t + ti);
+    float p = 0.f;
+    for (int d = deg - 1; d >= 0; --d) p = fmaf(p, tv, __ldg(C + l * deg + d));  // Horner
+    z[i] = fmaf(p, tv, __ldg(z0 + b * L + l));
+  }
+}
+
+// dz0[b,l] = sum_t dz[b,t,l]
+__global__ void poly_bwd_z0_kernel(const float* __restrict__ dz, int64_t B, int T, int L,
+                                   float* __restrict__ dz0) {
+  const int64_t total = B * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / L;
+    const int l = (int)(i - b * L);
+    float s = 0.f;
+    for (int ti = 0; ti < T; ++ti) s += dz[(b * T + ti) * L + l];
+    dz0[i] = s;
+  }
+}
+
+// partial[s][j] = sum over a slab of b of dz viewed as (B, T*L)
+__global__ void batch_colsum_partial_kernel(const float* __restrict__ x, int64_t B, int cols,
+                                            int64_t b_per_split, float* __restrict__ part) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  const int64_t b0 = (int64_t)blockIdx.y * b_per_split;
+  const int64_t b1 = min(B, b0 + b_per_split);
+  float s = 0.f;
+  for (int64_t b = b0; b < b1; ++b) s += x[b * cols + j];
+  part[(int64_t)blockIdx.y * cols + j] = s;
+}
+
+// dC[l,i] = sum_t (sum_s part[s][t*L+l]) * t^(i+1)
+__global__ void poly_bwd_coef_kernel(const float* __restrict__ part, int splits,
+                                     const float* __restrict__ t, int T, int L, int deg,
+                                     float* __restrict__ dC) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * deg) return;
+  const int l = i / deg, d = i % deg;
+  float acc = 0.f;
+  for (int ti = 0; ti < T; ++ti) {
+    float g = 0.f;
+    for (int s = 0; s < splits; ++s) g += part[(int64_t)s * T * L + ti * L + l];
+    const float tv = t[ti];
+    float pw = tv;
+    for (int k = 0; k < d; ++k) pw *= tv;
+    acc = fmaf(g, pw, acc);
+  }
+  dC[i] = acc;
+}
+
+// --------------------------------------------------------------- losses
+__device__ __forceinline__ void loss_terms(int kind, float d, float& val, float& grad) {
+  if (kind == CB_LOSS_MSE) { val = d * d; grad = 2.f * d; }
+  else if (kind == CB_LOSS_SMOOTHL1) {
+    const float a = fabsf(d);
+    if (a < 1.f) { val = 0.5f * d * d; grad = d; } else { val = a - 0.5f; grad = d > 0.f ? 1.f : -1.f; }
+  } else { val = fabsf(d); grad = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
+}
+
+__global__ void pointwise_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                      int64_t n, int kind, float gscale, float* __restrict__ part,
+                                      float* __restrict__ dpred) {
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v, g;
+    loss_terms(kind, pred[i] - __ldg(tgt + i), v, g);
+    s += v;
+    if (dpred) dpred[i] = g * gscale;
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+// trajectory + derivative terms of ModelWrapper.total_loss; one thread per (b,q) column.
+// smem: d[T][blockDim], g[T][blockDim]
+__global__ void latent_loss_kernel(const float* __restrict__ xhat, const float* __restrict__ x,
+                                   int64_t B, int T, int Q, float h, int kind, float w0, float w2,
+                                   float w3, float* __restrict__ part, float* __restrict__ dxhat) {
+  extern __shared__ float sm[];
+  const int nt = blockDim.x;
+  float* d = sm;
+  float* g = sm + (size_t)T * nt;
+  const int64_t cols = B * Q;
+  const int64_t c = (int64_t)blockIdx.x * nt + threadIdx.x;
+  const float inv_n = 1.f / (float)((double)B * T * Q);
+  const float ih = 1.f / h, ih2 = 1.f / (h * h);
+  float s = 0.f;
+  if (c < cols) {
+    const int64_t b = c / Q;
+    const int q = (int)(c - b * Q);
+    const int64_t base = b * T * Q + q;
+    float traj = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float dv = xhat[base + (int64_t)t * Q] - __ldg(x + base + (int64_t)t * Q);
+      d[t * nt + threadIdx.x] = dv;
+      float v, gr;
+      loss_terms(kind, dv, v, gr);
+      traj += v;
+      g[t * nt + threadIdx.x] = w0 * gr * inv_n;
+    }
+#define D_(t) d[(t) * nt + threadIdx.x]
+#define G_(t) g[(t) * nt + threadIdx.x]
+    float s1 = 0.f, s2 = 0.f;
+    const float c1 = 2.f * w2 * inv_n, c2 = 2.f * w3 * inv_n;
+    for (int t = 0; t < T; ++t) {
+      // first derivative row t (latent_neural_ode.py:554-563)
+      float e1;
+      if (t == 0) { e1 = (D_(1) - D_(0)) * ih; G_(1) += c1 * e1 * ih; G_(0) -= c1 * e1 * ih; }
+      else if (t == T - 1) { e1 = (D_(T - 1) - D_(T - 2)) * ih; G_(T - 1) += c1 * e1 * ih; G_(T - 2) -= c1 * e1 * ih; }
+      else { e1 = (D_(t + 1) - D_(t - 1)) * (0.5f * ih); G_(t + 1) += c1 * e1 * 0.5f * ih; G_(t - 1) -= c1 * e1 * 0.5f * ih; }
+      s1 += e1 * e1;
+      // second derivative row t (latent_neural_ode.py:565-582)
+      float e2;
+      if (t == 0) {
+        e2 = (2.f * D_(0) - 5.f * D_(1) + 4.f * D_(2) - D_(3)) * ih2;
+        const float k = c2 * e2 * ih2;
+        G_(0) += 2.f * k; G_(1) -= 5.f * k; G_(2) += 4.f * k; G_(3) -= k;
+      } else if (t == T - 1) {
+        e2 = (2.f * D_(T - 1) - 5.f * D_(T - 2) + 4.f * D_(T - 3) - D_(T - 4)) * ih2;
+        const float k = c2 * e2 * ih2;
+        G_(T - 1) += 2.f * k; G_(T - 2) -= 5.f * k; G_(T - 3) += 4.f * k; G_(T - 4) -= k;
+      } else {
+        e2 = (D_(t + 1) - 2.f * D_(t) + D_(t - 1)) * ih2;
+        const float k = c2 * e2 * ih2;
+        G_(t + 1) += k; G_(t) -= 2.f * k; G_(t - 1) += k;
+      }
+      s2 += e2 * e2;
+    }
+    s = (w0 * traj + w2 * s1 + w3 * s2) * inv_n;
+    if (dxhat)
+      for (int t = 0; t < T; ++t) dxhat[base + (int64_t)t * Q] = G_(t);
+#undef D_
+#undef G_
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+// --------------------------------------------------------------- optimizers
+constexpr int kMaxTensors = 48;
+struct TensorList {
+  float* p[kMaxTensors];
+  const float* g[kMaxTensors];
+  float* s1[kMaxTensors];
+  float* s2[kMaxTensors];
+  int64_t n[kMaxTensors];
+};
+
+struct AdamArgs { float lr, b1, b2, eps, wd, bc1, bc2_sqrt; };
+__global__ void adamw_kernel(const TensorList tl, const AdamArgs a) {
+  const int t = blockIdx.y;
+  const int64_t n = tl.n[t];
+  float* __restrict__ p = tl.p[t];
+  const float* __restrict__ g = tl.g[t];
+  float* __restrict__ m = tl.s1[t];
+  float* __restrict__ v = tl.s2[t];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    // torch.optim.AdamW (single-tensor formulation)
+    float pv = p[i] * (1.f - a.lr * a.wd);
+    const float gv = g[i];
+    const float mv = a.b1 * m[i] + (1.f - a.b1) * gv;
+    const float vv = a.b2 * v[i] + (1.f - a.b2) * gv * gv;
+    const float denom = sqrtf(vv) / a.bc2_sqrt + a.eps;
+    pv -= (a.lr / a.bc1) * (mv / denom);
+    p[i] = pv; m[i] = mv; v[i] = vv;
+  }
+}
+
+struct SgdArgs { float lr, momentum, wd; int first; };
+__global__ void sgd_kernel(const TensorList tl, const SgdArgs a) {
+  const int t = blockIdx.y;
+  const int64_t n = tl.n[t];
+  float* __restrict__ p = tl.p[t];
+  const float* __restrict__ g = tl.g[t];
+  float* __restrict__ buf = tl.s1[t];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float gv = g[i] + a.wd * p[i];
+    if (a.momentum != 0.f) {
+      gv = a.first ? gv : a.momentum * buf[i] + gv;
+      buf[i] = gv;
+    }
+    p[i] -= a.lr * gv;
+  }
+}
+
+struct SfArgs { float lr, beta1, b2, eps, wd, ckp1, bc2; int adam; };
+__global__ void schedulefree_kernel(const TensorList tl, const SfArgs a) {
+  const int t = blockIdx.y;
+  const int64_t n = tl.n[t];
+  float* __restrict__ y = tl.p[t];
+  const float* __restrict__ g = tl.g[t];
+  float* __restrict__ z = tl.s1[t];
+  float* __restrict__ v = tl.s2[t];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float yv = y[i], zv = z[i], gn = g[i];
+    if (a.adam) {
+      const float vv = a.b2 * v[i] + (1.f - a.b2) * gn * gn;
+      v[i] = vv;
+      gn = gn / (sqrtf(vv / a.bc2) + a.eps);
+    }
+    gn += a.wd * yv;
+    yv += a.ckp1 * (zv - yv);
+    yv += a.lr * (a.beta1 * (1.f - a.ckp1) - 1.f) * gn;
+    zv -= a.lr * gn;
+    y[i] = yv; z[i] = zv;
+  }
+}
+
+__global__ void lerp_kernel(const TensorList tl, float w) {
+  const int t = blockIdx.y;
+  const int64_t n = tl.n[t];
+  float* __restrict__ p = tl.p[t];
+  const float* __restrict__ z = tl.s1[t];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    p[i] = pv + w * (z[i] - pv);  // torch.lerp(p, z, w)
+  }
+}
+
+static int tensor_grid_x(const int64_t* sizes, int n) {
+  int64_t mx = 1;
+  for (int i = 0; i < n; ++i) mx = sizes[i] > mx ? sizes[i] : mx;
+  int64_t b = (mx + kThreads * 4 - 1) / (kThreads * 4);
+  if (b > 64) b = 64;
+  return (int)b;
+}
+
+// --------------------------------------------------------------- denormalise
+__global__ void denorm_kernel(const float* __restrict__ x, int64_t total, int Q, int mode,
+                              const float* __restrict__ dmin, const float* __restrict__ dmax,
+                              int pow10, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (mode == 1) {
+      const int q = (int)(i % Q);
+      const float lo = __ldg(dmin + q), hi = __ldg(dmax + q);
+      v = (v + 1.f) * (hi - lo) / 2.f + lo;  // abstract_surrogate.py:468 op order
+    }
+    if (pow10) v = exp10f(v);
+    out[i] = v;
+  }
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int32_t cb_deeponet_combine_fwd(const float* d_branch, const float* d_trunk, int64_t rows,
+                                           int32_t n_outputs, int32_t n_quantities, float* d_y,
+                                           void* stream) {
+  CB_CHECK_ARG(d_branch && d_trunk && d_y, "NULL pointer argument");
+  CB_CHECK_ARG(rows >= 0 && n_quantities >= 1 && n_outputs >= n_quantities,
+               "bad combine shape rows=%lld outputs=%d Q=%d", (long long)rows, n_outputs, n_quantities);
+  if (rows == 0) return CB_OK;
+  const int wpb = kThreads / 32;
+  int64_t blocks = (rows + wpb - 1) / wpb;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  combine_fwd_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+      d_branch, d_trunk, rows, n_outputs, n_quantities, d_y);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int32_t cb_deeponet_combine_bwd(const float* d_branch, const float* d_trunk,
+                                           const float* d_dy, int64_t rows, int32_t n_outputs,
+                                           int32_t n_quantities, float* d_dbranch, float* d_dtrunk,
+                                           void* stream) {
+  CB_CHECK_ARG(d_branch && d_trunk && d_dy && d_dbranch && d_dtrunk, "NULL pointer argument");
+  CB_CHECK_ARG(rows >= 0 && n_quantities >= 1 && n_outputs >= n_quantities, "bad combine shape");
+  if (rows == 0) return CB_OK;
+  combine_bwd_kernel<<<grid_for(rows * n_outputs), kThreads, 0, (cudaStream_t)stream>>>(
+      d_branch, d_trunk, d_dy, rows, n_outputs, n_quantities, d_dbranch, d_dtrunk);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int32_t cb_poly_eval_fwd(const float* d_coef, const float* d_z0, const float* d_t,
+                                    int64_t batch, int32_t n_t, int32_t latent, int32_t degree,
+                                    float* d_z, void* stream) {
+  CB_CHECK_ARG(d_coef && d_z0 && d_t && d_z, "NULL pointer argument");
+  CB_CHECK_ARG(batch >= 0 && n_t >= 1 && latent >= 1 && degree >= 1, "bad polynomial shape");
+  if (batch == 0) return CB_OK;
+  poly_fwd_kernel<<<grid_for(batch * n_t * latent), kThreads, 0, (cudaStream_t)stream>>>(
+      d_coef, d_z0, d_t, batch, n_t, latent, degree, d_z);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+static int poly_splits(int64_t batch) {
+  int64_t s = (batch + 63) / 64;
+  return (int)(s < 1 ? 1 : (s > 128 ? 128 : s));
+}
+
+extern "C" int32_t cb_poly_eval_bwd(const float* d_dz, const float* d_t, int64_t batch, int32_t n_t,
+                                    int32_t latent, int32_t degree, float* d_dz0, float* d_dcoef,
+                                    float* d_ws, int64_t ws_floats, void* stream) {
+  CB_CHECK_ARG(d_dz && d_t && d_dz0 && d_dcoef && d_ws, "NULL pointer argument");
+  CB_CHECK_ARG(batch >= 1 && n_t >= 1 && latent >= 1 && degree >= 1, "bad polynomial shape");
+  const int S = poly_splits(batch);
+  const int cols = n_t * latent;
+  if (ws_floats < (int64_t)S * cols) {
+    set_error("workspace too small: need %lld floats", (long long)S * cols);
+    return CB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  poly_bwd_z0_kernel<<<grid_for(batch * latent, 1), kThreads, 0, st>>>(d_dz, batch, n_t, latent, d_dz0);
+  CB_LAUNCH_CHECK();
+  const int64_t bps = (batch + S - 1) / S;
+  dim3 grid((cols + 127) / 128, S);
+  batch_colsum_partial_kernel<<<grid, 128, 0, st>>>(d_dz, batch, cols, bps, d_ws);
+  CB_LAUNCH_CHECK();
+  poly_bwd_coef_kernel<<<(latent * degree + 63) / 64, 64, 0, st>>>(d_ws, S, d_t, n_t, latent, degree, d_dcoef);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int32_t cb_pointwise_loss(const float* d_pred, const float* d_target, int64_t n,
+                                     int32_t kind, float scale, float* d_loss, float* d_dpred,
+                                     float* d_ws, int64_t ws_floats, void* stream) {
+  CB_CHECK_ARG(d_pred && d_target && d_loss && d_ws, "NULL pointer argument");
+  CB_CHECK_ARG(n >= 1, "empty loss input");
+  CB_CHECK_ARG(kind >= CB_LOSS_MSE && kind <= CB_LOSS_L1, "unknown loss kind %d", kind);
+  const int blocks = grid_for(n);
+  if (ws_floats < blocks) {
+    set_error("workspace too small: need %d floats", blocks);
+    return CB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv_n = (float)(1.0 / (double)n);
+  pointwise_loss_kernel<<<blocks, kThreads, 0, st>>>(d_pred, d_target, n, kind, scale * inv_n, d_ws, d_dpred);
+  CB_LAUNCH_CHECK();
+  final_sum_kernel<<<1, 256, 0, st>>>(d_ws, blocks, scale * inv_n, d_loss);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int32_t cb_latent_loss_fwd_bwd(const float* d_xhat, const float* d_x, int64_t batch,
+                                          int32_t n_t, int32_t n_q, int32_t n_timesteps_h,
+                                          int32_t kind, float w0, float w2, float w3, float* d_loss,
+                                          float* d_dxhat, float* d_ws, int64_t ws_floats,
+                                          void* stream) {
+  CB_CHECK_ARG(d_xhat && d_x && d_loss && d_ws, "NULL pointer argument");
+  CB_CHECK_ARG(batch >= 1 && n_q >= 1, "bad loss shape");
+  CB_CHECK_ARG(n_t >= 4, "latent loss needs >= 4 time points (4-point one-sided stencil), got %d", n_t);
+  CB_CHECK_ARG(n_timesteps_h >= 1, "n_timesteps_h must be >= 1");
+  CB_CHECK_ARG(kind == CB_LOSS_MSE || kind == CB_LOSS_SMOOTHL1, "unknown loss kind %d", kind);
+  int nt = 64;
+  size_t smem = (size_t)2 * n_t * nt * sizeof(float);
+  while (smem > 200 * 1024 && nt > 32) { nt /= 2; smem = (size_t)2 * n_t * nt * sizeof(float); }
+  CB_CHECK_ARG(smem <= 200 * 1024, "n_t=%d too large for the fused loss kernel", n_t);
+  const int64_t cols = batch * n_q;
+  const int64_t blocks = (cols + nt - 1) / nt;
+  CB_CHECK_ARG(blocks < (1ll << 31), "too many columns");
+  if (ws_floats < blocks) {
+    set_error("workspace too small: need %lld floats", (long long)blocks);
+    return CB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (smem > 48 * 1024)
+    CB_CUDA(cudaFuncSetAttribute(latent_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  latent_loss_kernel<<<(unsigned)blocks, nt, smem, st>>>(d_xhat, d_x, batch, n_t, n_q,
+                                                        1.f / (float)n_timesteps_h, kind, w0, w2, w3,
+                                                        d_ws, d_dxhat);
+  CB_LAUNCH_CHECK();
+  final_sum_kernel<<<1, 256, 0, st>>>(d_ws, (int)blocks, 1.f, d_loss);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+template <class F>
+static int32_t for_tensor_chunks(float* const* p, const float* const* g, float* const* s1,
+                                 float* const* s2, const int64_t* sizes, int n_tensors, F launch) {
+  CB_CHECK_ARG(p && sizes && n_tensors >= 0, "bad tensor list");
+  for (int c0 = 0; c0 < n_tensors; c0 += kMaxTensors) {
+    const int cnt = (n_tensors - c0 < kMaxTensors) ? n_tensors - c0 : kMaxTensors;
+    TensorList tl{};
+    for (int i = 0; i < cnt; ++i) {
+      tl.p[i] = p[c0 + i];
+      tl.g[i] = g ? g[c0 + i] : nullptr;
+      tl.s1[i] = s1 ? s1[c0 + i] : nullptr;
+      tl.s2[i] = s2 ? s2[c0 + i] : nullptr;
+      tl.n[i] = sizes[c0 + i];
+      CB_CHECK_ARG(tl.p[i] != nullptr && tl.n[i] >= 0, "bad tensor %d", c0 + i);
+    }
+    dim3 grid(tensor_grid_x(sizes + c0, cnt), cnt);
+    launch(tl, grid);
+    CB_LAUNCH_CHECK();
+  }
+  return CB_OK;
+}
+
+extern "C" int32_t cb_adamw_step(float* const* d_p, const float* const* d_g, float* const* d_m,
+                                 float* const* d_v, const int64_t* sizes, int32_t n_tensors,
+                                 float lr, float beta1, float beta2, float eps, float weight_decay,
+                                 int64_t step, void* stream) {
+  CB_CHECK_ARG(d_g && d_m && d_v && step >= 1, "bad AdamW arguments");
+  AdamArgs a{lr, beta1, beta2, eps, weight_decay,
+             (float)(1.0 - pow((double)beta1, (double)step)),
+             (float)sqrt(1.0 - pow((double)beta2, (double)step))};
+  cudaStream_t st = (cudaStream_t)stream;
+  return for_tensor_chunks(d_p, d_g, d_m, d_v, sizes, n_tensors, [&](const TensorList& tl, dim3 grid) {
+    adamw_kernel<<<grid, kThreads, 0, st>>>(tl, a);
+  });
+}
+
+extern "C" int32_t cb_sgd_step(float* const* d_p, const float* const* d_g, float* const* d_buf,
+                               const int64_t* sizes, int32_t n_tensors, float lr, float momentum,
+                               float weight_decay, int64_t step, void* stream) {
+  CB_CHECK_ARG(d_g && step >= 1 && (momentum == 0.f || d_buf), "bad SGD arguments");
+  SgdArgs a{lr, momentum, weight_decay, step == 1 ? 1 : 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  return for_tensor_chunks(d_p, d_g, d_buf, nullptr, sizes, n_tensors, [&](const TensorList& tl, dim3 grid) {
+    sgd_kernel<<<grid, kThreads, 0, st>>>(tl, a);
+  });
+}
+
+extern "C" int32_t cb_schedulefree_adamw_step(float* const* d_y, const float* const* d_g,
+                                              float* const* d_z, float* const* d_v,
+                                              const int64_t* sizes, int32_t n_tensors, float lr_k,
+                                              float beta1, float beta2, float eps, float weight_decay,
+                                              float ckp1, float bias_correction2, void* stream) {
+  CB_CHECK_ARG(d_g && d_z && d_v, "bad schedule-free AdamW arguments");
+  SfArgs a{lr_k, beta1, beta2, eps, weight_decay, ckp1, bias_correction2, 1};
+  cudaStream_t st = (cudaStream_t)stream;
+  return for_tensor_chunks(d_y, d_g, d_z, d_v, sizes, n_tensors, [&](const TensorList& tl, dim3 grid) {
+    schedulefree_kernel<<<grid, kThreads, 0, st>>>(tl, a);
+  });
+}
+
+extern "C" int32_t cb_schedulefree_sgd_step(float* const* d_y, const float* const* d_g,
+                                            float* const* d_z, const int64_t* sizes,
+                                            int32_t n_tensors, float lr_k, float momentum,
+                                            float weight_decay, float ckp1, void* stream) {
+  CB_CHECK_ARG(d_g && d_z, "bad schedule-free SGD arguments");
+  SfArgs a{lr_k, momentum, 0.f, 0.f, weight_decay, ckp1, 1.f, 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  return for_tensor_chunks(d_y, d_g, d_z, nullptr, sizes, n_tensors, [&](const TensorList& tl, dim3 grid) {
+    schedulefree_kernel<<<grid, kThreads, 0, st>>>(tl, a);
+  });
+}
+
+extern "C" int32_t cb_lerp_tensors(float* const* d_p, const float* const* d_z, const int64_t* sizes,
+                                   int32_t n_tensors, float w, void* stream) {
+  CB_CHECK_ARG(d_z, "bad lerp arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  return for_tensor_chunks(d_p, nullptr, const_cast<float* const*>(reinterpret_cast<const float* const*>(d_z)),
+                           nullptr, sizes, n_tensors, [&](const TensorList& tl, dim3 grid) {
+    lerp_kernel<<<grid, kThreads, 0, st>>>(tl, w);
+  });
+}
+
+extern "C" int32_t cb_denormalize(const float* d_x, int64_t n_rows, int32_t n_q, int32_t mode,
+                                  const float* d_min, const float* d_max, int32_t pow10,
+                                  float* d_out, void* stream) {
+  CB_CHECK_ARG(d_x && d_out, "NULL pointer argument");
+  CB_CHECK_ARG(n_rows >= 0 && n_q >= 1, "bad shape");
+  CB_CHECK_ARG(mode == 0 || (mode == 1 && d_min && d_max), "bad normalisation mode %d", mode);
+  if (n_rows == 0) return CB_OK;
+  denorm_kernel<<<grid_for(n_rows * n_q), kThreads, 0, (cudaStream_t)stream>>>(
+      d_x, n_rows * n_q, n_q, mode, d_min, d_max, pow10, d_out);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}

@@ -1,0 +1,208 @@
+/*
+ * codes_b200.h -- C ABI of libcodes_b200.so, the sm_100a replacement for the
+ * surrogate compute path of robin-janssen/CODES-Benchmark.
+ *
+ * The reference has no native code: every entry point below replaces a group
+ * of stock PyTorch ops inside one reference function (cited per function, paths
+ * relative to the reference root).  The Python plug-in classes in
+ * codes-benchmark_b200/codes_b200 bind these symbols with ctypes; INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative cb_status; the message
+ *    is available from cb_last_error() (thread-local).
+ *  - all pointers named d_* are CUDA device pointers borrowed for the duration
+ *    of the call (allocated and owned by the caller, e.g. torch tensors);
+ *    pointer *arrays* (W[], b[] ...) are host arrays of device pointers.
+ *  - all tensors are fp32, row-major, contiguous unless stated.
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call
+ *    synchronises the device.  The only mutable global state is the launch
+ *    counter (atomic), so the library is re-entrant from several host threads
+ *    / devices.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    returns CB_ERR_CUDA.
+ */
+#ifndef CODES_B200_H
+#define CODES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_MAX_LAYERS 16
+#define CB_API __attribute__((visibility("default")))
+
+typedef enum {
+  CB_OK = 0,
+  CB_ERR_ARG = -1,     /* invalid argument / unsupported shape            */
+  CB_ERR_CUDA = -2,    /* CUDA runtime error (message has the details)    */
+  CB_ERR_WORKSPACE = -3 /* workspace too small                            */
+} cb_status;
+
+/* activation ids (torch.nn defaults; codes/tune/optuna_fcts.py:25-39) */
+typedef enum {
+  CB_ACT_IDENTITY = 0, CB_ACT_RELU = 1, CB_ACT_LEAKYRELU = 2, CB_ACT_TANH = 3,
+  CB_ACT_GELU = 4, CB_ACT_ELU = 5, CB_ACT_SILU = 6, CB_ACT_SOFTPLUS = 7,
+  CB_ACT_MISH = 8, CB_ACT_SIGMOID = 9, CB_ACT_PRELU = 10
+} cb_act;
+
+typedef enum { CB_LOSS_MSE = 0, CB_LOSS_SMOOTHL1 = 1, CB_LOSS_L1 = 2 } cb_loss_kind;
+
+/* An nn.Sequential of Linear(+activation) layers:
+ *   FullyConnectedNet   codes/surrogates/FCNN/fcnn.py:81-98
+ *   BranchNet/TrunkNet  codes/surrogates/DeepONet/deeponet.py:15-84
+ *   Encoder/Decoder     codes/surrogates/LatentNeuralODE/latent_neural_ode.py:687-742
+ *   ODE.mlp             codes/surrogates/LatentNeuralODE/latent_neural_ode.py:627-634
+ * dims[0] = input width, dims[i+1] = output width of Linear i (nn.Linear
+ * weight layout (out,in) row-major).  `act` follows every Linear but the last;
+ * `final_act` follows the last (TANH for the coders, IDENTITY otherwise). */
+typedef struct {
+  int32_t n_layers;
+  int32_t dims[CB_MAX_LAYERS + 1];
+  int32_t act;
+  int32_t final_act;
+  float act_param; /* negative slope for LEAKYRELU / PRELU */
+} cb_mlp_desc;
+
+CB_API const char* cb_last_error(void);
+CB_API int32_t cb_version(void);
+/* number of CUDA kernels this library has launched (process-wide) since the
+ * last cb_reset_launch_count() (bench.py's gpu_launches claim). */
+CB_API int64_t cb_launch_count(void);
+CB_API void cb_reset_launch_count(void);
+
+/* ---------------------------------------------------------------- fp32 path */
+/* floats needed in `d_saved` by cb_mlp_forward_f32 when training:
+ * rows * sum_i 2*dims[i+1]  (post- and pre-activation of every layer). */
+CB_API int64_t cb_mlp_saved_floats(const cb_mlp_desc* desc, int64_t rows);
+/* scratch floats for forward (ping-pong activations) / backward. */
+CB_API int64_t cb_mlp_workspace_floats(const cb_mlp_desc* desc, int64_t rows, int32_t backward);
+
+/* y = chain(x).  Replaces nn.Sequential.forward of the nets listed above.
+ * d_saved may be NULL (inference). d_x:(rows,dims[0]) d_y:(rows,dims[n]). */
+CB_API int32_t cb_mlp_forward_f32(const cb_mlp_desc* desc, const float* const* d_W,
+                           const float* const* d_b, const float* d_x, int64_t rows,
+                           float* d_y, float* d_saved, float* d_workspace,
+                           int64_t workspace_floats, void* stream);
+
+/* autograd of the chain (replaces loss.backward() through nn.Linear/activations,
+ * e.g. fcnn.py:291).  d_dW[i]/d_db[i] are OVERWRITTEN with the gradients
+ * (deterministic two-pass reduction, cf. run_training.py:35);
+ * d_dx may be NULL.  d_db[i] may be NULL for bias-free layers. */
+CB_API int32_t cb_mlp_backward_f32(const cb_mlp_desc* desc, const float* const* d_W,
+                            const float* d_x, const float* d_saved, const float* d_dy,
+                            int64_t rows, float* const* d_dW, float* const* d_db,
+                            float* d_dx, float* d_workspace, int64_t workspace_floats,
+                            void* stream);
+
+/* ------------------------------------------------------- MultiONet combine */
+/* y[r,q] = sum_{k in split_q} branch[r,k]*trunk[r,k]; split sizes follow
+ * OperatorNetwork._calculate_split_sizes (deeponet.py:130-137, :245-253). */
+CB_API int32_t cb_deeponet_combine_fwd(const float* d_branch, const float* d_trunk, int64_t rows,
+                                int32_t n_outputs, int32_t n_quantities, float* d_y,
+                                void* stream);
+CB_API int32_t cb_deeponet_combine_bwd(const float* d_branch, const float* d_trunk, const float* d_dy,
+                                int64_t rows, int32_t n_outputs, int32_t n_quantities,
+                                float* d_dbranch, float* d_dtrunk, void* stream);
+
+/* ----------------------------------------------------- LatentPoly polynomial */
+/* z[b,t,l] = z0[b,l] + sum_{i=1..deg} C[l,i-1]*t[t]^i
+ * (Polynomial.forward latent_poly.py:489-512 + broadcast add :380). */
+CB_API int32_t cb_poly_eval_fwd(const float* d_coef, const float* d_z0, const float* d_t,
+                         int64_t batch, int32_t n_t, int32_t latent, int32_t degree,
+                         float* d_z, void* stream);
+/* dz0[b,l] = sum_t dz[b,t,l];  dC[l,i-1] = sum_{b,t} dz[b,t,l]*t^i (deterministic). */
+CB_API int32_t cb_poly_eval_bwd(const float* d_dz, const float* d_t, int64_t batch, int32_t n_t,
+                         int32_t latent, int32_t degree, float* d_dz0, float* d_dcoef,
+                         float* d_workspace, int64_t workspace_floats, void* stream);
+
+/* ------------------------------------------------------------------- losses */
+/* mean-reduced nn.MSELoss / nn.SmoothL1Loss(beta=1) / nn.L1Loss and its gradient
+ * (fcnn.py:290-291, deeponet.py:350-351, abstract_surrogate.py:705-709).
+ * d_loss: 1 float.  d_dpred may be NULL (loss only). grad is scaled by `scale`. */
+CB_API int32_t cb_pointwise_loss(const float* d_pred, const float* d_target, int64_t n, int32_t kind,
+                          float scale, float* d_loss, float* d_dpred, float* d_workspace,
+                          int64_t workspace_floats, void* stream);
+/* ModelWrapper.total_loss trajectory + derivative terms
+ * (latent_neural_ode.py:522-582 == latent_poly.py:383-443):
+ *   w0*crit(x_hat,x) + w2*MSE(D1 x_hat, D1 x) + w3*MSE(D2 x_hat, D2 x), h=1/n_timesteps_h.
+ * The identity term (w1) is a pointwise MSE handled by cb_pointwise_loss.
+ * x_hat,x:(batch,T,Q). d_loss: 1 float; d_dxhat:(batch,T,Q) may be NULL. */
+CB_API int32_t cb_latent_loss_fwd_bwd(const float* d_xhat, const float* d_x, int64_t batch, int32_t n_t,
+                               int32_t n_q, int32_t n_timesteps_h, int32_t kind, float w0, float w2,
+                               float w3, float* d_loss, float* d_dxhat, float* d_workspace,
+                               int64_t workspace_floats, void* stream);
+
+/* --------------------------------------------------------------- optimizers */
+/* Multi-tensor updates over a flat list (abstract_surrogate.py:773-811).
+ * d_p/d_g/... are host arrays of device pointers, sizes[] element counts. */
+CB_API int32_t cb_adamw_step(float* const* d_p, const float* const* d_g, float* const* d_m,
+                      float* const* d_v, const int64_t* sizes, int32_t n_tensors, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                      void* stream);
+CB_API int32_t cb_sgd_step(float* const* d_p, const float* const* d_g, float* const* d_buf,
+                    const int64_t* sizes, int32_t n_tensors, float lr, float momentum,
+                    float weight_decay, int64_t step, void* stream);
+/* schedulefree 1.4.1 AdamWScheduleFree / SGDScheduleFree (train-mode step);
+ * ckp1, lr_k, bias_correction2 are computed on the host from the step index. */
+CB_API int32_t cb_schedulefree_adamw_step(float* const* d_y, const float* const* d_g, float* const* d_z,
+                                   float* const* d_v, const int64_t* sizes, int32_t n_tensors,
+                                   float lr_k, float beta1, float beta2, float eps,
+                                   float weight_decay, float ckp1, float bias_correction2,
+                                   void* stream);
+CB_API int32_t cb_schedulefree_sgd_step(float* const* d_y, const float* const* d_g, float* const* d_z,
+                                 const int64_t* sizes, int32_t n_tensors, float lr_k,
+                                 float momentum, float weight_decay, float ckp1, void* stream);
+/* p <- lerp(p, z, w) over all tensors (schedulefree .train()/.eval() switch). */
+CB_API int32_t cb_lerp_tensors(float* const* d_p, const float* const* d_z, const int64_t* sizes,
+                        int32_t n_tensors, float w, void* stream);
+
+/* -------------------------------------------------------------- denormalise */
+/* AbstractSurrogateModel.denormalize (abstract_surrogate.py:435-487) on (n_rows,n_q):
+ * mode 0 = none, 1 = minmax with per-quantity d_min/d_max (length n_q);
+ * pow10 != 0 applies 10**x.  In-place allowed (d_out == d_x). */
+CB_API int32_t cb_denormalize(const float* d_x, int64_t n_rows, int32_t n_q, int32_t mode,
+                       const float* d_min, const float* d_max, int32_t pow10, float* d_out,
+                       void* stream);
+
+/* ------------------------------------------------- latent ODE integration */
+typedef struct {
+  cb_mlp_desc ode;     /* ODE.mlp (latent->width x (ode_layers+1)->latent) */
+  int32_t tanh_reg;    /* ODE.forward :647-653  reg*tanh(out/reg)          */
+  float reg_factor;
+  double rtol, atol;   /* IntegralController (latent_neural_ode.py:463-465) */
+  int32_t max_steps;   /* safety bound on RK iterations per trajectory     */
+} cb_lnode_desc;
+
+/* Replaces self.solver.solve(InitialValueProblem(y0=z0,t_eval)) + sol.ys
+ * (latent_neural_ode.py:510-517; torchode Tsit5 + IntegralController):
+ * z0:(batch,L) fp32 (encoder output, upcast to fp64 inside), t_eval:(T,) fp32,
+ * z_out:(batch,T,L) fp32, stats:(batch,2) int32 = {steps, accepted} (may be NULL;
+ * steps is negated when max_steps was exhausted).  The workspace receives the
+ * k-major repacked ODE-net weights (cb_lnode_workspace_floats). */
+CB_API int64_t cb_lnode_workspace_floats(const cb_lnode_desc* desc);
+CB_API int32_t cb_lnode_solve_fwd(const cb_lnode_desc* desc, const float* const* d_W,
+                           const float* const* d_b, const float* d_z0, const float* d_t_eval,
+                           int64_t batch, int32_t n_t, float* d_z_out, int32_t* d_stats,
+                           float* d_workspace, int64_t workspace_floats, void* stream);
+
+/* --------------------------------------------------- tensor-core (bf16) path */
+/* Opaque plan for a fused bf16 MLP chain on tcgen05 (weights converted/padded
+ * to bf16, TMA descriptors, job table).  See DESIGN.md. */
+typedef struct cb_tc_chain cb_tc_chain;
+CB_API int32_t cb_tc_chain_create(const cb_mlp_desc* desc, int32_t device, cb_tc_chain** out);
+CB_API void cb_tc_chain_destroy(cb_tc_chain* plan);
+/* (re)load fp32 weights into the plan's bf16 buffers (after an optimizer step). */
+CB_API int32_t cb_tc_chain_set_weights(cb_tc_chain* plan, const float* const* d_W,
+                                const float* const* d_b, void* stream);
+/* y = chain(x) with bf16 operands / fp32 accumulate. */
+CB_API int32_t cb_tc_chain_forward(cb_tc_chain* plan, const float* d_x, int64_t rows, float* d_y,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CODES_B200_H */
