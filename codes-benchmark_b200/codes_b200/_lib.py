@@ -71,10 +71,18 @@ _SIGNATURES = {
     "cb_denormalize": (_I32, [_P, _I64, _I32, _I32, _P, _P, _I32, _P, _P]),
     "cb_lnode_workspace_floats": (_I64, [C.POINTER(LnodeDesc)]),
     "cb_lnode_solve_fwd": (_I32, [C.POINTER(LnodeDesc), _PP, _PP, _P, _P, _I64, _I32, _P, _P, _P, _I64, _P]),
+    "cb_tc_supported": (_I32, []),
+    "cb_tc_chain_supported": (_I32, [C.POINTER(MlpDesc)]),
     "cb_tc_chain_create": (_I32, [C.POINTER(MlpDesc), _I32, C.POINTER(_P)]),
     "cb_tc_chain_destroy": (None, [_P]),
     "cb_tc_chain_set_weights": (_I32, [_P, _PP, _PP, _P]),
     "cb_tc_chain_forward": (_I32, [_P, _P, _I64, _P, _P]),
+    "cb_tc_multionet_supported": (_I32, [C.POINTER(MlpDesc), C.POINTER(MlpDesc), _I32]),
+    "cb_tc_multionet_create": (_I32, [C.POINTER(MlpDesc), C.POINTER(MlpDesc), _I32, _I32, C.POINTER(_P)]),
+    "cb_tc_multionet_destroy": (None, [_P]),
+    "cb_tc_multionet_workspace_bytes": (_I64, [_P, _I64]),
+    "cb_tc_multionet_set_weights": (_I32, [_P, _PP, _PP, _PP, _PP, _P]),
+    "cb_tc_multionet_forward": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _P]),
 }
 
 

@@ -1,4 +1,6 @@
-"""Tensor-core (tcgen05, bf16 operands / fp32 accumulate) execution of dense chains."""
+"""Tensor-core (tcgen05, bf16 operands / fp32 accumulate) execution of dense chains and of the
+fused MultiONet forward.  Plans (bf16 weight caches + TMA descriptors) are cached per module /
+device and refreshed when the fp32 parameters change (optimizer step, load_state_dict)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -6,53 +8,121 @@ import weakref
 
 import torch
 
+from . import ops
 from ._lib import check, lib, ptr_array
 
-_PLANS: dict = {}
 _ENABLED = {"ok": None}
 
 
-def supported(spec) -> bool:
-    """Whether the tcgen05 chain kernel handles this chain (else: fp32 FFMA path)."""
+def available() -> bool:
+    """True when the current CUDA device can run the tcgen05 kernels (compute capability 10.x)."""
     if _ENABLED["ok"] is None:
-        _ENABLED["ok"] = bool(lib().cb_tc_supported()) if hasattr(lib(), "cb_tc_supported") else False
-    if not _ENABLED["ok"]:
-        return False
-    return bool(lib().cb_tc_chain_supported(C.byref(spec.desc)))
+        _ENABLED["ok"] = bool(torch.cuda.is_available() and lib().cb_tc_supported())
+    return _ENABLED["ok"]
 
 
-class _Plan:
+def supported(spec) -> bool:
+    """Whether the fused chain kernel handles this chain shape (else: fp32 FFMA path)."""
+    return available() and bool(lib().cb_tc_chain_supported(C.byref(spec.desc)))
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _versions(tensors):
+    return tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+
+
+def _f32(ts):
+    return [None if t is None else t.detach().float().contiguous() for t in ts]
+
+
+class _ChainPlan:
     def __init__(self, spec, device):
         self.handle = C.c_void_p()
-        check(lib().cb_tc_chain_create(C.byref(spec.desc), device.index or 0, C.byref(self.handle)),
-              "tc_chain_create")
+        with torch.cuda.device(device):
+            check(lib().cb_tc_chain_create(C.byref(spec.desc), device.index or 0, C.byref(self.handle)),
+                  "tc_chain_create")
         self.versions = None
-        weakref.finalize(self, lib().cb_tc_chain_destroy, self.handle)
+        self._fin = weakref.finalize(self, lib().cb_tc_chain_destroy, self.handle)
+
+
+_CHAIN_PLANS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 
 def chain_forward(spec, x, weights, biases):
+    """y = chain(x) on the tensor cores; x:(..., dims[0]) fp32 -> (..., dims[-1]) fp32."""
     dev = x.device
-    key = (id(spec), dev.index)
-    plan = _PLANS.get(key)
-    if plan is None or plan.spec_ref() is not spec:
-        plan = _Plan(spec, dev)
-        plan.spec_ref = weakref.ref(spec)
-        _PLANS[key] = plan
+    per_spec = _CHAIN_PLANS.setdefault(spec, {})
+    plan = per_spec.get(dev.index)
+    if plan is None:
+        plan = per_spec[dev.index] = _ChainPlan(spec, dev)
     x2 = x.reshape(-1, spec.dims[0])
     if x2.dtype != torch.float32 or not x2.is_contiguous():
         x2 = x2.float().contiguous()
     rows = x2.shape[0]
-    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     with torch.cuda.device(dev):
-        versions = tuple((w.data_ptr(), w._version) for w in weights) + \
-            tuple((b.data_ptr(), b._version) for b in biases if b is not None)
+        versions = _versions(weights) + _versions(biases)
         if versions != plan.versions:  # weights changed (optimizer step / load_state_dict)
-            wl = [w.detach().contiguous() for w in weights]
-            bl = [None if b is None else b.detach().contiguous() for b in biases]
-            check(lib().cb_tc_chain_set_weights(plan.handle, ptr_array(wl), ptr_array(bl), stream),
+            wl, bl = _f32(weights), _f32(biases)
+            check(lib().cb_tc_chain_set_weights(plan.handle, ptr_array(wl), ptr_array(bl), _stream(dev)),
                   "tc_chain_set_weights")
             plan.versions = versions
         y = torch.empty((rows, spec.dims[-1]), device=dev, dtype=torch.float32)
         check(lib().cb_tc_chain_forward(plan.handle, C.c_void_p(x2.data_ptr()), rows,
-                                        C.c_void_p(y.data_ptr()), stream), "tc_chain_forward")
+                                        C.c_void_p(y.data_ptr()), _stream(dev)), "tc_chain_forward")
     return y.reshape(*x.shape[:-1], spec.dims[-1])
+
+
+class _MultiONetPlan:
+    def __init__(self, bspec, tspec, q, device):
+        self.handle = C.c_void_p()
+        with torch.cuda.device(device):
+            check(lib().cb_tc_multionet_create(C.byref(bspec.desc), C.byref(tspec.desc), q, device.index or 0,
+                                               C.byref(self.handle)), "tc_multionet_create")
+        self.versions = None
+        self.workspace = None
+        self._fin = weakref.finalize(self, lib().cb_tc_multionet_destroy, self.handle)
+
+
+_MULTIONET_PLANS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def multionet_forward(model, branch_input, trunk_input):
+    """Fused MultiONet forward; returns None when the shape is not supported by the fused kernels."""
+    if not available():
+        return None
+    bspec, tspec = model.branch_net.chain(), model.trunk_net.chain()
+    q = model.N
+    if not lib().cb_tc_multionet_supported(C.byref(bspec.desc), C.byref(tspec.desc), q):
+        return None
+    dev = branch_input.device
+    per_model = _MULTIONET_PLANS.setdefault(model, {})
+    key = (dev.index, id(bspec), id(tspec))
+    plan = per_model.get(key)
+    if plan is None:
+        per_model.clear()
+        plan = per_model[key] = _MultiONetPlan(bspec, tspec, q, dev)
+    bw, bb = ops.sequential_params(model.branch_net.network)
+    tw, tb = ops.sequential_params(model.trunk_net.network)
+    b2 = branch_input.reshape(-1, bspec.dims[0]).float().contiguous()
+    t2 = trunk_input.reshape(-1, tspec.dims[0]).float().contiguous()
+    rows = b2.shape[0]
+    if t2.shape[0] != rows:
+        raise ValueError("branch and trunk inputs must have the same number of rows")
+    with torch.cuda.device(dev):
+        versions = _versions(bw) + _versions(bb) + _versions(tw) + _versions(tb)
+        if versions != plan.versions:
+            check(lib().cb_tc_multionet_set_weights(plan.handle, ptr_array(_f32(bw)), ptr_array(_f32(bb)),
+                                                    ptr_array(_f32(tw)), ptr_array(_f32(tb)), _stream(dev)),
+                  "tc_multionet_set_weights")
+            plan.versions = versions
+        need = int(lib().cb_tc_multionet_workspace_bytes(plan.handle, rows))
+        if plan.workspace is None or plan.workspace.numel() < need or plan.workspace.device != dev:
+            plan.workspace = torch.empty(need, device=dev, dtype=torch.uint8)
+        y = torch.empty((rows, q), device=dev, dtype=torch.float32)
+        check(lib().cb_tc_multionet_forward(plan.handle, C.c_void_p(b2.data_ptr()), C.c_void_p(t2.data_ptr()), rows,
+                                            C.c_void_p(y.data_ptr()), C.c_void_p(plan.workspace.data_ptr()),
+                                            plan.workspace.numel(), _stream(dev)), "tc_multionet_forward")
+    return y

@@ -1,16 +1,1019 @@
-// placeholder until the tcgen05 chain lands (replaced below in this round)
+// Fused dense MLP chains on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// chain_kernel: one persistent CTA per SM owns a 128-row tile of the batch and pushes it through
+// ALL layers of the chain without leaving the SM.  Activations live in shared memory as the bf16
+// A operand (K-major, 128B-swizzled UMMA layout, two ping-pong buffers); weights stream from L2
+// through a TMA/mbarrier ring as the B operand (nn.Linear's (out,in) row-major layout is exactly
+// "N x K, K-major"); accumulators live in TMEM (4 slots x 128 fp32 columns) and are drained by
+// four epilogue warps that fuse activation + bf16 conversion and write the next layer's A operand
+// straight back into shared memory.  The bias is folded into the GEMM: every activation row
+// carries a constant 1.0 in column K and the packed weights carry the bias in that column, so the
+// epilogue never touches global memory.
+//
+// don_final_kernel: the last Linear of MultiONet's branch and trunk nets (K -> Q*f outputs each)
+// plus the per-quantity scalar product, fused: both 128-column accumulator chunks sit in TMEM at
+// the same time and the epilogue multiplies them and segment-sums over each quantity's f columns,
+// so the two (rows x Q*f) fp32 tensors of the reference (deeponet.py:241-253) never exist.
+//
+// Warp roles (192 threads):   warp 0     TMA producer (1 elected thread)
+//                             warp 1     tcgen05.mma issuer (1 elected thread) + TMEM alloc/dealloc
+//                             warps 2-5  epilogue, one TMEM lane quarter (32 rows) each
+// Work items ("jobs") are (layer, 128-column output chunk); MMA of job j+1 overlaps the epilogue of
+// job j through the TMEM slot ring, and layer l+1 starts on the k-blocks whose producing chunks of
+// layer l are already written (fine-grained dependency through the `epi_done` counter).
+//
+// Replaces the per-layer cuBLAS sgemm + bias/activation kernels the reference launches for
+//   FullyConnectedNet (fcnn.py:81-98), BranchNet/TrunkNet (deeponet.py:15-84),
+//   Encoder/Decoder (latent_neural_ode.py:687-742).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cstring>
+
 #include "cb_common.cuh"
-struct cb_tc_chain { int unused; };
-extern "C" int32_t cb_tc_chain_create(const cb_mlp_desc*, int32_t, cb_tc_chain**) {
-  cb::set_error("tensor-core chain not built yet");
-  return CB_ERR_ARG;
+
+namespace cb {
+namespace tc {
+
+constexpr int kTileM = 128;          // rows per CTA tile (UMMA_M)
+constexpr int kChunkN = 128;         // output columns per job (UMMA_N <= 128), one TMEM slot
+constexpr int kBlockK = 64;          // bf16 elements per 128B swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kSlots = 4;            // TMEM slots (4 x 128 = 512 columns)
+constexpr int kKBlockBytes = kTileM * kBlockK * 2;     // 16 KiB: one k-block of A or one B stage
+constexpr int kMaxJobs = 96;
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+constexpr int kMaxSmem = 232448;     // 227 KiB
+constexpr int kCtrlBytes = 16 * kMaxStages + 16 * kSlots + 64;
+
+enum { IN_F32 = 0, IN_BF16_TMA = 1 };
+enum { OUT_F32 = 0, OUT_BF16_TMA = 1 };
+
+struct Job { int16_t layer, n0, ncols, last_chunk; };
+
+struct ChainParams {
+  CUtensorMap tmap_w[CB_MAX_LAYERS];
+  CUtensorMap tmap_in;         // IN_BF16_TMA : (rows, ld_in) bf16
+  CUtensorMap tmap_out;        // OUT_BF16_TMA: (rows, ld_out) bf16
+  int K[CB_MAX_LAYERS];        // true input width (the ones column sits at index K)
+  int N[CB_MAX_LAYERS];        // true output width
+  int ksteps[CB_MAX_LAYERS];   // ceil((K+1)/16)
+  int nkb[CB_MAX_LAYERS];      // ceil(ksteps/4) k-blocks of 64
+  int first_job[CB_MAX_LAYERS];
+  int n_chunks[CB_MAX_LAYERS];
+  Job jobs[kMaxJobs];
+  int n_layers, n_jobs, final_act;
+  float act_param;
+  int stages, kb_max, in_mode, out_mode, out_nkb, stage_ld, ostage_in_x;
+  const float* x;
+  float* y;
+  long long rows;
+  int num_tiles;
+};
+
+struct FinalParams {
+  CUtensorMap tmap_w[2];       // branch / trunk last-layer weights (rows_alloc, Kp) bf16, bias folded
+  CUtensorMap tmap_in[2];      // hb / ht (rows, ld) bf16
+  int K, ksteps, nkb, n_jobs, n_out, Q, stages;
+  int seg_base, seg_rem;       // split sizes: seg_base + (q < seg_rem)   (deeponet.py:130-137)
+  float* y;                    // (rows, Q) fp32
+  long long rows;
+  int num_tiles;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-extern "C" void cb_tc_chain_destroy(cb_tc_chain*) {}
-extern "C" int32_t cb_tc_chain_set_weights(cb_tc_chain*, const float* const*, const float* const*, void*) {
-  cb::set_error("tensor-core chain not built yet");
-  return CB_ERR_ARG;
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-extern "C" int32_t cb_tc_chain_forward(cb_tc_chain*, const float*, int64_t, float*, void*) {
-  cb::set_error("tensor-core chain not built yet");
-  return CB_ERR_ARG;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands, fp32 accumulate, M=128
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) = 0 | SBO>>4 [32,46) = 1024>>4 | version [46,48) = 1 | layout [61,64) = 2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1 | a,b format BF16 [7,10),[10,13)=1 | K-major A,B |
+// n_dim N>>3 [17,23) | m_dim M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_volatile_shared(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+// byte offset of the 16-byte chunk holding columns [8*col8, 8*col8+8) of row r inside an activation buffer
+__device__ __forceinline__ uint32_t act_chunk_off(int r, int col8) {
+  const int kb = col8 >> 3, kg = col8 & 7;
+  return (uint32_t)(kb * kKBlockBytes + r * 128 + ((kg ^ (r & 7)) << 4));
+}
+
+// Activations of the bf16 path: hardware approximations (MUFU tanh/ex2/lg2) -- their error
+// (~2^-11 relative) is below the bf16 rounding of the value they produce.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x, float p) {
+  if constexpr (ACT == CB_ACT_RELU) return fmaxf(x, 0.f);
+  else if constexpr (ACT == CB_ACT_LEAKYRELU || ACT == CB_ACT_PRELU) return x >= 0.f ? x : p * x;
+  else if constexpr (ACT == CB_ACT_TANH) return tanh_fast(x);
+  else if constexpr (ACT == CB_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+  else if constexpr (ACT == CB_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
+  else if constexpr (ACT == CB_ACT_SILU) return __fdividef(x, 1.f + __expf(-x));
+  else if constexpr (ACT == CB_ACT_SOFTPLUS) return x > 20.f ? x : __logf(1.f + __expf(x));
+  else if constexpr (ACT == CB_ACT_MISH) return x * tanh_fast(x > 20.f ? x : __logf(1.f + __expf(x)));
+  else if constexpr (ACT == CB_ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-x));
+  else return x;
+}
+
+// activation + bf16 pack of `w` (16 or 32) accumulator columns -> next layer's A operand;
+// column `ones_col` receives the constant 1.0 that multiplies the folded bias.
+template <int ACT>
+__device__ __forceinline__ void epi_hidden(const uint32_t (&v)[32], int w, int nb, int ones_col, float p,
+                                           uint32_t xo, int r) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (g * 8 < w) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a = act_fast<ACT>(__uint_as_float(v[g * 8 + i]), p);
+        f[i] = (nb + g * 8 + i == ones_col) ? 1.f : a;
+      }
+      st_shared_v4(xo + act_chunk_off(r, (nb >> 3) + g), pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
+                   pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    }
+  }
+}
+
+struct Ctrl {
+  uint32_t bar_full, bar_empty, bar_tfull, bar_tempty, bar_in;
+  uint32_t* tmem_ptr;
+  int* epi_done;
+  int* in_staged;
+};
+
+__device__ __forceinline__ Ctrl carve_ctrl(uint32_t ctrl_addr, uint8_t* ctrl_ptr) {
+  Ctrl c;
+  c.bar_full = ctrl_addr;
+  c.bar_empty = ctrl_addr + 8 * kMaxStages;
+  c.bar_tfull = ctrl_addr + 16 * kMaxStages;
+  c.bar_tempty = c.bar_tfull + 8 * kSlots;
+  c.bar_in = c.bar_tempty + 8 * kSlots;
+  c.tmem_ptr = reinterpret_cast<uint32_t*>(ctrl_ptr + 16 * kMaxStages + 16 * kSlots + 8);
+  c.epi_done = reinterpret_cast<int*>(c.tmem_ptr + 1);
+  c.in_staged = c.epi_done + 1;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t setup_cta(const Ctrl& c, int stages, int warp) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(c.bar_full + 8 * s, 1); mbar_init(c.bar_empty + 8 * s, 1); }
+    for (int s = 0; s < kSlots; ++s) { mbar_init(c.bar_tfull + 8 * s, 1); mbar_init(c.bar_tempty + 8 * s, 128); }
+    mbar_init(c.bar_in, 1);
+    *c.epi_done = 0;
+    *c.in_staged = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(c.tmem_ptr)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  return *reinterpret_cast<volatile uint32_t*>(c.tmem_ptr);
+}
+
+__device__ __forceinline__ void teardown_cta(uint32_t tmem_base, int warp) {
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ====================================================================== chain kernel
+template <int ACT>
+__global__ void __launch_bounds__(kThreads, 1)
+chain_kernel(const __grid_constant__ ChainParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t xbytes = (uint32_t)P.kb_max * kKBlockBytes;
+  const uint32_t X0 = base, X1 = base + xbytes, ST0 = base + 2 * xbytes;
+  const uint32_t ctrl_addr = ST0 + (uint32_t)P.stages * kKBlockBytes;
+  const Ctrl C = carve_ctrl(ctrl_addr, gbase + (ctrl_addr - base));
+  // fp32 output staging (OUT_F32 only): the activation buffer that is idle during the last layer
+  // when it is large enough, else a dedicated region behind the control block
+  const uint32_t OSTG = P.ostage_in_x ? ((P.n_layers & 1) ? X1 : X0) : ctrl_addr + kCtrlBytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_base = setup_cta(C, P.stages, warp);
+  const int n_my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < n_my_tiles; ++it) {
+        if (P.in_mode == IN_BF16_TMA) {
+          // X0 may be refilled once every MMA/epilogue of the previous tile has retired
+          while (ld_volatile_shared(C.epi_done) < it * P.n_jobs) { }
+          __threadfence_block();
+          const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+          mbar_arrive_expect_tx(C.bar_in, (uint32_t)P.nkb[0] * kKBlockBytes);
+          for (int kb = 0; kb < P.nkb[0]; ++kb)
+            tma_load_2d(X0 + kb * kKBlockBytes, &P.tmap_in, kb * kBlockK, tile * kTileM, C.bar_in);
+        }
+        for (int j = 0; j < P.n_jobs; ++j) {
+          const Job job = P.jobs[j];
+          const int nkb = P.nkb[job.layer];
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(C.bar_empty + 8 * stage, phase ^ 1);
+            mbar_arrive_expect_tx(C.bar_full + 8 * stage, kKBlockBytes);
+            tma_load_2d(ST0 + stage * kKBlockBytes, &P.tmap_w[job.layer], kb * kBlockK, job.n0, C.bar_full + 8 * stage);
+            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int gj = 0;
+      for (int it = 0; it < n_my_tiles; ++it) {
+        for (int j = 0; j < P.n_jobs; ++j, ++gj) {
+          const Job job = P.jobs[j];
+          const int l = job.layer;
+          const int slot = gj & (kSlots - 1);
+          const uint32_t use = (uint32_t)(gj / kSlots);
+          mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
+          tcgen05_fence_after();
+          const uint32_t xa = (l & 1) ? X1 : X0;
+          const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
+          const uint32_t idesc = make_idesc(job.ncols);
+          const int nkb = P.nkb[l], ksteps = P.ksteps[l];
+          for (int kb = 0; kb < nkb; ++kb) {
+            // activation k-block kb must have been written by its producer
+            if (l == 0) {
+              if (P.in_mode == IN_BF16_TMA) { if (kb == 0) mbar_wait(C.bar_in, it & 1); }
+              else while (ld_volatile_shared(C.in_staged) < it + 1) { }
+            } else {
+              const int pc = min(kb >> 1, P.n_chunks[l - 1] - 1);
+              const int need = it * P.n_jobs + P.first_job[l - 1] + pc + 1;
+              while (ld_volatile_shared(C.epi_done) < need) { }
+            }
+            __threadfence_block();
+            mbar_wait(C.bar_full + 8 * stage, phase);
+            tcgen05_fence_after();
+            const int nks = min(4, ksteps - kb * 4);
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint64_t adesc = make_smem_desc(xa + kb * kKBlockBytes + ks * (kUmmaK * 2));
+              const uint64_t bdesc = make_smem_desc(ST0 + stage * kKBlockBytes + ks * (kUmmaK * 2));
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | ks) ? 1u : 0u);
+            }
+            umma_commit(C.bar_empty + 8 * stage);   // frees the weight stage when these MMAs retire
+            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(C.bar_tfull + 8 * slot);       // accumulator chunk complete -> epilogue
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================================================ epilogue warps (2..5)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // row inside the tile
+    const int et = threadIdx.x - 64;        // 0..127
+    const int K0 = P.K[0];
+    int gj = 0;
+    for (int it = 0; it < n_my_tiles; ++it) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const long long row_g = (long long)tile * kTileM + r;
+      const bool row_ok = row_g < P.rows;
+      if (P.in_mode == IN_F32) {
+        // stage the fp32 input rows as the bf16 A operand of layer 0: [x, 1, 0...] padded to 16*ksteps
+        const float* xr = P.x + row_g * K0;
+        const int nch = P.ksteps[0] * 2;    // 16-byte chunks (8 columns each)
+        for (int c = 0; c < nch; ++c) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = c * 8 + i;
+            f[i] = (k < K0) ? (row_ok ? __ldg(xr + k) : 0.f) : (k == K0 ? 1.f : 0.f);
+          }
+          st_shared_v4(X0 + act_chunk_off(r, c), pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
+                       pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        }
+        fence_proxy_async();
+        epi_bar_sync();
+        if (et == 0) { __threadfence_block(); atomicAdd(C.in_staged, 1); }
+      }
+      for (int j = 0; j < P.n_jobs; ++j, ++gj) {
+        const Job job = P.jobs[j];
+        const int l = job.layer;
+        const bool last = (l == P.n_layers - 1);
+        const bool to_smem = !last || P.out_mode == OUT_BF16_TMA;
+        const int slot = gj & (kSlots - 1);
+        const uint32_t use = (uint32_t)(gj / kSlots);
+        mbar_wait(C.bar_tfull + 8 * slot, use & 1);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * kChunkN;
+        const uint32_t xo = ((l + 1) & 1) ? X1 : X0;
+        const int N = P.N[l];
+        for (int c0 = 0; c0 < job.ncols; c0 += 32) {
+          uint32_t v[32];
+          const int w = min(32, job.ncols - c0);   // 32 or 16
+          if (w == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          const int nb = job.n0 + c0;
+          if (to_smem) {
+            epi_hidden<ACT>(v, w, nb, N, P.act_param, xo, r);
+          } else {
+            // final fp32 outputs: stage the row segment in shared memory (conflict-free float4 rows)
+            const bool tanh_out = (P.final_act == CB_ACT_TANH);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (g * 4 < w) {
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float z = __uint_as_float(v[g * 4 + i]);
+                  o[i] = tanh_out ? tanhf(z) : z;
+                }
+                st_shared_v4(OSTG + (uint32_t)((r * P.stage_ld + c0 + g * 4) * 4), __float_as_uint(o[0]),
+                             __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        mbar_arrive(C.bar_tempty + 8 * slot);
+        if (to_smem) {
+          if (job.last_chunk && (N & 15) == 0) {
+            // ones column starts a fresh 16-column k-step: write [1,0,...,0] (32 bytes)
+            st_shared_v4(xo + act_chunk_off(r, N >> 3), pack_bf16(1.f, 0.f), 0u, 0u, 0u);
+            st_shared_v4(xo + act_chunk_off(r, (N >> 3) + 1), 0u, 0u, 0u, 0u);
+          }
+          fence_proxy_async();                     // generic-proxy smem writes -> visible to tcgen05.mma / TMA
+          epi_bar_sync();
+          if (last && job.last_chunk) {
+            // OUT_BF16_TMA: the finished activation tile leaves through TMA stores (rows >= M are clipped)
+            if (et == 0) {
+              for (int kb = 0; kb < P.out_nkb; ++kb)
+                tma_store_2d(&P.tmap_out, xo + kb * kKBlockBytes, kb * kBlockK, tile * kTileM);
+              tma_store_commit();
+              tma_store_wait_read();
+            }
+            epi_bar_sync();
+          }
+        } else {
+          epi_bar_sync();
+          // coalesced copy-out: thread `et` owns column n0+et of every row of the tile
+          const int n = job.n0 + et;
+          if (et < job.ncols && n < N) {
+            const long long rows_left = P.rows - (long long)tile * kTileM;
+            const int nr = rows_left < kTileM ? (int)rows_left : kTileM;
+            float* yp = P.y + (long long)tile * kTileM * N + n;
+            for (int rr = 0; rr < nr; ++rr)
+              yp[(long long)rr * N] = ld_shared_f32(OSTG + (uint32_t)((rr * P.stage_ld + et) * 4));
+          }
+          epi_bar_sync();
+        }
+        if (et == 0) { __threadfence_block(); atomicAdd(C.epi_done, 1); }
+      }
+    }
+  }
+  teardown_cta(tmem_base, warp);
+}
+
+// ====================================================================== MultiONet final kernel
+// y[r,q] = sum_{k in split_q} (Wb hb + bb)[r,k] * (Wt ht + bt)[r,k]      (deeponet.py:241-253)
+__global__ void __launch_bounds__(kThreads, 1)
+don_final_kernel(const __grid_constant__ FinalParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t xbytes = (uint32_t)P.nkb * kKBlockBytes;
+  const uint32_t XB = base, XT = base + xbytes, ST0 = base + 2 * xbytes;
+  const uint32_t ctrl_addr = ST0 + (uint32_t)P.stages * kKBlockBytes;
+  const Ctrl C = carve_ctrl(ctrl_addr, gbase + (ctrl_addr - base));
+  const uint32_t OSTG = ctrl_addr + kCtrlBytes;      // (128, Q+1) fp32
+  const int out_ld = P.Q + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_base = setup_cta(C, P.stages, warp);
+  const int n_my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < n_my_tiles; ++it) {
+        while (ld_volatile_shared(C.epi_done) < it) { }      // previous tile fully consumed
+        __threadfence_block();
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        mbar_arrive_expect_tx(C.bar_in, 2u * P.nkb * kKBlockBytes);
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          tma_load_2d(XB + kb * kKBlockBytes, &P.tmap_in[0], kb * kBlockK, tile * kTileM, C.bar_in);
+          tma_load_2d(XT + kb * kKBlockBytes, &P.tmap_in[1], kb * kBlockK, tile * kTileM, C.bar_in);
+        }
+        for (int j = 0; j < P.n_jobs; ++j) {
+          for (int net = 0; net < 2; ++net) {
+            for (int kb = 0; kb < P.nkb; ++kb) {
+              mbar_wait(C.bar_empty + 8 * stage, phase ^ 1);
+              mbar_arrive_expect_tx(C.bar_full + 8 * stage, kKBlockBytes);
+              tma_load_2d(ST0 + stage * kKBlockBytes, &P.tmap_w[net], kb * kBlockK, j * kChunkN, C.bar_full + 8 * stage);
+              if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int gs = 0;   // global slot-use counter (2 per job)
+      for (int it = 0; it < n_my_tiles; ++it) {
+        mbar_wait(C.bar_in, it & 1);
+        tcgen05_fence_after();
+        for (int j = 0; j < P.n_jobs; ++j) {
+          const int ncols = min(kChunkN, P.n_out - j * kChunkN);
+          const uint32_t idesc = make_idesc(ncols);
+          for (int net = 0; net < 2; ++net, ++gs) {
+            const int slot = gs & (kSlots - 1);
+            const uint32_t use = (uint32_t)(gs / kSlots);
+            mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
+            tcgen05_fence_after();
+            const uint32_t xa = net ? XT : XB;
+            const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
+            for (int kb = 0; kb < P.nkb; ++kb) {
+              mbar_wait(C.bar_full + 8 * stage, phase);
+              tcgen05_fence_after();
+              const int nks = min(4, P.ksteps - kb * 4);
+              for (int ks = 0; ks < nks; ++ks) {
+                const uint64_t adesc = make_smem_desc(xa + kb * kKBlockBytes + ks * (kUmmaK * 2));
+                const uint64_t bdesc = make_smem_desc(ST0 + stage * kKBlockBytes + ks * (kUmmaK * 2));
+                umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | ks) ? 1u : 0u);
+              }
+              umma_commit(C.bar_empty + 8 * stage);
+              if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(C.bar_tfull + 8 * slot);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const int et = threadIdx.x - 64;
+    int gs = 0;
+    for (int it = 0; it < n_my_tiles; ++it) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      // running segment state: quantity index, end column of its split, partial sum
+      int qi = 0;
+      int seg_end = P.seg_base + (0 < P.seg_rem ? 1 : 0);
+      float acc = 0.f;
+      for (int j = 0; j < P.n_jobs; ++j, gs += 2) {
+        const int ncols = min(kChunkN, P.n_out - j * kChunkN);
+        const int slot_b = gs & (kSlots - 1), slot_t = (gs + 1) & (kSlots - 1);
+        mbar_wait(C.bar_tfull + 8 * slot_b, (uint32_t)(gs / kSlots) & 1);
+        mbar_wait(C.bar_tfull + 8 * slot_t, (uint32_t)((gs + 1) / kSlots) & 1);
+        tcgen05_fence_after();
+        const uint32_t ta_b = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)slot_b * kChunkN;
+        const uint32_t ta_t = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)slot_t * kChunkN;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t vb[32], vt[32];
+          const int w = min(32, ncols - c0);
+          if (w == 32) { tmem_ld32(ta_b + c0, vb); tmem_ld32(ta_t + c0, vt); }
+          else { tmem_ld16(ta_b + c0, vb); tmem_ld16(ta_t + c0, vt); }
+          tmem_ld_wait();
+          const int nb = j * kChunkN + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < w) {
+              acc = fmaf(__uint_as_float(vb[i]), __uint_as_float(vt[i]), acc);
+              if (nb + i + 1 == seg_end) {        // warp-uniform: end of quantity qi's split
+                if (qi < P.Q) st_shared_f32(OSTG + (uint32_t)((r * out_ld + qi) * 4), acc);
+                acc = 0.f;
+                ++qi;
+                seg_end += P.seg_base + (qi < P.seg_rem ? 1 : 0);
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        mbar_arrive(C.bar_tempty + 8 * slot_b);
+        mbar_arrive(C.bar_tempty + 8 * slot_t);
+      }
+      epi_bar_sync();
+      // coalesced copy-out of the (128, Q) tile: linear over the contiguous global block
+      {
+        const long long rows_left = P.rows - (long long)tile * kTileM;
+        const int nr = rows_left < kTileM ? (int)rows_left : kTileM;
+        float* yp = P.y + (long long)tile * kTileM * P.Q;
+        for (int idx = et; idx < nr * P.Q; idx += 128) {
+          const int rr = idx / P.Q, qq = idx - rr * P.Q;
+          yp[idx] = ld_shared_f32(OSTG + (uint32_t)((rr * out_ld + qq) * 4));
+        }
+      }
+      epi_bar_sync();
+      if (et == 0) { __threadfence_block(); atomicAdd(C.epi_done, 1); }
+    }
+  }
+  teardown_cta(tmem_base, warp);
+}
+
+// fp32 (N,K) row-major + bias -> bf16 (rows_alloc, Kp): [W | b | 0...], zero rows beyond N
+__global__ void pack_weights_kernel(const float* __restrict__ W, const float* __restrict__ b, int N, int K,
+                                    int rows_alloc, int Kp, __nv_bfloat16* __restrict__ Wp) {
+  const long long total = (long long)rows_alloc * Kp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / Kp), k = (int)(i % Kp);
+    float v = 0.f;
+    if (n < N) {
+      if (k < K) v = W[(long long)n * K + k];
+      else if (k == K && b) v = b[n];
+    }
+    Wp[i] = __float2bfloat16(v);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map (cols innermost), box = 64 columns x 128 rows, 128B swizzle
+static bool encode_bf16_map(CUtensorMap* map, const void* ptr, long long rows, long long cols_ld) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols_ld, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols_ld * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kTileM};
+  cuuint32_t estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+typedef void (*ChainKernelFn)(const ChainParams);
+static ChainKernelFn chain_kernel_for(int act) {
+  switch (act) {
+    case CB_ACT_RELU: return chain_kernel<CB_ACT_RELU>;
+    case CB_ACT_LEAKYRELU:
+    case CB_ACT_PRELU: return chain_kernel<CB_ACT_LEAKYRELU>;
+    case CB_ACT_TANH: return chain_kernel<CB_ACT_TANH>;
+    case CB_ACT_GELU: return chain_kernel<CB_ACT_GELU>;
+    case CB_ACT_ELU: return chain_kernel<CB_ACT_ELU>;
+    case CB_ACT_SILU: return chain_kernel<CB_ACT_SILU>;
+    case CB_ACT_SOFTPLUS: return chain_kernel<CB_ACT_SOFTPLUS>;
+    case CB_ACT_MISH: return chain_kernel<CB_ACT_MISH>;
+    case CB_ACT_SIGMOID: return chain_kernel<CB_ACT_SIGMOID>;
+    default: return chain_kernel<CB_ACT_IDENTITY>;
+  }
+}
+
+}  // namespace tc
+}  // namespace cb
+
+using namespace cb;
+using namespace cb::tc;
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct cb_tc_chain {
+  cb_mlp_desc desc;
+  int device;
+  int out_mode;                 // OUT_F32 | OUT_BF16_TMA
+  ChainParams P;
+  __nv_bfloat16* d_w[CB_MAX_LAYERS];
+  int Kp[CB_MAX_LAYERS], rows_alloc[CB_MAX_LAYERS];
+  int ld_out;                   // OUT_BF16_TMA: columns of the bf16 output (multiple of 64)
+  size_t smem_bytes;
+  int weights_set;
+};
+
+// Geometry of the fused chain.  Both ping-pong buffers, >= 2 weight stages and (OUT_F32) the fp32
+// output staging tile must fit in 227 KiB of shared memory.
+struct ChainGeom { int kb_max, stages, n_jobs, stage_ld, out_nkb, ostage_in_x; size_t smem; bool ok; };
+
+static ChainGeom chain_geometry(const cb_mlp_desc* d, int out_mode) {
+  ChainGeom g{};
+  g.kb_max = 1;
+  const int n = d->n_layers;
+  for (int i = 0; i < n; ++i) {
+    const int ksteps = (d->dims[i] + 1 + kUmmaK - 1) / kUmmaK;
+    const int nkb = (ksteps + 3) / 4;
+    g.kb_max = nkb > g.kb_max ? nkb : g.kb_max;
+    g.n_jobs += (round_up(d->dims[i + 1], 16) + kChunkN - 1) / kChunkN;
+  }
+  g.out_nkb = (d->dims[n] + 1 + kBlockK - 1) / kBlockK;
+  if (out_mode == OUT_BF16_TMA) g.kb_max = g.out_nkb > g.kb_max ? g.out_nkb : g.kb_max;
+  size_t ostage = 0;
+  if (out_mode == OUT_F32) {
+    const int np = round_up(d->dims[n], 16);
+    g.stage_ld = (np < kChunkN ? np : kChunkN) + 4;
+    ostage = (size_t)kTileM * g.stage_ld * sizeof(float);
+    if (ostage <= (size_t)g.kb_max * kKBlockBytes) { g.ostage_in_x = 1; ostage = 0; }
+  }
+  const long long fixed = 1024 /*align slack*/ + kCtrlBytes + (long long)ostage + 2ll * g.kb_max * kKBlockBytes;
+  long long stages = ((long long)kMaxSmem - fixed) / kKBlockBytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  g.stages = (int)stages;
+  g.smem = (size_t)(fixed + (stages > 0 ? stages : 0) * kKBlockBytes);
+  const bool final_ok = d->final_act == CB_ACT_IDENTITY || d->final_act == CB_ACT_TANH || out_mode == OUT_BF16_TMA;
+  g.ok = stages >= 2 && g.n_jobs <= kMaxJobs && final_ok;
+  return g;
+}
+
+extern "C" int32_t cb_tc_chain_supported(const cb_mlp_desc* desc) {
+  if (check_desc(desc) != CB_OK) return 0;
+  return chain_geometry(desc, OUT_F32).ok ? 1 : 0;
+}
+
+extern "C" int32_t cb_tc_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 && get_encode_fn() != nullptr;
+}
+
+extern "C" void cb_tc_chain_destroy(cb_tc_chain* plan) {
+  if (!plan) return;
+  for (int i = 0; i < CB_MAX_LAYERS; ++i)
+    if (plan->d_w[i]) cudaFree(plan->d_w[i]);
+  delete plan;
+}
+
+static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mode, cb_tc_chain** out) {
+  if (int32_t e = check_desc(desc)) return e;
+  CB_CHECK_ARG(out != nullptr, "out is NULL");
+  const ChainGeom g = chain_geometry(desc, out_mode);
+  CB_CHECK_ARG(g.ok, "chain not supported by the fused tcgen05 kernel (activations + weight stages exceed "
+                     "227 KiB, too many chunks, or unsupported final activation)");
+  CB_CHECK_ARG(get_encode_fn() != nullptr, "cuTensorMapEncodeTiled unavailable");
+  CB_CUDA(cudaSetDevice(device));
+  cb_tc_chain* pl = new cb_tc_chain();
+  memset(pl, 0, sizeof(*pl));
+  pl->desc = *desc;
+  pl->device = device;
+  pl->out_mode = out_mode;
+  ChainParams& P = pl->P;
+  P.n_layers = desc->n_layers;
+  P.final_act = desc->final_act; P.act_param = desc->act_param;
+  P.stages = g.stages; P.kb_max = g.kb_max;
+  P.in_mode = IN_F32; P.out_mode = out_mode; P.out_nkb = g.out_nkb; P.stage_ld = g.stage_ld; P.ostage_in_x = g.ostage_in_x;
+  pl->ld_out = g.out_nkb * kBlockK;
+  int nj = 0;
+  for (int i = 0; i < desc->n_layers; ++i) {
+    const int K = desc->dims[i], N = desc->dims[i + 1];
+    P.K[i] = K; P.N[i] = N;
+    P.ksteps[i] = (K + 1 + kUmmaK - 1) / kUmmaK;
+    P.nkb[i] = (P.ksteps[i] + 3) / 4;
+    P.first_job[i] = nj;
+    const int Np = round_up(N, 16);
+    int chunks = 0;
+    for (int n0 = 0; n0 < Np; n0 += kChunkN, ++chunks) {
+      Job jb;
+      jb.layer = (int16_t)i; jb.n0 = (int16_t)n0;
+      jb.ncols = (int16_t)((Np - n0) < kChunkN ? (Np - n0) : kChunkN);
+      jb.last_chunk = (int16_t)(n0 + kChunkN >= Np);
+      P.jobs[nj++] = jb;
+    }
+    P.n_chunks[i] = chunks;
+    pl->Kp[i] = P.nkb[i] * kBlockK;
+    pl->rows_alloc[i] = round_up(N, kChunkN);
+    if (cudaMalloc(&pl->d_w[i], (size_t)pl->rows_alloc[i] * pl->Kp[i] * sizeof(__nv_bfloat16)) != cudaSuccess) {
+      cb_tc_chain_destroy(pl);
+      set_error("cudaMalloc of the bf16 weight cache failed");
+      return CB_ERR_CUDA;
+    }
+    if (!encode_bf16_map(&P.tmap_w[i], pl->d_w[i], pl->rows_alloc[i], pl->Kp[i])) {
+      cb_tc_chain_destroy(pl);
+      set_error("cuTensorMapEncodeTiled failed for layer %d", i);
+      return CB_ERR_CUDA;
+    }
+  }
+  P.n_jobs = nj;
+  pl->smem_bytes = g.smem;
+  if (cudaFuncSetAttribute(chain_kernel_for(desc->act), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)pl->smem_bytes) != cudaSuccess) {
+    cb_tc_chain_destroy(pl);
+    set_error("cannot reserve %zu bytes of shared memory for the chain kernel: %s", g.smem,
+              cudaGetErrorString(cudaGetLastError()));
+    return CB_ERR_CUDA;
+  }
+  *out = pl;
+  return CB_OK;
+}
+
+extern "C" int32_t cb_tc_chain_create(const cb_mlp_desc* desc, int32_t device, cb_tc_chain** out) {
+  return chain_create(desc, device, OUT_F32, out);
+}
+
+extern "C" int32_t cb_tc_chain_set_weights(cb_tc_chain* plan, const float* const* d_W, const float* const* d_b,
+                                           void* stream) {
+  CB_CHECK_ARG(plan && d_W && d_b, "NULL pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < plan->P.n_layers; ++i) {
+    CB_CHECK_ARG(d_W[i] != nullptr, "weight %d is NULL", i);
+    const long long total = (long long)plan->rows_alloc[i] * plan->Kp[i];
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    pack_weights_kernel<<<blocks, 256, 0, st>>>(d_W[i], d_b[i], plan->P.N[i], plan->P.K[i], plan->rows_alloc[i],
+                                               plan->Kp[i], plan->d_w[i]);
+    CB_LAUNCH_CHECK();
+  }
+  plan->weights_set = 1;
+  return CB_OK;
+}
+
+// launch helper shared by the public forward and the MultiONet pipeline
+static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorMap* in_map, int64_t rows,
+                            float* d_y, const CUtensorMap* out_map, cudaStream_t st) {
+  ChainParams P = plan->P;
+  P.x = d_x; P.y = d_y; P.rows = rows;
+  if (in_map) { P.in_mode = IN_BF16_TMA; P.tmap_in = *in_map; }
+  if (out_map) P.tmap_out = *out_map;
+  P.num_tiles = (int)((rows + kTileM - 1) / kTileM);
+  const int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
+  chain_kernel_for(plan->desc.act)<<<grid, kThreads, plan->smem_bytes, st>>>(P);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int32_t cb_tc_chain_forward(cb_tc_chain* plan, const float* d_x, int64_t rows, float* d_y, void* stream) {
+  CB_CHECK_ARG(plan != nullptr, "plan is NULL");
+  CB_CHECK_ARG(plan->out_mode == OUT_F32, "plan was not created for fp32 output");
+  CB_CHECK_ARG(plan->weights_set, "cb_tc_chain_set_weights must be called first");
+  CB_CHECK_ARG(rows >= 0, "rows < 0");
+  if (rows == 0) return CB_OK;
+  CB_CHECK_ARG(d_x && d_y, "NULL pointer argument");
+  CB_CHECK_ARG(rows <= (int64_t)kTileM * 0x3fffffff, "too many rows");
+  return chain_launch(plan, d_x, nullptr, rows, d_y, nullptr, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------- MultiONet pipeline
+struct cb_tc_multionet {
+  cb_tc_chain* hidden[2];       // branch / trunk hidden chains (bf16 TMA output)
+  __nv_bfloat16* d_wlast[2];
+  int K, Kp, rows_alloc, n_out, Q, ld_h;
+  cb_mlp_desc desc[2];
+  FinalParams F;
+  size_t smem_final;
+  int weights_set;
+};
+
+extern "C" void cb_tc_multionet_destroy(cb_tc_multionet* m) {
+  if (!m) return;
+  for (int i = 0; i < 2; ++i) {
+    cb_tc_chain_destroy(m->hidden[i]);
+    if (m->d_wlast[i]) cudaFree(m->d_wlast[i]);
+  }
+  delete m;
+}
+
+static bool final_geometry(int K, int Q, int* nkb_out, int* stages_out, size_t* smem_out) {
+  const int ksteps = (K + 1 + kUmmaK - 1) / kUmmaK;
+  const int nkb = (ksteps + 3) / 4;
+  const size_t ostage = (size_t)kTileM * (Q + 1) * sizeof(float);
+  const long long fixed = 1024 + kCtrlBytes + (long long)ostage + 2ll * nkb * kKBlockBytes;
+  long long stages = ((long long)kMaxSmem - fixed) / kKBlockBytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (nkb_out) *nkb_out = nkb;
+  if (stages_out) *stages_out = (int)stages;
+  if (smem_out) *smem_out = (size_t)(fixed + (stages > 0 ? stages : 0) * kKBlockBytes);
+  return stages >= 2;
+}
+
+extern "C" int32_t cb_tc_multionet_supported(const cb_mlp_desc* branch, const cb_mlp_desc* trunk, int32_t Q) {
+  if (check_desc(branch) != CB_OK || check_desc(trunk) != CB_OK || Q < 1) return 0;
+  const int nb = branch->n_layers, nt = trunk->n_layers;
+  if (nb < 2 || nt < 2) return 0;
+  if (branch->dims[nb] != trunk->dims[nt] || branch->dims[nb - 1] != trunk->dims[nt - 1]) return 0;
+  if (branch->act != trunk->act || branch->final_act != CB_ACT_IDENTITY || trunk->final_act != CB_ACT_IDENTITY) return 0;
+  if (branch->dims[nb] < Q) return 0;
+  cb_mlp_desc hb = *branch, ht = *trunk;
+  hb.n_layers = nb - 1; ht.n_layers = nt - 1;
+  if (!chain_geometry(&hb, OUT_BF16_TMA).ok || !chain_geometry(&ht, OUT_BF16_TMA).ok) return 0;
+  return final_geometry(branch->dims[nb - 1], Q, nullptr, nullptr, nullptr) ? 1 : 0;
+}
+
+extern "C" int32_t cb_tc_multionet_create(const cb_mlp_desc* branch, const cb_mlp_desc* trunk, int32_t Q,
+                                          int32_t device, cb_tc_multionet** out) {
+  CB_CHECK_ARG(out != nullptr, "out is NULL");
+  CB_CHECK_ARG(cb_tc_multionet_supported(branch, trunk, Q), "MultiONet shape not supported by the fused kernels");
+  CB_CUDA(cudaSetDevice(device));
+  cb_tc_multionet* m = new cb_tc_multionet();
+  memset(m, 0, sizeof(*m));
+  m->desc[0] = *branch; m->desc[1] = *trunk;
+  const cb_mlp_desc* ds[2] = {branch, trunk};
+  for (int i = 0; i < 2; ++i) {
+    cb_mlp_desc h = *ds[i];
+    h.n_layers = ds[i]->n_layers - 1;
+    h.final_act = h.act;     // the last layer of the hidden chain is an ordinary hidden layer
+    if (int32_t e = chain_create(&h, device, OUT_BF16_TMA, &m->hidden[i])) { cb_tc_multionet_destroy(m); return e; }
+  }
+  const int nb = branch->n_layers;
+  m->K = branch->dims[nb - 1];
+  m->n_out = branch->dims[nb];
+  m->Q = Q;
+  int nkb = 0, stages = 0;
+  final_geometry(m->K, Q, &nkb, &stages, &m->smem_final);
+  m->Kp = nkb * kBlockK;
+  m->ld_h = m->hidden[0]->ld_out;
+  m->rows_alloc = round_up(m->n_out, kChunkN);
+  FinalParams& F = m->F;
+  F.K = m->K; F.ksteps = (m->K + 1 + kUmmaK - 1) / kUmmaK; F.nkb = nkb;
+  F.n_out = round_up(m->n_out, 16); F.n_jobs = (F.n_out + kChunkN - 1) / kChunkN;
+  F.Q = Q; F.stages = stages;
+  F.seg_base = m->n_out / Q; F.seg_rem = m->n_out % Q;
+  for (int i = 0; i < 2; ++i) {
+    if (cudaMalloc(&m->d_wlast[i], (size_t)m->rows_alloc * m->Kp * sizeof(__nv_bfloat16)) != cudaSuccess ||
+        !encode_bf16_map(&F.tmap_w[i], m->d_wlast[i], m->rows_alloc, m->Kp)) {
+      cb_tc_multionet_destroy(m);
+      set_error("allocation / tensor map of the last-layer weights failed");
+      return CB_ERR_CUDA;
+    }
+  }
+  if (cudaFuncSetAttribute(don_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_final) !=
+      cudaSuccess) {
+    cb_tc_multionet_destroy(m);
+    set_error("cannot reserve shared memory for the MultiONet final kernel");
+    return CB_ERR_CUDA;
+  }
+  *out = m;
+  return CB_OK;
+}
+
+extern "C" int64_t cb_tc_multionet_workspace_bytes(const cb_tc_multionet* m, int64_t rows) {
+  if (!m || rows < 0) return -1;
+  const int64_t padded = (rows + kTileM - 1) / kTileM * kTileM;
+  return 2 * padded * m->ld_h * (int64_t)sizeof(__nv_bfloat16) + 256;
+}
+
+extern "C" int32_t cb_tc_multionet_set_weights(cb_tc_multionet* m, const float* const* d_Wb,
+                                               const float* const* d_bb, const float* const* d_Wt,
+                                               const float* const* d_bt, void* stream) {
+  CB_CHECK_ARG(m && d_Wb && d_bb && d_Wt && d_bt, "NULL pointer argument");
+  if (int32_t e = cb_tc_chain_set_weights(m->hidden[0], d_Wb, d_bb, stream)) return e;
+  if (int32_t e = cb_tc_chain_set_weights(m->hidden[1], d_Wt, d_bt, stream)) return e;
+  const float* const* Ws[2] = {d_Wb, d_Wt};
+  const float* const* bs[2] = {d_bb, d_bt};
+  for (int i = 0; i < 2; ++i) {
+    const int last = m->desc[i].n_layers - 1;
+    const long long total = (long long)m->rows_alloc * m->Kp;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Ws[i][last], bs[i][last], m->n_out, m->K,
+                                                                 m->rows_alloc, m->Kp, m->d_wlast[i]);
+    CB_LAUNCH_CHECK();
+  }
+  m->weights_set = 1;
+  return CB_OK;
+}
+
+extern "C" int32_t cb_tc_multionet_forward(cb_tc_multionet* m, const float* d_branch_in, const float* d_trunk_in,
+                                           int64_t rows, float* d_y, void* d_workspace, int64_t workspace_bytes,
+                                           void* stream) {
+  CB_CHECK_ARG(m != nullptr, "plan is NULL");
+  CB_CHECK_ARG(m->weights_set, "cb_tc_multionet_set_weights must be called first");
+  CB_CHECK_ARG(rows >= 0, "rows < 0");
+  if (rows == 0) return CB_OK;
+  CB_CHECK_ARG(d_branch_in && d_trunk_in && d_y && d_workspace, "NULL pointer argument");
+  CB_CHECK_ARG(rows <= (int64_t)kTileM * 0x3fffffff, "too many rows");
+  if (workspace_bytes < cb_tc_multionet_workspace_bytes(m, rows)) {
+    set_error("workspace too small: %lld < %lld bytes", (long long)workspace_bytes,
+              (long long)cb_tc_multionet_workspace_bytes(m, rows));
+    return CB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t padded = (rows + kTileM - 1) / kTileM * kTileM;
+  uintptr_t wsp = ((uintptr_t)d_workspace + 127) & ~(uintptr_t)127;
+  __nv_bfloat16* h[2] = {reinterpret_cast<__nv_bfloat16*>(wsp),
+                         reinterpret_cast<__nv_bfloat16*>(wsp) + padded * m->ld_h};
+  CUtensorMap hmap[2];
+  for (int i = 0; i < 2; ++i)
+    CB_CHECK_ARG(encode_bf16_map(&hmap[i], h[i], rows, m->ld_h), "tensor map of the hidden activations failed");
+  if (int32_t e = chain_launch(m->hidden[0], d_branch_in, nullptr, rows, nullptr, &hmap[0], st)) return e;
+  if (int32_t e = chain_launch(m->hidden[1], d_trunk_in, nullptr, rows, nullptr, &hmap[1], st)) return e;
+  FinalParams F = m->F;
+  F.tmap_in[0] = hmap[0]; F.tmap_in[1] = hmap[1];
+  F.y = d_y; F.rows = rows;
+  F.num_tiles = (int)((rows + kTileM - 1) / kTileM);
+  const int grid = F.num_tiles < num_sms() ? F.num_tiles : num_sms();
+  don_final_kernel<<<grid, kThreads, m->smem_final, st>>>(F);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
 }

@@ -193,6 +193,11 @@ CB_API int32_t cb_lnode_solve_fwd(const cb_lnode_desc* desc, const float* const*
 /* Opaque plan for a fused bf16 MLP chain on tcgen05 (weights converted/padded
  * to bf16, TMA descriptors, job table).  See DESIGN.md. */
 typedef struct cb_tc_chain cb_tc_chain;
+/* 1 when the current device can run the tcgen05 path (compute capability 10.x). */
+CB_API int32_t cb_tc_supported(void);
+/* 1 when the fused chain kernel handles this shape (two bf16 activation buffers of
+ * 128 x max-width plus >= 2 weight stages must fit in 227 KiB of shared memory). */
+CB_API int32_t cb_tc_chain_supported(const cb_mlp_desc* desc);
 CB_API int32_t cb_tc_chain_create(const cb_mlp_desc* desc, int32_t device, cb_tc_chain** out);
 CB_API void cb_tc_chain_destroy(cb_tc_chain* plan);
 /* (re)load fp32 weights into the plan's bf16 buffers (after an optimizer step). */
@@ -201,6 +206,23 @@ CB_API int32_t cb_tc_chain_set_weights(cb_tc_chain* plan, const float* const* d_
 /* y = chain(x) with bf16 operands / fp32 accumulate. */
 CB_API int32_t cb_tc_chain_forward(cb_tc_chain* plan, const float* d_x, int64_t rows, float* d_y,
                             void* stream);
+
+/* Fused MultiONet forward on tensor cores (deeponet.py:226-253): hidden layers of the branch
+ * and trunk nets as two fused chains (bf16 activations handed over through `d_workspace`), then
+ * ONE kernel for both last Linears + the per-quantity split scalar product.
+ * branch_in:(rows, branch.dims[0]) trunk_in:(rows, trunk.dims[0]) fp32 -> y:(rows, Q) fp32. */
+typedef struct cb_tc_multionet cb_tc_multionet;
+CB_API int32_t cb_tc_multionet_supported(const cb_mlp_desc* branch, const cb_mlp_desc* trunk, int32_t n_quantities);
+CB_API int32_t cb_tc_multionet_create(const cb_mlp_desc* branch, const cb_mlp_desc* trunk, int32_t n_quantities,
+                                      int32_t device, cb_tc_multionet** out);
+CB_API void cb_tc_multionet_destroy(cb_tc_multionet* plan);
+CB_API int64_t cb_tc_multionet_workspace_bytes(const cb_tc_multionet* plan, int64_t rows);
+CB_API int32_t cb_tc_multionet_set_weights(cb_tc_multionet* plan, const float* const* d_Wb,
+                                           const float* const* d_bb, const float* const* d_Wt,
+                                           const float* const* d_bt, void* stream);
+CB_API int32_t cb_tc_multionet_forward(cb_tc_multionet* plan, const float* d_branch_in,
+                                       const float* d_trunk_in, int64_t rows, float* d_y,
+                                       void* d_workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
