@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark of the CODES surrogate compute path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload = BASELINE.json configs[1] (SURVEY.md 8d "cfg2"): MultiONet with the osu2008 per-dataset
+configuration (branch 29->275x5->2842, trunk 1->275x9->2842, LeakyReLU, Q=29, f=98) on
+osu2008-shaped synthetic data (29 quantities x 100 timesteps).  A STEP is one pass of the hot path
+(`MultiONet.forward` + the `predict` epilogue: write into the (N,T,Q) buffer, denormalise) over one
+loader batch of 65 536 rows = 655.36 trajectories (config_full.yaml:4).
+
+  value     trajectories/s with the whole test set resident in HBM (1.5 GB of inputs >> 126 MB L2)
+  e2e       trajectories/s through the public plug-in API -- `model.predict(val_loader)` on a loader
+            that yields HOST batches (pinned) + the L1 metric read back, H2D/D2H inside the timing
+  roofline  the dominant kernel (don_final_kernel: both last Linears + split scalar product):
+            algorithmic FLOPs per launch / its CUDA-event duration on the launch stream, against the
+            measured bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline  the reference's CPU algorithm (torch CPU ops port) on the host cores, bounded sample
+
+`--impl reference` times the reference's CPU algorithm for the same workload (oracle/torch_port.py,
+the same torch CPU ops the reference's nn.Modules execute: the reference package itself is Python
+and does not travel to the GPU box) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "codes-benchmark_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+Q, T = 29, 100
+ROWS_PER_STEP = 65536
+TRAJ_PER_STEP = ROWS_PER_STEP / T
+CFG = dict(hidden_size=275, branch_hidden_layers=5, trunk_hidden_layers=9, output_factor=98)
+MAC_BRANCH = 29 * 275 + 4 * 275 * 275 + 275 * 2842
+MAC_TRUNK = 1 * 275 + 8 * 275 * 275 + 275 * 2842
+FLOP_PER_ROW = 2 * (MAC_BRANCH + MAC_TRUNK + 2842)            # 4.963 MFLOP
+FLOP_PER_ROW_FINAL = 2 * (2 * 275 * 2842 + 2842)              # both last Linears + combine
+NORM = {"mode": "minmax", "min": [-10.0] * Q, "max": [0.0] * Q, "log10_transform": True}
+METRIC = "inference trajectories/sec (MultiONet, osu2008-shaped 29x100)"
+WORKLOAD = "cfg2: MultiONet osu2008 config, Q=29 T=100, batch 65536 rows/step"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["bf16_tflops"]), float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst)"
+    except Exception:
+        return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi SM clock + throttle reasons sampled during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, flag in zip(names, parts[2:6]):
+                if flag.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_x0(n_traj: int, seed: int) -> np.ndarray:
+    """Initial states of the SURVEY 8d generator (only x0 and the time grid feed MultiONet)."""
+    import oracle as O
+    return O.synthetic_dataset(n_traj, T, Q, seed=seed)
+
+
+def build_model(device: str):
+    import torch
+    from torch import nn
+    import codes_b200 as cb
+    torch.manual_seed(42)
+    m = cb.MultiONet(device, Q, T, 0, None, dict(CFG, activation=nn.LeakyReLU()))
+    m.normalisation = dict(NORM)
+    m.eval()
+    return m
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_forward_rate(rows: int, repeats: int, threads: int, seed: int = 1234):
+    """The reference's CPU algorithm for this forward (torch CPU ops, oracle/torch_port.py) on
+    `threads` host threads with the GPU model's weights; returns (traj/s, seconds)."""
+    import torch
+    from oracle import torch_port as TP
+    m = build_model("cpu")
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    bw = [sd[f"branch_net.network.{2 * i}.weight"] for i in range(6)]
+    bb = [sd[f"branch_net.network.{2 * i}.bias"] for i in range(6)]
+    tw = [sd[f"trunk_net.network.{2 * i}.weight"] for i in range(10)]
+    tb = [sd[f"trunk_net.network.{2 * i}.bias"] for i in range(10)]
+    n_traj = (rows + T - 1) // T
+    d = synthetic_x0(n_traj, seed)
+    branch = torch.from_numpy(np.repeat(d[:, 0, :], T, axis=0)[:rows].copy())
+    trunk = torch.from_numpy(np.tile(np.linspace(0, 1, T, dtype=np.float32), n_traj).reshape(-1, 1)[:rows].copy())
+    dmin, dmax = torch.tensor(NORM["min"]), torch.tensor(NORM["max"])
+    torch.set_num_threads(threads)
+
+    def one():
+        with torch.inference_mode():
+            y = TP.multionet_forward(branch, trunk, bw, bb, tw, tb, Q, "leakyrelu")
+            return TP.denormalize_minmax_log(y, dmin, dmax)
+
+    one()  # warm-up (thread pool, page faults)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        one()
+    dt = time.perf_counter() - t0
+    return repeats * rows / T / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    rows = 8192   # bounded sample of one 65536-row step
+    for _ in range(max(0, min(args.warmup, 2))):
+        cpu_forward_rate(rows, 1, cores)
+    rate, dt = cpu_forward_rate(rows, args.steps, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "trajectories/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{rows} rows per step ({rows / T:.2f} trajectories)"},
+        "cpu_baseline": {"value": rate, "unit": "trajectories/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {rows} rows of the cfg2 forward, torch-CPU fp32 port of the reference forward"},
+        "e2e": {"value": rate, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import codes_b200 as cb
+    from codes_b200 import _lib, ops, tc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    cb.set_precision("bf16")
+    model = build_model(device)
+
+    # ---- resident test set of this rank (weak scaling: every rank owns n_traj trajectories)
+    n_batches = min(100, max(8, args.steps))
+    n_traj = int(np.ceil(n_batches * ROWS_PER_STEP / T))
+    d = synthetic_x0(n_traj, seed=1234 + rank)
+    x0 = torch.from_numpy(np.ascontiguousarray(d[:, 0, :])).to(device)
+    branch_all = x0.repeat_interleave(T, dim=0)                                   # rows r = n*T + t
+    trunk_all = torch.linspace(0, 1, T, device=device).repeat(n_traj).reshape(-1, 1).contiguous()
+    rows_total = n_batches * ROWS_PER_STEP
+    preds = torch.empty((rows_total, Q), device=device, dtype=torch.float32)
+    dmin = torch.tensor(NORM["min"], device=device)
+    dmax = torch.tensor(NORM["max"], device=device)
+    del x0
+
+    def step(i: int):
+        b = i % n_batches
+        lo = b * ROWS_PER_STEP
+        y = tc.multionet_forward(model, branch_all[lo:lo + ROWS_PER_STEP], trunk_all[lo:lo + ROWS_PER_STEP])
+        if y is None:
+            raise RuntimeError("fused tensor-core MultiONet path unavailable on this device")
+        out = preds[lo:lo + ROWS_PER_STEP]
+        _lib.check(_lib.lib().cb_denormalize(y.data_ptr(), ROWS_PER_STEP, Q, 1, dmin.data_ptr(), dmax.data_ptr(), 1,
+                                             out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "denormalize")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.inference_mode():
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        _lib.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clocks:
+            e0.record()
+            for i in range(args.steps):
+                step(args.warmup + i)
+            e1.record()
+            barrier()
+        launches = _lib.launch_count()
+        elapsed_ms = e0.elapsed_time(e1)
+    t_max = torch.tensor([elapsed_ms], device=device)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t_max.item())
+    value = world * args.steps * TRAJ_PER_STEP / (elapsed_ms * 1e-3)
+
+    # ---- roofline leg (rank 0): per-kernel CUDA-event durations on the launch stream
+    roofline = None
+    e2e = None
+    cpu_baseline = None
+    if rank == 0:
+        peak_tf, peak_gbs, peak_src = peaks()
+        phases = []
+        with torch.inference_mode():
+            for i in range(3 + 10):
+                ms = []
+                lo = (i % n_batches) * ROWS_PER_STEP
+                tc.multionet_forward(model, branch_all[lo:lo + ROWS_PER_STEP], trunk_all[lo:lo + ROWS_PER_STEP],
+                                     phase_ms=ms)
+                if i >= 3:
+                    phases.append(ms)
+        ph = np.mean(np.array(phases), axis=0)
+        final_ms = float(ph[2])
+        achieved = FLOP_PER_ROW_FINAL * ROWS_PER_STEP / (final_ms * 1e-3) / 1e12
+        step_tf = FLOP_PER_ROW * ROWS_PER_STEP / (elapsed_ms / args.steps * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "kernel": "don_final_kernel (both last Linears 275->2842 + split scalar product)",
+            "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+            "traffic": None, "peak_source": peak_src,
+            "kernel_ms": {"branch_chain": float(ph[0]), "trunk_chain": float(ph[1]), "final": final_ms},
+            "flops_per_launch": FLOP_PER_ROW_FINAL * ROWS_PER_STEP,
+            "step_achieved": step_tf, "step_frac": step_tf / peak_tf,
+        }
+
+        # ---- e2e leg: public API with HOST batches (pinned), H2D + metric D2H inside the timed region
+        n_e2e = 16384
+        de = synthetic_x0(n_e2e, seed=4321)
+        _, _, val_loader = model.prepare_data(de, None, de, np.linspace(0, 1, T), ROWS_PER_STEP, shuffle=False)
+        steps_per_pass = len(val_loader)
+        passes = max(1, int(round(args.steps / steps_per_pass)))
+        p, t = model.predict(val_loader)          # warm-up pass
+        model._l1(p, t)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            p, t = model.predict(val_loader)
+            metric = model._l1(p, t)              # .item(): 4-byte D2H, like validate()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": passes * n_e2e / dt, "unit": "trajectories/s",
+               "h2d_bytes_per_step": ROWS_PER_STEP * (Q + 1 + Q) * 4, "d2h_bytes_per_step": 4.0 / steps_per_pass,
+               "api": "MultiONet.predict(val_loader) + L1 metric .item()", "passes": passes,
+               "steps_per_pass": steps_per_pass, "l1_metric": metric}
+        del p, t
+
+    if world > 1:
+        # every rank must reach the end together (rank 0 also ran the extra legs)
+        dist.barrier()
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        sample_rows = ROWS_PER_STEP
+        reps = 40
+        rate, dt = cpu_forward_rate(sample_rows, reps, cores)
+        cpu_baseline = {"value": rate, "unit": "trajectories/s", "cores": cores, "kind": "port",
+                        "sample": f"{reps} x {sample_rows} rows ({dt:.1f} s) of the same cfg2 forward, torch-CPU fp32 port of the reference forward"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rows_per_step": ROWS_PER_STEP, "trajectories_per_step": TRAJ_PER_STEP,
+                       "resident_batches": n_batches, "l2_policy": "inputs larger than L2 (rotating batches)",
+                       "precision": "bf16 operands, fp32 accumulate (tcgen05)", "parallelism": f"trajectory-sharded x{world}"},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

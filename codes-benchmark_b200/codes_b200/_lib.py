@@ -83,6 +83,7 @@ _SIGNATURES = {
     "cb_tc_multionet_workspace_bytes": (_I64, [_P, _I64]),
     "cb_tc_multionet_set_weights": (_I32, [_P, _PP, _PP, _PP, _PP, _P]),
     "cb_tc_multionet_forward": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _P]),
+    "cb_tc_multionet_forward_timed": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _P, C.POINTER(C.c_float)]),
 }
 
 

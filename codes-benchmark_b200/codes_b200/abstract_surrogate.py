@@ -119,7 +119,7 @@ class AbstractSurrogateModel(ABC, nn.Module):
         preds = targs = None
         done = 0
         with torch.inference_mode():
-            for inputs in data_loader:
+            for inputs in self._prefetch_to_device(data_loader):
                 p, t = self(inputs)
                 if preds is None:
                     shape = (p.shape[0] * n_batches, *p.shape[1:])
@@ -135,6 +135,38 @@ class AbstractSurrogateModel(ABC, nn.Module):
             targs = self.denormalize(targs[:done], leave_log, leave_norm)
         return (preds.reshape(-1, self.n_timesteps, self.n_quantities),
                 targs.reshape(-1, self.n_timesteps, self.n_quantities))
+
+    def _prefetch_to_device(self, data_loader):
+        """Yield the loader's batches with their tensors already on ``self.device``.
+
+        On CUDA the host->device copy of batch i+1 is issued on a side stream while batch i is
+        being computed (the loaders hand out pinned memory), instead of the reference's
+        copy-then-compute on one stream (abstract_surrogate.py:250-255)."""
+        dev = self.device
+        if dev is None or "cuda" not in str(dev) or not torch.cuda.is_available():
+            yield from data_loader
+            return
+        device = torch.device(dev)
+        copy_stream = torch.cuda.Stream(device)
+        pending = None
+        for batch in data_loader:
+            with torch.cuda.stream(copy_stream):
+                moved = tuple(x.to(device, non_blocking=True) if isinstance(x, Tensor) else x for x in batch)
+                ready = copy_stream.record_event()
+            if pending is not None:
+                yield self._await_batch(*pending, device)
+            pending = (moved, ready)
+        if pending is not None:
+            yield self._await_batch(*pending, device)
+
+    @staticmethod
+    def _await_batch(batch, ready, device):
+        cur = torch.cuda.current_stream(device)
+        cur.wait_event(ready)
+        for x in batch:
+            if isinstance(x, Tensor) and x.is_cuda:
+                x.record_stream(cur)
+        return batch
 
     def denormalize(self, data: Tensor | np.ndarray, leave_log: bool = False,
                     leave_norm: bool = False) -> Tensor | np.ndarray:
@@ -304,7 +336,7 @@ class AbstractSurrogateModel(ABC, nn.Module):
         self.eval()
         with torch.inference_mode():
             preds, targets = self.predict(test_loader)
-            final_loss = criterion(preds, targets).item()
+            final_loss = self._criterion_value(criterion, preds, targets)
         if final_loss < self.best_test_loss:
             self.best_epoch, self.best_test_loss = self.n_epochs - 1, final_loss
         else:
@@ -315,6 +347,15 @@ class AbstractSurrogateModel(ABC, nn.Module):
             pass
 
     # ------------------------------------------------------------------ validation
+    @staticmethod
+    def _criterion_value(criterion: nn.Module, a: Tensor, b: Tensor) -> float:
+        kinds = {nn.MSELoss: "mse", nn.SmoothL1Loss: "smoothl1", nn.L1Loss: "l1"}
+        kind = kinds.get(type(criterion))
+        if a.is_cuda and kind is not None and getattr(criterion, "reduction", "mean") == "mean" \
+                and float(getattr(criterion, "beta", 1.0)) == 1.0:
+            return float(ops.pointwise_loss(a, b, kind).item())
+        return float(criterion(a, b).item())
+
     def _l1(self, a: Tensor, b: Tensor) -> float:
         if a.is_cuda:
             return float(ops.pointwise_loss(a, b, "l1").item())

@@ -89,8 +89,9 @@ class _MultiONetPlan:
 _MULTIONET_PLANS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 
-def multionet_forward(model, branch_input, trunk_input):
-    """Fused MultiONet forward; returns None when the shape is not supported by the fused kernels."""
+def multionet_forward(model, branch_input, trunk_input, phase_ms=None):
+    """Fused MultiONet forward; returns None when the shape is not supported by the fused kernels.
+    ``phase_ms``: optional list that receives the per-kernel durations (bench.py roofline leg)."""
     if not available():
         return None
     bspec, tspec = model.branch_net.chain(), model.trunk_net.chain()
@@ -122,7 +123,17 @@ def multionet_forward(model, branch_input, trunk_input):
         if plan.workspace is None or plan.workspace.numel() < need or plan.workspace.device != dev:
             plan.workspace = torch.empty(need, device=dev, dtype=torch.uint8)
         y = torch.empty((rows, q), device=dev, dtype=torch.float32)
-        check(lib().cb_tc_multionet_forward(plan.handle, C.c_void_p(b2.data_ptr()), C.c_void_p(t2.data_ptr()), rows,
-                                            C.c_void_p(y.data_ptr()), C.c_void_p(plan.workspace.data_ptr()),
-                                            plan.workspace.numel(), _stream(dev)), "tc_multionet_forward")
+        if phase_ms is None:
+            check(lib().cb_tc_multionet_forward(plan.handle, C.c_void_p(b2.data_ptr()), C.c_void_p(t2.data_ptr()),
+                                                rows, C.c_void_p(y.data_ptr()),
+                                                C.c_void_p(plan.workspace.data_ptr()), plan.workspace.numel(),
+                                                _stream(dev)), "tc_multionet_forward")
+        else:
+            ms = (C.c_float * 3)()
+            check(lib().cb_tc_multionet_forward_timed(plan.handle, C.c_void_p(b2.data_ptr()),
+                                                      C.c_void_p(t2.data_ptr()), rows, C.c_void_p(y.data_ptr()),
+                                                      C.c_void_p(plan.workspace.data_ptr()),
+                                                      plan.workspace.numel(), _stream(dev), ms),
+                  "tc_multionet_forward_timed")
+            phase_ms[:] = [float(v) for v in ms]
     return y

@@ -984,9 +984,37 @@ extern "C" int32_t cb_tc_multionet_set_weights(cb_tc_multionet* m, const float* 
   return CB_OK;
 }
 
+static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_in, const float* d_trunk_in,
+                                      int64_t rows, float* d_y, void* d_workspace, int64_t workspace_bytes,
+                                      void* stream, cudaEvent_t* ev);
+
 extern "C" int32_t cb_tc_multionet_forward(cb_tc_multionet* m, const float* d_branch_in, const float* d_trunk_in,
                                            int64_t rows, float* d_y, void* d_workspace, int64_t workspace_bytes,
                                            void* stream) {
+  return multionet_forward_impl(m, d_branch_in, d_trunk_in, rows, d_y, d_workspace, workspace_bytes, stream, nullptr);
+}
+
+// Same launches with CUDA events recorded around each kernel ON THE LAUNCH STREAM; synchronises and
+// returns the three durations (branch hidden chain, trunk hidden chain, final kernel) in ms.
+extern "C" int32_t cb_tc_multionet_forward_timed(cb_tc_multionet* m, const float* d_branch_in,
+                                                 const float* d_trunk_in, int64_t rows, float* d_y,
+                                                 void* d_workspace, int64_t workspace_bytes, void* stream,
+                                                 float* phase_ms) {
+  CB_CHECK_ARG(phase_ms != nullptr, "phase_ms is NULL");
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; ++i) CB_CUDA(cudaEventCreate(&ev[i]));
+  int32_t e = multionet_forward_impl(m, d_branch_in, d_trunk_in, rows, d_y, d_workspace, workspace_bytes, stream, ev);
+  if (e == CB_OK) {
+    if (cudaEventSynchronize(ev[3]) != cudaSuccess) { set_error("event synchronize failed"); e = CB_ERR_CUDA; }
+    for (int i = 0; i < 3 && e == CB_OK; ++i) cudaEventElapsedTime(&phase_ms[i], ev[i], ev[i + 1]);
+  }
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+  return e;
+}
+
+static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_in, const float* d_trunk_in,
+                                      int64_t rows, float* d_y, void* d_workspace, int64_t workspace_bytes,
+                                      void* stream, cudaEvent_t* ev) {
   CB_CHECK_ARG(m != nullptr, "plan is NULL");
   CB_CHECK_ARG(m->weights_set, "cb_tc_multionet_set_weights must be called first");
   CB_CHECK_ARG(rows >= 0, "rows < 0");
@@ -1006,8 +1034,11 @@ extern "C" int32_t cb_tc_multionet_forward(cb_tc_multionet* m, const float* d_br
   CUtensorMap hmap[2];
   for (int i = 0; i < 2; ++i)
     CB_CHECK_ARG(encode_bf16_map(&hmap[i], h[i], rows, m->ld_h), "tensor map of the hidden activations failed");
+  if (ev) cudaEventRecord(ev[0], st);
   if (int32_t e = chain_launch(m->hidden[0], d_branch_in, nullptr, rows, nullptr, &hmap[0], st)) return e;
+  if (ev) cudaEventRecord(ev[1], st);
   if (int32_t e = chain_launch(m->hidden[1], d_trunk_in, nullptr, rows, nullptr, &hmap[1], st)) return e;
+  if (ev) cudaEventRecord(ev[2], st);
   FinalParams F = m->F;
   F.tmap_in[0] = hmap[0]; F.tmap_in[1] = hmap[1];
   F.y = d_y; F.rows = rows;
@@ -1015,5 +1046,6 @@ extern "C" int32_t cb_tc_multionet_forward(cb_tc_multionet* m, const float* d_br
   const int grid = F.num_tiles < num_sms() ? F.num_tiles : num_sms();
   don_final_kernel<<<grid, kThreads, m->smem_final, st>>>(F);
   CB_LAUNCH_CHECK();
+  if (ev) cudaEventRecord(ev[3], st);
   return CB_OK;
 }

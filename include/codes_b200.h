@@ -223,6 +223,12 @@ CB_API int32_t cb_tc_multionet_set_weights(cb_tc_multionet* plan, const float* c
 CB_API int32_t cb_tc_multionet_forward(cb_tc_multionet* plan, const float* d_branch_in,
                                        const float* d_trunk_in, int64_t rows, float* d_y,
                                        void* d_workspace, int64_t workspace_bytes, void* stream);
+/* Measurement aid for bench.py: same three launches with CUDA events recorded on `stream` around
+ * each kernel; synchronises and returns {branch chain, trunk chain, final kernel} durations (ms). */
+CB_API int32_t cb_tc_multionet_forward_timed(cb_tc_multionet* plan, const float* d_branch_in,
+                                             const float* d_trunk_in, int64_t rows, float* d_y,
+                                             void* d_workspace, int64_t workspace_bytes, void* stream,
+                                             float* phase_ms);
 
 #ifdef __cplusplus
 }
