@@ -15,9 +15,10 @@
 // the same time and the epilogue multiplies them and segment-sums over each quantity's f columns,
 // so the two (rows x Q*f) fp32 tensors of the reference (deeponet.py:241-253) never exist.
 //
-// Warp roles (192 threads):   warp 0     TMA producer (1 elected thread)
+// Warp roles (320 threads):   warp 0     TMA producer (1 elected thread)
 //                             warp 1     tcgen05.mma issuer (1 elected thread) + TMEM alloc/dealloc
-//                             warps 2-5  epilogue, one TMEM lane quarter (32 rows) each
+//                             warps 2-9  epilogue: two warps per TMEM lane quarter (32 rows), each
+//                                        taking every other 32-column group of a chunk
 // Work items ("jobs") are (layer, 128-column output chunk); MMA of job j+1 overlaps the epilogue of
 // job j through the TMEM slot ring, and layer l+1 starts on the k-blocks whose producing chunks of
 // layer l are already written (fine-grained dependency through the `epi_done` counter).
@@ -28,6 +29,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "cb_common.cuh"
@@ -42,8 +44,10 @@ constexpr int kUmmaK = 16;
 constexpr int kSlots = 4;            // TMEM slots (4 x 128 = 512 columns)
 constexpr int kKBlockBytes = kTileM * kBlockK * 2;     // 16 KiB: one k-block of A or one B stage
 constexpr int kMaxJobs = 96;
+constexpr int kMaxGroups = 128;      // 32-column groups of the MultiONet output layer (<= 4096 columns)
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiThreads = 256;   // 8 epilogue warps: two per TMEM lane quarter, splitting the columns
+constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kMaxSmem = 232448;     // 227 KiB
 constexpr int kCtrlBytes = 16 * kMaxStages + 16 * kSlots + 64;
 
@@ -53,9 +57,9 @@ enum { OUT_F32 = 0, OUT_BF16_TMA = 1 };
 struct Job { int16_t layer, n0, ncols, last_chunk; };
 
 struct ChainParams {
-  CUtensorMap tmap_w[CB_MAX_LAYERS];
   CUtensorMap tmap_in;         // IN_BF16_TMA : (rows, ld_in) bf16
   CUtensorMap tmap_out;        // OUT_BF16_TMA: (rows, ld_out) bf16
+  const __nv_bfloat16* w[CB_MAX_LAYERS];   // pre-tiled, pre-swizzled weights: tile (chunk, kb) = 16 KiB run
   int K[CB_MAX_LAYERS];        // true input width (the ones column sits at index K)
   int N[CB_MAX_LAYERS];        // true output width
   int ksteps[CB_MAX_LAYERS];   // ceil((K+1)/16)
@@ -73,10 +77,12 @@ struct ChainParams {
 };
 
 struct FinalParams {
-  CUtensorMap tmap_w[2];       // branch / trunk last-layer weights (rows_alloc, Kp) bf16, bias folded
   CUtensorMap tmap_in[2];      // hb / ht (rows, ld) bf16
+  const __nv_bfloat16* w[2];   // branch / trunk last-layer weights, pre-tiled (chunk, kb) 16 KiB runs, bias folded
   int K, ksteps, nkb, n_jobs, n_out, Q, stages;
   int seg_base, seg_rem;       // split sizes: seg_base + (q < seg_rem)   (deeponet.py:130-137)
+  int16_t grp_q[kMaxGroups];   // quantity whose split contains the first column of 32-column group g
+  int16_t grp_end[kMaxGroups]; // end column (exclusive) of that split
   float* y;                    // (rows, Q) fp32
   long long rows;
   int num_tiles;
@@ -113,6 +119,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// contiguous global -> shared bulk copy (the weights are pre-tiled so one stage = one 16 KiB run)
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
@@ -124,7 +136,7 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -137,6 +149,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// one lane of a converged warp (elect.sync): keeps the surrounding control flow warp-uniform so the
+// descriptor arithmetic stays in uniform registers and tcgen05.mma issues back to back
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xFFFFFFFF;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+  return pred != 0;
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) = 0 | SBO>>4 [32,46) = 1024>>4 | version [46,48) = 1 | layout [61,64) = 2
@@ -178,6 +197,9 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+__device__ __forceinline__ void red_shared_add_f32(uint32_t addr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
@@ -204,7 +226,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 template <int ACT>
 __device__ __forceinline__ float act_fast(float x, float p) {
   if constexpr (ACT == CB_ACT_RELU) return fmaxf(x, 0.f);
-  else if constexpr (ACT == CB_ACT_LEAKYRELU || ACT == CB_ACT_PRELU) return x >= 0.f ? x : p * x;
+  else if constexpr (ACT == CB_ACT_LEAKYRELU || ACT == CB_ACT_PRELU) return (p >= 0.f && p <= 1.f) ? fmaxf(x, p * x) : (x >= 0.f ? x : p * x);
   else if constexpr (ACT == CB_ACT_TANH) return tanh_fast(x);
   else if constexpr (ACT == CB_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
   else if constexpr (ACT == CB_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
@@ -215,8 +237,13 @@ __device__ __forceinline__ float act_fast(float x, float p) {
   else return x;
 }
 
-// activation + bf16 pack of `w` (16 or 32) accumulator columns -> next layer's A operand;
-// column `ones_col` receives the constant 1.0 that multiplies the folded bias.
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+// activation + bf16 pack of `w` (16 or 32) accumulator columns -> next layer's A operand.
+// If the group contains column `ones_col`, that element is overwritten with the constant 1.0 that
+// multiplies the folded bias (one predicated 2-byte store instead of a select per element).
 template <int ACT>
 __device__ __forceinline__ void epi_hidden(const uint32_t (&v)[32], int w, int nb, int ones_col, float p,
                                            uint32_t xo, int r) {
@@ -225,14 +252,13 @@ __device__ __forceinline__ void epi_hidden(const uint32_t (&v)[32], int w, int n
     if (g * 8 < w) {
       float f[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float a = act_fast<ACT>(__uint_as_float(v[g * 8 + i]), p);
-        f[i] = (nb + g * 8 + i == ones_col) ? 1.f : a;
-      }
+      for (int i = 0; i < 8; ++i) f[i] = act_fast<ACT>(__uint_as_float(v[g * 8 + i]), p);
       st_shared_v4(xo + act_chunk_off(r, (nb >> 3) + g), pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
                    pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
     }
   }
+  if (ones_col >= nb && ones_col < nb + w)
+    st_shared_u16(xo + act_chunk_off(r, ones_col >> 3) + (uint32_t)((ones_col & 7) * 2), (uint16_t)0x3F80);  // bf16(1.0)
 }
 
 struct Ctrl {
@@ -258,7 +284,7 @@ __device__ __forceinline__ Ctrl carve_ctrl(uint32_t ctrl_addr, uint8_t* ctrl_ptr
 __device__ __forceinline__ uint32_t setup_cta(const Ctrl& c, int stages, int warp) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(c.bar_full + 8 * s, 1); mbar_init(c.bar_empty + 8 * s, 1); }
-    for (int s = 0; s < kSlots; ++s) { mbar_init(c.bar_tfull + 8 * s, 1); mbar_init(c.bar_tempty + 8 * s, 128); }
+    for (int s = 0; s < kSlots; ++s) { mbar_init(c.bar_tfull + 8 * s, 1); mbar_init(c.bar_tempty + 8 * s, kEpiThreads); }
     mbar_init(c.bar_in, 1);
     *c.epi_done = 0;
     *c.in_staged = 0;
@@ -305,8 +331,8 @@ chain_kernel(const __grid_constant__ ChainParams P) {
   const int n_my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
-    // ============================================================ TMA producer
-    if (lane == 0) {
+    // ============================================================ TMA producer (warp-converged, one elected lane issues)
+    {
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < n_my_tiles; ++it) {
         if (P.in_mode == IN_BF16_TMA) {
@@ -314,26 +340,33 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           while (ld_volatile_shared(C.epi_done) < it * P.n_jobs) { }
           __threadfence_block();
           const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-          mbar_arrive_expect_tx(C.bar_in, (uint32_t)P.nkb[0] * kKBlockBytes);
-          for (int kb = 0; kb < P.nkb[0]; ++kb)
-            tma_load_2d(X0 + kb * kKBlockBytes, &P.tmap_in, kb * kBlockK, tile * kTileM, C.bar_in);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(C.bar_in, (uint32_t)P.nkb[0] * kKBlockBytes);
+            for (int kb = 0; kb < P.nkb[0]; ++kb)
+              tma_load_2d(X0 + kb * kKBlockBytes, &P.tmap_in, kb * kBlockK, tile * kTileM, C.bar_in);
+          }
+          __syncwarp();
         }
         for (int j = 0; j < P.n_jobs; ++j) {
           const Job job = P.jobs[j];
           const int nkb = P.nkb[job.layer];
+          const __nv_bfloat16* src = P.w[job.layer] + (size_t)(job.n0 / kChunkN) * nkb * (kKBlockBytes / 2);
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(C.bar_empty + 8 * stage, phase ^ 1);
-            mbar_arrive_expect_tx(C.bar_full + 8 * stage, kKBlockBytes);
-            tma_load_2d(ST0 + stage * kKBlockBytes, &P.tmap_w[job.layer], kb * kBlockK, job.n0, C.bar_full + 8 * stage);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(C.bar_full + 8 * stage, kKBlockBytes);
+              bulk_load(ST0 + stage * kKBlockBytes, src + (size_t)kb * (kKBlockBytes / 2), kKBlockBytes,
+                        C.bar_full + 8 * stage);
+            }
+            __syncwarp();
             if (++stage == P.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    if (lane == 0) {
+    // ============================================================ MMA issuer (warp-converged; one elected lane issues)
+    {
       int stage = 0; uint32_t phase = 0;
       int gj = 0;
       for (int it = 0; it < n_my_tiles; ++it) {
@@ -362,24 +395,30 @@ chain_kernel(const __grid_constant__ ChainParams P) {
             mbar_wait(C.bar_full + 8 * stage, phase);
             tcgen05_fence_after();
             const int nks = min(4, ksteps - kb * 4);
-            for (int ks = 0; ks < nks; ++ks) {
-              const uint64_t adesc = make_smem_desc(xa + kb * kKBlockBytes + ks * (kUmmaK * 2));
-              const uint64_t bdesc = make_smem_desc(ST0 + stage * kKBlockBytes + ks * (kUmmaK * 2));
-              umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | ks) ? 1u : 0u);
+            const uint64_t adesc = make_smem_desc(xa + kb * kKBlockBytes);
+            const uint64_t bdesc = make_smem_desc(ST0 + stage * kKBlockBytes);
+            if (elect_one()) {
+              // +2 in the descriptor's start-address field = +32 bytes = one 16-column k-step
+              umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+#pragma unroll
+              for (int ks = 1; ks < 4; ++ks)
+                if (ks < nks) umma_bf16(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
+              umma_commit(C.bar_empty + 8 * stage);   // frees the weight stage when these MMAs retire
             }
-            umma_commit(C.bar_empty + 8 * stage);   // frees the weight stage when these MMAs retire
+            __syncwarp();
             if (++stage == P.stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(C.bar_tfull + 8 * slot);       // accumulator chunk complete -> epilogue
+          if (elect_one()) umma_commit(C.bar_tfull + 8 * slot);   // accumulator chunk complete -> epilogue
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else {
-    // ============================================================ epilogue warps (2..5)
+    // ============================================================ epilogue warps (2..9)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;            // row inside the tile
-    const int et = threadIdx.x - 64;        // 0..127
+    const int h = (warp - 2) >> 2;          // column half: this warp takes 32-column groups with (group & 1) == h
+    const int et = threadIdx.x - 64;        // 0..255
     const int K0 = P.K[0];
     int gj = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
@@ -390,7 +429,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         // stage the fp32 input rows as the bf16 A operand of layer 0: [x, 1, 0...] padded to 16*ksteps
         const float* xr = P.x + row_g * K0;
         const int nch = P.ksteps[0] * 2;    // 16-byte chunks (8 columns each)
-        for (int c = 0; c < nch; ++c) {
+        for (int c = h; c < nch; c += 2) {
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -416,7 +455,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * kChunkN;
         const uint32_t xo = ((l + 1) & 1) ? X1 : X0;
         const int N = P.N[l];
-        for (int c0 = 0; c0 < job.ncols; c0 += 32) {
+        for (int c0 = h * 32; c0 < job.ncols; c0 += 64) {
           uint32_t v[32];
           const int w = min(32, job.ncols - c0);   // 32 or 16
           if (w == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
@@ -445,7 +484,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         tcgen05_fence_before();
         mbar_arrive(C.bar_tempty + 8 * slot);
         if (to_smem) {
-          if (job.last_chunk && (N & 15) == 0) {
+          if (h == 0 && job.last_chunk && (N & 15) == 0) {
             // ones column starts a fresh 16-column k-step: write [1,0,...,0] (32 bytes)
             st_shared_v4(xo + act_chunk_off(r, N >> 3), pack_bf16(1.f, 0.f), 0u, 0u, 0u);
             st_shared_v4(xo + act_chunk_off(r, (N >> 3) + 1), 0u, 0u, 0u, 0u);
@@ -464,14 +503,15 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           }
         } else {
           epi_bar_sync();
-          // coalesced copy-out: thread `et` owns column n0+et of every row of the tile
-          const int n = job.n0 + et;
-          if (et < job.ncols && n < N) {
+          // coalesced copy-out: thread owns column n0 + (et & 127) for the rows of parity (et >> 7)
+          const int col = et & 127;
+          const int n = job.n0 + col;
+          if (col < job.ncols && n < N) {
             const long long rows_left = P.rows - (long long)tile * kTileM;
-            const int nr = rows_left < kTileM ? (int)rows_left : kTileM;
+            const int nr = rows_left < kTileM ? (int)(rows_left < 0 ? 0 : rows_left) : kTileM;
             float* yp = P.y + (long long)tile * kTileM * N + n;
-            for (int rr = 0; rr < nr; ++rr)
-              yp[(long long)rr * N] = ld_shared_f32(OSTG + (uint32_t)((rr * P.stage_ld + et) * 4));
+            for (int rr = et >> 7; rr < nr; rr += 2)
+              yp[(long long)rr * N] = ld_shared_f32(OSTG + (uint32_t)((rr * P.stage_ld + col) * 4));
           }
           epi_bar_sync();
         }
@@ -494,7 +534,7 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
   const uint32_t XB = base, XT = base + xbytes, ST0 = base + 2 * xbytes;
   const uint32_t ctrl_addr = ST0 + (uint32_t)P.stages * kKBlockBytes;
   const Ctrl C = carve_ctrl(ctrl_addr, gbase + (ctrl_addr - base));
-  const uint32_t OSTG = ctrl_addr + kCtrlBytes;      // (128, Q+1) fp32
+  const uint32_t OSTG = ctrl_addr + kCtrlBytes;      // (128, Q+1) fp32 output staging tile
   const int out_ld = P.Q + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -502,76 +542,99 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
   const int n_my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < n_my_tiles; ++it) {
-        while (ld_volatile_shared(C.epi_done) < it) { }      // previous tile fully consumed
-        __threadfence_block();
-        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    // TMA producer: warp-converged, one elected lane issues
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < n_my_tiles; ++it) {
+      while (ld_volatile_shared(C.epi_done) < it) { }      // previous tile fully consumed
+      __threadfence_block();
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      if (elect_one()) {
         mbar_arrive_expect_tx(C.bar_in, 2u * P.nkb * kKBlockBytes);
         for (int kb = 0; kb < P.nkb; ++kb) {
           tma_load_2d(XB + kb * kKBlockBytes, &P.tmap_in[0], kb * kBlockK, tile * kTileM, C.bar_in);
           tma_load_2d(XT + kb * kKBlockBytes, &P.tmap_in[1], kb * kBlockK, tile * kTileM, C.bar_in);
         }
-        for (int j = 0; j < P.n_jobs; ++j) {
-          for (int net = 0; net < 2; ++net) {
-            for (int kb = 0; kb < P.nkb; ++kb) {
-              mbar_wait(C.bar_empty + 8 * stage, phase ^ 1);
+      }
+      __syncwarp();
+      for (int j = 0; j < P.n_jobs; ++j) {
+        for (int net = 0; net < 2; ++net) {
+          const __nv_bfloat16* src = P.w[net] + (size_t)j * P.nkb * (kKBlockBytes / 2);
+          for (int kb = 0; kb < P.nkb; ++kb) {
+            mbar_wait(C.bar_empty + 8 * stage, phase ^ 1);
+            if (elect_one()) {
               mbar_arrive_expect_tx(C.bar_full + 8 * stage, kKBlockBytes);
-              tma_load_2d(ST0 + stage * kKBlockBytes, &P.tmap_w[net], kb * kBlockK, j * kChunkN, C.bar_full + 8 * stage);
-              if (++stage == P.stages) { stage = 0; phase ^= 1; }
+              bulk_load(ST0 + stage * kKBlockBytes, src + (size_t)kb * (kKBlockBytes / 2), kKBlockBytes,
+                        C.bar_full + 8 * stage);
             }
+            __syncwarp();
+            if (++stage == P.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int gs = 0;   // global slot-use counter (2 per job)
-      for (int it = 0; it < n_my_tiles; ++it) {
-        mbar_wait(C.bar_in, it & 1);
-        tcgen05_fence_after();
-        for (int j = 0; j < P.n_jobs; ++j) {
-          const int ncols = min(kChunkN, P.n_out - j * kChunkN);
-          const uint32_t idesc = make_idesc(ncols);
-          for (int net = 0; net < 2; ++net, ++gs) {
-            const int slot = gs & (kSlots - 1);
-            const uint32_t use = (uint32_t)(gs / kSlots);
-            mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
+    // MMA issuer: warp-converged control flow, one elected lane issues
+    int stage = 0; uint32_t phase = 0;
+    int gs = 0;   // global slot-use counter (2 per job)
+    for (int it = 0; it < n_my_tiles; ++it) {
+      mbar_wait(C.bar_in, it & 1);
+      tcgen05_fence_after();
+      for (int j = 0; j < P.n_jobs; ++j) {
+        const int ncols = min(kChunkN, P.n_out - j * kChunkN);
+        const uint32_t idesc = make_idesc(ncols);
+        for (int net = 0; net < 2; ++net, ++gs) {
+          const int slot = gs & (kSlots - 1);
+          const uint32_t use = (uint32_t)(gs / kSlots);
+          mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
+          tcgen05_fence_after();
+          const uint32_t xa = net ? XT : XB;
+          const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
+          for (int kb = 0; kb < P.nkb; ++kb) {
+            mbar_wait(C.bar_full + 8 * stage, phase);
             tcgen05_fence_after();
-            const uint32_t xa = net ? XT : XB;
-            const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
-            for (int kb = 0; kb < P.nkb; ++kb) {
-              mbar_wait(C.bar_full + 8 * stage, phase);
-              tcgen05_fence_after();
-              const int nks = min(4, P.ksteps - kb * 4);
-              for (int ks = 0; ks < nks; ++ks) {
-                const uint64_t adesc = make_smem_desc(xa + kb * kKBlockBytes + ks * (kUmmaK * 2));
-                const uint64_t bdesc = make_smem_desc(ST0 + stage * kKBlockBytes + ks * (kUmmaK * 2));
-                umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | ks) ? 1u : 0u);
-              }
+            const int nks = min(4, P.ksteps - kb * 4);
+            const uint64_t adesc = make_smem_desc(xa + kb * kKBlockBytes);
+            const uint64_t bdesc = make_smem_desc(ST0 + stage * kKBlockBytes);
+            if (elect_one()) {
+              umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+#pragma unroll
+              for (int ks = 1; ks < 4; ++ks)
+                if (ks < nks) umma_bf16(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
               umma_commit(C.bar_empty + 8 * stage);
-              if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(C.bar_tfull + 8 * slot);
+            __syncwarp();
+            if (++stage == P.stages) { stage = 0; phase ^= 1; }
           }
+          if (elect_one()) umma_commit(C.bar_tfull + 8 * slot);
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else {
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
-    const int et = threadIdx.x - 64;
+    const int h = (warp - 2) >> 2;          // this warp takes the 32-column groups with (group & 1) == h
+    const int et = threadIdx.x - 64;        // 0..255
+    const uint32_t my_row = OSTG + (uint32_t)((r * out_ld) * 4);
+    // Each of the two column-half warps of a row keeps ONE running partial per quantity in a register
+    // and adds it to shared memory exactly once (red.shared): every y[r,q] is 0 + a + b with a, b the
+    // two halves' partials -> commutative, hence bitwise deterministic.
+    int cur_q = -1;
+    float cur_acc = 0.f;
+    auto add_to = [&](int qq, float s) {
+      if (qq != cur_q) {
+        if (cur_q >= 0 && cur_q < P.Q) red_shared_add_f32(my_row + (uint32_t)(cur_q * 4), cur_acc);
+        cur_q = qq;
+        cur_acc = 0.f;
+      }
+      cur_acc += s;
+    };
     int gs = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      // running segment state: quantity index, end column of its split, partial sum
-      int qi = 0;
-      int seg_end = P.seg_base + (0 < P.seg_rem ? 1 : 0);
-      float acc = 0.f;
+      if (h == 0)
+        for (int qq = 0; qq < P.Q; ++qq) st_shared_f32(my_row + (uint32_t)(qq * 4), 0.f);
+      epi_bar_sync();
       for (int j = 0; j < P.n_jobs; ++j, gs += 2) {
         const int ncols = min(kChunkN, P.n_out - j * kChunkN);
         const int slot_b = gs & (kSlots - 1), slot_t = (gs + 1) & (kSlots - 1);
@@ -580,23 +643,53 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
         tcgen05_fence_after();
         const uint32_t ta_b = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)slot_b * kChunkN;
         const uint32_t ta_t = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)slot_t * kChunkN;
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
+        for (int c0 = h * 32; c0 < ncols; c0 += 64) {
           uint32_t vb[32], vt[32];
           const int w = min(32, ncols - c0);
           if (w == 32) { tmem_ld32(ta_b + c0, vb); tmem_ld32(ta_t + c0, vt); }
           else { tmem_ld16(ta_b + c0, vb); tmem_ld16(ta_t + c0, vt); }
           tmem_ld_wait();
           const int nb = j * kChunkN + c0;
+          const int g = nb >> 5;
+          int qi = P.grp_q[g];
+          int seg_end = P.grp_end[g];
+          float pr[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i < w) {
-              acc = fmaf(__uint_as_float(vb[i]), __uint_as_float(vt[i]), acc);
-              if (nb + i + 1 == seg_end) {        // warp-uniform: end of quantity qi's split
-                if (qi < P.Q) st_shared_f32(OSTG + (uint32_t)((r * out_ld + qi) * 4), acc);
-                acc = 0.f;
-                ++qi;
-                seg_end += P.seg_base + (qi < P.seg_rem ? 1 : 0);
+          for (int i = 0; i < 32; ++i) pr[i] = (i < w) ? __uint_as_float(vb[i]) * __uint_as_float(vt[i]) : 0.f;
+          if (seg_end >= nb + w) {
+            // whole group inside one split: 4 independent partial sums
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) { s0 += pr[i]; s1 += pr[i + 1]; s2 += pr[i + 2]; s3 += pr[i + 3]; }
+            add_to(qi, (s0 + s1) + (s2 + s3));
+          } else {
+            const int next_sz = P.seg_base + (qi + 1 < P.seg_rem ? 1 : 0);
+            if (seg_end + next_sz >= nb + w) {
+              // exactly one split boundary inside the group, at offset k
+              const int k = seg_end - nb;
+              float lo = 0.f, hi = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const bool below = i < k;
+                lo += below ? pr[i] : 0.f;
+                hi += below ? 0.f : pr[i];
               }
+              add_to(qi, lo);
+              add_to(qi + 1, hi);
+            } else {
+              // several boundaries (splits narrower than a group): element-wise walk (warp-uniform branches)
+              float acc = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                acc += pr[i];
+                if (nb + i + 1 == seg_end) {
+                  add_to(qi, acc);
+                  acc = 0.f;
+                  ++qi;
+                  seg_end += P.seg_base + (qi < P.seg_rem ? 1 : 0);
+                }
+              }
+              add_to(qi, acc);
             }
           }
         }
@@ -604,13 +697,14 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
         mbar_arrive(C.bar_tempty + 8 * slot_b);
         mbar_arrive(C.bar_tempty + 8 * slot_t);
       }
+      add_to(-1, 0.f);   // flush the last running partial
       epi_bar_sync();
-      // coalesced copy-out of the (128, Q) tile: linear over the contiguous global block
+      // coalesced copy-out of the (128, Q) tile, linear over the contiguous global block
       {
         const long long rows_left = P.rows - (long long)tile * kTileM;
-        const int nr = rows_left < kTileM ? (int)rows_left : kTileM;
+        const int nr = rows_left < kTileM ? (int)(rows_left < 0 ? 0 : rows_left) : kTileM;
         float* yp = P.y + (long long)tile * kTileM * P.Q;
-        for (int idx = et; idx < nr * P.Q; idx += 128) {
+        for (int idx = et; idx < nr * P.Q; idx += kEpiThreads) {
           const int rr = idx / P.Q, qq = idx - rr * P.Q;
           yp[idx] = ld_shared_f32(OSTG + (uint32_t)((rr * out_ld + qq) * 4));
         }
@@ -622,10 +716,14 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
   teardown_cta(tmem_base, warp);
 }
 
-// fp32 (N,K) row-major + bias -> bf16 (rows_alloc, Kp): [W | b | 0...], zero rows beyond N
+// fp32 (N,K) row-major + bias -> bf16 tiles in the exact shared-memory image of a weight stage:
+// tile (chunk = n/128, kb = k/64) is a contiguous 16 KiB run holding rows n%128 of 128 bytes each with
+// the 16-byte chunks XOR-swizzled by (row & 7) (the UMMA SWIZZLE_128B K-major layout).  Column K holds
+// the bias, rows >= N and columns > K are zero.
 __global__ void pack_weights_kernel(const float* __restrict__ W, const float* __restrict__ b, int N, int K,
                                     int rows_alloc, int Kp, __nv_bfloat16* __restrict__ Wp) {
   const long long total = (long long)rows_alloc * Kp;
+  const int nkb = Kp / kBlockK;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(i / Kp), k = (int)(i % Kp);
@@ -634,7 +732,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, const float* __
       if (k < K) v = W[(long long)n * K + k];
       else if (k == K && b) v = b[n];
     }
-    Wp[i] = __float2bfloat16(v);
+    const int chunk = n / kChunkN, r = n % kChunkN, kb = k / kBlockK, kk = k % kBlockK;
+    const size_t off = ((size_t)chunk * nkb + kb) * (kKBlockBytes / 2) + (size_t)r * kBlockK +
+                       (size_t)(((kk >> 3) ^ (r & 7)) << 3) + (kk & 7);
+    Wp[off] = __float2bfloat16(v);
   }
 }
 
@@ -691,6 +792,14 @@ using namespace cb;
 using namespace cb::tc;
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// experiment knob (profiling only): CB_TC_MAX_CTAS caps the persistent grid
+static int grid_cap() {
+  const char* e = getenv("CB_TC_MAX_CTAS");
+  const int cap = e ? atoi(e) : 0;
+  const int sms = num_sms();
+  return (cap > 0 && cap < sms) ? cap : sms;
+}
 
 struct cb_tc_chain {
   cb_mlp_desc desc;
@@ -799,11 +908,7 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
       set_error("cudaMalloc of the bf16 weight cache failed");
       return CB_ERR_CUDA;
     }
-    if (!encode_bf16_map(&P.tmap_w[i], pl->d_w[i], pl->rows_alloc[i], pl->Kp[i])) {
-      cb_tc_chain_destroy(pl);
-      set_error("cuTensorMapEncodeTiled failed for layer %d", i);
-      return CB_ERR_CUDA;
-    }
+    P.w[i] = pl->d_w[i];
   }
   P.n_jobs = nj;
   pl->smem_bytes = g.smem;
@@ -847,7 +952,7 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
   if (in_map) { P.in_mode = IN_BF16_TMA; P.tmap_in = *in_map; }
   if (out_map) P.tmap_out = *out_map;
   P.num_tiles = (int)((rows + kTileM - 1) / kTileM);
-  const int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
+  const int grid = P.num_tiles < grid_cap() ? P.num_tiles : grid_cap();
   chain_kernel_for(plan->desc.act)<<<grid, kThreads, plan->smem_bytes, st>>>(P);
   CB_LAUNCH_CHECK();
   return CB_OK;
@@ -891,6 +996,7 @@ static bool final_geometry(int K, int Q, int* nkb_out, int* stages_out, size_t* 
   const long long fixed = 1024 + kCtrlBytes + (long long)ostage + 2ll * nkb * kKBlockBytes;
   long long stages = ((long long)kMaxSmem - fixed) / kKBlockBytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (const char* e = getenv("CB_TC_MAX_STAGES")) { const int c = atoi(e); if (c >= 2 && c < stages) stages = c; }  // experiment knob
   if (nkb_out) *nkb_out = nkb;
   if (stages_out) *stages_out = (int)stages;
   if (smem_out) *smem_out = (size_t)(fixed + (stages > 0 ? stages : 0) * kKBlockBytes);
@@ -903,7 +1009,7 @@ extern "C" int32_t cb_tc_multionet_supported(const cb_mlp_desc* branch, const cb
   if (nb < 2 || nt < 2) return 0;
   if (branch->dims[nb] != trunk->dims[nt] || branch->dims[nb - 1] != trunk->dims[nt - 1]) return 0;
   if (branch->act != trunk->act || branch->final_act != CB_ACT_IDENTITY || trunk->final_act != CB_ACT_IDENTITY) return 0;
-  if (branch->dims[nb] < Q) return 0;
+  if (branch->dims[nb] < Q || branch->dims[nb] > 32 * kMaxGroups - 32) return 0;
   cb_mlp_desc hb = *branch, ht = *trunk;
   hb.n_layers = nb - 1; ht.n_layers = nt - 1;
   if (!chain_geometry(&hb, OUT_BF16_TMA).ok || !chain_geometry(&ht, OUT_BF16_TMA).ok) return 0;
@@ -939,13 +1045,23 @@ extern "C" int32_t cb_tc_multionet_create(const cb_mlp_desc* branch, const cb_ml
   F.n_out = round_up(m->n_out, 16); F.n_jobs = (F.n_out + kChunkN - 1) / kChunkN;
   F.Q = Q; F.stages = stages;
   F.seg_base = m->n_out / Q; F.seg_rem = m->n_out % Q;
+  {
+    // split containing the first column of every 32-column group (padding columns map to Q)
+    int qi = 0, end = F.seg_base + (0 < F.seg_rem ? 1 : 0);
+    for (int g = 0; g * 32 < F.n_out; ++g) {
+      const int col = g * 32;
+      while (qi < Q && col >= end) { ++qi; end += F.seg_base + (qi < F.seg_rem ? 1 : 0); }
+      F.grp_q[g] = (int16_t)qi;
+      F.grp_end[g] = (int16_t)(qi < Q ? end : 32767);
+    }
+  }
   for (int i = 0; i < 2; ++i) {
-    if (cudaMalloc(&m->d_wlast[i], (size_t)m->rows_alloc * m->Kp * sizeof(__nv_bfloat16)) != cudaSuccess ||
-        !encode_bf16_map(&F.tmap_w[i], m->d_wlast[i], m->rows_alloc, m->Kp)) {
+    if (cudaMalloc(&m->d_wlast[i], (size_t)m->rows_alloc * m->Kp * sizeof(__nv_bfloat16)) != cudaSuccess) {
       cb_tc_multionet_destroy(m);
-      set_error("allocation / tensor map of the last-layer weights failed");
+      set_error("allocation of the last-layer weights failed");
       return CB_ERR_CUDA;
     }
+    F.w[i] = m->d_wlast[i];
   }
   if (cudaFuncSetAttribute(don_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_final) !=
       cudaSuccess) {
@@ -1043,7 +1159,7 @@ static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_
   F.tmap_in[0] = hmap[0]; F.tmap_in[1] = hmap[1];
   F.y = d_y; F.rows = rows;
   F.num_tiles = (int)((rows + kTileM - 1) / kTileM);
-  const int grid = F.num_tiles < num_sms() ? F.num_tiles : num_sms();
+  const int grid = F.num_tiles < grid_cap() ? F.num_tiles : grid_cap();
   don_final_kernel<<<grid, kThreads, m->smem_final, st>>>(F);
   CB_LAUNCH_CHECK();
   if (ev) cudaEventRecord(ev[3], st);

@@ -1,0 +1,155 @@
+// Microbenchmark: cycles per tcgen05.mma (SS mode, bf16, M=128) for several N and smem layouts.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_rate umma_rate.cu && ./umma_rate
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred P1;\n\tW:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra D;\n\tbra W;\n\tD:\n\t}"
+               ::"r"(bar), "r"(parity) : "memory");
+}
+
+// mode 0: same A/B k-step every MMA; mode 1: walk 4 k-steps x nkb k-blocks (like the real kernels)
+__global__ void __launch_bounds__(128, 1) bench(int N, int n_mma, int mode, int nkb, long long* out) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_ptr)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // zero the operand area (finite values)
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(nkb * 16384 * 2 + 16384 * 2) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(raw + (base - smem_u32(raw)))[i] = 0x3c003c00u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_ptr;
+  if (threadIdx.x == 0) {
+    const uint32_t A = base, B = base + nkb * 16384;
+    const uint32_t idesc = make_idesc(N);
+    long long t0 = clock64();
+    for (int i = 0; i < n_mma; ++i) {
+      uint32_t ao = 0, bo = 0;
+      if (mode == 1) { const int ks = i & 3, kb = (i >> 2) % nkb; ao = kb * 16384 + ks * 32; bo = (N > 128 ? kb * 32768 : kb * 16384) + ks * 32; }
+      umma(tmem, make_desc(A + ao), make_desc(B + bo), idesc, i > 0);
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    long long t1 = clock64();
+    mbar_wait(smem_u32(&bar), 0);
+    long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xFFFFFFFF;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void umma_acc(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");
+}
+// warp-converged issue loop, elect.sync around the MMAs, 4 k-steps unrolled per k-block
+__global__ void __launch_bounds__(128, 1) bench2(int N, int n_kb_iters, int nkb, long long* out) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_ptr)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(nkb * 16384 * 2 + 16384 * 2) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(raw + (base - smem_u32(raw)))[i] = 0x3c003c00u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_ptr;
+  if (warp == 1) {
+    const uint32_t A = base, B = base + nkb * 16384;
+    const uint32_t idesc = make_idesc(N);
+    long long t0 = clock64();
+    int kb = 0;
+    for (int i = 0; i < n_kb_iters; ++i) {
+      const uint64_t ad = make_desc(A + kb * 16384);
+      const uint64_t bd = make_desc(B + kb * (N > 128 ? 32768 : 16384));
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_acc(tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc);
+      }
+      __syncwarp();
+      if (++kb == nkb) kb = 0;
+    }
+    if (elect_one())
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    __syncwarp();
+    long long t1 = clock64();
+    mbar_wait(smem_u32(&bar), 0);
+    long long t2 = clock64();
+    if ((threadIdx.x & 31) == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+int main() {
+  long long* d; cudaMalloc(&d, 16);
+  cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int n_mma = 512;
+  for (int mode = 0; mode < 2; ++mode)
+    for (int N : {32, 64, 128, 256}) {
+      const int nkb = 3;
+      for (int rep = 0; rep < 2; ++rep) bench<<<1, 128, 200 * 1024>>>(N, n_mma, mode, nkb, d);
+      long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+      cudaError_t e = cudaGetLastError();
+      printf("mode %d N=%3d: issue %.1f cyc/mma, complete %.1f cyc/mma (ideal %d)  %s\n", mode, N, (double)h[0] / n_mma,
+             (double)h[1] / n_mma, 128 * N / 256, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    }
+  cudaFuncSetAttribute(bench2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  for (int N : {32, 64, 128, 256}) {
+    for (int rep = 0; rep < 2; ++rep) bench2<<<1, 128, 200 * 1024>>>(N, n_mma / 4, 3, d);
+    long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaGetLastError();
+    printf("elect N=%3d: issue %.1f cyc/mma, complete %.1f cyc/mma (ideal %d) %s\n", N, (double)h[0] / n_mma,
+           (double)h[1] / n_mma, 128 * N / 256, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  }
+  // all SMs busy: does the rate change under chip-wide load?
+  for (int N : {128, 256}) {
+    bench<<<148, 128, 200 * 1024>>>(N, n_mma, 1, 3, d);
+    bench<<<148, 128, 200 * 1024>>>(N, n_mma, 1, 3, d);
+    long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("148 CTAs N=%3d: complete %.1f cyc/mma\n", N, (double)h[1] / n_mma);
+  }
+  return 0;
+}
