@@ -74,6 +74,7 @@ struct ChainParams {
   float* y;
   long long rows;
   int num_tiles;
+  unsigned long long* trace;   // debug timeline (CB_TC_TRACE), NULL in production
 };
 
 struct FinalParams {
@@ -210,6 +211,30 @@ __device__ __forceinline__ int ld_volatile_shared(const int* p) {
   asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
   return v;
 }
+__device__ __forceinline__ void red_release_inc(int* p) {
+  asm volatile("red.release.cta.shared.add.s32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
+}
+// spin until the shared counter reaches `need`; `seen` caches the last observed value so that an
+// already satisfied dependency costs no memory operation at all
+__device__ __forceinline__ void wait_counter(const int* p, int need, int& seen) {
+  if (seen >= need) return;
+  int v;
+  do {
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  } while (v < need);
+  seen = v;
+}
+// non-blocking probe of an mbarrier phase (result consumed later: lets the probe's latency overlap)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
 // byte offset of the 16-byte chunk holding columns [8*col8, 8*col8+8) of row r inside an activation buffer
 __device__ __forceinline__ uint32_t act_chunk_off(int r, int col8) {
   const int kb = col8 >> 3, kg = col8 & 7;
@@ -260,6 +285,18 @@ __device__ __forceinline__ void epi_hidden(const uint32_t (&v)[32], int w, int n
   if (ones_col >= nb && ones_col < nb + w)
     st_shared_u16(xo + act_chunk_off(r, ones_col >> 3) + (uint32_t)((ones_col & 7) * 2), (uint16_t)0x3F80);  // bf16(1.0)
 }
+
+// debug timeline: role-private ring of (clock << 24 | tag << 16 | arg) words, CTA 0 only
+#ifndef CB_TC_ENABLE_TRACE
+#define CB_TRACE(role, tag, arg) do { (void)tn; } while (0)
+#else
+#define CB_TRACE(role, tag, arg)                                                                   \
+  do {                                                                                             \
+    if (P.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tn < 8190)                        \
+      P.trace[(role) * 8192 + tn++] = ((unsigned long long)clock64() << 24) |                      \
+                                      ((unsigned long long)(tag) << 16) | (unsigned)((arg) & 0xffff); \
+  } while (0)
+#endif
 
 struct Ctrl {
   uint32_t bar_full, bar_empty, bar_tfull, bar_tempty, bar_in;
@@ -334,11 +371,12 @@ chain_kernel(const __grid_constant__ ChainParams P) {
     // ============================================================ TMA producer (warp-converged, one elected lane issues)
     {
       int stage = 0; uint32_t phase = 0;
+      int tn = 0;
+      int seen_epi = 0;
       for (int it = 0; it < n_my_tiles; ++it) {
         if (P.in_mode == IN_BF16_TMA) {
           // X0 may be refilled once every MMA/epilogue of the previous tile has retired
-          while (ld_volatile_shared(C.epi_done) < it * P.n_jobs) { }
-          __threadfence_block();
+          wait_counter(C.epi_done, it * P.n_jobs, seen_epi);
           const int tile = (int)blockIdx.x + it * (int)gridDim.x;
           if (elect_one()) {
             mbar_arrive_expect_tx(C.bar_in, (uint32_t)P.nkb[0] * kKBlockBytes);
@@ -353,6 +391,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           const __nv_bfloat16* src = P.w[job.layer] + (size_t)(job.n0 / kChunkN) * nkb * (kKBlockBytes / 2);
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(C.bar_empty + 8 * stage, phase ^ 1);
+            CB_TRACE(0, 1, j * 8 + kb);
             if (elect_one()) {
               mbar_arrive_expect_tx(C.bar_full + 8 * stage, kKBlockBytes);
               bulk_load(ST0 + stage * kKBlockBytes, src + (size_t)kb * (kKBlockBytes / 2), kKBlockBytes,
@@ -369,6 +408,9 @@ chain_kernel(const __grid_constant__ ChainParams P) {
     {
       int stage = 0; uint32_t phase = 0;
       int gj = 0;
+      int tn = 0;
+      int seen_in = 0, seen_epi = 0;
+      const uint64_t bdesc0 = make_smem_desc(ST0);
       for (int it = 0; it < n_my_tiles; ++it) {
         for (int j = 0; j < P.n_jobs; ++j, ++gj) {
           const Job job = P.jobs[j];
@@ -376,29 +418,35 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           const int slot = gj & (kSlots - 1);
           const uint32_t use = (uint32_t)(gj / kSlots);
           mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
+          CB_TRACE(1, 2, j);
           tcgen05_fence_after();
-          const uint32_t xa = (l & 1) ? X1 : X0;
           const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
           const uint32_t idesc = make_idesc(job.ncols);
-          const int nkb = P.nkb[l], ksteps = P.ksteps[l];
+          const int nkb = P.nkb[l];
+          const int last_nks = P.ksteps[l] - (nkb - 1) * 4;
+          const uint64_t adesc0 = make_smem_desc((l & 1) ? X1 : X0);
+          // dependency bookkeeping: k-block kb of this layer's input was written by chunk kb/2 of the
+          // previous layer (or by the input staging / input TMA for layer 0)
+          int need0 = 0, last_pc = 0;
+          if (l == 0) {
+            if (P.in_mode == IN_BF16_TMA) mbar_wait(C.bar_in, it & 1);
+            else wait_counter(C.in_staged, it + 1, seen_in);
+          } else {
+            need0 = it * P.n_jobs + P.first_job[l - 1] + 1;
+            last_pc = P.n_chunks[l - 1] - 1;
+          }
           for (int kb = 0; kb < nkb; ++kb) {
-            // activation k-block kb must have been written by its producer
-            if (l == 0) {
-              if (P.in_mode == IN_BF16_TMA) { if (kb == 0) mbar_wait(C.bar_in, it & 1); }
-              else while (ld_volatile_shared(C.in_staged) < it + 1) { }
-            } else {
-              const int pc = min(kb >> 1, P.n_chunks[l - 1] - 1);
-              const int need = it * P.n_jobs + P.first_job[l - 1] + pc + 1;
-              while (ld_volatile_shared(C.epi_done) < need) { }
-            }
-            __threadfence_block();
+            if (l != 0) wait_counter(C.epi_done, need0 + min(kb >> 1, last_pc), seen_epi);
+            CB_TRACE(1, 3, j * 8 + kb);
             mbar_wait(C.bar_full + 8 * stage, phase);
+            CB_TRACE(1, 4, j * 8 + kb);
             tcgen05_fence_after();
-            const int nks = min(4, ksteps - kb * 4);
-            const uint64_t adesc = make_smem_desc(xa + kb * kKBlockBytes);
-            const uint64_t bdesc = make_smem_desc(ST0 + stage * kKBlockBytes);
+            const int nks = (kb == nkb - 1) ? last_nks : 4;
+            // descriptor start-address field counts 16-byte units: +1024 per 16 KiB k-block / stage,
+            // +2 per 16-column k-step
+            const uint64_t adesc = adesc0 + (uint64_t)(kb * (kKBlockBytes >> 4));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kKBlockBytes >> 4));
             if (elect_one()) {
-              // +2 in the descriptor's start-address field = +32 bytes = one 16-column k-step
               umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
 #pragma unroll
               for (int ks = 1; ks < 4; ++ks)
@@ -421,6 +469,8 @@ chain_kernel(const __grid_constant__ ChainParams P) {
     const int et = threadIdx.x - 64;        // 0..255
     const int K0 = P.K[0];
     int gj = 0;
+    int tn = 0;
+    const int trole = (warp == 2) ? 2 : (warp == 6 ? 3 : 4);
     for (int it = 0; it < n_my_tiles; ++it) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const long long row_g = (long long)tile * kTileM + r;
@@ -441,7 +491,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         }
         fence_proxy_async();
         epi_bar_sync();
-        if (et == 0) { __threadfence_block(); atomicAdd(C.in_staged, 1); }
+        if (et == 0) red_release_inc(C.in_staged);
       }
       for (int j = 0; j < P.n_jobs; ++j, ++gj) {
         const Job job = P.jobs[j];
@@ -450,7 +500,9 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         const bool to_smem = !last || P.out_mode == OUT_BF16_TMA;
         const int slot = gj & (kSlots - 1);
         const uint32_t use = (uint32_t)(gj / kSlots);
+        if (trole < 4) CB_TRACE(trole, 5, j);
         mbar_wait(C.bar_tfull + 8 * slot, use & 1);
+        if (trole < 4) CB_TRACE(trole, 6, j);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * kChunkN;
         const uint32_t xo = ((l + 1) & 1) ? X1 : X0;
@@ -483,6 +535,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         }
         tcgen05_fence_before();
         mbar_arrive(C.bar_tempty + 8 * slot);
+        if (trole < 4) CB_TRACE(trole, 7, j);
         if (to_smem) {
           if (h == 0 && job.last_chunk && (N & 15) == 0) {
             // ones column starts a fresh 16-column k-step: write [1,0,...,0] (32 bytes)
@@ -490,7 +543,9 @@ chain_kernel(const __grid_constant__ ChainParams P) {
             st_shared_v4(xo + act_chunk_off(r, (N >> 3) + 1), 0u, 0u, 0u, 0u);
           }
           fence_proxy_async();                     // generic-proxy smem writes -> visible to tcgen05.mma / TMA
+          if (trole < 4) CB_TRACE(trole, 8, j);
           epi_bar_sync();
+          if (trole < 4) CB_TRACE(trole, 9, j);
           if (last && job.last_chunk) {
             // OUT_BF16_TMA: the finished activation tile leaves through TMA stores (rows >= M are clipped)
             if (et == 0) {
@@ -515,7 +570,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           }
           epi_bar_sync();
         }
-        if (et == 0) { __threadfence_block(); atomicAdd(C.epi_done, 1); }
+        if (et == 0) red_release_inc(C.epi_done);
       }
     }
   }
@@ -544,9 +599,9 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
   if (warp == 0) {
     // TMA producer: warp-converged, one elected lane issues
     int stage = 0; uint32_t phase = 0;
+    int seen_epi = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
-      while (ld_volatile_shared(C.epi_done) < it) { }      // previous tile fully consumed
-      __threadfence_block();
+      wait_counter(C.epi_done, it, seen_epi);              // previous tile fully consumed
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       if (elect_one()) {
         mbar_arrive_expect_tx(C.bar_in, 2u * P.nkb * kKBlockBytes);
@@ -576,6 +631,9 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
     // MMA issuer: warp-converged control flow, one elected lane issues
     int stage = 0; uint32_t phase = 0;
     int gs = 0;   // global slot-use counter (2 per job)
+    const int nkb = P.nkb;
+    const int last_nks = P.ksteps - (nkb - 1) * 4;
+    const uint64_t bdesc0 = make_smem_desc(ST0);
     for (int it = 0; it < n_my_tiles; ++it) {
       mbar_wait(C.bar_in, it & 1);
       tcgen05_fence_after();
@@ -587,14 +645,14 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
           const uint32_t use = (uint32_t)(gs / kSlots);
           mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
           tcgen05_fence_after();
-          const uint32_t xa = net ? XT : XB;
+          const uint64_t adesc0 = make_smem_desc(net ? XT : XB);
           const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
-          for (int kb = 0; kb < P.nkb; ++kb) {
+          for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(C.bar_full + 8 * stage, phase);
             tcgen05_fence_after();
-            const int nks = min(4, P.ksteps - kb * 4);
-            const uint64_t adesc = make_smem_desc(xa + kb * kKBlockBytes);
-            const uint64_t bdesc = make_smem_desc(ST0 + stage * kKBlockBytes);
+            const int nks = (kb == nkb - 1) ? last_nks : 4;
+            const uint64_t adesc = adesc0 + (uint64_t)(kb * (kKBlockBytes >> 4));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kKBlockBytes >> 4));
             if (elect_one()) {
               umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
 #pragma unroll
@@ -710,7 +768,7 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
         }
       }
       epi_bar_sync();
-      if (et == 0) { __threadfence_block(); atomicAdd(C.epi_done, 1); }
+      if (et == 0) red_release_inc(C.epi_done);
     }
   }
   teardown_cta(tmem_base, warp);
@@ -953,8 +1011,21 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
   if (out_map) P.tmap_out = *out_map;
   P.num_tiles = (int)((rows + kTileM - 1) / kTileM);
   const int grid = P.num_tiles < grid_cap() ? P.num_tiles : grid_cap();
+  const char* trace_path = getenv("CB_TC_TRACE");   // debug only: dump a per-role timeline of CTA 0
+  P.trace = nullptr;
+  if (trace_path) {
+    CB_CUDA(cudaMalloc(&P.trace, 4 * 8192 * sizeof(unsigned long long)));
+    CB_CUDA(cudaMemsetAsync(P.trace, 0, 4 * 8192 * sizeof(unsigned long long), st));
+  }
   chain_kernel_for(plan->desc.act)<<<grid, kThreads, plan->smem_bytes, st>>>(P);
   CB_LAUNCH_CHECK();
+  if (trace_path) {
+    static unsigned long long host[4 * 8192];
+    CB_CUDA(cudaStreamSynchronize(st));
+    CB_CUDA(cudaMemcpy(host, P.trace, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(P.trace);
+    if (FILE* f = fopen(trace_path, "wb")) { fwrite(host, 1, sizeof(host), f); fclose(f); }
+  }
   return CB_OK;
 }
 

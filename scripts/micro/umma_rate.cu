@@ -74,14 +74,17 @@ __device__ __forceinline__ void umma_acc(uint32_t d, uint64_t a, uint64_t b, uin
                ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");
 }
 // warp-converged issue loop, elect.sync around the MMAs, 4 k-steps unrolled per k-block
-__global__ void __launch_bounds__(128, 1) bench2(int N, int n_kb_iters, int nkb, long long* out) {
+__global__ void __launch_bounds__(128, 1) bench2(int N, int n_kb_iters, int nkb, long long* out, int flags = 0) {
   extern __shared__ uint8_t raw[];
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2, bar3;
   __shared__ uint32_t tmem_ptr;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar3)));
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar3)) : "memory");  // phase 0 complete
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -101,11 +104,15 @@ __global__ void __launch_bounds__(128, 1) bench2(int N, int n_kb_iters, int nkb,
     long long t0 = clock64();
     int kb = 0;
     for (int i = 0; i < n_kb_iters; ++i) {
+      if (flags & 4) mbar_wait(smem_u32(&bar3), 0);   // already-complete barrier
+      if (flags & 2) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint64_t ad = make_desc(A + kb * 16384);
       const uint64_t bd = make_desc(B + kb * (N > 128 ? 32768 : 16384));
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) umma_acc(tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc);
+        if (flags & 1)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
       }
       __syncwarp();
       if (++kb == nkb) kb = 0;
@@ -144,6 +151,12 @@ int main() {
     printf("elect N=%3d: issue %.1f cyc/mma, complete %.1f cyc/mma (ideal %d) %s\n", N, (double)h[0] / n_mma,
            (double)h[1] / n_mma, 128 * N / 256, e == cudaSuccess ? "" : cudaGetErrorString(e));
   }
+  for (int flags : {0, 1, 2, 4, 7})
+    for (int N : {32, 128}) {
+      for (int rep = 0; rep < 2; ++rep) bench2<<<1, 128, 200 * 1024>>>(N, n_mma / 4, 3, d, flags);
+      long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+      printf("flags=%d (1 commit,2 fence,4 wait) N=%3d: %.1f cyc per k-block (4 MMAs)\n", flags, N, (double)h[1] / (n_mma / 4));
+    }
   // all SMs busy: does the rate change under chip-wide load?
   for (int N : {128, 256}) {
     bench<<<148, 128, 200 * 1024>>>(N, n_mma, 1, 3, d);
