@@ -308,9 +308,13 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         sample_rows = ROWS_PER_STEP
         reps = 40
-        rate, dt = cpu_forward_rate(sample_rows, reps, cores)
-        cpu_baseline = {"value": rate, "unit": "trajectories/s", "cores": cores, "kind": "port",
-                        "sample": f"{reps} x {sample_rows} rows ({dt:.1f} s) of the same cfg2 forward, torch-CPU fp32 port of the reference forward"}
+        if args.no_cpu_baseline:
+            cpu_baseline = None
+        else:
+            rate, dt = cpu_forward_rate(sample_rows, reps, cores)
+            cpu_baseline = {"value": rate, "unit": "trajectories/s", "cores": cores, "kind": "port",
+                            "sample": f"{reps} x {sample_rows} rows ({dt:.1f} s) of the same cfg2 forward, "
+                                      "torch-CPU fp32 port of the reference forward"}
         line = {
             "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -332,6 +336,8 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true",
+                    help="skip the host-side cpu_baseline leg (profiling runs under ncu only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

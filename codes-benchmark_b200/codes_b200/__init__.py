@@ -17,6 +17,7 @@ from .latent_neural_ode import ODE, LatentNeuralODE, ModelWrapper
 from .latent_poly import LatentPoly, Polynomial, PolynomialModelWrapper
 from .loaders import RowBatchIterable
 from .ops import precision_mode, set_precision
+from . import parallel, train  # noqa: E402,F401  (host-side sharding / task orchestration)
 
 surrogate_classes = [MultiONet, FullyConnected, LatentNeuralODE, LatentPoly]
 

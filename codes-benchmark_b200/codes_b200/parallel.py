@@ -1,0 +1,82 @@
+"""One-process-per-GPU sharding of test-set inference.
+
+Trajectories are independent, so every rank runs ``model.predict`` on a contiguous block of the
+test set (loader order is preserved) and the blocks -- or only the reduced error tensors -- are
+exchanged once: ``all_gather`` / ``all_reduce`` over NCCL (NVLink 5 / NVSwitch) on GPUs, gloo in the
+CPU tests.  The reference evaluates on ``devices[0]`` only (bench_fcts.py:67-68); there is no
+collective on the training path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Contiguous block [lo, hi) of ``n`` items owned by ``rank`` (sizes differ by at most one)."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _world(group=None) -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def sharded_predict(model, dataset: np.ndarray, timesteps: np.ndarray, batch_size: int, leave_log: bool = False,
+                    leave_norm: bool = False, gather: bool = True, group=None):
+    """predict() of ``dataset`` (N,T,Q) split by trajectory over the ranks of ``group``.
+
+    Returns (predictions, targets): the full (N,T,Q) tensors on every rank when ``gather`` is
+    True (one all_gather of the padded blocks), else this rank's block and its [lo, hi) bounds.
+    """
+    rank, world = _world(group)
+    n = dataset.shape[0]
+    lo, hi = shard_bounds(n, rank, world)
+    block = max(hi - lo, 0)
+    if block > 0:
+        _, _, loader = model.prepare_data(dataset[lo:hi], None, dataset[lo:hi], timesteps, batch_size, shuffle=False)
+        preds, targs = model.predict(loader, leave_log=leave_log, leave_norm=leave_norm)
+    else:  # more ranks than trajectories
+        t, q = dataset.shape[1], dataset.shape[2]
+        dev = model.device if (model.device and "cuda" in str(model.device)) else "cpu"
+        preds = torch.empty((0, t, q), dtype=torch.float32, device=dev)
+        targs = torch.empty((0, t, q), dtype=torch.float32, device=dev)
+    if not gather or world == 1:
+        return (preds, targs) if gather else (preds, targs, (lo, hi))
+    cap = (n + world - 1) // world                         # padded block length
+    out = []
+    for x in (preds, targs):
+        pad = torch.zeros((cap, *x.shape[1:]), dtype=x.dtype, device=x.device)
+        pad[:block] = x
+        full = torch.empty((world * cap, *x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(full, pad, group=group)
+        pieces = [full[r * cap:r * cap + (shard_bounds(n, r, world)[1] - shard_bounds(n, r, world)[0])]
+                  for r in range(world)]
+        out.append(torch.cat(pieces, dim=0))
+    return out[0], out[1]
+
+
+def sharded_error_metrics(preds: torch.Tensor, targs: torch.Tensor, group=None) -> dict:
+    """Global error metrics from per-rank blocks with ONE all_reduce of a small tensor
+    (sum |e|, sum e^2, sum |e|/|t|, count): the metric math of bench_fcts.py:243-271 without moving
+    the (N,T,Q) predictions off the rank that produced them."""
+    err = (preds - targs).double()
+    stats = torch.stack([err.abs().sum(), (err * err).sum(),
+                         (err.abs() / targs.double().abs().clamp_min(1e-300)).sum(),
+                         torch.tensor(float(err.numel()), dtype=torch.float64, device=err.device)])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    s_abs, s_sq, s_rel, cnt = (float(v) for v in stats.cpu())
+    cnt = max(cnt, 1.0)
+    return {"MAE": s_abs / cnt, "RMSE": (s_sq / cnt) ** 0.5, "MRE": s_rel / cnt, "count": int(cnt)}
+
+
+def ensemble_mean_std(member_preds: list[torch.Tensor]) -> tuple[torch.Tensor, torch.Tensor]:
+    """DeepEnsemble statistics on device: mean and std(ddof=1) over members
+    (bench_fcts.py:1061-1074 does this in numpy on the host)."""
+    stack = torch.stack(member_preds, dim=0)
+    return stack.mean(dim=0), stack.std(dim=0, unbiased=True)
