@@ -273,7 +273,8 @@ def run_ours(args):
         roofline = {
             "bound": "tensor", "kernel": "don_final_kernel (both last Linears 275->2842 + split scalar product)",
             "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-            "traffic": None, "peak_source": peak_src,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full`, profiles/r1_tc_kernels_ncu_full.md
+            "traffic": 92423168, "traffic_unit": "bytes/launch (ncu r1)", "peak_source": peak_src,
             "kernel_ms": {"branch_chain": float(ph[0]), "trunk_chain": float(ph[1]), "final": final_ms},
             "flops_per_launch": FLOP_PER_ROW_FINAL * ROWS_PER_STEP,
             "step_achieved": step_tf, "step_frac": step_tf / peak_tf,
@@ -285,8 +286,9 @@ def run_ours(args):
         _, _, val_loader = model.prepare_data(de, None, de, np.linspace(0, 1, T), ROWS_PER_STEP, shuffle=False)
         steps_per_pass = len(val_loader)
         passes = max(1, int(round(args.steps / steps_per_pass)))
-        p, t = model.predict(val_loader)          # warm-up pass
-        model._l1(p, t)
+        for _ in range(3):                        # warm-up passes (allocator pools, copy stream)
+            p, t = model.predict(val_loader)
+            model._l1(p, t)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(passes):

@@ -147,7 +147,10 @@ class AbstractSurrogateModel(ABC, nn.Module):
             yield from data_loader
             return
         device = torch.device(dev)
-        copy_stream = torch.cuda.Stream(device)
+        copy_stream = self.__dict__.get("_copy_stream")
+        if copy_stream is None or copy_stream.device != device:
+            copy_stream = self.__dict__["_copy_stream"] = torch.cuda.Stream(device)
+        copy_stream.wait_stream(torch.cuda.current_stream(device))
         pending = None
         for batch in data_loader:
             with torch.cuda.stream(copy_stream):

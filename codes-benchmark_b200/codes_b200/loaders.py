@@ -64,5 +64,7 @@ class RowBatchIterable(IterableDataset):
 def make_loader(dataset: IterableDataset, device: str | None, num_workers: int = 0) -> DataLoader:
     """``DataLoader(batch_size=None)``: the dataset already yields whole batches."""
     pin = device is not None and "cuda" in str(device) and torch.cuda.is_available()
+    if getattr(dataset, "pin", False) and not getattr(dataset, "shuffle", True):
+        pin = False   # base tensors are pinned once and batches are slices of them: no per-batch pin thread
     return DataLoader(dataset, batch_size=None, num_workers=num_workers, pin_memory=pin,
                       persistent_workers=False)
