@@ -40,6 +40,11 @@ class LnodeDesc(C.Structure):
     ]
 
 
+class LnodeTape(C.Structure):
+    _fields_ = [("d_n", C.c_void_p), ("d_t", C.c_void_p), ("d_dt", C.c_void_p), ("d_y", C.c_void_p),
+                ("d_k", C.c_void_p), ("cap", C.c_int32)]
+
+
 _LIB = None
 _LOCK = threading.Lock()
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libcodes_b200.so")
@@ -70,7 +75,11 @@ _SIGNATURES = {
     "cb_lerp_tensors": (_I32, [_PP, _PP, C.POINTER(_I64), _I32, _F, _P]),
     "cb_denormalize": (_I32, [_P, _I64, _I32, _I32, _P, _P, _I32, _P, _P]),
     "cb_lnode_workspace_floats": (_I64, [C.POINTER(LnodeDesc)]),
-    "cb_lnode_solve_fwd": (_I32, [C.POINTER(LnodeDesc), _PP, _PP, _P, _P, _I64, _I32, _P, _P, _P, _I64, _P]),
+    "cb_lnode_solve_fwd": (_I32, [C.POINTER(LnodeDesc), _PP, _PP, _P, _P, _I64, _I32, _P, _P, _P, _I64,
+                                  C.POINTER(LnodeTape), _P]),
+    "cb_lnode_bwd_workspace_floats": (_I64, [C.POINTER(LnodeDesc), _I64]),
+    "cb_lnode_solve_bwd": (_I32, [C.POINTER(LnodeDesc), _PP, _PP, _P, _I64, _I32, C.POINTER(LnodeTape), _P, _P, _PP,
+                                  _PP, _P, _P, _I64, _P]),
     "cb_tc_supported": (_I32, []),
     "cb_tc_chain_supported": (_I32, [C.POINTER(MlpDesc)]),
     "cb_tc_chain_create": (_I32, [C.POINTER(MlpDesc), _I32, C.POINTER(_P)]),

@@ -321,18 +321,27 @@ def denormalize(x: Tensor, mode: int, dmin: Tensor | None, dmax: Tensor | None, 
 
 
 # --------------------------------------------------------------------------- latent ODE solve
-def lnode_solve(spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor, tanh_reg: bool, reg_factor: float,
-                rtol: float, atol: float, max_steps: int = 100000, return_stats: bool = False):
-    """Adaptive Tsit5 solve of dz/dt = ODE-net(z); z0:(B,L) -> (B,T,L) fp32."""
-    _require_cuda(z0, t_eval)
-    z0c, tc = _f32c(z0), _f32c(t_eval)
-    B, Lat = z0c.shape
-    T = tc.shape[0]
+TAPE_CAP = 96   # accepted steps recorded per trajectory for the backward sweep
+
+
+def _lnode_desc(spec: ChainSpec, tanh_reg: bool, reg_factor: float, rtol: float, atol: float, max_steps: int):
     d = _lib.LnodeDesc()
     d.ode = spec.desc
     d.tanh_reg = int(bool(tanh_reg))
     d.reg_factor = float(reg_factor)
     d.rtol, d.atol, d.max_steps = float(rtol), float(atol), int(max_steps)
+    return d
+
+
+def lnode_solve(spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor, tanh_reg: bool, reg_factor: float,
+                rtol: float, atol: float, max_steps: int = 100000, return_stats: bool = False, record_tape: bool = False):
+    """Adaptive Tsit5 solve of dz/dt = ODE-net(z); z0:(B,L) -> (B,T,L) fp32.
+    ``record_tape`` additionally returns the accepted-step record the backward sweep consumes."""
+    _require_cuda(z0, t_eval)
+    z0c, tc = _f32c(z0), _f32c(t_eval)
+    B, Lat = z0c.shape
+    T = tc.shape[0]
+    d = _lnode_desc(spec, tanh_reg, reg_factor, rtol, atol, max_steps)
     dev = z0c.device
     out = torch.empty((B, T, Lat), device=dev, dtype=torch.float32)
     stats = torch.empty((B, 2), device=dev, dtype=torch.int32)
@@ -343,10 +352,47 @@ def lnode_solve(spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor, ta
     ws = torch.empty(wsf, device=dev, dtype=torch.float32)
     wl = [_f32c(w.detach()) for w in weights]
     bl = [_f32c(b.detach()) for b in biases]
+    tape = tape_bufs = None
+    if record_tape:
+        cap = TAPE_CAP
+        tape_bufs = (torch.empty(B, device=dev, dtype=torch.int32),
+                     torch.empty((B, cap), device=dev, dtype=torch.float64),
+                     torch.empty((B, cap), device=dev, dtype=torch.float64),
+                     torch.empty((B, cap, Lat), device=dev, dtype=torch.float64),
+                     torch.empty((B, cap, 7, Lat), device=dev, dtype=torch.float32))
+        tape = _lib.LnodeTape(*[t.data_ptr() for t in tape_bufs], cap)
     with torch.cuda.device(dev):
         check(L.cb_lnode_solve_fwd(C.byref(d), ptr_array(wl), ptr_array(bl), _p(z0c), _p(tc), B, T, _p(out),
-                                   _p(stats), _p(ws), wsf, _stream(z0c)), "lnode_solve_fwd")
-    return (out, stats) if return_stats else out
+                                   _p(stats), _p(ws), wsf, C.byref(tape) if tape is not None else None,
+                                   _stream(z0c)), "lnode_solve_fwd")
+    res = (out, stats) if return_stats else (out,)
+    if record_tape:
+        res = res + (tape_bufs,)
+    return res if len(res) > 1 else res[0]
+
+
+def lnode_solve_backward(spec: ChainSpec, weights, biases, t_eval: Tensor, tape_bufs, g: Tensor, tanh_reg: bool,
+                         reg_factor: float, rtol: float, atol: float):
+    """Discrete-adjoint backward of ``lnode_solve``: returns (dz0, dW list, db list, dreg)."""
+    g = _f32c(g)
+    B, T, Lat = g.shape
+    dev = g.device
+    d = _lnode_desc(spec, tanh_reg, reg_factor, rtol, atol, 1)
+    L = lib()
+    wl = [_f32c(w.detach()) for w in weights]
+    bl = [_f32c(b.detach()) for b in biases]
+    dz0 = torch.empty((B, Lat), device=dev, dtype=torch.float32)
+    dW = [torch.empty_like(w) for w in wl]
+    db = [torch.empty_like(b) for b in bl]
+    dreg = torch.zeros((), device=dev, dtype=torch.float32)
+    wsf = int(L.cb_lnode_bwd_workspace_floats(C.byref(d), B))
+    ws = torch.empty(wsf, device=dev, dtype=torch.float32)
+    tape = _lib.LnodeTape(*[t.data_ptr() for t in tape_bufs], tape_bufs[1].shape[1])
+    with torch.cuda.device(dev):
+        check(L.cb_lnode_solve_bwd(C.byref(d), ptr_array(wl), ptr_array(bl), _p(_f32c(t_eval)), B, T, C.byref(tape),
+                                   _p(g), _p(dz0), ptr_array(dW), ptr_array(db), _p(dreg), _p(ws), wsf,
+                                   _stream(g)), "lnode_solve_bwd")
+    return dz0, dW, db, dreg
 
 
 # --------------------------------------------------------------------------- precision dispatch
@@ -403,17 +449,29 @@ class _LnodeSolveFn(torch.autograd.Function):
         n = spec.n_layers
         weights, biases = params[:n], params[n:]
         cfg = wrapper.config
-        out, stats = lnode_solve(spec, weights, biases, z0.detach(), t_eval, cfg.ode_tanh_reg,
-                                 float(reg_factor.detach()) if cfg.ode_tanh_reg else 1.0,
-                                 cfg.rtol, cfg.atol, return_stats=True)
+        reg = float(reg_factor.detach()) if cfg.ode_tanh_reg else 1.0
+        need_grad = any(ctx.needs_input_grad)
+        res = lnode_solve(spec, weights, biases, z0.detach(), t_eval, cfg.ode_tanh_reg, reg, cfg.rtol, cfg.atol,
+                          return_stats=True, record_tape=need_grad)
+        out, stats = res[0], res[1]
         wrapper.last_solver_stats = stats
+        if need_grad:
+            tape = res[2]
+            ctx.spec, ctx.cfg, ctx.reg, ctx.n = spec, cfg, reg, n
+            ctx.save_for_backward(t_eval, *tape, *[p.detach() for p in params])
         return out
 
     @staticmethod
     def backward(ctx, dz: Tensor):
-        raise NotImplementedError(
-            "codes_b200: the backward sweep of the persistent latent-ODE integrator is not built yet "
-            "(LatentNeuralODE inference is supported; training lands next round)")
+        t_eval, *rest = ctx.saved_tensors
+        tape, params = rest[:5], rest[5:]
+        n, cfg = ctx.n, ctx.cfg
+        if int(tape[0].min()) < 0:
+            raise RuntimeError(f"latent ODE backward: a trajectory needed more than {TAPE_CAP} accepted steps "
+                               "(tape overflow) or did not finish")
+        dz0, dW, db, dreg = lnode_solve_backward(ctx.spec, params[:n], params[n:], t_eval, tape, dz,
+                                                 cfg.ode_tanh_reg, ctx.reg, cfg.rtol, cfg.atol)
+        return (None, None, dz0, None, dreg if cfg.ode_tanh_reg else None, *dW, *db)
 
 
 def lnode_integrate(wrapper, spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor) -> Tensor:

@@ -140,11 +140,21 @@ __device__ __forceinline__ void ode_rhs(const LnodeParams& P, const float* __res
   __syncthreads();
 }
 
+// accepted-step record for the backward sweep (all pointers NULL in inference)
+struct Tape {
+  int32_t* n;    // (batch)           accepted steps, -1 if `cap` was exceeded
+  double* t;     // (batch, cap)      step start time
+  double* dt;    // (batch, cap)      step size
+  double* y;     // (batch, cap, L)   state at the step start
+  float* k;      // (batch, cap, 7, L) stage derivatives (fp32-exact values)
+  int cap;
+};
+
 template <int TB>
 __global__ void lnode_solve_kernel(const LnodeParams P, const float* __restrict__ gW,
                                    const float* __restrict__ gB, const float* __restrict__ z0,
                                    const float* __restrict__ t_eval_f, int64_t batch,
-                                   float* __restrict__ z_out, int* __restrict__ stats) {
+                                   float* __restrict__ z_out, int* __restrict__ stats, const Tape tape) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int L = P.L, T = P.T;
   // ---- carve shared memory (doubles first)
@@ -291,6 +301,17 @@ __global__ void lnode_solve_kernel(const LnodeParams P, const float* __restrict_
           ++j;
         }
         snext[t] = j;
+        if (tape.n) {
+          const int sidx = snac[t] - 1;
+          if (sidx < tape.cap) {
+            const int64_t o = b * tape.cap + sidx;
+            tape.t[o] = tc;
+            tape.dt[o] = dt;
+            for (int l = 0; l < L; ++l) tape.y[o * L + l] = sy[l * TB + t];
+            for (int i = 0; i < 7; ++i)
+              for (int l = 0; l < L; ++l) tape.k[(o * 7 + i) * L + l] = kf[i * L * TB + l * TB + t];
+          }
+        }
         for (int l = 0; l < L; ++l) {
           sy[l * TB + t] = syn[l * TB + t];
           kf[l * TB + t] = kf[6 * L * TB + l * TB + t];  // FSAL
@@ -312,6 +333,7 @@ __global__ void lnode_solve_kernel(const LnodeParams P, const float* __restrict_
       stats[b * 2 + 0] = srun[tid] ? -snst[tid] : snst[tid];  // negative: max_steps exhausted
       stats[b * 2 + 1] = snac[tid];
     }
+    if (tape.n) tape.n[b] = (snac[tid] <= tape.cap && !srun[tid]) ? snac[tid] : -1;
   }
 }
 
@@ -337,29 +359,17 @@ extern "C" int64_t cb_lnode_workspace_floats(const cb_lnode_desc* desc) {
   return w + 64;
 }
 
-extern "C" int32_t cb_lnode_solve_fwd(const cb_lnode_desc* desc, const float* const* d_W,
-                                      const float* const* d_b, const float* d_z0,
-                                      const float* d_t_eval, int64_t batch, int32_t n_t,
-                                      float* d_z_out, int32_t* d_stats, float* d_ws,
-                                      int64_t ws_floats, void* stream) {
+static int32_t build_params(const cb_lnode_desc* desc, int32_t n_t, LnodeParams& P) {
   CB_CHECK_ARG(desc != nullptr, "cb_lnode_desc is NULL");
   if (int32_t e = check_desc(&desc->ode)) return e;
-  CB_CHECK_ARG(d_W && d_b && d_z0 && d_t_eval && d_z_out && d_ws, "NULL pointer argument");
   const cb_mlp_desc& m = desc->ode;
   CB_CHECK_ARG(m.dims[0] == m.dims[m.n_layers], "ODE net must map latent -> latent (%d vs %d)",
                m.dims[0], m.dims[m.n_layers]);
   CB_CHECK_ARG(m.final_act == CB_ACT_IDENTITY, "ODE net has no final activation");
-  CB_CHECK_ARG(batch >= 0 && n_t >= 2 && n_t <= 4096, "bad batch/n_t");
+  CB_CHECK_ARG(n_t >= 2 && n_t <= 4096, "bad n_t");
   CB_CHECK_ARG(desc->rtol > 0 && desc->atol > 0 && desc->max_steps > 0, "bad tolerances");
   CB_CHECK_ARG(!desc->tanh_reg || desc->reg_factor != 0.f, "reg_factor must be non-zero");
-  if (batch == 0) return CB_OK;
-  const int64_t need = cb_lnode_workspace_floats(desc);
-  if (ws_floats < need) {
-    set_error("workspace too small: %lld < %lld floats", (long long)ws_floats, (long long)need);
-    return CB_ERR_WORKSPACE;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  LnodeParams P{};
+  P = LnodeParams{};
   P.n_layers = m.n_layers;
   P.L = m.dims[0]; P.T = n_t;
   P.act = m.act; P.act_param = m.act_param;
@@ -377,29 +387,57 @@ extern "C" int32_t cb_lnode_solve_fwd(const cb_lnode_desc* desc, const float* co
   for (int i = 0; i < m.n_layers; ++i) { P.b_off[i] = boff; boff += P.Wp[i]; }
   P.total_b = boff;
   P.wmax_p = wmax;
-  float* gW = d_ws;
-  float* gB = d_ws + P.total_w;
-  for (int i = 0; i < m.n_layers; ++i) {
+  return CB_OK;
+}
+
+static int32_t pack_weights(const LnodeParams& P, const float* const* d_W, const float* const* d_b, float* gW,
+                            float* gB, cudaStream_t st) {
+  for (int i = 0; i < P.n_layers; ++i) {
     const int total = P.K[i] * P.Wp[i];
     lnode_pack_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_W[i], d_b[i], P.K[i], P.N[i], P.Wp[i],
                                                            gW + P.w_off[i], gB + P.b_off[i]);
     CB_LAUNCH_CHECK();
   }
+  return CB_OK;
+}
+
+extern "C" int32_t cb_lnode_solve_fwd(const cb_lnode_desc* desc, const float* const* d_W,
+                                      const float* const* d_b, const float* d_z0,
+                                      const float* d_t_eval, int64_t batch, int32_t n_t,
+                                      float* d_z_out, int32_t* d_stats, float* d_ws,
+                                      int64_t ws_floats, const cb_lnode_tape* tape, void* stream) {
+  LnodeParams P;
+  if (int32_t e = build_params(desc, n_t, P)) return e;
+  CB_CHECK_ARG(batch >= 0, "bad batch");
+  if (batch == 0) return CB_OK;
+  CB_CHECK_ARG(d_W && d_b && d_z0 && d_t_eval && d_z_out && d_ws, "NULL pointer argument");
+  const int64_t need = cb_lnode_workspace_floats(desc);
+  if (ws_floats < need) {
+    set_error("workspace too small: %lld < %lld floats", (long long)ws_floats, (long long)need);
+    return CB_ERR_WORKSPACE;
+  }
+  Tape tp{};
+  if (tape) {
+    CB_CHECK_ARG(tape->d_n && tape->d_t && tape->d_dt && tape->d_y && tape->d_k && tape->cap >= 1, "bad tape");
+    tp.n = tape->d_n; tp.t = tape->d_t; tp.dt = tape->d_dt; tp.y = tape->d_y; tp.k = tape->d_k; tp.cap = tape->cap;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* gW = d_ws;
+  float* gB = d_ws + P.total_w;
+  if (int32_t e = pack_weights(P, d_W, d_b, gW, gB, st)) return e;
   int dev = 0, max_smem = 0;
   CB_CUDA(cudaGetDevice(&dev));
   CB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  // prefer 2 CTAs/SM with resident weights; fall back to streamed weights, then TB=32
+  // prefer resident weights; fall back to streamed weights, then TB=32
   P.weights_in_smem = 1;
   bool use64 = true;
-  if (lnode_smem_bytes<64>(P) > (size_t)max_smem / 2) {
+  if (lnode_smem_bytes<64>(P) > (size_t)max_smem) {
+    P.weights_in_smem = 0;
     if (lnode_smem_bytes<64>(P) > (size_t)max_smem) {
-      P.weights_in_smem = 0;
-      if (lnode_smem_bytes<64>(P) > (size_t)max_smem) {
-        use64 = false;
-        P.weights_in_smem = 1;
-        if (lnode_smem_bytes<32>(P) > (size_t)max_smem) P.weights_in_smem = 0;
-        CB_CHECK_ARG(lnode_smem_bytes<32>(P) <= (size_t)max_smem, "ODE net too wide for the integrator");
-      }
+      use64 = false;
+      P.weights_in_smem = 1;
+      if (lnode_smem_bytes<32>(P) > (size_t)max_smem) P.weights_in_smem = 0;
+      CB_CHECK_ARG(lnode_smem_bytes<32>(P) <= (size_t)max_smem, "ODE net too wide for the integrator");
     }
   }
   if (use64) {
@@ -407,13 +445,392 @@ extern "C" int32_t cb_lnode_solve_fwd(const cb_lnode_desc* desc, const float* co
     CB_CUDA(cudaFuncSetAttribute(lnode_solve_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = P.wmax_p >= 128 ? 256 : 128;
     lnode_solve_kernel<64><<<(unsigned)((batch + 63) / 64), threads, smem, st>>>(
-        P, gW, gB, d_z0, d_t_eval, batch, d_z_out, d_stats);
+        P, gW, gB, d_z0, d_t_eval, batch, d_z_out, d_stats, tp);
   } else {
     const size_t smem = lnode_smem_bytes<32>(P);
     CB_CUDA(cudaFuncSetAttribute(lnode_solve_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lnode_solve_kernel<32><<<(unsigned)((batch + 31) / 32), 256, smem, st>>>(
-        P, gW, gB, d_z0, d_t_eval, batch, d_z_out, d_stats);
+        P, gW, gB, d_z0, d_t_eval, batch, d_z_out, d_stats, tp);
   }
   CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+// ====================================================================== backward sweep
+namespace cb {
+
+constexpr int kBT = 32;     // trajectories per CTA in the backward kernel
+constexpr int kBThreads = 128;
+
+// out[j][t] = act(sum_k Wt[k][j] in[k][t] + b[j]); also stores the pre-activation z
+__device__ __forceinline__ void bwd_fwd_layer(const float* __restrict__ Wt, const float* __restrict__ bias, int K,
+                                              int N, int Wp, const float* __restrict__ in, float* __restrict__ a_out,
+                                              float* __restrict__ z_out, int act, float ap) {
+  constexpr int TB = kBT, TG = TB / 4;
+  const int tg = threadIdx.x % TG;
+  for (int jg = threadIdx.x / TG; jg < Wp / 8; jg += kBThreads / TG) {
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float bj = bias[jg * 8 + j];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc[j][t] = bj;
+    }
+    for (int k = 0; k < K; ++k) {
+      const float4 w0 = *reinterpret_cast<const float4*>(Wt + (size_t)k * Wp + jg * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(Wt + (size_t)k * Wp + jg * 8 + 4);
+      const float4 a = *reinterpret_cast<const float4*>(in + k * TB + tg * 4);
+      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[j][t] = fmaf(w[j], av[t], acc[j][t]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int jj = jg * 8 + j;
+      if (jj < N) {
+        float4 z = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        *reinterpret_cast<float4*>(z_out + (size_t)jj * TB + tg * 4) = z;
+        float4 o = make_float4(act_fwd(act, z.x, ap), act_fwd(act, z.y, ap), act_fwd(act, z.z, ap), act_fwd(act, z.w, ap));
+        *reinterpret_cast<float4*>(a_out + (size_t)jj * TB + tg * 4) = o;
+      }
+    }
+  }
+}
+
+// dWt[k][j] += sum_t a_in[k][t] * delta[j][t];  db[j] += sum_t delta[j][t]   (this CTA's private global slab)
+__device__ __forceinline__ void bwd_wgrad(const float* __restrict__ a_in, const float* __restrict__ delta, int K, int N,
+                                          int Wp, float* __restrict__ dWt, float* __restrict__ db) {
+  constexpr int TB = kBT;
+  const int njg = Wp / 4;
+  for (int idx = threadIdx.x; idx < K * njg; idx += kBThreads) {
+    const int k = idx / njg, jg = idx - k * njg;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t4 = 0; t4 < TB / 4; ++t4) {
+      const float4 a = *reinterpret_cast<const float4*>(a_in + k * TB + t4 * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int jj = jg * 4 + j;
+        if (jj < N) {
+          const float4 d = *reinterpret_cast<const float4*>(delta + (size_t)jj * TB + t4 * 4);
+          acc[j] += a.x * d.x + a.y * d.y + a.z * d.z + a.w * d.w;
+        }
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(dWt + (size_t)k * Wp + jg * 4);
+    float4 cur = *dst;
+    cur.x += acc[0]; cur.y += acc[1]; cur.z += acc[2]; cur.w += acc[3];
+    *dst = cur;
+  }
+  for (int j = threadIdx.x; j < N; j += kBThreads) {
+    float sacc = 0.f;
+    for (int t = 0; t < TB; ++t) sacc += delta[(size_t)j * TB + t];
+    db[j] += sacc;
+  }
+}
+
+// d_prev[k][t] = (sum_j Wt[k][j] delta[j][t]) * act'(z_prev[k][t])   (z_prev NULL -> no activation: network input)
+__device__ __forceinline__ void bwd_dgrad(const float* __restrict__ Wt, const float* __restrict__ delta, int K, int N,
+                                          int Wp, const float* __restrict__ z_prev, float* __restrict__ d_prev, int act,
+                                          float ap) {
+  constexpr int TB = kBT, TG = TB / 4;
+  for (int idx = threadIdx.x; idx < K * TG; idx += kBThreads) {
+    const int k = idx / TG, tg = idx - k * TG;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < N; ++j) {
+      const float w = Wt[(size_t)k * Wp + j];
+      const float4 d = *reinterpret_cast<const float4*>(delta + (size_t)j * TB + tg * 4);
+      acc[0] = fmaf(w, d.x, acc[0]); acc[1] = fmaf(w, d.y, acc[1]);
+      acc[2] = fmaf(w, d.z, acc[2]); acc[3] = fmaf(w, d.w, acc[3]);
+    }
+    if (z_prev) {
+      const float4 z = *reinterpret_cast<const float4*>(z_prev + (size_t)k * TB + tg * 4);
+      acc[0] *= act_bwd(act, z.x, ap); acc[1] *= act_bwd(act, z.y, ap);
+      acc[2] *= act_bwd(act, z.z, ap); acc[3] *= act_bwd(act, z.w, ap);
+    }
+    *reinterpret_cast<float4*>(d_prev + (size_t)k * TB + tg * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
+// Discrete adjoint of the accepted Tsit5 steps (step sizes treated as constants), reverse sweep over the
+// tape; one CTA owns kBT trajectories and a private gradient slab in global memory.
+__global__ void __launch_bounds__(kBThreads, 1)
+lnode_bwd_kernel(const LnodeParams P, const float* __restrict__ gW, const float* __restrict__ gB,
+                 const float* __restrict__ t_eval_f, int64_t batch, const Tape tape,
+                 const float* __restrict__ g_out, float* __restrict__ dz0, float* __restrict__ slabs,
+                 int slab_floats) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TB = kBT;
+  const int L = P.L, T = P.T, nl = P.n_layers;
+  double* lam = reinterpret_cast<double*>(smem_raw);   // [L][TB]   dL/dy_{n+1}
+  double* kap = lam + L * TB;                          // [7][L][TB] stage adjoints
+  double* ysum = kap + 7 * L * TB;                     // [L][TB]   sum of u_m + direct eval-point terms
+  double* ste = ysum + L * TB;                         // [T]
+  double* s_t = ste + ((T + 1) & ~1);                  // [TB] step start
+  double* s_dt = s_t + TB;                             // [TB]
+  double* s_y = s_dt + TB;                             // [L][TB]
+  float* s_k = reinterpret_cast<float*>(s_y + L * TB); // [7][L][TB]
+  float* xin = s_k + 7 * L * TB;                       // [wmax_p][TB] stage input (layer-0 activation)
+  float* acts = xin + (size_t)P.wmax_p * TB;           // [nl][wmax_p][TB] post-activations
+  float* zs = acts + (size_t)nl * P.wmax_p * TB;       // [nl][wmax_p][TB] pre-activations
+  float* d0 = zs + (size_t)nl * P.wmax_p * TB;         // [wmax_p][TB] delta ping
+  float* d1 = d0 + (size_t)P.wmax_p * TB;              // [wmax_p][TB] delta pong
+  float* sB = d1 + (size_t)P.wmax_p * TB;
+  float* sW = sB + P.total_b;
+  int* s_n = reinterpret_cast<int*>(sW + (P.weights_in_smem ? P.total_w : 0));   // [TB] accepted steps
+  int* s_j = s_n + TB;                                 // [TB] highest eval index not yet consumed
+  __shared__ float red[kBThreads];
+
+  const int tid = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * TB;
+  float* slab = slabs + (size_t)blockIdx.x * slab_floats;   // [total_w | total_b | 1]
+  float* dWt = slab;
+  float* dB = slab + P.total_w;
+  for (int i = tid; i < slab_floats; i += kBThreads) slab[i] = 0.f;
+  for (int i = tid; i < P.total_b; i += kBThreads) sB[i] = gB[i];
+  if (P.weights_in_smem)
+    for (int i = tid; i < P.total_w / 4; i += kBThreads)
+      reinterpret_cast<float4*>(sW)[i] = reinterpret_cast<const float4*>(gW)[i];
+  const float* W = P.weights_in_smem ? sW : gW;
+  for (int i = tid; i < T; i += kBThreads) ste[i] = (double)t_eval_f[i];
+  for (int i = tid; i < L * TB; i += kBThreads) lam[i] = 0.0;
+  if (tid < TB) {
+    const int64_t b = b0 + tid;
+    s_n[tid] = (b < batch) ? max(tape.n[b], 0) : 0;
+    s_j[tid] = T - 1;
+  }
+  __syncthreads();
+  // grid points the forward filled with the final state (round-off at t_end): gradient goes straight to lambda
+  if (tid < TB && s_n[tid] > 0) {
+    const int64_t b = b0 + tid;
+    const int64_t o = b * tape.cap + (s_n[tid] - 1);
+    const double t_fin = tape.t[o] + tape.dt[o];
+    int j = s_j[tid];
+    while (j >= 1 && ste[j] > t_fin) {
+      for (int l = 0; l < L; ++l) lam[l * TB + tid] += (double)g_out[(b * T + j) * L + l];
+      --j;
+    }
+    s_j[tid] = j;
+  }
+  int smax = 0;
+  for (int t = 0; t < TB; ++t) smax = max(smax, s_n[t]);
+  float dreg = 0.f;   // per-thread partial of dL/d reg_factor
+  __syncthreads();
+
+  for (int s = smax - 1; s >= 0; --s) {
+    // ---- load the step record, direct adjoints of the stage derivatives and of y_n
+    for (int i = tid; i < L * TB; i += kBThreads) {
+      const int l = i / TB, t = i % TB;
+      const bool on = s < s_n[t];
+      const int64_t o = (b0 + t) * tape.cap + s;
+      s_y[i] = on ? tape.y[o * L + l] : 0.0;
+      for (int m = 0; m < 7; ++m) s_k[m * L * TB + i] = on ? tape.k[(o * 7 + m) * L + l] : 0.f;
+      ysum[i] = 0.0;
+    }
+    if (tid < TB) {
+      const bool on = s < s_n[tid];
+      const int64_t o = (b0 + tid) * tape.cap + s;
+      s_t[tid] = on ? tape.t[o] : 0.0;
+      s_dt[tid] = on ? tape.dt[o] : 0.0;
+    }
+    __syncthreads();
+    if (tid < TB) {
+      const int t = tid;
+      const bool on = s < s_n[t];
+      const int64_t b = b0 + t;
+      const double dt = s_dt[t], tn = s_t[t];
+      // kappa_i = dt * (b_i * lambda + sum_j btheta_i(theta_j) g_j),  ysum = sum_j g_j
+      for (int l = 0; l < L; ++l) {
+        for (int i = 0; i < 6; ++i) kap[i * L * TB + l * TB + t] = on ? dt * c_a[6][i] * lam[l * TB + t] : 0.0;  // b_i
+        kap[6 * L * TB + l * TB + t] = 0.0;                                                                  // b_7 = 0
+      }
+      if (on) {
+        int j = s_j[t];
+        while (j >= 1 && ste[j] > tn) {
+          const double th = (ste[j] - tn) / dt;
+          const double th2 = th * th, th3 = th2 * th, th4 = th2 * th2;
+          for (int l = 0; l < L; ++l) {
+            const double g = (double)g_out[(b * T + j) * L + l];
+            ysum[l * TB + t] += g;
+#pragma unroll
+            for (int i = 0; i < 7; ++i)
+              kap[i * L * TB + l * TB + t] += dt * (c_r[i][0] * th + c_r[i][1] * th2 + c_r[i][2] * th3 + c_r[i][3] * th4) * g;
+          }
+          --j;
+        }
+        s_j[t] = j;
+      }
+    }
+    __syncthreads();
+    // ---- stages 7..1: recompute f at the stage state, back-propagate kappa_m through it
+    for (int m = 6; m >= 0; --m) {
+      for (int i = tid; i < L * TB; i += kBThreads) {
+        const int t = i % TB;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+          if (j < m) acc += c_a[m][j] * (double)s_k[j * L * TB + i];
+        xin[i] = (float)(s_y[i] + s_dt[t] * acc);
+      }
+      __syncthreads();
+      const float* in = xin;
+      for (int li = 0; li < nl; ++li) {
+        const bool last = (li == nl - 1);
+        bwd_fwd_layer(W + P.w_off[li], sB + P.b_off[li], P.K[li], P.N[li], P.Wp[li], in,
+                      acts + (size_t)li * P.wmax_p * TB, zs + (size_t)li * P.wmax_p * TB,
+                      last ? CB_ACT_IDENTITY : P.act, P.act_param);
+        __syncthreads();
+        in = acts + (size_t)li * P.wmax_p * TB;
+      }
+      // delta at the network output: kappa_m through reg*tanh(o/reg)
+      float* dcur = d0;
+      float* dnext = d1;
+      for (int i = tid; i < L * TB; i += kBThreads) {
+        const float o = zs[(size_t)(nl - 1) * P.wmax_p * TB + i];
+        float kq = (float)kap[m * L * TB + i];
+        if (P.tanh_reg) {
+          const float th = tanhf(o / P.reg);
+          const float sech2 = 1.f - th * th;
+          dreg += kq * (th - (o / P.reg) * sech2);
+          kq *= sech2;
+        }
+        dcur[i] = kq;
+      }
+      __syncthreads();
+      for (int li = nl - 1; li >= 0; --li) {
+        const float* a_in = (li == 0) ? xin : acts + (size_t)(li - 1) * P.wmax_p * TB;
+        bwd_wgrad(a_in, dcur, P.K[li], P.N[li], P.Wp[li], dWt + P.w_off[li], dB + P.b_off[li]);
+        bwd_dgrad(W + P.w_off[li], dcur, P.K[li], P.N[li], P.Wp[li],
+                  (li == 0) ? nullptr : zs + (size_t)(li - 1) * P.wmax_p * TB, dnext, P.act, P.act_param);
+        __syncthreads();
+        float* tmp = dcur; dcur = dnext; dnext = tmp;
+      }
+      // u_m = dcur [L][TB]: scatter to earlier stage adjoints and to y_n
+      for (int i = tid; i < L * TB; i += kBThreads) {
+        const int t = i % TB;
+        const double u = (double)dcur[i];
+        ysum[i] += u;
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+          if (j < m) kap[j * L * TB + i] += s_dt[t] * c_a[m][j] * u;
+      }
+      __syncthreads();
+    }
+    // ---- dL/dy_n
+    for (int i = tid; i < L * TB; i += kBThreads) {
+      const int t = i % TB;
+      if (s < s_n[t]) lam[i] += ysum[i];
+    }
+    __syncthreads();
+  }
+  // z_out[:,0] = z0 and y_0 = z0
+  for (int i = tid; i < L * TB; i += kBThreads) {
+    const int l = i / TB, t = i % TB;
+    const int64_t b = b0 + t;
+    if (b < batch) dz0[b * L + l] = (float)(lam[i] + (double)g_out[(b * T) * L + l]);
+  }
+  red[tid] = dreg;
+  __syncthreads();
+  if (tid == 0) {
+    float sacc = 0.f;
+    for (int i = 0; i < kBThreads; ++i) sacc += red[i];
+    slab[P.total_w + P.total_b] = sacc;
+  }
+}
+
+static size_t lnode_bwd_smem_bytes(const LnodeParams& P) {
+  const int TB = kBT;
+  size_t dbl = (size_t)(P.L * TB * (1 + 7 + 1 + 1) + ((P.T + 1) & ~1) + 2 * TB) * sizeof(double);
+  size_t flt = ((size_t)7 * P.L * TB + (size_t)P.wmax_p * TB * (1 + 2 * P.n_layers + 2) + P.total_b +
+                (P.weights_in_smem ? P.total_w : 0)) * sizeof(float);
+  return dbl + flt + 2 * TB * sizeof(int);
+}
+
+// sum the CTA slabs in fixed order and unpack Wt[k][jp] -> dW[j][k] (nn.Linear layout)
+__global__ void lnode_bwd_reduce_kernel(const float* __restrict__ slabs, int n_slabs, int slab_floats, int w_off,
+                                        int b_off, int total_w, int K, int N, int Wp, float* __restrict__ dW,
+                                        float* __restrict__ db) {
+  const int total = N * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i / K, k = i - j * K;
+    float sacc = 0.f;
+    for (int c = 0; c < n_slabs; ++c) sacc += slabs[(size_t)c * slab_floats + w_off + (size_t)k * Wp + j];
+    dW[i] = sacc;
+  }
+  if (db)
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+      float sacc = 0.f;
+      for (int c = 0; c < n_slabs; ++c) sacc += slabs[(size_t)c * slab_floats + total_w + b_off + j];
+      db[j] = sacc;
+    }
+}
+
+__global__ void lnode_bwd_reduce_reg_kernel(const float* __restrict__ slabs, int n_slabs, int slab_floats, int off,
+                                            float* __restrict__ dreg) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float sacc = 0.f;
+    for (int c = 0; c < n_slabs; ++c) sacc += slabs[(size_t)c * slab_floats + off];
+    dreg[0] = sacc;
+  }
+}
+
+}  // namespace cb
+
+extern "C" int64_t cb_lnode_bwd_workspace_floats(const cb_lnode_desc* desc, int64_t batch) {
+  LnodeParams P;
+  if (batch < 0 || build_params(desc, 2, P) != CB_OK) return -1;
+  const int64_t n_cta = (batch + kBT - 1) / kBT;
+  const int64_t slab = (P.total_w + P.total_b + 1 + 3) & ~3;
+  return (int64_t)P.total_w + P.total_b + 64 + n_cta * slab;
+}
+
+extern "C" int32_t cb_lnode_solve_bwd(const cb_lnode_desc* desc, const float* const* d_W, const float* const* d_b,
+                                      const float* d_t_eval, int64_t batch, int32_t n_t, const cb_lnode_tape* tape,
+                                      const float* d_g, float* d_dz0, float* const* d_dW, float* const* d_db,
+                                      float* d_dreg, float* d_ws, int64_t ws_floats, void* stream) {
+  LnodeParams P;
+  if (int32_t e = build_params(desc, n_t, P)) return e;
+  CB_CHECK_ARG(batch >= 1, "bad batch");
+  CB_CHECK_ARG(d_W && d_b && d_t_eval && tape && d_g && d_dz0 && d_dW && d_db && d_ws, "NULL pointer argument");
+  CB_CHECK_ARG(tape->d_n && tape->d_t && tape->d_dt && tape->d_y && tape->d_k && tape->cap >= 1, "bad tape");
+  CB_CHECK_ARG(!desc->tanh_reg || d_dreg, "d_dreg required with tanh_reg");
+  const int64_t need = cb_lnode_bwd_workspace_floats(desc, batch);
+  if (ws_floats < need) {
+    set_error("workspace too small: %lld < %lld floats", (long long)ws_floats, (long long)need);
+    return CB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* gW = d_ws;
+  float* gB = d_ws + P.total_w;
+  float* slabs = d_ws + ((P.total_w + P.total_b + 63) & ~3);   // 16-byte aligned behind the packed weights
+  const int slab_floats = (P.total_w + P.total_b + 1 + 3) & ~3;
+  const int n_cta = (int)((batch + kBT - 1) / kBT);
+  if (int32_t e = pack_weights(P, d_W, d_b, gW, gB, st)) return e;
+  int dev = 0, max_smem = 0;
+  CB_CUDA(cudaGetDevice(&dev));
+  CB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  P.weights_in_smem = 1;
+  if (lnode_bwd_smem_bytes(P) > (size_t)max_smem) P.weights_in_smem = 0;
+  const size_t smem = lnode_bwd_smem_bytes(P);
+  CB_CHECK_ARG(smem <= (size_t)max_smem, "ODE net too wide for the backward sweep kernel (%zu bytes of shared memory)", smem);
+  CB_CUDA(cudaFuncSetAttribute(lnode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  Tape tp{tape->d_n, tape->d_t, tape->d_dt, tape->d_y, tape->d_k, tape->cap};
+  lnode_bwd_kernel<<<n_cta, kBThreads, smem, st>>>(P, gW, gB, d_t_eval, batch, tp, d_g, d_dz0, slabs, slab_floats);
+  CB_LAUNCH_CHECK();
+  for (int i = 0; i < P.n_layers; ++i) {
+    const int total = P.N[i] * P.K[i];
+    int blocks = (total + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    lnode_bwd_reduce_kernel<<<blocks, 256, 0, st>>>(slabs, n_cta, slab_floats, P.w_off[i], P.b_off[i], P.total_w,
+                                                   P.K[i], P.N[i], P.Wp[i], d_dW[i], d_db[i]);
+    CB_LAUNCH_CHECK();
+  }
+  if (d_dreg) {
+    lnode_bwd_reduce_reg_kernel<<<1, 32, 0, st>>>(slabs, n_cta, slab_floats, P.total_w + P.total_b, d_dreg);
+    CB_LAUNCH_CHECK();
+  }
   return CB_OK;
 }

@@ -183,11 +183,38 @@ typedef struct {
  * z_out:(batch,T,L) fp32, stats:(batch,2) int32 = {steps, accepted} (may be NULL;
  * steps is negated when max_steps was exhausted).  The workspace receives the
  * k-major repacked ODE-net weights (cb_lnode_workspace_floats). */
+/* Accepted-step record written by the forward solve for the backward sweep (training).  All
+ * buffers are caller-owned device memory: n:(batch) int32, t/dt:(batch,cap) fp64,
+ * y:(batch,cap,L) fp64, k:(batch,cap,7,L) fp32.  n[b] = -1 if a trajectory needed more than
+ * `cap` accepted steps. */
+typedef struct {
+  int32_t* d_n;
+  double* d_t;
+  double* d_dt;
+  double* d_y;
+  float* d_k;
+  int32_t cap;
+} cb_lnode_tape;
+
 CB_API int64_t cb_lnode_workspace_floats(const cb_lnode_desc* desc);
 CB_API int32_t cb_lnode_solve_fwd(const cb_lnode_desc* desc, const float* const* d_W,
                            const float* const* d_b, const float* d_z0, const float* d_t_eval,
                            int64_t batch, int32_t n_t, float* d_z_out, int32_t* d_stats,
-                           float* d_workspace, int64_t workspace_floats, void* stream);
+                           float* d_workspace, int64_t workspace_floats,
+                           const cb_lnode_tape* tape /* NULL in inference */, void* stream);
+
+/* Backward of the solve (replaces loss.backward() through torchode's AutoDiffAdjoint,
+ * latent_neural_ode.py:219,469): discrete adjoint of the accepted Tsit5 steps and of the dense
+ * output, reverse sweep over the tape in one persistent kernel (step sizes are treated as
+ * constants, i.e. no gradient through the step-size controller).
+ * g:(batch,T,L) = dL/dz_out;  outputs: dz0:(batch,L), dW[i]:(out,in), db[i]:(out), dreg:(1). */
+CB_API int64_t cb_lnode_bwd_workspace_floats(const cb_lnode_desc* desc, int64_t batch);
+CB_API int32_t cb_lnode_solve_bwd(const cb_lnode_desc* desc, const float* const* d_W,
+                                  const float* const* d_b, const float* d_t_eval, int64_t batch,
+                                  int32_t n_t, const cb_lnode_tape* tape, const float* d_g,
+                                  float* d_dz0, float* const* d_dW, float* const* d_db,
+                                  float* d_dreg, float* d_workspace, int64_t workspace_floats,
+                                  void* stream);
 
 /* --------------------------------------------------- tensor-core (bf16) path */
 /* Opaque plan for a fused bf16 MLP chain on tcgen05 (weights converted/padded

@@ -352,3 +352,104 @@ def test_training_is_bitwise_deterministic():
     b, lb = run()
     assert torch.equal(a, b)
     np.testing.assert_array_equal(la, lb)
+
+
+# ------------------------------------------------------------------ latent ODE backward sweep
+def _torch_ode_net(m, dtype=torch.float64):
+    """CPU float64 copy of the ODE net f(z) = reg*tanh(MLP(z)/reg) with leaf parameters."""
+    lin = [mod for mod in m.model.ode.mlp if isinstance(mod, nn.Linear)]
+    ws = [l.weight.detach().cpu().to(dtype).requires_grad_() for l in lin]
+    bs = [l.bias.detach().cpu().to(dtype).requires_grad_() for l in lin]
+    reg = m.model.ode.reg_factor.detach().cpu().to(dtype).requires_grad_()
+    act = m.model.ode.activation
+
+    def f(z):
+        h = z
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            h = h @ w.T + b
+            if i < len(ws) - 1:
+                h = act(h)
+        return reg * torch.tanh(h / reg) if m.config.ode_tanh_reg else h
+    return f, ws, bs, reg
+
+
+@pytest.mark.parametrize("act_cls,tanh_reg", [(nn.Tanh, True), (nn.SiLU, False), (nn.ReLU, True)])
+def test_lnode_backward_matches_autograd_replay(act_cls, tanh_reg):
+    """dL/dz0, dL/dW, dL/db, dL/dreg of the persistent backward sweep vs torch.autograd through a
+    float64 replay of the same accepted steps (oracle/torch_lnode.py).  Tolerance 2e-3 relative to the
+    largest gradient entry (fp32 MLP in the kernel vs fp64 replay)."""
+    import codes_b200 as cb
+    from codes_b200 import ops
+    from oracle.torch_lnode import replay_solve
+    torch.manual_seed(11)
+    T, Lat = 24, 4
+    m = cb.LatentNeuralODE(DEV, 6, T, 0, None, {"latent_features": Lat, "ode_layers": 2, "ode_width": 32,
+                                                 "activation": act_cls(), "ode_tanh_reg": tanh_reg})
+    with torch.no_grad():
+        for p in m.model.ode.mlp.parameters():
+            p.mul_(2.5)
+        m.model.ode.reg_factor.fill_(0.9)
+    B = 37
+    g = torch.Generator().manual_seed(5)
+    z0 = (torch.rand(B, Lat, generator=g) * 2 - 1)
+    wgt = torch.randn(B, T, Lat, generator=g)
+    t = torch.linspace(0, 1, T)
+    w, b = ops.sequential_params(m.model.ode.mlp)
+    z0d = z0.to(DEV).requires_grad_()
+    zs = ops.lnode_integrate(m.model, m.model.ode.chain(), w, b, z0d, t.to(DEV))
+    (zs * wgt.to(DEV)).sum().backward()
+    # tape of the same forward (deterministic kernel) for the replay
+    _, stats, tape = ops.lnode_solve(m.model.ode.chain(), w, b, z0.to(DEV), t.to(DEV), tanh_reg, 0.9, 1e-6, 1e-6,
+                                     return_stats=True, record_tape=True)
+    n_acc = tape[0].cpu()
+    assert (n_acc > 0).all() and torch.equal(n_acc, stats[:, 1].cpu())
+    f, ws, bs, reg = _torch_ode_net(m)
+    z0c = z0.double().requires_grad_()
+    zr = replay_solve(f, z0c, t.double(), tape[1].cpu(), tape[2].cpu(), n_acc)
+    np.testing.assert_allclose(t2n(zs), zr.detach().numpy(), rtol=2e-6, atol=2e-5)  # fp32 MLP vs fp64 replay
+    (zr * wgt.double()).sum().backward()
+
+    def close(a, ref, what):
+        ref = ref.numpy()
+        scale = max(np.abs(ref).max(), 1e-12)
+        err = np.abs(t2n(a).astype(np.float64) - ref).max() / scale
+        assert err < 2e-3, (what, err)
+
+    close(z0d.grad, z0c.grad, "dz0")
+    lin = [mod for mod in m.model.ode.mlp if isinstance(mod, nn.Linear)]
+    for i, l in enumerate(lin):
+        close(l.weight.grad, ws[i].grad, f"dW{i}")
+        close(l.bias.grad, bs[i].grad, f"db{i}")
+    if tanh_reg:
+        close(m.model.ode.reg_factor.grad.reshape(1), reg.grad.reshape(1), "dreg")
+
+
+def test_lnode_fit_runs_and_is_deterministic():
+    import codes_b200 as cb
+    d = O.synthetic_dataset(48, 16, 5, seed=9)
+
+    def run():
+        torch.manual_seed(0)
+        m = cb.LatentNeuralODE(DEV, 5, 16, 0, None, {"learning_rate": 1e-3, "scheduler": "poly"})
+        tr, te, _ = m.prepare_data(d, d[:8], None, np.linspace(0, 1, 16), 16, shuffle=True)
+        losses = []
+        opt, sch = m.setup_optimizer_and_scheduler(4)
+        for epoch in range(4):
+            for batch in tr:
+                opt.zero_grad()
+                xp, xt = m(batch)
+                loss = m.model.total_loss(xt, xp, None, m.config.loss_function)
+                loss.backward()
+                opt.step()
+                losses.append(loss.item())
+            sch.step()
+        return losses, torch.cat([p.detach().flatten() for p in m.parameters()]).cpu()
+
+    l1, p1 = run()
+    l2, p2 = run()
+    assert l1 == l2 and torch.equal(p1, p2)
+    assert np.isfinite(l1).all() and l1[-1] < l1[0]
+    m = cb.LatentNeuralODE(DEV, 5, 16, 0, None, {})
+    tr, te, _ = m.prepare_data(d, d[:8], None, np.linspace(0, 1, 16), 16, shuffle=True)
+    m.fit(tr, te, epochs=2)
+    assert m.n_epochs == 2 and np.isfinite(m.train_loss).all()
