@@ -348,7 +348,7 @@ __device__ __forceinline__ void teardown_cta(uint32_t tmem_base, int warp) {
 }
 
 // ====================================================================== chain kernel
-template <int ACT>
+template <int ACT, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -411,6 +411,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
       int tn = 0;
       int seen_in = 0, seen_epi = 0;
       const uint64_t bdesc0 = make_smem_desc(ST0);
+      constexpr bool pair = PAIR;   // host picks PAIR only when the ring has >= 4 stages (a shallower ring would drain)
       for (int it = 0; it < n_my_tiles; ++it) {
         for (int j = 0; j < P.n_jobs; ++j, ++gj) {
           const Job job = P.jobs[j];
@@ -435,25 +436,43 @@ chain_kernel(const __grid_constant__ ChainParams P) {
             need0 = it * P.n_jobs + P.first_job[l - 1] + 1;
             last_pc = P.n_chunks[l - 1] - 1;
           }
-          for (int kb = 0; kb < nkb; ++kb) {
-            if (l != 0) wait_counter(C.epi_done, need0 + min(kb >> 1, last_pc), seen_epi);
+          // two k-blocks (8 MMAs, 512 tensor cycles) per loop iteration: the waits, fences and branch
+          // overhead of the issuing warp (~300-400 cycles per iteration) then hide behind the MMAs.
+          // Both k-blocks belong to this job, so their activation dependencies never involve the
+          // MMAs about to be issued (no self-wait).
+          for (int kb = 0; kb < nkb; kb += (pair ? 2 : 1)) {
+            const bool two = pair && (kb + 1 < nkb);
+            if (l != 0) wait_counter(C.epi_done, need0 + min((kb + (two ? 1 : 0)) >> 1, last_pc), seen_epi);
             CB_TRACE(1, 3, j * 8 + kb);
+            int stage_b = stage + 1; uint32_t phase_b = phase;
+            if (stage_b == P.stages) { stage_b = 0; phase_b ^= 1; }
             mbar_wait(C.bar_full + 8 * stage, phase);
+            if (two) mbar_wait(C.bar_full + 8 * stage_b, phase_b);
             CB_TRACE(1, 4, j * 8 + kb);
             tcgen05_fence_after();
-            const int nks = (kb == nkb - 1) ? last_nks : 4;
             // descriptor start-address field counts 16-byte units: +1024 per 16 KiB k-block / stage,
             // +2 per 16-column k-step
             const uint64_t adesc = adesc0 + (uint64_t)(kb * (kKBlockBytes >> 4));
             const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kKBlockBytes >> 4));
+            const uint64_t bdesc_b = bdesc0 + (uint64_t)(stage_b * (kKBlockBytes >> 4));
+            const int nks_a = (kb == nkb - 1) ? last_nks : 4;
+            const int nks_b = (kb + 1 == nkb - 1) ? last_nks : 4;
             if (elect_one()) {
               umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
 #pragma unroll
               for (int ks = 1; ks < 4; ++ks)
-                if (ks < nks) umma_bf16(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
+                if (ks < nks_a) umma_bf16(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
               umma_commit(C.bar_empty + 8 * stage);   // frees the weight stage when these MMAs retire
+              if (two) {
+                const uint64_t adesc_b = adesc + (uint64_t)(kKBlockBytes >> 4);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  if (ks < nks_b) umma_bf16(d_tmem, adesc_b + (uint64_t)(2 * ks), bdesc_b + (uint64_t)(2 * ks), idesc, 1u);
+                umma_commit(C.bar_empty + 8 * stage_b);
+              }
             }
             __syncwarp();
+            if (two) { stage = stage_b; phase = phase_b; }
             if (++stage == P.stages) { stage = 0; phase ^= 1; }
           }
           if (elect_one()) umma_commit(C.bar_tfull + 8 * slot);   // accumulator chunk complete -> epilogue
@@ -827,20 +846,24 @@ static bool encode_bf16_map(CUtensorMap* map, const void* ptr, long long rows, l
 }
 
 typedef void (*ChainKernelFn)(const ChainParams);
-static ChainKernelFn chain_kernel_for(int act) {
+template <bool PAIR>
+static ChainKernelFn chain_kernel_for_act(int act) {
   switch (act) {
-    case CB_ACT_RELU: return chain_kernel<CB_ACT_RELU>;
+    case CB_ACT_RELU: return chain_kernel<CB_ACT_RELU, PAIR>;
     case CB_ACT_LEAKYRELU:
-    case CB_ACT_PRELU: return chain_kernel<CB_ACT_LEAKYRELU>;
-    case CB_ACT_TANH: return chain_kernel<CB_ACT_TANH>;
-    case CB_ACT_GELU: return chain_kernel<CB_ACT_GELU>;
-    case CB_ACT_ELU: return chain_kernel<CB_ACT_ELU>;
-    case CB_ACT_SILU: return chain_kernel<CB_ACT_SILU>;
-    case CB_ACT_SOFTPLUS: return chain_kernel<CB_ACT_SOFTPLUS>;
-    case CB_ACT_MISH: return chain_kernel<CB_ACT_MISH>;
-    case CB_ACT_SIGMOID: return chain_kernel<CB_ACT_SIGMOID>;
-    default: return chain_kernel<CB_ACT_IDENTITY>;
+    case CB_ACT_PRELU: return chain_kernel<CB_ACT_LEAKYRELU, PAIR>;
+    case CB_ACT_TANH: return chain_kernel<CB_ACT_TANH, PAIR>;
+    case CB_ACT_GELU: return chain_kernel<CB_ACT_GELU, PAIR>;
+    case CB_ACT_ELU: return chain_kernel<CB_ACT_ELU, PAIR>;
+    case CB_ACT_SILU: return chain_kernel<CB_ACT_SILU, PAIR>;
+    case CB_ACT_SOFTPLUS: return chain_kernel<CB_ACT_SOFTPLUS, PAIR>;
+    case CB_ACT_MISH: return chain_kernel<CB_ACT_MISH, PAIR>;
+    case CB_ACT_SIGMOID: return chain_kernel<CB_ACT_SIGMOID, PAIR>;
+    default: return chain_kernel<CB_ACT_IDENTITY, PAIR>;
   }
+}
+static ChainKernelFn chain_kernel_for(int act, int stages) {
+  return stages >= 4 ? chain_kernel_for_act<true>(act) : chain_kernel_for_act<false>(act);
 }
 
 }  // namespace tc
@@ -970,7 +993,7 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
   }
   P.n_jobs = nj;
   pl->smem_bytes = g.smem;
-  if (cudaFuncSetAttribute(chain_kernel_for(desc->act), cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(chain_kernel_for(desc->act, g.stages), cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)pl->smem_bytes) != cudaSuccess) {
     cb_tc_chain_destroy(pl);
     set_error("cannot reserve %zu bytes of shared memory for the chain kernel: %s", g.smem,
@@ -1017,7 +1040,7 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
     CB_CUDA(cudaMalloc(&P.trace, 4 * 8192 * sizeof(unsigned long long)));
     CB_CUDA(cudaMemsetAsync(P.trace, 0, 4 * 8192 * sizeof(unsigned long long), st));
   }
-  chain_kernel_for(plan->desc.act)<<<grid, kThreads, plan->smem_bytes, st>>>(P);
+  chain_kernel_for(plan->desc.act, P.stages)<<<grid, kThreads, plan->smem_bytes, st>>>(P);
   CB_LAUNCH_CHECK();
   if (trace_path) {
     static unsigned long long host[4 * 8192];
