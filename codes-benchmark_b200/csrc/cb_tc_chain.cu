@@ -608,8 +608,6 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
   const uint32_t XB = base, XT = base + xbytes, ST0 = base + 2 * xbytes;
   const uint32_t ctrl_addr = ST0 + (uint32_t)P.stages * kKBlockBytes;
   const Ctrl C = carve_ctrl(ctrl_addr, gbase + (ctrl_addr - base));
-  const uint32_t OSTG = ctrl_addr + kCtrlBytes;      // (128, Q+1) fp32 output staging tile
-  const int out_ld = P.Q + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_base = setup_cta(C, P.stages, warp);
@@ -692,15 +690,16 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
     const int r = q4 * 32 + lane;
     const int h = (warp - 2) >> 2;          // this warp takes the 32-column groups with (group & 1) == h
     const int et = threadIdx.x - 64;        // 0..255
-    const uint32_t my_row = OSTG + (uint32_t)((r * out_ld) * 4);
     // Each of the two column-half warps of a row keeps ONE running partial per quantity in a register
-    // and adds it to shared memory exactly once (red.shared): every y[r,q] is 0 + a + b with a, b the
-    // two halves' partials -> commutative, hence bitwise deterministic.
+    // and adds it to y exactly once (red.global.add on the pre-zeroed output): every y[r,q] is
+    // 0 + a + b with a, b the two halves' partials -> commutative, hence bitwise deterministic.
+    // No staging tile in shared memory: its 15 KiB buy a fourth weight stage.
     int cur_q = -1;
     float cur_acc = 0.f;
+    float* yrow = nullptr;
     auto add_to = [&](int qq, float s) {
       if (qq != cur_q) {
-        if (cur_q >= 0 && cur_q < P.Q) red_shared_add_f32(my_row + (uint32_t)(cur_q * 4), cur_acc);
+        if (cur_q >= 0 && cur_q < P.Q && yrow) atomicAdd(yrow + cur_q, cur_acc);
         cur_q = qq;
         cur_acc = 0.f;
       }
@@ -709,9 +708,8 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
     int gs = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      if (h == 0)
-        for (int qq = 0; qq < P.Q; ++qq) st_shared_f32(my_row + (uint32_t)(qq * 4), 0.f);
-      epi_bar_sync();
+      const long long row_g = (long long)tile * kTileM + r;
+      yrow = (row_g < P.rows) ? P.y + row_g * P.Q : nullptr;
       for (int j = 0; j < P.n_jobs; ++j, gs += 2) {
         const int ncols = min(kChunkN, P.n_out - j * kChunkN);
         const int slot_b = gs & (kSlots - 1), slot_t = (gs + 1) & (kSlots - 1);
@@ -775,18 +773,7 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
         mbar_arrive(C.bar_tempty + 8 * slot_t);
       }
       add_to(-1, 0.f);   // flush the last running partial
-      epi_bar_sync();
-      // coalesced copy-out of the (128, Q) tile, linear over the contiguous global block
-      {
-        const long long rows_left = P.rows - (long long)tile * kTileM;
-        const int nr = rows_left < kTileM ? (int)(rows_left < 0 ? 0 : rows_left) : kTileM;
-        float* yp = P.y + (long long)tile * kTileM * P.Q;
-        for (int idx = et; idx < nr * P.Q; idx += kEpiThreads) {
-          const int rr = idx / P.Q, qq = idx - rr * P.Q;
-          yp[idx] = ld_shared_f32(OSTG + (uint32_t)((rr * out_ld + qq) * 4));
-        }
-      }
-      epi_bar_sync();
+      epi_bar_sync();    // every epilogue warp has released its TMEM slots and consumed the tile
       if (et == 0) red_release_inc(C.epi_done);
     }
   }
@@ -1086,8 +1073,8 @@ extern "C" void cb_tc_multionet_destroy(cb_tc_multionet* m) {
 static bool final_geometry(int K, int Q, int* nkb_out, int* stages_out, size_t* smem_out) {
   const int ksteps = (K + 1 + kUmmaK - 1) / kUmmaK;
   const int nkb = (ksteps + 3) / 4;
-  const size_t ostage = (size_t)kTileM * (Q + 1) * sizeof(float);
-  const long long fixed = 1024 + kCtrlBytes + (long long)ostage + 2ll * nkb * kKBlockBytes;
+  (void)Q;
+  const long long fixed = 1024 + kCtrlBytes + 2ll * nkb * kKBlockBytes;
   long long stages = ((long long)kMaxSmem - fixed) / kKBlockBytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (const char* e = getenv("CB_TC_MAX_STAGES")) { const int c = atoi(e); if (c >= 2 && c < stages) stages = c; }  // experiment knob
@@ -1249,6 +1236,7 @@ static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_
   if (ev) cudaEventRecord(ev[1], st);
   if (int32_t e = chain_launch(m->hidden[1], d_trunk_in, nullptr, rows, nullptr, &hmap[1], st)) return e;
   if (ev) cudaEventRecord(ev[2], st);
+  CB_CUDA(cudaMemsetAsync(d_y, 0, (size_t)rows * m->Q * sizeof(float), st));   // the final kernel accumulates into y
   FinalParams F = m->F;
   F.tmap_in[0] = hmap[0]; F.tmap_in[1] = hmap[1];
   F.y = d_y; F.rows = rows;
