@@ -327,7 +327,9 @@ static int tensor_grid_x(const int64_t* sizes, int n) {
   int64_t mx = 1;
   for (int i = 0; i < n; ++i) mx = sizes[i] > mx ? sizes[i] : mx;
   int64_t b = (mx + kThreads * 4 - 1) / (kThreads * 4);
-  if (b > 64) b = 64;
+  const int64_t cap = (int64_t)num_sms() * 4 / (n > 0 ? (n < 8 ? n : 8) : 1) + 1;   // ~4 CTAs per SM over the big tensors
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
   return (int)b;
 }
 

@@ -69,41 +69,44 @@ __global__ void lnode_pack_kernel(const float* __restrict__ W, const float* __re
     bp[j] = (j < N && b) ? b[j] : 0.f;
 }
 
-template <int TB>
+// out[j][t] = act(sum_k Wt[k][j] in[k][t] + b[j]) for the TB trajectories of the CTA.  Thread tile =
+// JT outputs x 4 trajectories (JT = 8 with 128 threads, JT = 4 with 256 threads: twice the warps to
+// hide the LDS/FFMA latency when the net is narrow).
+template <int TB, int JT>
 __device__ __forceinline__ void mlp_layer(const float* __restrict__ Wt, const float* __restrict__ bias,
                                           int K, int N, int Wp, const float* __restrict__ in,
                                           float* __restrict__ out, int act, float ap) {
   constexpr int TG = TB / 4;
   const int tg = threadIdx.x % TG;
   const int jstep = blockDim.x / TG;
-  for (int jg = threadIdx.x / TG; jg < Wp / 8; jg += jstep) {
-    float acc[8][4];
-    {
-      const float4 b0 = *reinterpret_cast<const float4*>(bias + jg * 8);
-      const float4 b1 = *reinterpret_cast<const float4*>(bias + jg * 8 + 4);
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  for (int jg = threadIdx.x / TG; jg < Wp / JT; jg += jstep) {
+    float acc[JT][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < JT; ++j) {
+      const float bj = bias[jg * JT + j];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) acc[j][t] = bb[j];
+      for (int t = 0; t < 4; ++t) acc[j][t] = bj;
     }
-    const float* wp = Wt + jg * 8;
+    const float* wp = Wt + jg * JT;
     const float* ip = in + tg * 4;
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-      const float4 w0 = *reinterpret_cast<const float4*>(wp + (size_t)k * Wp);
-      const float4 w1 = *reinterpret_cast<const float4*>(wp + (size_t)k * Wp + 4);
+      float w[JT];
+#pragma unroll
+      for (int j4 = 0; j4 < JT / 4; ++j4) {
+        const float4 wv = *reinterpret_cast<const float4*>(wp + (size_t)k * Wp + j4 * 4);
+        w[j4 * 4] = wv.x; w[j4 * 4 + 1] = wv.y; w[j4 * 4 + 2] = wv.z; w[j4 * 4 + 3] = wv.w;
+      }
       const float4 a = *reinterpret_cast<const float4*>(ip + k * TB);
-      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
       const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < JT; ++j)
 #pragma unroll
         for (int t = 0; t < 4; ++t) acc[j][t] = fmaf(w[j], av[t], acc[j][t]);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int jj = jg * 8 + j;
+    for (int j = 0; j < JT; ++j) {
+      const int jj = jg * JT + j;
       if (jj < N) {
         float4 o;
         o.x = act_fwd(act, acc[j][0], ap);
@@ -118,7 +121,7 @@ __device__ __forceinline__ void mlp_layer(const float* __restrict__ Wt, const fl
 
 // f(in) -> kout[l][t] : full ODE net on the TB trajectories of this CTA.
 // `a0` holds the fp32 stage state [L][TB]; a0/a1 are ping-pong buffers.
-template <int TB>
+template <int TB, int JT>
 __device__ __forceinline__ void ode_rhs(const LnodeParams& P, const float* __restrict__ W,
                                         const float* __restrict__ Bv, float* a0, float* a1,
                                         float* __restrict__ kout) {
@@ -126,7 +129,7 @@ __device__ __forceinline__ void ode_rhs(const LnodeParams& P, const float* __res
   float* out = a1;
   for (int i = 0; i < P.n_layers; ++i) {
     const bool last = (i == P.n_layers - 1);
-    mlp_layer<TB>(W + P.w_off[i], Bv + P.b_off[i], P.K[i], P.N[i], P.Wp[i], in, out,
+    mlp_layer<TB, JT>(W + P.w_off[i], Bv + P.b_off[i], P.K[i], P.N[i], P.Wp[i], in, out,
                   last ? CB_ACT_IDENTITY : P.act, P.act_param);
     __syncthreads();
     float* tmp = in; in = out; out = tmp;
@@ -150,7 +153,7 @@ struct Tape {
   int cap;
 };
 
-template <int TB>
+template <int TB, int JT>
 __global__ void lnode_solve_kernel(const LnodeParams P, const float* __restrict__ gW,
                                    const float* __restrict__ gB, const float* __restrict__ z0,
                                    const float* __restrict__ t_eval_f, int64_t batch,
@@ -203,7 +206,7 @@ __global__ void lnode_solve_kernel(const LnodeParams P, const float* __restrict_
     snac[tid] = 0;
   }
   // ---- f0
-  ode_rhs<TB>(P, W, sB, a0, a1, kf);
+  ode_rhs<TB, JT>(P, W, sB, a0, a1, kf);
   // ---- Hairer initial step, part 1: h0 and the Euler probe
   if (tid < TB) {
     double d0 = 0, d1 = 0;
@@ -224,7 +227,7 @@ __global__ void lnode_solve_kernel(const LnodeParams P, const float* __restrict_
     a0[i] = (float)(sy[i] + sh0[t] * (double)kf[i]);
   }
   __syncthreads();
-  ode_rhs<TB>(P, W, sB, a0, a1, kf + L * TB);  // f1 -> slot 1
+  ode_rhs<TB, JT>(P, W, sB, a0, a1, kf + L * TB);  // f1 -> slot 1
   if (tid < TB) {
     double d2 = 0;
     for (int l = 0; l < L; ++l) {
@@ -259,7 +262,7 @@ __global__ void lnode_solve_kernel(const LnodeParams P, const float* __restrict_
         if (s == 6) syn[i] = ys;
       }
       __syncthreads();
-      ode_rhs<TB>(P, W, sB, a0, a1, kf + s * L * TB);
+      ode_rhs<TB, JT>(P, W, sB, a0, a1, kf + s * L * TB);
     }
     if (tid < TB && srun[tid]) {
       const int t = tid;
@@ -442,14 +445,14 @@ extern "C" int32_t cb_lnode_solve_fwd(const cb_lnode_desc* desc, const float* co
   }
   if (use64) {
     const size_t smem = lnode_smem_bytes<64>(P);
-    CB_CUDA(cudaFuncSetAttribute(lnode_solve_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int threads = P.wmax_p >= 128 ? 256 : 128;
-    lnode_solve_kernel<64><<<(unsigned)((batch + 63) / 64), threads, smem, st>>>(
+    // 256 threads with 4-output thread tiles: 8 warps per SM keep the FFMA pipe busier than 4
+    CB_CUDA(cudaFuncSetAttribute(lnode_solve_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lnode_solve_kernel<64, 4><<<(unsigned)((batch + 63) / 64), 256, smem, st>>>(
         P, gW, gB, d_z0, d_t_eval, batch, d_z_out, d_stats, tp);
   } else {
     const size_t smem = lnode_smem_bytes<32>(P);
-    CB_CUDA(cudaFuncSetAttribute(lnode_solve_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lnode_solve_kernel<32><<<(unsigned)((batch + 31) / 32), 256, smem, st>>>(
+    CB_CUDA(cudaFuncSetAttribute(lnode_solve_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lnode_solve_kernel<32, 8><<<(unsigned)((batch + 31) / 32), 256, smem, st>>>(
         P, gW, gB, d_z0, d_t_eval, batch, d_z_out, d_stats, tp);
   }
   CB_LAUNCH_CHECK();
