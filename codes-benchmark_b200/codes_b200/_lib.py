@@ -73,6 +73,7 @@ _SIGNATURES = {
     "cb_schedulefree_adamw_step": (_I32, [_PP, _PP, _PP, _PP, C.POINTER(_I64), _I32, _F, _F, _F, _F, _F, _F, _F, _P]),
     "cb_schedulefree_sgd_step": (_I32, [_PP, _PP, _PP, C.POINTER(_I64), _I32, _F, _F, _F, _F, _P]),
     "cb_lerp_tensors": (_I32, [_PP, _PP, C.POINTER(_I64), _I32, _F, _P]),
+    "cb_gather_rows": (_I32, [_P, _P, _I64, _I64, _I32, _P, _P]),
     "cb_denormalize": (_I32, [_P, _I64, _I32, _I32, _P, _P, _I32, _P, _P]),
     "cb_lnode_workspace_floats": (_I64, [C.POINTER(LnodeDesc)]),
     "cb_lnode_solve_fwd": (_I32, [C.POINTER(LnodeDesc), _PP, _PP, _P, _P, _I64, _I32, _P, _P, _P, _I64,

@@ -124,7 +124,7 @@ class MultiONet(OperatorNetwork):
         tensors = [torch.from_numpy(np.ascontiguousarray(a)).float()
                    for a in (branch, trunk, data.reshape(-1, Q))]
         pin = pin_memory and self.device is not None and "cuda" in self.device and torch.cuda.is_available()
-        ds = RowBatchIterable(tensors, batch_size, shuffle, pin=pin)
+        ds = RowBatchIterable(tensors, batch_size, shuffle, pin=pin, device=self.device)
         return make_loader(ds, self.device, num_workers)
 
     def prepare_data(self, dataset_train, dataset_test, dataset_val, timesteps, batch_size, shuffle=True,

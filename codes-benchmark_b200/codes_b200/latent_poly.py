@@ -100,7 +100,8 @@ class LatentPoly(AbstractSurrogateModel):
         params_t = None if dataset_params is None else torch.from_numpy(dataset_params).float()
         pin = pin_memory and self.device is not None and "cuda" in self.device and torch.cuda.is_available()
         ds = RowBatchIterable([data_t, params_t], batch_size, shuffle,
-                              layout=[("t", 0), ("c", 0), ("t", 1)], constants=[t_t], pin=pin)
+                              layout=[("t", 0), ("c", 0), ("t", 1)], constants=[t_t], pin=pin,
+                              device=self.device)
         return make_loader(ds, self.device, num_workers)
 
     def prepare_data(self, dataset_train, dataset_test, dataset_val, timesteps, batch_size=128, shuffle=True,

@@ -37,7 +37,7 @@ class RowBatchIterable(IterableDataset):
 
     def __init__(self, tensors: Sequence[torch.Tensor | None], batch_size: int, shuffle: bool,
                  layout: Sequence[tuple[str, int]] | None = None, constants: Sequence[torch.Tensor] = (),
-                 pin: bool = False):
+                 pin: bool = False, device: str | None = None):
         self.tensors = [_maybe_pin(t, pin) for t in tensors]
         self.constants = [_maybe_pin(c, pin) for c in constants]
         # layout: output tuple description, ("t", i) -> batched tensor i, ("c", i) -> constant i
@@ -46,12 +46,33 @@ class RowBatchIterable(IterableDataset):
         self.bs = int(batch_size)
         self.shuffle = bool(shuffle)
         self.pin = pin
+        # shuffled (training) loaders on a CUDA device keep the dataset in HBM and gather
+        # every batch with cb_gather_rows; the permutation still comes from torch.randperm on the CPU
+        # generator, so the batch contents equal the reference's for the same seed.
+        self.device = device if (device is not None and "cuda" in str(device) and self.shuffle
+                                 and device_loader_enabled() and torch.cuda.is_available()) else None
+        self._resident = None
 
     def __len__(self) -> int:
         return math.ceil(self.N / self.bs)
 
+    def _iter_device(self, perm: torch.Tensor):
+        from . import ops
+        if self._resident is None:
+            self._resident = ([None if t is None else t.to(self.device, non_blocking=True) for t in self.tensors],
+                              [c.to(self.device, non_blocking=True) for c in self.constants])
+        tensors, constants = self._resident
+        perm_dev = perm.to(self.device, non_blocking=True)
+        for start in range(0, self.N, self.bs):
+            idx = perm_dev[start:start + self.bs]
+            batch = [None if t is None else ops.gather_rows(t, idx) for t in tensors]
+            yield tuple(batch[i] if kind == "t" else constants[i] for kind, i in self.layout)
+
     def __iter__(self):
         perm = torch.randperm(self.N) if self.shuffle else None
+        if self.device is not None:
+            yield from self._iter_device(perm)
+            return
         for start in range(0, self.N, self.bs):
             if perm is None:
                 batch = [None if t is None else t[start:start + self.bs] for t in self.tensors]
@@ -61,10 +82,18 @@ class RowBatchIterable(IterableDataset):
             yield tuple(batch[i] if kind == "t" else self.constants[i] for kind, i in self.layout)
 
 
+def device_loader_enabled() -> bool:
+    """CODES_B200_DEVICE_LOADER=0 restores host batches + H2D per step for training loaders."""
+    import os
+    return os.environ.get("CODES_B200_DEVICE_LOADER", "1") != "0"
+
+
 def make_loader(dataset: IterableDataset, device: str | None, num_workers: int = 0) -> DataLoader:
     """``DataLoader(batch_size=None)``: the dataset already yields whole batches."""
     pin = device is not None and "cuda" in str(device) and torch.cuda.is_available()
     if getattr(dataset, "pin", False) and not getattr(dataset, "shuffle", True):
         pin = False   # base tensors are pinned once and batches are slices of them: no per-batch pin thread
+    if getattr(dataset, "device", None) is not None:
+        pin, num_workers = False, 0   # batches are produced on the device
     return DataLoader(dataset, batch_size=None, num_workers=num_workers, pin_memory=pin,
                       persistent_workers=False)

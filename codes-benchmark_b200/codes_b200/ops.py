@@ -307,6 +307,20 @@ def latent_traj_loss(x_hat: Tensor, x: Tensor, n_timesteps_h: int, kind: str, w0
                             False)[0]
 
 
+# --------------------------------------------------------------------------- batch gather
+def gather_rows(src: Tensor, idx: Tensor) -> Tensor:
+    """src[idx] along dim 0 for a device-resident fp32 dataset (idx: int64 on the same device)."""
+    _require_cuda(src, idx)
+    n_src = src.shape[0]
+    row = src[0].numel() if n_src else 0
+    out = torch.empty((idx.shape[0], *src.shape[1:]), device=src.device, dtype=torch.float32)
+    if idx.shape[0] == 0 or row == 0:
+        return out
+    with torch.cuda.device(src.device):
+        check(lib().cb_gather_rows(_p(src), _p(idx), idx.shape[0], n_src, row, _p(out), _stream(src)), "gather_rows")
+    return out
+
+
 # --------------------------------------------------------------------------- denormalise
 def denormalize(x: Tensor, mode: int, dmin: Tensor | None, dmax: Tensor | None, pow10: bool) -> Tensor:
     _require_cuda(x)

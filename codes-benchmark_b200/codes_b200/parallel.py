@@ -80,3 +80,34 @@ def ensemble_mean_std(member_preds: list[torch.Tensor]) -> tuple[torch.Tensor, t
     (bench_fcts.py:1061-1074 does this in numpy on the host)."""
     stack = torch.stack(member_preds, dim=0)
     return stack.mean(dim=0), stack.std(dim=0, unbiased=True)
+
+
+def ensemble_predict(models, data_loader, leave_log: bool = True):
+    """DeepEnsemble evaluation (bench_fcts.py:1058-1074) with every batch copied to the device ONCE and
+    pushed through all members back to back, instead of one full load + predict pass per member.
+    Returns (member predictions list of (N,T,Q), targets (N,T,Q), mean, std(ddof=1)) on the device."""
+    first = models[0]
+    n_batches = len(data_loader)
+    bufs = None
+    targs = None
+    done = 0
+    with torch.inference_mode():
+        for inputs in first._prefetch_to_device(data_loader):
+            outs = [m(inputs) for m in models]
+            p0, t0 = outs[0]
+            if bufs is None:
+                shape = (p0.shape[0] * n_batches, *p0.shape[1:])
+                bufs = [torch.empty(shape, dtype=p0.dtype, device=p0.device) for _ in models]
+                targs = torch.empty(shape, dtype=p0.dtype, device=p0.device)
+            n = p0.shape[0]
+            for buf, (p, _) in zip(bufs, outs):
+                buf[done:done + n].copy_(p)
+            targs[done:done + n].copy_(t0)
+            done += n
+        if bufs is None:
+            raise RuntimeError("ensemble_predict() called with an empty data loader")
+        shape3 = (-1, first.n_timesteps, first.n_quantities)
+        preds = [m.denormalize(b[:done], leave_log, False).reshape(shape3) for m, b in zip(models, bufs)]
+        targs = first.denormalize(targs[:done], leave_log, False).reshape(shape3)
+        mean, std = ensemble_mean_std(preds)
+    return preds, targs, mean, std

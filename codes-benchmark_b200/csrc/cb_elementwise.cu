@@ -333,6 +333,26 @@ static int tensor_grid_x(const int64_t* sizes, int n) {
   return (int)b;
 }
 
+// --------------------------------------------------------------- batch gather (device-resident loaders)
+// out[i, :] = src[idx[i], :]  -- one warp per output row, 16-byte lanes when the row size allows
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, int64_t n_out,
+                                   int64_t n_src, int row_floats, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t i = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); i < n_out; i += (int64_t)gridDim.x * wpb) {
+    int64_t r = idx[i];
+    r = r < 0 ? 0 : (r >= n_src ? n_src - 1 : r);
+    const float* s = src + r * row_floats;
+    float* d = out + i * row_floats;
+    if ((row_floats & 3) == 0) {
+      for (int c = lane; c < row_floats / 4; c += 32)
+        reinterpret_cast<float4*>(d)[c] = __ldg(reinterpret_cast<const float4*>(s) + c);
+    } else {
+      for (int c = lane; c < row_floats; c += 32) d[c] = __ldg(s + c);
+    }
+  }
+}
+
 // --------------------------------------------------------------- denormalise
 __global__ void denorm_kernel(const float* __restrict__ x, int64_t total, int Q, int mode,
                               const float* __restrict__ dmin, const float* __restrict__ dmax,
@@ -557,6 +577,20 @@ extern "C" int32_t cb_lerp_tensors(float* const* d_p, const float* const* d_z, c
                            nullptr, sizes, n_tensors, [&](const TensorList& tl, dim3 grid) {
     lerp_kernel<<<grid, kThreads, 0, st>>>(tl, w);
   });
+}
+
+extern "C" int32_t cb_gather_rows(const float* d_src, const int64_t* d_idx, int64_t n_out, int64_t n_src,
+                                  int32_t row_floats, float* d_out, void* stream) {
+  CB_CHECK_ARG(n_out >= 0 && n_src >= 1 && row_floats >= 1, "bad gather shape");
+  if (n_out == 0) return CB_OK;
+  CB_CHECK_ARG(d_src && d_idx && d_out, "NULL pointer argument");
+  const int wpb = kThreads / 32;
+  int64_t blocks = (n_out + wpb - 1) / wpb;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  gather_rows_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(d_src, d_idx, n_out, n_src, row_floats, d_out);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
 }
 
 extern "C" int32_t cb_denormalize(const float* d_x, int64_t n_rows, int32_t n_q, int32_t mode,

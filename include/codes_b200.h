@@ -168,6 +168,13 @@ CB_API int32_t cb_denormalize(const float* d_x, int64_t n_rows, int32_t n_q, int
                        const float* d_min, const float* d_max, int32_t pow10, float* d_out,
                        void* stream);
 
+/* ------------------------------------------------------ device-resident loaders */
+/* out[i,:] = src[idx[i],:] (row_floats fp32 per row): the per-batch fancy-index gather of
+ * FCFlatBatchIterable / FlatBatchIterable / FlatSeqBatchIterable (fcnn.py:28-32, don_utils.py:82-84,
+ * utilities.py:47-53) on a dataset that stays in HBM; idx is the epoch permutation slice (int64). */
+CB_API int32_t cb_gather_rows(const float* d_src, const int64_t* d_idx, int64_t n_out, int64_t n_src,
+                              int32_t row_floats, float* d_out, void* stream);
+
 /* ------------------------------------------------- latent ODE integration */
 typedef struct {
   cb_mlp_desc ode;     /* ODE.mlp (latent->width x (ode_layers+1)->latent) */

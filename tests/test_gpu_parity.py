@@ -453,3 +453,50 @@ def test_lnode_fit_runs_and_is_deterministic():
     tr, te, _ = m.prepare_data(d, d[:8], None, np.linspace(0, 1, 16), 16, shuffle=True)
     m.fit(tr, te, epochs=2)
     assert m.n_epochs == 2 and np.isfinite(m.train_loss).all()
+
+
+# ------------------------------------------------------------------ device-resident loaders, ensembles
+def test_device_resident_training_loader_matches_host_loader(monkeypatch):
+    """same permutation stream and batch contents as the host loader (bit-exact gather)."""
+    import codes_b200 as cb
+    d = O.synthetic_dataset(13, 9, 4, seed=3)
+    ts = np.linspace(0, 1, 9)
+    for cls in (cb.FullyConnected, cb.MultiONet, cb.LatentPoly, cb.LatentNeuralODE):
+        m = cls(DEV, 4, 9, 0, None, {})
+        monkeypatch.setenv("CODES_B200_DEVICE_LOADER", "1")
+        dev_loader, _, _ = m.prepare_data(d, None, None, ts, 10, shuffle=True)
+        monkeypatch.setenv("CODES_B200_DEVICE_LOADER", "0")
+        host_loader, _, _ = m.prepare_data(d, None, None, ts, 10, shuffle=True)
+        for epoch in range(2):
+            torch.manual_seed(100 + epoch)
+            a = list(dev_loader)
+            torch.manual_seed(100 + epoch)
+            b = list(host_loader)
+            assert len(a) == len(b) == len(host_loader)
+            for ba, bb in zip(a, b):
+                for xa, xb in zip(ba, bb):
+                    if xa is None:
+                        assert xb is None
+                        continue
+                    assert xa.is_cuda and not xb.is_cuda
+                    assert torch.equal(xa.cpu(), xb)
+
+
+def test_ensemble_predict_equals_member_predicts():
+    import codes_b200 as cb
+    from codes_b200 import parallel
+    d = O.synthetic_dataset(40, 12, 5, seed=8)
+    members = []
+    for i in range(3):
+        torch.manual_seed(42 + i)
+        m = cb.MultiONet(DEV, 5, 12, 0, None, {"hidden_size": 32, "output_factor": 4})
+        m.normalisation = {"mode": "minmax", "min": -3.0, "max": 1.0, "log10_transform": True}
+        members.append(m)
+    _, _, val = members[0].prepare_data(d, None, d, np.linspace(0, 1, 12), 128, shuffle=False)
+    preds, targs, mean, std = parallel.ensemble_predict(members, val, leave_log=True)
+    for m, p in zip(members, preds):
+        pi, ti = m.predict(val, leave_log=True)
+        assert torch.equal(pi, p) and torch.equal(ti, targs)
+    stack = np.stack([t2n(p) for p in preds])
+    np.testing.assert_allclose(t2n(mean), stack.mean(0), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(t2n(std), stack.std(0, ddof=1), rtol=1e-4, atol=1e-6)
