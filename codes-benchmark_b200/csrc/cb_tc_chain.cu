@@ -70,6 +70,7 @@ struct ChainParams {
   int n_layers, n_jobs, final_act;
   float act_param;
   int stages, kb_max, in_mode, out_mode, out_nkb, stage_ld, ostage_in_x;
+  int inplace;                 // wide chains: ONE activation buffer, layers fully serialised (see chain_geometry)
   const float* x;
   float* y;
   long long rows;
@@ -356,7 +357,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
   const uint32_t xbytes = (uint32_t)P.kb_max * kKBlockBytes;
-  const uint32_t X0 = base, X1 = base + xbytes, ST0 = base + 2 * xbytes;
+  const uint32_t X0 = base, X1 = P.inplace ? base : base + xbytes, ST0 = base + (P.inplace ? 1 : 2) * xbytes;
   const uint32_t ctrl_addr = ST0 + (uint32_t)P.stages * kKBlockBytes;
   const Ctrl C = carve_ctrl(ctrl_addr, gbase + (ctrl_addr - base));
   // fp32 output staging (OUT_F32 only): the activation buffer that is idle during the last layer
@@ -442,7 +443,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           // MMAs about to be issued (no self-wait).
           for (int kb = 0; kb < nkb; kb += (pair ? 2 : 1)) {
             const bool two = pair && (kb + 1 < nkb);
-            if (l != 0) wait_counter(C.epi_done, need0 + min((kb + (two ? 1 : 0)) >> 1, last_pc), seen_epi);
+            if (l != 0) wait_counter(C.epi_done, need0 + (P.inplace ? last_pc : min((kb + (two ? 1 : 0)) >> 1, last_pc)), seen_epi);
             CB_TRACE(1, 3, j * 8 + kb);
             int stage_b = stage + 1; uint32_t phase_b = phase;
             if (stage_b == P.stages) { stage_b = 0; phase_b ^= 1; }
@@ -520,6 +521,12 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         const int slot = gj & (kSlots - 1);
         const uint32_t use = (uint32_t)(gj / kSlots);
         if (trole < 4) CB_TRACE(trole, 5, j);
+        if (P.inplace && to_smem) {
+          // the epilogue overwrites the buffer the layer's MMAs read: wait until the LAST chunk of this
+          // layer has been accumulated (tcgen05.commit order => all earlier MMAs have retired too)
+          const int gl = gj + (P.first_job[l] + P.n_chunks[l] - 1 - j);
+          mbar_wait(C.bar_tfull + 8 * (gl & (kSlots - 1)), (uint32_t)(gl / kSlots) & 1);
+        }
         mbar_wait(C.bar_tfull + 8 * slot, use & 1);
         if (trole < 4) CB_TRACE(trole, 6, j);
         tcgen05_fence_after();
@@ -883,7 +890,7 @@ struct cb_tc_chain {
 
 // Geometry of the fused chain.  Both ping-pong buffers, >= 2 weight stages and (OUT_F32) the fp32
 // output staging tile must fit in 227 KiB of shared memory.
-struct ChainGeom { int kb_max, stages, n_jobs, stage_ld, out_nkb, ostage_in_x; size_t smem; bool ok; };
+struct ChainGeom { int kb_max, stages, n_jobs, stage_ld, out_nkb, ostage_in_x, inplace; size_t smem; bool ok; };
 
 static ChainGeom chain_geometry(const cb_mlp_desc* d, int out_mode) {
   ChainGeom g{};
@@ -904,8 +911,27 @@ static ChainGeom chain_geometry(const cb_mlp_desc* d, int out_mode) {
     ostage = (size_t)kTileM * g.stage_ld * sizeof(float);
     if (ostage <= (size_t)g.kb_max * kKBlockBytes) { g.ostage_in_x = 1; ostage = 0; }
   }
-  const long long fixed = 1024 /*align slack*/ + kCtrlBytes + (long long)ostage + 2ll * g.kb_max * kKBlockBytes;
+  long long fixed = 1024 /*align slack*/ + kCtrlBytes + (long long)ostage + 2ll * g.kb_max * kKBlockBytes;
   long long stages = ((long long)kMaxSmem - fixed) / kKBlockBytes;
+  if (stages < 2) {
+    // Wide chain: fall back to ONE activation buffer updated in place.  Every chunk of a layer must then
+    // sit in TMEM at once (<= 4 slots x 128 columns) and the layers run strictly one after the other.
+    int max_chunks = 0;
+    for (int i = 0; i < n; ++i) {
+      const bool hidden_like = (i < n - 1) || out_mode == OUT_BF16_TMA;
+      const int chunks = (round_up(d->dims[i + 1], 16) + kChunkN - 1) / kChunkN;
+      if (hidden_like && chunks > max_chunks) max_chunks = chunks;
+    }
+    if (max_chunks <= kSlots) {
+      if (out_mode == OUT_F32 && g.ostage_in_x) {   // no idle buffer to alias: dedicated staging tile
+        g.ostage_in_x = 0;
+        ostage = (size_t)kTileM * g.stage_ld * sizeof(float);
+      }
+      fixed = 1024 + kCtrlBytes + (long long)ostage + 1ll * g.kb_max * kKBlockBytes;
+      stages = ((long long)kMaxSmem - fixed) / kKBlockBytes;
+      g.inplace = 1;
+    }
+  }
   if (stages > kMaxStages) stages = kMaxStages;
   g.stages = (int)stages;
   g.smem = (size_t)(fixed + (stages > 0 ? stages : 0) * kKBlockBytes);
@@ -950,7 +976,7 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
   P.n_layers = desc->n_layers;
   P.final_act = desc->final_act; P.act_param = desc->act_param;
   P.stages = g.stages; P.kb_max = g.kb_max;
-  P.in_mode = IN_F32; P.out_mode = out_mode; P.out_nkb = g.out_nkb; P.stage_ld = g.stage_ld; P.ostage_in_x = g.ostage_in_x;
+  P.in_mode = IN_F32; P.out_mode = out_mode; P.out_nkb = g.out_nkb; P.stage_ld = g.stage_ld; P.ostage_in_x = g.ostage_in_x; P.inplace = g.inplace;
   pl->ld_out = g.out_nkb * kBlockK;
   int nj = 0;
   for (int i = 0; i < desc->n_layers; ++i) {

@@ -34,6 +34,8 @@ with torch.no_grad():
     run([29] + [128] * 5, "leakyrelu", R, "tc")
     run([5] + [64] * 3 + [29], "relu", R * 4, "tc")
     run([6] + [150] * 5 + [5], "relu", R, "tc")
+    run([11] + [470] * 5 + [10], "elu", R, "tc")
+    run([11] + [470] * 5 + [10], "elu", 65536, "fp32")
     run([29] + [275] * 5, "leakyrelu", 65536, "fp32")
     run([6] + [800] * 8 + [5], "gelu", 65536, "fp32")
 

@@ -45,6 +45,7 @@ def test_host_side_queries_do_not_need_a_gpu():
     # fused tcgen05 chain geometry: 275-wide nets fit, 800-wide ones do not (fp32 FFMA path instead)
     assert L.cb_tc_chain_supported(C.byref(_lib.make_desc([29] + [275] * 5 + [2842], "leakyrelu"))) == 1
     assert L.cb_tc_chain_supported(C.byref(_lib.make_desc([6] + [800] * 8 + [5], "gelu"))) == 0
+    assert L.cb_tc_chain_supported(C.byref(_lib.make_desc([11] + [470] * 5 + [10], "elu"))) == 1   # in-place mode
     b = _lib.make_desc([29] + [275] * 5 + [2842], "leakyrelu")
     t = _lib.make_desc([1] + [275] * 9 + [2842], "leakyrelu")
     assert L.cb_tc_multionet_supported(C.byref(b), C.byref(t), 29) == 1

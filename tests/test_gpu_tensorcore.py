@@ -41,6 +41,11 @@ CHAINS = [
     ([9, 100, 100, 9], "softplus", "identity", 64),
     ([9, 100, 100, 9], "mish", "identity", 64),
     ([9, 100, 100, 9], "sigmoid", "identity", 64),
+    # wide chains: single activation buffer updated in place (FCNN primordial 470x5 ELU, osu2008 493x1 Tanh)
+    ([11, 470, 470, 470, 470, 470, 10], "elu", "identity", 700),
+    ([30, 493, 29], "tanh", "identity", 257),
+    ([6, 511, 511, 5], "gelu", "identity", 129),
+    ([6, 384, 384, 384, 5], "relu", "identity", 1000),
 ]
 
 
