@@ -94,6 +94,15 @@ _SIGNATURES = {
     "cb_tc_multionet_set_weights": (_I32, [_P, _PP, _PP, _PP, _PP, _P]),
     "cb_tc_multionet_forward": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _P]),
     "cb_tc_multionet_forward_timed": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _P, C.POINTER(C.c_float)]),
+    "cb_tc_train_create": (_I32, [C.POINTER(MlpDesc), _I32, _I32, C.POINTER(_P)]),
+    "cb_tc_train_destroy": (None, [_P]),
+    "cb_tc_train_ld": (_I32, [_P, _I32]),
+    "cb_tc_train_saved_bytes": (_I64, [_P, _I64]),
+    "cb_tc_train_scratch_bytes": (_I64, [_P, _I64]),
+    "cb_tc_train_forward": (_I32, [_P, _PP, _PP, _P, _I64, _P, _P, _I64, _P]),
+    "cb_tc_train_backward": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _PP, _PP, _P, _P]),
+    "cb_tc_combine_fwd": (_I32, [_P, _P, _I64, _I32, _I32, _I32, _P, _P]),
+    "cb_tc_combine_bwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P]),
 }
 
 

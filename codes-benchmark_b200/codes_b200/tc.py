@@ -137,3 +137,138 @@ def multionet_forward(model, branch_input, trunk_input, phase_ms=None):
                   "tc_multionet_forward_timed")
             phase_ms[:] = [float(v) for v in ms]
     return y
+
+
+# --------------------------------------------------------------------------- tensor-core training path
+class _TrainPlan:
+    def __init__(self, spec, device, out_bf16):
+        self.handle = C.c_void_p()
+        with torch.cuda.device(device):
+            check(lib().cb_tc_train_create(C.byref(spec.desc), device.index or 0, int(out_bf16),
+                                           C.byref(self.handle)), "tc_train_create")
+        self.ld_out = int(lib().cb_tc_train_ld(self.handle, spec.n_layers))
+        self.scratch = None
+        self._fin = weakref.finalize(self, lib().cb_tc_train_destroy, self.handle)
+
+
+_TRAIN_PLANS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _train_plan(spec, dev, out_bf16):
+    per_spec = _TRAIN_PLANS.setdefault(spec, {})
+    key = (dev.index, bool(out_bf16))
+    plan = per_spec.get(key)
+    if plan is None:
+        plan = per_spec[key] = _TrainPlan(spec, dev, out_bf16)
+    return plan
+
+
+def train_supported(spec) -> bool:
+    """Tensor-core training handles identity / tanh final activations on a tcgen05 device."""
+    return available() and spec.final_act in ("identity", "tanh")
+
+
+class _TcTrainChainFn(torch.autograd.Function):
+    """y = chain(x) with bf16 tensor-core GEMMs in both directions (fp32 accumulate, fp32 gradients)."""
+
+    @staticmethod
+    def forward(ctx, spec, out_bf16, x, *params):
+        n = spec.n_layers
+        weights, biases = params[:n], params[n:]
+        dev = x.device
+        plan = _train_plan(spec, dev, out_bf16)
+        x2 = x.reshape(-1, spec.dims[0])
+        if x2.dtype != torch.float32 or not x2.is_contiguous():
+            x2 = x2.float().contiguous()
+        rows = x2.shape[0]
+        L = lib()
+        with torch.cuda.device(dev):
+            if out_bf16:
+                y = torch.empty((rows, plan.ld_out), device=dev, dtype=torch.bfloat16)
+            else:
+                y = torch.empty((rows, spec.dims[-1]), device=dev, dtype=torch.float32)
+            if rows == 0:
+                ctx.rows = 0
+                return y if out_bf16 else y.reshape(*x.shape[:-1], spec.dims[-1])
+            nbytes = int(L.cb_tc_train_saved_bytes(plan.handle, rows))
+            saved = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            wl, bl = _f32(weights), _f32(biases)
+            check(L.cb_tc_train_forward(plan.handle, ptr_array(wl), ptr_array(bl), C.c_void_p(x2.data_ptr()), rows,
+                                        C.c_void_p(y.data_ptr()), C.c_void_p(saved.data_ptr()), nbytes,
+                                        _stream(dev)), "tc_train_forward")
+        ctx.spec, ctx.plan, ctx.rows, ctx.out_bf16 = spec, plan, rows, out_bf16
+        ctx.x_shape = x.shape
+        ctx.has_bias = [b is not None for b in biases]
+        ctx.w_shapes = [tuple(w.shape) for w in weights]
+        ctx.save_for_backward(saved, y)
+        return y if out_bf16 else y.reshape(*x.shape[:-1], spec.dims[-1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        spec, plan, rows = ctx.spec, ctx.plan, ctx.rows
+        n = spec.n_layers
+        saved, y = ctx.saved_tensors
+        dev = saved.device
+        L = lib()
+        need_dx = ctx.needs_input_grad[2]
+        if ctx.out_bf16:
+            dy2 = dy.contiguous()
+            if dy2.dtype != torch.bfloat16:
+                dy2 = dy2.to(torch.bfloat16)
+        else:
+            dy2 = dy.reshape(rows, spec.dims[-1])
+            if dy2.dtype != torch.float32 or not dy2.is_contiguous():
+                dy2 = dy2.float().contiguous()
+        with torch.cuda.device(dev):
+            dW = [torch.empty(s, device=dev, dtype=torch.float32) for s in ctx.w_shapes]
+            db = [torch.empty(s[0], device=dev, dtype=torch.float32) if hb else None
+                  for s, hb in zip(ctx.w_shapes, ctx.has_bias)]
+            dx = torch.empty((rows, spec.dims[0]), device=dev, dtype=torch.float32) if need_dx else None
+            nbytes = int(L.cb_tc_train_scratch_bytes(plan.handle, rows))
+            if plan.scratch is None or plan.scratch.numel() < nbytes:
+                plan.scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            check(L.cb_tc_train_backward(plan.handle, C.c_void_p(dy2.data_ptr()),
+                                         C.c_void_p(None if ctx.out_bf16 else y.data_ptr()), rows,
+                                         C.c_void_p(saved.data_ptr()), C.c_void_p(plan.scratch.data_ptr()),
+                                         plan.scratch.numel(), ptr_array(dW), ptr_array(db),
+                                         C.c_void_p(None if dx is None else dx.data_ptr()), _stream(dev)),
+                  "tc_train_backward")
+        gx = dx.reshape(ctx.x_shape) if need_dx else None
+        return (None, None, gx, *dW, *db)
+
+
+def train_chain(spec, x, weights, biases, out_bf16: bool = False):
+    """Differentiable y = chain(x) on the tensor cores (training path)."""
+    return _TcTrainChainFn.apply(spec, out_bf16, x, *weights, *biases)
+
+
+class _TcCombineFn(torch.autograd.Function):
+    """MultiONet split scalar product on bf16 (rows, ld) branch / trunk outputs."""
+
+    @staticmethod
+    def forward(ctx, b, t, n_out, q):
+        rows, ld = b.shape
+        y = torch.empty((rows, q), device=b.device, dtype=torch.float32)
+        with torch.cuda.device(b.device):
+            check(lib().cb_tc_combine_fwd(C.c_void_p(b.data_ptr()), C.c_void_p(t.data_ptr()), rows, n_out, q, ld,
+                                          C.c_void_p(y.data_ptr()), _stream(b.device)), "tc_combine_fwd")
+        ctx.save_for_backward(b, t)
+        ctx.n_out, ctx.q = n_out, q
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        b, t = ctx.saved_tensors
+        rows, ld = b.shape
+        dy = dy.float().contiguous()
+        db, dt = torch.empty_like(b), torch.empty_like(t)
+        with torch.cuda.device(b.device):
+            check(lib().cb_tc_combine_bwd(C.c_void_p(b.data_ptr()), C.c_void_p(t.data_ptr()),
+                                          C.c_void_p(dy.data_ptr()), rows, ctx.n_out, ctx.q, ld,
+                                          C.c_void_p(db.data_ptr()), C.c_void_p(dt.data_ptr()),
+                                          _stream(b.device)), "tc_combine_bwd")
+        return db, dt, None, None
+
+
+def combine_bf16(b, t, n_out: int, q: int):
+    return _TcCombineFn.apply(b, t, n_out, q)

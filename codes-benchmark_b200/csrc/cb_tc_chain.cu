@@ -33,22 +33,18 @@
 #include <cstring>
 
 #include "cb_common.cuh"
+#include "cb_tc_ptx.cuh"
 
 namespace cb {
 namespace tc {
 
-constexpr int kTileM = 128;          // rows per CTA tile (UMMA_M)
 constexpr int kChunkN = 128;         // output columns per job (UMMA_N <= 128), one TMEM slot
-constexpr int kBlockK = 64;          // bf16 elements per 128B swizzle row
-constexpr int kUmmaK = 16;
 constexpr int kSlots = 4;            // TMEM slots (4 x 128 = 512 columns)
-constexpr int kKBlockBytes = kTileM * kBlockK * 2;     // 16 KiB: one k-block of A or one B stage
 constexpr int kMaxJobs = 96;
 constexpr int kMaxGroups = 128;      // 32-column groups of the MultiONet output layer (<= 4096 columns)
 constexpr int kMaxStages = 8;
 constexpr int kEpiThreads = 256;   // 8 epilogue warps: two per TMEM lane quarter, splitting the columns
 constexpr int kThreads = 64 + kEpiThreads;
-constexpr int kMaxSmem = 232448;     // 227 KiB
 constexpr int kCtrlBytes = 16 * kMaxStages + 16 * kSlots + 64;
 
 enum { IN_F32 = 0, IN_BF16_TMA = 1 };
@@ -89,183 +85,6 @@ struct FinalParams {
   long long rows;
   int num_tiles;
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
-      "@P1 bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-// contiguous global -> shared bulk copy (the weights are pre-tiled so one stage = one 16 KiB run)
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands, fp32 accumulate, M=128
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// one lane of a converged warp (elect.sync): keeps the surrounding control flow warp-uniform so the
-// descriptor arithmetic stays in uniform registers and tcgen05.mma issues back to back
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xFFFFFFFF;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
-  return pred != 0;
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start>>4 [0,14) | LBO>>4 [16,30) = 0 | SBO>>4 [32,46) = 1024>>4 | version [46,48) = 1 | layout [61,64) = 2
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1 | a,b format BF16 [7,10),[10,13)=1 | K-major A,B |
-// n_dim N>>3 [17,23) | m_dim M>>4 [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void red_shared_add_f32(uint32_t addr, float v) {
-  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ int ld_volatile_shared(const int* p) {
-  int v;
-  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_inc(int* p) {
-  asm volatile("red.release.cta.shared.add.s32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
-}
-// spin until the shared counter reaches `need`; `seen` caches the last observed value so that an
-// already satisfied dependency costs no memory operation at all
-__device__ __forceinline__ void wait_counter(const int* p, int need, int& seen) {
-  if (seen >= need) return;
-  int v;
-  do {
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-  } while (v < need);
-  seen = v;
-}
-// non-blocking probe of an mbarrier phase (result consumed later: lets the probe's latency overlap)
-__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P1;\n\t"
-      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok;
-}
-// byte offset of the 16-byte chunk holding columns [8*col8, 8*col8+8) of row r inside an activation buffer
-__device__ __forceinline__ uint32_t act_chunk_off(int r, int col8) {
-  const int kb = col8 >> 3, kg = col8 & 7;
-  return (uint32_t)(kb * kKBlockBytes + r * 128 + ((kg ^ (r & 7)) << 4));
-}
-
-// Activations of the bf16 path: hardware approximations (MUFU tanh/ex2/lg2) -- their error
-// (~2^-11 relative) is below the bf16 rounding of the value they produce.
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-template <int ACT>
-__device__ __forceinline__ float act_fast(float x, float p) {
-  if constexpr (ACT == CB_ACT_RELU) return fmaxf(x, 0.f);
-  else if constexpr (ACT == CB_ACT_LEAKYRELU || ACT == CB_ACT_PRELU) return (p >= 0.f && p <= 1.f) ? fmaxf(x, p * x) : (x >= 0.f ? x : p * x);
-  else if constexpr (ACT == CB_ACT_TANH) return tanh_fast(x);
-  else if constexpr (ACT == CB_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
-  else if constexpr (ACT == CB_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
-  else if constexpr (ACT == CB_ACT_SILU) return __fdividef(x, 1.f + __expf(-x));
-  else if constexpr (ACT == CB_ACT_SOFTPLUS) return x > 20.f ? x : __logf(1.f + __expf(x));
-  else if constexpr (ACT == CB_ACT_MISH) return x * tanh_fast(x > 20.f ? x : __logf(1.f + __expf(x)));
-  else if constexpr (ACT == CB_ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-x));
-  else return x;
-}
-
-__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
-}
 
 // activation + bf16 pack of `w` (16 or 32) accumulator columns -> next layer's A operand.
 // If the group contains column `ones_col`, that element is overwritten with the constant 1.0 that

@@ -1,0 +1,924 @@
+// Tensor-core TRAINING path of the dense chains (tcgen05 + TMEM + TMA, sm_100a): one persistent,
+// warp-specialised bf16 GEMM kernel with four epilogues serves the forward layer, the data gradient and
+// the weight gradient of every nn.Linear of
+//   FullyConnectedNet (fcnn.py:81-98), BranchNet/TrunkNet (deeponet.py:15-84),
+//   Encoder/Decoder (latent_neural_ode.py:687-742)
+// i.e. what `loss.backward()` (fcnn.py:291, deeponet.py:351, latent_neural_ode.py:219,
+// latent_poly.py:219) runs as cuBLAS sgemm + elementwise kernels in the reference.
+//
+//   forward   H_l  = act(H_{l-1} W_l^T + b_l)       A = H_{l-1} (K-major)   B = W_l   (K-major)
+//   dgrad     dZ_{l-1} = (dZ_l W_l) * act'(.)       A = dZ_l    (K-major)   B = W_l^T (K-major, packed copy)
+//   wgrad     dW_l = dZ_l^T H_{l-1}, db_l           A = dZ_l    (MN-major)  B = H_{l-1} (MN-major)
+//
+// Activations live in HBM/L2 as bf16 (rows, ld) matrices, ld = round_up(width + 1, 64); column `width`
+// holds the constant 1.0 that multiplies the bias column of the packed weights, so the bias add is part
+// of the forward GEMM and db is column `K` of the weight-gradient GEMM.  The weight gradient is
+// split over the batch rows (one (tile, split) work item per CTA); the fp32 partial tiles are reduced in
+// a fixed order by wgrad_reduce_kernel -> deterministic gradients (cf. run_training.py:35).
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 tcgen05.mma issuer (+ TMEM alloc), warps 2-9
+// epilogue (two warps per TMEM lane quarter, alternating 64-column blocks).  Tile = 128 rows x up to 256
+// columns (one tcgen05.mma N), k-block = 64; 4 stages of (16 KiB A + 32 KiB B); two 256-column fp32
+// accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.  bf16 outputs leave
+// through a swizzled staging buffer + TMA store, fp32 outputs are stored directly.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "cb_common.cuh"
+#include "cb_tc_ptx.cuh"
+
+namespace cb {
+namespace tcg {
+
+using namespace cb::tc;
+
+constexpr int kStageA = 16384;                 // 128 x 64 bf16
+constexpr int kBoxBytes = 8192;                // one 64 x 64 bf16 TMA box = 64 rows of the B operand per k-block
+constexpr int kMaxStages = 6;
+constexpr int kStaging = 16384;                // one 128 x 64 bf16 output block
+constexpr int kNumStaging = 3;                 // ring of output blocks: aux prefetch / compute in place / store drain
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr int kAccCols = 256;                  // TMEM columns per accumulator slot
+constexpr int kCtrl = 256;
+
+enum { EPI_FWD_BF16 = 0, EPI_FWD_F32 = 1, EPI_DGRAD_BF16 = 2, EPI_DGRAD_F32 = 3, EPI_WGRAD = 4 };
+enum { AUX_NONE = 0, AUX_H = 1, AUX_Z = 2 };
+
+struct GemmParams {
+  CUtensorMap tmA, tmB;        // operand loads
+  CUtensorMap tmOut, tmOut2;   // bf16 stores: activation (or gradient) / pre-activation
+  CUtensorMap tmAux;           // dgrad: h (AUX_H) or z (AUX_Z) of the layer whose pre-activation gradient is produced
+  int m_tiles, n_tiles, n_blocks, splits;
+  int kblocks, kb_per_split, last_nks;
+  int a_mn, b_mn;              // 1: operand is MN-major (reduction index = matrix row), 64 x 64 boxes
+  int b_box_rows;              // K-major B: rows of the TMA box (= widest column tile)
+  int stages, stage_bytes, staging_bytes;
+  int act, save_z, aux_kind, ones_col;
+  float act_param;
+  int n_true;                  // columns >= n_true are padding (forced to zero / not stored)
+  long long m_bound;           // valid output rows
+  float* out_f32;              // fp32 outputs (EPI_*_F32: (m_bound, n_true) dense; EPI_WGRAD: partials)
+  long long ld_out_f32, partial_stride;
+};
+
+struct Item { int m_tile, n_blk0, n_nblk, kb0, kb1, split; };
+
+__device__ __forceinline__ Item decode_item(const GemmParams& P, int item) {
+  Item it;
+  const int tiles = P.m_tiles * P.n_tiles;
+  it.split = item / tiles;
+  const int t = item - it.split * tiles;
+  it.m_tile = t / P.n_tiles;
+  const int nt = t - it.m_tile * P.n_tiles;
+  const int base = P.n_blocks / P.n_tiles, rem = P.n_blocks - base * P.n_tiles;
+  it.n_nblk = base + (nt < rem ? 1 : 0);
+  it.n_blk0 = nt * base + (nt < rem ? nt : rem);
+  it.kb0 = it.split * P.kb_per_split;
+  it.kb1 = min(P.kblocks, it.kb0 + P.kb_per_split);
+  return it;
+}
+
+// MN-major SWIZZLE_128B descriptor: 64-element MN groups (one TMA box each) kBoxBytes apart (LBO),
+// 8-row k groups 1024 B apart (SBO).  cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in uint128.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(kBoxBytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc_mn(int n, int a_mn, int b_mn) {
+  return make_idesc(n) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16);
+}
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// f = act(v) over one thread's 32 accumulator columns (straight-line code per activation)
+template <int ACT>
+__device__ __forceinline__ void act_block(const uint32_t (&v)[32], float (&f)[32], float p) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = act_fast<ACT>(__uint_as_float(v[i]), p);
+}
+__device__ __forceinline__ void act_block_rt(int act, const uint32_t (&v)[32], float (&f)[32], float p) {
+  switch (act) {
+    case CB_ACT_RELU: act_block<CB_ACT_RELU>(v, f, p); break;
+    case CB_ACT_LEAKYRELU:
+    case CB_ACT_PRELU: act_block<CB_ACT_LEAKYRELU>(v, f, p); break;
+    case CB_ACT_TANH: act_block<CB_ACT_TANH>(v, f, p); break;
+    case CB_ACT_GELU: act_block<CB_ACT_GELU>(v, f, p); break;
+    case CB_ACT_ELU: act_block<CB_ACT_ELU>(v, f, p); break;
+    case CB_ACT_SILU: act_block<CB_ACT_SILU>(v, f, p); break;
+    case CB_ACT_SOFTPLUS: act_block<CB_ACT_SOFTPLUS>(v, f, p); break;
+    case CB_ACT_MISH: act_block<CB_ACT_MISH>(v, f, p); break;
+    case CB_ACT_SIGMOID: act_block<CB_ACT_SIGMOID>(v, f, p); break;
+    default: act_block<CB_ACT_IDENTITY>(v, f, p); break;
+  }
+}
+// act'(.) from the saved activation h = act(z) (FROM_Z = false) or from the saved pre-activation z
+template <int ACT, bool FROM_Z>
+__device__ __forceinline__ float dact(float a, float p) {
+  if constexpr (FROM_Z) {
+    if constexpr (ACT == CB_ACT_GELU)
+      return 0.5f * (1.f + erff(a * 0.70710678118654752440f)) + a * __expf(-0.5f * a * a) * 0.39894228040143267794f;
+    else if constexpr (ACT == CB_ACT_SILU) { const float s = __fdividef(1.f, 1.f + __expf(-a)); return s * (1.f + a * (1.f - s)); }
+    else if constexpr (ACT == CB_ACT_MISH) {
+      const float sp = a > 20.f ? a : __logf(1.f + __expf(a)), t = tanh_fast(sp);
+      const float s = a > 20.f ? 1.f : __fdividef(1.f, 1.f + __expf(-a));
+      return t + a * (1.f - t * t) * s;
+    } else return a >= 0.f ? 1.f : p;   // leaky / prelu with a negative slope
+  } else {
+    if constexpr (ACT == CB_ACT_RELU) return a > 0.f ? 1.f : 0.f;
+    else if constexpr (ACT == CB_ACT_LEAKYRELU) return a > 0.f ? 1.f : p;
+    else if constexpr (ACT == CB_ACT_TANH) return 1.f - a * a;
+    else if constexpr (ACT == CB_ACT_ELU) return a > 0.f ? 1.f : a + 1.f;
+    else if constexpr (ACT == CB_ACT_SOFTPLUS) return 1.f - __expf(-a);
+    else if constexpr (ACT == CB_ACT_SIGMOID) return a * (1.f - a);
+    else return 1.f;
+  }
+}
+template <int ACT, bool FROM_Z>
+__device__ __forceinline__ void dact_block(const uint32_t (&v)[32], const uint32_t (&aw)[16], float (&f)[32], float p) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    f[2 * i] = __uint_as_float(v[2 * i]) * dact<ACT, FROM_Z>(bf16_lo(aw[i]), p);
+    f[2 * i + 1] = __uint_as_float(v[2 * i + 1]) * dact<ACT, FROM_Z>(bf16_hi(aw[i]), p);
+  }
+}
+__device__ __forceinline__ void dact_block_rt(int act, int aux_kind, const uint32_t (&v)[32], const uint32_t (&aw)[16],
+                                              float (&f)[32], float p) {
+  switch (act) {
+    case CB_ACT_RELU: dact_block<CB_ACT_RELU, false>(v, aw, f, p); break;
+    case CB_ACT_LEAKYRELU:
+    case CB_ACT_PRELU:
+      if (aux_kind == AUX_Z) dact_block<CB_ACT_LEAKYRELU, true>(v, aw, f, p);
+      else dact_block<CB_ACT_LEAKYRELU, false>(v, aw, f, p);
+      break;
+    case CB_ACT_TANH: dact_block<CB_ACT_TANH, false>(v, aw, f, p); break;
+    case CB_ACT_GELU: dact_block<CB_ACT_GELU, true>(v, aw, f, p); break;
+    case CB_ACT_ELU: dact_block<CB_ACT_ELU, false>(v, aw, f, p); break;
+    case CB_ACT_SILU: dact_block<CB_ACT_SILU, true>(v, aw, f, p); break;
+    case CB_ACT_SOFTPLUS: dact_block<CB_ACT_SOFTPLUS, false>(v, aw, f, p); break;
+    case CB_ACT_MISH: dact_block<CB_ACT_MISH, true>(v, aw, f, p); break;
+    case CB_ACT_SIGMOID: dact_block<CB_ACT_SIGMOID, false>(v, aw, f, p); break;
+    default: dact_block<CB_ACT_IDENTITY, false>(v, aw, f, p); break;
+  }
+}
+
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read_le(int n) {
+  if (n == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (n == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t OST = base + P.stages * P.stage_bytes;       // staging ring (48 KiB; absent for EPI_WGRAD)
+  const uint32_t ctrl = OST + P.staging_bytes;
+  const uint32_t bar_full = ctrl, bar_empty = ctrl + 8 * kMaxStages, bar_tfull = ctrl + 16 * kMaxStages,
+                 bar_tempty = bar_tfull + 16, bar_aux = bar_tfull + 32;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(gbase + (ctrl - base) + 16 * kMaxStages + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, kEpiThreads); }
+    for (int s = 0; s < kNumStaging; ++s) mbar_init(bar_aux + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
+  const int n_items = P.m_tiles * P.n_tiles * P.splits;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    int stage = 0; uint32_t phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item it = decode_item(P, item);
+      const uint32_t bytes = (uint32_t)kStageA + (P.b_mn ? (uint32_t)it.n_nblk * kBoxBytes : (uint32_t)P.b_box_rows * 128u);
+      for (int kb = it.kb0; kb < it.kb1; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (elect_one()) {
+          const uint32_t sa = base + stage * P.stage_bytes, sb = sa + kStageA, full = bar_full + 8 * stage;
+          mbar_arrive_expect_tx(full, bytes);
+          if (P.a_mn) {
+            tma_load_2d(sa, &P.tmA, it.m_tile * kTileM, kb * kBlockK, full);
+            tma_load_2d(sa + kBoxBytes, &P.tmA, it.m_tile * kTileM + 64, kb * kBlockK, full);
+          } else {
+            tma_load_2d(sa, &P.tmA, kb * kBlockK, it.m_tile * kTileM, full);
+          }
+          if (P.b_mn) {
+            for (int g = 0; g < it.n_nblk; ++g)
+              tma_load_2d(sb + g * kBoxBytes, &P.tmB, (it.n_blk0 + g) * 64, kb * kBlockK, full);
+          } else {
+            tma_load_2d(sb, &P.tmB, kb * kBlockK, it.n_blk0 * 64, full);
+          }
+        }
+        __syncwarp();
+        if (++stage == P.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    int stage = 0; uint32_t phase = 0;
+    int li = 0;
+    // descriptor increments per 16-element k-step, in 16-byte units: K-major +32 B, MN-major +16 rows x 128 B
+    const uint64_t a_step = P.a_mn ? 128u : 2u, b_step = P.b_mn ? 128u : 2u;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+      const Item it = decode_item(P, item);
+      const int slot = li & 1;
+      mbar_wait(bar_tempty + 8 * slot, ((uint32_t)(li >> 1) & 1) ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)slot * kAccCols;
+      const uint32_t idesc = make_idesc_mn(it.n_nblk * 64, P.a_mn, P.b_mn);
+      for (int kb = it.kb0; kb < it.kb1; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tcgen05_fence_after();
+        const uint32_t sa = base + stage * P.stage_bytes, sb = sa + kStageA;
+        const uint64_t adesc = P.a_mn ? make_smem_desc_mn(sa) : make_smem_desc(sa);
+        const uint64_t bdesc = P.b_mn ? make_smem_desc_mn(sb) : make_smem_desc(sb);
+        const int nks = (kb == P.kblocks - 1) ? P.last_nks : 4;
+        if (elect_one()) {
+          umma_bf16(d_tmem, adesc, bdesc, idesc, kb != it.kb0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 1; ks < 4; ++ks)
+            if (ks < nks) umma_bf16(d_tmem, adesc + a_step * ks, bdesc + b_step * ks, idesc, 1u);
+          umma_commit(bar_empty + 8 * stage);
+        }
+        __syncwarp();
+        if (++stage == P.stages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(bar_tfull + 8 * slot);
+      __syncwarp();
+    }
+  } else {
+    // ============================================================ epilogue warps (2..9)
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int r = q * 32 + lane;            // row inside the tile
+    const int h = (warp - 2) >> 2;          // column half: columns [32h, 32h+32) of every 64-column block
+    const int et = threadIdx.x - 64;        // 0..255
+    const bool leader = et == 0;
+    constexpr bool kStaged = MODE == EPI_FWD_BF16 || MODE == EPI_DGRAD_BF16;
+    const bool has_aux = MODE == EPI_DGRAD_BF16 && P.aux_kind != AUX_NONE;
+    int gb = 0;                              // staging-ring position (one per bf16 block stored)
+    int li = 0;
+    if (has_aux && leader && (int)blockIdx.x < n_items) {
+      const Item it0 = decode_item(P, blockIdx.x);
+      mbar_arrive_expect_tx(bar_aux, kStaging);
+      tma_load_2d(OST, &P.tmAux, it0.n_blk0 * 64, it0.m_tile * kTileM, bar_aux);
+    }
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+      const Item it = decode_item(P, item);
+      const int slot = li & 1;
+      mbar_wait(bar_tfull + 8 * slot, (uint32_t)(li >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * kAccCols;
+      const long long row_g = (long long)it.m_tile * kTileM + r;
+      for (int cb = 0; cb < it.n_nblk; ++cb) {
+        const int col_blk = (it.n_blk0 + cb) * 64;          // first global output column of this block
+        const int col0 = col_blk + h * 32;                  // first column owned by this thread
+        uint32_t v[32];
+        tmem_ld32(taddr + cb * 64 + h * 32, v);
+        if constexpr (kStaged) {
+          const int buf = gb % kNumStaging;
+          const uint32_t ost = OST + buf * kStaging;
+          if (leader) {
+            // ring slot (gb+1) was last read by the store issued two blocks ago
+            tma_store_wait_read_le(1);
+            if (has_aux) {
+              // prefetch the aux block of the NEXT output block into the next ring slot
+              int nm = it.m_tile, nc = col_blk + 64;
+              bool more = true;
+              if (cb + 1 == it.n_nblk) {
+                more = item + (int)gridDim.x < n_items;
+                if (more) { const Item nx = decode_item(P, item + gridDim.x); nm = nx.m_tile; nc = nx.n_blk0 * 64; }
+              }
+              if (more) {
+                const int nb = (gb + 1) % kNumStaging;
+                mbar_arrive_expect_tx(bar_aux + 8 * nb, kStaging);
+                tma_load_2d(OST + nb * kStaging, &P.tmAux, nc, nm * kTileM, bar_aux + 8 * nb);
+              }
+            }
+          }
+          float f[32];
+          if constexpr (MODE == EPI_DGRAD_BF16) {
+            if (has_aux) {
+              uint32_t aw[16];
+              mbar_wait(bar_aux + 8 * buf, (uint32_t)(gb / kNumStaging) & 1);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int c8 = h * 4 + g;
+                ld_shared_v4(ost + (uint32_t)(r * 128 + ((c8 ^ (r & 7)) << 4)), aw[g * 4], aw[g * 4 + 1], aw[g * 4 + 2],
+                             aw[g * 4 + 3]);
+              }
+              tmem_ld_wait();
+              dact_block_rt(P.act, P.aux_kind, v, aw, f, P.act_param);
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            }
+          } else {
+            tmem_ld_wait();
+            act_block_rt(P.act, v, f, P.act_param);
+          }
+          const int n_pass = (MODE == EPI_FWD_BF16 && P.save_z) ? 2 : 1;
+          for (int pass = 0; pass < n_pass; ++pass) {
+            const int pbuf = (gb + pass) % kNumStaging;
+            const uint32_t pst = OST + pbuf * kStaging;
+            if (pass == 1) {
+              if (leader) tma_store_wait_read_le(1);
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            const bool edge = col0 + 32 > P.n_true;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float val = pass == 0 ? f[g * 8 + i] : __uint_as_float(v[g * 8 + i]);
+                if (edge) {
+                  const int col = col0 + g * 8 + i;
+                  if (col >= P.n_true) val = (pass == 0 && col == P.ones_col) ? 1.f : 0.f;
+                }
+                o[i] = val;
+              }
+              const int c8 = h * 4 + g;
+              st_shared_v4(pst + (uint32_t)(r * 128 + ((c8 ^ (r & 7)) << 4)), pack_bf16(o[0], o[1]),
+                           pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            }
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (leader) {
+              tma_store_2d(pass == 0 ? &P.tmOut : &P.tmOut2, pst, col_blk, it.m_tile * kTileM);
+              tma_store_commit();
+            }
+          }
+          gb += n_pass;
+        } else if constexpr (MODE == EPI_WGRAD) {
+          tmem_ld_wait();
+          if (row_g < P.m_bound) {
+            float* op = P.out_f32 + (long long)it.split * P.partial_stride + row_g * P.ld_out_f32 + col0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<uint4*>(op + g * 4) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          }
+        } else {
+          // fp32 (m_bound, n_true) output: transpose through shared memory, then coalesced row segments
+          tmem_ld_wait();
+          const bool tanh_out = (MODE == EPI_FWD_F32) && P.act == CB_ACT_TANH;
+          constexpr int kLd = 65;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float z = __uint_as_float(v[i]);
+            st_shared_f32(OST + (uint32_t)((r * kLd + h * 32 + i) * 4), tanh_out ? tanhf(z) : z);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const int c = et & 63;
+          if (col_blk + c < P.n_true) {
+            for (int rr = et >> 6; rr < kTileM; rr += 4) {
+              const long long rg = (long long)it.m_tile * kTileM + rr;
+              if (rg < P.m_bound) P.out_f32[rg * P.ld_out_f32 + col_blk + c] = ld_shared_f32(OST + (uint32_t)((rr * kLd + c) * 4));
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(bar_tempty + 8 * slot);
+    }
+    if constexpr (kStaged) {
+      // the bulk stores must be complete before the kernel's writes are consumed / shared memory is released
+      if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------- helper kernels (HBM-bound)
+// fp32 (rows, K) -> bf16 (rows, ld): [x, 1, 0...]  (layer-0 operand with the bias column)
+__global__ void pack_rows_kernel(const float* __restrict__ x, long long rows, int K, int ld, int ones_col,
+                                 __nv_bfloat16* __restrict__ out) {
+  const long long total = rows * (ld / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (ld / 8);
+    const int c0 = (int)(i % (ld / 8)) * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      f[j] = c < K ? x[r * K + c] : (c == ones_col ? 1.f : 0.f);
+    }
+    *reinterpret_cast<uint4*>(out + r * ld + c0) =
+        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+  }
+}
+
+// dZ_last = dy * final_act'(y): fp32 (rows, N) -> bf16 (rows, ld), padding zero.  final_act is identity or tanh.
+__global__ void pack_dy_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long rows, int N,
+                               int ld, int tanh_out, __nv_bfloat16* __restrict__ out) {
+  const long long total = rows * (ld / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (ld / 8);
+    const int c0 = (int)(i % (ld / 8)) * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      float g = 0.f;
+      if (c < N) {
+        g = dy[r * N + c];
+        if (tanh_out) { const float t = y[r * N + c]; g *= 1.f - t * t; }
+      }
+      f[j] = g;
+    }
+    *reinterpret_cast<uint4*>(out + r * ld + c0) =
+        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+  }
+}
+
+// fp32 nn.Linear weight (N,K) + bias -> bf16 Wp (rows_alloc, ldK) = [W | b | 0] and its transpose
+// Wt (ldK_rows, ldN) = W^T (no bias row: the ones column carries no gradient).
+__global__ void pack_weight_pair_kernel(const float* __restrict__ W, const float* __restrict__ b, int N, int K,
+                                        int wp_rows, int ldK, int wt_rows, int ldN,
+                                        __nv_bfloat16* __restrict__ Wp, __nv_bfloat16* __restrict__ Wt) {
+  const long long n_wp = (long long)wp_rows * ldK, n_wt = (long long)wt_rows * ldN;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_wp + n_wt;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_wp) {
+      const int n = (int)(i / ldK), k = (int)(i % ldK);
+      float v = 0.f;
+      if (n < N) v = k < K ? W[(long long)n * K + k] : (k == K && b ? b[n] : 0.f);
+      Wp[i] = __float2bfloat16(v);
+    } else {
+      const long long j = i - n_wp;
+      const int k = (int)(j / ldN), n = (int)(j % ldN);
+      Wt[j] = __float2bfloat16((k < K && n < N) ? W[(long long)n * K + k] : 0.f);
+    }
+  }
+}
+
+// dW[n,k] = sum_s partial[s][n][k] (k < K), db[n] = sum_s partial[s][n][K]; fixed summation order.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, long long stride, int N, int K,
+                                    int ld, float* __restrict__ dW, float* __restrict__ db) {
+  const long long total = (long long)N * (K + 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / (K + 1)), k = (int)(i % (K + 1));
+    const float* p = part + (long long)n * ld + k;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += p[s * stride];
+    if (k < K) dW[(long long)n * K + k] = acc;
+    else if (db) db[n] = acc;
+  }
+}
+
+// MultiONet combine on the bf16 last-layer outputs (deeponet.py:245-253):
+//   y[r,q] = sum_{k in split_q} B[r,k] T[r,k]; one warp per row.
+__global__ void combine_bf16_fwd_kernel(const __nv_bfloat16* __restrict__ B, const __nv_bfloat16* __restrict__ T,
+                                        long long rows, int n_out, int Q, int ld, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int seg_base = n_out / Q, seg_rem = n_out % Q;
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
+       r += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const __nv_bfloat16* b = B + r * ld;
+    const __nv_bfloat16* t = T + r * ld;
+    int start = 0;
+    for (int q = 0; q < Q; ++q) {
+      const int sz = seg_base + (q < seg_rem ? 1 : 0);
+      float acc = 0.f;
+      for (int k = start + lane; k < start + sz; k += 32) acc += __bfloat162float(b[k]) * __bfloat162float(t[k]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) y[r * Q + q] = acc;
+      start += sz;
+    }
+  }
+}
+// dB[r,k] = dy[r,q(k)] T[r,k], dT[r,k] = dy[r,q(k)] B[r,k]; padding columns (>= n_out) are written as zero.
+__global__ void combine_bf16_bwd_kernel(const __nv_bfloat16* __restrict__ B, const __nv_bfloat16* __restrict__ T,
+                                        const float* __restrict__ dy, long long rows, int n_out, int Q, int ld,
+                                        __nv_bfloat16* __restrict__ dB, __nv_bfloat16* __restrict__ dT) {
+  const int seg_base = n_out / Q, seg_rem = n_out % Q;
+  const int big = seg_rem * (seg_base + 1);     // columns covered by the (seg_base+1)-wide splits
+  const long long total = rows * (ld / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (ld / 8);
+    const int c0 = (int)(i % (ld / 8)) * 8;
+    const uint4 bv = *reinterpret_cast<const uint4*>(B + r * ld + c0);
+    const uint4 tv = *reinterpret_cast<const uint4*>(T + r * ld + c0);
+    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w}, tw[4] = {tv.x, tv.y, tv.z, tv.w};
+    uint32_t ob[4], ot[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gb[2], gt[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = c0 + 2 * j + e;
+        float g = 0.f;
+        if (c < n_out) {
+          const int q = c < big ? c / (seg_base + 1) : seg_rem + (c - big) / seg_base;
+          g = dy[r * Q + q];
+        }
+        const float bb = e ? bf16_hi(bw[j]) : bf16_lo(bw[j]);
+        const float tt = e ? bf16_hi(tw[j]) : bf16_lo(tw[j]);
+        gb[e] = c < n_out ? g * tt : 0.f;
+        gt[e] = c < n_out ? g * bb : 0.f;
+      }
+      ob[j] = pack_bf16(gb[0], gb[1]);
+      ot[j] = pack_bf16(gt[0], gt[1]);
+    }
+    *reinterpret_cast<uint4*>(dB + r * ld + c0) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+    *reinterpret_cast<uint4*>(dT + r * ld + c0) = make_uint4(ot[0], ot[1], ot[2], ot[3]);
+  }
+}
+
+}  // namespace tcg
+}  // namespace cb
+
+using namespace cb;
+using namespace cb::tc;
+using namespace cb::tcg;
+
+static int round_up_i(int v, int m) { return (v + m - 1) / m * m; }
+static long long round_up_ll(long long v, long long m) { return (v + m - 1) / m * m; }
+static int ew_blocks(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---------------------------------------------------------------------------- single GEMM launch
+struct GemmCall {
+  int mode;
+  const __nv_bfloat16* A; long long a_rows, a_cols, a_ld; int a_mn;
+  const __nv_bfloat16* B; long long b_rows, b_cols, b_ld; int b_mn;
+  long long m_out;         // output rows (GEMM M)
+  int n_out_ld;            // output columns, padded to a multiple of 64
+  int n_true;              // true output columns
+  long long k_total;       // reduction length actually needed (true, unpadded)
+  __nv_bfloat16* out_bf16; long long out_rows, out_ld;
+  __nv_bfloat16* out2_bf16;
+  float* out_f32; long long ld_out_f32;
+  int act; float act_param; int ones_col; int aux_kind;
+  const __nv_bfloat16* aux; long long ld_aux;
+  int splits;              // wgrad only
+  long long partial_stride;
+};
+
+template <int MODE>
+static cudaError_t set_smem_attr() {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (done_dev == dev) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  if (e == cudaSuccess) done_dev = dev;
+  return e;
+}
+
+static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_blocks = c.n_out_ld / 64;
+  P.n_tiles = (P.n_blocks + 3) / 4;
+  P.m_tiles = (int)((c.m_out + kTileM - 1) / kTileM);
+  P.kblocks = (int)((c.k_total + kBlockK - 1) / kBlockK);
+  const int ksteps = (int)((c.k_total + kUmmaK - 1) / kUmmaK);
+  P.last_nks = ksteps - (P.kblocks - 1) * 4;
+  P.splits = c.splits > 0 ? c.splits : 1;
+  P.kb_per_split = (P.kblocks + P.splits - 1) / P.splits;
+  P.splits = (P.kblocks + P.kb_per_split - 1) / P.kb_per_split;
+  P.a_mn = c.a_mn; P.b_mn = c.b_mn;
+  const int widest = (P.n_blocks + P.n_tiles - 1) / P.n_tiles;
+  P.b_box_rows = widest * 64;
+  P.stage_bytes = kStageA + widest * kBoxBytes;
+  P.staging_bytes = c.mode == EPI_WGRAD ? 0 : kNumStaging * kStaging;
+  P.stages = (kMaxSmem - 1024 - P.staging_bytes - kCtrl) / P.stage_bytes;
+  if (P.stages > kMaxStages) P.stages = kMaxStages;
+  const size_t smem = 1024 + (size_t)P.stages * P.stage_bytes + P.staging_bytes + kCtrl;
+  P.act = c.act; P.act_param = c.act_param; P.ones_col = c.ones_col; P.aux_kind = c.aux_kind;
+  P.save_z = c.out2_bf16 != nullptr;
+  P.n_true = c.n_true; P.m_bound = c.m_out;
+  P.out_f32 = c.out_f32; P.ld_out_f32 = c.ld_out_f32; P.partial_stride = c.partial_stride;
+  CB_CHECK_ARG(P.kblocks >= 1 && P.m_tiles >= 1 && P.n_blocks >= 1 && P.stages >= 2, "empty GEMM");
+  bool ok = true;
+  if (c.a_mn) ok = ok && encode_bf16_box(&P.tmA, c.A, c.a_rows, c.a_cols, c.a_ld, 64, 64);
+  else ok = ok && encode_bf16_box(&P.tmA, c.A, c.a_rows, c.a_cols, c.a_ld, 64, kTileM);
+  if (c.b_mn) ok = ok && encode_bf16_box(&P.tmB, c.B, c.b_rows, c.b_cols, c.b_ld, 64, 64);
+  else ok = ok && encode_bf16_box(&P.tmB, c.B, c.b_rows, c.b_cols, c.b_ld, 64, P.b_box_rows);
+  if (c.out_bf16) ok = ok && encode_bf16_box(&P.tmOut, c.out_bf16, c.out_rows, c.out_ld, c.out_ld, 64, kTileM);
+  if (c.out2_bf16) ok = ok && encode_bf16_box(&P.tmOut2, c.out2_bf16, c.out_rows, c.out_ld, c.out_ld, 64, kTileM);
+  if (c.aux_kind != AUX_NONE) ok = ok && encode_bf16_box(&P.tmAux, c.aux, c.out_rows, c.ld_aux, c.ld_aux, 64, kTileM);
+  CB_CHECK_ARG(ok, "cuTensorMapEncodeTiled failed for a GEMM operand");
+  const long long items = (long long)P.m_tiles * P.n_tiles * P.splits;
+  const int grid = (int)(items < num_sms() ? items : num_sms());
+  switch (c.mode) {
+    case EPI_FWD_BF16:
+      CB_CUDA(set_smem_attr<EPI_FWD_BF16>());
+      gemm_kernel<EPI_FWD_BF16><<<grid, kThreads, smem, st>>>(P); break;
+    case EPI_FWD_F32:
+      CB_CUDA(set_smem_attr<EPI_FWD_F32>());
+      gemm_kernel<EPI_FWD_F32><<<grid, kThreads, smem, st>>>(P); break;
+    case EPI_DGRAD_BF16:
+      CB_CUDA(set_smem_attr<EPI_DGRAD_BF16>());
+      gemm_kernel<EPI_DGRAD_BF16><<<grid, kThreads, smem, st>>>(P); break;
+    case EPI_DGRAD_F32:
+      CB_CUDA(set_smem_attr<EPI_DGRAD_F32>());
+      gemm_kernel<EPI_DGRAD_F32><<<grid, kThreads, smem, st>>>(P); break;
+    default:
+      CB_CUDA(set_smem_attr<EPI_WGRAD>());
+      gemm_kernel<EPI_WGRAD><<<grid, kThreads, smem, st>>>(P); break;
+  }
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+// ---------------------------------------------------------------------------- training plan
+static bool act_needs_z(int act, float p) {
+  return act == CB_ACT_GELU || act == CB_ACT_SILU || act == CB_ACT_MISH ||
+         ((act == CB_ACT_LEAKYRELU || act == CB_ACT_PRELU) && p < 0.f);
+}
+
+struct cb_tc_train {
+  cb_mlp_desc desc;
+  int device;
+  int out_bf16;                 // last layer leaves as bf16 (rows, ld[n]) instead of fp32 (rows, dims[n])
+  int n;
+  int ld[CB_MAX_LAYERS + 1];    // padded widths of the bf16 activations: round_up(dims[i] + 1, 64)
+  int needs_z;
+  __nv_bfloat16* wp[CB_MAX_LAYERS];   // (wp_rows, ld[i])    [W | b | 0]
+  __nv_bfloat16* wt[CB_MAX_LAYERS];   // (wt_rows, ld[i+1])  W^T
+  int wp_rows[CB_MAX_LAYERS], wt_rows[CB_MAX_LAYERS];
+};
+
+extern "C" void cb_tc_train_destroy(cb_tc_train* p) {
+  if (!p) return;
+  for (int i = 0; i < CB_MAX_LAYERS; ++i) {
+    if (p->wp[i]) cudaFree(p->wp[i]);
+    if (p->wt[i]) cudaFree(p->wt[i]);
+  }
+  delete p;
+}
+
+extern "C" int32_t cb_tc_train_create(const cb_mlp_desc* desc, int32_t device, int32_t out_bf16, cb_tc_train** out) {
+  if (int32_t e = check_desc(desc)) return e;
+  CB_CHECK_ARG(out != nullptr, "out is NULL");
+  CB_CHECK_ARG(desc->final_act == CB_ACT_IDENTITY || (desc->final_act == CB_ACT_TANH && !out_bf16),
+               "final activation must be identity (or tanh with fp32 output)");
+  CB_CHECK_ARG(tensor_map_encoder() != nullptr, "cuTensorMapEncodeTiled unavailable");
+  CB_CUDA(cudaSetDevice(device));
+  cb_tc_train* p = new cb_tc_train();
+  memset(p, 0, sizeof(*p));
+  p->desc = *desc; p->device = device; p->out_bf16 = out_bf16; p->n = desc->n_layers;
+  p->needs_z = act_needs_z(desc->act, desc->act_param) ? 1 : 0;
+  for (int i = 0; i <= p->n; ++i) p->ld[i] = round_up_i(desc->dims[i] + 1, 64);
+  for (int i = 0; i < p->n; ++i) {
+    // rows padded so that every TMA box of a weight operand stays inside the allocation
+    p->wp_rows[i] = round_up_i(p->ld[i + 1], 256);
+    p->wt_rows[i] = round_up_i(p->ld[i], 256);
+    if (cudaMalloc(&p->wp[i], (size_t)p->wp_rows[i] * p->ld[i] * 2) != cudaSuccess ||
+        cudaMalloc(&p->wt[i], (size_t)p->wt_rows[i] * p->ld[i + 1] * 2) != cudaSuccess) {
+      cb_tc_train_destroy(p);
+      set_error("cudaMalloc of the bf16 weight copies failed");
+      return CB_ERR_CUDA;
+    }
+  }
+  *out = p;
+  return CB_OK;
+}
+
+static long long rows_pad(long long rows) { return round_up_ll(rows, kTileM); }
+
+// Layout of the saved-activation buffer: H_0 (packed input), H_1 .. H_{n-1} [, Z_1 .. Z_{n-1}] [, H_n when out_bf16]
+static long long saved_offset(const cb_tc_train* p, long long rows, int i, int z) {
+  const long long rp = rows_pad(rows);
+  long long off = 0;
+  for (int j = 0; j < p->n; ++j) { if (!z && j == i) return off; off += rp * p->ld[j] * 2; }
+  if (p->needs_z)
+    for (int j = 1; j < p->n; ++j) { if (z && j == i) return off; off += rp * p->ld[j] * 2; }
+  return off;
+}
+
+extern "C" int64_t cb_tc_train_saved_bytes(const cb_tc_train* p, int64_t rows) {
+  if (!p || rows < 0) return -1;
+  return saved_offset(p, rows, -1, 0) + 256;
+}
+
+static int wgrad_splits(const cb_tc_train* p, int i, long long rows) {
+  const int m_tiles = (p->desc.dims[i + 1] + kTileM - 1) / kTileM;
+  const int n_tiles = (p->ld[i] / 64 + 3) / 4;
+  const int kblocks = (int)((rows + kBlockK - 1) / kBlockK);
+  int s = num_sms() / (m_tiles * n_tiles);
+  if (s < 1) s = 1;
+  if (s > kblocks) s = kblocks;
+  return s;
+}
+
+extern "C" int64_t cb_tc_train_scratch_bytes(const cb_tc_train* p, int64_t rows) {
+  if (!p || rows < 0) return -1;
+  const long long rp = rows_pad(rows);
+  int ld_max = 0;
+  long long part = 0;
+  for (int i = 0; i <= p->n; ++i) ld_max = p->ld[i] > ld_max ? p->ld[i] : ld_max;
+  for (int i = 0; i < p->n; ++i) {
+    const long long b = (long long)wgrad_splits(p, i, rows) * p->desc.dims[i + 1] * p->ld[i] * 4;
+    part = b > part ? b : part;
+  }
+  return 2 * rp * ld_max * 2 + part + 512;
+}
+
+// y = chain(x), saving the bf16 activations for cb_tc_train_backward.
+extern "C" int32_t cb_tc_train_forward(cb_tc_train* p, const float* const* d_W, const float* const* d_b,
+                                       const float* d_x, int64_t rows, void* d_y, void* d_saved,
+                                       int64_t saved_bytes, void* stream) {
+  CB_CHECK_ARG(p && d_W && d_b, "NULL pointer argument");
+  CB_CHECK_ARG(rows >= 0, "rows < 0");
+  if (rows == 0) return CB_OK;
+  CB_CHECK_ARG(d_x && d_y && d_saved, "NULL pointer argument");
+  CB_CHECK_ARG(((uintptr_t)d_saved & 255) == 0, "saved buffer must be 256-byte aligned");
+  if (saved_bytes < cb_tc_train_saved_bytes(p, rows)) { set_error("saved buffer too small"); return CB_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = p->n;
+  const long long rp = rows_pad(rows);
+  uint8_t* sv = reinterpret_cast<uint8_t*>(d_saved);
+  for (int i = 0; i < n; ++i) {
+    CB_CHECK_ARG(d_W[i] != nullptr, "weight %d is NULL", i);
+    const long long total = (long long)p->wp_rows[i] * p->ld[i] + (long long)p->wt_rows[i] * p->ld[i + 1];
+    pack_weight_pair_kernel<<<ew_blocks(total), 256, 0, st>>>(d_W[i], d_b[i], p->desc.dims[i + 1], p->desc.dims[i],
+                                                           p->wp_rows[i], p->ld[i], p->wt_rows[i], p->ld[i + 1],
+                                                           p->wp[i], p->wt[i]);
+    CB_LAUNCH_CHECK();
+  }
+  __nv_bfloat16* h0 = reinterpret_cast<__nv_bfloat16*>(sv + saved_offset(p, rows, 0, 0));
+  pack_rows_kernel<<<ew_blocks(rows * (p->ld[0] / 8)), 256, 0, st>>>(d_x, rows, p->desc.dims[0], p->ld[0],
+                                                                   p->desc.dims[0], h0);
+  CB_LAUNCH_CHECK();
+  for (int i = 0; i < n; ++i) {
+    const bool last = i == n - 1;
+    GemmCall c;
+    memset(&c, 0, sizeof(c));
+    c.A = reinterpret_cast<__nv_bfloat16*>(sv + saved_offset(p, rows, i, 0));
+    c.a_rows = rows; c.a_cols = p->ld[i]; c.a_ld = p->ld[i];
+    c.B = p->wp[i]; c.b_rows = p->wp_rows[i]; c.b_cols = p->ld[i]; c.b_ld = p->ld[i];
+    c.m_out = rows; c.k_total = p->desc.dims[i] + 1;
+    c.n_true = p->desc.dims[i + 1];
+    c.act_param = p->desc.act_param;
+    if (last && !p->out_bf16) {
+      c.mode = EPI_FWD_F32;
+      c.n_out_ld = round_up_i(c.n_true, 64);
+      c.out_f32 = reinterpret_cast<float*>(d_y); c.ld_out_f32 = c.n_true;
+      c.act = p->desc.final_act;
+    } else {
+      c.mode = EPI_FWD_BF16;
+      c.n_out_ld = p->ld[i + 1];
+      c.out_bf16 = last ? reinterpret_cast<__nv_bfloat16*>(d_y)
+                        : reinterpret_cast<__nv_bfloat16*>(sv + saved_offset(p, rows, i + 1, 0));
+      c.out_rows = rows; c.out_ld = p->ld[i + 1];
+      c.act = last ? CB_ACT_IDENTITY : p->desc.act;
+      c.ones_col = last ? -1 : c.n_true;
+      if (!last && p->needs_z) c.out2_bf16 = reinterpret_cast<__nv_bfloat16*>(sv + saved_offset(p, rows, i + 1, 1));
+    }
+    if (int32_t e = launch_gemm(c, st)) return e;
+  }
+  (void)rp;
+  return CB_OK;
+}
+
+// Gradients of the chain.  d_dy: fp32 (rows, dims[n]) (or bf16 (rows, ld[n]) with zero padding when the
+// plan was created with out_bf16); d_y: the fp32 forward output (needed for a tanh final activation).
+// d_dW[i] (out,in) / d_db[i] (out) are overwritten; d_dx (rows, dims[0]) fp32 may be NULL.
+extern "C" int32_t cb_tc_train_backward(cb_tc_train* p, const void* d_dy, const float* d_y, int64_t rows,
+                                        const void* d_saved, void* d_scratch, int64_t scratch_bytes,
+                                        float* const* d_dW, float* const* d_db, float* d_dx, void* stream) {
+  CB_CHECK_ARG(p && d_dW && d_db, "NULL pointer argument");
+  CB_CHECK_ARG(rows > 0, "rows must be positive");
+  CB_CHECK_ARG(d_dy && d_saved && d_scratch, "NULL pointer argument");
+  CB_CHECK_ARG(((uintptr_t)d_scratch & 255) == 0, "scratch buffer must be 256-byte aligned");
+  if (scratch_bytes < cb_tc_train_scratch_bytes(p, rows)) { set_error("scratch buffer too small"); return CB_ERR_WORKSPACE; }
+  CB_CHECK_ARG(p->desc.final_act != CB_ACT_TANH || d_y != nullptr, "tanh output needs y for the backward pass");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = p->n;
+  const long long rp = rows_pad(rows);
+  int ld_max = 0;
+  for (int i = 0; i <= n; ++i) ld_max = p->ld[i] > ld_max ? p->ld[i] : ld_max;
+  const uint8_t* sv = reinterpret_cast<const uint8_t*>(d_saved);
+  __nv_bfloat16* dz[2] = {reinterpret_cast<__nv_bfloat16*>(d_scratch),
+                          reinterpret_cast<__nv_bfloat16*>(d_scratch) + rp * ld_max};
+  float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d_scratch) + 2 * rp * ld_max * 2 + 256);
+  const __nv_bfloat16* cur;
+  int pp = 0;
+  if (p->out_bf16) {
+    cur = reinterpret_cast<const __nv_bfloat16*>(d_dy);
+  } else {
+    pack_dy_kernel<<<ew_blocks(rows * (p->ld[n] / 8)), 256, 0, st>>>(reinterpret_cast<const float*>(d_dy), d_y, rows,
+                                                                   p->desc.dims[n], p->ld[n],
+                                                                   p->desc.final_act == CB_ACT_TANH ? 1 : 0, dz[0]);
+    CB_LAUNCH_CHECK();
+    cur = dz[0];
+    pp = 1;
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    const int N = p->desc.dims[i + 1], K = p->desc.dims[i];
+    const __nv_bfloat16* hin = reinterpret_cast<const __nv_bfloat16*>(sv + saved_offset(p, rows, i, 0));
+    {
+      // weight gradient: dW = dZ^T [H | 1]
+      GemmCall c;
+      memset(&c, 0, sizeof(c));
+      c.mode = EPI_WGRAD;
+      c.A = cur; c.a_rows = rows; c.a_cols = p->ld[i + 1]; c.a_ld = p->ld[i + 1]; c.a_mn = 1;
+      c.B = hin; c.b_rows = rows; c.b_cols = p->ld[i]; c.b_ld = p->ld[i]; c.b_mn = 1;
+      c.m_out = N; c.n_out_ld = p->ld[i]; c.n_true = K + 1; c.k_total = rows;
+      c.splits = wgrad_splits(p, i, rows);
+      c.out_f32 = part; c.ld_out_f32 = p->ld[i]; c.partial_stride = (long long)N * p->ld[i];
+      if (int32_t e = launch_gemm(c, st)) return e;
+      const int kb = (int)((rows + kBlockK - 1) / kBlockK);
+      const int per = (kb + c.splits - 1) / c.splits;
+      const int splits = (kb + per - 1) / per;
+      CB_CHECK_ARG(d_dW[i] != nullptr, "dW[%d] is NULL", i);
+      wgrad_reduce_kernel<<<ew_blocks((long long)N * (K + 1)), 256, 0, st>>>(part, splits, c.partial_stride, N, K,
+                                                                            p->ld[i], d_dW[i], d_db[i]);
+      CB_LAUNCH_CHECK();
+    }
+    if (i == 0 && !d_dx) break;
+    {
+      // data gradient: dZ_{i-1} = (dZ_i W_i) * act'(.)   (i == 0: dx, fp32, no activation)
+      GemmCall c;
+      memset(&c, 0, sizeof(c));
+      c.A = cur; c.a_rows = rows; c.a_cols = p->ld[i + 1]; c.a_ld = p->ld[i + 1];
+      c.B = p->wt[i]; c.b_rows = p->wt_rows[i]; c.b_cols = p->ld[i + 1]; c.b_ld = p->ld[i + 1];
+      c.m_out = rows; c.k_total = N; c.n_true = K;
+      c.act = p->desc.act; c.act_param = p->desc.act_param; c.ones_col = -1;
+      if (i == 0) {
+        c.mode = EPI_DGRAD_F32;
+        c.n_out_ld = round_up_i(K, 64);
+        c.out_f32 = d_dx; c.ld_out_f32 = K;
+      } else {
+        c.mode = EPI_DGRAD_BF16;
+        c.n_out_ld = p->ld[i];
+        c.out_bf16 = dz[pp]; c.out_rows = rows; c.out_ld = p->ld[i];
+        c.aux_kind = p->desc.act == CB_ACT_IDENTITY ? AUX_NONE : (p->needs_z ? AUX_Z : AUX_H);
+        c.aux = reinterpret_cast<const __nv_bfloat16*>(sv + saved_offset(p, rows, i, p->needs_z));
+        c.ld_aux = p->ld[i];
+      }
+      if (int32_t e = launch_gemm(c, st)) return e;
+      cur = dz[pp];
+      pp ^= 1;
+    }
+  }
+  return CB_OK;
+}
+
+// ---------------------------------------------------------------------------- MultiONet combine (bf16)
+extern "C" int32_t cb_tc_combine_fwd(const void* d_B, const void* d_T, int64_t rows, int32_t n_out, int32_t Q,
+                                     int32_t ld, float* d_y, void* stream) {
+  CB_CHECK_ARG(rows >= 0 && n_out >= Q && Q >= 1 && ld >= n_out && ld % 8 == 0, "bad combine shape");
+  if (rows == 0) return CB_OK;
+  CB_CHECK_ARG(d_B && d_T && d_y, "NULL pointer argument");
+  long long blocks = (rows + 7) / 8;
+  if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+  combine_bf16_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_B), reinterpret_cast<const __nv_bfloat16*>(d_T), rows, n_out, Q, ld, d_y);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int32_t cb_tc_combine_bwd(const void* d_B, const void* d_T, const float* d_dy, int64_t rows,
+                                     int32_t n_out, int32_t Q, int32_t ld, void* d_dB, void* d_dT, void* stream) {
+  CB_CHECK_ARG(rows >= 0 && n_out >= Q && Q >= 1 && ld >= n_out && ld % 8 == 0, "bad combine shape");
+  if (rows == 0) return CB_OK;
+  CB_CHECK_ARG(d_B && d_T && d_dy && d_dB && d_dT, "NULL pointer argument");
+  combine_bf16_bwd_kernel<<<ew_blocks(rows * (ld / 8)), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_B), reinterpret_cast<const __nv_bfloat16*>(d_T), d_dy, rows, n_out, Q, ld,
+      reinterpret_cast<__nv_bfloat16*>(d_dB), reinterpret_cast<__nv_bfloat16*>(d_dT));
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int32_t cb_tc_train_ld(const cb_tc_train* p, int32_t layer) {
+  if (!p || layer < 0 || layer > p->n) return -1;
+  return p->ld[layer];
+}

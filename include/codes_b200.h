@@ -264,6 +264,38 @@ CB_API int32_t cb_tc_multionet_forward_timed(cb_tc_multionet* plan, const float*
                                              void* d_workspace, int64_t workspace_bytes, void* stream,
                                              float* phase_ms);
 
+/* ------------------------------------------- tensor-core (bf16) TRAINING path */
+/* Forward + backward of a dense chain on tcgen05 (bf16 operands, fp32 accumulate), one GEMM launch per
+ * layer and direction: replaces loss.backward() through nn.Linear / activations (fcnn.py:291,
+ * deeponet.py:351, latent_neural_ode.py:219, latent_poly.py:219) when the precision mode allows bf16.
+ * The plan owns bf16 copies of the weights ([W|b] and W^T), refreshed by every forward call.
+ * out_bf16 != 0: the last layer (identity activation) is written as bf16 (rows, cb_tc_train_ld(plan,n))
+ * and the incoming gradient has the same layout (MultiONet branch / trunk outputs). */
+typedef struct cb_tc_train cb_tc_train;
+CB_API int32_t cb_tc_train_create(const cb_mlp_desc* desc, int32_t device, int32_t out_bf16, cb_tc_train** out);
+CB_API void cb_tc_train_destroy(cb_tc_train* plan);
+/* padded width (elements) of the bf16 activation matrix entering layer `layer` (layer == n: the output). */
+CB_API int32_t cb_tc_train_ld(const cb_tc_train* plan, int32_t layer);
+/* bytes of the saved-activation buffer (forward -> backward) and of the backward scratch. */
+CB_API int64_t cb_tc_train_saved_bytes(const cb_tc_train* plan, int64_t rows);
+CB_API int64_t cb_tc_train_scratch_bytes(const cb_tc_train* plan, int64_t rows);
+/* y = chain(x): x fp32 (rows, dims[0]); y fp32 (rows, dims[n]) or bf16 (rows, ld_n). */
+CB_API int32_t cb_tc_train_forward(cb_tc_train* plan, const float* const* d_W, const float* const* d_b,
+                                   const float* d_x, int64_t rows, void* d_y, void* d_saved,
+                                   int64_t saved_bytes, void* stream);
+/* d_dW[i] (out,in) / d_db[i] (out) fp32 are OVERWRITTEN (deterministic split reduction); d_dx may be
+ * NULL; d_y (the fp32 forward output) is only read for a tanh final activation. */
+CB_API int32_t cb_tc_train_backward(cb_tc_train* plan, const void* d_dy, const float* d_y, int64_t rows,
+                                    const void* d_saved, void* d_scratch, int64_t scratch_bytes,
+                                    float* const* d_dW, float* const* d_db, float* d_dx, void* stream);
+/* MultiONet split scalar product on the bf16 last-layer outputs and its gradient
+ * (deeponet.py:245-253): B,T,dB,dT bf16 (rows, ld); y, dy fp32 (rows, Q). */
+CB_API int32_t cb_tc_combine_fwd(const void* d_B, const void* d_T, int64_t rows, int32_t n_outputs,
+                                 int32_t n_quantities, int32_t ld, float* d_y, void* stream);
+CB_API int32_t cb_tc_combine_bwd(const void* d_B, const void* d_T, const float* d_dy, int64_t rows,
+                                 int32_t n_outputs, int32_t n_quantities, int32_t ld, void* d_dB,
+                                 void* d_dT, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
