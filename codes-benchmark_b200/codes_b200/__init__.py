@@ -16,7 +16,7 @@ from .latent_common import Decoder, Encoder
 from .latent_neural_ode import ODE, LatentNeuralODE, ModelWrapper
 from .latent_poly import LatentPoly, Polynomial, PolynomialModelWrapper
 from .loaders import RowBatchIterable
-from .ops import precision_mode, set_precision
+from .ops import precision_mode, set_precision, set_train_precision, train_precision_mode
 from . import parallel, train  # noqa: E402,F401  (host-side sharding / task orchestration)
 
 surrogate_classes = [MultiONet, FullyConnected, LatentNeuralODE, LatentPoly]
@@ -26,7 +26,8 @@ __all__ = [
     "OperatorNetwork", "FullyConnected", "FullyConnectedNet", "LatentNeuralODE", "ModelWrapper", "ODE",
     "Encoder", "Decoder", "LatentPoly", "Polynomial", "PolynomialModelWrapper", "RowBatchIterable",
     "AbstractSurrogateBaseConfig", "FCNNBaseConfig", "MultiONetBaseConfig", "LatentNeuralODEBaseConfig",
-    "LatentPolynomialBaseConfig", "precision_mode", "set_precision",
+    "LatentPolynomialBaseConfig", "precision_mode", "set_precision", "set_train_precision",
+    "train_precision_mode",
 ]
 
 

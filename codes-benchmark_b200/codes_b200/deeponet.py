@@ -103,6 +103,9 @@ class MultiONet(OperatorNetwork):
         fused = ops.try_fused_multionet(self, branch_input, trunk_input)
         if fused is not None:
             return fused, targets
+        y = ops.try_tc_multionet_training(self, branch_input, trunk_input)
+        if y is not None:
+            return y, targets
         b = self.branch_net(branch_input)
         t = self.trunk_net(trunk_input)
         return ops.deeponet_combine(b, t, self.N), targets

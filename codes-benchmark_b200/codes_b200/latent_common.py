@@ -31,7 +31,7 @@ class _Coder(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         w, b = ops.sequential_params(self.mlp)
-        return ops.run_chain(self.chain(), x, w, b)
+        return ops.run_chain(self.chain(), x, w, b, tc_train=False)
 
 
 class Encoder(_Coder):

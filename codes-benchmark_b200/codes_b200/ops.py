@@ -432,15 +432,66 @@ def set_precision(mode: str) -> None:
     _PRECISION["mode"] = mode
 
 
-def run_chain(spec: ChainSpec, x: Tensor, weights, biases) -> Tensor:
-    """Dispatch a dense chain: tensor-core path for gradient-free calls in bf16 mode,
-    fp32 FFMA path otherwise."""
+_TRAIN_PRECISION = {"mode": None}
+TC_TRAIN_MIN_ROWS = 2048   # below this a chain is launch-bound: the fp32 path is as fast and exact
+
+
+def train_precision_mode() -> str:
+    """Arithmetic of the FullyConnected / MultiONet chains when gradients are needed: 'bf16'
+    (default: tcgen05 GEMMs in forward, dgrad and wgrad; fp32 accumulate, fp32 master weights,
+    gradients and optimizer state; loss curves track the fp32 mode within 1 %, see
+    tests/test_gpu_tc_training.py) or 'fp32' (FFMA kernels, exact mode).  Selected by
+    ``set_train_precision`` / ``CODES_B200_TRAIN_PRECISION``; ``set_precision('fp32')`` always wins."""
+    import os
+    if _TRAIN_PRECISION["mode"] is None:
+        _TRAIN_PRECISION["mode"] = os.environ.get("CODES_B200_TRAIN_PRECISION", "bf16").lower()
+    return "fp32" if precision_mode() == "fp32" else _TRAIN_PRECISION["mode"]
+
+
+def set_train_precision(mode: str) -> None:
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("train precision must be 'fp32' or 'bf16'")
+    _TRAIN_PRECISION["mode"] = mode
+
+
+def _use_tc_training(spec: ChainSpec, x: Tensor) -> bool:
+    if train_precision_mode() != "bf16" or x.numel() // max(spec.dims[0], 1) < TC_TRAIN_MIN_ROWS:
+        return False
+    from . import tc
+    return tc.train_supported(spec)
+
+
+def run_chain(spec: ChainSpec, x: Tensor, weights, biases, tc_train: bool = True) -> Tensor:
+    """Dispatch a dense chain: tensor-core inference path for gradient-free calls in bf16 mode,
+    tensor-core training path when gradients are needed and the training precision is bf16,
+    fp32 FFMA path otherwise.  ``tc_train=False`` pins the differentiable path to fp32 (the latent
+    models' coders: their outputs feed finite-difference loss terms that amplify bf16 rounding by
+    1/h^2 = n_timesteps^2, latent_neural_ode.py:560-604)."""
     needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in weights))
     if not needs_grad and precision_mode() == "bf16":
         from . import tc
         if tc.supported(spec):
             return tc.chain_forward(spec, x, weights, biases)
+    if needs_grad and tc_train and _use_tc_training(spec, x):
+        from . import tc
+        return tc.train_chain(spec, x, weights, biases)
     return mlp_chain(spec, x, weights, biases)
+
+
+def try_tc_multionet_training(model, branch_input: Tensor, trunk_input: Tensor):
+    """MultiONet forward for training on the tensor cores: both nets as bf16 GEMM chains whose
+    last layers stay bf16 (rows, ld), combined by the bf16 split scalar product; or None."""
+    if not (torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())):
+        return None
+    bspec, tspec = model.branch_net.chain(), model.trunk_net.chain()
+    if not (_use_tc_training(bspec, branch_input) and _use_tc_training(tspec, trunk_input)):
+        return None
+    from . import tc
+    bw, bb = sequential_params(model.branch_net.network)
+    tw, tb = sequential_params(model.trunk_net.network)
+    b = tc.train_chain(bspec, branch_input, bw, bb, out_bf16=True)
+    t = tc.train_chain(tspec, trunk_input, tw, tb, out_bf16=True)
+    return tc.combine_bf16(b, t, bspec.dims[-1], model.N)
 
 
 def try_fused_multionet(model, branch_input: Tensor, trunk_input: Tensor):

@@ -28,6 +28,13 @@ def _sizes(tensors):
     return arr
 
 
+def _touch(params) -> None:
+    """The kernels update parameters through raw pointers: bump the tensors' version counters so
+    that caches keyed on them (the bf16 weight copies of the tensor-core plans, codes_b200/tc.py)
+    notice the update, exactly as an in-place torch op would."""
+    torch.autograd.graph.increment_version(list(params))
+
+
 class _FusedBase(Optimizer):
     def _collect(self, group):
         params = [p for p in group["params"] if p.grad is not None]
@@ -74,6 +81,7 @@ class FusedAdamW(_FusedBase):
                                           float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]),
                                           float(group["weight_decay"]), int(group["step"]), _stream(dev)),
                       "adamw_step")
+                _touch(params)
         return loss
 
 
@@ -100,6 +108,7 @@ class FusedSGD(_FusedBase):
                                         ptr_array(bufs) if bufs else None, _sizes(params), len(params),
                                         float(group["lr"]), float(group["momentum"]), float(group["weight_decay"]),
                                         int(group["step"]), _stream(dev)), "sgd_step")
+                _touch(params)
         return loss
 
 
@@ -127,6 +136,7 @@ class _ScheduleFreeBase(_FusedBase):
                     check(lib().cb_lerp_tensors(ptr_array(params), ptr_array([self.state[p]["z"] for p in params]),
                                                 _sizes(params), len(params), float(w), _stream(dev)),
                           "lerp_tensors")
+                    _touch(params)
             group["train_mode"] = to_train
 
     @torch.no_grad()
@@ -182,6 +192,7 @@ class FusedAdamWScheduleFree(_ScheduleFreeBase):
                                                        float(group["eps"]), float(group["weight_decay"]),
                                                        float(ckp1), float(bc2), _stream(dev)),
                       "schedulefree_adamw_step")
+                _touch(params)
             group["k"] += 1
         return loss
 
@@ -216,5 +227,6 @@ class FusedSGDScheduleFree(_ScheduleFreeBase):
                                                      ptr_array(z), _sizes(params), len(params), float(lr_k),
                                                      float(group["momentum"]), float(group["weight_decay"]),
                                                      float(ckp1), _stream(dev)), "schedulefree_sgd_step")
+                _touch(params)
             group["k"] += 1
         return loss
