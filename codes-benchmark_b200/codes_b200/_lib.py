@@ -79,6 +79,7 @@ _SIGNATURES = {
     "cb_lnode_solve_fwd": (_I32, [C.POINTER(LnodeDesc), _PP, _PP, _P, _P, _I64, _I32, _P, _P, _P, _I64,
                                   C.POINTER(LnodeTape), _P]),
     "cb_lnode_bwd_workspace_floats": (_I64, [C.POINTER(LnodeDesc), _I64]),
+    "cb_lnode_bwd_supported": (_I32, [C.POINTER(LnodeDesc), _I32]),
     "cb_lnode_solve_bwd": (_I32, [C.POINTER(LnodeDesc), _PP, _PP, _P, _I64, _I32, C.POINTER(LnodeTape), _P, _P, _PP,
                                   _PP, _P, _P, _I64, _P]),
     "cb_tc_supported": (_I32, []),

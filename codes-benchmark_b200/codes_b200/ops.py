@@ -508,6 +508,9 @@ def try_fused_multionet(model, branch_input: Tensor, trunk_input: Tensor):
 
 
 # --------------------------------------------------------------------------- latent ODE (autograd wrapper)
+FORCE_WIDE_LNODE_BACKWARD = False   # tests: run the level-synchronous sweep on a net the kernel also handles
+
+
 class _LnodeSolveFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, wrapper, spec: ChainSpec, z0: Tensor, t_eval: Tensor, reg_factor: Tensor, *params: Tensor):
@@ -534,9 +537,27 @@ class _LnodeSolveFn(torch.autograd.Function):
         if int(tape[0].min()) < 0:
             raise RuntimeError(f"latent ODE backward: a trajectory needed more than {TAPE_CAP} accepted steps "
                                "(tape overflow) or did not finish")
-        dz0, dW, db, dreg = lnode_solve_backward(ctx.spec, params[:n], params[n:], t_eval, tape, dz,
-                                                 cfg.ode_tanh_reg, ctx.reg, cfg.rtol, cfg.atol)
-        return (None, None, dz0, None, dreg if cfg.ode_tanh_reg else None, *dW, *db)
+        d = _lnode_desc(ctx.spec, cfg.ode_tanh_reg, ctx.reg, cfg.rtol, cfg.atol, 1)
+        if not FORCE_WIDE_LNODE_BACKWARD and lib().cb_lnode_bwd_supported(C.byref(d), int(t_eval.shape[0])):
+            dz0, dW, db, dreg = lnode_solve_backward(ctx.spec, params[:n], params[n:], t_eval, tape, dz,
+                                                     cfg.ode_tanh_reg, ctx.reg, cfg.rtol, cfg.atol)
+            return (None, None, dz0, None, dreg if cfg.ode_tanh_reg else None, *dW, *db)
+        # wide ODE net: level-synchronous discrete adjoint over the same tape (lnode_wide.py)
+        from . import lnode_wide
+        spec = ctx.spec
+        leaves = [p.detach().clone().requires_grad_(True) for p in params]
+        reg_leaf = torch.tensor(ctx.reg, device=dz.device, dtype=torch.float32, requires_grad=True)
+
+        def rhs(z64):
+            out = mlp_chain(spec, z64.to(torch.float32), leaves[:n], leaves[n:])
+            if cfg.ode_tanh_reg:
+                out = reg_leaf * torch.tanh(out / reg_leaf)
+            return out.to(torch.float64)
+
+        wide_params = leaves + ([reg_leaf] if cfg.ode_tanh_reg else [])
+        dz0, grads = lnode_wide.solve_backward(rhs, wide_params, t_eval, tape, dz)
+        dreg = grads[-1] if cfg.ode_tanh_reg else None
+        return (None, None, dz0, None, dreg, *grads[:2 * n])
 
 
 def lnode_integrate(wrapper, spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor) -> Tensor:

@@ -790,6 +790,19 @@ extern "C" int64_t cb_lnode_bwd_workspace_floats(const cb_lnode_desc* desc, int6
   return (int64_t)P.total_w + P.total_b + 64 + n_cta * slab;
 }
 
+// 1 when the persistent backward-sweep kernel can hold the per-step activations of this ODE net in shared
+// memory; wide nets (e.g. the primordial config: 480 x 8 Linears) use the level-synchronous host sweep.
+extern "C" int32_t cb_lnode_bwd_supported(const cb_lnode_desc* desc, int32_t n_t) {
+  LnodeParams P;
+  if (build_params(desc, n_t, P) != CB_OK) return 0;
+  int dev = 0, max_smem = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+    max_smem = 232448;
+  P.weights_in_smem = 0;
+  return lnode_bwd_smem_bytes(P) <= (size_t)max_smem ? 1 : 0;
+}
+
 extern "C" int32_t cb_lnode_solve_bwd(const cb_lnode_desc* desc, const float* const* d_W, const float* const* d_b,
                                       const float* d_t_eval, int64_t batch, int32_t n_t, const cb_lnode_tape* tape,
                                       const float* d_g, float* d_dz0, float* const* d_dW, float* const* d_db,

@@ -216,6 +216,9 @@ CB_API int32_t cb_lnode_solve_fwd(const cb_lnode_desc* desc, const float* const*
  * constants, i.e. no gradient through the step-size controller).
  * g:(batch,T,L) = dL/dz_out;  outputs: dz0:(batch,L), dW[i]:(out,in), db[i]:(out), dreg:(1). */
 CB_API int64_t cb_lnode_bwd_workspace_floats(const cb_lnode_desc* desc, int64_t batch);
+/* 1 when cb_lnode_solve_bwd handles this ODE net (per-step activations fit in shared memory); wider
+ * nets are differentiated by the level-synchronous sweep of codes_b200/lnode_wide.py over the same tape. */
+CB_API int32_t cb_lnode_bwd_supported(const cb_lnode_desc* desc, int32_t n_t);
 CB_API int32_t cb_lnode_solve_bwd(const cb_lnode_desc* desc, const float* const* d_W,
                                   const float* const* d_b, const float* d_t_eval, int64_t batch,
                                   int32_t n_t, const cb_lnode_tape* tape, const float* d_g,

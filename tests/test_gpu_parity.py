@@ -424,6 +424,51 @@ def test_lnode_backward_matches_autograd_replay(act_cls, tanh_reg):
         close(m.model.ode.reg_factor.grad.reshape(1), reg.grad.reshape(1), "dreg")
 
 
+@pytest.mark.parametrize("act_cls,tanh_reg", [(nn.SiLU, True), (nn.ReLU, False)])
+def test_lnode_wide_backward_matches_kernel_sweep(act_cls, tanh_reg, monkeypatch):
+    """The level-synchronous sweep used for ODE nets too wide for the persistent backward kernel
+    (codes_b200/lnode_wide.py, primordial config) differentiates the same tape: on a net both handle,
+    its gradients agree with the kernel sweep to 1e-4 of the largest entry; a 480-wide net (kernel path
+    unavailable) produces finite gradients through the same entry point."""
+    import codes_b200 as cb
+    from codes_b200 import ops
+    torch.manual_seed(3)
+    T, Lat, B = 30, 5, 70
+    m = cb.LatentNeuralODE(DEV, 6, T, 0, None, {"latent_features": Lat, "ode_layers": 2, "ode_width": 48,
+                                                 "activation": act_cls(), "ode_tanh_reg": tanh_reg})
+    with torch.no_grad():
+        for p in m.model.ode.mlp.parameters():
+            p.mul_(2.0)
+        m.model.ode.reg_factor.fill_(1.1)
+    g = torch.Generator().manual_seed(8)
+    z0 = (torch.rand(B, Lat, generator=g) * 2 - 1).to(DEV)
+    wgt = torch.randn(B, T, Lat, generator=g).to(DEV)
+    t = torch.linspace(0, 1, T).to(DEV)
+    w, b = ops.sequential_params(m.model.ode.mlp)
+    grads = {}
+    for force in (False, True):
+        monkeypatch.setattr(ops, "FORCE_WIDE_LNODE_BACKWARD", force)
+        m.zero_grad()
+        z0d = z0.clone().requires_grad_()
+        (ops.lnode_integrate(m.model, m.model.ode.chain(), w, b, z0d, t) * wgt).sum().backward()
+        grads[force] = [z0d.grad.clone()] + [p.grad.clone() for p in m.model.ode.parameters() if p.grad is not None]
+    assert len(grads[True]) == len(grads[False])
+    for a, ref in zip(grads[True], grads[False]):
+        scale = max(float(ref.abs().max()), 1e-12)
+        assert float((a - ref).abs().max()) / scale < 1e-4
+    monkeypatch.setattr(ops, "FORCE_WIDE_LNODE_BACKWARD", False)
+    wide = cb.LatentNeuralODE(DEV, 10, T, 0, None, {"latent_features": 9, "ode_layers": 6, "ode_width": 480,
+                                                     "coder_layers": 1, "coder_width": 580, "activation": nn.SiLU(),
+                                                     "ode_tanh_reg": True})
+    d = O.synthetic_dataset(64, T, 10, seed=2)
+    tr, _, _ = wide.prepare_data(d, None, None, np.linspace(0, 1, T), 64, shuffle=False)
+    xp, xt = wide(next(iter(tr)))
+    wide.model.total_loss(xt, xp, None, nn.MSELoss()).backward()
+    for p in wide.parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+    assert float(wide.model.ode.mlp[2].weight.grad.abs().max()) > 0
+
+
 def test_lnode_fit_runs_and_is_deterministic():
     import codes_b200 as cb
     d = O.synthetic_dataset(48, 16, 5, seed=9)
