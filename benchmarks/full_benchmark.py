@@ -93,8 +93,9 @@ def main():
     for task in mine:
         try:
             m = T.train_task(task, config, train, test, ts, dev, PRIMORDIAL[task[0]], info)
+            (sub, _), _ = T.get_data_subset((train, test), ts, task[1], task[2])
+            samples += sub.shape[0] * m.n_epochs
             results.append((T.model_name_for(task), float(m.test_loss[-1]), float(m.fit.duration)))
-            samples += m.n_train_samples * m.n_epochs
         except Exception as e:  # noqa: BLE001  (the reference's worker also records and continues)
             failed.append((T.model_name_for(task), repr(e)))
     torch.cuda.synchronize()

@@ -88,10 +88,14 @@ def bench_flat(name, cls, cfg, Q, T, n_train, n_test, batch_rows, dims_list, ext
         loss.backward()
         opt.step()
 
-    sps = time_train(step, tr, 12)
-    res["train_rows_per_s"] = sps * batch_rows
-    res["train_samples_per_s"] = sps * batch_rows / T
-    res["train_tflops_fp32"] = sps * batch_rows * 3 * flop_row / 1e12
+    # training arithmetic: bf16 = tcgen05 GEMMs for forward / dgrad / wgrad (default), fp32 = FFMA exact mode
+    for mode in ("bf16", "fp32"):
+        cb.set_train_precision(mode)
+        sps = time_train(step, tr, 30 if mode == "bf16" else 8)
+        res[f"train_rows_per_s_{mode}"] = sps * batch_rows
+        res[f"train_samples_per_s_{mode}"] = sps * batch_rows / T
+        res[f"train_tflops_{mode}"] = sps * batch_rows * 3 * flop_row / 1e12
+    cb.set_train_precision("bf16")
     return res, m
 
 

@@ -496,7 +496,18 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
 }
 
 // MultiONet combine on the bf16 last-layer outputs (deeponet.py:245-253):
-//   y[r,q] = sum_{k in split_q} B[r,k] T[r,k]; one warp per row.
+//   y[r,q] = sum_{k in split_q} B[r,k] T[r,k].  One warp per row, one lane per quantity: a lane walks its
+// split with 16-byte loads (the warp as a whole consumes the row's cache lines, so L1 absorbs the stride);
+// fixed summation order -> deterministic.  HBM-bound: 4 * n_out bytes read per row.
+__device__ __forceinline__ float dot8_bf16(uint4 a, uint4 b, float acc) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    acc = fmaf(bf16_lo(aw[i]), bf16_lo(bw[i]), acc);
+    acc = fmaf(bf16_hi(aw[i]), bf16_hi(bw[i]), acc);
+  }
+  return acc;
+}
 __global__ void combine_bf16_fwd_kernel(const __nv_bfloat16* __restrict__ B, const __nv_bfloat16* __restrict__ T,
                                         long long rows, int n_out, int Q, int ld, float* __restrict__ y) {
   const int lane = threadIdx.x & 31;
@@ -505,54 +516,65 @@ __global__ void combine_bf16_fwd_kernel(const __nv_bfloat16* __restrict__ B, con
        r += (long long)gridDim.x * (blockDim.x >> 5)) {
     const __nv_bfloat16* b = B + r * ld;
     const __nv_bfloat16* t = T + r * ld;
-    int start = 0;
-    for (int q = 0; q < Q; ++q) {
-      const int sz = seg_base + (q < seg_rem ? 1 : 0);
+    for (int q = lane; q < Q; q += 32) {
+      int k = q * seg_base + (q < seg_rem ? q : seg_rem);
+      const int end = k + seg_base + (q < seg_rem ? 1 : 0);
       float acc = 0.f;
-      for (int k = start + lane; k < start + sz; k += 32) acc += __bfloat162float(b[k]) * __bfloat162float(t[k]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) y[r * Q + q] = acc;
-      start += sz;
+      for (; k < end && (k & 7); ++k) acc = fmaf(__bfloat162float(b[k]), __bfloat162float(t[k]), acc);
+      for (; k + 8 <= end; k += 8)
+        acc = dot8_bf16(*reinterpret_cast<const uint4*>(b + k), *reinterpret_cast<const uint4*>(t + k), acc);
+      for (; k < end; ++k) acc = fmaf(__bfloat162float(b[k]), __bfloat162float(t[k]), acc);
+      y[r * Q + q] = acc;
     }
   }
 }
 // dB[r,k] = dy[r,q(k)] T[r,k], dT[r,k] = dy[r,q(k)] B[r,k]; padding columns (>= n_out) are written as zero.
+// One thread per 8 columns; the split index is found once per chunk and advanced at the boundaries.
 __global__ void combine_bf16_bwd_kernel(const __nv_bfloat16* __restrict__ B, const __nv_bfloat16* __restrict__ T,
                                         const float* __restrict__ dy, long long rows, int n_out, int Q, int ld,
                                         __nv_bfloat16* __restrict__ dB, __nv_bfloat16* __restrict__ dT) {
   const int seg_base = n_out / Q, seg_rem = n_out % Q;
   const int big = seg_rem * (seg_base + 1);     // columns covered by the (seg_base+1)-wide splits
-  const long long total = rows * (ld / 8);
+  const int chunks = ld / 8;
+  const long long total = rows * chunks;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / (ld / 8);
-    const int c0 = (int)(i % (ld / 8)) * 8;
-    const uint4 bv = *reinterpret_cast<const uint4*>(B + r * ld + c0);
-    const uint4 tv = *reinterpret_cast<const uint4*>(T + r * ld + c0);
-    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w}, tw[4] = {tv.x, tv.y, tv.z, tv.w};
-    uint32_t ob[4], ot[4];
+    const long long r = i / chunks;
+    const int c0 = (int)(i - r * chunks) * 8;
+    uint4 ob = make_uint4(0, 0, 0, 0), ot = make_uint4(0, 0, 0, 0);
+    if (c0 < n_out) {
+      const uint4 bv = *reinterpret_cast<const uint4*>(B + r * ld + c0);
+      const uint4 tv = *reinterpret_cast<const uint4*>(T + r * ld + c0);
+      const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w}, tw[4] = {tv.x, tv.y, tv.z, tv.w};
+      int q = c0 < big ? c0 / (seg_base + 1) : seg_rem + (c0 - big) / seg_base;
+      int end = (q + 1) * seg_base + (q + 1 < seg_rem ? q + 1 : seg_rem);   // first column of split q+1
+      float g = dy[r * Q + q];
+      uint32_t wb[4], wt[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float gb[2], gt[2];
+      for (int j = 0; j < 4; ++j) {
+        float gb[2], gt[2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = c0 + 2 * j + e;
-        float g = 0.f;
-        if (c < n_out) {
-          const int q = c < big ? c / (seg_base + 1) : seg_rem + (c - big) / seg_base;
-          g = dy[r * Q + q];
+        for (int e = 0; e < 2; ++e) {
+          const int c = c0 + 2 * j + e;
+          while (c >= end && q + 1 < Q) {
+            ++q;
+            end += seg_base + (q < seg_rem ? 1 : 0);
+            g = dy[r * Q + q];
+          }
+          const bool ok = c < n_out;
+          const float bb = e ? bf16_hi(bw[j]) : bf16_lo(bw[j]);
+          const float tt = e ? bf16_hi(tw[j]) : bf16_lo(tw[j]);
+          gb[e] = ok ? g * tt : 0.f;
+          gt[e] = ok ? g * bb : 0.f;
         }
-        const float bb = e ? bf16_hi(bw[j]) : bf16_lo(bw[j]);
-        const float tt = e ? bf16_hi(tw[j]) : bf16_lo(tw[j]);
-        gb[e] = c < n_out ? g * tt : 0.f;
-        gt[e] = c < n_out ? g * bb : 0.f;
+        wb[j] = pack_bf16(gb[0], gb[1]);
+        wt[j] = pack_bf16(gt[0], gt[1]);
       }
-      ob[j] = pack_bf16(gb[0], gb[1]);
-      ot[j] = pack_bf16(gt[0], gt[1]);
+      ob = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+      ot = make_uint4(wt[0], wt[1], wt[2], wt[3]);
     }
-    *reinterpret_cast<uint4*>(dB + r * ld + c0) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
-    *reinterpret_cast<uint4*>(dT + r * ld + c0) = make_uint4(ot[0], ot[1], ot[2], ot[3]);
+    *reinterpret_cast<uint4*>(dB + r * ld + c0) = ob;
+    *reinterpret_cast<uint4*>(dT + r * ld + c0) = ot;
   }
 }
 
@@ -911,7 +933,7 @@ extern "C" int32_t cb_tc_combine_bwd(const void* d_B, const void* d_T, const flo
   CB_CHECK_ARG(rows >= 0 && n_out >= Q && Q >= 1 && ld >= n_out && ld % 8 == 0, "bad combine shape");
   if (rows == 0) return CB_OK;
   CB_CHECK_ARG(d_B && d_T && d_dy && d_dB && d_dT, "NULL pointer argument");
-  combine_bf16_bwd_kernel<<<ew_blocks(rows * (ld / 8)), 256, 0, (cudaStream_t)stream>>>(
+  combine_bf16_bwd_kernel<<<(int)((rows * (ld / 8) + 255) / 256 < (long long)num_sms() * 16 ? (rows * (ld / 8) + 255) / 256 : (long long)num_sms() * 16), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(d_B), reinterpret_cast<const __nv_bfloat16*>(d_T), d_dy, rows, n_out, Q, ld,
       reinterpret_cast<__nv_bfloat16*>(d_dB), reinterpret_cast<__nv_bfloat16*>(d_dT));
   CB_LAUNCH_CHECK();
