@@ -253,7 +253,6 @@ def run_ours(args):
 
     # ---- roofline leg (rank 0): per-kernel CUDA-event durations on the launch stream
     roofline = None
-    e2e = None
     cpu_baseline = None
     if rank == 0:
         peak_tf, peak_gbs, peak_src = peaks()
@@ -280,27 +279,76 @@ def run_ours(args):
             "step_achieved": step_tf, "step_frac": step_tf / peak_tf,
         }
 
-        # ---- e2e leg: public API with HOST batches (pinned), H2D + metric D2H inside the timed region
-        n_e2e = 16384
-        de = synthetic_x0(n_e2e, seed=4321)
-        _, _, val_loader = model.prepare_data(de, None, de, np.linspace(0, 1, T), ROWS_PER_STEP, shuffle=False)
-        steps_per_pass = len(val_loader)
-        passes = max(1, int(round(args.steps / steps_per_pass)))
-        for _ in range(3):                        # warm-up passes (allocator pools, copy stream)
-            p, t = model.predict(val_loader)
-            model._l1(p, t)
-        torch.cuda.synchronize()
+    # ---- e2e leg (ALL ranks, weak scaling): public API with HOST batches (pinned), H2D + metric D2H inside
+    # the timed region; aggregate = trajectories of all ranks / slowest rank's wall time between barriers
+    n_e2e = 16384
+    de = synthetic_x0(n_e2e, seed=4321 + rank)
+    _, _, val_loader = model.prepare_data(de, None, de, np.linspace(0, 1, T), ROWS_PER_STEP, shuffle=False)
+    steps_per_pass = len(val_loader)
+    passes = max(12, int(round(args.steps / steps_per_pass)))
+    for _ in range(8):                        # warm-up passes: the side-stream allocator pool of the H2D prefetch
+                                              # needs a few passes to stop growing (pass_ms_rank0 shows the steady state)
+        p, t = model.predict(val_loader)
+        model._l1(p, t)
+    barrier()
+    t0 = time.perf_counter()
+    pass_ms = []
+    for _ in range(passes):
+        tp = time.perf_counter()
+        p, t = model.predict(val_loader)
+        metric = model._l1(p, t)              # .item(): 4-byte D2H, like validate()
+        pass_ms.append(round((time.perf_counter() - tp) * 1e3, 2))
+    torch.cuda.synchronize()
+    dt_e2e = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt_e2e, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * passes * n_e2e / float(dt_e2e.item()), "unit": "trajectories/s",
+           "h2d_bytes_per_step": ROWS_PER_STEP * (Q + 1 + Q) * 4, "d2h_bytes_per_step": 4.0 / steps_per_pass,
+           "api": "MultiONet.predict(val_loader) + L1 metric .item(), every rank on its own shard",
+           "passes": passes, "steps_per_pass": steps_per_pass, "pass_ms_rank0": pass_ms, "l1_metric": metric}
+    del p, t
+
+    # ---- training leg (ALL ranks, independent models = the benchmark's task parallelism): steady-state fit
+    # step (forward, loss, backward, AdamW) of the same MultiONet config, bf16 tensor-core training mode
+    train = None
+    if not args.no_train:
+        tr_model = build_model(device)
+        tr_model.train()
+        n_tr = int(np.ceil(4 * ROWS_PER_STEP / T))
+        tr_loader, _, _ = tr_model.prepare_data(synthetic_x0(n_tr, seed=99 + rank), None, None, np.linspace(0, 1, T),
+                                                ROWS_PER_STEP, shuffle=True)
+        opt, _ = tr_model.setup_optimizer_and_scheduler(100)
+        opt.train()
+        batches = []
+        for bt in tr_loader:
+            batches.append(bt)
+            if len(batches) == 4:
+                break
+
+        def train_step(bt):
+            opt.zero_grad()
+            out, tgt = tr_model(bt)
+            loss = ops.pointwise_loss(out, tgt, "mse")
+            loss.backward()
+            opt.step()
+
+        for i in range(3):
+            train_step(batches[i % len(batches)])
+        barrier()
+        n_train_steps = max(10, min(50, args.steps // 4))
         t0 = time.perf_counter()
-        for _ in range(passes):
-            p, t = model.predict(val_loader)
-            metric = model._l1(p, t)              # .item(): 4-byte D2H, like validate()
+        for i in range(n_train_steps):
+            train_step(batches[i % len(batches)])
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e2e = {"value": passes * n_e2e / dt, "unit": "trajectories/s",
-               "h2d_bytes_per_step": ROWS_PER_STEP * (Q + 1 + Q) * 4, "d2h_bytes_per_step": 4.0 / steps_per_pass,
-               "api": "MultiONet.predict(val_loader) + L1 metric .item()", "passes": passes,
-               "steps_per_pass": steps_per_pass, "l1_metric": metric}
-        del p, t
+        dt_tr = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_tr, op=dist.ReduceOp.MAX)
+        sps = world * n_train_steps * TRAJ_PER_STEP / float(dt_tr.item())
+        train = {"value": sps, "unit": "train samples (trajectories)/s", "steps": n_train_steps,
+                 "rows_per_step": ROWS_PER_STEP, "precision": cb.train_precision_mode(),
+                 "algorithmic_tflops": sps * T * 3 * FLOP_PER_ROW / 1e12,
+                 "what": "MultiONet cfg2 fit step (forward + MSE + backward + AdamW), host batches, one model per rank"}
+        del tr_model, opt, batches
 
     if world > 1:
         # every rank must reach the end together (rank 0 also ran the extra legs)
@@ -325,7 +373,7 @@ def run_ours(args):
                        "resident_batches": n_batches, "l2_policy": "inputs larger than L2 (rotating batches)",
                        "precision": "bf16 operands, fp32 accumulate (tcgen05)", "parallelism": f"trajectory-sharded x{world}"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -338,6 +386,7 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
     ap.add_argument("--no-cpu-baseline", action="store_true",
                     help="skip the host-side cpu_baseline leg (profiling runs under ncu only)")
     args = ap.parse_args()

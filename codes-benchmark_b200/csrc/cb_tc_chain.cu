@@ -42,7 +42,7 @@ constexpr int kChunkN = 128;         // output columns per job (UMMA_N <= 128), 
 constexpr int kSlots = 4;            // TMEM slots (4 x 128 = 512 columns)
 constexpr int kMaxJobs = 96;
 constexpr int kMaxGroups = 128;      // 32-column groups of the MultiONet output layer (<= 4096 columns)
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kEpiThreads = 256;   // 8 epilogue warps: two per TMEM lane quarter, splitting the columns
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kCtrlBytes = 16 * kMaxStages + 16 * kSlots + 64;
@@ -77,6 +77,8 @@ struct ChainParams {
 struct FinalParams {
   CUtensorMap tmap_in[2];      // hb / ht (rows, ld) bf16
   const __nv_bfloat16* w[2];   // branch / trunk last-layer weights, pre-tiled (chunk, kb) 16 KiB runs, bias folded
+  CUtensorMap tmap_w[2];       // the same buffers as (rows, 64) tensors, 64-row boxes (CTA-pair kernel)
+  long long* dbg;              // CB_TC_FINAL_DBG: per-role cycle counters of CTA 0 (debug), else NULL
   int K, ksteps, nkb, n_jobs, n_out, Q, stages;
   int seg_base, seg_rem;       // split sizes: seg_base + (q < seg_rem)   (deeponet.py:130-137)
   int16_t grp_q[kMaxGroups];   // quantity whose split contains the first column of 32-column group g
@@ -422,8 +424,24 @@ chain_kernel(const __grid_constant__ ChainParams P) {
   teardown_cta(tmem_base, warp);
 }
 
+// debug instrumentation of the MMA warp (cycle counters per wait reason): compile with -DCB_TC_ENABLE_FINAL_DBG
+#ifdef CB_TC_ENABLE_FINAL_DBG
+#define CB_CLK() clock64()
+#else
+#define CB_CLK() 0ll
+#endif
+
 // ====================================================================== MultiONet final kernel
 // y[r,q] = sum_{k in split_q} (Wb hb + bb)[r,k] * (Wt ht + bt)[r,k]      (deeponet.py:241-253)
+//
+// PAIR = true: two CTAs of a cluster (one TPC) work on two neighbouring 128-row tiles with
+// tcgen05.mma.cta_group::2 (M = 256): every weight k-block is split between the two CTAs' shared memory
+// (N/2 rows = 8 KiB each), so the same shared memory holds twice as many stages in flight -- the kernel is
+// bound by the latency of the weight ring (bytes in flight per SM), not by L2 bandwidth -- and L2 -> SM
+// traffic per row halves.  The leader CTA (rank 0) issues all MMAs; both CTAs run their own TMA producer
+// (own activation tiles, own half of every weight stage; transaction bytes credited to the leader's
+// barriers) and their own epilogue (own 128 TMEM lanes); tcgen05.commit multicasts to both CTAs.
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 don_final_kernel(const __grid_constant__ FinalParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -431,38 +449,86 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
   const uint32_t xbytes = (uint32_t)P.nkb * kKBlockBytes;
+  constexpr uint32_t kStageBytes = PAIR ? kKBlockBytes / 2 : kKBlockBytes;
   const uint32_t XB = base, XT = base + xbytes, ST0 = base + 2 * xbytes;
-  const uint32_t ctrl_addr = ST0 + (uint32_t)P.stages * kKBlockBytes;
+  const uint32_t ctrl_addr = ST0 + (uint32_t)P.stages * kStageBytes;
   const Ctrl C = carve_ctrl(ctrl_addr, gbase + (ctrl_addr - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_base = setup_cta(C, P.stages, warp);
-  const int n_my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  uint32_t tmem_base;
+  if constexpr (PAIR) {
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < P.stages; ++s) { mbar_init(C.bar_full + 8 * s, 1); mbar_init(C.bar_empty + 8 * s, 1); }
+      // tempty: one arrival per epilogue warp of BOTH CTAs (on the leader's barrier)
+      for (int s = 0; s < kSlots; ++s) { mbar_init(C.bar_tfull + 8 * s, 1); mbar_init(C.bar_tempty + 8 * s, 2 * (kEpiThreads / 32)); }
+      mbar_init(C.bar_in, 1);
+      *C.epi_done = 0;
+      *C.in_staged = 0;
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(C.tmem_ptr)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    tmem_base = *reinterpret_cast<volatile uint32_t*>(C.tmem_ptr);
+  } else {
+    tmem_base = setup_cta(C, P.stages, warp);
+  }
+  const int units = PAIR ? (P.num_tiles + 1) / 2 : P.num_tiles;            // tile pairs / tiles
+  const int my0 = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int stride = PAIR ? (int)num_clusters_x() : (int)gridDim.x;
+  const int n_my_tiles = (units - my0 + stride - 1) / stride;
+  // barriers owned by the leader CTA, as shared::cluster addresses (identity for the leader itself)
+  const uint32_t L_bar_in = PAIR ? mapa_shared(C.bar_in, 0) : C.bar_in;
+  const uint32_t L_bar_full = PAIR ? mapa_shared(C.bar_full, 0) : C.bar_full;
+  const uint32_t L_bar_tempty = PAIR ? mapa_shared(C.bar_tempty, 0) : C.bar_tempty;
 
   if (warp == 0) {
     // TMA producer: warp-converged, one elected lane issues
     int stage = 0; uint32_t phase = 0;
     int seen_epi = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
-      wait_counter(C.epi_done, it, seen_epi);              // previous tile fully consumed
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      wait_counter(C.epi_done, it, seen_epi);              // previous tile fully consumed (this CTA)
+      const int tile = PAIR ? (my0 + it * stride) * 2 + (int)rank : my0 + it * stride;
       if (elect_one()) {
-        mbar_arrive_expect_tx(C.bar_in, 2u * P.nkb * kKBlockBytes);
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          tma_load_2d(XB + kb * kKBlockBytes, &P.tmap_in[0], kb * kBlockK, tile * kTileM, C.bar_in);
-          tma_load_2d(XT + kb * kKBlockBytes, &P.tmap_in[1], kb * kBlockK, tile * kTileM, C.bar_in);
+        if constexpr (PAIR) {
+          if (leader) mbar_arrive_expect_tx(C.bar_in, 4u * P.nkb * kKBlockBytes);    // both CTAs' hb + ht tiles
+          for (int kb = 0; kb < P.nkb; ++kb) {
+            tma_load_2d_pair(XB + kb * kKBlockBytes, &P.tmap_in[0], kb * kBlockK, tile * kTileM, L_bar_in);
+            tma_load_2d_pair(XT + kb * kKBlockBytes, &P.tmap_in[1], kb * kBlockK, tile * kTileM, L_bar_in);
+          }
+        } else {
+          mbar_arrive_expect_tx(C.bar_in, 2u * P.nkb * kKBlockBytes);
+          for (int kb = 0; kb < P.nkb; ++kb) {
+            tma_load_2d(XB + kb * kKBlockBytes, &P.tmap_in[0], kb * kBlockK, tile * kTileM, C.bar_in);
+            tma_load_2d(XT + kb * kKBlockBytes, &P.tmap_in[1], kb * kBlockK, tile * kTileM, C.bar_in);
+          }
         }
       }
       __syncwarp();
       for (int j = 0; j < P.n_jobs; ++j) {
+        const int ncols = min(kChunkN, P.n_out - j * kChunkN);
         for (int net = 0; net < 2; ++net) {
           const __nv_bfloat16* src = P.w[net] + (size_t)j * P.nkb * (kKBlockBytes / 2);
           for (int kb = 0; kb < P.nkb; ++kb) {
             mbar_wait(C.bar_empty + 8 * stage, phase ^ 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(C.bar_full + 8 * stage, kKBlockBytes);
-              bulk_load(ST0 + stage * kKBlockBytes, src + (size_t)kb * (kKBlockBytes / 2), kKBlockBytes,
-                        C.bar_full + 8 * stage);
+              if constexpr (PAIR) {
+                // this CTA's half of the chunk's weight rows: rows [rank * ncols/2, +64) of tile (j, kb)
+                if (leader) mbar_arrive_expect_tx(C.bar_full + 8 * stage, kKBlockBytes);
+                tma_load_2d_pair(ST0 + stage * kStageBytes, &P.tmap_w[net], 0,
+                                 (j * P.nkb + kb) * kChunkN + (int)rank * (ncols >> 1), L_bar_full + 8 * stage);
+              } else {
+                mbar_arrive_expect_tx(C.bar_full + 8 * stage, kKBlockBytes);
+                bulk_load(ST0 + stage * kKBlockBytes, src + (size_t)kb * (kKBlockBytes / 2), kKBlockBytes,
+                          C.bar_full + 8 * stage);
+              }
             }
             __syncwarp();
             if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -471,44 +537,71 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
       }
     }
   } else if (warp == 1) {
-    // MMA issuer: warp-converged control flow, one elected lane issues
-    int stage = 0; uint32_t phase = 0;
-    int gs = 0;   // global slot-use counter (2 per job)
-    const int nkb = P.nkb;
-    const int last_nks = P.ksteps - (nkb - 1) * 4;
-    const uint64_t bdesc0 = make_smem_desc(ST0);
-    for (int it = 0; it < n_my_tiles; ++it) {
-      mbar_wait(C.bar_in, it & 1);
-      tcgen05_fence_after();
-      for (int j = 0; j < P.n_jobs; ++j) {
-        const int ncols = min(kChunkN, P.n_out - j * kChunkN);
-        const uint32_t idesc = make_idesc(ncols);
-        for (int net = 0; net < 2; ++net, ++gs) {
-          const int slot = gs & (kSlots - 1);
-          const uint32_t use = (uint32_t)(gs / kSlots);
-          mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
-          tcgen05_fence_after();
-          const uint64_t adesc0 = make_smem_desc(net ? XT : XB);
-          const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(C.bar_full + 8 * stage, phase);
+    // MMA issuer: warp-converged control flow, one elected lane issues (PAIR: leader CTA only)
+    if (leader) {
+      int stage = 0; uint32_t phase = 0;
+      int gs = 0;   // global slot-use counter (2 per job)
+      const int nkb = P.nkb;
+      const int last_nks = P.ksteps - (nkb - 1) * 4;
+      const uint64_t bdesc0 = make_smem_desc(ST0);
+      long long c_in = 0, c_tempty = 0, c_full = 0, c_issue = 0;
+      const long long c_start = CB_CLK();
+      for (int it = 0; it < n_my_tiles; ++it) {
+        long long c0 = CB_CLK();
+        mbar_wait(C.bar_in, it & 1);
+        tcgen05_fence_after();
+        c_in += CB_CLK() - c0;
+        for (int j = 0; j < P.n_jobs; ++j) {
+          const int ncols = min(kChunkN, P.n_out - j * kChunkN);
+          const uint32_t idesc = PAIR ? make_idesc_pair(ncols) : make_idesc(ncols);
+          for (int net = 0; net < 2; ++net, ++gs) {
+            const int slot = gs & (kSlots - 1);
+            const uint32_t use = (uint32_t)(gs / kSlots);
+            c0 = CB_CLK();
+            mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
             tcgen05_fence_after();
-            const int nks = (kb == nkb - 1) ? last_nks : 4;
-            const uint64_t adesc = adesc0 + (uint64_t)(kb * (kKBlockBytes >> 4));
-            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kKBlockBytes >> 4));
-            if (elect_one()) {
-              umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+            c_tempty += CB_CLK() - c0;
+            const uint64_t adesc0 = make_smem_desc(net ? XT : XB);
+            const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
+            for (int kb = 0; kb < nkb; ++kb) {
+              c0 = CB_CLK();
+              mbar_wait(C.bar_full + 8 * stage, phase);
+              tcgen05_fence_after();
+              const long long c1 = CB_CLK();
+              c_full += c1 - c0;
+              const int nks = (kb == nkb - 1) ? last_nks : 4;
+              const uint64_t adesc = adesc0 + (uint64_t)(kb * (kKBlockBytes >> 4));
+              const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kStageBytes >> 4));
+              if (elect_one()) {
+                if constexpr (PAIR) {
+                  umma_bf16_pair(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
 #pragma unroll
-              for (int ks = 1; ks < 4; ++ks)
-                if (ks < nks) umma_bf16(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
-              umma_commit(C.bar_empty + 8 * stage);
+                  for (int ks = 1; ks < 4; ++ks)
+                    if (ks < nks) umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
+                  umma_commit_pair(C.bar_empty + 8 * stage);
+                } else {
+                  umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+#pragma unroll
+                  for (int ks = 1; ks < 4; ++ks)
+                    if (ks < nks) umma_bf16(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
+                  umma_commit(C.bar_empty + 8 * stage);
+                }
+              }
+              __syncwarp();
+              c_issue += CB_CLK() - c1;
+              if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) {
+              if constexpr (PAIR) umma_commit_pair(C.bar_tfull + 8 * slot);
+              else umma_commit(C.bar_tfull + 8 * slot);
             }
             __syncwarp();
-            if (++stage == P.stages) { stage = 0; phase ^= 1; }
           }
-          if (elect_one()) umma_commit(C.bar_tfull + 8 * slot);
-          __syncwarp();
         }
+      }
+      if (P.dbg && blockIdx.x == 0 && lane == 0) {
+        P.dbg[0] = CB_CLK() - c_start; P.dbg[1] = c_in; P.dbg[2] = c_tempty; P.dbg[3] = c_full; P.dbg[4] = c_issue;
+        P.dbg[5] = n_my_tiles;
       }
     }
   } else {
@@ -533,7 +626,7 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
     };
     int gs = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int tile = PAIR ? (my0 + it * stride) * 2 + (int)rank : my0 + it * stride;
       const long long row_g = (long long)tile * kTileM + r;
       yrow = (row_g < P.rows) ? P.y + row_g * P.Q : nullptr;
       for (int j = 0; j < P.n_jobs; ++j, gs += 2) {
@@ -595,15 +688,32 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
           }
         }
         tcgen05_fence_before();
-        mbar_arrive(C.bar_tempty + 8 * slot_b);
-        mbar_arrive(C.bar_tempty + 8 * slot_t);
+        if constexpr (PAIR) {
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cluster(L_bar_tempty + 8 * slot_b);
+            mbar_arrive_cluster(L_bar_tempty + 8 * slot_t);
+          }
+        } else {
+          mbar_arrive(C.bar_tempty + 8 * slot_b);
+          mbar_arrive(C.bar_tempty + 8 * slot_t);
+        }
       }
       add_to(-1, 0.f);   // flush the last running partial
       epi_bar_sync();    // every epilogue warp has released its TMEM slots and consumed the tile
       if (et == 0) red_release_inc(C.epi_done);
     }
   }
-  teardown_cta(tmem_base, warp);
+  if constexpr (PAIR) {
+    tcgen05_fence_before();
+    cluster_sync_all();          // the leader's MMAs write the peer's TMEM: nobody leaves early
+    if (warp == 1) {
+      tcgen05_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+  } else {
+    teardown_cta(tmem_base, warp);
+  }
 }
 
 // fp32 (N,K) row-major + bias -> bf16 tiles in the exact shared-memory image of a weight stage:
@@ -903,6 +1013,8 @@ struct cb_tc_multionet {
   cb_mlp_desc desc[2];
   FinalParams F;
   size_t smem_final;
+  int pair;                     // CTA-pair (cta_group::2) final kernel
+  int stages_pair; size_t smem_pair;
   int weights_set;
 };
 
@@ -915,17 +1027,18 @@ extern "C" void cb_tc_multionet_destroy(cb_tc_multionet* m) {
   delete m;
 }
 
-static bool final_geometry(int K, int Q, int* nkb_out, int* stages_out, size_t* smem_out) {
+static bool final_geometry(int K, int Q, int* nkb_out, int* stages_out, size_t* smem_out, bool pair = false) {
   const int ksteps = (K + 1 + kUmmaK - 1) / kUmmaK;
   const int nkb = (ksteps + 3) / 4;
   (void)Q;
+  const long long stage_bytes = pair ? kKBlockBytes / 2 : kKBlockBytes;
   const long long fixed = 1024 + kCtrlBytes + 2ll * nkb * kKBlockBytes;
-  long long stages = ((long long)kMaxSmem - fixed) / kKBlockBytes;
+  long long stages = ((long long)kMaxSmem - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (const char* e = getenv("CB_TC_MAX_STAGES")) { const int c = atoi(e); if (c >= 2 && c < stages) stages = c; }  // experiment knob
   if (nkb_out) *nkb_out = nkb;
   if (stages_out) *stages_out = (int)stages;
-  if (smem_out) *smem_out = (size_t)(fixed + (stages > 0 ? stages : 0) * kKBlockBytes);
+  if (smem_out) *smem_out = (size_t)(fixed + (stages > 0 ? stages : 0) * stage_bytes);
   return stages >= 2;
 }
 
@@ -963,6 +1076,10 @@ extern "C" int32_t cb_tc_multionet_create(const cb_mlp_desc* branch, const cb_ml
   m->Q = Q;
   int nkb = 0, stages = 0;
   final_geometry(m->K, Q, &nkb, &stages, &m->smem_final);
+  {
+    const char* e = getenv("CB_TC_NO_PAIR");
+    m->pair = !(e && atoi(e) != 0) && final_geometry(m->K, Q, nullptr, &m->stages_pair, &m->smem_pair, true);
+  }
   m->Kp = nkb * kBlockK;
   m->ld_h = m->hidden[0]->ld_out;
   m->rows_alloc = round_up(m->n_out, kChunkN);
@@ -989,7 +1106,14 @@ extern "C" int32_t cb_tc_multionet_create(const cb_mlp_desc* branch, const cb_ml
     }
     F.w[i] = m->d_wlast[i];
   }
-  if (cudaFuncSetAttribute(don_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_final) !=
+  for (int i = 0; i < 2 && m->pair; ++i)
+    if (!encode_bf16_rows64(&F.tmap_w[i], m->d_wlast[i], (long long)m->rows_alloc * (m->Kp / kBlockK), 64)) m->pair = 0;
+  if (m->pair && cudaFuncSetAttribute(don_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)m->smem_pair) != cudaSuccess) {
+    cudaGetLastError();
+    m->pair = 0;
+  }
+  if (cudaFuncSetAttribute(don_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_final) !=
       cudaSuccess) {
     cb_tc_multionet_destroy(m);
     set_error("cannot reserve shared memory for the MultiONet final kernel");
@@ -1087,8 +1211,37 @@ static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_
   F.y = d_y; F.rows = rows;
   F.num_tiles = (int)((rows + kTileM - 1) / kTileM);
   const int grid = F.num_tiles < grid_cap() ? F.num_tiles : grid_cap();
-  don_final_kernel<<<grid, kThreads, m->smem_final, st>>>(F);
+  F.dbg = nullptr;
+  const char* dbg_env = getenv("CB_TC_FINAL_DBG");
+  if (dbg_env) { CB_CUDA(cudaMalloc(&F.dbg, 64)); CB_CUDA(cudaMemsetAsync(F.dbg, 0, 64, st)); }
+  if (m->pair) {
+    // one cluster of two CTAs per pair of 128-row tiles, persistent over the pairs
+    const int pairs = (F.num_tiles + 1) / 2;
+    const int clusters = pairs < grid_cap() / 2 ? pairs : grid_cap() / 2;
+    F.stages = m->stages_pair;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = m->smem_pair;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CB_CUDA(cudaLaunchKernelEx(&cfg, don_final_kernel<true>, F));
+  } else {
+    don_final_kernel<false><<<grid, kThreads, m->smem_final, st>>>(F);
+  }
   CB_LAUNCH_CHECK();
+  if (dbg_env) {
+    long long h[8];
+    CB_CUDA(cudaStreamSynchronize(st));
+    CB_CUDA(cudaMemcpy(h, F.dbg, 64, cudaMemcpyDeviceToHost));
+    cudaFree(F.dbg);
+    fprintf(stderr, "[final dbg] MMA warp of CTA 0: total %lld cycles over %lld tiles: wait A tiles %lld, wait TMEM slot %lld, "
+                    "wait weight stage %lld, issue %lld\n", h[0], h[5], h[1], h[2], h[3], h[4]);
+  }
   if (ev) cudaEventRecord(ev[3], st);
   return CB_OK;
 }

@@ -11,7 +11,7 @@ _, _, vl = m.prepare_data(de, None, de, np.linspace(0, 1, 100), 65536, shuffle=F
 print("prepare", time.perf_counter() - t0, "threads", torch.get_num_threads(), os.environ.get("OMP_NUM_THREADS"))
 ds = vl.dataset
 print("pinned:", [t.is_pinned() for t in ds.tensors])
-for rep in range(3):
+for rep in range(12):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     n = 0
     for b in vl:
@@ -21,4 +21,6 @@ for rep in range(3):
     t2 = time.perf_counter()
     l = m._l1(p, t)
     t3 = time.perf_counter()
-    print(f"iterate loader {t1-t0:.4f}s  predict {t2-t1:.4f}s  l1 {t3-t2:.4f}s")
+    print(f"iterate loader {t1-t0:.4f}s  predict {t2-t1:.4f}s  l1 {t3-t2:.4f}s  -> {16384/(t3-t1):.0f} traj/s", flush=True)
+    if rep == 5:
+        print("sleep 2s (idle gap)"); time.sleep(2.0)
