@@ -101,6 +101,8 @@ _SIGNATURES = {
     "cb_tc_train_saved_bytes": (_I64, [_P, _I64]),
     "cb_tc_train_scratch_bytes": (_I64, [_P, _I64]),
     "cb_tc_train_forward": (_I32, [_P, _PP, _PP, _P, _I64, _P, _P, _I64, _P]),
+    "cb_tc_train_infer_bytes": (_I64, [_P, _I64]),
+    "cb_tc_train_infer": (_I32, [_P, _PP, _PP, _P, _I64, _P, _P, _I64, _P]),
     "cb_tc_train_backward": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _PP, _PP, _P, _P]),
     "cb_tc_combine_fwd": (_I32, [_P, _P, _I64, _I32, _I32, _I32, _P, _P]),
     "cb_tc_combine_bwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P]),

@@ -472,6 +472,8 @@ def run_chain(spec: ChainSpec, x: Tensor, weights, biases, tc_train: bool = True
         from . import tc
         if tc.supported(spec):
             return tc.chain_forward(spec, x, weights, biases)
+        if tc.train_supported(spec) and x.numel() // max(spec.dims[0], 1) >= TC_TRAIN_MIN_ROWS:
+            return tc.gemm_chain_forward(spec, x, weights, biases)    # too wide for the fused kernel: GEMM per layer
     if needs_grad and tc_train and _use_tc_training(spec, x):
         from . import tc
         return tc.train_chain(spec, x, weights, biases)

@@ -168,6 +168,29 @@ def train_supported(spec) -> bool:
     return available() and spec.final_act in ("identity", "tanh")
 
 
+def gemm_chain_forward(spec, x, weights, biases):
+    """Gradient-free y = chain(x) with one tensor-core GEMM launch per layer (wide chains that the fused
+    single-launch kernel does not hold in shared memory)."""
+    dev = x.device
+    plan = _train_plan(spec, dev, False)
+    x2 = x.reshape(-1, spec.dims[0])
+    if x2.dtype != torch.float32 or not x2.is_contiguous():
+        x2 = x2.float().contiguous()
+    rows = x2.shape[0]
+    L = lib()
+    with torch.cuda.device(dev):
+        y = torch.empty((rows, spec.dims[-1]), device=dev, dtype=torch.float32)
+        if rows:
+            nbytes = int(L.cb_tc_train_infer_bytes(plan.handle, rows))
+            if plan.scratch is None or plan.scratch.numel() < nbytes:
+                plan.scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            wl, bl = _f32(weights), _f32(biases)
+            check(L.cb_tc_train_infer(plan.handle, ptr_array(wl), ptr_array(bl), C.c_void_p(x2.data_ptr()), rows,
+                                      C.c_void_p(y.data_ptr()), C.c_void_p(plan.scratch.data_ptr()),
+                                      plan.scratch.numel(), _stream(dev)), "tc_train_infer")
+    return y.reshape(*x.shape[:-1], spec.dims[-1])
+
+
 class _TcTrainChainFn(torch.autograd.Function):
     """y = chain(x) with bf16 tensor-core GEMMs in both directions (fp32 accumulate, fp32 gradients)."""
 

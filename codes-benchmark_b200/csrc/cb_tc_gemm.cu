@@ -773,20 +773,17 @@ extern "C" int64_t cb_tc_train_scratch_bytes(const cb_tc_train* p, int64_t rows)
   return 2 * rp * ld_max * 2 + part + 512;
 }
 
-// y = chain(x), saving the bf16 activations for cb_tc_train_backward.
-extern "C" int32_t cb_tc_train_forward(cb_tc_train* p, const float* const* d_W, const float* const* d_b,
-                                       const float* d_x, int64_t rows, void* d_y, void* d_saved,
-                                       int64_t saved_bytes, void* stream) {
-  CB_CHECK_ARG(p && d_W && d_b, "NULL pointer argument");
-  CB_CHECK_ARG(rows >= 0, "rows < 0");
-  if (rows == 0) return CB_OK;
-  CB_CHECK_ARG(d_x && d_y && d_saved, "NULL pointer argument");
-  CB_CHECK_ARG(((uintptr_t)d_saved & 255) == 0, "saved buffer must be 256-byte aligned");
-  if (saved_bytes < cb_tc_train_saved_bytes(p, rows)) { set_error("saved buffer too small"); return CB_ERR_WORKSPACE; }
-  cudaStream_t st = (cudaStream_t)stream;
+// shared by the training forward (activations saved per layer) and the gradient-free forward
+// (two ping-pong activation buffers, no pre-activation stores)
+static int32_t chain_forward_impl(cb_tc_train* p, const float* const* d_W, const float* const* d_b, const float* d_x,
+                                  int64_t rows, void* d_y, uint8_t* buf, bool keep, cudaStream_t st) {
   const int n = p->n;
   const long long rp = rows_pad(rows);
-  uint8_t* sv = reinterpret_cast<uint8_t*>(d_saved);
+  int ld_max = 0;
+  for (int i = 0; i <= n; ++i) ld_max = p->ld[i] > ld_max ? p->ld[i] : ld_max;
+  auto act_ptr = [&](int i) -> __nv_bfloat16* {
+    return reinterpret_cast<__nv_bfloat16*>(keep ? buf + saved_offset(p, rows, i, 0) : buf + (size_t)(i & 1) * rp * ld_max * 2);
+  };
   for (int i = 0; i < n; ++i) {
     CB_CHECK_ARG(d_W[i] != nullptr, "weight %d is NULL", i);
     const long long total = (long long)p->wp_rows[i] * p->ld[i] + (long long)p->wt_rows[i] * p->ld[i + 1];
@@ -795,15 +792,14 @@ extern "C" int32_t cb_tc_train_forward(cb_tc_train* p, const float* const* d_W, 
                                                            p->wp[i], p->wt[i]);
     CB_LAUNCH_CHECK();
   }
-  __nv_bfloat16* h0 = reinterpret_cast<__nv_bfloat16*>(sv + saved_offset(p, rows, 0, 0));
   pack_rows_kernel<<<ew_blocks(rows * (p->ld[0] / 8)), 256, 0, st>>>(d_x, rows, p->desc.dims[0], p->ld[0],
-                                                                   p->desc.dims[0], h0);
+                                                                   p->desc.dims[0], act_ptr(0));
   CB_LAUNCH_CHECK();
   for (int i = 0; i < n; ++i) {
     const bool last = i == n - 1;
     GemmCall c;
     memset(&c, 0, sizeof(c));
-    c.A = reinterpret_cast<__nv_bfloat16*>(sv + saved_offset(p, rows, i, 0));
+    c.A = act_ptr(i);
     c.a_rows = rows; c.a_cols = p->ld[i]; c.a_ld = p->ld[i];
     c.B = p->wp[i]; c.b_rows = p->wp_rows[i]; c.b_cols = p->ld[i]; c.b_ld = p->ld[i];
     c.m_out = rows; c.k_total = p->desc.dims[i] + 1;
@@ -817,17 +813,48 @@ extern "C" int32_t cb_tc_train_forward(cb_tc_train* p, const float* const* d_W, 
     } else {
       c.mode = EPI_FWD_BF16;
       c.n_out_ld = p->ld[i + 1];
-      c.out_bf16 = last ? reinterpret_cast<__nv_bfloat16*>(d_y)
-                        : reinterpret_cast<__nv_bfloat16*>(sv + saved_offset(p, rows, i + 1, 0));
+      c.out_bf16 = last ? reinterpret_cast<__nv_bfloat16*>(d_y) : act_ptr(i + 1);
       c.out_rows = rows; c.out_ld = p->ld[i + 1];
       c.act = last ? CB_ACT_IDENTITY : p->desc.act;
       c.ones_col = last ? -1 : c.n_true;
-      if (!last && p->needs_z) c.out2_bf16 = reinterpret_cast<__nv_bfloat16*>(sv + saved_offset(p, rows, i + 1, 1));
+      if (keep && !last && p->needs_z) c.out2_bf16 = reinterpret_cast<__nv_bfloat16*>(buf + saved_offset(p, rows, i + 1, 1));
     }
     if (int32_t e = launch_gemm(c, st)) return e;
   }
-  (void)rp;
   return CB_OK;
+}
+
+// y = chain(x), saving the bf16 activations for cb_tc_train_backward.
+extern "C" int32_t cb_tc_train_forward(cb_tc_train* p, const float* const* d_W, const float* const* d_b,
+                                       const float* d_x, int64_t rows, void* d_y, void* d_saved,
+                                       int64_t saved_bytes, void* stream) {
+  CB_CHECK_ARG(p && d_W && d_b, "NULL pointer argument");
+  CB_CHECK_ARG(rows >= 0, "rows < 0");
+  if (rows == 0) return CB_OK;
+  CB_CHECK_ARG(d_x && d_y && d_saved, "NULL pointer argument");
+  CB_CHECK_ARG(((uintptr_t)d_saved & 255) == 0, "saved buffer must be 256-byte aligned");
+  if (saved_bytes < cb_tc_train_saved_bytes(p, rows)) { set_error("saved buffer too small"); return CB_ERR_WORKSPACE; }
+  return chain_forward_impl(p, d_W, d_b, d_x, rows, d_y, reinterpret_cast<uint8_t*>(d_saved), true, (cudaStream_t)stream);
+}
+
+// Gradient-free y = chain(x) with one tensor-core GEMM per layer (chains too wide for the fused single-launch
+// kernel of cb_tc_chain_forward, e.g. FullyConnected 6 -> 800 x 8 -> 5): two ping-pong activation buffers.
+extern "C" int64_t cb_tc_train_infer_bytes(const cb_tc_train* p, int64_t rows) {
+  if (!p || rows < 0) return -1;
+  int ld_max = 0;
+  for (int i = 0; i <= p->n; ++i) ld_max = p->ld[i] > ld_max ? p->ld[i] : ld_max;
+  return 2 * rows_pad(rows) * ld_max * 2 + 256;
+}
+extern "C" int32_t cb_tc_train_infer(cb_tc_train* p, const float* const* d_W, const float* const* d_b,
+                                     const float* d_x, int64_t rows, void* d_y, void* d_workspace,
+                                     int64_t workspace_bytes, void* stream) {
+  CB_CHECK_ARG(p && d_W && d_b, "NULL pointer argument");
+  CB_CHECK_ARG(rows >= 0, "rows < 0");
+  if (rows == 0) return CB_OK;
+  CB_CHECK_ARG(d_x && d_y && d_workspace, "NULL pointer argument");
+  CB_CHECK_ARG(((uintptr_t)d_workspace & 255) == 0, "workspace must be 256-byte aligned");
+  if (workspace_bytes < cb_tc_train_infer_bytes(p, rows)) { set_error("workspace too small"); return CB_ERR_WORKSPACE; }
+  return chain_forward_impl(p, d_W, d_b, d_x, rows, d_y, reinterpret_cast<uint8_t*>(d_workspace), false, (cudaStream_t)stream);
 }
 
 // Gradients of the chain.  d_dy: fp32 (rows, dims[n]) (or bf16 (rows, ld[n]) with zero padding when the

@@ -286,6 +286,12 @@ CB_API int64_t cb_tc_train_scratch_bytes(const cb_tc_train* plan, int64_t rows);
 CB_API int32_t cb_tc_train_forward(cb_tc_train* plan, const float* const* d_W, const float* const* d_b,
                                    const float* d_x, int64_t rows, void* d_y, void* d_saved,
                                    int64_t saved_bytes, void* stream);
+/* gradient-free y = chain(x), one tensor-core GEMM per layer, for chains too wide for the fused
+ * single-launch kernel (cb_tc_chain_supported == 0), e.g. FullyConnected 6 -> 800 x 8 -> 5. */
+CB_API int64_t cb_tc_train_infer_bytes(const cb_tc_train* plan, int64_t rows);
+CB_API int32_t cb_tc_train_infer(cb_tc_train* plan, const float* const* d_W, const float* const* d_b,
+                                 const float* d_x, int64_t rows, void* d_y, void* d_workspace,
+                                 int64_t workspace_bytes, void* stream);
 /* d_dW[i] (out,in) / d_db[i] (out) fp32 are OVERWRITTEN (deterministic split reduction); d_dx may be
  * NULL; d_y (the fp32 forward output) is only read for a tanh final activation. */
 CB_API int32_t cb_tc_train_backward(cb_tc_train* plan, const void* d_dy, const float* d_y, int64_t rows,

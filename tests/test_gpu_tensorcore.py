@@ -67,6 +67,41 @@ def test_chain_matches_oracle(dims, act, fact, rows):
     assert np.abs(y - ref).max() <= 2e-2 * np.abs(ref).max()
 
 
+WIDE_CHAINS = [
+    ([6, 800, 800, 800, 800, 800, 800, 800, 800, 5], "gelu", "identity", 3000),   # FCNN simple_ode config (cfg1)
+    ([30, 600, 600, 29], "relu", "identity", 2049),
+    ([9, 580, 10], "silu", "tanh", 4096),                                          # primordial LNODE decoder
+]
+
+
+@pytest.mark.parametrize("dims,act,fact,rows", WIDE_CHAINS)
+def test_wide_chain_per_layer_gemms_match_oracle(dims, act, fact, rows):
+    """chains too wide for the fused single-launch kernel run one tensor-core GEMM per layer
+    (cb_tc_train_infer); same bf16 tolerance as the fused chain."""
+    tc = _tc()
+    from codes_b200 import ops
+    rng = np.random.default_rng(sum(dims) + rows)
+    ws = [(rng.normal(size=(b, a)) / np.sqrt(a)).astype(np.float32) for a, b in zip(dims[:-1], dims[1:])]
+    bs = [(rng.normal(size=(b,)) * 0.1).astype(np.float32) for b in dims[1:]]
+    x = rng.uniform(-1, 1, size=(rows, dims[0])).astype(np.float32)
+    spec = ops.ChainSpec(dims, act, fact)
+    wt = [torch.from_numpy(w).to(DEV) for w in ws]
+    bt = [torch.from_numpy(b).to(DEV) for b in bs]
+    y = tc.gemm_chain_forward(spec, torch.from_numpy(x).to(DEV), wt, bt).cpu().numpy()
+    ref = O.mlp_chain(x, ws, bs, act, fact)
+    assert rel_l2(y, ref) <= 1e-2
+    assert np.abs(y - ref).max() <= 2e-2 * np.abs(ref).max()
+    if not tc.supported(spec):
+        import codes_b200 as cb
+        cb.set_precision("bf16")
+        try:
+            with torch.no_grad():
+                y2 = ops.run_chain(spec, torch.from_numpy(x).to(DEV), wt, bt).cpu().numpy()   # dispatcher picks this path
+        finally:
+            cb.set_precision("fp32")
+        np.testing.assert_array_equal(y2, y)
+
+
 def test_chain_weight_refresh_after_update():
     """the bf16 weight cache must follow in-place parameter updates (optimizer steps)."""
     tc = _tc()
