@@ -37,6 +37,7 @@ class LnodeDesc(C.Structure):
         ("rtol", C.c_double),
         ("atol", C.c_double),
         ("max_steps", C.c_int32),
+        ("n_err", C.c_int32),
     ]
 
 
@@ -66,6 +67,8 @@ _SIGNATURES = {
     "cb_deeponet_combine_bwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "cb_poly_eval_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _P]),
     "cb_poly_eval_bwd": (_I32, [_P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _I64, _P]),
+    "cb_poly_eval_batched_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _P]),
+    "cb_poly_eval_batched_bwd": (_I32, [_P, _P, _I64, _I32, _I32, _I32, _P, _P, _P]),
     "cb_pointwise_loss": (_I32, [_P, _P, _I64, _I32, _F, _P, _P, _P, _I64, _P]),
     "cb_latent_loss_fwd_bwd": (_I32, [_P, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _F, _P, _P, _P, _I64, _P]),
     "cb_adamw_step": (_I32, [_PP, _PP, _PP, _PP, C.POINTER(_I64), _I32, _F, _F, _F, _F, _F, _I64, _P]),

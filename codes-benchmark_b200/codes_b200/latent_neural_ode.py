@@ -52,6 +52,32 @@ class ODE(nn.Module):
         return out.to(torch.float64)
 
 
+class ODEWithParams(nn.Module):
+    """Fixed parameters injected into the ODE net (latent_neural_ode.py:659-684): the solver state is the
+    latent vector, the net sees [z, p].  Same module tree as the reference (``base_ode``) => same
+    state_dict keys.  On the B200 path the parameters ride along as extra CONSTANT state features (the last
+    Linear is padded with zero rows, so dp/dt = 0) that are excluded from the controller's error norm."""
+
+    def __init__(self, base_ode: ODE, n_parameters: int, latent_dim: int):
+        super().__init__()
+        self.base_ode = base_ode
+        self.latent_dim = latent_dim
+        self.n_parameters = n_parameters
+        self.p_const = None
+
+    @property
+    def reg_factor(self):
+        return self.base_ode.reg_factor
+
+    def set_params(self, params: Tensor):
+        self.p_const = params
+
+    def forward(self, t, y: Tensor) -> Tensor:
+        if self.p_const is None:
+            raise RuntimeError("Call set_params() before solving.")
+        return self.base_ode(t, torch.cat([y, self.p_const.to(y.dtype)], dim=1))
+
+
 class ModelWrapper(LatentLossMixin, nn.Module):
     def __init__(self, config, n_quantities: int, n_parameters: int = 0, n_timesteps: int = 101,
                  dtype: torch.dtype = torch.float32):
@@ -63,10 +89,6 @@ class ModelWrapper(LatentLossMixin, nn.Module):
         self.dtype = dtype
         self.n_timesteps = n_timesteps
         enc_in = n_quantities + (n_parameters if (n_parameters > 0 and config.encode_params) else 0)
-        if n_parameters > 0 and not config.encode_params:
-            raise NotImplementedError(
-                "LatentNeuralODE with parameters injected into the ODE net (encode_params=False) "
-                "is not part of the B200 hot path yet")
         if config.model_version == "v1":
             self.encoder = OldEncoder(enc_in, latent, config.layers_factor, config.activation)
         elif config.model_version == "v2":
@@ -74,8 +96,15 @@ class ModelWrapper(LatentLossMixin, nn.Module):
                                    config.activation, dtype)
         else:
             raise ValueError(f"Unknown model version {config.model_version}. Supported versions: 'v1', 'v2'.")
-        self.ode = ODE(latent, latent, config.activation, config.ode_layers, config.ode_width,
+        self.inject_params = n_parameters > 0 and not config.encode_params
+        if self.inject_params:
+            base = ODE(latent + n_parameters, latent, config.activation, config.ode_layers, config.ode_width,
                        config.ode_tanh_reg, dtype)
+            self.ode = ODEWithParams(base, n_parameters, latent)
+        else:
+            self.ode = ODE(latent, latent, config.activation, config.ode_layers, config.ode_width,
+                           config.ode_tanh_reg, dtype)
+        self._aug_chain = None
         if config.model_version == "v1":
             self.decoder = OldDecoder(n_quantities, latent, config.layers_factor, config.activation)
         else:
@@ -88,14 +117,29 @@ class ModelWrapper(LatentLossMixin, nn.Module):
             return torch.cat([x0, params.to(x0.device)], dim=1)
         return x0
 
-    def integrate(self, z0: Tensor, t_range: Tensor) -> Tensor:
+    def integrate(self, z0: Tensor, t_range: Tensor, params: Tensor | None = None) -> Tensor:
         """(B,L) -> (B,T,L): persistent Tsit5 kernel (fp64 state, rtol/atol from the config)."""
-        w, b = ops.sequential_params(self.ode.mlp)
-        return ops.lnode_integrate(self, self.ode.chain(), w, b, z0, t_range)
+        if not self.inject_params:
+            w, b = ops.sequential_params(self.ode.mlp)
+            return ops.lnode_integrate(self, self.ode.chain(), w, b, z0, t_range)
+        if params is None:
+            raise RuntimeError("this model injects fixed parameters into the ODE net: params must be given")
+        base = self.ode.base_ode
+        w, b = ops.sequential_params(base.mlp)
+        L, P = z0.shape[1], self.n_parameters
+        # augmented state [z, p] with dp/dt = 0: pad the last Linear with P zero rows
+        w = list(w[:-1]) + [torch.cat([w[-1], w[-1].new_zeros((P, w[-1].shape[1]))], dim=0)]
+        b = list(b[:-1]) + [torch.cat([b[-1], b[-1].new_zeros(P)], dim=0)]
+        spec0 = base.chain()
+        if self._aug_chain is None or self._aug_chain.act_param != spec0.act_param:
+            self._aug_chain = ops.ChainSpec(spec0.dims[:-1] + [L + P], spec0.act, "identity", spec0.act_param)
+        y0 = torch.cat([z0, params.to(z0.device, z0.dtype)], dim=1)
+        traj = ops.lnode_integrate(self, self._aug_chain, w, b, y0, t_range, reg_factor=base.reg_factor, n_err=L)
+        return traj[:, :, :L].contiguous()
 
     def forward(self, x0: Tensor, t_range: Tensor, params: Tensor | None = None) -> Tensor:
         z0 = self.encoder(self._encoder_input(x0, params))
-        latent_traj = self.integrate(z0, t_range)
+        latent_traj = self.integrate(z0, t_range, params)
         return self.decoder(latent_traj)
 
 

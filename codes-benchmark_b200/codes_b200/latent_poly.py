@@ -45,10 +45,9 @@ class PolynomialModelWrapper(LatentLossMixin, nn.Module):
         self.n_timesteps = n_timesteps
         self.n_parameters = n_parameters
         latent = config.latent_features
-        if config.coeff_network and n_parameters > 0:
-            raise NotImplementedError(
-                "LatentPoly coeff_network (parametric datasets) is not part of the B200 hot path yet")
-        enc_in = config.n_quantities + n_parameters
+        self.use_coeff_net = bool(config.coeff_network and n_parameters > 0)
+        # with the coefficient network the encoder sees only the raw state (latent_poly.py:262-270)
+        enc_in = config.n_quantities + (0 if self.use_coeff_net else n_parameters)
         if config.model_version == "v1":
             self.encoder = OldEncoder(enc_in, latent, config.layers_factor, config.activation).to(device)
             self.decoder = OldDecoder(config.n_quantities, latent, config.layers_factor,
@@ -59,10 +58,34 @@ class PolynomialModelWrapper(LatentLossMixin, nn.Module):
             self.decoder = Decoder(config.n_quantities, latent, config.coder_layers, config.coder_width,
                                    config.activation).to(device)
         self.poly = Polynomial(degree=config.degree, dimension=latent).to(device)
-        self.coefficient_net = None
+        if self.use_coeff_net:
+            # same module nesting as the reference (latent_poly.py:319-339) => same state_dict keys
+            act = config.activation
+            self.coefficient_net = nn.Sequential(
+                nn.Linear(n_parameters, config.coeff_width, dtype=torch.float32), act,
+                *[nn.Sequential(nn.Linear(config.coeff_width, config.coeff_width, dtype=torch.float32), act)
+                  for _ in range(config.coeff_layers - 1)],
+                nn.Linear(config.coeff_width, latent * config.degree, dtype=torch.float32)).to(device)
+        else:
+            self.coefficient_net = None
+        self._coef_chain = None
+
+    def _coef_params(self):
+        lin = [m for m in self.coefficient_net.modules() if isinstance(m, nn.Linear)]
+        return [m.weight for m in lin], [m.bias for m in lin]
+
+    def coefficients(self, params: Tensor) -> Tensor:
+        """(B, P) -> (B, L, deg): the coefficient network as one fused dense chain."""
+        w, b = self._coef_params()
+        name, ap = ops.activation_spec(self.config.activation)
+        if self._coef_chain is None or self._coef_chain.act_param != ap:
+            dims = [w[0].shape[1]] + [x.shape[0] for x in w]
+            self._coef_chain = ops.ChainSpec(dims, name, "identity", ap)
+        out = ops.run_chain(self._coef_chain, params, w, b, tc_train=False)
+        return out.reshape(params.shape[0], self.config.latent_features, self.config.degree)
 
     def _encoder_input(self, x0: Tensor, params: Tensor | None) -> Tensor:
-        if params is not None:
+        if params is not None and not self.config.coeff_network:
             return torch.cat([x0, params.to(x0.device)], dim=1)
         return x0
 
@@ -70,7 +93,12 @@ class PolynomialModelWrapper(LatentLossMixin, nn.Module):
         """x:(B,T,Q) (only x[:,0] is used), t_range:(T,) -> (B,T,Q)  (latent_poly.py:343-381)."""
         x0 = x[:, 0, :].contiguous()
         z0 = self.encoder(self._encoder_input(x0, params))
-        z = ops.poly_eval(self.poly.coef.weight, z0, t_range)
+        if self.config.coeff_network and params is not None:
+            if self.coefficient_net is None:
+                raise RuntimeError("coeff_network=True needs n_parameters > 0 at construction")
+            z = ops.poly_eval_batched(self.coefficients(params.to(x0.device).float()), z0, t_range)
+        else:
+            z = ops.poly_eval(self.poly.coef.weight, z0, t_range)
         return self.decoder(z)
 
 

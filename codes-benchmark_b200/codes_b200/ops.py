@@ -229,6 +229,39 @@ def poly_eval(coef: Tensor, z0: Tensor, t: Tensor) -> Tensor:
     return _PolyFn.apply(coef, z0, t)
 
 
+class _PolyBatchedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coef: Tensor, z0: Tensor, t: Tensor):
+        _require_cuda(coef, z0, t)
+        coef, z0, t = _f32c(coef), _f32c(z0), _f32c(t)
+        B, Lat, deg = coef.shape
+        T = t.shape[0]
+        z = torch.empty((B, T, Lat), device=z0.device, dtype=torch.float32)
+        with torch.cuda.device(z0.device):
+            check(lib().cb_poly_eval_batched_fwd(_p(coef), _p(z0), _p(t), B, T, Lat, deg, _p(z), _stream(z0)),
+                  "poly_eval_batched_fwd")
+        ctx.save_for_backward(t)
+        ctx.shape = (B, T, Lat, deg)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz: Tensor):
+        (t,) = ctx.saved_tensors
+        B, T, Lat, deg = ctx.shape
+        dz = _f32c(dz)
+        dz0 = torch.empty((B, Lat), device=dz.device, dtype=torch.float32)
+        dcoef = torch.empty((B, Lat, deg), device=dz.device, dtype=torch.float32)
+        with torch.cuda.device(dz.device):
+            check(lib().cb_poly_eval_batched_bwd(_p(dz), _p(t), B, T, Lat, deg, _p(dz0), _p(dcoef), _stream(dz)),
+                  "poly_eval_batched_bwd")
+        return dcoef, dz0, None
+
+
+def poly_eval_batched(coef: Tensor, z0: Tensor, t: Tensor) -> Tensor:
+    """z[b,t,:] = z0[b,:] + sum_i coef[b,:,i-1] t^i with per-trajectory coefficients (B, L, deg)."""
+    return _PolyBatchedFn.apply(coef, z0, t)
+
+
 # --------------------------------------------------------------------------- losses
 def _loss_ws(dev, n_floats: int) -> Tensor:
     return torch.empty(max(n_floats, 1), device=dev, dtype=torch.float32)
@@ -338,24 +371,27 @@ def denormalize(x: Tensor, mode: int, dmin: Tensor | None, dmax: Tensor | None, 
 TAPE_CAP = 96   # accepted steps recorded per trajectory for the backward sweep
 
 
-def _lnode_desc(spec: ChainSpec, tanh_reg: bool, reg_factor: float, rtol: float, atol: float, max_steps: int):
+def _lnode_desc(spec: ChainSpec, tanh_reg: bool, reg_factor: float, rtol: float, atol: float, max_steps: int,
+                n_err: int = 0):
     d = _lib.LnodeDesc()
     d.ode = spec.desc
     d.tanh_reg = int(bool(tanh_reg))
     d.reg_factor = float(reg_factor)
     d.rtol, d.atol, d.max_steps = float(rtol), float(atol), int(max_steps)
+    d.n_err = int(n_err)
     return d
 
 
 def lnode_solve(spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor, tanh_reg: bool, reg_factor: float,
-                rtol: float, atol: float, max_steps: int = 100000, return_stats: bool = False, record_tape: bool = False):
+                rtol: float, atol: float, max_steps: int = 100000, return_stats: bool = False, record_tape: bool = False,
+                n_err: int = 0):
     """Adaptive Tsit5 solve of dz/dt = ODE-net(z); z0:(B,L) -> (B,T,L) fp32.
     ``record_tape`` additionally returns the accepted-step record the backward sweep consumes."""
     _require_cuda(z0, t_eval)
     z0c, tc = _f32c(z0), _f32c(t_eval)
     B, Lat = z0c.shape
     T = tc.shape[0]
-    d = _lnode_desc(spec, tanh_reg, reg_factor, rtol, atol, max_steps)
+    d = _lnode_desc(spec, tanh_reg, reg_factor, rtol, atol, max_steps, n_err)
     dev = z0c.device
     out = torch.empty((B, T, Lat), device=dev, dtype=torch.float32)
     stats = torch.empty((B, 2), device=dev, dtype=torch.int32)
@@ -386,12 +422,12 @@ def lnode_solve(spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor, ta
 
 
 def lnode_solve_backward(spec: ChainSpec, weights, biases, t_eval: Tensor, tape_bufs, g: Tensor, tanh_reg: bool,
-                         reg_factor: float, rtol: float, atol: float):
+                         reg_factor: float, rtol: float, atol: float, n_err: int = 0):
     """Discrete-adjoint backward of ``lnode_solve``: returns (dz0, dW list, db list, dreg)."""
     g = _f32c(g)
     B, T, Lat = g.shape
     dev = g.device
-    d = _lnode_desc(spec, tanh_reg, reg_factor, rtol, atol, 1)
+    d = _lnode_desc(spec, tanh_reg, reg_factor, rtol, atol, 1, n_err)
     L = lib()
     wl = [_f32c(w.detach()) for w in weights]
     bl = [_f32c(b.detach()) for b in biases]
@@ -515,19 +551,20 @@ FORCE_WIDE_LNODE_BACKWARD = False   # tests: run the level-synchronous sweep on 
 
 class _LnodeSolveFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, wrapper, spec: ChainSpec, z0: Tensor, t_eval: Tensor, reg_factor: Tensor, *params: Tensor):
+    def forward(ctx, wrapper, spec: ChainSpec, n_err: int, z0: Tensor, t_eval: Tensor, reg_factor: Tensor,
+                *params: Tensor):
         n = spec.n_layers
         weights, biases = params[:n], params[n:]
         cfg = wrapper.config
         reg = float(reg_factor.detach()) if cfg.ode_tanh_reg else 1.0
         need_grad = any(ctx.needs_input_grad)
         res = lnode_solve(spec, weights, biases, z0.detach(), t_eval, cfg.ode_tanh_reg, reg, cfg.rtol, cfg.atol,
-                          return_stats=True, record_tape=need_grad)
+                          return_stats=True, record_tape=need_grad, n_err=n_err)
         out, stats = res[0], res[1]
         wrapper.last_solver_stats = stats
         if need_grad:
             tape = res[2]
-            ctx.spec, ctx.cfg, ctx.reg, ctx.n = spec, cfg, reg, n
+            ctx.spec, ctx.cfg, ctx.reg, ctx.n, ctx.n_err = spec, cfg, reg, n, n_err
             ctx.save_for_backward(t_eval, *tape, *[p.detach() for p in params])
         return out
 
@@ -539,11 +576,11 @@ class _LnodeSolveFn(torch.autograd.Function):
         if int(tape[0].min()) < 0:
             raise RuntimeError(f"latent ODE backward: a trajectory needed more than {TAPE_CAP} accepted steps "
                                "(tape overflow) or did not finish")
-        d = _lnode_desc(ctx.spec, cfg.ode_tanh_reg, ctx.reg, cfg.rtol, cfg.atol, 1)
+        d = _lnode_desc(ctx.spec, cfg.ode_tanh_reg, ctx.reg, cfg.rtol, cfg.atol, 1, ctx.n_err)
         if not FORCE_WIDE_LNODE_BACKWARD and lib().cb_lnode_bwd_supported(C.byref(d), int(t_eval.shape[0])):
             dz0, dW, db, dreg = lnode_solve_backward(ctx.spec, params[:n], params[n:], t_eval, tape, dz,
-                                                     cfg.ode_tanh_reg, ctx.reg, cfg.rtol, cfg.atol)
-            return (None, None, dz0, None, dreg if cfg.ode_tanh_reg else None, *dW, *db)
+                                                     cfg.ode_tanh_reg, ctx.reg, cfg.rtol, cfg.atol, ctx.n_err)
+            return (None, None, None, dz0, None, dreg if cfg.ode_tanh_reg else None, *dW, *db)
         # wide ODE net: level-synchronous discrete adjoint over the same tape (lnode_wide.py)
         from . import lnode_wide
         spec = ctx.spec
@@ -559,8 +596,12 @@ class _LnodeSolveFn(torch.autograd.Function):
         wide_params = leaves + ([reg_leaf] if cfg.ode_tanh_reg else [])
         dz0, grads = lnode_wide.solve_backward(rhs, wide_params, t_eval, tape, dz)
         dreg = grads[-1] if cfg.ode_tanh_reg else None
-        return (None, None, dz0, None, dreg, *grads[:2 * n])
+        return (None, None, None, dz0, None, dreg, *grads[:2 * n])
 
 
-def lnode_integrate(wrapper, spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor) -> Tensor:
-    return _LnodeSolveFn.apply(wrapper, spec, z0, t_eval, wrapper.ode.reg_factor, *weights, *biases)
+def lnode_integrate(wrapper, spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor, reg_factor=None,
+                    n_err: int = 0) -> Tensor:
+    """Differentiable adaptive solve; ``n_err`` > 0 restricts the controller's error norm to the leading
+    state features (fixed parameters carried as constant extra features)."""
+    reg = wrapper.ode.reg_factor if reg_factor is None else reg_factor
+    return _LnodeSolveFn.apply(wrapper, spec, int(n_err), z0, t_eval, reg, *weights, *biases)

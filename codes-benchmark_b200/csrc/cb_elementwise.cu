@@ -416,6 +416,52 @@ extern "C" int32_t cb_poly_eval_fwd(const float* d_coef, const float* d_z0, cons
   return CB_OK;
 }
 
+// Per-trajectory coefficients (LatentPoly coefficient network, latent_poly.py:357-377):
+//   z[b,t,l] = z0[b,l] + sum_{i=1..deg} C[b,l,i-1] t^i
+__global__ void poly_batched_fwd_kernel(const float* __restrict__ C, const float* __restrict__ z0,
+                                        const float* __restrict__ t, int64_t B, int T, int L, int deg,
+                                        float* __restrict__ z) {
+  const int64_t total = B * T * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int l = (int)(i % L);
+    const int64_t bt = i / L;
+    const int ti = (int)(bt % T);
+    const int64_t b = bt / T;
+    const float tv = __ldg(t + ti);
+    const float* c = C + (b * L + l) * deg;
+    float p = 0.f;
+    for (int d = deg - 1; d >= 0; --d) p = fmaf(p, tv, __ldg(c + d));  // Horner
+    z[i] = fmaf(p, tv, __ldg(z0 + b * L + l));
+  }
+}
+// dz0[b,l] = sum_t dz[b,t,l];  dC[b,l,i-1] = sum_t dz[b,t,l] t^i   (one thread per (b,l): fixed order)
+__global__ void poly_batched_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ t, int64_t B, int T,
+                                        int L, int deg, float* __restrict__ dz0, float* __restrict__ dC) {
+  const int64_t total = B * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / L;
+    const int l = (int)(i - b * L);
+    float s0 = 0.f;
+    float acc[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) acc[d] = 0.f;
+    for (int ti = 0; ti < T; ++ti) {
+      const float g = dz[(b * T + ti) * L + l];
+      const float tv = __ldg(t + ti);
+      s0 += g;
+      float pw = tv;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        if (d < deg) { acc[d] = fmaf(g, pw, acc[d]); pw *= tv; }
+      }
+    }
+    dz0[i] = s0;
+    for (int d = 0; d < deg; ++d) dC[i * deg + d] = acc[d];
+  }
+}
+
 static int poly_splits(int64_t batch) {
   int64_t s = (batch + 63) / 64;
   return (int)(s < 1 ? 1 : (s > 128 ? 128 : s));
@@ -440,6 +486,29 @@ extern "C" int32_t cb_poly_eval_bwd(const float* d_dz, const float* d_t, int64_t
   batch_colsum_partial_kernel<<<grid, 128, 0, st>>>(d_dz, batch, cols, bps, d_ws);
   CB_LAUNCH_CHECK();
   poly_bwd_coef_kernel<<<(latent * degree + 63) / 64, 64, 0, st>>>(d_ws, S, d_t, n_t, latent, degree, d_dcoef);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int32_t cb_poly_eval_batched_fwd(const float* d_coef, const float* d_z0, const float* d_t, int64_t batch,
+                                            int32_t n_t, int32_t latent, int32_t degree, float* d_z, void* stream) {
+  CB_CHECK_ARG(d_coef && d_z0 && d_t && d_z, "NULL pointer argument");
+  CB_CHECK_ARG(batch >= 0 && n_t >= 1 && latent >= 1 && degree >= 1 && degree <= 16, "bad polynomial shape");
+  if (batch == 0) return CB_OK;
+  poly_batched_fwd_kernel<<<grid_for(batch * n_t * latent), kThreads, 0, (cudaStream_t)stream>>>(
+      d_coef, d_z0, d_t, batch, n_t, latent, degree, d_z);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int32_t cb_poly_eval_batched_bwd(const float* d_dz, const float* d_t, int64_t batch, int32_t n_t,
+                                            int32_t latent, int32_t degree, float* d_dz0, float* d_dcoef,
+                                            void* stream) {
+  CB_CHECK_ARG(d_dz && d_t && d_dz0 && d_dcoef, "NULL pointer argument");
+  CB_CHECK_ARG(batch >= 0 && n_t >= 1 && latent >= 1 && degree >= 1 && degree <= 16, "bad polynomial shape");
+  if (batch == 0) return CB_OK;
+  poly_batched_bwd_kernel<<<grid_for(batch * latent, 1), kThreads, 0, (cudaStream_t)stream>>>(
+      d_dz, d_t, batch, n_t, latent, degree, d_dz0, d_dcoef);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

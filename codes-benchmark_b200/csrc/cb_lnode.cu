@@ -54,6 +54,7 @@ struct LnodeParams {
   double rtol, atol;
   int max_steps;
   int L, T, wmax_p;
+  int Le;                     // leading state features that enter the error / step-size norms (<= L)
   int weights_in_smem;
 };
 
@@ -210,13 +211,13 @@ __global__ void lnode_solve_kernel(const LnodeParams P, const float* __restrict_
   // ---- Hairer initial step, part 1: h0 and the Euler probe
   if (tid < TB) {
     double d0 = 0, d1 = 0;
-    for (int l = 0; l < L; ++l) {
+    for (int l = 0; l < P.Le; ++l) {
       const double y = sy[l * TB + tid], f = (double)kf[l * TB + tid];
       const double sc = P.atol + fabs(y) * P.rtol;
       d0 += (y / sc) * (y / sc);
       d1 += (f / sc) * (f / sc);
     }
-    d0 = sqrt(d0 / L); d1 = sqrt(d1 / L);
+    d0 = sqrt(d0 / P.Le); d1 = sqrt(d1 / P.Le);
     const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
     sh0[tid] = h0;
     sdt[tid] = d1;  // stash d1
@@ -230,14 +231,14 @@ __global__ void lnode_solve_kernel(const LnodeParams P, const float* __restrict_
   ode_rhs<TB, JT>(P, W, sB, a0, a1, kf + L * TB);  // f1 -> slot 1
   if (tid < TB) {
     double d2 = 0;
-    for (int l = 0; l < L; ++l) {
+    for (int l = 0; l < P.Le; ++l) {
       const double y = sy[l * TB + tid];
       const double sc = P.atol + fabs(y) * P.rtol;
       const double df = ((double)kf[L * TB + l * TB + tid] - (double)kf[l * TB + tid]) / sc;
       d2 += df * df;
     }
     const double h0 = sh0[tid], d1 = sdt[tid];
-    d2 = sqrt(d2 / L) / h0;
+    d2 = sqrt(d2 / P.Le) / h0;
     const double md = fmax(d1, d2);
     const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / md, 1.0 / 6.0);
     double dt = fmin(100.0 * h0, h1);
@@ -268,7 +269,7 @@ __global__ void lnode_solve_kernel(const LnodeParams P, const float* __restrict_
       const int t = tid;
       const double dt = sdt[t], tc = st[t];
       double r2 = 0.0;
-      for (int l = 0; l < L; ++l) {
+      for (int l = 0; l < P.Le; ++l) {
         double e = 0.0;
 #pragma unroll
         for (int j = 0; j < 7; ++j) e += c_berr[j] * (double)kf[j * L * TB + l * TB + t];
@@ -276,7 +277,7 @@ __global__ void lnode_solve_kernel(const LnodeParams P, const float* __restrict_
         const double bound = P.atol + P.rtol * fmax(fabs(sy[l * TB + t]), fabs(syn[l * TB + t]));
         r2 += (e / bound) * (e / bound);
       }
-      const double ratio = sqrt(r2 / L);
+      const double ratio = sqrt(r2 / P.Le);
       const bool accept = ratio < 1.0;
       double fac = (ratio == 0.0) ? 10.0 : 0.9 * pow(ratio, -0.2);
       fac = fmin(10.0, fmax(0.2, fac));
@@ -375,6 +376,7 @@ static int32_t build_params(const cb_lnode_desc* desc, int32_t n_t, LnodeParams&
   P = LnodeParams{};
   P.n_layers = m.n_layers;
   P.L = m.dims[0]; P.T = n_t;
+  P.Le = (desc->n_err > 0 && desc->n_err <= P.L) ? desc->n_err : P.L;
   P.act = m.act; P.act_param = m.act_param;
   P.tanh_reg = desc->tanh_reg; P.reg = desc->reg_factor;
   P.rtol = desc->rtol; P.atol = desc->atol; P.max_steps = desc->max_steps;

@@ -179,9 +179,11 @@ __global__ void act_bwd_mul_kernel(const float* __restrict__ dy, const float* __
   if (i < n) out[i] = dy[i] * act_bwd(act, z[i], p);
 }
 
+constexpr int kSmallTileMaxN = 64;   // output widths up to this use the 128 x 32 tile (no padded columns for 32 / 64-wide coders)
+
 template <bool A_KC, bool B_KC>
 static int32_t launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
-  if (g.N > 48) {
+  if (g.N > kSmallTileMaxN) {
     constexpr int BM = 128, BN = 128, BK = 8, TM = 8, TN = 8;
     dim3 grid((unsigned)((g.M + BM - 1) / BM), (g.N + BN - 1) / BN, splits);
     sgemm_kernel<BM, BN, BK, TM, TN, A_KC, B_KC><<<grid, (BM / TM) * (BN / TN), 0, st>>>(g);
@@ -194,11 +196,22 @@ static int32_t launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
   return CB_OK;
 }
 
-static int wgrad_splits(int64_t rows) {
-  // enough row-slabs to fill the machine, fixed function of `rows` (determinism)
+// Row slabs of the weight-gradient GEMM dW (N x K) = G^T H: a fixed function of the shapes (determinism).
+// Narrow layers (the 32 / 64-wide coders of the latent models) have one or two output tiles, so the
+// parallelism must come from the row split: ~4 CTAs per SM, at least 128 rows each.  Wide layers keep
+// 2048-row slabs.
+static int wgrad_splits(int64_t rows, int N, int K) {
+  const int bn = K > kSmallTileMaxN ? 128 : 32;
+  const int64_t tiles = (int64_t)((N + 127) / 128) * ((K + bn - 1) / bn);
   int64_t s = (rows + 2047) / 2048;
+  if (tiles < 16) {
+    int64_t want = 592 / tiles;
+    const int64_t cap = (rows + 127) / 128;
+    if (want > cap) want = cap;
+    if (want > s) s = want;
+  }
   if (s < 1) s = 1;
-  if (s > 296) s = 296;
+  if (s > 1024) s = 1024;
   return (int)s;
 }
 
@@ -251,8 +264,14 @@ extern "C" int64_t cb_mlp_workspace_floats(const cb_mlp_desc* desc, int64_t rows
       int64_t s = (int64_t)desc->dims[i] * desc->dims[i + 1];
       maxw = s > maxw ? s : maxw;
     }
-    const int S = wgrad_splits(rows);
-    w += (int64_t)S * (maxw + md);
+    int64_t part = 0;
+    for (int i = 0; i < desc->n_layers; ++i) {
+      const int64_t S = wgrad_splits(rows, desc->dims[i + 1], desc->dims[i]);
+      const int64_t need = S * ((int64_t)desc->dims[i] * desc->dims[i + 1] + desc->dims[i + 1]);
+      part = need > part ? need : part;
+    }
+    (void)maxw;
+    w += part;
   }
   return w;
 }
@@ -321,8 +340,6 @@ extern "C" int32_t cb_mlp_backward_f32(const cb_mlp_desc* desc, const float* con
   SavedLayout L = saved_layout(desc, rows);
   float* gbuf[2] = {d_ws, d_ws + rows * md};
   float* part = d_ws + 2 * rows * md;
-  const int S = wgrad_splits(rows);
-  const int64_t rows_per_split = (rows + S - 1) / S;
 
   const float* g_cur = d_dy;  // dL/dz of the current layer once final act' is applied
   int which = 0;
@@ -336,6 +353,8 @@ extern "C" int32_t cb_mlp_backward_f32(const cb_mlp_desc* desc, const float* con
   }
   for (int i = n - 1; i >= 0; --i) {
     const int N = desc->dims[i + 1], K = desc->dims[i];
+    const int S = wgrad_splits(rows, N, K);
+    const int64_t rows_per_split = (rows + S - 1) / S;
     const float* h_in = (i == 0) ? d_x : d_saved + L.post[i - 1];
     // ---- wgrad: dW[n,k] = sum_r G[r,n] H[r,k]   (M'=N, N'=K, reduction over rows)
     {

@@ -119,6 +119,16 @@ CB_API int32_t cb_poly_eval_bwd(const float* d_dz, const float* d_t, int64_t bat
                          int32_t latent, int32_t degree, float* d_dz0, float* d_dcoef,
                          float* d_workspace, int64_t workspace_floats, void* stream);
 
+/* Per-trajectory coefficients predicted by LatentPoly's coefficient network from the fixed parameters
+ * (latent_poly.py:357-377: basis (B,T,deg) bmm coef^T): coef:(batch,latent,degree) ->
+ * z[b,t,l] = z0[b,l] + sum_i coef[b,l,i-1] t^i, and its gradient (degree <= 16). */
+CB_API int32_t cb_poly_eval_batched_fwd(const float* d_coef, const float* d_z0, const float* d_t,
+                                        int64_t batch, int32_t n_t, int32_t latent, int32_t degree,
+                                        float* d_z, void* stream);
+CB_API int32_t cb_poly_eval_batched_bwd(const float* d_dz, const float* d_t, int64_t batch, int32_t n_t,
+                                        int32_t latent, int32_t degree, float* d_dz0, float* d_dcoef,
+                                        void* stream);
+
 /* ------------------------------------------------------------------- losses */
 /* mean-reduced nn.MSELoss / nn.SmoothL1Loss(beta=1) / nn.L1Loss and its gradient
  * (fcnn.py:290-291, deeponet.py:350-351, abstract_surrogate.py:705-709).
@@ -182,6 +192,10 @@ typedef struct {
   float reg_factor;
   double rtol, atol;   /* IntegralController (latent_neural_ode.py:463-465) */
   int32_t max_steps;   /* safety bound on RK iterations per trajectory     */
+  int32_t n_err;       /* leading state features in the error / step-size norms; 0 = all.  Fixed
+                        * parameters injected into the ODE net (ODEWithParams, latent_neural_ode.py:
+                        * 659-684) ride along as extra constant state features with zero derivative and
+                        * are excluded here, so the controller sees the same latent_dim-feature RMS norm. */
 } cb_lnode_desc;
 
 /* Replaces self.solver.solve(InitialValueProblem(y0=z0,t_eval)) + sol.ys

@@ -171,10 +171,22 @@ def poly_eval(coef, t):
     return basis @ coef.T  # (T, L)
 
 
-def latent_poly_forward(x0, t, enc_w, enc_b, dec_w, dec_b, coef, act="relu", act_param=0.01):
-    """x0:(B,Q), t:(T,) -> (B,T,Q).  encoder/decoder end in tanh."""
+def latent_poly_forward(x0, t, enc_w, enc_b, dec_w, dec_b, coef, act="relu", act_param=0.01, params=None,
+                        coef_w=None, coef_b=None):
+    """x0:(B,Q), t:(T,) -> (B,T,Q).  encoder/decoder end in tanh.
+    params:(B,P) with coef_w/coef_b: coefficient-network scheme (latent_poly.py:357-377: per-trajectory
+    coefficients, encoder sees x0 only); params without coef_w: concatenated to the encoder input."""
+    if params is not None and coef_w is None:
+        x0 = np.concatenate([np.asarray(x0, np.float64), np.asarray(params, np.float64)], axis=1)
     z0 = mlp_chain(x0, enc_w, enc_b, act, "tanh", act_param)       # (B,L)
-    z = z0[:, None, :] + poly_eval(coef, t)[None, :, :]             # (B,T,L)
+    if params is not None and coef_w is not None:
+        B, L = z0.shape
+        c = mlp_chain(params, coef_w, coef_b, act, "identity", act_param).reshape(B, L, -1)   # (B,L,deg)
+        tt = np.asarray(t, np.float64)
+        basis = np.stack([tt ** i for i in range(1, c.shape[2] + 1)], axis=-1)                   # (T,deg)
+        z = z0[:, None, :] + np.einsum("td,bld->btl", basis, c)
+    else:
+        z = z0[:, None, :] + poly_eval(coef, t)[None, :, :]         # (B,T,L)
     B, T, L = z.shape
     y = mlp_chain(z.reshape(B * T, L), dec_w, dec_b, act, "tanh", act_param)
     return y.reshape(B, T, -1)
@@ -459,11 +471,20 @@ def lnode_rhs(z64, ode_w, ode_b, act="relu", act_param=0.01, tanh_reg=True, reg_
 
 
 def lnode_forward(x0, t, enc_w, enc_b, ode_w, ode_b, dec_w, dec_b, act="relu", act_param=0.01,
-                  tanh_reg=True, reg_factor=1.0, rtol=1e-6, atol=1e-6, return_latent=False):
-    """ModelWrapper.forward (latent_neural_ode.py:495-520). x0:(B,Q) -> (B,T,Q)."""
+                  tanh_reg=True, reg_factor=1.0, rtol=1e-6, atol=1e-6, return_latent=False, params=None,
+                  encode_params=False):
+    """ModelWrapper.forward (latent_neural_ode.py:495-520). x0:(B,Q) -> (B,T,Q).
+    params:(B,P): concatenated to the encoder input (encode_params) or injected into the ODE net as
+    constants, ODEWithParams (latent_neural_ode.py:659-684): the solver state stays latent_dim wide."""
+    if params is not None and encode_params:
+        x0 = np.concatenate([np.asarray(x0, np.float64), np.asarray(params, np.float64)], axis=1)
     z0 = mlp_chain(x0, enc_w, enc_b, act, "tanh", act_param).astype(np.float32).astype(np.float64)
     t64 = np.asarray(t, np.float32).astype(np.float64)
-    f = lambda z: lnode_rhs(z, ode_w, ode_b, act, act_param, tanh_reg, reg_factor)  # noqa: E731
+    if params is not None and not encode_params:
+        p64 = np.asarray(params, np.float32).astype(np.float64)
+        f = lambda z: lnode_rhs(np.concatenate([z, p64], axis=1), ode_w, ode_b, act, act_param, tanh_reg, reg_factor)  # noqa: E731
+    else:
+        f = lambda z: lnode_rhs(z, ode_w, ode_b, act, act_param, tanh_reg, reg_factor)  # noqa: E731
     zs, n_steps, n_acc = tsit5_solve(f, z0, t64, rtol, atol)
     B, T, L = zs.shape
     y = mlp_chain(zs.astype(np.float32).reshape(B * T, L), dec_w, dec_b, act, "tanh", act_param)

@@ -220,6 +220,51 @@ def gen_latentpoly():
     save("latentpoly", **out)
 
 
+# ---------------------------------------------------------------- LatentPoly with fixed parameters (P > 0)
+def gen_latentpoly_params():
+    """both parametric schemes of latent_poly.py:343-381: coefficient network (coef from params, encoder on
+    x0 only) and parameter concatenation into the encoder input."""
+    out = {}
+    T, Q, P = 9, 5, 3
+    d = data(6, T, Q, 77)
+    prm = np.random.default_rng(78).uniform(-1, 1, (6, P)).astype(np.float32)
+    for tag, coeff in (("coef", True), ("cat", False)):
+        torch.manual_seed(21)
+        cfg = {"latent_features": 3, "degree": 2, "coder_layers": 2, "coder_width": 12, "activation": nn.GELU(),
+               "coeff_network": coeff, "coeff_width": 10, "coeff_layers": 3, "learning_rate": 1e-3,
+               "optimizer": "adamw", "scheduler": "cosine", "eta_min": 1e-5}
+        m = S.LatentPoly("cpu", Q, T, P, None, cfg)
+        with torch.no_grad():
+            m.model.poly.coef.weight.mul_(2.0)
+        loader, _, _ = m.prepare_data(d, None, None, np.linspace(0, 1, T), 3, shuffle=False,
+                                      dataset_train_params=prm)
+        batches = [b for b in loader]
+        out.update(sd_np(m, f"{tag}.init."))
+        y, x = m(batches[0])
+        out[f"{tag}.y0"] = y.detach().numpy()
+        loss = m.model.total_loss(x, y, batches[0][2])
+        out[f"{tag}.loss0"] = np.array(loss.item())
+        optimizer, scheduler = m.setup_optimizer_and_scheduler(4)
+        losses, first = [], True
+        for epoch in range(2):
+            for b in batches:
+                optimizer.zero_grad()
+                y, x = m(b)
+                loss = m.model.total_loss(x, y, b[2])
+                loss.backward()
+                if first:
+                    out.update(grads_np(m, f"{tag}.grad0."))
+                    first = False
+                optimizer.step()
+                losses.append(loss.item())
+            scheduler.step()
+        out.update(sd_np(m, f"{tag}.final."))
+        out[f"{tag}.losses"] = np.array(losses)
+    out["data"] = d
+    out["params"] = prm
+    save("latentpoly_params", **out)
+
+
 # ---------------------------------------------------------------- LatentNeuralODE parts (no torchode)
 def gen_lnode_parts():
     out = {}
@@ -259,4 +304,5 @@ if __name__ == "__main__":
     gen_fcnn_predict()
     gen_multionet()
     gen_latentpoly()
+    gen_latentpoly_params()
     gen_lnode_parts()

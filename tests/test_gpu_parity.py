@@ -208,6 +208,52 @@ def test_latentpoly_forward_loss_grads_training(golden):
         np.testing.assert_allclose(t2n(v), g[f"final.{k}"], rtol=2e-3, atol=2e-4)
 
 
+@pytest.mark.parametrize("tag", ["coef", "cat"])
+def test_latentpoly_parametric_variants(golden, tag):
+    """LatentPoly with fixed parameters: coefficient network (cb_poly_eval_batched_fwd/bwd) and
+    encoder concatenation -- forward, loss, first-step gradients and a 2-epoch AdamW trajectory vs the live
+    reference (tests/golden/latentpoly_params.npz); state_dict keys identical to the reference's."""
+    import codes_b200 as cb
+    g = golden("latentpoly_params")
+    T, Q, P = 9, 5, 3
+    cfg = {"latent_features": 3, "degree": 2, "coder_layers": 2, "coder_width": 12, "activation": nn.GELU(),
+           "coeff_network": tag == "coef", "coeff_width": 10, "coeff_layers": 3, "learning_rate": 1e-3,
+           "optimizer": "adamw", "scheduler": "cosine", "eta_min": 1e-5}
+    m = cb.LatentPoly(DEV, Q, T, P, None, cfg)
+    ref_keys = sorted(k[len(tag) + 6:] for k in g if k.startswith(f"{tag}.init."))
+    assert sorted(m.state_dict().keys()) == ref_keys
+    load_sd(m, g, f"{tag}.init.")
+    loader, _, _ = m.prepare_data(g["data"], None, None, np.linspace(0, 1, T), 3, shuffle=False,
+                                  dataset_train_params=g["params"])
+    batches = list(loader)
+    y, x = m(batches[0])
+    np.testing.assert_allclose(t2n(y), g[f"{tag}.y0"], rtol=3e-5, atol=3e-5)
+    loss = m.model.total_loss(x, y, batches[0][2])
+    np.testing.assert_allclose(loss.item(), g[f"{tag}.loss0"], rtol=2e-4)
+    optimizer, scheduler = m.setup_optimizer_and_scheduler(4)
+    losses, first = [], True
+    for epoch in range(2):
+        for b in batches:
+            optimizer.zero_grad()
+            y, x = m(b)
+            loss = m.model.total_loss(x, y, b[2])
+            loss.backward()
+            if first:
+                for n_, p in m.named_parameters():
+                    if f"{tag}.grad0.{n_}" not in g:      # unused module (poly.coef under the coefficient network)
+                        assert p.grad is None or float(p.grad.abs().max()) == 0.0
+                        continue
+                    ref = g[f"{tag}.grad0.{n_}"]
+                    np.testing.assert_allclose(t2n(p.grad), ref, rtol=2e-3, atol=2e-4 * np.abs(ref).max())
+                first = False
+            optimizer.step()
+            losses.append(loss.item())
+        scheduler.step()
+    np.testing.assert_allclose(losses, g[f"{tag}.losses"], rtol=2e-3)
+    for k, v in m.state_dict().items():
+        np.testing.assert_allclose(t2n(v), g[f"{tag}.final.{k}"], rtol=2e-3, atol=2e-4)
+
+
 def test_lnode_parts(golden):
     import codes_b200 as cb
     g = golden("lnode_parts")
@@ -286,6 +332,57 @@ def test_lnode_full_forward_matches_oracle():
     ref = O.lnode_forward(d[:, 0, :], np.linspace(0, 1, T), ew, eb, ow, ob, dw, db, "relu",
                           tanh_reg=True, reg_factor=1.0)
     np.testing.assert_allclose(y, ref, rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("encode_params", [False, True])
+def test_lnode_parametric_variants(encode_params, monkeypatch):
+    """LatentNeuralODE with fixed parameters: injected into the ODE net (ODEWithParams,
+    latent_neural_ode.py:659-684; here constant extra state features excluded from the error norm) or
+    concatenated to the encoder input -- forward vs the numpy oracle (which integrates the latent_dim-wide
+    state with the parameters in a closure, like the reference), gradients: kernel sweep vs level-synchronous
+    sweep, and one fit epoch."""
+    import codes_b200 as cb
+    from codes_b200 import ops
+    torch.manual_seed(6)
+    T, Q, P = 24, 7, 3
+    m = cb.LatentNeuralODE(DEV, Q, T, P, None, {"latent_features": 4, "ode_layers": 2, "ode_width": 24, "coder_width": 16,
+                                                 "coder_layers": 2, "activation": nn.SiLU(), "encode_params": encode_params})
+    with torch.no_grad():
+        for p in m.model.ode.parameters():
+            if p.dim() == 2:
+                p.mul_(2.0)
+    d = O.synthetic_dataset(20, T, Q, seed=4)
+    prm = np.random.default_rng(5).uniform(-1, 1, (20, P)).astype(np.float32)
+    loader, _, _ = m.prepare_data(d, None, None, np.linspace(0, 1, T), 20, shuffle=False, dataset_train_params=prm)
+    batch = next(iter(loader))
+    with torch.no_grad():
+        y = t2n(m(batch)[0])
+    sd = {k: t2n(v) for k, v in m.state_dict().items()}
+    chain = lambda p, idx: ([sd[f"{p}.{i}.weight"] for i in idx], [sd[f"{p}.{i}.bias"] for i in idx])  # noqa: E731
+    ode_prefix = "model.ode.mlp" if encode_params else "model.ode.base_ode.mlp"
+    ew, eb = chain("model.encoder.mlp", [0, 2, 4])
+    dw, db = chain("model.decoder.mlp", [0, 2, 4])
+    ow, ob = chain(ode_prefix, [0, 2, 4, 6])
+    ref, zs, n_steps, n_acc = O.lnode_forward(d[:, 0, :], np.linspace(0, 1, T), ew, eb, ow, ob, dw, db, "silu",
+                                               tanh_reg=True, reg_factor=1.0, return_latent=True, params=prm,
+                                               encode_params=encode_params)
+    np.testing.assert_allclose(y, ref, rtol=0, atol=3e-5)
+    # same controller up to borderline accept/reject decisions (fp32 MLP in the kernel, fp64 in the oracle)
+    assert np.abs(t2n(m.model.last_solver_stats[:, 0]).astype(np.int64) - np.asarray(n_steps)).max() <= 1
+    grads = {}
+    for force in (False, True):
+        monkeypatch.setattr(ops, "FORCE_WIDE_LNODE_BACKWARD", force)
+        m.zero_grad()
+        xp, xt = m(batch)
+        m.model.total_loss(xt, xp, batch[2].to(DEV), nn.MSELoss()).backward()
+        grads[force] = {n_: p.grad.clone() for n_, p in m.named_parameters()}
+    for n_, gk in grads[False].items():
+        assert torch.isfinite(gk).all()
+        scale = max(float(gk.abs().max()), 1e-12)
+        assert float((grads[True][n_] - gk).abs().max()) / scale < 2e-4, n_
+    monkeypatch.setattr(ops, "FORCE_WIDE_LNODE_BACKWARD", False)
+    m.fit(loader, loader, epochs=1)
+    assert np.isfinite(m.train_loss).all()
 
 
 @pytest.mark.parametrize("opt", ["adamw", "sgd"])

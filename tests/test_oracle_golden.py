@@ -156,6 +156,24 @@ def test_latentpoly_forward_loss(golden):
     np.testing.assert_allclose(loss, g["loss0"], rtol=1e-4)
 
 
+def test_latentpoly_parametric_forward(golden):
+    """P > 0: coefficient-network scheme and encoder-concatenation scheme vs the live reference."""
+    g = golden("latentpoly_params")
+    d, prm = g["data"][:3], g["params"][:3]
+    t = np.linspace(0, 1, d.shape[1])
+    for tag in ("coef", "cat"):
+        ew, eb = chain(g, f"{tag}.init.model.encoder.mlp.", [0, 2, 4])
+        dw, db = chain(g, f"{tag}.init.model.decoder.mlp.", [0, 2, 4])
+        kw = {}
+        if tag == "coef":
+            names = ["0", "2.0", "3.0", "4"]
+            kw = {"coef_w": [g[f"coef.init.model.coefficient_net.{n}.weight"] for n in names],
+                  "coef_b": [g[f"coef.init.model.coefficient_net.{n}.bias"] for n in names]}
+        y = O.latent_poly_forward(d[:, 0, :], t, ew, eb, dw, db, g[f"{tag}.init.model.poly.coef.weight"], "gelu",
+                                  params=prm, **kw)
+        np.testing.assert_allclose(y, g[f"{tag}.y0"], rtol=2e-5, atol=2e-5)
+
+
 def test_lnode_parts(golden):
     g = golden("lnode_parts")
     ew, eb = chain(g, "sd.model.encoder.mlp.", [0, 2, 4])
