@@ -217,5 +217,8 @@ def test_activation_mapping_and_unsupported_modules():
         ops.activation_spec(nn.GELU(approximate="tanh"))
     with pytest.raises(NotImplementedError):
         ops.activation_spec(nn.Hardtanh())
-    with pytest.raises(NotImplementedError):
-        cb.LatentPoly("cpu", 3, 5, 2, None, {"coeff_network": True})
+    # parametric variants construct with the reference's module tree (state_dict key parity)
+    m = cb.LatentPoly("cpu", 3, 5, 2, None, {"coeff_network": True, "coeff_layers": 3})
+    assert "model.coefficient_net.2.0.weight" in m.state_dict() and m.model.encoder.mlp[0].in_features == 3
+    m = cb.LatentNeuralODE("cpu", 3, 5, 2, None, {})
+    assert "model.ode.base_ode.mlp.0.weight" in m.state_dict() and m.model.ode.base_ode.mlp[0].in_features == 5 + 2
