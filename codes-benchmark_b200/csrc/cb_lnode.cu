@@ -353,6 +353,18 @@ static size_t lnode_smem_bytes(const LnodeParams& P) {
 
 using namespace cb;
 
+// Dynamic shared memory a kernel may request: the opt-in per-block maximum minus the kernel's STATIC shared
+// memory (reduction scratch etc.) -- requesting more makes cudaFuncSetAttribute fail with "invalid argument".
+template <typename K>
+static int usable_dynamic_smem(K kernel) {
+  int dev = 0, max_smem = 232448;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) max_smem -= (int)fa.sharedSizeBytes;
+  else cudaGetLastError();
+  return max_smem;
+}
+
 extern "C" int64_t cb_lnode_workspace_floats(const cb_lnode_desc* desc) {
   if (!desc || check_desc(&desc->ode) != CB_OK) return -1;
   int64_t w = 0;
@@ -430,9 +442,8 @@ extern "C" int32_t cb_lnode_solve_fwd(const cb_lnode_desc* desc, const float* co
   float* gW = d_ws;
   float* gB = d_ws + P.total_w;
   if (int32_t e = pack_weights(P, d_W, d_b, gW, gB, st)) return e;
-  int dev = 0, max_smem = 0;
-  CB_CUDA(cudaGetDevice(&dev));
-  CB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  int max_smem = usable_dynamic_smem(lnode_solve_kernel<64, 4>);
+  { const int m32 = usable_dynamic_smem(lnode_solve_kernel<32, 8>); max_smem = m32 < max_smem ? m32 : max_smem; }
   // prefer resident weights; fall back to streamed weights, then TB=32
   P.weights_in_smem = 1;
   bool use64 = true;
@@ -797,10 +808,7 @@ extern "C" int64_t cb_lnode_bwd_workspace_floats(const cb_lnode_desc* desc, int6
 extern "C" int32_t cb_lnode_bwd_supported(const cb_lnode_desc* desc, int32_t n_t) {
   LnodeParams P;
   if (build_params(desc, n_t, P) != CB_OK) return 0;
-  int dev = 0, max_smem = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
-    max_smem = 232448;
+  const int max_smem = usable_dynamic_smem(lnode_bwd_kernel);
   P.weights_in_smem = 0;
   return lnode_bwd_smem_bytes(P) <= (size_t)max_smem ? 1 : 0;
 }
@@ -827,9 +835,7 @@ extern "C" int32_t cb_lnode_solve_bwd(const cb_lnode_desc* desc, const float* co
   const int slab_floats = (P.total_w + P.total_b + 1 + 3) & ~3;
   const int n_cta = (int)((batch + kBT - 1) / kBT);
   if (int32_t e = pack_weights(P, d_W, d_b, gW, gB, st)) return e;
-  int dev = 0, max_smem = 0;
-  CB_CUDA(cudaGetDevice(&dev));
-  CB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const int max_smem = usable_dynamic_smem(lnode_bwd_kernel);
   P.weights_in_smem = 1;
   if (lnode_bwd_smem_bytes(P) > (size_t)max_smem) P.weights_in_smem = 0;
   const size_t smem = lnode_bwd_smem_bytes(P);
