@@ -7,6 +7,8 @@
 //   forward  Z[r,n]  = sum_k H[r,k]  W[n,k]   (+bias, activation epilogue)
 //   dgrad    Gp[r,k] = sum_n G[r,n]  W[n,k]   (* act'(z_prev) epilogue)
 //   wgrad    dW[n,k] = sum_r G[r,n]  H[r,k]   (split over rows, 2-pass deterministic)
+#include <cstdlib>
+
 #include "cb_common.cuh"
 
 namespace cb {
@@ -245,6 +247,290 @@ static int max_dim(const cb_mlp_desc* d) {
   return m;
 }
 
+
+// ============================================================================ narrow chains (width <= 64)
+// The coders of the latent models (Encoder / Decoder, latent_neural_ode.py:687-742; defaults 32 / 64 wide,
+// 4 Linears) are launch- and latency-bound on the per-layer SGEMM path: ~25 launches per backward, each a
+// handful of CTAs waiting on dependent global loads.  These two kernels run the WHOLE chain per 64-row tile
+// inside one persistent CTA with every weight in shared memory:
+//   narrow_fwd_kernel   all layers forward; writes y and (training) the saved post-/pre-activations
+//   narrow_bwd_kernel   all layers backward: dgrad chain + wgrad/bias-grad accumulated in shared memory
+//                       over the CTA's tiles (fixed tile -> CTA map), one slab per CTA
+//   narrow_reduce_kernel  fixed-order sum of the slabs -> deterministic dW / db
+// fp32 FFMA, same formulas as the SGEMM path (act_fwd / act_bwd on the fp32 pre-activation).
+constexpr int kNarrowRows = 64;
+constexpr int kNarrowThreads = 256;
+constexpr int kNarrowMaxLayers = 6;
+
+struct NarrowParams {
+  int n, act, final_act;
+  float ap;
+  int K[kNarrowMaxLayers], N[kNarrowMaxLayers];
+  const float* W[kNarrowMaxLayers];
+  const float* b[kNarrowMaxLayers];
+  float* post[kNarrowMaxLayers];       // saved activations (forward writes, backward reads); may be NULL
+  float* pre[kNarrowMaxLayers];
+  const float* x;
+  float* y;                            // forward output
+  const float* dy;                     // backward input
+  float* dx;                           // backward: gradient w.r.t. x (nullable)
+  float* slabs;                        // backward: [n_cta][n][WP*WP + WP]
+  long long rows;
+  int num_tiles;
+};
+
+// vector of V (2 or 4) consecutive floats in shared memory (one LDS.64 / LDS.128)
+template <int V> struct NVec;
+template <> struct NVec<4> { float v[4]; __device__ __forceinline__ void load(const float* p) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
+template <> struct NVec<2> { float v[2]; __device__ __forceinline__ void load(const float* p) { const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; } };
+
+// acc[4][TC] += rows[4][0..kmax) . Wm[0..kmax)[tx*TC..]   (rows: 4 tile rows of `src`, 4 k's per step:
+// 4 LDS.128 for the rows + 4 vector loads of the weights per 16*TC FMAs)
+template <int WP, int TC>
+__device__ __forceinline__ void narrow_rows_times_w(const float* __restrict__ src, int ld, int row0, const float* __restrict__ Wm,
+                                                    int col0, int kmax, float (&acc)[4][TC]) {
+  for (int k = 0; k < kmax; k += 4) {
+    NVec<4> a[4];
+    NVec<TC> w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i].load(src + (row0 + i) * ld + k);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) w[kk].load(Wm + (k + kk) * WP + col0);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < TC; ++c) acc[i][c] = fmaf(a[i].v[kk], w[kk].v[c], acc[i][c]);
+  }
+}
+
+template <int WP>
+__global__ void __launch_bounds__(kNarrowThreads) narrow_fwd_kernel(const NarrowParams P) {
+  constexpr int TR = 4, TC = WP / 16, LD = WP + 4;
+  extern __shared__ __align__(16) float nsm[];
+  float* Wt = nsm;                                   // [n][WP][WP]  Wt[l][k][j] = W_l[j][k]
+  float* bs = Wt + P.n * WP * WP;                    // [n][WP]
+  float* A0 = bs + P.n * WP;                         // [2][64][LD]
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  // transpose on the way in: global reads run along k (coalesced), the strided shared-memory writes are cheap
+#pragma unroll 8
+  for (int idx = tid; idx < P.n * WP * WP; idx += kNarrowThreads) {
+    const int l = idx / (WP * WP), rem = idx - l * WP * WP, j = rem / WP, k = rem - j * WP;
+    Wt[l * WP * WP + k * WP + j] = (j < P.N[l] && k < P.K[l]) ? __ldg(P.W[l] + (size_t)j * P.K[l] + k) : 0.f;
+  }
+  for (int idx = tid; idx < P.n * WP; idx += kNarrowThreads) {
+    const int l = idx / WP, j = idx - l * WP;
+    bs[idx] = (j < P.N[l] && P.b[l]) ? __ldg(P.b[l] + j) : 0.f;
+  }
+  for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+    const long long r0 = (long long)tile * kNarrowRows;
+    __syncthreads();
+    const int K0 = P.K[0];
+    for (int idx = tid; idx < kNarrowRows * WP; idx += kNarrowThreads) {
+      const int r = idx / WP, k = idx - r * WP;
+      A0[r * LD + k] = (k < K0 && r0 + r < P.rows) ? __ldg(P.x + (r0 + r) * K0 + k) : 0.f;
+    }
+    __syncthreads();
+    int cur = 0;
+    for (int l = 0; l < P.n; ++l) {
+      const float* A = A0 + cur * kNarrowRows * LD;
+      float* An = A0 + (cur ^ 1) * kNarrowRows * LD;
+      float acc[TR][TC];
+#pragma unroll
+      for (int c = 0; c < TC; ++c) {
+        const float bj = bs[l * WP + tx * TC + c];
+#pragma unroll
+        for (int i = 0; i < TR; ++i) acc[i][c] = bj;
+      }
+      narrow_rows_times_w<WP, TC>(A, LD, ty * TR, Wt + l * WP * WP, tx * TC, (P.K[l] + 3) & ~3, acc);
+      const bool last = l == P.n - 1;
+      const int act = last ? P.final_act : P.act;
+      const int Nl = P.N[l];
+#pragma unroll
+      for (int i = 0; i < TR; ++i) {
+        const int r = ty * TR + i;
+        const long long rg = r0 + r;
+#pragma unroll
+        for (int c = 0; c < TC; ++c) {
+          const int col = tx * TC + c;
+          const float z = acc[i][c];
+          const float h = act_fwd(act, z, P.ap);
+          if (col < Nl && rg < P.rows) {
+            if (P.pre[l]) P.pre[l][rg * Nl + col] = z;
+            if (last) P.y[rg * Nl + col] = h;
+            else if (P.post[l]) P.post[l][rg * Nl + col] = h;
+          }
+          if (!last) An[r * LD + col] = (col < Nl) ? h : 0.f;
+        }
+      }
+      __syncthreads();
+      cur ^= 1;
+    }
+  }
+}
+
+template <int WP>
+__global__ void __launch_bounds__(kNarrowThreads) narrow_bwd_kernel(const NarrowParams P) {
+  constexpr int TR = 4, TC = WP / 16, LD = WP + 4, WT = WP / 16;   // WT x WT cells of dW per thread
+  extern __shared__ __align__(16) float nsm[];
+  float* Wj = nsm;                                   // [n][WP][WP]  Wj[l][j][k] = W_l[j][k]
+  float* dWa = Wj + P.n * WP * WP;                   // [n][WP][WP]
+  float* dba = dWa + P.n * WP * WP;                  // [n][WP]
+  float* G = dba + P.n * WP;                         // [64][LD] gradient w.r.t. the current layer's pre-activation
+  float* Gp = G + kNarrowRows * LD;
+  float* Hs = Gp + kNarrowRows * LD;                 // layer input tile
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+#pragma unroll 8
+  for (int idx = tid; idx < P.n * WP * WP; idx += kNarrowThreads) {
+    const int l = idx / (WP * WP), rem = idx - l * WP * WP, j = rem / WP, k = rem - j * WP;
+    Wj[idx] = (j < P.N[l] && k < P.K[l]) ? __ldg(P.W[l] + (size_t)j * P.K[l] + k) : 0.f;
+    dWa[idx] = 0.f;
+  }
+  for (int idx = tid; idx < P.n * WP; idx += kNarrowThreads) dba[idx] = 0.f;
+  for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+    const long long r0 = (long long)tile * kNarrowRows;
+    __syncthreads();
+    {
+      const int l = P.n - 1, Nl = P.N[l];
+      for (int idx = tid; idx < kNarrowRows * WP; idx += kNarrowThreads) {
+        const int r = idx / WP, j = idx - r * WP;
+        float g = 0.f;
+        if (j < Nl && r0 + r < P.rows) {
+          g = __ldg(P.dy + (r0 + r) * Nl + j);
+          if (P.final_act != CB_ACT_IDENTITY) g *= act_bwd(P.final_act, __ldg(P.pre[l] + (r0 + r) * Nl + j), P.ap);
+        }
+        G[r * LD + j] = g;
+      }
+    }
+    float* g_cur = G;
+    float* g_nxt = Gp;
+    for (int l = P.n - 1; l >= 0; --l) {
+      const int Kl = P.K[l], Nl = P.N[l];
+      const float* src = (l == 0) ? P.x : P.post[l - 1];
+      for (int idx = tid; idx < kNarrowRows * WP; idx += kNarrowThreads) {
+        const int r = idx / WP, k = idx - r * WP;
+        Hs[r * LD + k] = (k < Kl && r0 + r < P.rows) ? __ldg(src + (r0 + r) * Kl + k) : 0.f;
+      }
+      __syncthreads();
+      {
+        // weight gradient: cells (j0.., k0..) of dW_l, summed over the tile's rows in row order
+        const int j0 = ty * WT, k0 = tx * WT;
+        float acc[WT][WT], gs[WT];
+#pragma unroll
+        for (int a = 0; a < WT; ++a) {
+          gs[a] = 0.f;
+#pragma unroll
+          for (int c = 0; c < WT; ++c) acc[a][c] = 0.f;
+        }
+#pragma unroll 4
+        for (int r = 0; r < kNarrowRows; ++r) {
+          NVec<WT> g, h;
+          g.load(g_cur + r * LD + j0);
+          h.load(Hs + r * LD + k0);
+#pragma unroll
+          for (int a = 0; a < WT; ++a) {
+            gs[a] += g.v[a];
+#pragma unroll
+            for (int c = 0; c < WT; ++c) acc[a][c] = fmaf(g.v[a], h.v[c], acc[a][c]);
+          }
+        }
+        float* dst = dWa + l * WP * WP;
+#pragma unroll
+        for (int a = 0; a < WT; ++a) {
+#pragma unroll
+          for (int c = 0; c < WT; ++c) dst[(j0 + a) * WP + k0 + c] += acc[a][c];
+          if (tx == 0) dba[l * WP + j0 + a] += gs[a];
+        }
+      }
+      if (l > 0 || P.dx) {
+        // data gradient: Gp[r][k] = sum_j G[r][j] W[j][k]  (* act'(z_{l-1}))
+        float acc[TR][TC];
+#pragma unroll
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+          for (int c = 0; c < TC; ++c) acc[i][c] = 0.f;
+        narrow_rows_times_w<WP, TC>(g_cur, LD, ty * TR, Wj + l * WP * WP, tx * TC, (Nl + 3) & ~3, acc);
+#pragma unroll
+        for (int i = 0; i < TR; ++i) {
+          const int r = ty * TR + i;
+          const long long rg = r0 + r;
+#pragma unroll
+          for (int c = 0; c < TC; ++c) {
+            const int k = tx * TC + c;
+            float v = acc[i][c];
+            if (l > 0) {
+              if (k < Kl && rg < P.rows) v *= act_bwd(P.act, __ldg(P.pre[l - 1] + rg * Kl + k), P.ap);
+              else v = 0.f;
+              g_nxt[r * LD + k] = v;
+            } else if (k < Kl && rg < P.rows) {
+              P.dx[rg * Kl + k] = v;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      float* t = g_cur; g_cur = g_nxt; g_nxt = t;
+    }
+  }
+  __syncthreads();
+  float* slab = P.slabs + (size_t)blockIdx.x * P.n * (WP * WP + WP);
+  for (int idx = tid; idx < P.n * WP * WP; idx += kNarrowThreads) {
+    const int l = idx / (WP * WP);
+    slab[(size_t)l * (WP * WP + WP) + (idx - l * WP * WP)] = dWa[idx];
+  }
+  for (int idx = tid; idx < P.n * WP; idx += kNarrowThreads) {
+    const int l = idx / WP;
+    slab[(size_t)l * (WP * WP + WP) + WP * WP + (idx - l * WP)] = dba[idx];
+  }
+}
+
+// dW[j][k] = sum_cta slab[cta][l][j][k], db[j] = sum_cta slab[cta][l][WP*WP + j]   (fixed order; blockIdx.y = layer)
+struct NarrowReduce {
+  int n, n_cta, WP;
+  int N[kNarrowMaxLayers], K[kNarrowMaxLayers];
+  float* dW[kNarrowMaxLayers];
+  float* db[kNarrowMaxLayers];
+};
+__global__ void narrow_reduce_kernel(const float* __restrict__ slabs, const NarrowReduce R) {
+  const int l = blockIdx.y, WP = R.WP, N = R.N[l], K = R.K[l];
+  const size_t per_l = (size_t)WP * WP + WP, per_cta = per_l * R.n;
+  float* dW = R.dW[l];
+  float* db = R.db[l];
+  const int total = N * K + (db ? N : 0);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    size_t off;
+    if (i < N * K) { const int j = i / K, k = i - j * K; off = (size_t)j * WP + k; }
+    else off = (size_t)WP * WP + (i - N * K);
+    float acc = 0.f;
+    for (int c = 0; c < R.n_cta; ++c) acc += slabs[(size_t)c * per_cta + (size_t)l * per_l + off];
+    if (i < N * K) dW[i] = acc; else db[i - N * K] = acc;
+  }
+}
+
+// 0 = not a narrow chain, else the padded width (32 or 64)
+static int narrow_width(const cb_mlp_desc* d) {
+  if (getenv("CB_NO_NARROW_CHAIN")) return 0;
+  int m = 0;
+  for (int i = 0; i <= d->n_layers; ++i) m = d->dims[i] > m ? d->dims[i] : m;
+  if (m > 64) return 0;
+  const int wp = m <= 32 ? 32 : 64;
+  if (d->n_layers > (wp == 32 ? kNarrowMaxLayers : 5)) return 0;   // backward: 2 weight-sized arrays per layer in smem
+  return wp;
+}
+static int narrow_ctas(int64_t rows, int wp = 64) {
+  const int64_t tiles = (rows + kNarrowRows - 1) / kNarrowRows;
+  const int cap = num_sms() * (wp == 32 ? 2 : 1);   // 32-wide chains: two CTAs fit per SM
+  return (int)(tiles < cap ? tiles : cap);
+}
+static size_t narrow_fwd_smem(int n, int wp) { return ((size_t)n * wp * wp + (size_t)n * wp + 2 * kNarrowRows * (wp + 4)) * sizeof(float); }
+static size_t narrow_bwd_smem(int n, int wp) { return ((size_t)2 * n * wp * wp + (size_t)n * wp + 3 * kNarrowRows * (wp + 4)) * sizeof(float); }
+static int64_t narrow_slab_floats(const cb_mlp_desc* d, int64_t rows) {
+  const int wp = narrow_width(d);
+  if (!wp) return 0;
+  return (int64_t)narrow_ctas(rows, wp) * d->n_layers * ((int64_t)wp * wp + wp);
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -271,7 +557,8 @@ extern "C" int64_t cb_mlp_workspace_floats(const cb_mlp_desc* desc, int64_t rows
       part = need > part ? need : part;
     }
     (void)maxw;
-    w += part;
+    const int64_t slabs = narrow_slab_floats(desc, rows);
+    w += part > slabs ? part : slabs;
   }
   return w;
 }
@@ -295,6 +582,29 @@ extern "C" int32_t cb_mlp_forward_f32(const cb_mlp_desc* desc, const float* cons
     }
   }
   SavedLayout L = saved_layout(desc, rows);
+  if (const int wp = narrow_width(desc)) {
+    // whole chain in one persistent launch (weights in shared memory)
+    NarrowParams P{};
+    P.n = n; P.act = desc->act; P.final_act = desc->final_act; P.ap = desc->act_param;
+    for (int i = 0; i < n; ++i) {
+      P.K[i] = desc->dims[i]; P.N[i] = desc->dims[i + 1];
+      P.W[i] = d_W[i]; P.b[i] = d_b[i];
+      P.post[i] = (d_saved && L.post[i] >= 0) ? d_saved + L.post[i] : nullptr;
+      P.pre[i] = (d_saved && L.pre[i] >= 0) ? d_saved + L.pre[i] : nullptr;
+    }
+    P.x = d_x; P.y = d_y; P.rows = rows;
+    P.num_tiles = (int)((rows + kNarrowRows - 1) / kNarrowRows);
+    const size_t smem = narrow_fwd_smem(n, wp);
+    if (wp == 32) {
+      CB_CUDA(cudaFuncSetAttribute(narrow_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      narrow_fwd_kernel<32><<<narrow_ctas(rows, 32), kNarrowThreads, smem, st>>>(P);
+    } else {
+      CB_CUDA(cudaFuncSetAttribute(narrow_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      narrow_fwd_kernel<64><<<narrow_ctas(rows), kNarrowThreads, smem, st>>>(P);
+    }
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
   const float* in = d_x;
   for (int i = 0; i < n; ++i) {
     const bool last = (i == n - 1);
@@ -340,6 +650,35 @@ extern "C" int32_t cb_mlp_backward_f32(const cb_mlp_desc* desc, const float* con
   SavedLayout L = saved_layout(desc, rows);
   float* gbuf[2] = {d_ws, d_ws + rows * md};
   float* part = d_ws + 2 * rows * md;
+  if (const int wp = narrow_width(desc)) {
+    NarrowParams P{};
+    P.n = n; P.act = desc->act; P.final_act = desc->final_act; P.ap = desc->act_param;
+    for (int i = 0; i < n; ++i) {
+      P.K[i] = desc->dims[i]; P.N[i] = desc->dims[i + 1];
+      P.W[i] = d_W[i];
+      P.post[i] = (d_saved && L.post[i] >= 0) ? const_cast<float*>(d_saved) + L.post[i] : nullptr;
+      P.pre[i] = (d_saved && L.pre[i] >= 0) ? const_cast<float*>(d_saved) + L.pre[i] : nullptr;
+      CB_CHECK_ARG(d_dW[i] != nullptr, "dW[%d] is NULL", i);
+    }
+    P.x = d_x; P.dy = d_dy; P.dx = d_dx; P.rows = rows; P.slabs = part;
+    P.num_tiles = (int)((rows + kNarrowRows - 1) / kNarrowRows);
+    const int ctas = narrow_ctas(rows, wp);
+    const size_t smem = narrow_bwd_smem(n, wp);
+    if (wp == 32) {
+      CB_CUDA(cudaFuncSetAttribute(narrow_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      narrow_bwd_kernel<32><<<ctas, kNarrowThreads, smem, st>>>(P);
+    } else {
+      CB_CUDA(cudaFuncSetAttribute(narrow_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      narrow_bwd_kernel<64><<<ctas, kNarrowThreads, smem, st>>>(P);
+    }
+    CB_LAUNCH_CHECK();
+    NarrowReduce R{};
+    R.n = n; R.n_cta = ctas; R.WP = wp;
+    for (int i = 0; i < n; ++i) { R.N[i] = P.N[i]; R.K[i] = P.K[i]; R.dW[i] = d_dW[i]; R.db[i] = d_db[i]; }
+    narrow_reduce_kernel<<<dim3((wp * wp + wp + 255) / 256, n), 256, 0, st>>>(part, R);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
 
   const float* g_cur = d_dy;  // dL/dz of the current layer once final act' is applied
   int which = 0;
