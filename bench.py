@@ -325,14 +325,14 @@ def run_ours(args):
             if len(batches) == 4:
                 break
 
-        def train_step(bt):
-            opt.zero_grad()
+        def fwd_bwd(bt):
             out, tgt = tr_model(bt)
             loss = ops.pointwise_loss(out, tgt, "mse")
             loss.backward()
-            opt.step()
+            return loss
 
-        for i in range(3):
+        train_step = tr_model._train_stepper(opt, fwd_bwd)   # the fit loop's stepper (eager warm-up, then CUDA graph)
+        for i in range(6):
             train_step(batches[i % len(batches)])
         barrier()
         n_train_steps = max(10, min(50, args.steps // 4))

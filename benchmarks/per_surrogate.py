@@ -38,7 +38,8 @@ def mac(dims):
 
 
 def time_predict(model, loader, n_traj, passes=3):
-    model.predict(loader)
+    for _ in range(4):            # warm-up passes (plans, allocator pools of the H2D prefetch stream)
+        model.predict(loader)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(passes):
@@ -51,8 +52,8 @@ def time_predict(model, loader, n_traj, passes=3):
 def time_train(step_fn, loader, n_steps):
     it = iter(loader)
     batches = [next(it) for _ in range(min(n_steps, len(loader)))]
-    for b in batches[:2]:
-        step_fn(b)
+    for i in range(6):                       # eager warm-up steps of the stepper + the graph capture
+        step_fn(batches[i % len(batches)])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     n = 0
@@ -81,16 +82,19 @@ def bench_flat(name, cls, cfg, Q, T, n_train, n_test, batch_rows, dims_list, ext
     kind = cb.fcnn.criterion_kind(m.config.loss_function)
     m.train(); opt.train()
 
-    def step(batch):
-        opt.zero_grad()
+    def fwd_bwd(batch):
         out = m(batch)
         loss = cb.ops.pointwise_loss(out[0], out[1], kind)
         loss.backward()
-        opt.step()
+        return loss
+
+    def step(batch):                                   # the fit loop's stepper: eager warm-up, then a CUDA graph
+        m._train_stepper(opt, fwd_bwd)(batch)
 
     # training arithmetic: bf16 = tcgen05 GEMMs for forward / dgrad / wgrad (default), fp32 = FFMA exact mode
     for mode in ("bf16", "fp32"):
         cb.set_train_precision(mode)
+        m.__dict__.pop("_stepper", None)               # new arithmetic => new captured graph
         sps = time_train(step, tr, 30 if mode == "bf16" else 8)
         res[f"train_rows_per_s_{mode}"] = sps * batch_rows
         res[f"train_samples_per_s_{mode}"] = sps * batch_rows / T
@@ -121,14 +125,16 @@ def bench_latent(name, cls, cfg, Q, T, n_train, n_test, batch, flop_traj):
     m.train(); opt.train()
     crit = getattr(m.config, "loss_function", nn.MSELoss())
 
-    def step(batch):
-        opt.zero_grad()
+    def fwd_bwd(batch):
         xp, xt = m(batch)
         loss = m.model.total_loss(xt, xp, None, crit) if isinstance(m, cb.LatentNeuralODE) else m.model.total_loss(xt, xp, None)
         loss.backward()
-        opt.step()
+        return loss
 
-    sps = time_train(step, tr, 12)
+    def step(batch):
+        m._train_stepper(opt, fwd_bwd, graphable=not isinstance(m, cb.LatentNeuralODE))(batch)
+
+    sps = time_train(step, tr, 60)
     res["train_samples_per_s"] = sps * batch
     return res, m
 

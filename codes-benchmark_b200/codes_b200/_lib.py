@@ -75,6 +75,8 @@ _SIGNATURES = {
     "cb_sgd_step": (_I32, [_PP, _PP, _PP, C.POINTER(_I64), _I32, _F, _F, _F, _I64, _P]),
     "cb_schedulefree_adamw_step": (_I32, [_PP, _PP, _PP, _PP, C.POINTER(_I64), _I32, _F, _F, _F, _F, _F, _F, _F, _P]),
     "cb_schedulefree_sgd_step": (_I32, [_PP, _PP, _PP, C.POINTER(_I64), _I32, _F, _F, _F, _F, _P]),
+    "cb_set_floats": (_I32, [_P, _I32, C.POINTER(_F), _P]),
+    "cb_optimizer_step_dev": (_I32, [_I32, _PP, _PP, _PP, _PP, C.POINTER(_I64), _I32, _P, _P]),
     "cb_lerp_tensors": (_I32, [_PP, _PP, C.POINTER(_I64), _I32, _F, _P]),
     "cb_gather_rows": (_I32, [_P, _P, _I64, _I64, _I32, _P, _P]),
     "cb_denormalize": (_I32, [_P, _I64, _I32, _I32, _P, _P, _I32, _P, _P]),

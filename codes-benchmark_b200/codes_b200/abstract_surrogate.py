@@ -105,6 +105,17 @@ class AbstractSurrogateModel(ABC, nn.Module):
     def fit(self, train_loader, test_loader, epochs, position, description, multi_objective):
         ...
 
+    # ------------------------------------------------------------------ training step
+    def _train_stepper(self, optimizer, fwd_bwd, graphable: bool = True):
+        """step(batch) for the fit loops: eager for the first batches of a shape, then a captured CUDA graph
+        of forward + loss + backward + fused optimizer update (codes_b200/graph_step.py)."""
+        from .graph_step import GraphedTrainStep
+        st = self.__dict__.get("_stepper")
+        if st is None or st.optimizer is not optimizer:
+            st = GraphedTrainStep(fwd_bwd, optimizer, self.device, enabled=graphable)
+            self.__dict__["_stepper"] = st
+        return st
+
     # ------------------------------------------------------------------ inference
     def predict(self, data_loader: DataLoader, leave_log: bool = False,
                 leave_norm: bool = False) -> tuple[Tensor, Tensor]:

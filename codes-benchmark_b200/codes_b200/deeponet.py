@@ -173,12 +173,16 @@ class MultiONet(OperatorNetwork):
 
     def epoch(self, data_loader: DataLoader, criterion: nn.Module, optimizer: torch.optim.Optimizer):
         kind = criterion_kind(criterion)
-        for branch_input, trunk_input, targets in data_loader:
-            optimizer.zero_grad()
-            outputs, targets = self((branch_input, trunk_input, targets))
+
+        def fwd_bwd(batch):
+            outputs, targets = self(batch)
             loss = ops.pointwise_loss(outputs, targets, kind)
             loss.backward()
-            optimizer.step()
+            return loss
+
+        step = self._train_stepper(optimizer, fwd_bwd)
+        for batch in data_loader:
+            step(batch)
 
 
 AbstractSurrogateModel.register(MultiONet)

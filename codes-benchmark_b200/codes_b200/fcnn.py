@@ -145,12 +145,16 @@ class FullyConnected(AbstractSurrogateModel):
 
     def epoch(self, data_loader: DataLoader, criterion: nn.Module, optimizer: torch.optim.Optimizer):
         kind = criterion_kind(criterion)
-        for inputs, targets in data_loader:
-            optimizer.zero_grad()
-            outputs, targets = self((inputs, targets))
+
+        def fwd_bwd(batch):
+            outputs, targets = self(batch)
             loss = ops.pointwise_loss(outputs, targets, kind)
             loss.backward()
-            optimizer.step()
+            return loss
+
+        step = self._train_stepper(optimizer, fwd_bwd)
+        for batch in data_loader:
+            step(batch)
 
 
 AbstractSurrogateModel.register(FullyConnected)

@@ -160,16 +160,17 @@ class LatentPoly(AbstractSurrogateModel):
         optimizer.train()
         self.setup_checkpoint()
         epoch = -1
+        def fwd_bwd(batch):
+            x_pred, x_true = self(batch)
+            params = batch[2].to(self.device) if isinstance(batch[2], Tensor) else None
+            loss = self.model.total_loss(x_true, x_pred, params)
+            loss.backward()
+            return loss
+
+        step = self._train_stepper(optimizer, fwd_bwd)
         for epoch in progress_bar:
             for batch in train_loader:
-                params = batch[2]
-                optimizer.zero_grad()
-                x_pred, x_true = self(batch)
-                if isinstance(params, Tensor):
-                    params = params.to(self.device)
-                loss = self.model.total_loss(x_true, x_pred, params)
-                loss.backward()
-                optimizer.step()
+                step(batch)
             scheduler.step()
             self.validate(epoch=epoch, train_loader=train_loader, test_loader=test_loader,
                           optimizer=optimizer, progress_bar=progress_bar, total_epochs=epochs,

@@ -10,6 +10,7 @@ unchanged; the update itself runs in ``libcodes_b200.so``.
 from __future__ import annotations
 
 import ctypes as C
+import struct
 
 import torch
 from torch.optim import Optimizer
@@ -26,6 +27,11 @@ def _sizes(tensors):
     for i, t in enumerate(tensors):
         arr[i] = t.numel()
     return arr
+
+
+def _f32(x: float) -> float:
+    """x rounded to fp32 (what a by-value float argument of the C ABI sees)."""
+    return struct.unpack("f", struct.pack("f", float(x)))[0]
 
 
 def _touch(params) -> None:
@@ -53,6 +59,52 @@ class _FusedBase(Optimizer):
             if nme not in st:
                 st[nme] = torch.zeros_like(p, memory_format=torch.preserve_format)
         return st
+
+    # ---- CUDA-graph support (codes_b200/graph_step.py): the update kernel inside a captured training step
+    # reads its scalars from a small device buffer; the host side of a step (`graph_prepare`) advances the
+    # counters exactly like `step()` and rewrites that buffer, then the graph is replayed.
+    _kind = -1
+
+    def _graph_hyper(self, group):       # -> list of floats in the device layout of cb_optimizer_step_dev
+        raise NotImplementedError
+
+    def _graph_states(self, group, params):   # -> (state list 1 | None, state list 2 | None)
+        raise NotImplementedError
+
+    @torch.no_grad()
+    def graph_prepare(self):
+        bufs = self.__dict__.setdefault("_hyper_dev", {})
+        for gi, group in enumerate(self.param_groups):
+            params = [p for p in group["params"] if p.requires_grad]
+            if not params:
+                continue
+            vals = [float(v) for v in self._graph_hyper(group)]
+            dev = params[0].device
+            if gi not in bufs:
+                bufs[gi] = torch.zeros(16, device=dev, dtype=torch.float32)
+            arr = (C.c_float * len(vals))(*vals)
+            with torch.cuda.device(dev):
+                check(lib().cb_set_floats(C.c_void_p(bufs[gi].data_ptr()), len(vals), arr, _stream(dev)), "set_floats")
+
+    @torch.no_grad()
+    def graph_launch(self):
+        """Called INSIDE the capture instead of step(): enqueue the update reading the device scalars."""
+        bufs = self.__dict__["_hyper_dev"]
+        for gi, group in enumerate(self.param_groups):
+            params = self._collect(group)
+            if not params:
+                continue
+            s1, s2 = self._graph_states(group, params)
+            dev = params[0].device
+            with torch.cuda.device(dev):
+                check(lib().cb_optimizer_step_dev(self._kind, ptr_array(params), ptr_array([p.grad for p in params]),
+                                                  ptr_array(s1) if s1 else None, ptr_array(s2) if s2 else None,
+                                                  _sizes(params), len(params), C.c_void_p(bufs[gi].data_ptr()),
+                                                  _stream(dev)), "optimizer_step_dev")
+
+    def graph_after(self):
+        for group in self.param_groups:
+            _touch([p for p in group["params"] if p.requires_grad])
 
 
 class FusedAdamW(_FusedBase):
@@ -85,6 +137,19 @@ class FusedAdamW(_FusedBase):
         return loss
 
 
+    _kind = 0
+
+    def _graph_hyper(self, group):
+        group["step"] += 1
+        t = group["step"]
+        b1, b2 = (_f32(b) for b in group["betas"])      # cb_adamw_step forms the corrections from the fp32 betas
+        return [group["lr"], b1, b2, group["eps"], group["weight_decay"], 1.0 - b1 ** t, (1.0 - b2 ** t) ** 0.5]
+
+    def _graph_states(self, group, params):
+        st = [self._state(p, "exp_avg", "exp_avg_sq") for p in params]
+        return [x["exp_avg"] for x in st], [x["exp_avg_sq"] for x in st]
+
+
 class FusedSGD(_FusedBase):
     """torch.optim.SGD semantics (L2 weight decay folded into the gradient, momentum buffer)."""
 
@@ -110,6 +175,18 @@ class FusedSGD(_FusedBase):
                                         int(group["step"]), _stream(dev)), "sgd_step")
                 _touch(params)
         return loss
+
+
+    _kind = 1
+
+    def _graph_hyper(self, group):
+        group["step"] += 1
+        return [group["lr"], group["momentum"], group["weight_decay"], 1.0 if group["step"] == 1 else 0.0]
+
+    def _graph_states(self, group, params):
+        if group["momentum"] == 0.0:
+            return None, None
+        return [self._state(p, "momentum_buffer")["momentum_buffer"] for p in params], None
 
 
 class _ScheduleFreeBase(_FusedBase):
@@ -197,6 +274,21 @@ class FusedAdamWScheduleFree(_ScheduleFreeBase):
         return loss
 
 
+    _kind = 2
+
+    def _graph_hyper(self, group):
+        if not group["train_mode"]:
+            raise RuntimeError("optimizer.train() must be called before step() (schedule-free)")
+        lr_k, ckp1 = self._schedule(group)
+        bc2 = 1.0 - group["beta2"] ** (group["k"] + 1)
+        group["k"] += 1
+        return [lr_k, group["beta1"], group["beta2"], group["eps"], group["weight_decay"], ckp1, bc2]
+
+    def _graph_states(self, group, params):
+        self._init_z(params)
+        return [self.state[p]["z"] for p in params], [self._state(p, "exp_avg_sq")["exp_avg_sq"] for p in params]
+
+
 class FusedSGDScheduleFree(_ScheduleFreeBase):
     """SGDScheduleFree(lr, momentum, weight_decay, warmup_steps, r=0, weight_lr_power=2)."""
 
@@ -230,3 +322,16 @@ class FusedSGDScheduleFree(_ScheduleFreeBase):
                 _touch(params)
             group["k"] += 1
         return loss
+
+    _kind = 3
+
+    def _graph_hyper(self, group):
+        if not group["train_mode"]:
+            raise RuntimeError("optimizer.train() must be called before step() (schedule-free)")
+        lr_k, ckp1 = self._schedule(group)
+        group["k"] += 1
+        return [lr_k, group["momentum"], 0.0, 0.0, group["weight_decay"], ckp1, 1.0]
+
+    def _graph_states(self, group, params):
+        self._init_z(params)
+        return [self.state[p]["z"] for p in params], None

@@ -248,8 +248,13 @@ struct TensorList {
   int64_t n[kMaxTensors];
 };
 
+// Every optimizer kernel can take its scalars from DEVICE memory (`dev`, same field order as the by-value
+// struct): a training step captured in a CUDA graph keeps replaying while the host only rewrites those
+// few floats (learning-rate schedule, bias corrections, schedule-free weights) between replays.
 struct AdamArgs { float lr, b1, b2, eps, wd, bc1, bc2_sqrt; };
-__global__ void adamw_kernel(const TensorList tl, const AdamArgs a) {
+__global__ void adamw_kernel(const TensorList tl, const AdamArgs a0, const float* __restrict__ dev) {
+  AdamArgs a = a0;
+  if (dev) { a.lr = dev[0]; a.b1 = dev[1]; a.b2 = dev[2]; a.eps = dev[3]; a.wd = dev[4]; a.bc1 = dev[5]; a.bc2_sqrt = dev[6]; }
   const int t = blockIdx.y;
   const int64_t n = tl.n[t];
   float* __restrict__ p = tl.p[t];
@@ -270,7 +275,9 @@ __global__ void adamw_kernel(const TensorList tl, const AdamArgs a) {
 }
 
 struct SgdArgs { float lr, momentum, wd; int first; };
-__global__ void sgd_kernel(const TensorList tl, const SgdArgs a) {
+__global__ void sgd_kernel(const TensorList tl, const SgdArgs a0, const float* __restrict__ dev) {
+  SgdArgs a = a0;
+  if (dev) { a.lr = dev[0]; a.momentum = dev[1]; a.wd = dev[2]; a.first = dev[3] != 0.f; }
   const int t = blockIdx.y;
   const int64_t n = tl.n[t];
   float* __restrict__ p = tl.p[t];
@@ -288,7 +295,9 @@ __global__ void sgd_kernel(const TensorList tl, const SgdArgs a) {
 }
 
 struct SfArgs { float lr, beta1, b2, eps, wd, ckp1, bc2; int adam; };
-__global__ void schedulefree_kernel(const TensorList tl, const SfArgs a) {
+__global__ void schedulefree_kernel(const TensorList tl, const SfArgs a0, const float* __restrict__ dev) {
+  SfArgs a = a0;
+  if (dev) { a.lr = dev[0]; a.beta1 = dev[1]; a.b2 = dev[2]; a.eps = dev[3]; a.wd = dev[4]; a.ckp1 = dev[5]; a.bc2 = dev[6]; }
   const int t = blockIdx.y;
   const int64_t n = tl.n[t];
   float* __restrict__ y = tl.p[t];
@@ -598,7 +607,7 @@ extern "C" int32_t cb_adamw_step(float* const* d_p, const float* const* d_g, flo
              (float)sqrt(1.0 - pow((double)beta2, (double)step))};
   cudaStream_t st = (cudaStream_t)stream;
   return for_tensor_chunks(d_p, d_g, d_m, d_v, sizes, n_tensors, [&](const TensorList& tl, dim3 grid) {
-    adamw_kernel<<<grid, kThreads, 0, st>>>(tl, a);
+    adamw_kernel<<<grid, kThreads, 0, st>>>(tl, a, nullptr);
   });
 }
 
@@ -609,7 +618,7 @@ extern "C" int32_t cb_sgd_step(float* const* d_p, const float* const* d_g, float
   SgdArgs a{lr, momentum, weight_decay, step == 1 ? 1 : 0};
   cudaStream_t st = (cudaStream_t)stream;
   return for_tensor_chunks(d_p, d_g, d_buf, nullptr, sizes, n_tensors, [&](const TensorList& tl, dim3 grid) {
-    sgd_kernel<<<grid, kThreads, 0, st>>>(tl, a);
+    sgd_kernel<<<grid, kThreads, 0, st>>>(tl, a, nullptr);
   });
 }
 
@@ -622,7 +631,7 @@ extern "C" int32_t cb_schedulefree_adamw_step(float* const* d_y, const float* co
   SfArgs a{lr_k, beta1, beta2, eps, weight_decay, ckp1, bias_correction2, 1};
   cudaStream_t st = (cudaStream_t)stream;
   return for_tensor_chunks(d_y, d_g, d_z, d_v, sizes, n_tensors, [&](const TensorList& tl, dim3 grid) {
-    schedulefree_kernel<<<grid, kThreads, 0, st>>>(tl, a);
+    schedulefree_kernel<<<grid, kThreads, 0, st>>>(tl, a, nullptr);
   });
 }
 
@@ -634,7 +643,41 @@ extern "C" int32_t cb_schedulefree_sgd_step(float* const* d_y, const float* cons
   SfArgs a{lr_k, momentum, 0.f, 0.f, weight_decay, ckp1, 1.f, 0};
   cudaStream_t st = (cudaStream_t)stream;
   return for_tensor_chunks(d_y, d_g, d_z, nullptr, sizes, n_tensors, [&](const TensorList& tl, dim3 grid) {
-    schedulefree_kernel<<<grid, kThreads, 0, st>>>(tl, a);
+    schedulefree_kernel<<<grid, kThreads, 0, st>>>(tl, a, nullptr);
+  });
+}
+
+// ---- capturable variants: scalars read from device memory (see adamw_kernel)
+struct FloatPack { float v[16]; };
+__global__ void set_floats_kernel(float* __restrict__ dst, int n, const FloatPack vals) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = vals.v[threadIdx.x];
+}
+// d_dst[0..n) = h_vals[0..n) (n <= 16): the values travel as kernel arguments, so the host buffer may be
+// reused immediately and the write is ordered on `stream` like any other launch.
+extern "C" int32_t cb_set_floats(float* d_dst, int32_t n, const float* h_vals, void* stream) {
+  CB_CHECK_ARG(d_dst && h_vals && n >= 1 && n <= 16, "bad cb_set_floats arguments");
+  FloatPack pk{};
+  for (int i = 0; i < n; ++i) pk.v[i] = h_vals[i];
+  set_floats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_dst, n, pk);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+// kind: 0 AdamW {lr,b1,b2,eps,wd,bc1,sqrt(bc2)}  1 SGD {lr,momentum,wd,first}
+//       2 schedule-free AdamW {lr_k,beta1,beta2,eps,wd,ckp1,bc2}  3 schedule-free SGD {lr_k,momentum,-,-,wd,ckp1,-}
+extern "C" int32_t cb_optimizer_step_dev(int32_t kind, float* const* d_p, const float* const* d_g, float* const* d_s1,
+                                         float* const* d_s2, const int64_t* sizes, int32_t n_tensors,
+                                         const float* d_hyper, void* stream) {
+  CB_CHECK_ARG(d_g && d_hyper && kind >= 0 && kind <= 3, "bad cb_optimizer_step_dev arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  return for_tensor_chunks(d_p, d_g, d_s1, d_s2, sizes, n_tensors, [&](const TensorList& tl, dim3 grid) {
+    if (kind == 0) adamw_kernel<<<grid, kThreads, 0, st>>>(tl, AdamArgs{}, d_hyper);
+    else if (kind == 1) sgd_kernel<<<grid, kThreads, 0, st>>>(tl, SgdArgs{}, d_hyper);
+    else {
+      SfArgs a{};
+      a.adam = kind == 2 ? 1 : 0;
+      schedulefree_kernel<<<grid, kThreads, 0, st>>>(tl, a, d_hyper);
+    }
   });
 }
 

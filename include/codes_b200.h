@@ -166,6 +166,15 @@ CB_API int32_t cb_schedulefree_adamw_step(float* const* d_y, const float* const*
 CB_API int32_t cb_schedulefree_sgd_step(float* const* d_y, const float* const* d_g, float* const* d_z,
                                  const int64_t* sizes, int32_t n_tensors, float lr_k,
                                  float momentum, float weight_decay, float ckp1, void* stream);
+/* Capturable variants (training step captured in a CUDA graph, codes_b200/graph_step.py): the scalars are
+ * read from device memory (d_hyper, field order below) that the host rewrites with cb_set_floats between
+ * replays.  kind 0 AdamW {lr,b1,b2,eps,wd,1-b1^t,sqrt(1-b2^t)}; 1 SGD {lr,momentum,wd,first};
+ * 2 schedule-free AdamW {lr_k,beta1,beta2,eps,wd,ckp1,bias_correction2}; 3 schedule-free SGD
+ * {lr_k,momentum,-,-,wd,ckp1,-}.  State arrays as in the by-value entry points (s1: m / buf / z; s2: v). */
+CB_API int32_t cb_set_floats(float* d_dst, int32_t n, const float* h_vals, void* stream);
+CB_API int32_t cb_optimizer_step_dev(int32_t kind, float* const* d_p, const float* const* d_g,
+                                     float* const* d_s1, float* const* d_s2, const int64_t* sizes,
+                                     int32_t n_tensors, const float* d_hyper, void* stream);
 /* p <- lerp(p, z, w) over all tensors (schedulefree .train()/.eval() switch). */
 CB_API int32_t cb_lerp_tensors(float* const* d_p, const float* const* d_z, const int64_t* sizes,
                         int32_t n_tensors, float w, void* stream);

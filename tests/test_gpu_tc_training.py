@@ -168,3 +168,44 @@ def test_fit_loss_curve_tracks_fp32_mode(which):
         assert np.all(np.isfinite(a))
         assert b[-1] < b[0], (a, b)              # training made progress
         np.testing.assert_allclose(a, b, rtol=2e-2)
+
+
+@pytest.mark.parametrize("which", ["fcnn", "multionet", "latentpoly", "latentpoly_sf"])
+def test_cuda_graph_training_step_matches_eager(which, monkeypatch):
+    """fit() with the training step captured in a CUDA graph (codes_b200/graph_step.py: eager for the first
+    batches of a shape, then forward + loss + backward + fused optimizer replayed from one graph, optimizer
+    scalars rewritten on the device between replays) ends at the same weights as the eager loop: same kernels,
+    same order, same learning-rate schedule / bias corrections / schedule-free weights."""
+    import codes_b200 as cb
+    Q, T, n = 5, 20, 64
+    d = O.synthetic_dataset(n, T, Q, seed=13)
+    finals, replays = {}, {}
+    try:
+        for graphs in ("0", "1"):
+            monkeypatch.setenv("CODES_B200_CUDA_GRAPH", graphs)
+            cb.set_precision("bf16"); cb.set_train_precision("fp32")
+            torch.manual_seed(7); np.random.seed(7)
+            if which == "fcnn":
+                m = cb.FullyConnected(DEV, Q, T, 0, None, {"hidden_size": 48, "num_hidden_layers": 2, "learning_rate": 1e-3,
+                                                            "eta_min": 1e-5})
+                bs = 256
+            elif which == "multionet":
+                m = cb.MultiONet(DEV, Q, T, 0, None, {"hidden_size": 32, "branch_hidden_layers": 2, "trunk_hidden_layers": 2,
+                                                       "output_factor": 6, "learning_rate": 1e-3, "scheduler": "poly"})
+                bs = 256
+            else:
+                cfg = {"latent_features": 3, "degree": 2, "coder_width": 16, "coder_layers": 2, "learning_rate": 1e-3,
+                       "eta_min": 1e-5}
+                if which == "latentpoly_sf":
+                    cfg.update({"scheduler": "schedulefree", "optimizer": "sgd", "momentum": 0.3})
+                m = cb.LatentPoly(DEV, Q, T, 0, None, cfg)
+                bs = 16
+            tr, te, _ = m.prepare_data(d, d[:8], None, np.linspace(0, 1, T), bs, shuffle=True)
+            m.fit(tr, te, epochs=6)
+            finals[graphs] = [p.detach().clone() for p in m.parameters()]
+            replays[graphs] = m.__dict__["_stepper"].replays
+    finally:
+        cb.set_precision("fp32"); cb.set_train_precision("bf16")
+    assert replays["0"] == 0 and replays["1"] > 5, replays
+    for a, b in zip(finals["1"], finals["0"]):
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-7)
