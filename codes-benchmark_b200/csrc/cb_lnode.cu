@@ -56,6 +56,7 @@ struct LnodeParams {
   int L, T, wmax_p;
   int Le;                     // leading state features that enter the error / step-size norms (<= L)
   int weights_in_smem;
+  int grads_in_smem;          // backward: gradient accumulators in shared memory (flushed to the slab once)
 };
 
 // Wt[k][jp] = W[jp][k] (zero for jp >= N); bias padded
@@ -389,6 +390,7 @@ static int32_t build_params(const cb_lnode_desc* desc, int32_t n_t, LnodeParams&
   P.n_layers = m.n_layers;
   P.L = m.dims[0]; P.T = n_t;
   P.Le = (desc->n_err > 0 && desc->n_err <= P.L) ? desc->n_err : P.L;
+  P.weights_in_smem = 0; P.grads_in_smem = 0;
   P.act = m.act; P.act_param = m.act_param;
   P.tanh_reg = desc->tanh_reg; P.reg = desc->reg_factor;
   P.rtol = desc->rtol; P.atol = desc->atol; P.max_steps = desc->max_steps;
@@ -479,10 +481,11 @@ constexpr int kBT = 32;     // trajectories per CTA in the backward kernel
 constexpr int kBThreads = 128;
 
 // out[j][t] = act(sum_k Wt[k][j] in[k][t] + b[j]); also stores the pre-activation z
+template <int TB>
 __device__ __forceinline__ void bwd_fwd_layer(const float* __restrict__ Wt, const float* __restrict__ bias, int K,
                                               int N, int Wp, const float* __restrict__ in, float* __restrict__ a_out,
                                               float* __restrict__ z_out, int act, float ap) {
-  constexpr int TB = kBT, TG = TB / 4;
+  constexpr int TG = TB / 4;
   const int tg = threadIdx.x % TG;
   for (int jg = threadIdx.x / TG; jg < Wp / 8; jg += kBThreads / TG) {
     float acc[8][4];
@@ -517,9 +520,9 @@ __device__ __forceinline__ void bwd_fwd_layer(const float* __restrict__ Wt, cons
 }
 
 // dWt[k][j] += sum_t a_in[k][t] * delta[j][t];  db[j] += sum_t delta[j][t]   (this CTA's private global slab)
+template <int TB>
 __device__ __forceinline__ void bwd_wgrad(const float* __restrict__ a_in, const float* __restrict__ delta, int K, int N,
                                           int Wp, float* __restrict__ dWt, float* __restrict__ db) {
-  constexpr int TB = kBT;
   const int njg = Wp / 4;
   for (int idx = threadIdx.x; idx < K * njg; idx += kBThreads) {
     const int k = idx / njg, jg = idx - k * njg;
@@ -549,10 +552,11 @@ __device__ __forceinline__ void bwd_wgrad(const float* __restrict__ a_in, const 
 }
 
 // d_prev[k][t] = (sum_j Wt[k][j] delta[j][t]) * act'(z_prev[k][t])   (z_prev NULL -> no activation: network input)
+template <int TB>
 __device__ __forceinline__ void bwd_dgrad(const float* __restrict__ Wt, const float* __restrict__ delta, int K, int N,
                                           int Wp, const float* __restrict__ z_prev, float* __restrict__ d_prev, int act,
                                           float ap) {
-  constexpr int TB = kBT, TG = TB / 4;
+  constexpr int TG = TB / 4;
   for (int idx = threadIdx.x; idx < K * TG; idx += kBThreads) {
     const int k = idx / TG, tg = idx - k * TG;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -573,13 +577,13 @@ __device__ __forceinline__ void bwd_dgrad(const float* __restrict__ Wt, const fl
 
 // Discrete adjoint of the accepted Tsit5 steps (step sizes treated as constants), reverse sweep over the
 // tape; one CTA owns kBT trajectories and a private gradient slab in global memory.
+template <int TB>
 __global__ void __launch_bounds__(kBThreads, 1)
 lnode_bwd_kernel(const LnodeParams P, const float* __restrict__ gW, const float* __restrict__ gB,
                  const float* __restrict__ t_eval_f, int64_t batch, const Tape tape,
                  const float* __restrict__ g_out, float* __restrict__ dz0, float* __restrict__ slabs,
                  int slab_floats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int TB = kBT;
   const int L = P.L, T = P.T, nl = P.n_layers;
   double* lam = reinterpret_cast<double*>(smem_raw);   // [L][TB]   dL/dy_{n+1}
   double* kap = lam + L * TB;                          // [7][L][TB] stage adjoints
@@ -603,9 +607,15 @@ lnode_bwd_kernel(const LnodeParams P, const float* __restrict__ gW, const float*
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * TB;
   float* slab = slabs + (size_t)blockIdx.x * slab_floats;   // [total_w | total_b | 1]
-  float* dWt = slab;
-  float* dB = slab + P.total_w;
-  for (int i = tid; i < slab_floats; i += kBThreads) slab[i] = 0.f;
+  // gradient accumulators: shared memory when they fit (no global read-modify-write on the critical path),
+  // else this CTA's global slab
+  float* sgrad = reinterpret_cast<float*>(s_j + TB);
+  float* dWt = P.grads_in_smem ? sgrad : slab;
+  float* dB = dWt + P.total_w;
+  if (P.grads_in_smem)
+    for (int i = tid; i < P.total_w + P.total_b; i += kBThreads) sgrad[i] = 0.f;
+  else
+    for (int i = tid; i < slab_floats; i += kBThreads) slab[i] = 0.f;
   for (int i = tid; i < P.total_b; i += kBThreads) sB[i] = gB[i];
   if (P.weights_in_smem)
     for (int i = tid; i < P.total_w / 4; i += kBThreads)
@@ -695,7 +705,7 @@ lnode_bwd_kernel(const LnodeParams P, const float* __restrict__ gW, const float*
       const float* in = xin;
       for (int li = 0; li < nl; ++li) {
         const bool last = (li == nl - 1);
-        bwd_fwd_layer(W + P.w_off[li], sB + P.b_off[li], P.K[li], P.N[li], P.Wp[li], in,
+        bwd_fwd_layer<TB>(W + P.w_off[li], sB + P.b_off[li], P.K[li], P.N[li], P.Wp[li], in,
                       acts + (size_t)li * P.wmax_p * TB, zs + (size_t)li * P.wmax_p * TB,
                       last ? CB_ACT_IDENTITY : P.act, P.act_param);
         __syncthreads();
@@ -718,8 +728,8 @@ lnode_bwd_kernel(const LnodeParams P, const float* __restrict__ gW, const float*
       __syncthreads();
       for (int li = nl - 1; li >= 0; --li) {
         const float* a_in = (li == 0) ? xin : acts + (size_t)(li - 1) * P.wmax_p * TB;
-        bwd_wgrad(a_in, dcur, P.K[li], P.N[li], P.Wp[li], dWt + P.w_off[li], dB + P.b_off[li]);
-        bwd_dgrad(W + P.w_off[li], dcur, P.K[li], P.N[li], P.Wp[li],
+        bwd_wgrad<TB>(a_in, dcur, P.K[li], P.N[li], P.Wp[li], dWt + P.w_off[li], dB + P.b_off[li]);
+        bwd_dgrad<TB>(W + P.w_off[li], dcur, P.K[li], P.N[li], P.Wp[li],
                   (li == 0) ? nullptr : zs + (size_t)(li - 1) * P.wmax_p * TB, dnext, P.act, P.act_param);
         __syncthreads();
         float* tmp = dcur; dcur = dnext; dnext = tmp;
@@ -748,6 +758,10 @@ lnode_bwd_kernel(const LnodeParams P, const float* __restrict__ gW, const float*
     const int64_t b = b0 + t;
     if (b < batch) dz0[b * L + l] = (float)(lam[i] + (double)g_out[(b * T) * L + l]);
   }
+  if (P.grads_in_smem) {
+    __syncthreads();
+    for (int i = tid; i < P.total_w + P.total_b; i += kBThreads) slab[i] = sgrad[i];
+  }
   red[tid] = dreg;
   __syncthreads();
   if (tid == 0) {
@@ -757,12 +771,11 @@ lnode_bwd_kernel(const LnodeParams P, const float* __restrict__ gW, const float*
   }
 }
 
-static size_t lnode_bwd_smem_bytes(const LnodeParams& P) {
-  const int TB = kBT;
+static size_t lnode_bwd_smem_bytes(const LnodeParams& P, int TB = kBT) {
   size_t dbl = (size_t)(P.L * TB * (1 + 7 + 1 + 1) + ((P.T + 1) & ~1) + 2 * TB) * sizeof(double);
   size_t flt = ((size_t)7 * P.L * TB + (size_t)P.wmax_p * TB * (1 + 2 * P.n_layers + 2) + P.total_b +
                 (P.weights_in_smem ? P.total_w : 0)) * sizeof(float);
-  return dbl + flt + 2 * TB * sizeof(int);
+  return dbl + flt + 2 * TB * sizeof(int) + (P.grads_in_smem ? (size_t)(P.total_w + P.total_b) * sizeof(float) : 0);
 }
 
 // sum the CTA slabs in fixed order and unpack Wt[k][jp] -> dW[j][k] (nn.Linear layout)
@@ -798,7 +811,7 @@ __global__ void lnode_bwd_reduce_reg_kernel(const float* __restrict__ slabs, int
 extern "C" int64_t cb_lnode_bwd_workspace_floats(const cb_lnode_desc* desc, int64_t batch) {
   LnodeParams P;
   if (batch < 0 || build_params(desc, 2, P) != CB_OK) return -1;
-  const int64_t n_cta = (batch + kBT - 1) / kBT;
+  const int64_t n_cta = (batch + 15) / 16;     // upper bound: the 16-trajectory variant launches the most CTAs
   const int64_t slab = (P.total_w + P.total_b + 1 + 3) & ~3;
   return (int64_t)P.total_w + P.total_b + 64 + n_cta * slab;
 }
@@ -808,8 +821,9 @@ extern "C" int64_t cb_lnode_bwd_workspace_floats(const cb_lnode_desc* desc, int6
 extern "C" int32_t cb_lnode_bwd_supported(const cb_lnode_desc* desc, int32_t n_t) {
   LnodeParams P;
   if (build_params(desc, n_t, P) != CB_OK) return 0;
-  const int max_smem = usable_dynamic_smem(lnode_bwd_kernel);
+  const int max_smem = usable_dynamic_smem(lnode_bwd_kernel<kBT>);
   P.weights_in_smem = 0;
+  P.grads_in_smem = 0;
   return lnode_bwd_smem_bytes(P) <= (size_t)max_smem ? 1 : 0;
 }
 
@@ -833,16 +847,31 @@ extern "C" int32_t cb_lnode_solve_bwd(const cb_lnode_desc* desc, const float* co
   float* gB = d_ws + P.total_w;
   float* slabs = d_ws + ((P.total_w + P.total_b + 63) & ~3);   // 16-byte aligned behind the packed weights
   const int slab_floats = (P.total_w + P.total_b + 1 + 3) & ~3;
-  const int n_cta = (int)((batch + kBT - 1) / kBT);
   if (int32_t e = pack_weights(P, d_W, d_b, gW, gB, st)) return e;
-  const int max_smem = usable_dynamic_smem(lnode_bwd_kernel);
-  P.weights_in_smem = 1;
-  if (lnode_bwd_smem_bytes(P) > (size_t)max_smem) P.weights_in_smem = 0;
-  const size_t smem = lnode_bwd_smem_bytes(P);
-  CB_CHECK_ARG(smem <= (size_t)max_smem, "ODE net too wide for the backward sweep kernel (%zu bytes of shared memory)", smem);
-  CB_CUDA(cudaFuncSetAttribute(lnode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   Tape tp{tape->d_n, tape->d_t, tape->d_dt, tape->d_y, tape->d_k, tape->cap};
-  lnode_bwd_kernel<<<n_cta, kBThreads, smem, st>>>(P, gW, gB, d_t_eval, batch, tp, d_g, d_dz0, slabs, slab_floats);
+  // Small batches (the reference trains with 512 / 717 trajectories per step): 16 trajectories per CTA with the
+  // weights AND the gradient accumulators in shared memory -- twice the CTAs and no global read-modify-write
+  // in the wgrad loop.  Otherwise 32 per CTA, accumulators in the CTA's global slab.
+  const int max16 = usable_dynamic_smem(lnode_bwd_kernel<16>);
+  P.weights_in_smem = 1; P.grads_in_smem = 1;
+  const bool small = batch <= 16 * (int64_t)num_sms() && lnode_bwd_smem_bytes(P, 16) <= (size_t)max16;
+  int n_cta;
+  if (small) {
+    n_cta = (int)((batch + 15) / 16);
+    const size_t smem = lnode_bwd_smem_bytes(P, 16);
+    CB_CUDA(cudaFuncSetAttribute(lnode_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lnode_bwd_kernel<16><<<n_cta, kBThreads, smem, st>>>(P, gW, gB, d_t_eval, batch, tp, d_g, d_dz0, slabs, slab_floats);
+  } else {
+    n_cta = (int)((batch + kBT - 1) / kBT);
+    const int max_smem = usable_dynamic_smem(lnode_bwd_kernel<kBT>);
+    P.grads_in_smem = 0;
+    P.weights_in_smem = 1;
+    if (lnode_bwd_smem_bytes(P) > (size_t)max_smem) P.weights_in_smem = 0;
+    const size_t smem = lnode_bwd_smem_bytes(P);
+    CB_CHECK_ARG(smem <= (size_t)max_smem, "ODE net too wide for the backward sweep kernel (%zu bytes of shared memory)", smem);
+    CB_CUDA(cudaFuncSetAttribute(lnode_bwd_kernel<kBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lnode_bwd_kernel<kBT><<<n_cta, kBThreads, smem, st>>>(P, gW, gB, d_t_eval, batch, tp, d_g, d_dz0, slabs, slab_floats);
+  }
   CB_LAUNCH_CHECK();
   for (int i = 0; i < P.n_layers; ++i) {
     const int total = P.N[i] * P.K[i];
