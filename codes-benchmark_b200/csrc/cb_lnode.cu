@@ -486,29 +486,33 @@ __device__ __forceinline__ void bwd_fwd_layer(const float* __restrict__ Wt, cons
                                               int N, int Wp, const float* __restrict__ in, float* __restrict__ a_out,
                                               float* __restrict__ z_out, int act, float ap) {
   constexpr int TG = TB / 4;
+  constexpr int JW = TB >= 32 ? 8 : 4;     // outputs per thread: narrower tiles keep more threads busy at TB = 16
   const int tg = threadIdx.x % TG;
-  for (int jg = threadIdx.x / TG; jg < Wp / 8; jg += kBThreads / TG) {
-    float acc[8][4];
+  for (int jg = threadIdx.x / TG; jg < Wp / JW; jg += kBThreads / TG) {
+    float acc[JW][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float bj = bias[jg * 8 + j];
+    for (int j = 0; j < JW; ++j) {
+      const float bj = bias[jg * JW + j];
 #pragma unroll
       for (int t = 0; t < 4; ++t) acc[j][t] = bj;
     }
     for (int k = 0; k < K; ++k) {
-      const float4 w0 = *reinterpret_cast<const float4*>(Wt + (size_t)k * Wp + jg * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(Wt + (size_t)k * Wp + jg * 8 + 4);
+      float w[JW];
+#pragma unroll
+      for (int q = 0; q < JW / 4; ++q) {
+        const float4 wv = *reinterpret_cast<const float4*>(Wt + (size_t)k * Wp + jg * JW + q * 4);
+        w[q * 4] = wv.x; w[q * 4 + 1] = wv.y; w[q * 4 + 2] = wv.z; w[q * 4 + 3] = wv.w;
+      }
       const float4 a = *reinterpret_cast<const float4*>(in + k * TB + tg * 4);
-      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
       const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < JW; ++j)
 #pragma unroll
         for (int t = 0; t < 4; ++t) acc[j][t] = fmaf(w[j], av[t], acc[j][t]);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int jj = jg * 8 + j;
+    for (int j = 0; j < JW; ++j) {
+      const int jj = jg * JW + j;
       if (jj < N) {
         float4 z = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
         *reinterpret_cast<float4*>(z_out + (size_t)jj * TB + tg * 4) = z;
