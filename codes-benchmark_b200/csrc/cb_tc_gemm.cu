@@ -508,8 +508,59 @@ __device__ __forceinline__ float dot8_bf16(uint4 a, uint4 b, float acc) {
   }
   return acc;
 }
+// Two phases per row (one warp per row): (1) every lane multiplies 16-byte chunks of B and T (coalesced,
+// 512 B per warp instruction) and writes each chunk's product sums -- split at the one quantity boundary a
+// chunk can contain -- to a per-warp shared array; (2) lane q adds the partials of its quantity in column
+// order.  Fixed summation order -> deterministic.  Needs split sizes >= 8 (else the scalar kernel below).
 __global__ void combine_bf16_fwd_kernel(const __nv_bfloat16* __restrict__ B, const __nv_bfloat16* __restrict__ T,
                                         long long rows, int n_out, int Q, int ld, float* __restrict__ y) {
+  extern __shared__ float csm[];                         // [warps][2 * chunks]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunks = (n_out + 7) / 8;
+  float* part = csm + (size_t)warp * 2 * chunks;
+  const int seg_base = n_out / Q, seg_rem = n_out % Q;
+  const int big = seg_rem * (seg_base + 1);
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + warp; r < rows;
+       r += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const uint4* b = reinterpret_cast<const uint4*>(B + r * ld);
+    const uint4* t = reinterpret_cast<const uint4*>(T + r * ld);
+    for (int c = lane; c < chunks; c += 32) {
+      const uint4 bv = __ldg(b + c), tv = __ldg(t + c);
+      const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w}, tw[4] = {tv.x, tv.y, tv.z, tv.w};
+      const int c0 = c * 8;
+      // quantity of the chunk's first column and the first column of the next quantity
+      const int q0 = c0 < big ? c0 / (seg_base + 1) : seg_rem + (c0 - big) / seg_base;
+      const int end = (q0 + 1) * seg_base + (q0 + 1 < seg_rem ? q0 + 1 : seg_rem);
+      float lo = 0.f, hi = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float p0 = bf16_lo(bw[i]) * bf16_lo(tw[i]), p1 = bf16_hi(bw[i]) * bf16_hi(tw[i]);
+        const int k0 = c0 + 2 * i, k1 = k0 + 1;
+        if (k0 < n_out) { if (k0 < end) lo += p0; else hi += p0; }
+        if (k1 < n_out) { if (k1 < end) lo += p1; else hi += p1; }
+      }
+      part[2 * c] = lo;
+      part[2 * c + 1] = hi;
+    }
+    __syncwarp();
+    for (int q = lane; q < Q; q += 32) {
+      const int start = q * seg_base + (q < seg_rem ? q : seg_rem);
+      const int stop = start + seg_base + (q < seg_rem ? 1 : 0);          // exclusive
+      const int cf = start >> 3, cl = (stop - 1) >> 3;
+      float acc = 0.f;
+      for (int c = cf; c <= cl; ++c) {
+        // chunk c contributes its "lo" part if its first column belongs to q, else its "hi" part
+        const int c0 = c * 8;
+        acc += (c0 >= start) ? part[2 * c] : part[2 * c + 1];
+      }
+      y[r * Q + q] = acc;
+    }
+    __syncwarp();
+  }
+}
+// splits narrower than 8 columns: one lane per quantity walks its split
+__global__ void combine_bf16_fwd_scalar_kernel(const __nv_bfloat16* __restrict__ B, const __nv_bfloat16* __restrict__ T,
+                                               long long rows, int n_out, int Q, int ld, float* __restrict__ y) {
   const int lane = threadIdx.x & 31;
   const int seg_base = n_out / Q, seg_rem = n_out % Q;
   for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
@@ -520,9 +571,6 @@ __global__ void combine_bf16_fwd_kernel(const __nv_bfloat16* __restrict__ B, con
       int k = q * seg_base + (q < seg_rem ? q : seg_rem);
       const int end = k + seg_base + (q < seg_rem ? 1 : 0);
       float acc = 0.f;
-      for (; k < end && (k & 7); ++k) acc = fmaf(__bfloat162float(b[k]), __bfloat162float(t[k]), acc);
-      for (; k + 8 <= end; k += 8)
-        acc = dot8_bf16(*reinterpret_cast<const uint4*>(b + k), *reinterpret_cast<const uint4*>(t + k), acc);
       for (; k < end; ++k) acc = fmaf(__bfloat162float(b[k]), __bfloat162float(t[k]), acc);
       y[r * Q + q] = acc;
     }
@@ -949,8 +997,13 @@ extern "C" int32_t cb_tc_combine_fwd(const void* d_B, const void* d_T, int64_t r
   CB_CHECK_ARG(d_B && d_T && d_y, "NULL pointer argument");
   long long blocks = (rows + 7) / 8;
   if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
-  combine_bf16_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d_B), reinterpret_cast<const __nv_bfloat16*>(d_T), rows, n_out, Q, ld, d_y);
+  const __nv_bfloat16* Bp = reinterpret_cast<const __nv_bfloat16*>(d_B);
+  const __nv_bfloat16* Tp = reinterpret_cast<const __nv_bfloat16*>(d_T);
+  const size_t smem = (size_t)8 * 2 * ((n_out + 7) / 8) * sizeof(float);
+  if (n_out / Q >= 8 && smem <= 48 * 1024)
+    combine_bf16_fwd_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(Bp, Tp, rows, n_out, Q, ld, d_y);
+  else
+    combine_bf16_fwd_scalar_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(Bp, Tp, rows, n_out, Q, ld, d_y);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

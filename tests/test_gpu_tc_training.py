@@ -209,3 +209,32 @@ def test_cuda_graph_training_step_matches_eager(which, monkeypatch):
     assert replays["0"] == 0 and replays["1"] > 5, replays
     for a, b in zip(finals["1"], finals["0"]):
         torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("n_out,Q,rows", [(2842, 29, 1000), (2845, 29, 513), (1300, 10, 64), (77, 7, 300), (50, 10, 33), (9, 9, 5)])
+def test_bf16_combine_forward_backward(n_out, Q, rows):
+    """split scalar product on the bf16 branch / trunk outputs (deeponet.py:130-137, 245-253) incl. uneven
+    splits (first n_out % Q quantities one column wider) and splits narrower than one 16-byte chunk."""
+    tc = _tc()
+    ld = (n_out + 1 + 63) // 64 * 64
+    g = torch.Generator(device=DEV).manual_seed(n_out + Q)
+    b = torch.zeros(rows, ld, device=DEV, dtype=torch.bfloat16)
+    t = torch.zeros(rows, ld, device=DEV, dtype=torch.bfloat16)
+    b[:, :n_out] = torch.randn(rows, n_out, device=DEV, generator=g)
+    t[:, :n_out] = torch.randn(rows, n_out, device=DEV, generator=g)
+    b[:, n_out:] = 7.0                                   # padding must never leak into a sum
+    b.requires_grad_(True); t.requires_grad_(True)
+    y = tc.combine_bf16(b, t, n_out, Q)
+    base, rem = divmod(n_out, Q)
+    sizes = [base + (1 if i < rem else 0) for i in range(Q)]
+    prod = (b.detach().float() * t.detach().float())[:, :n_out]
+    ref = torch.stack([s.sum(1) for s in prod.split(sizes, dim=1)], dim=1)
+    torch.testing.assert_close(y, ref, rtol=1e-5, atol=1e-4)
+    y2 = tc.combine_bf16(b, t, n_out, Q)
+    assert torch.equal(y, y2)                            # fixed summation order
+    dy = torch.randn(rows, Q, device=DEV, generator=g)
+    y.backward(dy)
+    expand = torch.repeat_interleave(dy, torch.tensor(sizes, device=DEV), dim=1)
+    torch.testing.assert_close(b.grad[:, :n_out].float(), (expand * t.detach().float()[:, :n_out]), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(t.grad[:, :n_out].float(), (expand * b.detach().float()[:, :n_out]), rtol=1e-2, atol=1e-2)
+    assert float(b.grad[:, n_out:].abs().max()) == 0.0 and float(t.grad[:, n_out:].abs().max()) == 0.0
