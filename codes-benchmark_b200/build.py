@@ -21,6 +21,10 @@ FLAGS = [
 ]
 
 
+# e.g. CB_EXTRA_NVCC_FLAGS="-DCB_TC_ENABLE_FINAL_DBG" for the cycle-counter instrumentation of the tcgen05 kernels
+FLAGS += os.environ.get("CB_EXTRA_NVCC_FLAGS", "").split()
+
+
 def _newer(src, dst):
     return not os.path.exists(dst) or os.path.getmtime(src) > os.path.getmtime(dst)
 

@@ -72,6 +72,7 @@ struct ChainParams {
   long long rows;
   int num_tiles;
   unsigned long long* trace;   // debug timeline (CB_TC_TRACE), NULL in production
+  long long* dbg;              // CB_TC_CHAIN_DBG: cycle counters of CTA 0's MMA warp (debug), else NULL
 };
 
 struct FinalParams {
@@ -169,6 +170,13 @@ __device__ __forceinline__ void teardown_cta(uint32_t tmem_base, int warp) {
   }
 }
 
+// debug instrumentation of the MMA warp (cycle counters per wait reason): compile with -DCB_TC_ENABLE_FINAL_DBG
+#ifdef CB_TC_ENABLE_FINAL_DBG
+#define CB_CLK() clock64()
+#else
+#define CB_CLK() 0ll
+#endif
+
 // ====================================================================== chain kernel
 template <int ACT, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -234,15 +242,19 @@ chain_kernel(const __grid_constant__ ChainParams P) {
       int seen_in = 0, seen_epi = 0;
       const uint64_t bdesc0 = make_smem_desc(ST0);
       constexpr bool pair = PAIR;   // host picks PAIR only when the ring has >= 4 stages (a shallower ring would drain)
+      long long c_tempty = 0, c_dep = 0, c_full = 0, c_issue = 0, c_in = 0;
+      const long long c_start = CB_CLK();
       for (int it = 0; it < n_my_tiles; ++it) {
         for (int j = 0; j < P.n_jobs; ++j, ++gj) {
           const Job job = P.jobs[j];
           const int l = job.layer;
           const int slot = gj & (kSlots - 1);
           const uint32_t use = (uint32_t)(gj / kSlots);
+          long long c0 = CB_CLK();
           mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
           CB_TRACE(1, 2, j);
           tcgen05_fence_after();
+          c_tempty += CB_CLK() - c0;
           const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
           const uint32_t idesc = make_idesc(job.ncols);
           const int nkb = P.nkb[l];
@@ -252,8 +264,10 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           // previous layer (or by the input staging / input TMA for layer 0)
           int need0 = 0, last_pc = 0;
           if (l == 0) {
+            c0 = CB_CLK();
             if (P.in_mode == IN_BF16_TMA) mbar_wait(C.bar_in, it & 1);
             else wait_counter(C.in_staged, it + 1, seen_in);
+            c_in += CB_CLK() - c0;
           } else {
             need0 = it * P.n_jobs + P.first_job[l - 1] + 1;
             last_pc = P.n_chunks[l - 1] - 1;
@@ -264,7 +278,10 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           // MMAs about to be issued (no self-wait).
           for (int kb = 0; kb < nkb; kb += (pair ? 2 : 1)) {
             const bool two = pair && (kb + 1 < nkb);
+            c0 = CB_CLK();
             if (l != 0) wait_counter(C.epi_done, need0 + (P.inplace ? last_pc : min((kb + (two ? 1 : 0)) >> 1, last_pc)), seen_epi);
+            const long long c1 = CB_CLK();
+            c_dep += c1 - c0;
             CB_TRACE(1, 3, j * 8 + kb);
             int stage_b = stage + 1; uint32_t phase_b = phase;
             if (stage_b == P.stages) { stage_b = 0; phase_b ^= 1; }
@@ -272,6 +289,8 @@ chain_kernel(const __grid_constant__ ChainParams P) {
             if (two) mbar_wait(C.bar_full + 8 * stage_b, phase_b);
             CB_TRACE(1, 4, j * 8 + kb);
             tcgen05_fence_after();
+            const long long c2 = CB_CLK();
+            c_full += c2 - c1;
             // descriptor start-address field counts 16-byte units: +1024 per 16 KiB k-block / stage,
             // +2 per 16-column k-step
             const uint64_t adesc = adesc0 + (uint64_t)(kb * (kKBlockBytes >> 4));
@@ -294,12 +313,17 @@ chain_kernel(const __grid_constant__ ChainParams P) {
               }
             }
             __syncwarp();
+            c_issue += CB_CLK() - c2;
             if (two) { stage = stage_b; phase = phase_b; }
             if (++stage == P.stages) { stage = 0; phase ^= 1; }
           }
           if (elect_one()) umma_commit(C.bar_tfull + 8 * slot);   // accumulator chunk complete -> epilogue
           __syncwarp();
         }
+      }
+      if (P.dbg && blockIdx.x == 0 && lane == 0) {
+        P.dbg[0] = CB_CLK() - c_start; P.dbg[1] = c_in; P.dbg[2] = c_tempty; P.dbg[3] = c_dep; P.dbg[4] = c_full;
+        P.dbg[5] = c_issue; P.dbg[6] = n_my_tiles;
       }
     }
   } else {
@@ -423,13 +447,6 @@ chain_kernel(const __grid_constant__ ChainParams P) {
   }
   teardown_cta(tmem_base, warp);
 }
-
-// debug instrumentation of the MMA warp (cycle counters per wait reason): compile with -DCB_TC_ENABLE_FINAL_DBG
-#ifdef CB_TC_ENABLE_FINAL_DBG
-#define CB_CLK() clock64()
-#else
-#define CB_CLK() 0ll
-#endif
 
 // ====================================================================== MultiONet final kernel
 // y[r,q] = sum_{k in split_q} (Wb hb + bb)[r,k] * (Wt ht + bt)[r,k]      (deeponet.py:241-253)
@@ -982,8 +999,20 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
     CB_CUDA(cudaMalloc(&P.trace, 4 * 8192 * sizeof(unsigned long long)));
     CB_CUDA(cudaMemsetAsync(P.trace, 0, 4 * 8192 * sizeof(unsigned long long), st));
   }
+  P.dbg = nullptr;
+  const char* dbg_env = getenv("CB_TC_CHAIN_DBG");
+  if (dbg_env) { CB_CUDA(cudaMalloc(&P.dbg, 64)); CB_CUDA(cudaMemsetAsync(P.dbg, 0, 64, st)); }
   chain_kernel_for(plan->desc.act, P.stages)<<<grid, kThreads, plan->smem_bytes, st>>>(P);
   CB_LAUNCH_CHECK();
+  if (dbg_env) {
+    long long h[8];
+    CB_CUDA(cudaStreamSynchronize(st));
+    CB_CUDA(cudaMemcpy(h, P.dbg, 64, cudaMemcpyDeviceToHost));
+    cudaFree(P.dbg);
+    fprintf(stderr, "[chain dbg] %d layers, %d jobs/tile, %d stages: MMA warp of CTA 0: total %lld cycles over %lld tiles: wait input %lld, "
+                    "wait TMEM slot %lld, wait previous layer's epilogue %lld, wait weight stage %lld, issue %lld\n",
+            P.n_layers, P.n_jobs, P.stages, h[0], h[6], h[1], h[2], h[3], h[4], h[5]);
+  }
   if (trace_path) {
     static unsigned long long host[4 * 8192];
     CB_CUDA(cudaStreamSynchronize(st));
