@@ -17,9 +17,21 @@ continues eagerly.
 from __future__ import annotations
 
 import os
+import threading
 
 import torch
 from torch import Tensor
+
+# one capture at a time per process: several worker threads may train different models on the same GPU
+# (train.parallel_training with a device listed more than once, like config_full.yaml:16 of the reference)
+_CAPTURE_LOCK = threading.Lock()
+# stream capture and unrelated CUDA work of OTHER host threads on the same device do not mix (capture
+# isolation errors), so workers that share a GPU train eagerly: train.parallel_training sets this flag
+_TLS = threading.local()
+
+
+def disable_for_this_thread(flag: bool = True) -> None:
+    _TLS.disabled = bool(flag)
 
 
 def graphs_enabled() -> bool:
@@ -40,7 +52,7 @@ class GraphedTrainStep:
         self.fwd_bwd, self.optimizer = fwd_bwd, optimizer
         self.device = torch.device(device)
         self.enabled = bool(enabled and graphs_enabled() and self.device.type == "cuda"
-                            and hasattr(optimizer, "graph_launch"))
+                            and hasattr(optimizer, "graph_launch") and not getattr(_TLS, "disabled", False))
         self.seen: dict = {}
         self.sig = None
         self.graph = None
@@ -62,11 +74,13 @@ class GraphedTrainStep:
         self.static = tuple(b.clone() if isinstance(b, Tensor) else b for b in dev_batch)
         self.optimizer.zero_grad(set_to_none=True)
         self.optimizer.graph_prepare()
-        torch.cuda.synchronize(self.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            loss = self.fwd_bwd(self.static)
-            self.optimizer.graph_launch()
+        with _CAPTURE_LOCK:
+            torch.cuda.current_stream(self.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            # thread_local: other host threads keep launching / allocating on their own streams meanwhile
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                loss = self.fwd_bwd(self.static)
+                self.optimizer.graph_launch()
         self.graph, self.loss, self.sig = graph, loss, _signature(batch)
         graph.replay()                      # the capture itself executes nothing: run this step now
         self.optimizer.graph_after()

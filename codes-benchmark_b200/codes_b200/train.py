@@ -169,6 +169,26 @@ def parallel_training(tasks: Sequence[Task], device_list: Sequence[str], train_f
     guard = threading.Lock()
 
     def worker(device: str, idx: int):
+        # every worker gets its own CUDA stream: two workers on the same GPU (a device listed twice, as in
+        # config_full.yaml:16) then overlap their kernels instead of serialising on the default stream
+        stream_ctx = None
+        try:
+            import torch
+            if str(device).startswith("cuda") and torch.cuda.is_available():
+                stream_ctx = torch.cuda.stream(torch.cuda.Stream(device))
+                stream_ctx.__enter__()
+                if list(device_list).count(device) > 1:
+                    from .graph_step import disable_for_this_thread
+                    disable_for_this_thread(True)      # shared GPU: no stream capture next to other threads' work
+        except Exception:  # noqa: BLE001  (host-only tests run without torch.cuda)
+            stream_ctx = None
+        try:
+            _worker_loop(device, idx)
+        finally:
+            if stream_ctx is not None:
+                stream_ctx.__exit__(None, None, None)
+
+    def _worker_loop(device: str, idx: int):
         while True:
             try:
                 task = queue.get_nowait()
