@@ -116,6 +116,11 @@ class AbstractSurrogateModel(ABC, nn.Module):
             self.__dict__["_stepper"] = st
         return st
 
+    def _finish_training(self) -> None:
+        """Release the captured training graph (its private memory pool holds a whole step's activations)."""
+        st = self.__dict__.pop("_stepper", None)
+        self.__dict__["_graph_replays"] = st.replays if st is not None else 0
+
     # ------------------------------------------------------------------ inference
     def predict(self, data_loader: DataLoader, leave_log: bool = False,
                 leave_norm: bool = False) -> tuple[Tensor, Tensor]:

@@ -168,6 +168,7 @@ class MultiONet(OperatorNetwork):
                           optimizer=optimizer, progress_bar=progress_bar, total_epochs=epochs,
                           multi_objective=multi_objective)
         progress_bar.close()
+        self._finish_training()
         self.n_epochs = epoch + 1
         self.get_checkpoint(test_loader, criterion)
 

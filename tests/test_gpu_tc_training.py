@@ -203,7 +203,7 @@ def test_cuda_graph_training_step_matches_eager(which, monkeypatch):
             tr, te, _ = m.prepare_data(d, d[:8], None, np.linspace(0, 1, T), bs, shuffle=True)
             m.fit(tr, te, epochs=6)
             finals[graphs] = [p.detach().clone() for p in m.parameters()]
-            replays[graphs] = m.__dict__["_stepper"].replays
+            replays[graphs] = m.__dict__["_graph_replays"]
     finally:
         cb.set_precision("fp32"); cb.set_train_precision("bf16")
     assert replays["0"] == 0 and replays["1"] > 5, replays
