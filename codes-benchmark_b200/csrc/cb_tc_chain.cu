@@ -45,6 +45,17 @@ constexpr int kMaxGroups = 128;      // 32-column groups of the MultiONet output
 constexpr int kMaxStages = 12;
 constexpr int kEpiThreads = 256;   // 8 epilogue warps: two per TMEM lane quarter, splitting the columns
 constexpr int kThreads = 64 + kEpiThreads;
+// chain kernel: more epilogue warps (its layer-to-layer critical path IS the epilogue): EW/4 warps per TMEM lane
+// quarter, each taking every (EW/4)-th 32-column group of a chunk
+#ifndef CB_CHAIN_EPI_WARPS
+#define CB_CHAIN_EPI_WARPS 16
+#endif
+constexpr int kCEpiWarps = CB_CHAIN_EPI_WARPS;
+constexpr int kCEpiThreads = 32 * kCEpiWarps;
+constexpr int kCThreads = 64 + kCEpiThreads;
+constexpr int kCColStride = 32 * (kCEpiWarps / 4);
+static_assert(kCEpiWarps % 4 == 0 && kCEpiWarps >= 4 && kCEpiWarps <= 16, "epilogue warps: 4, 8, 12 or 16");
+__device__ __forceinline__ void chain_epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kCEpiThreads) : "memory"); }
 constexpr int kCtrlBytes = 16 * kMaxStages + 16 * kSlots + 64;
 
 enum { IN_F32 = 0, IN_BF16_TMA = 1 };
@@ -55,6 +66,9 @@ struct Job { int16_t layer, n0, ncols, last_chunk; };
 struct ChainParams {
   CUtensorMap tmap_in;         // IN_BF16_TMA : (rows, ld_in) bf16
   CUtensorMap tmap_out;        // OUT_BF16_TMA: (rows, ld_out) bf16
+  CUtensorMap tmap_w64;        // CTA-pair mode: ALL layers' packed weights as one (rows, 64) tensor, 64-row boxes
+  CUtensorMap tmap_w8;         //   the same tensor with 8-row boxes (half chunks narrower than 64 rows)
+  int w_row0[CB_MAX_LAYERS];   //   first row of layer l inside that tensor
   const __nv_bfloat16* w[CB_MAX_LAYERS];   // pre-tiled, pre-swizzled weights: tile (chunk, kb) = 16 KiB run
   int K[CB_MAX_LAYERS];        // true input width (the ones column sits at index K)
   int N[CB_MAX_LAYERS];        // true output width
@@ -71,6 +85,11 @@ struct ChainParams {
   float* y;
   long long rows;
   int num_tiles;
+  // TMEM-resident variant (chain_ts_kernel)
+  int ts_slots;                // weight slots (one whole chunk of a layer each) in shared memory
+  int ts_acol;                 // first TMEM column of the packed bf16 activations (the accumulators start at column 0)
+  __nv_bfloat16* yb;           // OUT_BF16_TMA: bf16 output (rows, ld_yb), written with plain vector stores
+  int ld_yb;
   unsigned long long* trace;   // debug timeline (CB_TC_TRACE), NULL in production
   long long* dbg;              // CB_TC_CHAIN_DBG: cycle counters of CTA 0's MMA warp (debug), else NULL
 };
@@ -126,6 +145,8 @@ struct Ctrl {
   uint32_t* tmem_ptr;
   int* epi_done;
   int* in_staged;
+  int* epi_done_peer;    // CTA-pair mode: the peer CTA's counters (kept in the leader's shared memory)
+  int* in_staged_peer;
 };
 
 __device__ __forceinline__ Ctrl carve_ctrl(uint32_t ctrl_addr, uint8_t* ctrl_ptr) {
@@ -138,13 +159,15 @@ __device__ __forceinline__ Ctrl carve_ctrl(uint32_t ctrl_addr, uint8_t* ctrl_ptr
   c.tmem_ptr = reinterpret_cast<uint32_t*>(ctrl_ptr + 16 * kMaxStages + 16 * kSlots + 8);
   c.epi_done = reinterpret_cast<int*>(c.tmem_ptr + 1);
   c.in_staged = c.epi_done + 1;
+  c.epi_done_peer = c.epi_done + 2;
+  c.in_staged_peer = c.epi_done + 3;
   return c;
 }
 
-__device__ __forceinline__ uint32_t setup_cta(const Ctrl& c, int stages, int warp) {
+__device__ __forceinline__ uint32_t setup_cta(const Ctrl& c, int stages, int warp, int tempty_count = kEpiThreads) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(c.bar_full + 8 * s, 1); mbar_init(c.bar_empty + 8 * s, 1); }
-    for (int s = 0; s < kSlots; ++s) { mbar_init(c.bar_tfull + 8 * s, 1); mbar_init(c.bar_tempty + 8 * s, kEpiThreads); }
+    for (int s = 0; s < kSlots; ++s) { mbar_init(c.bar_tfull + 8 * s, 1); mbar_init(c.bar_tempty + 8 * s, tempty_count); }
     mbar_init(c.bar_in, 1);
     *c.epi_done = 0;
     *c.in_staged = 0;
@@ -178,24 +201,65 @@ __device__ __forceinline__ void teardown_cta(uint32_t tmem_base, int warp) {
 #endif
 
 // ====================================================================== chain kernel
-template <int ACT, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1)
+// CG2 = true: two CTAs of a cluster (one TPC) push two neighbouring 128-row tiles through the chain in
+// lock step with tcgen05.mma.cta_group::2 (M = 256).  Every weight k-block is split between the two CTAs'
+// shared memory (ncols/2 rows each), which HALVES the L2 -> SM weight stream per row -- the single-CTA
+// kernel pulls ~245 KB of weights per 128-row tile and 275-wide layer, 70+ % of the measured L2 throughput
+// cap with all 148 SMs streaming -- and doubles the stages in flight.  The leader CTA (rank 0) issues all
+// MMAs; both CTAs run their own weight producer (own half of every stage, transaction bytes credited to
+// the leader's barrier), their own input staging and their own epilogue (own 128 TMEM lanes, own
+// activation buffers).  The dependency counters of both CTAs live in the leader's shared memory.
+template <int ACT, bool PAIR, bool CG2>
+__global__ void __launch_bounds__(kCThreads, 1)
 chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
   const uint32_t xbytes = (uint32_t)P.kb_max * kKBlockBytes;
+  constexpr uint32_t kStageBytes = CG2 ? kKBlockBytes / 2 : kKBlockBytes;
   const uint32_t X0 = base, X1 = P.inplace ? base : base + xbytes, ST0 = base + (P.inplace ? 1 : 2) * xbytes;
-  const uint32_t ctrl_addr = ST0 + (uint32_t)P.stages * kKBlockBytes;
+  const uint32_t ctrl_addr = ST0 + (uint32_t)P.stages * kStageBytes;
   const Ctrl C = carve_ctrl(ctrl_addr, gbase + (ctrl_addr - base));
   // fp32 output staging (OUT_F32 only): the activation buffer that is idle during the last layer
   // when it is large enough, else a dedicated region behind the control block
   const uint32_t OSTG = P.ostage_in_x ? ((P.n_layers & 1) ? X1 : X0) : ctrl_addr + kCtrlBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_base = setup_cta(C, P.stages, warp);
-  const int n_my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t rank = CG2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  uint32_t tmem_base;
+  if constexpr (CG2) {
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < P.stages; ++s) { mbar_init(C.bar_full + 8 * s, 1); mbar_init(C.bar_empty + 8 * s, 1); }
+      // tempty: one arrival per epilogue warp of BOTH CTAs (on the leader's barrier)
+      for (int s = 0; s < kSlots; ++s) { mbar_init(C.bar_tfull + 8 * s, 1); mbar_init(C.bar_tempty + 8 * s, 2 * kCEpiWarps); }
+      mbar_init(C.bar_in, 1);
+      *C.epi_done = 0; *C.in_staged = 0; *C.epi_done_peer = 0; *C.in_staged_peer = 0;
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(C.tmem_ptr)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    tmem_base = *reinterpret_cast<volatile uint32_t*>(C.tmem_ptr);
+  } else {
+    tmem_base = setup_cta(C, P.stages, warp, kCEpiThreads);
+  }
+  // work units: 128-row tiles, or (CG2) pairs of neighbouring tiles, one per cluster
+  const int units = CG2 ? (P.num_tiles + 1) / 2 : P.num_tiles;
+  const int my0 = CG2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int stride = CG2 ? (int)num_clusters_x() : (int)gridDim.x;
+  const int n_my_tiles = (units - my0 + stride - 1) / stride;
+  // barriers / counters owned by the leader CTA, as shared::cluster addresses
+  const uint32_t L_bar_full = CG2 ? mapa_shared(C.bar_full, 0) : C.bar_full;
+  const uint32_t L_bar_tempty = CG2 ? mapa_shared(C.bar_tempty, 0) : C.bar_tempty;
+  const uint32_t L_epi_done = CG2 ? mapa_shared(smem_u32(leader ? C.epi_done : C.epi_done_peer), 0) : 0u;
+  const uint32_t L_in_staged = CG2 ? mapa_shared(smem_u32(leader ? C.in_staged : C.in_staged_peer), 0) : 0u;
 
   if (warp == 0) {
     // ============================================================ TMA producer (warp-converged, one elected lane issues)
@@ -204,9 +268,9 @@ chain_kernel(const __grid_constant__ ChainParams P) {
       int tn = 0;
       int seen_epi = 0;
       for (int it = 0; it < n_my_tiles; ++it) {
-        if (P.in_mode == IN_BF16_TMA) {
+        if (!CG2 && P.in_mode == IN_BF16_TMA) {
           // X0 may be refilled once every MMA/epilogue of the previous tile has retired
-          wait_counter(C.epi_done, it * P.n_jobs, seen_epi);
+          wait_counter(C.epi_done, it * P.n_jobs * kCEpiWarps, seen_epi);
           const int tile = (int)blockIdx.x + it * (int)gridDim.x;
           if (elect_one()) {
             mbar_arrive_expect_tx(C.bar_in, (uint32_t)P.nkb[0] * kKBlockBytes);
@@ -219,13 +283,27 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           const Job job = P.jobs[j];
           const int nkb = P.nkb[job.layer];
           const __nv_bfloat16* src = P.w[job.layer] + (size_t)(job.n0 / kChunkN) * nkb * (kKBlockBytes / 2);
+          // CG2: this CTA's half of the chunk's weight rows = rows [rank * ncols/2, +ncols/2) of tile (chunk, kb)
+          const int half = job.ncols >> 1;
+          const int wrow = P.w_row0[job.layer] + (job.n0 / kChunkN) * nkb * kChunkN + (int)rank * half;
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(C.bar_empty + 8 * stage, phase ^ 1);
             CB_TRACE(0, 1, j * 8 + kb);
             if (elect_one()) {
-              mbar_arrive_expect_tx(C.bar_full + 8 * stage, kKBlockBytes);
-              bulk_load(ST0 + stage * kKBlockBytes, src + (size_t)kb * (kKBlockBytes / 2), kKBlockBytes,
-                        C.bar_full + 8 * stage);
+              if constexpr (CG2) {
+                if (leader) mbar_arrive_expect_tx(C.bar_full + 8 * stage, (uint32_t)job.ncols * 128u);
+                const uint32_t dst = ST0 + stage * kStageBytes;
+                if (half == 64) {
+                  tma_load_2d_pair(dst, &P.tmap_w64, 0, wrow + kb * kChunkN, L_bar_full + 8 * stage);
+                } else {
+                  for (int i = 0; i < half; i += 8)
+                    tma_load_2d_pair(dst + i * 128, &P.tmap_w8, 0, wrow + kb * kChunkN + i, L_bar_full + 8 * stage);
+                }
+              } else {
+                mbar_arrive_expect_tx(C.bar_full + 8 * stage, kKBlockBytes);
+                bulk_load(ST0 + stage * kKBlockBytes, src + (size_t)kb * (kKBlockBytes / 2), kKBlockBytes,
+                          C.bar_full + 8 * stage);
+              }
             }
             __syncwarp();
             if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -234,12 +312,13 @@ chain_kernel(const __grid_constant__ ChainParams P) {
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer (warp-converged; one elected lane issues)
-    {
+    // ============================================================ MMA issuer (warp-converged; one elected lane issues;
+    //                                                              CG2: the leader CTA issues for both)
+    if (leader) {
       int stage = 0; uint32_t phase = 0;
       int gj = 0;
       int tn = 0;
-      int seen_in = 0, seen_epi = 0;
+      int seen_in = 0, seen_epi = 0, seen_in_p = 0, seen_epi_p = 0;
       const uint64_t bdesc0 = make_smem_desc(ST0);
       constexpr bool pair = PAIR;   // host picks PAIR only when the ring has >= 4 stages (a shallower ring would drain)
       long long c_tempty = 0, c_dep = 0, c_full = 0, c_issue = 0, c_in = 0;
@@ -256,7 +335,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           tcgen05_fence_after();
           c_tempty += CB_CLK() - c0;
           const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
-          const uint32_t idesc = make_idesc(job.ncols);
+          const uint32_t idesc = CG2 ? make_idesc_pair(job.ncols) : make_idesc(job.ncols);
           const int nkb = P.nkb[l];
           const int last_nks = P.ksteps[l] - (nkb - 1) * 4;
           const uint64_t adesc0 = make_smem_desc((l & 1) ? X1 : X0);
@@ -265,8 +344,13 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           int need0 = 0, last_pc = 0;
           if (l == 0) {
             c0 = CB_CLK();
-            if (P.in_mode == IN_BF16_TMA) mbar_wait(C.bar_in, it & 1);
-            else wait_counter(C.in_staged, it + 1, seen_in);
+            if constexpr (CG2) {
+              wait_counter_cluster(C.in_staged, (it + 1) * kCEpiWarps, seen_in);
+              wait_counter_cluster(C.in_staged_peer, (it + 1) * kCEpiWarps, seen_in_p);
+            } else {
+              if (P.in_mode == IN_BF16_TMA) mbar_wait(C.bar_in, it & 1);
+              else wait_counter(C.in_staged, (it + 1) * kCEpiWarps, seen_in);
+            }
             c_in += CB_CLK() - c0;
           } else {
             need0 = it * P.n_jobs + P.first_job[l - 1] + 1;
@@ -279,7 +363,16 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           for (int kb = 0; kb < nkb; kb += (pair ? 2 : 1)) {
             const bool two = pair && (kb + 1 < nkb);
             c0 = CB_CLK();
-            if (l != 0) wait_counter(C.epi_done, need0 + (P.inplace ? last_pc : min((kb + (two ? 1 : 0)) >> 1, last_pc)), seen_epi);
+            if (l != 0) {
+              // every epilogue warp bumps the counter once per job
+              const int need = (need0 + (P.inplace ? last_pc : min((kb + (two ? 1 : 0)) >> 1, last_pc))) * kCEpiWarps;
+              if constexpr (CG2) {
+                wait_counter_cluster(C.epi_done, need, seen_epi);
+                wait_counter_cluster(C.epi_done_peer, need, seen_epi_p);
+              } else {
+                wait_counter(C.epi_done, need, seen_epi);
+              }
+            }
             const long long c1 = CB_CLK();
             c_dep += c1 - c0;
             CB_TRACE(1, 3, j * 8 + kb);
@@ -291,33 +384,52 @@ chain_kernel(const __grid_constant__ ChainParams P) {
             tcgen05_fence_after();
             const long long c2 = CB_CLK();
             c_full += c2 - c1;
-            // descriptor start-address field counts 16-byte units: +1024 per 16 KiB k-block / stage,
+            // descriptor start-address field counts 16-byte units: +1024 per 16 KiB k-block,
             // +2 per 16-column k-step
             const uint64_t adesc = adesc0 + (uint64_t)(kb * (kKBlockBytes >> 4));
-            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kKBlockBytes >> 4));
-            const uint64_t bdesc_b = bdesc0 + (uint64_t)(stage_b * (kKBlockBytes >> 4));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kStageBytes >> 4));
+            const uint64_t bdesc_b = bdesc0 + (uint64_t)(stage_b * (kStageBytes >> 4));
             const int nks_a = (kb == nkb - 1) ? last_nks : 4;
             const int nks_b = (kb + 1 == nkb - 1) ? last_nks : 4;
             if (elect_one()) {
-              umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+              if constexpr (CG2) {
+                umma_bf16_pair(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
 #pragma unroll
-              for (int ks = 1; ks < 4; ++ks)
-                if (ks < nks_a) umma_bf16(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
-              umma_commit(C.bar_empty + 8 * stage);   // frees the weight stage when these MMAs retire
-              if (two) {
-                const uint64_t adesc_b = adesc + (uint64_t)(kKBlockBytes >> 4);
+                for (int ks = 1; ks < 4; ++ks)
+                  if (ks < nks_a) umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
+                umma_commit_pair(C.bar_empty + 8 * stage);
+                if (two) {
+                  const uint64_t adesc_b = adesc + (uint64_t)(kKBlockBytes >> 4);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  if (ks < nks_b) umma_bf16(d_tmem, adesc_b + (uint64_t)(2 * ks), bdesc_b + (uint64_t)(2 * ks), idesc, 1u);
-                umma_commit(C.bar_empty + 8 * stage_b);
+                  for (int ks = 0; ks < 4; ++ks)
+                    if (ks < nks_b) umma_bf16_pair(d_tmem, adesc_b + (uint64_t)(2 * ks), bdesc_b + (uint64_t)(2 * ks), idesc, 1u);
+                  umma_commit_pair(C.bar_empty + 8 * stage_b);
+                }
+              } else {
+                umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+#pragma unroll
+                for (int ks = 1; ks < 4; ++ks)
+                  if (ks < nks_a) umma_bf16(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
+                umma_commit(C.bar_empty + 8 * stage);   // frees the weight stage when these MMAs retire
+                if (two) {
+                  const uint64_t adesc_b = adesc + (uint64_t)(kKBlockBytes >> 4);
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    if (ks < nks_b) umma_bf16(d_tmem, adesc_b + (uint64_t)(2 * ks), bdesc_b + (uint64_t)(2 * ks), idesc, 1u);
+                  umma_commit(C.bar_empty + 8 * stage_b);
+                }
               }
             }
             __syncwarp();
+            CB_TRACE(1, 10, j * 8 + kb);
             c_issue += CB_CLK() - c2;
             if (two) { stage = stage_b; phase = phase_b; }
             if (++stage == P.stages) { stage = 0; phase ^= 1; }
           }
-          if (elect_one()) umma_commit(C.bar_tfull + 8 * slot);   // accumulator chunk complete -> epilogue
+          if (elect_one()) {   // accumulator chunk complete -> epilogue (of both CTAs)
+            if constexpr (CG2) umma_commit_pair(C.bar_tfull + 8 * slot);
+            else umma_commit(C.bar_tfull + 8 * slot);
+          }
           __syncwarp();
         }
       }
@@ -330,21 +442,21 @@ chain_kernel(const __grid_constant__ ChainParams P) {
     // ============================================================ epilogue warps (2..9)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;            // row inside the tile
-    const int h = (warp - 2) >> 2;          // column half: this warp takes 32-column groups with (group & 1) == h
-    const int et = threadIdx.x - 64;        // 0..255
+    const int h = (warp - 2) >> 2;          // this warp takes the 32-column groups with group % (EW/4) == h
+    const int et = threadIdx.x - 64;        // 0..kCEpiThreads-1
     const int K0 = P.K[0];
     int gj = 0;
     int tn = 0;
     const int trole = (warp == 2) ? 2 : (warp == 6 ? 3 : 4);
     for (int it = 0; it < n_my_tiles; ++it) {
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int tile = CG2 ? (my0 + it * stride) * 2 + (int)rank : my0 + it * stride;
       const long long row_g = (long long)tile * kTileM + r;
       const bool row_ok = row_g < P.rows;
-      if (P.in_mode == IN_F32) {
+      if (CG2 || P.in_mode == IN_F32) {
         // stage the fp32 input rows as the bf16 A operand of layer 0: [x, 1, 0...] padded to 16*ksteps
         const float* xr = P.x + row_g * K0;
         const int nch = P.ksteps[0] * 2;    // 16-byte chunks (8 columns each)
-        for (int c = h; c < nch; c += 2) {
+        for (int c = h; c < nch; c += kCEpiWarps / 4) {
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -355,8 +467,11 @@ chain_kernel(const __grid_constant__ ChainParams P) {
                        pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
         }
         fence_proxy_async();
-        epi_bar_sync();
-        if (et == 0) red_release_inc(C.in_staged);
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG2) red_release_inc_cluster(L_in_staged);
+          else red_release_inc(C.in_staged);
+        }
       }
       for (int j = 0; j < P.n_jobs; ++j, ++gj) {
         const Job job = P.jobs[j];
@@ -378,7 +493,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * kChunkN;
         const uint32_t xo = ((l + 1) & 1) ? X1 : X0;
         const int N = P.N[l];
-        for (int c0 = h * 32; c0 < job.ncols; c0 += 64) {
+        for (int c0 = h * 32; c0 < job.ncols; c0 += kCColStride) {
           uint32_t v[32];
           const int w = min(32, job.ncols - c0);   // 32 or 16
           if (w == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
@@ -405,7 +520,12 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           }
         }
         tcgen05_fence_before();
-        mbar_arrive(C.bar_tempty + 8 * slot);
+        if constexpr (CG2) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(L_bar_tempty + 8 * slot);
+        } else {
+          mbar_arrive(C.bar_tempty + 8 * slot);
+        }
         if (trole < 4) CB_TRACE(trole, 7, j);
         if (to_smem) {
           if (h == 0 && job.last_chunk && (N & 15) == 0) {
@@ -415,9 +535,9 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           }
           fence_proxy_async();                     // generic-proxy smem writes -> visible to tcgen05.mma / TMA
           if (trole < 4) CB_TRACE(trole, 8, j);
-          epi_bar_sync();
-          if (trole < 4) CB_TRACE(trole, 9, j);
+          // no CTA-wide barrier on the layer-to-layer path: every warp publishes its own columns (below)
           if (last && job.last_chunk) {
+            chain_epi_bar_sync();
             // OUT_BF16_TMA: the finished activation tile leaves through TMA stores (rows >= M are clipped)
             if (et == 0) {
               for (int kb = 0; kb < P.out_nkb; ++kb)
@@ -425,27 +545,364 @@ chain_kernel(const __grid_constant__ ChainParams P) {
               tma_store_commit();
               tma_store_wait_read();
             }
-            epi_bar_sync();
+            chain_epi_bar_sync();
           }
         } else {
-          epi_bar_sync();
-          // coalesced copy-out: thread owns column n0 + (et & 127) for the rows of parity (et >> 7)
+          chain_epi_bar_sync();
+          // coalesced copy-out: thread owns column n0 + (et & 127) for the rows r with r % (EW/4) == et >> 7
           const int col = et & 127;
           const int n = job.n0 + col;
           if (col < job.ncols && n < N) {
             const long long rows_left = P.rows - (long long)tile * kTileM;
             const int nr = rows_left < kTileM ? (int)(rows_left < 0 ? 0 : rows_left) : kTileM;
             float* yp = P.y + (long long)tile * kTileM * N + n;
-            for (int rr = et >> 7; rr < nr; rr += 2)
+            for (int rr = et >> 7; rr < nr; rr += kCEpiWarps / 4)
               yp[(long long)rr * N] = ld_shared_f32(OSTG + (uint32_t)((rr * P.stage_ld + col) * 4));
           }
-          epi_bar_sync();
+          chain_epi_bar_sync();
         }
-        if (et == 0) red_release_inc(C.epi_done);
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG2) red_release_inc_cluster(L_epi_done);
+          else red_release_inc(C.epi_done);
+        }
       }
     }
   }
-  teardown_cta(tmem_base, warp);
+  if constexpr (CG2) {
+    tcgen05_fence_before();
+    cluster_sync_all();          // the leader's MMAs write the peer's TMEM: nobody leaves early
+    if (warp == 1) {
+      tcgen05_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+  } else {
+    teardown_cta(tmem_base, warp);
+  }
+}
+
+// ====================================================================== TMEM-resident chain kernel
+// Same contract as chain_kernel, different data path: the activations of the 128-row tile never touch shared
+// memory.  The A operand of every layer lives in TENSOR MEMORY (lane = row, bf16 pairs packed along K,
+// tcgen05.mma "TS" form), the epilogue reads the fp32 accumulators with tcgen05.ld, applies the activation
+// and writes the next layer's A operand back with tcgen05.st.  Why: a 128x128x16 SS-form MMA reads 8 KB of
+// shared memory in its 64 cycles (= the full 128 B/clk of the SM), so the epilogue's shared-memory stores and
+// the MMAs throttled each other, and the 160 KiB of ping-pong activation buffers left room for only 4 weight
+// stages.  Here shared memory holds nothing but weights: a SLOT is one whole output chunk of a layer (all its
+// k-blocks, one mbarrier, one bulk copy), so the issuing warp does one wait per 18 MMAs instead of one per 4.
+// TMEM map: columns [0, Np) fp32 accumulators of the current layer (chunk c at 128 c), columns
+// [ts_acol, ts_acol + Kp/2) the packed activations.  A layer's epilogue keeps its packed outputs in registers
+// until the layer's last MMA has retired (the MMAs still read the old activations), then stores them in place.
+// CG2: CTA pairs as in chain_kernel (each CTA loads half of every weight tile; leader issues M = 256 MMAs).
+constexpr int kTsMaxChunks = 3;       // 128-column chunks per layer (widths up to 383)
+constexpr int kTsMaxSlots = 8;
+constexpr int kTsCtrlBytes = 256;
+
+template <int ACT, bool CG2>
+__global__ void __launch_bounds__(kCThreads, 1)
+chain_ts_kernel(const __grid_constant__ ChainParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  constexpr uint32_t kTileBytes = CG2 ? kKBlockBytes / 2 : kKBlockBytes;
+  const uint32_t slot_bytes = (uint32_t)P.kb_max * kTileBytes;
+  const uint32_t W0 = base;
+  const uint32_t ctrl = W0 + (uint32_t)P.ts_slots * slot_bytes;
+  const uint32_t bar_wfull = ctrl, bar_wempty = ctrl + 8 * kTsMaxSlots, bar_tfull = ctrl + 16 * kTsMaxSlots;
+  uint8_t* ctrl_ptr = gbase + (ctrl - base);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ctrl_ptr + 16 * kTsMaxSlots + 8 * kTsMaxChunks + 8);
+  int* a_ready = reinterpret_cast<int*>(tmem_ptr + 1);        // epochs of A published by this CTA's epilogue warps
+  int* a_ready_peer = a_ready + 1;                            // CG2: the peer's counter, kept in the leader
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.ts_slots; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
+    for (int c = 0; c < kTsMaxChunks; ++c) mbar_init(bar_tfull + 8 * c, 1);
+    *a_ready = 0; *a_ready_peer = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    if constexpr (CG2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tcgen05_fence_before();
+  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
+
+  const int units = CG2 ? (P.num_tiles + 1) / 2 : P.num_tiles;
+  const int my0 = CG2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int stride = CG2 ? (int)num_clusters_x() : (int)gridDim.x;
+  const int n_my_tiles = (units - my0 + stride - 1) / stride;
+  const uint32_t L_wfull = CG2 ? mapa_shared(bar_wfull, 0) : bar_wfull;
+  const uint32_t L_a_ready = CG2 ? mapa_shared(smem_u32(leader ? a_ready : a_ready_peer), 0) : 0u;
+
+  if (warp == 0) {
+    // ============================================================ weight producer: one slot = one (layer, chunk)
+    int slot = 0; uint32_t phase = 0;
+    for (int it = 0; it < n_my_tiles; ++it) {
+      for (int j = 0; j < P.n_jobs; ++j) {
+        const Job job = P.jobs[j];
+        const int nkb = P.nkb[job.layer];
+        mbar_wait(bar_wempty + 8 * slot, phase ^ 1);
+        if (elect_one()) {
+          const uint32_t dst = W0 + (uint32_t)slot * slot_bytes;
+          if constexpr (CG2) {
+            const int half = job.ncols >> 1;
+            const int wrow = P.w_row0[job.layer] + (job.n0 / kChunkN) * nkb * kChunkN + (int)rank * half;
+            if (leader) mbar_arrive_expect_tx(bar_wfull + 8 * slot, (uint32_t)(job.ncols * 128 * nkb));
+            for (int kb = 0; kb < nkb; ++kb) {
+              if (half == 64) {
+                tma_load_2d_pair(dst + kb * kTileBytes, &P.tmap_w64, 0, wrow + kb * kChunkN, L_wfull + 8 * slot);
+              } else {
+                for (int i = 0; i < half; i += 8)
+                  tma_load_2d_pair(dst + kb * kTileBytes + i * 128, &P.tmap_w8, 0, wrow + kb * kChunkN + i, L_wfull + 8 * slot);
+              }
+            }
+          } else {
+            const __nv_bfloat16* src = P.w[job.layer] + (size_t)(job.n0 / kChunkN) * nkb * (kKBlockBytes / 2);
+            if (job.ncols == kChunkN) {
+              // the chunk's k-blocks are one contiguous run of nkb x 16 KiB
+              mbar_arrive_expect_tx(bar_wfull + 8 * slot, (uint32_t)nkb * kKBlockBytes);
+              bulk_load(dst, src, (uint32_t)nkb * kKBlockBytes, bar_wfull + 8 * slot);
+            } else {
+              // narrow chunk: only its ncols rows of every tile
+              mbar_arrive_expect_tx(bar_wfull + 8 * slot, (uint32_t)(nkb * job.ncols * 128));
+              for (int kb = 0; kb < nkb; ++kb)
+                bulk_load(dst + kb * kKBlockBytes, src + (size_t)kb * (kKBlockBytes / 2), (uint32_t)job.ncols * 128u,
+                          bar_wfull + 8 * slot);
+            }
+          }
+        }
+        __syncwarp();
+        if (++slot == P.ts_slots) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    if (leader) {
+      int slot = 0; uint32_t phase = 0;
+      int seen = 0, seen_p = 0, epoch = 0;
+      const uint32_t a_tmem = tmem_base + (uint32_t)P.ts_acol;
+      long long c_dep = 0, c_full = 0, c_issue = 0;
+      const long long c_start = CB_CLK();
+      for (int it = 0; it < n_my_tiles; ++it) {
+        for (int l = 0; l < P.n_layers; ++l, ++epoch) {
+          // this layer's A operand (input staging or the previous layer's epilogue) is complete in TMEM and the
+          // accumulator columns have been read out
+          long long c0 = CB_CLK();
+          if constexpr (CG2) {
+            wait_counter_cluster(a_ready, (epoch + 1) * kCEpiWarps, seen);
+            wait_counter_cluster(a_ready_peer, (epoch + 1) * kCEpiWarps, seen_p);
+          } else {
+            wait_counter(a_ready, (epoch + 1) * kCEpiWarps, seen);
+          }
+          tcgen05_fence_after();
+          c_dep += CB_CLK() - c0;
+          const int nkb = P.nkb[l];
+          const int last_nks = P.ksteps[l] - (nkb - 1) * 4;
+          for (int c = 0; c < P.n_chunks[l]; ++c) {
+            const Job job = P.jobs[P.first_job[l] + c];
+            c0 = CB_CLK();
+            mbar_wait(bar_wfull + 8 * slot, phase);
+            tcgen05_fence_after();
+            const long long c1 = CB_CLK();
+            c_full += c1 - c0;
+            const uint32_t d_tmem = tmem_base + (uint32_t)c * kChunkN;
+            const uint32_t idesc = CG2 ? make_idesc_pair(job.ncols) : make_idesc(job.ncols);
+            const uint64_t bdesc0 = make_smem_desc(W0 + (uint32_t)slot * slot_bytes);
+            if (elect_one()) {
+              for (int kb = 0; kb < nkb; ++kb) {
+                const int nks = (kb == nkb - 1) ? last_nks : 4;
+                const uint64_t bdesc = bdesc0 + (uint64_t)(kb * (kTileBytes >> 4));
+                const uint32_t a_kb = a_tmem + (uint32_t)(kb * 32);      // 4 k-steps x 8 packed columns
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks < nks) {
+                    if constexpr (CG2) umma_bf16_ts_pair(d_tmem, a_kb + 8 * ks, bdesc + (uint64_t)(2 * ks), idesc, (kb | ks) ? 1u : 0u);
+                    else umma_bf16_ts(d_tmem, a_kb + 8 * ks, bdesc + (uint64_t)(2 * ks), idesc, (kb | ks) ? 1u : 0u);
+                  }
+                }
+              }
+              if constexpr (CG2) { umma_commit_pair(bar_wempty + 8 * slot); umma_commit_pair(bar_tfull + 8 * c); }
+              else { umma_commit(bar_wempty + 8 * slot); umma_commit(bar_tfull + 8 * c); }
+            }
+            __syncwarp();
+            c_issue += CB_CLK() - c1;
+            if (++slot == P.ts_slots) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+      if (P.dbg && blockIdx.x == 0 && lane == 0) {
+        P.dbg[0] = CB_CLK() - c_start; P.dbg[1] = 0; P.dbg[2] = 0; P.dbg[3] = c_dep; P.dbg[4] = c_full;
+        P.dbg[5] = c_issue; P.dbg[6] = n_my_tiles;
+      }
+    }
+  } else {
+    // ============================================================ epilogue warps (2..17)
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int r = q * 32 + lane;            // row inside the tile
+    const int h = (warp - 2) >> 2;          // this warp owns columns [32 h, 32 h + 32) of every 128-column chunk
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t a_tmem = lane_base + (uint32_t)P.ts_acol;
+    const int K0 = P.K[0];
+    uint32_t tphase = 0;                    // bit c: parity of the next completion of tfull[c]
+    long long c_epi = 0, c_twait = 0, c_e1 = 0, c_e2 = 0, c_e3 = 0; long long ce1 = 0, ce2 = 0;
+    auto publish = [&]() {
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG2) red_release_inc_cluster(L_a_ready);
+        else red_release_inc(a_ready);
+      }
+    };
+    for (int it = 0; it < n_my_tiles; ++it) {
+      const int tile = CG2 ? (my0 + it * stride) * 2 + (int)rank : my0 + it * stride;
+      const long long row_g = (long long)tile * kTileM + r;
+      const bool row_ok = row_g < P.rows;
+      {
+        // layer 0's A operand: [x, 1, 0...] padded to 16 * ksteps, 16 elements (8 packed columns) per unit
+        const float* xr = P.x + row_g * K0;
+        for (int u = h; u < P.ksteps[0]; u += kCEpiWarps / 4) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = u * 16 + 2 * i;
+            const float lo = (k < K0) ? (row_ok ? __ldg(xr + k) : 0.f) : (k == K0 ? 1.f : 0.f);
+            const float hi = (k + 1 < K0) ? (row_ok ? __ldg(xr + k + 1) : 0.f) : (k + 1 == K0 ? 1.f : 0.f);
+            pk[i] = pack_bf16(lo, hi);
+          }
+          tmem_st8(a_tmem + (uint32_t)(u * 8), pk);
+        }
+        publish();
+      }
+      for (int l = 0; l < P.n_layers; ++l) {
+        const bool last = (l == P.n_layers - 1);
+        const bool hidden_like = !last || P.out_mode == OUT_BF16_TMA;
+        const int N = P.N[l];
+        const int Np = (N + 15) & ~15;
+        const int nch = P.n_chunks[l];
+        uint32_t R[kTsMaxChunks][16];
+        long long ce0 = CB_CLK();
+#pragma unroll
+        for (int c = 0; c < kTsMaxChunks; ++c) {
+          if (c < nch) {
+            const long long cw0 = CB_CLK();
+            mbar_wait(bar_tfull + 8 * c, (tphase >> c) & 1u);
+            if (c == nch - 1) { ce0 = CB_CLK(); }
+            c_twait += CB_CLK() - cw0;
+            tphase ^= 1u << c;
+            tcgen05_fence_after();
+            const int nb = c * kChunkN + h * 32;
+            const int w = min(32, Np - nb);          // 32, 16 or <= 0
+            if (w > 0) {
+              uint32_t v[32];
+              if (w == 32) tmem_ld32(lane_base + (uint32_t)nb, v); else tmem_ld16(lane_base + (uint32_t)nb, v);
+              tmem_ld_wait();
+              if (c == nch - 1) ce1 = CB_CLK();
+              if (hidden_like) {
+                if (nb + w <= N) {
+                  // group entirely inside the layer's true width (warp-uniform): activation + pack only
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    R[c][i] = (2 * i < w) ? pack_bf16(act_fast<ACT>(__uint_as_float(v[2 * i]), P.act_param),
+                                                      act_fast<ACT>(__uint_as_float(v[2 * i + 1]), P.act_param))
+                                          : 0u;
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const int n = nb + 2 * i;
+                    float lo = act_fast<ACT>(__uint_as_float(v[2 * i]), P.act_param);
+                    float hi = act_fast<ACT>(__uint_as_float(v[2 * i + 1]), P.act_param);
+                    // column N carries the constant 1.0 that multiplies the folded bias; padding columns are zero
+                    if (n >= N) lo = (n == N) ? 1.f : 0.f;
+                    if (n + 1 >= N) hi = (n + 1 == N) ? 1.f : 0.f;
+                    R[c][i] = (2 * i < w) ? pack_bf16(lo, hi) : 0u;
+                  }
+                }
+              } else if (row_ok) {
+                // final fp32 outputs straight to global memory
+                const bool tanh_out = (P.final_act == CB_ACT_TANH);
+                float* yp = P.y + row_g * N;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const int n = nb + i;
+                  if (i < w && n < N) {
+                    const float z = __uint_as_float(v[i]);
+                    yp[n] = tanh_out ? tanhf(z) : z;
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (hidden_like) {
+          // every tfull of the layer has been observed: its MMAs have retired and no longer read the old A
+          uint32_t ones[8] = {pack_bf16(1.f, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          const bool ones_unit = ((N & 15) == 0) && h == 0;   // column N opens a fresh 16-element k-step
+          if (!last) {
+            ce2 = CB_CLK();
+#pragma unroll
+            for (int c = 0; c < kTsMaxChunks; ++c) {
+              if (c < nch) {
+                const int nb = c * kChunkN + h * 32;
+                const int w = min(32, Np - nb);
+                if (w == 32) tmem_st16(a_tmem + (uint32_t)(nb >> 1), R[c]);
+                else if (w == 16) tmem_st8(a_tmem + (uint32_t)(nb >> 1), R[c]);
+              }
+            }
+            if (ones_unit) tmem_st8(a_tmem + (uint32_t)(N >> 1), ones);
+            tmem_st_wait();
+            const long long ce3 = CB_CLK();
+            publish();
+            const long long ce4 = CB_CLK();
+            c_epi += ce4 - ce0; c_e1 += ce1 - ce0; c_e2 += ce2 - ce1; c_e3 += ce3 - ce2;
+          } else if (row_ok) {
+            // OUT_BF16_TMA contract (rows, ld) bf16 incl. the ones column: plain 16-byte stores
+            __nv_bfloat16* yr = P.yb + row_g * P.ld_yb;
+#pragma unroll
+            for (int c = 0; c < kTsMaxChunks; ++c) {
+              if (c < nch) {
+                const int nb = c * kChunkN + h * 32;
+                const int w = min(32, Np - nb);
+                if (w > 0) {
+                  uint4* dst = reinterpret_cast<uint4*>(yr + nb);
+                  dst[0] = make_uint4(R[c][0], R[c][1], R[c][2], R[c][3]);
+                  dst[1] = make_uint4(R[c][4], R[c][5], R[c][6], R[c][7]);
+                  if (w == 32) {
+                    dst[2] = make_uint4(R[c][8], R[c][9], R[c][10], R[c][11]);
+                    dst[3] = make_uint4(R[c][12], R[c][13], R[c][14], R[c][15]);
+                  }
+                }
+              }
+            }
+            if (ones_unit) {
+              uint4* dst = reinterpret_cast<uint4*>(yr + N);
+              dst[0] = make_uint4(ones[0], 0u, 0u, 0u);
+              dst[1] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+        }
+      }
+    }
+    if (P.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) { P.dbg[1] = c_epi; P.dbg[2] = c_twait; P.dbg[8] = c_e1; P.dbg[9] = c_e2; P.dbg[10] = c_e3; }
+  }
+  tcgen05_fence_before();
+  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    if constexpr (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
 }
 
 // ====================================================================== MultiONet final kernel
@@ -786,24 +1243,42 @@ static bool encode_bf16_map(CUtensorMap* map, const void* ptr, long long rows, l
 }
 
 typedef void (*ChainKernelFn)(const ChainParams);
-template <bool PAIR>
+template <bool PAIR, bool CG2>
 static ChainKernelFn chain_kernel_for_act(int act) {
   switch (act) {
-    case CB_ACT_RELU: return chain_kernel<CB_ACT_RELU, PAIR>;
+    case CB_ACT_RELU: return chain_kernel<CB_ACT_RELU, PAIR, CG2>;
     case CB_ACT_LEAKYRELU:
-    case CB_ACT_PRELU: return chain_kernel<CB_ACT_LEAKYRELU, PAIR>;
-    case CB_ACT_TANH: return chain_kernel<CB_ACT_TANH, PAIR>;
-    case CB_ACT_GELU: return chain_kernel<CB_ACT_GELU, PAIR>;
-    case CB_ACT_ELU: return chain_kernel<CB_ACT_ELU, PAIR>;
-    case CB_ACT_SILU: return chain_kernel<CB_ACT_SILU, PAIR>;
-    case CB_ACT_SOFTPLUS: return chain_kernel<CB_ACT_SOFTPLUS, PAIR>;
-    case CB_ACT_MISH: return chain_kernel<CB_ACT_MISH, PAIR>;
-    case CB_ACT_SIGMOID: return chain_kernel<CB_ACT_SIGMOID, PAIR>;
-    default: return chain_kernel<CB_ACT_IDENTITY, PAIR>;
+    case CB_ACT_PRELU: return chain_kernel<CB_ACT_LEAKYRELU, PAIR, CG2>;
+    case CB_ACT_TANH: return chain_kernel<CB_ACT_TANH, PAIR, CG2>;
+    case CB_ACT_GELU: return chain_kernel<CB_ACT_GELU, PAIR, CG2>;
+    case CB_ACT_ELU: return chain_kernel<CB_ACT_ELU, PAIR, CG2>;
+    case CB_ACT_SILU: return chain_kernel<CB_ACT_SILU, PAIR, CG2>;
+    case CB_ACT_SOFTPLUS: return chain_kernel<CB_ACT_SOFTPLUS, PAIR, CG2>;
+    case CB_ACT_MISH: return chain_kernel<CB_ACT_MISH, PAIR, CG2>;
+    case CB_ACT_SIGMOID: return chain_kernel<CB_ACT_SIGMOID, PAIR, CG2>;
+    default: return chain_kernel<CB_ACT_IDENTITY, PAIR, CG2>;
   }
 }
 static ChainKernelFn chain_kernel_for(int act, int stages) {
-  return stages >= 4 ? chain_kernel_for_act<true>(act) : chain_kernel_for_act<false>(act);
+  return stages >= 4 ? chain_kernel_for_act<true, false>(act) : chain_kernel_for_act<false, false>(act);
+}
+// CTA-pair (cta_group::2) variant; its ring of half-size stages always has >= 4 entries
+static ChainKernelFn chain_pair_kernel_for(int act) { return chain_kernel_for_act<true, true>(act); }
+template <bool CG2>
+static ChainKernelFn chain_ts_kernel_for(int act) {
+  switch (act) {
+    case CB_ACT_RELU: return chain_ts_kernel<CB_ACT_RELU, CG2>;
+    case CB_ACT_LEAKYRELU:
+    case CB_ACT_PRELU: return chain_ts_kernel<CB_ACT_LEAKYRELU, CG2>;
+    case CB_ACT_TANH: return chain_ts_kernel<CB_ACT_TANH, CG2>;
+    case CB_ACT_GELU: return chain_ts_kernel<CB_ACT_GELU, CG2>;
+    case CB_ACT_ELU: return chain_ts_kernel<CB_ACT_ELU, CG2>;
+    case CB_ACT_SILU: return chain_ts_kernel<CB_ACT_SILU, CG2>;
+    case CB_ACT_SOFTPLUS: return chain_ts_kernel<CB_ACT_SOFTPLUS, CG2>;
+    case CB_ACT_MISH: return chain_ts_kernel<CB_ACT_MISH, CG2>;
+    case CB_ACT_SIGMOID: return chain_ts_kernel<CB_ACT_SIGMOID, CG2>;
+    default: return chain_ts_kernel<CB_ACT_IDENTITY, CG2>;
+  }
 }
 
 }  // namespace tc
@@ -827,8 +1302,13 @@ struct cb_tc_chain {
   int device;
   int out_mode;                 // OUT_F32 | OUT_BF16_TMA
   ChainParams P;
+  __nv_bfloat16* d_wall;        // one allocation holding every layer's packed weights (d_w[i] point into it)
   __nv_bfloat16* d_w[CB_MAX_LAYERS];
   int Kp[CB_MAX_LAYERS], rows_alloc[CB_MAX_LAYERS];
+  int cg2;                      // CTA-pair kernel available for this chain
+  int stages_cg2; size_t smem_cg2;
+  int ts, ts_pair;              // TMEM-resident kernel available (single CTA / CTA pairs)
+  int ts_slots[2]; size_t smem_ts[2];   // [0] single CTA, [1] CTA pairs
   int ld_out;                   // OUT_BF16_TMA: columns of the bf16 output (multiple of 64)
   size_t smem_bytes;
   int weights_set;
@@ -836,7 +1316,9 @@ struct cb_tc_chain {
 
 // Geometry of the fused chain.  Both ping-pong buffers, >= 2 weight stages and (OUT_F32) the fp32
 // output staging tile must fit in 227 KiB of shared memory.
-struct ChainGeom { int kb_max, stages, n_jobs, stage_ld, out_nkb, ostage_in_x, inplace; size_t smem; bool ok; };
+struct ChainGeom { int kb_max, stages, n_jobs, stage_ld, out_nkb, ostage_in_x, inplace; size_t smem; bool ok;
+                   int stages_cg2; size_t smem_cg2; bool cg2_ok;
+                   bool ts_ok; int ts_acol, ts_slots[2]; size_t smem_ts[2]; };
 
 static ChainGeom chain_geometry(const cb_mlp_desc* d, int out_mode) {
   ChainGeom g{};
@@ -859,6 +1341,14 @@ static ChainGeom chain_geometry(const cb_mlp_desc* d, int out_mode) {
   }
   long long fixed = 1024 /*align slack*/ + kCtrlBytes + (long long)ostage + 2ll * g.kb_max * kKBlockBytes;
   long long stages = ((long long)kMaxSmem - fixed) / kKBlockBytes;
+  {
+    // CTA-pair variant (ping-pong buffers only): every stage holds half a weight k-block (8 KiB)
+    long long s2 = ((long long)kMaxSmem - fixed) / (kKBlockBytes / 2);
+    if (s2 > kMaxStages) s2 = kMaxStages;
+    g.stages_cg2 = (int)s2;
+    g.smem_cg2 = (size_t)(fixed + (s2 > 0 ? s2 : 0) * (kKBlockBytes / 2));
+    g.cg2_ok = s2 >= 4;
+  }
   if (stages < 2) {
     // Wide chain: fall back to ONE activation buffer updated in place.  Every chunk of a layer must then
     // sit in TMEM at once (<= 4 slots x 128 columns) and the layers run strictly one after the other.
@@ -883,6 +1373,32 @@ static ChainGeom chain_geometry(const cb_mlp_desc* d, int out_mode) {
   g.smem = (size_t)(fixed + (stages > 0 ? stages : 0) * kKBlockBytes);
   const bool final_ok = d->final_act == CB_ACT_IDENTITY || d->final_act == CB_ACT_TANH || out_mode == OUT_BF16_TMA;
   g.ok = stages >= 2 && g.n_jobs <= kMaxJobs && final_ok;
+  g.cg2_ok = g.cg2_ok && g.ok && !g.inplace;
+  {
+    // TMEM-resident variant: accumulators (max padded width) + packed activations (max padded K / 2) in 512 columns,
+    // at most kTsMaxChunks chunks per layer, shared memory = weight slots of kb_max tiles
+    int acc = 0, acols = 0, kbm = 1, chunks = 0;
+    for (int i = 0; i < n; ++i) {
+      const int np = round_up(d->dims[i + 1], 16);
+      const int ksteps = (d->dims[i] + 1 + kUmmaK - 1) / kUmmaK;
+      acc = np > acc ? np : acc;
+      acols = ksteps * 8 > acols ? ksteps * 8 : acols;
+      kbm = (ksteps + 3) / 4 > kbm ? (ksteps + 3) / 4 : kbm;
+      const int ch = (np + kChunkN - 1) / kChunkN;
+      chunks = ch > chunks ? ch : chunks;
+    }
+    g.ts_acol = round_up(acc, 32);
+    g.ts_ok = final_ok && g.n_jobs <= kMaxJobs && chunks <= kTsMaxChunks && g.ts_acol + acols <= 512;
+    for (int v = 0; v < 2; ++v) {
+      const long long slot = (long long)g.kb_max * (v ? kKBlockBytes / 2 : kKBlockBytes);   // = the kernel's P.kb_max
+      long long slots = ((long long)kMaxSmem - 1024 - kTsCtrlBytes) / slot;
+      if (slots > kTsMaxSlots) slots = kTsMaxSlots;
+      g.ts_slots[v] = (int)slots;
+      g.smem_ts[v] = (size_t)(1024 + kTsCtrlBytes + (slots > 0 ? slots : 0) * slot);
+    }
+    g.ts_ok = g.ts_ok && g.ts_slots[0] >= 2;
+    (void)kbm;
+  }
   return g;
 }
 
@@ -900,8 +1416,7 @@ extern "C" int32_t cb_tc_supported(void) {
 
 extern "C" void cb_tc_chain_destroy(cb_tc_chain* plan) {
   if (!plan) return;
-  for (int i = 0; i < CB_MAX_LAYERS; ++i)
-    if (plan->d_w[i]) cudaFree(plan->d_w[i]);
+  if (plan->d_wall) cudaFree(plan->d_wall);
   delete plan;
 }
 
@@ -943,14 +1458,47 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
     P.n_chunks[i] = chunks;
     pl->Kp[i] = P.nkb[i] * kBlockK;
     pl->rows_alloc[i] = round_up(N, kChunkN);
-    if (cudaMalloc(&pl->d_w[i], (size_t)pl->rows_alloc[i] * pl->Kp[i] * sizeof(__nv_bfloat16)) != cudaSuccess) {
+  }
+  P.n_jobs = nj;
+  {
+    // one buffer for all layers: layer i is a run of (rows_alloc * Kp / 64) rows of 64 bf16 (128 bytes)
+    long long rows64 = 0;
+    for (int i = 0; i < desc->n_layers; ++i) {
+      P.w_row0[i] = (int)rows64;
+      rows64 += (long long)pl->rows_alloc[i] * (pl->Kp[i] / kBlockK);
+    }
+    if (cudaMalloc(&pl->d_wall, (size_t)rows64 * kBlockK * sizeof(__nv_bfloat16)) != cudaSuccess) {
       cb_tc_chain_destroy(pl);
       set_error("cudaMalloc of the bf16 weight cache failed");
       return CB_ERR_CUDA;
     }
-    P.w[i] = pl->d_w[i];
+    for (int i = 0; i < desc->n_layers; ++i) {
+      pl->d_w[i] = pl->d_wall + (size_t)P.w_row0[i] * kBlockK;
+      P.w[i] = pl->d_w[i];
+    }
+    const char* e = getenv("CB_TC_CHAIN_PAIR");   // opt-in (slower than the single-CTA kernel while the epilogue bounds the chain)
+    pl->cg2 = g.cg2_ok && (e && atoi(e) != 0) && encode_bf16_rows64(&P.tmap_w64, pl->d_wall, rows64, 64) &&
+              encode_bf16_rows64(&P.tmap_w8, pl->d_wall, rows64, 8);
+    pl->stages_cg2 = g.stages_cg2;
+    pl->smem_cg2 = g.smem_cg2;
+    {
+      const char* t = getenv("CB_TC_CHAIN_TS");      // experiment knob: 0 = shared-memory-activation kernel only
+      pl->ts = g.ts_ok && !(t && atoi(t) == 0);
+      pl->ts_pair = pl->ts && (e && atoi(e) != 0) && encode_bf16_rows64(&P.tmap_w64, pl->d_wall, rows64, 64) &&
+                    encode_bf16_rows64(&P.tmap_w8, pl->d_wall, rows64, 8);
+      P.ts_acol = g.ts_acol;
+      for (int v = 0; v < 2; ++v) { pl->ts_slots[v] = g.ts_slots[v]; pl->smem_ts[v] = g.smem_ts[v]; }
+      if (pl->ts && cudaFuncSetAttribute(chain_ts_kernel_for<false>(desc->act), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)pl->smem_ts[0]) != cudaSuccess) { cudaGetLastError(); pl->ts = 0; pl->ts_pair = 0; }
+      if (pl->ts_pair && cudaFuncSetAttribute(chain_ts_kernel_for<true>(desc->act), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)pl->smem_ts[1]) != cudaSuccess) { cudaGetLastError(); pl->ts_pair = 0; }
+    }
+    if (pl->cg2 && cudaFuncSetAttribute(chain_pair_kernel_for(desc->act), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)pl->smem_cg2) != cudaSuccess) {
+      cudaGetLastError();
+      pl->cg2 = 0;
+    }
   }
-  P.n_jobs = nj;
   pl->smem_bytes = g.smem;
   if (cudaFuncSetAttribute(chain_kernel_for(desc->act, g.stages), cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)pl->smem_bytes) != cudaSuccess) {
@@ -986,7 +1534,8 @@ extern "C" int32_t cb_tc_chain_set_weights(cb_tc_chain* plan, const float* const
 
 // launch helper shared by the public forward and the MultiONet pipeline
 static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorMap* in_map, int64_t rows,
-                            float* d_y, const CUtensorMap* out_map, cudaStream_t st) {
+                            float* d_y, const CUtensorMap* out_map, cudaStream_t st, __nv_bfloat16* d_yb = nullptr,
+                            int ld_yb = 0) {
   ChainParams P = plan->P;
   P.x = d_x; P.y = d_y; P.rows = rows;
   if (in_map) { P.in_mode = IN_BF16_TMA; P.tmap_in = *in_map; }
@@ -1001,14 +1550,55 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
   }
   P.dbg = nullptr;
   const char* dbg_env = getenv("CB_TC_CHAIN_DBG");
-  if (dbg_env) { CB_CUDA(cudaMalloc(&P.dbg, 64)); CB_CUDA(cudaMemsetAsync(P.dbg, 0, 64, st)); }
-  chain_kernel_for(plan->desc.act, P.stages)<<<grid, kThreads, plan->smem_bytes, st>>>(P);
+  if (dbg_env) { CB_CUDA(cudaMalloc(&P.dbg, 128)); CB_CUDA(cudaMemsetAsync(P.dbg, 0, 128, st)); }
+  const bool ts = plan->ts && !in_map && (plan->out_mode == OUT_F32 || d_yb != nullptr) && !trace_path;
+  if (ts) {
+    // TMEM-resident activations; CTA pairs need two tiles per cluster
+    const bool pair = plan->ts_pair && P.num_tiles >= 2;
+    P.yb = d_yb; P.ld_yb = ld_yb;
+    P.ts_slots = plan->ts_slots[pair ? 1 : 0];
+    if (pair) {
+      const int pairs = (P.num_tiles + 1) / 2;
+      const int clusters = pairs < grid_cap() / 2 ? pairs : grid_cap() / 2;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2 * clusters);
+      cfg.blockDim = dim3(kCThreads);
+      cfg.dynamicSmemBytes = plan->smem_ts[1];
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      CB_CUDA(cudaLaunchKernelEx(&cfg, chain_ts_kernel_for<true>(plan->desc.act), P));
+    } else {
+      chain_ts_kernel_for<false>(plan->desc.act)<<<grid, kCThreads, plan->smem_ts[0], st>>>(P);
+    }
+  } else if (plan->cg2 && !in_map && P.num_tiles >= 2) {
+    const int pairs = (P.num_tiles + 1) / 2;
+    const int clusters = pairs < grid_cap() / 2 ? pairs : grid_cap() / 2;
+    P.stages = plan->stages_cg2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kCThreads);
+    cfg.dynamicSmemBytes = plan->smem_cg2;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CB_CUDA(cudaLaunchKernelEx(&cfg, chain_pair_kernel_for(plan->desc.act), P));
+  } else {
+    chain_kernel_for(plan->desc.act, P.stages)<<<grid, kCThreads, plan->smem_bytes, st>>>(P);
+  }
   CB_LAUNCH_CHECK();
   if (dbg_env) {
-    long long h[8];
+    long long h[16];
     CB_CUDA(cudaStreamSynchronize(st));
-    CB_CUDA(cudaMemcpy(h, P.dbg, 64, cudaMemcpyDeviceToHost));
+    CB_CUDA(cudaMemcpy(h, P.dbg, 128, cudaMemcpyDeviceToHost));
     cudaFree(P.dbg);
+    if (ts) fprintf(stderr, "[chain-ts dbg] epilogue warp 2: last tfull -> published %lld (ld %lld, act %lld, st %lld), waiting tfull %lld; ", h[1], h[8], h[9], h[10], h[2]);
     fprintf(stderr, "[chain dbg] %d layers, %d jobs/tile, %d stages: MMA warp of CTA 0: total %lld cycles over %lld tiles: wait input %lld, "
                     "wait TMEM slot %lld, wait previous layer's epilogue %lld, wait weight stage %lld, issue %lld\n",
             P.n_layers, P.n_jobs, P.stages, h[0], h[6], h[1], h[2], h[3], h[4], h[5]);
@@ -1230,9 +1820,9 @@ static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_
   for (int i = 0; i < 2; ++i)
     CB_CHECK_ARG(encode_bf16_map(&hmap[i], h[i], rows, m->ld_h), "tensor map of the hidden activations failed");
   if (ev) cudaEventRecord(ev[0], st);
-  if (int32_t e = chain_launch(m->hidden[0], d_branch_in, nullptr, rows, nullptr, &hmap[0], st)) return e;
+  if (int32_t e = chain_launch(m->hidden[0], d_branch_in, nullptr, rows, nullptr, &hmap[0], st, h[0], m->ld_h)) return e;
   if (ev) cudaEventRecord(ev[1], st);
-  if (int32_t e = chain_launch(m->hidden[1], d_trunk_in, nullptr, rows, nullptr, &hmap[1], st)) return e;
+  if (int32_t e = chain_launch(m->hidden[1], d_trunk_in, nullptr, rows, nullptr, &hmap[1], st, h[1], m->ld_h)) return e;
   if (ev) cudaEventRecord(ev[2], st);
   CB_CUDA(cudaMemsetAsync(d_y, 0, (size_t)rows * m->Q * sizeof(float), st));   // the final kernel accumulates into y
   FinalParams F = m->F;

@@ -113,6 +113,41 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+// registers -> TMEM: lane (row) i of the warp's quarter writes its 16 / 8 values to columns [c, c+16) / [c, c+8)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem: lane = row, bf16 pairs packed along K] * B[smem]^T   ("TS" form: the A operand never touches
+// shared memory)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -177,7 +212,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 template <int ACT>
 __device__ __forceinline__ float act_fast(float x, float p) {
   if constexpr (ACT == CB_ACT_RELU) return fmaxf(x, 0.f);
-  else if constexpr (ACT == CB_ACT_LEAKYRELU || ACT == CB_ACT_PRELU) return (p >= 0.f && p <= 1.f) ? fmaxf(x, p * x) : (x >= 0.f ? x : p * x);
+  else if constexpr (ACT == CB_ACT_LEAKYRELU || ACT == CB_ACT_PRELU) return fmaf(p, fminf(x, 0.f), fmaxf(x, 0.f));
   else if constexpr (ACT == CB_ACT_TANH) return tanh_fast(x);
   else if constexpr (ACT == CB_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
   else if constexpr (ACT == CB_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
@@ -220,6 +255,18 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// dependency counters that live in the leader CTA's shared memory and are bumped by either CTA of a pair
+__device__ __forceinline__ void red_release_inc_cluster(uint32_t cluster_addr) {
+  asm volatile("red.release.cluster.shared::cluster.add.s32 [%0], 1;" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void wait_counter_cluster(const int* p, int need, int& seen) {
+  if (seen >= need) return;
+  int v;
+  do {
+    asm volatile("ld.acquire.cluster.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  } while (v < need);
+  seen = v;
 }
 // TMA tile load issued by either CTA of a pair into its OWN shared memory; the transaction bytes are
 // credited to the mbarrier at `bar_cluster_addr` (the leader CTA's barrier)

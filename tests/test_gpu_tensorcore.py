@@ -67,6 +67,39 @@ def test_chain_matches_oracle(dims, act, fact, rows):
     assert np.abs(y - ref).max() <= 2e-2 * np.abs(ref).max()
 
 
+PAIR_CHAINS = [
+    ([29, 275, 275, 275, 275, 275, 29], "leakyrelu", "identity", 129),        # two tiles, the second almost empty
+    ([1, 275, 275, 275, 275, 275, 275, 275, 275, 275, 29], "leakyrelu", "identity", 128 * 7 + 5),   # odd tile count
+    ([6, 150, 150, 150, 150, 150, 5], "relu", "identity", 40000),             # several pairs per cluster
+    ([5, 64, 64, 64, 29], "relu", "tanh", 5000),
+    ([11, 256, 256, 11], "gelu", "identity", 1300),
+    ([9, 100, 112, 9], "elu", "identity", 640),                               # half chunks of 50 -> 56 and 8 rows
+]
+
+
+@pytest.mark.parametrize("dims,act,fact,rows", PAIR_CHAINS)
+def test_chain_kernel_variants_are_bitwise_identical(dims, act, fact, rows, monkeypatch):
+    """four kernels compute the fused chain: activations in tensor memory (default) or in shared memory
+    (CB_TC_CHAIN_TS=0), each on single CTAs or on CTA pairs (cta_group::2, CB_TC_CHAIN_PAIR=1: two 128-row tiles
+    per cluster, weight k-blocks split between the CTAs).  All accumulate every output in the same order."""
+    tc = _tc()
+    from codes_b200 import ops
+    rng = np.random.default_rng(sum(dims) + rows)
+    ws = [torch.from_numpy((rng.normal(size=(b, a)) / np.sqrt(a)).astype(np.float32)).to(DEV) for a, b in zip(dims[:-1], dims[1:])]
+    bs = [torch.from_numpy((rng.normal(size=(b,)) * 0.1).astype(np.float32)).to(DEV) for b in dims[1:]]
+    x = torch.from_numpy(rng.uniform(-1, 1, size=(rows, dims[0])).astype(np.float32)).to(DEV)
+    outs = {}
+    for ts in ("1", "0"):
+        for pair in ("0", "1"):
+            monkeypatch.setenv("CB_TC_CHAIN_TS", ts)              # both read when the plan is created
+            monkeypatch.setenv("CB_TC_CHAIN_PAIR", pair)
+            outs[ts, pair] = tc.chain_forward(ops.ChainSpec(dims, act, fact), x, ws, bs).cpu().numpy()
+    ref = O.mlp_chain(x.cpu().numpy(), [w.cpu().numpy() for w in ws], [b.cpu().numpy() for b in bs], act, fact)
+    assert rel_l2(outs["1", "0"], ref) <= 1e-2
+    for key, y in outs.items():
+        np.testing.assert_array_equal(y, outs["1", "0"], err_msg=f"variant TS={key[0]} PAIR={key[1]}")
+
+
 WIDE_CHAINS = [
     ([6, 800, 800, 800, 800, 800, 800, 800, 800, 5], "gelu", "identity", 3000),   # FCNN simple_ode config (cfg1)
     ([30, 600, 600, 29], "relu", "identity", 2049),
