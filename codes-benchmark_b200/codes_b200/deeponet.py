@@ -127,7 +127,10 @@ class MultiONet(OperatorNetwork):
         tensors = [torch.from_numpy(np.ascontiguousarray(a)).float()
                    for a in (branch, trunk, data.reshape(-1, Q))]
         pin = pin_memory and self.device is not None and "cuda" in self.device and torch.cuda.is_available()
-        ds = RowBatchIterable(tensors, batch_size, shuffle, pin=pin, device=self.device)
+        # rows r = n*T + t: branch (and the params) depend on n only, the time grid on t only
+        structure = ["repeat", "tile" if (dataset_params is None or params_in_branch) else "full", "full"]
+        ds = RowBatchIterable(tensors, batch_size, shuffle, pin=pin, device=self.device,
+                              row_structure=structure, period=T)
         return make_loader(ds, self.device, num_workers)
 
     def prepare_data(self, dataset_train, dataset_test, dataset_val, timesteps, batch_size, shuffle=True,

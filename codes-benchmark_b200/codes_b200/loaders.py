@@ -37,8 +37,23 @@ class RowBatchIterable(IterableDataset):
 
     def __init__(self, tensors: Sequence[torch.Tensor | None], batch_size: int, shuffle: bool,
                  layout: Sequence[tuple[str, int]] | None = None, constants: Sequence[torch.Tensor] = (),
-                 pin: bool = False, device: str | None = None):
+                 pin: bool = False, device: str | None = None,
+                 row_structure: Sequence[str] | None = None, period: int = 0):
         self.tensors = [_maybe_pin(t, pin) for t in tensors]
+        # SURVEY 8f N1 for un-shuffled (test / validation) loaders of the flat-row models, rows r = n*T + t:
+        # a tensor marked "repeat" only depends on n = r // T (the T-fold repeated x0 rows), one marked "tile"
+        # only on t = r % T (the time grid).  Iterating the loader still yields the reference's full batches;
+        # ``compact_batches`` lets ``predict`` copy each distinct row to the device once and expand it there.
+        self.period = int(period)
+        self.row_structure = list(row_structure) if row_structure is not None else None
+        self._compact = None
+        if self.row_structure is not None and self.period > 0 and not shuffle:
+            self._compact = [None if t is None else
+                             _maybe_pin(t[::self.period].contiguous(), pin) if kind == "repeat" else
+                             _maybe_pin(t[:self.period].contiguous(), pin) if kind == "tile" else None
+                             for t, kind in zip(self.tensors, self.row_structure)]
+        self._tile_dev = {}
+        self._idx_cache = {}
         self.constants = [_maybe_pin(c, pin) for c in constants]
         # layout: output tuple description, ("t", i) -> batched tensor i, ("c", i) -> constant i
         self.layout = list(layout) if layout is not None else [("t", i) for i in range(len(tensors))]
@@ -68,6 +83,47 @@ class RowBatchIterable(IterableDataset):
             batch = [None if t is None else ops.gather_rows(t, idx) for t in tensors]
             yield tuple(batch[i] if kind == "t" else constants[i] for kind, i in self.layout)
 
+    def compact_ok(self) -> bool:
+        return self._compact is not None and dedup_h2d_enabled()
+
+    def compact_batches(self, device: torch.device):
+        """Yield ``(batch_on_device, h2d_bytes)`` for every un-shuffled batch, issuing the copies and the on-device
+        expansion on the CURRENT stream.  Each batch equals ``tuple(x.to(device) for x in next(iter(self)))`` bit for
+        bit; "repeat" tensors move one row per trajectory, "tile" tensors stay resident after the first batch."""
+        from . import ops
+        T = self.period
+        for start in range(0, self.N, self.bs):
+            stop = min(self.N, start + self.bs)
+            rows = stop - start
+            key = (start % T, rows)
+            idx = self._idx_cache.get((device, key))
+            if idx is None:
+                r = torch.arange(rows, device=device, dtype=torch.int64) + (start % T)
+                idx = self._idx_cache[(device, key)] = (torch.div(r, T, rounding_mode="floor"), torch.remainder(r, T))
+            n_lo, n_hi = start // T, (stop - 1) // T + 1
+            nbytes = 0
+            batch = []
+            for i, (t, kind) in enumerate(zip(self.tensors, self.row_structure)):
+                if t is None:
+                    batch.append(None)
+                elif kind == "repeat":
+                    src = self._compact[i][n_lo:n_hi]
+                    nbytes += src.numel() * src.element_size()
+                    batch.append(ops.gather_rows(src.to(device, non_blocking=True), idx[0]))
+                elif kind == "tile":
+                    res = self._tile_dev.get((device, i))
+                    if res is None:
+                        src = self._compact[i]
+                        nbytes += src.numel() * src.element_size()
+                        res = self._tile_dev[(device, i)] = src.to(device, non_blocking=True)
+                    batch.append(ops.gather_rows(res, idx[1]))
+                else:
+                    src = t[start:stop]
+                    nbytes += src.numel() * src.element_size()
+                    batch.append(src.to(device, non_blocking=True))
+            consts = [c.to(device, non_blocking=True) for c in self.constants]
+            yield tuple(batch[i] if kind == "t" else consts[i] for kind, i in self.layout), nbytes
+
     def __iter__(self):
         perm = torch.randperm(self.N) if self.shuffle else None
         if self.device is not None:
@@ -86,6 +142,12 @@ def device_loader_enabled() -> bool:
     """CODES_B200_DEVICE_LOADER=0 restores host batches + H2D per step for training loaders."""
     import os
     return os.environ.get("CODES_B200_DEVICE_LOADER", "1") != "0"
+
+
+def dedup_h2d_enabled() -> bool:
+    """CODES_B200_DEDUP_H2D=0: ``predict`` copies the loader's full (T-fold repeated) batches as the reference does."""
+    import os
+    return os.environ.get("CODES_B200_DEDUP_H2D", "1") != "0"
 
 
 def make_loader(dataset: IterableDataset, device: str | None, num_workers: int = 0) -> DataLoader:

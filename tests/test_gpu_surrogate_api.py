@@ -140,3 +140,28 @@ def test_parametric_construction_forward_and_fit(name, data):
     m.fit(tr, te, epochs=1, position=0, description="test", multi_objective=False)
     preds, targets = m.predict(va)
     assert preds.shape == targets.shape == (C["n_val"], C["n_timesteps"], C["n_chemicals"])
+
+
+@pytest.mark.parametrize("n,T,bs", [(37, 20, 256), (50, 100, 1000), (8, 7, 1024)])
+def test_predict_with_deduplicated_h2d_equals_full_batches(n, T, bs, monkeypatch):
+    """predict() over an un-shuffled MultiONet loader copies x0 once per trajectory and rebuilds the loader's
+    T-fold repeated rows on the device (cb_gather_rows): results must equal the full-batch copy bit for bit, for batch
+    sizes that cut trajectories in two and for a ragged last batch."""
+    import codes_b200 as cb
+    Q = 6
+    rng = np.random.default_rng(n + T)
+    d = rng.uniform(-1, 1, size=(n, T, Q)).astype(np.float32)
+    torch.manual_seed(3)
+    m = cb.MultiONet("cuda:0", Q, T, 0, None, {"hidden_size": 48, "branch_hidden_layers": 2, "trunk_hidden_layers": 2,
+                                               "output_factor": 5})
+    _, _, val = m.prepare_data(d, None, d, np.linspace(0, 1, T), bs, shuffle=False)
+    assert val.dataset.compact_ok()
+    h0 = m.__dict__.get("_h2d_bytes", 0)
+    p1, t1 = m.predict(val)
+    moved = m.__dict__["_h2d_bytes"] - h0
+    assert moved < 4 * (n * T * Q + (n + len(val)) * Q + T) + 64      # targets + x0 (+ one straddled trajectory per batch) + grid
+    monkeypatch.setenv("CODES_B200_DEDUP_H2D", "0")
+    assert not val.dataset.compact_ok()
+    p2, t2 = m.predict(val)
+    assert torch.equal(p1, p2) and torch.equal(t1, t2)
+    np.testing.assert_array_equal(t1.cpu().numpy(), d)
