@@ -45,15 +45,17 @@ constexpr int kMaxGroups = 128;      // 32-column groups of the MultiONet output
 constexpr int kMaxStages = 12;
 constexpr int kEpiThreads = 256;   // 8 epilogue warps: two per TMEM lane quarter, splitting the columns
 constexpr int kThreads = 64 + kEpiThreads;
-// chain kernel: more epilogue warps (its layer-to-layer critical path IS the epilogue): EW/4 warps per TMEM lane
-// quarter, each taking every (EW/4)-th 32-column group of a chunk
+// chain kernels: EW/4 epilogue warps per TMEM lane quarter ("column classes"), each taking every (EW/4)-th 32-column
+// group.  12 warps = 3 classes: a 288-column layer (the 275-wide MultiONet nets) is 9 groups = 3 per warp, and 448
+// threads leave 146 registers per thread (the TS kernel keeps up to 4 packed groups + one raw group in registers)
 #ifndef CB_CHAIN_EPI_WARPS
-#define CB_CHAIN_EPI_WARPS 16
+#define CB_CHAIN_EPI_WARPS 12
 #endif
 constexpr int kCEpiWarps = CB_CHAIN_EPI_WARPS;
 constexpr int kCEpiThreads = 32 * kCEpiWarps;
 constexpr int kCThreads = 64 + kCEpiThreads;
 constexpr int kCColStride = 32 * (kCEpiWarps / 4);
+constexpr int kTsLast = kCColStride;   // TS kernel: width of a layer's last chunk = one 32-column group per warp
 static_assert(kCEpiWarps % 4 == 0 && kCEpiWarps >= 4 && kCEpiWarps <= 16, "epilogue warps: 4, 8, 12 or 16");
 __device__ __forceinline__ void chain_epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kCEpiThreads) : "memory"); }
 constexpr int kCtrlBytes = 16 * kMaxStages + 16 * kSlots + 64;
@@ -87,7 +89,10 @@ struct ChainParams {
   int num_tiles;
   // TMEM-resident variant (chain_ts_kernel)
   int ts_slots;                // weight slots (one whole chunk of a layer each) in shared memory
-  int ts_acol;                 // first TMEM column of the packed bf16 activations (the accumulators start at column 0)
+  int ts_acol;                 // first TMEM column of the packed bf16 activations (the accumulator ring starts at column 0)
+  int ts_slot_bytes;           // bytes of one weight slot
+  int ts_kbs;                  // k-block tiles per weight slot
+  int ts_nodep;                // EXPERIMENT (CB_TC_TS_NODEP, wrong results): 1 = MMAs do not wait for the epilogue, 2 = no weights wait either
   __nv_bfloat16* yb;           // OUT_BF16_TMA: bf16 output (rows, ld_yb), written with plain vector stores
   int ld_yb;
   unsigned long long* trace;   // debug timeline (CB_TC_TRACE), NULL in production
@@ -467,7 +472,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
                        pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
         }
         fence_proxy_async();
-        __syncwarp();
+        chain_epi_bar_sync();   // counters are running totals: keep the warps within one phase of each other
         if (lane == 0) {
           if constexpr (CG2) red_release_inc_cluster(L_in_staged);
           else red_release_inc(C.in_staged);
@@ -535,9 +540,10 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           }
           fence_proxy_async();                     // generic-proxy smem writes -> visible to tcgen05.mma / TMA
           if (trole < 4) CB_TRACE(trole, 8, j);
-          // no CTA-wide barrier on the layer-to-layer path: every warp publishes its own columns (below)
+          // the completion counter is a running total over (warp, job): the barrier keeps every warp within one job
+          // of the others, so "total >= 16 (J + 1)" does mean "every warp has written job J"
+          chain_epi_bar_sync();
           if (last && job.last_chunk) {
-            chain_epi_bar_sync();
             // OUT_BF16_TMA: the finished activation tile leaves through TMA stores (rows >= M are clipped)
             if (et == 0) {
               for (int kb = 0; kb < P.out_nkb; ++kb)
@@ -584,66 +590,58 @@ chain_kernel(const __grid_constant__ ChainParams P) {
 // ====================================================================== TMEM-resident chain kernel
 // Same contract as chain_kernel, different data path: the activations of the 128-row tile never touch shared
 // memory.  The A operand of every layer lives in TENSOR MEMORY (lane = row, bf16 pairs packed along K,
-// tcgen05.mma "TS" form), the epilogue reads the fp32 accumulators with tcgen05.ld, applies the activation
-// and writes the next layer's A operand back with tcgen05.st.  Why: a 128x128x16 SS-form MMA reads 8 KB of
-// shared memory in its 64 cycles (= the full 128 B/clk of the SM), so the epilogue's shared-memory stores and
-// the MMAs throttled each other, and the 160 KiB of ping-pong activation buffers left room for only 4 weight
-// stages.  Here shared memory holds nothing but weights: a SLOT is one whole output chunk of a layer (all its
-// k-blocks, one mbarrier, one bulk copy), so the issuing warp does one wait per 18 MMAs instead of one per 4.
-// TMEM map: columns [0, Np) fp32 accumulators of the current layer (chunk c at 128 c), columns
-// [ts_acol, ts_acol + Kp/2) the packed activations.  A layer's epilogue keeps its packed outputs in registers
-// until the layer's last MMA has retired (the MMAs still read the old activations), then stores them in place.
-// CG2: CTA pairs as in chain_kernel (each CTA loads half of every weight tile; leader issues M = 256 MMAs).
-constexpr int kTsMaxChunks = 3;       // 128-column chunks per layer (widths up to 383)
-constexpr int kTsMaxSlots = 8;
+// tcgen05.mma "TS" form); the epilogue reads the fp32 accumulators with tcgen05.ld, applies the activation
+// and writes the next layer's A operand back with tcgen05.st.  Measured facts behind the design (profiles/
+// r1_chain_ts_notes.md): (1) issuing one tcgen05.mma costs the issuing thread ~60 cycles whatever its shape, so a
+// layer is cut into as FEW instructions as possible -- at most two output chunks, the first up to 256 columns
+// wide (a 128x160x16 MMA is 80 tensor cycles, above the issue cost; the 128-column instructions of chain_kernel
+// were issue-bound); (2) every MMA -> epilogue -> MMA hand-off costs ~1.5 k cycles of latency, so there is ONE
+// hand-off per layer instead of one per 128-column chunk; (3) a 128x128x16 SS-form MMA reads 8 KB of shared memory
+// in 64 cycles (the SM's full 128 B/clk), so activations in shared memory throttle the MMAs -- here shared memory
+// holds nothing but weights: a SLOT is ts_kbs consecutive k-block tiles of one output chunk (one mbarrier, one bulk
+// copy of up to 48 KiB).
+// TMEM map (512 columns): [0, Np) fp32 accumulators of the current layer, [ts_acol, ts_acol + Kp/2) the packed
+// activations, updated IN PLACE: the epilogue converts a chunk as soon as its MMAs have retired (overlapping the
+// next chunk's MMAs), keeps the packed values in registers and stores them once the layer's last MMA has retired.
+// Chunking of a layer with padded width Np: Np <= 96 -> one chunk; else [Np - 96 columns (<= 256), 96 columns]: the
+// last chunk is what the epilogue works on while the tensor pipe idles, 96 columns = one 32-column group per warp.
+constexpr int kTsMaxSlots = 8;        // weight slots
 constexpr int kTsCtrlBytes = 256;
 
-template <int ACT, bool CG2>
+template <int ACT>
 __global__ void __launch_bounds__(kCThreads, 1)
 chain_ts_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  constexpr uint32_t kTileBytes = CG2 ? kKBlockBytes / 2 : kKBlockBytes;
-  const uint32_t slot_bytes = (uint32_t)P.kb_max * kTileBytes;
+  const uint32_t slot_bytes = (uint32_t)P.ts_slot_bytes;
   const uint32_t W0 = base;
   const uint32_t ctrl = W0 + (uint32_t)P.ts_slots * slot_bytes;
-  const uint32_t bar_wfull = ctrl, bar_wempty = ctrl + 8 * kTsMaxSlots, bar_tfull = ctrl + 16 * kTsMaxSlots;
+  const uint32_t bar_wfull = ctrl, bar_wempty = ctrl + 8 * kTsMaxSlots, bar_tfull = ctrl + 16 * kTsMaxSlots;   // tfull[2]
   uint8_t* ctrl_ptr = gbase + (ctrl - base);
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ctrl_ptr + 16 * kTsMaxSlots + 8 * kTsMaxChunks + 8);
-  int* a_ready = reinterpret_cast<int*>(tmem_ptr + 1);        // epochs of A published by this CTA's epilogue warps
-  int* a_ready_peer = a_ready + 1;                            // CG2: the peer's counter, kept in the leader
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ctrl_ptr + 16 * kTsMaxSlots + 16 + 8 + 8);
+  // bar_aready: epochs of A published by the epilogue warps, one arrival per warp and (tile, layer) -- an mbarrier
+  // (release semantics built in) instead of a counter + red.release, which costs a MEMBAR per publish.  A warp cannot
+  // start epoch e + 1 before the MMAs of epoch e have run, and those wait for ALL warps' epoch e.
+  const uint32_t bar_aready = bar_tfull + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = CG2 ? cluster_ctarank() : 0u;
-  const bool leader = rank == 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.ts_slots; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
-    for (int c = 0; c < kTsMaxChunks; ++c) mbar_init(bar_tfull + 8 * c, 1);
-    *a_ready = 0; *a_ready_peer = 0;
+    mbar_init(bar_tfull, 1); mbar_init(bar_tfull + 8, 1);
+    mbar_init(bar_aready, kCEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    if constexpr (CG2) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
-  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
+  __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
-
-  const int units = CG2 ? (P.num_tiles + 1) / 2 : P.num_tiles;
-  const int my0 = CG2 ? (int)cluster_id_x() : (int)blockIdx.x;
-  const int stride = CG2 ? (int)num_clusters_x() : (int)gridDim.x;
-  const int n_my_tiles = (units - my0 + stride - 1) / stride;
-  const uint32_t L_wfull = CG2 ? mapa_shared(bar_wfull, 0) : bar_wfull;
-  const uint32_t L_a_ready = CG2 ? mapa_shared(smem_u32(leader ? a_ready : a_ready_peer), 0) : 0u;
+  const int n_my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
     // ============================================================ weight producer: one slot = one (layer, chunk)
@@ -652,125 +650,107 @@ chain_ts_kernel(const __grid_constant__ ChainParams P) {
       for (int j = 0; j < P.n_jobs; ++j) {
         const Job job = P.jobs[j];
         const int nkb = P.nkb[job.layer];
-        mbar_wait(bar_wempty + 8 * slot, phase ^ 1);
-        if (elect_one()) {
-          const uint32_t dst = W0 + (uint32_t)slot * slot_bytes;
-          if constexpr (CG2) {
-            const int half = job.ncols >> 1;
-            const int wrow = P.w_row0[job.layer] + (job.n0 / kChunkN) * nkb * kChunkN + (int)rank * half;
-            if (leader) mbar_arrive_expect_tx(bar_wfull + 8 * slot, (uint32_t)(job.ncols * 128 * nkb));
-            for (int kb = 0; kb < nkb; ++kb) {
-              if (half == 64) {
-                tma_load_2d_pair(dst + kb * kTileBytes, &P.tmap_w64, 0, wrow + kb * kChunkN, L_wfull + 8 * slot);
-              } else {
-                for (int i = 0; i < half; i += 8)
-                  tma_load_2d_pair(dst + kb * kTileBytes + i * 128, &P.tmap_w8, 0, wrow + kb * kChunkN + i, L_wfull + 8 * slot);
-              }
-            }
-          } else {
-            const __nv_bfloat16* src = P.w[job.layer] + (size_t)(job.n0 / kChunkN) * nkb * (kKBlockBytes / 2);
-            if (job.ncols == kChunkN) {
-              // the chunk's k-blocks are one contiguous run of nkb x 16 KiB
-              mbar_arrive_expect_tx(bar_wfull + 8 * slot, (uint32_t)nkb * kKBlockBytes);
-              bulk_load(dst, src, (uint32_t)nkb * kKBlockBytes, bar_wfull + 8 * slot);
-            } else {
-              // narrow chunk: only its ncols rows of every tile
-              mbar_arrive_expect_tx(bar_wfull + 8 * slot, (uint32_t)(nkb * job.ncols * 128));
-              for (int kb = 0; kb < nkb; ++kb)
-                bulk_load(dst + kb * kKBlockBytes, src + (size_t)kb * (kKBlockBytes / 2), (uint32_t)job.ncols * 128u,
-                          bar_wfull + 8 * slot);
-            }
+        for (int kb0 = 0; kb0 < nkb; kb0 += P.ts_kbs) {
+          mbar_wait(bar_wempty + 8 * slot, phase ^ 1);
+          if (elect_one()) {
+            // the chunk's k-block tiles (ncols rows of 128 bytes each) follow each other in global memory
+            const uint32_t bytes = (uint32_t)(min(P.ts_kbs, nkb - kb0) * job.ncols * 128);
+            const __nv_bfloat16* src = P.w[job.layer] + ((size_t)job.n0 * nkb + (size_t)kb0 * job.ncols) * kBlockK;
+            mbar_arrive_expect_tx(bar_wfull + 8 * slot, bytes);
+            bulk_load(W0 + (uint32_t)slot * slot_bytes, src, bytes, bar_wfull + 8 * slot);
           }
+          __syncwarp();
+          if (++slot == P.ts_slots) { slot = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++slot == P.ts_slots) { slot = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
-    if (leader) {
-      int slot = 0; uint32_t phase = 0;
-      int seen = 0, seen_p = 0, epoch = 0;
-      const uint32_t a_tmem = tmem_base + (uint32_t)P.ts_acol;
-      long long c_dep = 0, c_full = 0, c_issue = 0;
-      const long long c_start = CB_CLK();
-      for (int it = 0; it < n_my_tiles; ++it) {
-        for (int l = 0; l < P.n_layers; ++l, ++epoch) {
-          // this layer's A operand (input staging or the previous layer's epilogue) is complete in TMEM and the
-          // accumulator columns have been read out
-          long long c0 = CB_CLK();
-          if constexpr (CG2) {
-            wait_counter_cluster(a_ready, (epoch + 1) * kCEpiWarps, seen);
-            wait_counter_cluster(a_ready_peer, (epoch + 1) * kCEpiWarps, seen_p);
-          } else {
-            wait_counter(a_ready, (epoch + 1) * kCEpiWarps, seen);
-          }
-          tcgen05_fence_after();
-          c_dep += CB_CLK() - c0;
-          const int nkb = P.nkb[l];
-          const int last_nks = P.ksteps[l] - (nkb - 1) * 4;
-          for (int c = 0; c < P.n_chunks[l]; ++c) {
-            const Job job = P.jobs[P.first_job[l] + c];
+    int slot = 0; uint32_t phase = 0;
+    int epoch = 0;
+    int tn = 0;
+    const uint32_t a_tmem = tmem_base + (uint32_t)P.ts_acol;
+    long long c_dep = 0, c_full = 0, c_issue = 0;
+    const long long c_start = CB_CLK();
+    for (int it = 0; it < n_my_tiles; ++it) {
+      for (int l = 0; l < P.n_layers; ++l, ++epoch) {
+        // this layer's A operand (input staging or the previous layer's epilogue) is complete in TMEM and the
+        // accumulator columns have been read out
+        long long c0 = CB_CLK();
+        if (!P.ts_nodep) mbar_spin(bar_aready, (uint32_t)epoch & 1u);
+        tcgen05_fence_after();
+        CB_TRACE(1, 3, l);
+        c_dep += CB_CLK() - c0;
+        const int nkb = P.nkb[l];
+        const int last_nks = P.ksteps[l] - (nkb - 1) * 4;
+        for (int c = 0; c < P.n_chunks[l]; ++c) {
+          const Job job = P.jobs[P.first_job[l] + c];
+          const uint32_t d_tmem = tmem_base + (uint32_t)job.n0;
+          const uint32_t idesc = make_idesc(job.ncols);
+          const uint32_t tile_units = (uint32_t)(job.ncols * 128) >> 4;     // descriptor units per k-block tile
+          for (int kb0 = 0; kb0 < nkb; kb0 += P.ts_kbs) {
             c0 = CB_CLK();
-            mbar_wait(bar_wfull + 8 * slot, phase);
+            mbar_spin(bar_wfull + 8 * slot, phase);
             tcgen05_fence_after();
+            CB_TRACE(1, 4, l * 8 + c);
             const long long c1 = CB_CLK();
             c_full += c1 - c0;
-            const uint32_t d_tmem = tmem_base + (uint32_t)c * kChunkN;
-            const uint32_t idesc = CG2 ? make_idesc_pair(job.ncols) : make_idesc(job.ncols);
-            const uint64_t bdesc0 = make_smem_desc(W0 + (uint32_t)slot * slot_bytes);
+            const int kb1 = min(nkb, kb0 + P.ts_kbs);
             if (elect_one()) {
-              for (int kb = 0; kb < nkb; ++kb) {
-                const int nks = (kb == nkb - 1) ? last_nks : 4;
-                const uint64_t bdesc = bdesc0 + (uint64_t)(kb * (kTileBytes >> 4));
-                const uint32_t a_kb = a_tmem + (uint32_t)(kb * 32);      // 4 k-steps x 8 packed columns
+              uint64_t bd = make_smem_desc(W0 + (uint32_t)slot * slot_bytes);
+              uint32_t at = a_tmem + (uint32_t)(kb0 * 32);
+              for (int kb = kb0; kb < kb1; ++kb) {
+                if (kb < nkb - 1) {
+                  umma_bf16_ts(d_tmem, at, bd, idesc, kb ? 1u : 0u);
+                  umma_bf16_ts(d_tmem, at + 8, bd + 2, idesc, 1u);
+                  umma_bf16_ts(d_tmem, at + 16, bd + 4, idesc, 1u);
+                  umma_bf16_ts(d_tmem, at + 24, bd + 6, idesc, 1u);
+                } else {
+                  umma_bf16_ts(d_tmem, at, bd, idesc, kb ? 1u : 0u);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  if (ks < nks) {
-                    if constexpr (CG2) umma_bf16_ts_pair(d_tmem, a_kb + 8 * ks, bdesc + (uint64_t)(2 * ks), idesc, (kb | ks) ? 1u : 0u);
-                    else umma_bf16_ts(d_tmem, a_kb + 8 * ks, bdesc + (uint64_t)(2 * ks), idesc, (kb | ks) ? 1u : 0u);
-                  }
+                  for (int ks = 1; ks < 4; ++ks)
+                    if (ks < last_nks) umma_bf16_ts(d_tmem, at + 8 * ks, bd + (uint64_t)(2 * ks), idesc, 1u);
                 }
+                at += 32; bd += tile_units;
               }
-              if constexpr (CG2) { umma_commit_pair(bar_wempty + 8 * slot); umma_commit_pair(bar_tfull + 8 * c); }
-              else { umma_commit(bar_wempty + 8 * slot); umma_commit(bar_tfull + 8 * c); }
+              umma_commit(bar_wempty + 8 * slot);
+              if (kb1 == nkb) umma_commit(bar_tfull + 8 * c);
             }
             __syncwarp();
+            CB_TRACE(1, 10, l * 8 + c);
             c_issue += CB_CLK() - c1;
             if (++slot == P.ts_slots) { slot = 0; phase ^= 1; }
           }
         }
       }
-      if (P.dbg && blockIdx.x == 0 && lane == 0) {
-        P.dbg[0] = CB_CLK() - c_start; P.dbg[1] = 0; P.dbg[2] = 0; P.dbg[3] = c_dep; P.dbg[4] = c_full;
-        P.dbg[5] = c_issue; P.dbg[6] = n_my_tiles;
-      }
+    }
+    if (P.dbg && blockIdx.x == 0 && lane == 0) {
+      P.dbg[0] = CB_CLK() - c_start; P.dbg[3] = c_dep; P.dbg[4] = c_full; P.dbg[5] = c_issue; P.dbg[6] = n_my_tiles;
     }
   } else {
     // ============================================================ epilogue warps (2..17)
     const int q = warp & 3;                 // TMEM lane quarter
     const int r = q * 32 + lane;            // row inside the tile
-    const int h = (warp - 2) >> 2;          // this warp owns columns [32 h, 32 h + 32) of every 128-column chunk
+    const int h = (warp - 2) >> 2;          // column class: this warp takes the 32-column groups g with g % C == h, C = EW/4
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t a_tmem = lane_base + (uint32_t)P.ts_acol;
     const int K0 = P.K[0];
     uint32_t tphase = 0;                    // bit c: parity of the next completion of tfull[c]
-    long long c_epi = 0, c_twait = 0, c_e1 = 0, c_e2 = 0, c_e3 = 0; long long ce1 = 0, ce2 = 0;
+    int tn = 0;
+    const int trole = (warp == 2) ? 2 : (warp == 6 ? 3 : 4);
     auto publish = [&]() {
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG2) red_release_inc_cluster(L_a_ready);
-        else red_release_inc(a_ready);
-      }
+      if (lane == 0) mbar_arrive(bar_aready);
     };
     for (int it = 0; it < n_my_tiles; ++it) {
-      const int tile = CG2 ? (my0 + it * stride) * 2 + (int)rank : my0 + it * stride;
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const long long row_g = (long long)tile * kTileM + r;
       const bool row_ok = row_g < P.rows;
       {
-        // layer 0's A operand: [x, 1, 0...] padded to 16 * ksteps, 16 elements (8 packed columns) per unit
+        // layer 0's A operand: [x, 1, 0...] padded to 16 * ksteps, 16 elements (8 packed columns) per unit.
+        // Every MMA that read A for the previous tile has retired: this warp observed all its tfull barriers.
         const float* xr = P.x + row_g * K0;
         for (int u = h; u < P.ksteps[0]; u += kCEpiWarps / 4) {
           uint32_t pk[8];
@@ -791,117 +771,125 @@ chain_ts_kernel(const __grid_constant__ ChainParams P) {
         const int N = P.N[l];
         const int Np = (N + 15) & ~15;
         const int nch = P.n_chunks[l];
-        uint32_t R[kTsMaxChunks][16];
-        long long ce0 = CB_CLK();
+        const int split = nch == 2 ? Np - kTsLast : 0;      // columns [0, split) belong to chunk 0
+        constexpr int C = kCEpiWarps / 4;
+        // packed outputs held in registers until the layer's last MMA has retired: slots 0..2 = chunk-0 groups h, h + C,
+        // h + 2C (converted while the tensor pipe works on the last chunk), slot 3 = the last chunk's group h.
+        // (plain unrolled code, no helper taking the arrays by reference: that pushed them to local memory)
+        uint32_t R[4][16];
+        if (trole < 4) CB_TRACE(trole, 5, l);
 #pragma unroll
-        for (int c = 0; c < kTsMaxChunks; ++c) {
-          if (c < nch) {
-            const long long cw0 = CB_CLK();
-            mbar_wait(bar_tfull + 8 * c, (tphase >> c) & 1u);
-            if (c == nch - 1) { ce0 = CB_CLK(); }
-            c_twait += CB_CLK() - cw0;
-            tphase ^= 1u << c;
+        for (int e = 0; e < 4; ++e) {
+          int nb, w;
+          if (e < 3) {
+            nb = (h + C * e) * 32;
+            w = min(32, split - nb);                 // <= 0 for single-chunk layers (split = 0)
+            if (e == 0 && nch == 2) {
+              mbar_spin(bar_tfull, tphase & 1u);
+              tphase ^= 1u;
+              tcgen05_fence_after();
+            }
+          } else {
+            // last chunk: after its tfull every MMA of the layer has retired
+            const int cl = nch - 1;
+            mbar_spin(bar_tfull + 8 * cl, (tphase >> cl) & 1u);
+            tphase ^= 1u << cl;
             tcgen05_fence_after();
-            const int nb = c * kChunkN + h * 32;
-            const int w = min(32, Np - nb);          // 32, 16 or <= 0
-            if (w > 0) {
-              uint32_t v[32];
-              if (w == 32) tmem_ld32(lane_base + (uint32_t)nb, v); else tmem_ld16(lane_base + (uint32_t)nb, v);
-              tmem_ld_wait();
-              if (c == nch - 1) ce1 = CB_CLK();
-              if (hidden_like) {
-                if (nb + w <= N) {
-                  // group entirely inside the layer's true width (warp-uniform): activation + pack only
+            if (trole < 4) CB_TRACE(trole, 6, l);
+            nb = split + h * 32;
+            w = min(32, Np - nb);
+          }
+          if (w > 0) {
+            uint32_t v[32];
+            if (w == 32) tmem_ld32(lane_base + (uint32_t)nb, v); else tmem_ld16(lane_base + (uint32_t)nb, v);
+            tmem_ld_wait();
+            if (hidden_like) {
+              // four straight-line variants (all conditions warp-uniform): full / half group, inside / across the
+              // layer's true width N -- a per-element "i < w" select compiles to a branch per element
+              if (nb + w <= N) {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    R[c][i] = (2 * i < w) ? pack_bf16(act_fast<ACT>(__uint_as_float(v[2 * i]), P.act_param),
-                                                      act_fast<ACT>(__uint_as_float(v[2 * i + 1]), P.act_param))
-                                          : 0u;
-                } else {
+                for (int i = 0; i < 8; ++i)
+                  R[e][i] = pack_bf16(act_fast<ACT>(__uint_as_float(v[2 * i]), P.act_param),
+                                      act_fast<ACT>(__uint_as_float(v[2 * i + 1]), P.act_param));
+                if (w == 32) {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) {
+                  for (int i = 8; i < 16; ++i)
+                    R[e][i] = pack_bf16(act_fast<ACT>(__uint_as_float(v[2 * i]), P.act_param),
+                                        act_fast<ACT>(__uint_as_float(v[2 * i + 1]), P.act_param));
+                }
+              } else {
+                // column N carries the constant 1.0 that multiplies the folded bias; padding columns are zero
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  if (i < 8 || w == 32) {
                     const int n = nb + 2 * i;
-                    float lo = act_fast<ACT>(__uint_as_float(v[2 * i]), P.act_param);
-                    float hi = act_fast<ACT>(__uint_as_float(v[2 * i + 1]), P.act_param);
-                    // column N carries the constant 1.0 that multiplies the folded bias; padding columns are zero
-                    if (n >= N) lo = (n == N) ? 1.f : 0.f;
-                    if (n + 1 >= N) hi = (n + 1 == N) ? 1.f : 0.f;
-                    R[c][i] = (2 * i < w) ? pack_bf16(lo, hi) : 0u;
+                    const float lo = act_fast<ACT>(__uint_as_float(v[2 * i]), P.act_param);
+                    const float hi = act_fast<ACT>(__uint_as_float(v[2 * i + 1]), P.act_param);
+                    R[e][i] = pack_bf16(n < N ? lo : (n == N ? 1.f : 0.f), n + 1 < N ? hi : (n + 1 == N ? 1.f : 0.f));
                   }
                 }
-              } else if (row_ok) {
-                // final fp32 outputs straight to global memory
-                const bool tanh_out = (P.final_act == CB_ACT_TANH);
-                float* yp = P.y + row_g * N;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const int n = nb + i;
-                  if (i < w && n < N) {
-                    const float z = __uint_as_float(v[i]);
-                    yp[n] = tanh_out ? tanhf(z) : z;
-                  }
+              }
+            } else if (row_ok) {
+              // final fp32 outputs straight to global memory
+              const bool tanh_out = (P.final_act == CB_ACT_TANH);
+              float* yp = P.y + row_g * N;
+#pragma unroll   // (full: a partially unrolled loop would index v[] dynamically and push it to local memory)
+              for (int i = 0; i < 32; ++i) {
+                const int n = nb + i;
+                if (i < w && n < N) {
+                  const float z = __uint_as_float(v[i]);
+                  yp[n] = tanh_out ? tanhf(z) : z;
                 }
               }
             }
           }
         }
+        if (trole < 4) CB_TRACE(trole, 7, l);
         if (hidden_like) {
-          // every tfull of the layer has been observed: its MMAs have retired and no longer read the old A
-          uint32_t ones[8] = {pack_bf16(1.f, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-          const bool ones_unit = ((N & 15) == 0) && h == 0;   // column N opens a fresh 16-element k-step
-          if (!last) {
-            ce2 = CB_CLK();
 #pragma unroll
-            for (int c = 0; c < kTsMaxChunks; ++c) {
-              if (c < nch) {
-                const int nb = c * kChunkN + h * 32;
-                const int w = min(32, Np - nb);
-                if (w == 32) tmem_st16(a_tmem + (uint32_t)(nb >> 1), R[c]);
-                else if (w == 16) tmem_st8(a_tmem + (uint32_t)(nb >> 1), R[c]);
-              }
-            }
-            if (ones_unit) tmem_st8(a_tmem + (uint32_t)(N >> 1), ones);
-            tmem_st_wait();
-            const long long ce3 = CB_CLK();
-            publish();
-            const long long ce4 = CB_CLK();
-            c_epi += ce4 - ce0; c_e1 += ce1 - ce0; c_e2 += ce2 - ce1; c_e3 += ce3 - ce2;
-          } else if (row_ok) {
-            // OUT_BF16_TMA contract (rows, ld) bf16 incl. the ones column: plain 16-byte stores
-            __nv_bfloat16* yr = P.yb + row_g * P.ld_yb;
-#pragma unroll
-            for (int c = 0; c < kTsMaxChunks; ++c) {
-              if (c < nch) {
-                const int nb = c * kChunkN + h * 32;
-                const int w = min(32, Np - nb);
-                if (w > 0) {
-                  uint4* dst = reinterpret_cast<uint4*>(yr + nb);
-                  dst[0] = make_uint4(R[c][0], R[c][1], R[c][2], R[c][3]);
-                  dst[1] = make_uint4(R[c][4], R[c][5], R[c][6], R[c][7]);
-                  if (w == 32) {
-                    dst[2] = make_uint4(R[c][8], R[c][9], R[c][10], R[c][11]);
-                    dst[3] = make_uint4(R[c][12], R[c][13], R[c][14], R[c][15]);
-                  }
+          for (int e = 0; e < 4; ++e) {
+            const int nb = (e < 3) ? (h + C * e) * 32 : split + h * 32;
+            const int w = min(32, ((e < 3) ? split : Np) - nb);
+            if (w > 0) {
+              if (!last) {
+                // the next layer's A operand, in place
+                if (w == 32) tmem_st16(a_tmem + (uint32_t)(nb >> 1), R[e]); else tmem_st8(a_tmem + (uint32_t)(nb >> 1), R[e]);
+              } else if (row_ok) {
+                // OUT_BF16_TMA contract (rows, ld) bf16 incl. the ones column: plain 16-byte stores
+                uint4* dst = reinterpret_cast<uint4*>(P.yb + row_g * P.ld_yb + nb);
+                dst[0] = make_uint4(R[e][0], R[e][1], R[e][2], R[e][3]);
+                dst[1] = make_uint4(R[e][4], R[e][5], R[e][6], R[e][7]);
+                if (w == 32) {
+                  dst[2] = make_uint4(R[e][8], R[e][9], R[e][10], R[e][11]);
+                  dst[3] = make_uint4(R[e][12], R[e][13], R[e][14], R[e][15]);
                 }
               }
             }
-            if (ones_unit) {
-              uint4* dst = reinterpret_cast<uint4*>(yr + N);
+          }
+          if ((N & 15) == 0 && h == 0) {
+            // column N opens a fresh 16-element k-step: [1, 0, ..., 0]
+            uint32_t ones[8] = {pack_bf16(1.f, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (!last) tmem_st8(a_tmem + (uint32_t)(N >> 1), ones);
+            else if (row_ok) {
+              uint4* dst = reinterpret_cast<uint4*>(P.yb + row_g * P.ld_yb + N);
               dst[0] = make_uint4(ones[0], 0u, 0u, 0u);
               dst[1] = make_uint4(0u, 0u, 0u, 0u);
             }
           }
+          if (trole < 4) CB_TRACE(trole, 8, l);
+          if (!last) {
+            publish();
+            if (trole < 4) CB_TRACE(trole, 9, l);
+          }
         }
       }
     }
-    if (P.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) { P.dbg[1] = c_epi; P.dbg[2] = c_twait; P.dbg[8] = c_e1; P.dbg[9] = c_e2; P.dbg[10] = c_e3; }
   }
   tcgen05_fence_before();
-  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    if constexpr (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -1195,7 +1183,7 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
 // the 16-byte chunks XOR-swizzled by (row & 7) (the UMMA SWIZZLE_128B K-major layout).  Column K holds
 // the bias, rows >= N and columns > K are zero.
 __global__ void pack_weights_kernel(const float* __restrict__ W, const float* __restrict__ b, int N, int K,
-                                    int rows_alloc, int Kp, __nv_bfloat16* __restrict__ Wp) {
+                                    int rows_alloc, int Kp, __nv_bfloat16* __restrict__ Wp, int chunk_rows) {
   const long long total = (long long)rows_alloc * Kp;
   const int nkb = Kp / kBlockK;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -1206,8 +1194,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, const float* __
       if (k < K) v = W[(long long)n * K + k];
       else if (k == K && b) v = b[n];
     }
-    const int chunk = n / kChunkN, r = n % kChunkN, kb = k / kBlockK, kk = k % kBlockK;
-    const size_t off = ((size_t)chunk * nkb + kb) * (kKBlockBytes / 2) + (size_t)r * kBlockK +
+    const int chunk = n / chunk_rows, r = n % chunk_rows, kb = k / kBlockK, kk = k % kBlockK;
+    const size_t off = ((size_t)chunk * nkb + kb) * ((size_t)chunk_rows * kBlockK) + (size_t)r * kBlockK +
                        (size_t)(((kk >> 3) ^ (r & 7)) << 3) + (kk & 7);
     Wp[off] = __float2bfloat16(v);
   }
@@ -1264,20 +1252,44 @@ static ChainKernelFn chain_kernel_for(int act, int stages) {
 }
 // CTA-pair (cta_group::2) variant; its ring of half-size stages always has >= 4 entries
 static ChainKernelFn chain_pair_kernel_for(int act) { return chain_kernel_for_act<true, true>(act); }
-template <bool CG2>
 static ChainKernelFn chain_ts_kernel_for(int act) {
   switch (act) {
-    case CB_ACT_RELU: return chain_ts_kernel<CB_ACT_RELU, CG2>;
+    case CB_ACT_RELU: return chain_ts_kernel<CB_ACT_RELU>;
     case CB_ACT_LEAKYRELU:
-    case CB_ACT_PRELU: return chain_ts_kernel<CB_ACT_LEAKYRELU, CG2>;
-    case CB_ACT_TANH: return chain_ts_kernel<CB_ACT_TANH, CG2>;
-    case CB_ACT_GELU: return chain_ts_kernel<CB_ACT_GELU, CG2>;
-    case CB_ACT_ELU: return chain_ts_kernel<CB_ACT_ELU, CG2>;
-    case CB_ACT_SILU: return chain_ts_kernel<CB_ACT_SILU, CG2>;
-    case CB_ACT_SOFTPLUS: return chain_ts_kernel<CB_ACT_SOFTPLUS, CG2>;
-    case CB_ACT_MISH: return chain_ts_kernel<CB_ACT_MISH, CG2>;
-    case CB_ACT_SIGMOID: return chain_ts_kernel<CB_ACT_SIGMOID, CG2>;
-    default: return chain_ts_kernel<CB_ACT_IDENTITY, CG2>;
+    case CB_ACT_PRELU: return chain_ts_kernel<CB_ACT_LEAKYRELU>;
+    case CB_ACT_TANH: return chain_ts_kernel<CB_ACT_TANH>;
+    case CB_ACT_GELU: return chain_ts_kernel<CB_ACT_GELU>;
+    case CB_ACT_ELU: return chain_ts_kernel<CB_ACT_ELU>;
+    case CB_ACT_SILU: return chain_ts_kernel<CB_ACT_SILU>;
+    case CB_ACT_SOFTPLUS: return chain_ts_kernel<CB_ACT_SOFTPLUS>;
+    case CB_ACT_MISH: return chain_ts_kernel<CB_ACT_MISH>;
+    case CB_ACT_SIGMOID: return chain_ts_kernel<CB_ACT_SIGMOID>;
+    default: return chain_ts_kernel<CB_ACT_IDENTITY>;
+  }
+}
+
+// TS kernel: first output column of chunk c of a layer with padded width np (see the kernel's header comment)
+static inline int ts_split(int np) { return np > kTsLast ? np - kTsLast : 0; }
+
+// fp32 (N,K) + bias -> bf16 weight tiles of the TS kernel: chunk 0 = rows [0, split), chunk 1 = rows [split, Np); inside
+// a chunk the k-block tiles (chunk rows x 128 bytes, 16-byte units XOR-swizzled by row & 7) follow each other.
+__global__ void pack_weights_ts_kernel(const float* __restrict__ W, const float* __restrict__ b, int N, int K, int Np,
+                                       int Kp, int split, __nv_bfloat16* __restrict__ Wp) {
+  const long long total = (long long)Np * Kp;
+  const int nkb = Kp / kBlockK;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / Kp), k = (int)(i % Kp);
+    float v = 0.f;
+    if (n < N) {
+      if (k < K) v = W[(long long)n * K + k];
+      else if (k == K && b) v = b[n];
+    }
+    const int n0 = n < split ? 0 : split;
+    const int rows = n < split ? split : Np - split;
+    const int r = n - n0, kb = k / kBlockK, kk = k % kBlockK;
+    const size_t off = ((size_t)n0 * nkb + (size_t)kb * rows + r) * kBlockK + (size_t)(((kk >> 3) ^ (r & 7)) << 3) + (kk & 7);
+    Wp[off] = __float2bfloat16(v);
   }
 }
 
@@ -1307,8 +1319,9 @@ struct cb_tc_chain {
   int Kp[CB_MAX_LAYERS], rows_alloc[CB_MAX_LAYERS];
   int cg2;                      // CTA-pair kernel available for this chain
   int stages_cg2; size_t smem_cg2;
-  int ts, ts_pair;              // TMEM-resident kernel available (single CTA / CTA pairs)
-  int ts_slots[2]; size_t smem_ts[2];   // [0] single CTA, [1] CTA pairs
+  int chunk_rows;               // output columns per job = rows per packed weight tile (128, or W of the TS kernel)
+  int ts;                       // this plan runs the TMEM-resident kernel (its weights are packed for it)
+  int ts_slots; size_t smem_ts;
   int ld_out;                   // OUT_BF16_TMA: columns of the bf16 output (multiple of 64)
   size_t smem_bytes;
   int weights_set;
@@ -1318,7 +1331,7 @@ struct cb_tc_chain {
 // output staging tile must fit in 227 KiB of shared memory.
 struct ChainGeom { int kb_max, stages, n_jobs, stage_ld, out_nkb, ostage_in_x, inplace; size_t smem; bool ok;
                    int stages_cg2; size_t smem_cg2; bool cg2_ok;
-                   bool ts_ok; int ts_acol, ts_slots[2]; size_t smem_ts[2]; };
+                   bool ts_ok; int ts_acol, ts_slot_bytes, ts_kbs, ts_slots, ts_jobs; size_t smem_ts; };
 
 static ChainGeom chain_geometry(const cb_mlp_desc* d, int out_mode) {
   ChainGeom g{};
@@ -1375,29 +1388,35 @@ static ChainGeom chain_geometry(const cb_mlp_desc* d, int out_mode) {
   g.ok = stages >= 2 && g.n_jobs <= kMaxJobs && final_ok;
   g.cg2_ok = g.cg2_ok && g.ok && !g.inplace;
   {
-    // TMEM-resident variant: accumulators (max padded width) + packed activations (max padded K / 2) in 512 columns,
-    // at most kTsMaxChunks chunks per layer, shared memory = weight slots of kb_max tiles
-    int acc = 0, acols = 0, kbm = 1, chunks = 0;
+    // TMEM-resident variant: accumulators of one layer (max padded width <= 384: at most two chunks, the first <= 256
+    // columns) + the packed activations (max padded K / 2 columns) in 512 TMEM columns; shared memory = weight slots
+    int np_max = 16, aw = 8, widest = 16, nkb_max = 1;
+    g.ts_jobs = 0;
     for (int i = 0; i < n; ++i) {
       const int np = round_up(d->dims[i + 1], 16);
       const int ksteps = (d->dims[i] + 1 + kUmmaK - 1) / kUmmaK;
-      acc = np > acc ? np : acc;
-      acols = ksteps * 8 > acols ? ksteps * 8 : acols;
-      kbm = (ksteps + 3) / 4 > kbm ? (ksteps + 3) / 4 : kbm;
-      const int ch = (np + kChunkN - 1) / kChunkN;
-      chunks = ch > chunks ? ch : chunks;
+      const int nkb = (ksteps + 3) / 4;
+      np_max = np > np_max ? np : np_max;
+      aw = ksteps * 8 > aw ? ksteps * 8 : aw;
+      nkb_max = nkb > nkb_max ? nkb : nkb_max;
+      const int split = ts_split(np);
+      const int wd = split > np - split ? split : np - split;
+      widest = wd > widest ? wd : widest;
+      g.ts_jobs += split ? 2 : 1;
     }
-    g.ts_acol = round_up(acc, 32);
-    g.ts_ok = final_ok && g.n_jobs <= kMaxJobs && chunks <= kTsMaxChunks && g.ts_acol + acols <= 512;
-    for (int v = 0; v < 2; ++v) {
-      const long long slot = (long long)g.kb_max * (v ? kKBlockBytes / 2 : kKBlockBytes);   // = the kernel's P.kb_max
-      long long slots = ((long long)kMaxSmem - 1024 - kTsCtrlBytes) / slot;
-      if (slots > kTsMaxSlots) slots = kTsMaxSlots;
-      g.ts_slots[v] = (int)slots;
-      g.smem_ts[v] = (size_t)(1024 + kTsCtrlBytes + (slots > 0 ? slots : 0) * slot);
-    }
-    g.ts_ok = g.ts_ok && g.ts_slots[0] >= 2;
-    (void)kbm;
+    g.ts_acol = round_up(np_max, 32);
+    // slot = as many k-block tiles of the widest chunk as fit in 48 KiB (>= 1), at least 3 slots in flight
+    int kbs = (48 * 1024) / (widest * 128);
+    if (kbs < 1) kbs = 1;
+    if (kbs > nkb_max) kbs = nkb_max;
+    g.ts_kbs = kbs;
+    g.ts_slot_bytes = round_up(kbs * widest * 128, 1024);
+    g.ts_ok = final_ok && np_max <= kTsLast + 256 && g.ts_acol + aw <= 512 && g.ts_jobs <= kMaxJobs;
+    long long slots = ((long long)kMaxSmem - 1024 - kTsCtrlBytes) / g.ts_slot_bytes;
+    if (slots > kTsMaxSlots) slots = kTsMaxSlots;
+    g.ts_slots = (int)slots;
+    g.smem_ts = (size_t)(1024 + kTsCtrlBytes + (slots > 0 ? slots : 0) * g.ts_slot_bytes);
+    g.ts_ok = g.ts_ok && g.ts_slots >= 2;
   }
   return g;
 }
@@ -1439,6 +1458,12 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
   P.stages = g.stages; P.kb_max = g.kb_max;
   P.in_mode = IN_F32; P.out_mode = out_mode; P.out_nkb = g.out_nkb; P.stage_ld = g.stage_ld; P.ostage_in_x = g.ostage_in_x; P.inplace = g.inplace;
   pl->ld_out = g.out_nkb * kBlockK;
+  const char* ts_env = getenv("CB_TC_CHAIN_TS");       // experiment knob: 0 = shared-memory-activation kernels only
+  const char* pair_env = getenv("CB_TC_CHAIN_PAIR");   // opt-in: CTA pairs (cta_group::2), see DESIGN.md 4.1
+  pl->ts = g.ts_ok && !(ts_env && atoi(ts_env) == 0);
+  // the TS kernel has its own chunking and weight packing; a plan uses one kernel family
+  const int chunk = kChunkN;
+  pl->chunk_rows = chunk;
   int nj = 0;
   for (int i = 0; i < desc->n_layers; ++i) {
     const int K = desc->dims[i], N = desc->dims[i + 1];
@@ -1448,16 +1473,23 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
     P.first_job[i] = nj;
     const int Np = round_up(N, 16);
     int chunks = 0;
-    for (int n0 = 0; n0 < Np; n0 += kChunkN, ++chunks) {
-      Job jb;
-      jb.layer = (int16_t)i; jb.n0 = (int16_t)n0;
-      jb.ncols = (int16_t)((Np - n0) < kChunkN ? (Np - n0) : kChunkN);
-      jb.last_chunk = (int16_t)(n0 + kChunkN >= Np);
-      P.jobs[nj++] = jb;
+    if (pl->ts) {
+      const int split = ts_split(Np);
+      if (split) { Job j0; j0.layer = (int16_t)i; j0.n0 = 0; j0.ncols = (int16_t)split; j0.last_chunk = 0; P.jobs[nj++] = j0; ++chunks; }
+      Job j1; j1.layer = (int16_t)i; j1.n0 = (int16_t)split; j1.ncols = (int16_t)(Np - split); j1.last_chunk = 1;
+      P.jobs[nj++] = j1; ++chunks;
+    } else {
+      for (int n0 = 0; n0 < Np; n0 += chunk, ++chunks) {
+        Job jb;
+        jb.layer = (int16_t)i; jb.n0 = (int16_t)n0;
+        jb.ncols = (int16_t)((Np - n0) < chunk ? (Np - n0) : chunk);
+        jb.last_chunk = (int16_t)(n0 + chunk >= Np);
+        P.jobs[nj++] = jb;
+      }
     }
     P.n_chunks[i] = chunks;
     pl->Kp[i] = P.nkb[i] * kBlockK;
-    pl->rows_alloc[i] = round_up(N, kChunkN);
+    pl->rows_alloc[i] = pl->ts ? Np : round_up(N, chunk);
   }
   P.n_jobs = nj;
   {
@@ -1476,22 +1508,20 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
       pl->d_w[i] = pl->d_wall + (size_t)P.w_row0[i] * kBlockK;
       P.w[i] = pl->d_w[i];
     }
-    const char* e = getenv("CB_TC_CHAIN_PAIR");   // opt-in (slower than the single-CTA kernel while the epilogue bounds the chain)
-    pl->cg2 = g.cg2_ok && (e && atoi(e) != 0) && encode_bf16_rows64(&P.tmap_w64, pl->d_wall, rows64, 64) &&
+    const char* e = pair_env;
+    pl->cg2 = !pl->ts && g.cg2_ok && (e && atoi(e) != 0) && encode_bf16_rows64(&P.tmap_w64, pl->d_wall, rows64, 64) &&
               encode_bf16_rows64(&P.tmap_w8, pl->d_wall, rows64, 8);
     pl->stages_cg2 = g.stages_cg2;
     pl->smem_cg2 = g.smem_cg2;
     {
-      const char* t = getenv("CB_TC_CHAIN_TS");      // experiment knob: 0 = shared-memory-activation kernel only
-      pl->ts = g.ts_ok && !(t && atoi(t) == 0);
-      pl->ts_pair = pl->ts && (e && atoi(e) != 0) && encode_bf16_rows64(&P.tmap_w64, pl->d_wall, rows64, 64) &&
-                    encode_bf16_rows64(&P.tmap_w8, pl->d_wall, rows64, 8);
-      P.ts_acol = g.ts_acol;
-      for (int v = 0; v < 2; ++v) { pl->ts_slots[v] = g.ts_slots[v]; pl->smem_ts[v] = g.smem_ts[v]; }
-      if (pl->ts && cudaFuncSetAttribute(chain_ts_kernel_for<false>(desc->act), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)pl->smem_ts[0]) != cudaSuccess) { cudaGetLastError(); pl->ts = 0; pl->ts_pair = 0; }
-      if (pl->ts_pair && cudaFuncSetAttribute(chain_ts_kernel_for<true>(desc->act), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)pl->smem_ts[1]) != cudaSuccess) { cudaGetLastError(); pl->ts_pair = 0; }
+      P.ts_acol = g.ts_acol; P.ts_slot_bytes = g.ts_slot_bytes; P.ts_kbs = g.ts_kbs;
+      pl->ts_slots = g.ts_slots; pl->smem_ts = g.smem_ts;
+      if (pl->ts && cudaFuncSetAttribute(chain_ts_kernel_for(desc->act), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)pl->smem_ts) != cudaSuccess) {
+        cb_tc_chain_destroy(pl);
+        set_error("cannot reserve %zu bytes of shared memory for the TMEM-resident chain kernel", g.smem_ts);
+        return CB_ERR_CUDA;
+      }
     }
     if (pl->cg2 && cudaFuncSetAttribute(chain_pair_kernel_for(desc->act), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)pl->smem_cg2) != cudaSuccess) {
@@ -1524,8 +1554,12 @@ extern "C" int32_t cb_tc_chain_set_weights(cb_tc_chain* plan, const float* const
     const long long total = (long long)plan->rows_alloc[i] * plan->Kp[i];
     int blocks = (int)((total + 255) / 256);
     if (blocks > 1184) blocks = 1184;
-    pack_weights_kernel<<<blocks, 256, 0, st>>>(d_W[i], d_b[i], plan->P.N[i], plan->P.K[i], plan->rows_alloc[i],
-                                               plan->Kp[i], plan->d_w[i]);
+    if (plan->ts)
+      pack_weights_ts_kernel<<<blocks, 256, 0, st>>>(d_W[i], d_b[i], plan->P.N[i], plan->P.K[i], plan->rows_alloc[i],
+                                                    plan->Kp[i], ts_split(plan->rows_alloc[i]), plan->d_w[i]);
+    else
+      pack_weights_kernel<<<blocks, 256, 0, st>>>(d_W[i], d_b[i], plan->P.N[i], plan->P.K[i], plan->rows_alloc[i],
+                                                 plan->Kp[i], plan->d_w[i], plan->chunk_rows);
     CB_LAUNCH_CHECK();
   }
   plan->weights_set = 1;
@@ -1551,29 +1585,13 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
   P.dbg = nullptr;
   const char* dbg_env = getenv("CB_TC_CHAIN_DBG");
   if (dbg_env) { CB_CUDA(cudaMalloc(&P.dbg, 128)); CB_CUDA(cudaMemsetAsync(P.dbg, 0, 128, st)); }
-  const bool ts = plan->ts && !in_map && (plan->out_mode == OUT_F32 || d_yb != nullptr) && !trace_path;
+  const bool ts = plan->ts != 0;   // (its weights are packed for the TS kernel: no other kernel may run this plan)
+  if (ts) CB_CHECK_ARG(!in_map && (plan->out_mode == OUT_F32 || d_yb != nullptr), "TS chain: unsupported launch mode");
   if (ts) {
-    // TMEM-resident activations; CTA pairs need two tiles per cluster
-    const bool pair = plan->ts_pair && P.num_tiles >= 2;
     P.yb = d_yb; P.ld_yb = ld_yb;
-    P.ts_slots = plan->ts_slots[pair ? 1 : 0];
-    if (pair) {
-      const int pairs = (P.num_tiles + 1) / 2;
-      const int clusters = pairs < grid_cap() / 2 ? pairs : grid_cap() / 2;
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3(2 * clusters);
-      cfg.blockDim = dim3(kCThreads);
-      cfg.dynamicSmemBytes = plan->smem_ts[1];
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
-      CB_CUDA(cudaLaunchKernelEx(&cfg, chain_ts_kernel_for<true>(plan->desc.act), P));
-    } else {
-      chain_ts_kernel_for<false>(plan->desc.act)<<<grid, kCThreads, plan->smem_ts[0], st>>>(P);
-    }
+    P.ts_slots = plan->ts_slots;
+    { const char* nd = getenv("CB_TC_TS_NODEP"); P.ts_nodep = nd ? atoi(nd) : 0; }
+    chain_ts_kernel_for(plan->desc.act)<<<grid, kCThreads, plan->smem_ts, st>>>(P);
   } else if (plan->cg2 && !in_map && P.num_tiles >= 2) {
     const int pairs = (P.num_tiles + 1) / 2;
     const int clusters = pairs < grid_cap() / 2 ? pairs : grid_cap() / 2;
@@ -1598,7 +1616,7 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
     CB_CUDA(cudaStreamSynchronize(st));
     CB_CUDA(cudaMemcpy(h, P.dbg, 128, cudaMemcpyDeviceToHost));
     cudaFree(P.dbg);
-    if (ts) fprintf(stderr, "[chain-ts dbg] epilogue warp 2: last tfull -> published %lld (ld %lld, act %lld, st %lld), waiting tfull %lld; ", h[1], h[8], h[9], h[10], h[2]);
+    if (ts) fprintf(stderr, "[chain-ts] ");
     fprintf(stderr, "[chain dbg] %d layers, %d jobs/tile, %d stages: MMA warp of CTA 0: total %lld cycles over %lld tiles: wait input %lld, "
                     "wait TMEM slot %lld, wait previous layer's epilogue %lld, wait weight stage %lld, issue %lld\n",
             P.n_layers, P.n_jobs, P.stages, h[0], h[6], h[1], h[2], h[3], h[4], h[5]);
@@ -1762,7 +1780,7 @@ extern "C" int32_t cb_tc_multionet_set_weights(cb_tc_multionet* m, const float* 
     int blocks = (int)((total + 255) / 256);
     if (blocks > 1184) blocks = 1184;
     pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Ws[i][last], bs[i][last], m->n_out, m->K,
-                                                                 m->rows_alloc, m->Kp, m->d_wlast[i]);
+                                                                 m->rows_alloc, m->Kp, m->d_wlast[i], kChunkN);
     CB_LAUNCH_CHECK();
   }
   m->weights_set = 1;

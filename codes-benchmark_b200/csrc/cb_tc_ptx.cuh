@@ -34,6 +34,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
 }
+// pure polling wait (mbarrier.test_wait never suspends the thread): for the latency-critical hand-offs of the
+// chain kernels, where a parked warp's wake-up would sit on the layer-to-layer critical path
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+#ifdef CB_TC_NO_SPIN
+  mbar_wait(bar, parity);
+#else
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+#endif
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }

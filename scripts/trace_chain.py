@@ -27,7 +27,7 @@ for role in range(4):
         ev.append((int(w >> 24), role, int((w >> 16) & 0xff), int(w & 0xffff)))
 ev.sort()
 t0 = ev[0][0]
-names = {1: "P:empty-ok->load", 2: "M:slot-free job", 3: "M:dep-ok kb", 4: "M:data-ok kb", 5: "E:wait job", 6: "E:acc-ready job", 7: "E:drained job", 8: "E:fenced", 9: "E:synced", 10: "M:issued kb"}
+names = {1: "P:empty-ok->load", 2: "M:slot-free job", 3: "M:dep-ok kb", 4: "M:data-ok kb", 5: "E:wait job", 6: "E:acc-ready job", 7: "E:loaded job", 8: "E:stored", 9: "E:published", 10: "M:issued kb"}
 with open(os.path.join(ROOT, "gpurun_out", "trace.txt"), "w") as f:
     for t, role, tag, arg in ev:
         a = f"j{arg>>3} kb{arg&7}" if tag in (1, 3, 4, 10) else f"j{arg}"
