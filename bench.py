@@ -273,7 +273,7 @@ def run_ours(args):
             "bound": "tensor", "kernel": "don_final_kernel (both last Linears 275->2842 + split scalar product)",
             "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full`, profiles/r1_don_final_pair_ncu_full.md
-            "traffic": 99773440, "traffic_unit": "bytes/launch (ncu r1, CTA-pair kernel: 95.24 MB read + 4.53 MB written)", "peak_source": peak_src,
+            "traffic": 99332352, "traffic_unit": "bytes/launch (ncu r1, CTA-pair kernel: 95.24 MB read + 4.09 MB written, profiles/r1_tc_kernels_ncu_full.md)", "peak_source": peak_src,
             "kernel_ms": {"branch_chain": float(ph[0]), "trunk_chain": float(ph[1]), "final": final_ms},
             "flops_per_launch": FLOP_PER_ROW_FINAL * ROWS_PER_STEP,
             "step_achieved": step_tf, "step_frac": step_tf / peak_tf,
