@@ -63,7 +63,7 @@ constexpr int kCtrlBytes = 16 * kMaxStages + 16 * kSlots + 64;
 enum { IN_F32 = 0, IN_BF16_TMA = 1 };
 enum { OUT_F32 = 0, OUT_BF16_TMA = 1 };
 
-struct Job { int16_t layer, n0, ncols, last_chunk; };
+struct Job { int16_t layer, n0, ncols, last_chunk, sub; };   // sub: which of the two interleaved tiles (dual mode)
 
 struct ChainParams {
   CUtensorMap tmap_in;         // IN_BF16_TMA : (rows, ld_in) bf16
@@ -83,6 +83,8 @@ struct ChainParams {
   float act_param;
   int stages, kb_max, in_mode, out_mode, out_nkb, stage_ld, ostage_in_x;
   int inplace;                 // wide chains: ONE activation buffer, layers fully serialised (see chain_geometry)
+  int dual;                    // two 128-row tiles per iteration, each with its own in-place buffer (X0 / X1); the job list
+                               // alternates the tiles layer by layer so one tile's epilogue hides behind the other's MMAs
   const float* x;
   float* y;
   long long rows;
@@ -176,6 +178,7 @@ __device__ __forceinline__ uint32_t setup_cta(const Ctrl& c, int stages, int war
     mbar_init(c.bar_in, 1);
     *c.epi_done = 0;
     *c.in_staged = 0;
+    c.in_staged_peer[1] = 0; c.in_staged_peer[2] = 0;   // dual mode: jobs issued by the two MMA warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -215,7 +218,7 @@ __device__ __forceinline__ void teardown_cta(uint32_t tmem_base, int warp) {
 // the leader's barrier), their own input staging and their own epilogue (own 128 TMEM lanes, own
 // activation buffers).  The dependency counters of both CTAs live in the leader's shared memory.
 template <int ACT, bool PAIR, bool CG2>
-__global__ void __launch_bounds__(kCThreads, 1)
+__global__ void __launch_bounds__(kCThreads + 32, 1)
 chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -223,7 +226,8 @@ chain_kernel(const __grid_constant__ ChainParams P) {
   uint8_t* gbase = smem_raw + (base - raw);
   const uint32_t xbytes = (uint32_t)P.kb_max * kKBlockBytes;
   constexpr uint32_t kStageBytes = CG2 ? kKBlockBytes / 2 : kKBlockBytes;
-  const uint32_t X0 = base, X1 = P.inplace ? base : base + xbytes, ST0 = base + (P.inplace ? 1 : 2) * xbytes;
+  const bool one_buf = P.inplace && !P.dual;
+  const uint32_t X0 = base, X1 = one_buf ? base : base + xbytes, ST0 = base + (one_buf ? 1 : 2) * xbytes;
   const uint32_t ctrl_addr = ST0 + (uint32_t)P.stages * kStageBytes;
   const Ctrl C = carve_ctrl(ctrl_addr, gbase + (ctrl_addr - base));
   // fp32 output staging (OUT_F32 only): the activation buffer that is idle during the last layer
@@ -256,7 +260,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
     tmem_base = setup_cta(C, P.stages, warp, kCEpiThreads);
   }
   // work units: 128-row tiles, or (CG2) pairs of neighbouring tiles, one per cluster
-  const int units = CG2 ? (P.num_tiles + 1) / 2 : P.num_tiles;
+  const int units = (CG2 || P.dual) ? (P.num_tiles + 1) / 2 : P.num_tiles;
   const int my0 = CG2 ? (int)cluster_id_x() : (int)blockIdx.x;
   const int stride = CG2 ? (int)num_clusters_x() : (int)gridDim.x;
   const int n_my_tiles = (units - my0 + stride - 1) / stride;
@@ -316,14 +320,22 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 2 + kCEpiWarps) {
     // ============================================================ MMA issuer (warp-converged; one elected lane issues;
     //                                                              CG2: the leader CTA issues for both)
-    if (leader) {
+    // dual mode: TWO issuing warps, one per tile (warp 1: tile 0, the extra last warp: tile 1).  Both walk the same
+    // job list and keep the same stage / slot arithmetic but issue only their own tile's jobs: the waits and loop
+    // overhead of one (more than half of a single issuer's time) overlap the other's tcgen05.mma stream.  Each
+    // tcgen05.commit covers the MMAs of the thread that executes it, i.e. exactly the jobs it releases.
+    const int my_sub = (warp == 1) ? 0 : 1;
+    if (leader && (warp == 1 || P.dual)) {
       int stage = 0; uint32_t phase = 0;
       int gj = 0;
       int tn = 0;
       int seen_in = 0, seen_epi = 0, seen_in_p = 0, seen_epi_p = 0;
+      int other_gj = 0, seen_other = 0;                   // dual: jobs the other issuer must have issued first
+      int* issued_mine = C.in_staged_peer + 1 + my_sub;   // (two ints behind the counters of the control block)
+      int* issued_other = C.in_staged_peer + 1 + (my_sub ^ 1);
       const uint64_t bdesc0 = make_smem_desc(ST0);
       constexpr bool pair = PAIR;   // host picks PAIR only when the ring has >= 4 stages (a shallower ring would drain)
       long long c_tempty = 0, c_dep = 0, c_full = 0, c_issue = 0, c_in = 0;
@@ -332,6 +344,15 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         for (int j = 0; j < P.n_jobs; ++j, ++gj) {
           const Job job = P.jobs[j];
           const int l = job.layer;
+          if (P.dual && job.sub != my_sub) {
+            // the other issuer's job: skip it, keeping this warp's view of the weight ring in step; remember it --
+            // this warp must not touch the weight ring before the other one has issued that job (an mbarrier
+            // parity wait is only meaningful within one phase of the barrier's state)
+            for (int kb = 0; kb < P.nkb[l]; ++kb)
+              if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            other_gj = gj + 1;
+            continue;
+          }
           const int slot = gj & (kSlots - 1);
           const uint32_t use = (uint32_t)(gj / kSlots);
           long long c0 = CB_CLK();
@@ -343,7 +364,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           const uint32_t idesc = CG2 ? make_idesc_pair(job.ncols) : make_idesc(job.ncols);
           const int nkb = P.nkb[l];
           const int last_nks = P.ksteps[l] - (nkb - 1) * 4;
-          const uint64_t adesc0 = make_smem_desc((l & 1) ? X1 : X0);
+          const uint64_t adesc0 = make_smem_desc((P.dual ? job.sub : (l & 1)) ? X1 : X0);
           // dependency bookkeeping: k-block kb of this layer's input was written by chunk kb/2 of the
           // previous layer (or by the input staging / input TMA for layer 0)
           int need0 = 0, last_pc = 0;
@@ -358,7 +379,8 @@ chain_kernel(const __grid_constant__ ChainParams P) {
             }
             c_in += CB_CLK() - c0;
           } else {
-            need0 = it * P.n_jobs + P.first_job[l - 1] + 1;
+            // (dual: the jobs of layer l-1 are [tile 0's chunks][tile 1's chunks]; this tile's come first / second)
+            need0 = it * P.n_jobs + P.first_job[l - 1] + 1 + (P.dual ? job.sub * P.n_chunks[l - 1] : 0);
             last_pc = P.n_chunks[l - 1] - 1;
           }
           // two k-blocks (8 MMAs, 512 tensor cycles) per loop iteration: the waits, fences and branch
@@ -383,6 +405,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
             CB_TRACE(1, 3, j * 8 + kb);
             int stage_b = stage + 1; uint32_t phase_b = phase;
             if (stage_b == P.stages) { stage_b = 0; phase_b ^= 1; }
+            if (P.dual) wait_counter(issued_other, other_gj, seen_other);
             mbar_wait(C.bar_full + 8 * stage, phase);
             if (two) mbar_wait(C.bar_full + 8 * stage_b, phase_b);
             CB_TRACE(1, 4, j * 8 + kb);
@@ -434,17 +457,18 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           if (elect_one()) {   // accumulator chunk complete -> epilogue (of both CTAs)
             if constexpr (CG2) umma_commit_pair(C.bar_tfull + 8 * slot);
             else umma_commit(C.bar_tfull + 8 * slot);
+            if (P.dual) asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(issued_mine)), "r"(gj + 1) : "memory");
           }
           __syncwarp();
         }
       }
-      if (P.dbg && blockIdx.x == 0 && lane == 0) {
+      if (P.dbg && blockIdx.x == 0 && lane == 0 && warp == 1) {
         P.dbg[0] = CB_CLK() - c_start; P.dbg[1] = c_in; P.dbg[2] = c_tempty; P.dbg[3] = c_dep; P.dbg[4] = c_full;
         P.dbg[5] = c_issue; P.dbg[6] = n_my_tiles;
       }
     }
-  } else {
-    // ============================================================ epilogue warps (2..9)
+  } else if (warp < 2 + kCEpiWarps) {
+    // ============================================================ epilogue warps (2 .. 2 + EW - 1)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;            // row inside the tile
     const int h = (warp - 2) >> 2;          // this warp takes the 32-column groups with group % (EW/4) == h
@@ -454,22 +478,26 @@ chain_kernel(const __grid_constant__ ChainParams P) {
     int tn = 0;
     const int trole = (warp == 2) ? 2 : (warp == 6 ? 3 : 4);
     for (int it = 0; it < n_my_tiles; ++it) {
-      const int tile = CG2 ? (my0 + it * stride) * 2 + (int)rank : my0 + it * stride;
-      const long long row_g = (long long)tile * kTileM + r;
-      const bool row_ok = row_g < P.rows;
+      const int tile0 = CG2 ? (my0 + it * stride) * 2 + (int)rank : (P.dual ? (my0 + it * stride) * 2 : my0 + it * stride);
       if (CG2 || P.in_mode == IN_F32) {
         // stage the fp32 input rows as the bf16 A operand of layer 0: [x, 1, 0...] padded to 16*ksteps
-        const float* xr = P.x + row_g * K0;
-        const int nch = P.ksteps[0] * 2;    // 16-byte chunks (8 columns each)
-        for (int c = h; c < nch; c += kCEpiWarps / 4) {
-          float f[8];
+        // (dual: both tiles, into X0 and X1)
+        for (int sb = 0; sb < (P.dual ? 2 : 1); ++sb) {
+          const long long row_s = (long long)(tile0 + sb) * kTileM + r;
+          const bool ok_s = row_s < P.rows;
+          const float* xr = P.x + row_s * K0;
+          const uint32_t xs = sb ? X1 : X0;
+          const int nch = P.ksteps[0] * 2;    // 16-byte chunks (8 columns each)
+          for (int c = h; c < nch; c += kCEpiWarps / 4) {
+            float f[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int k = c * 8 + i;
-            f[i] = (k < K0) ? (row_ok ? __ldg(xr + k) : 0.f) : (k == K0 ? 1.f : 0.f);
+            for (int i = 0; i < 8; ++i) {
+              const int k = c * 8 + i;
+              f[i] = (k < K0) ? (ok_s ? __ldg(xr + k) : 0.f) : (k == K0 ? 1.f : 0.f);
+            }
+            st_shared_v4(xs + act_chunk_off(r, c), pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
+                         pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
           }
-          st_shared_v4(X0 + act_chunk_off(r, c), pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
-                       pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
         }
         fence_proxy_async();
         chain_epi_bar_sync();   // counters are running totals: keep the warps within one phase of each other
@@ -481,6 +509,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
       for (int j = 0; j < P.n_jobs; ++j, ++gj) {
         const Job job = P.jobs[j];
         const int l = job.layer;
+        const int tile = tile0 + (P.dual ? job.sub : 0);
         const bool last = (l == P.n_layers - 1);
         const bool to_smem = !last || P.out_mode == OUT_BF16_TMA;
         const int slot = gj & (kSlots - 1);
@@ -488,15 +517,15 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         if (trole < 4) CB_TRACE(trole, 5, j);
         if (P.inplace && to_smem) {
           // the epilogue overwrites the buffer the layer's MMAs read: wait until the LAST chunk of this
-          // layer has been accumulated (tcgen05.commit order => all earlier MMAs have retired too)
-          const int gl = gj + (P.first_job[l] + P.n_chunks[l] - 1 - j);
+          // (tile's) layer has been accumulated (tcgen05.commit order => all earlier MMAs have retired too)
+          const int gl = gj + (P.first_job[l] + (P.dual ? job.sub * P.n_chunks[l] : 0) + P.n_chunks[l] - 1 - j);
           mbar_wait(C.bar_tfull + 8 * (gl & (kSlots - 1)), (uint32_t)(gl / kSlots) & 1);
         }
         mbar_wait(C.bar_tfull + 8 * slot, use & 1);
         if (trole < 4) CB_TRACE(trole, 6, j);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * kChunkN;
-        const uint32_t xo = ((l + 1) & 1) ? X1 : X0;
+        const uint32_t xo = (P.dual ? job.sub : ((l + 1) & 1)) ? X1 : X0;
         const int N = P.N[l];
         for (int c0 = h * 32; c0 < job.ncols; c0 += kCColStride) {
           uint32_t v[32];
@@ -1320,6 +1349,7 @@ struct cb_tc_chain {
   int cg2;                      // CTA-pair kernel available for this chain
   int stages_cg2; size_t smem_cg2;
   int chunk_rows;               // output columns per job = rows per packed weight tile (128, or W of the TS kernel)
+  int dual;                     // shared-memory kernel in dual-tile mode (CB_TC_CHAIN_DUAL=1)
   int ts;                       // this plan runs the TMEM-resident kernel (its weights are packed for it)
   int ts_slots; size_t smem_ts;
   int ld_out;                   // OUT_BF16_TMA: columns of the bf16 output (multiple of 64)
@@ -1331,7 +1361,8 @@ struct cb_tc_chain {
 // output staging tile must fit in 227 KiB of shared memory.
 struct ChainGeom { int kb_max, stages, n_jobs, stage_ld, out_nkb, ostage_in_x, inplace; size_t smem; bool ok;
                    int stages_cg2; size_t smem_cg2; bool cg2_ok;
-                   bool ts_ok; int ts_acol, ts_slot_bytes, ts_kbs, ts_slots, ts_jobs; size_t smem_ts; };
+                   bool ts_ok; int ts_acol, ts_slot_bytes, ts_kbs, ts_slots, ts_jobs; size_t smem_ts;
+                   bool dual_ok; int stages_dual, stage_ld_dual; size_t smem_dual; };
 
 static ChainGeom chain_geometry(const cb_mlp_desc* d, int out_mode) {
   ChainGeom g{};
@@ -1387,6 +1418,28 @@ static ChainGeom chain_geometry(const cb_mlp_desc* d, int out_mode) {
   const bool final_ok = d->final_act == CB_ACT_IDENTITY || d->final_act == CB_ACT_TANH || out_mode == OUT_BF16_TMA;
   g.ok = stages >= 2 && g.n_jobs <= kMaxJobs && final_ok;
   g.cg2_ok = g.cg2_ok && g.ok && !g.inplace;
+  {
+    // dual mode: two tiles per iteration, each with ONE in-place activation buffer; dedicated fp32 staging tile
+    int max_chunks = 0;
+    for (int i = 0; i < n; ++i) {
+      const int chunks = (round_up(d->dims[i + 1], 16) + kChunkN - 1) / kChunkN;
+      const bool hidden_like = (i < n - 1) || out_mode == OUT_BF16_TMA;
+      if (hidden_like && chunks > max_chunks) max_chunks = chunks;
+    }
+    size_t ost = 0;
+    g.stage_ld_dual = 0;
+    if (out_mode == OUT_F32) {
+      const int np = round_up(d->dims[n], 16);
+      g.stage_ld_dual = (np < kChunkN ? np : kChunkN) + 4;
+      ost = (size_t)kTileM * g.stage_ld_dual * sizeof(float);
+    }
+    const long long fx = 1024 + kCtrlBytes + (long long)ost + 2ll * g.kb_max * kKBlockBytes;
+    long long st = ((long long)kMaxSmem - fx) / kKBlockBytes;
+    if (st > kMaxStages) st = kMaxStages;
+    g.stages_dual = (int)st;
+    g.smem_dual = (size_t)(fx + (st > 0 ? st : 0) * kKBlockBytes);
+    g.dual_ok = final_ok && st >= 3 && 2 * g.n_jobs <= kMaxJobs && max_chunks < kSlots;
+  }
   {
     // TMEM-resident variant: accumulators of one layer (max padded width <= 384: at most two chunks, the first <= 256
     // columns) + the packed activations (max padded K / 2 columns) in 512 TMEM columns; shared memory = weight slots
@@ -1460,7 +1513,13 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
   pl->ld_out = g.out_nkb * kBlockK;
   const char* ts_env = getenv("CB_TC_CHAIN_TS");       // experiment knob: 0 = shared-memory-activation kernels only
   const char* pair_env = getenv("CB_TC_CHAIN_PAIR");   // opt-in: CTA pairs (cta_group::2), see DESIGN.md 4.1
-  pl->ts = g.ts_ok && !(ts_env && atoi(ts_env) == 0);
+  const char* dual_env = getenv("CB_TC_CHAIN_DUAL");   // opt-in: two interleaved tiles per CTA in the shared-memory kernel
+  pl->dual = g.dual_ok && g.ok && dual_env && atoi(dual_env) != 0;
+  pl->ts = !pl->dual && g.ts_ok && !(ts_env && atoi(ts_env) == 0);
+  if (pl->dual) {
+    P.dual = 1; P.inplace = 1; P.ostage_in_x = 0; P.stage_ld = g.stage_ld_dual ? g.stage_ld_dual : P.stage_ld;
+    P.stages = g.stages_dual;
+  }
   // the TS kernel has its own chunking and weight packing; a plan uses one kernel family
   const int chunk = kChunkN;
   pl->chunk_rows = chunk;
@@ -1475,16 +1534,20 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
     int chunks = 0;
     if (pl->ts) {
       const int split = ts_split(Np);
-      if (split) { Job j0; j0.layer = (int16_t)i; j0.n0 = 0; j0.ncols = (int16_t)split; j0.last_chunk = 0; P.jobs[nj++] = j0; ++chunks; }
-      Job j1; j1.layer = (int16_t)i; j1.n0 = (int16_t)split; j1.ncols = (int16_t)(Np - split); j1.last_chunk = 1;
+      if (split) { Job j0; j0.layer = (int16_t)i; j0.n0 = 0; j0.ncols = (int16_t)split; j0.last_chunk = 0; j0.sub = 0; P.jobs[nj++] = j0; ++chunks; }
+      Job j1; j1.layer = (int16_t)i; j1.n0 = (int16_t)split; j1.ncols = (int16_t)(Np - split); j1.last_chunk = 1; j1.sub = 0;
       P.jobs[nj++] = j1; ++chunks;
     } else {
-      for (int n0 = 0; n0 < Np; n0 += chunk, ++chunks) {
-        Job jb;
-        jb.layer = (int16_t)i; jb.n0 = (int16_t)n0;
-        jb.ncols = (int16_t)((Np - n0) < chunk ? (Np - n0) : chunk);
-        jb.last_chunk = (int16_t)(n0 + chunk >= Np);
-        P.jobs[nj++] = jb;
+      for (int sub = 0; sub < (pl->dual ? 2 : 1); ++sub) {
+        chunks = 0;
+        for (int n0 = 0; n0 < Np; n0 += chunk, ++chunks) {
+          Job jb;
+          jb.layer = (int16_t)i; jb.n0 = (int16_t)n0;
+          jb.ncols = (int16_t)((Np - n0) < chunk ? (Np - n0) : chunk);
+          jb.last_chunk = (int16_t)(n0 + chunk >= Np);
+          jb.sub = (int16_t)sub;
+          P.jobs[nj++] = jb;
+        }
       }
     }
     P.n_chunks[i] = chunks;
@@ -1509,7 +1572,7 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
       P.w[i] = pl->d_w[i];
     }
     const char* e = pair_env;
-    pl->cg2 = !pl->ts && g.cg2_ok && (e && atoi(e) != 0) && encode_bf16_rows64(&P.tmap_w64, pl->d_wall, rows64, 64) &&
+    pl->cg2 = !pl->ts && !pl->dual && g.cg2_ok && (e && atoi(e) != 0) && encode_bf16_rows64(&P.tmap_w64, pl->d_wall, rows64, 64) &&
               encode_bf16_rows64(&P.tmap_w8, pl->d_wall, rows64, 8);
     pl->stages_cg2 = g.stages_cg2;
     pl->smem_cg2 = g.smem_cg2;
@@ -1529,8 +1592,8 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
       pl->cg2 = 0;
     }
   }
-  pl->smem_bytes = g.smem;
-  if (cudaFuncSetAttribute(chain_kernel_for(desc->act, g.stages), cudaFuncAttributeMaxDynamicSharedMemorySize,
+  pl->smem_bytes = pl->dual ? g.smem_dual : g.smem;
+  if (cudaFuncSetAttribute(chain_kernel_for(desc->act, pl->dual ? g.stages_dual : g.stages), cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)pl->smem_bytes) != cudaSuccess) {
     cb_tc_chain_destroy(pl);
     set_error("cannot reserve %zu bytes of shared memory for the chain kernel: %s", g.smem,
@@ -1575,7 +1638,8 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
   if (in_map) { P.in_mode = IN_BF16_TMA; P.tmap_in = *in_map; }
   if (out_map) P.tmap_out = *out_map;
   P.num_tiles = (int)((rows + kTileM - 1) / kTileM);
-  const int grid = P.num_tiles < grid_cap() ? P.num_tiles : grid_cap();
+  const int units = plan->dual ? (P.num_tiles + 1) / 2 : P.num_tiles;
+  const int grid = units < grid_cap() ? units : grid_cap();
   const char* trace_path = getenv("CB_TC_TRACE");   // debug only: dump a per-role timeline of CTA 0
   P.trace = nullptr;
   if (trace_path) {
@@ -1608,7 +1672,7 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
     cfg.attrs = attr; cfg.numAttrs = 1;
     CB_CUDA(cudaLaunchKernelEx(&cfg, chain_pair_kernel_for(plan->desc.act), P));
   } else {
-    chain_kernel_for(plan->desc.act, P.stages)<<<grid, kCThreads, plan->smem_bytes, st>>>(P);
+    chain_kernel_for(plan->desc.act, P.stages)<<<grid, plan->dual ? kCThreads + 32 : kCThreads, plan->smem_bytes, st>>>(P);
   }
   CB_LAUNCH_CHECK();
   if (dbg_env) {
@@ -1808,7 +1872,7 @@ extern "C" int32_t cb_tc_multionet_forward_timed(cb_tc_multionet* m, const float
   for (int i = 0; i < 4; ++i) CB_CUDA(cudaEventCreate(&ev[i]));
   int32_t e = multionet_forward_impl(m, d_branch_in, d_trunk_in, rows, d_y, d_workspace, workspace_bytes, stream, ev);
   if (e == CB_OK) {
-    if (cudaEventSynchronize(ev[3]) != cudaSuccess) { set_error("event synchronize failed"); e = CB_ERR_CUDA; }
+    if (cudaError_t ce = cudaEventSynchronize(ev[3]); ce != cudaSuccess) { set_error("event synchronize failed: %s", cudaGetErrorString(ce)); e = CB_ERR_CUDA; }
     for (int i = 0; i < 3 && e == CB_OK; ++i) cudaEventElapsedTime(&phase_ms[i], ev[i], ev[i + 1]);
   }
   for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);

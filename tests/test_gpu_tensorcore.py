@@ -81,8 +81,8 @@ PAIR_CHAINS = [
 def test_chain_kernel_variants_are_bitwise_identical(dims, act, fact, rows, monkeypatch):
     """three kernels compute the fused chain: activations in tensor memory (default; up to 256-column MMAs), or in
     shared memory (CB_TC_CHAIN_TS=0; 128-column MMAs) on single CTAs or on CTA pairs (cta_group::2,
-    CB_TC_CHAIN_PAIR=1: two 128-row tiles per cluster, weight k-blocks split between the CTAs).  All accumulate
-    every output over K in the same order."""
+    CB_TC_CHAIN_PAIR=1: two 128-row tiles per cluster, weight k-blocks split between the CTAs) or with two
+    interleaved tiles per CTA (CB_TC_CHAIN_DUAL=1).  All accumulate every output over K in the same order."""
     tc = _tc()
     from codes_b200 import ops
     rng = np.random.default_rng(sum(dims) + rows)
@@ -90,14 +90,15 @@ def test_chain_kernel_variants_are_bitwise_identical(dims, act, fact, rows, monk
     bs = [torch.from_numpy((rng.normal(size=(b,)) * 0.1).astype(np.float32)).to(DEV) for b in dims[1:]]
     x = torch.from_numpy(rng.uniform(-1, 1, size=(rows, dims[0])).astype(np.float32)).to(DEV)
     outs = {}
-    for ts, pair in (("1", "0"), ("0", "0"), ("0", "1")):
-        monkeypatch.setenv("CB_TC_CHAIN_TS", ts)              # both read when the plan is created
+    for ts, pair, dual in (("1", "0", "0"), ("0", "0", "0"), ("0", "1", "0"), ("0", "0", "1")):
+        monkeypatch.setenv("CB_TC_CHAIN_TS", ts)              # all read when the plan is created
         monkeypatch.setenv("CB_TC_CHAIN_PAIR", pair)
-        outs[ts, pair] = tc.chain_forward(ops.ChainSpec(dims, act, fact), x, ws, bs).cpu().numpy()
+        monkeypatch.setenv("CB_TC_CHAIN_DUAL", dual)
+        outs[ts, pair, dual] = tc.chain_forward(ops.ChainSpec(dims, act, fact), x, ws, bs).cpu().numpy()
     ref = O.mlp_chain(x.cpu().numpy(), [w.cpu().numpy() for w in ws], [b.cpu().numpy() for b in bs], act, fact)
-    assert rel_l2(outs["1", "0"], ref) <= 1e-2
+    assert rel_l2(outs["1", "0", "0"], ref) <= 1e-2
     for key, y in outs.items():
-        np.testing.assert_array_equal(y, outs["1", "0"], err_msg=f"variant TS={key[0]} PAIR={key[1]}")
+        np.testing.assert_array_equal(y, outs["1", "0", "0"], err_msg=f"variant TS={key[0]} PAIR={key[1]} DUAL={key[2]}")
 
 
 WIDE_CHAINS = [
