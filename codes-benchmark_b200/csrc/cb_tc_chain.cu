@@ -94,7 +94,6 @@ struct ChainParams {
   int ts_acol;                 // first TMEM column of the packed bf16 activations (the accumulator ring starts at column 0)
   int ts_slot_bytes;           // bytes of one weight slot
   int ts_kbs;                  // k-block tiles per weight slot
-  int ts_nodep;                // EXPERIMENT (CB_TC_TS_NODEP, wrong results): 1 = MMAs do not wait for the epilogue, 2 = no weights wait either
   __nv_bfloat16* yb;           // OUT_BF16_TMA: bf16 output (rows, ld_yb), written with plain vector stores
   int ld_yb;
   unsigned long long* trace;   // debug timeline (CB_TC_TRACE), NULL in production
@@ -706,7 +705,7 @@ chain_ts_kernel(const __grid_constant__ ChainParams P) {
         // this layer's A operand (input staging or the previous layer's epilogue) is complete in TMEM and the
         // accumulator columns have been read out
         long long c0 = CB_CLK();
-        if (!P.ts_nodep) mbar_spin(bar_aready, (uint32_t)epoch & 1u);
+        mbar_spin(bar_aready, (uint32_t)epoch & 1u);
         tcgen05_fence_after();
         CB_TRACE(1, 3, l);
         c_dep += CB_CLK() - c0;
@@ -1654,7 +1653,6 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
   if (ts) {
     P.yb = d_yb; P.ld_yb = ld_yb;
     P.ts_slots = plan->ts_slots;
-    { const char* nd = getenv("CB_TC_TS_NODEP"); P.ts_nodep = nd ? atoi(nd) : 0; }
     chain_ts_kernel_for(plan->desc.act)<<<grid, kCThreads, plan->smem_ts, st>>>(P);
   } else if (plan->cg2 && !in_map && P.num_tiles >= 2) {
     const int pairs = (P.num_tiles + 1) / 2;
@@ -1717,6 +1715,11 @@ struct cb_tc_multionet {
   int pair;                     // CTA-pair (cta_group::2) final kernel
   int stages_pair; size_t smem_pair;
   int weights_set;
+  // the two hidden chains are independent: the trunk chain runs on a side stream, so its CTAs start on the SMs whose
+  // branch-chain CTA had only 3 of the 512 / 148 = 3.46 tiles (and vice versa) instead of waiting for the slowest SM
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  int overlap;
 };
 
 extern "C" void cb_tc_multionet_destroy(cb_tc_multionet* m) {
@@ -1725,6 +1728,9 @@ extern "C" void cb_tc_multionet_destroy(cb_tc_multionet* m) {
     cb_tc_chain_destroy(m->hidden[i]);
     if (m->d_wlast[i]) cudaFree(m->d_wlast[i]);
   }
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
+  if (m->side) cudaStreamDestroy(m->side);
   delete m;
 }
 
@@ -1820,6 +1826,14 @@ extern "C" int32_t cb_tc_multionet_create(const cb_mlp_desc* branch, const cb_ml
     set_error("cannot reserve shared memory for the MultiONet final kernel");
     return CB_ERR_CUDA;
   }
+  {
+    const char* e = getenv("CB_TC_NO_CHAIN_OVERLAP");
+    m->overlap = !(e && atoi(e) != 0) &&
+                 cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    if (!m->overlap) cudaGetLastError();
+  }
   *out = m;
   return CB_OK;
 }
@@ -1901,12 +1915,22 @@ static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_
   CUtensorMap hmap[2];
   for (int i = 0; i < 2; ++i)
     CB_CHECK_ARG(encode_bf16_map(&hmap[i], h[i], rows, m->ld_h), "tensor map of the hidden activations failed");
+  // (the per-kernel timing variant keeps everything on one stream)
+  const bool overlap = m->overlap && !ev && !getenv("CB_TC_CHAIN_DBG") && !getenv("CB_TC_TRACE");
   if (ev) cudaEventRecord(ev[0], st);
+  if (overlap) {
+    CB_CUDA(cudaEventRecord(m->ev_fork, st));
+    CB_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+  }
   if (int32_t e = chain_launch(m->hidden[0], d_branch_in, nullptr, rows, nullptr, &hmap[0], st, h[0], m->ld_h)) return e;
   if (ev) cudaEventRecord(ev[1], st);
-  if (int32_t e = chain_launch(m->hidden[1], d_trunk_in, nullptr, rows, nullptr, &hmap[1], st, h[1], m->ld_h)) return e;
+  if (int32_t e = chain_launch(m->hidden[1], d_trunk_in, nullptr, rows, nullptr, &hmap[1], overlap ? m->side : st, h[1], m->ld_h)) return e;
   if (ev) cudaEventRecord(ev[2], st);
   CB_CUDA(cudaMemsetAsync(d_y, 0, (size_t)rows * m->Q * sizeof(float), st));   // the final kernel accumulates into y
+  if (overlap) {
+    CB_CUDA(cudaEventRecord(m->ev_join, m->side));
+    CB_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
+  }
   FinalParams F = m->F;
   F.tmap_in[0] = hmap[0]; F.tmap_in[1] = hmap[1];
   F.y = d_y; F.rows = rows;
