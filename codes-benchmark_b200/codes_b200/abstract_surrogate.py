@@ -13,6 +13,7 @@ kernels, and the concrete classes' ``forward`` run hand-written sm_100a kernels.
 from __future__ import annotations
 
 import dataclasses
+import contextlib
 import os
 import time
 from abc import ABC, abstractmethod
@@ -134,17 +135,28 @@ class AbstractSurrogateModel(ABC, nn.Module):
         n_batches = len(data_loader)
         preds = targs = None
         done = 0
+        # consecutive batches are independent: on CUDA they alternate between the current stream and a second one, so
+        # the SMs that run out of tiles at the end of one batch's persistent kernels (65 536 rows = 3.46 tiles per
+        # SM) pick up the next batch's kernels instead of idling.  Everything is joined before denormalising.
+        streams = self._predict_streams()
         with torch.inference_mode():
-            for inputs in self._prefetch_to_device(data_loader):
-                p, t = self(inputs)
-                if preds is None:
-                    shape = (p.shape[0] * n_batches, *p.shape[1:])
-                    preds = torch.empty(shape, dtype=p.dtype, device=p.device)
-                    targs = torch.empty(shape, dtype=p.dtype, device=p.device)
-                n = p.shape[0]
-                preds[done:done + n].copy_(p)
-                targs[done:done + n].copy_(t)
-                done += n
+            for i, inputs in enumerate(self._prefetch_to_device(data_loader, streams)):
+                s = streams[i % len(streams)] if streams else None
+                if s is not None and i == 1:
+                    s.wait_stream(streams[0])     # weight caches / output buffers were set up by batch 0
+                with (torch.cuda.stream(s) if s is not None else contextlib.nullcontext()):
+                    p, t = self(inputs)
+                    if preds is None:
+                        shape = (p.shape[0] * n_batches, *p.shape[1:])
+                        preds = torch.empty(shape, dtype=p.dtype, device=p.device)
+                        targs = torch.empty(shape, dtype=p.dtype, device=p.device)
+                    n = p.shape[0]
+                    preds[done:done + n].copy_(p)
+                    targs[done:done + n].copy_(t)
+                    done += n
+            if streams:
+                for s in streams[1:]:
+                    streams[0].wait_stream(s)
             if preds is None:
                 raise RuntimeError("predict() called with an empty data loader")
             preds = self.denormalize(preds[:done], leave_log, leave_norm)
@@ -152,7 +164,21 @@ class AbstractSurrogateModel(ABC, nn.Module):
         return (preds.reshape(-1, self.n_timesteps, self.n_quantities),
                 targs.reshape(-1, self.n_timesteps, self.n_quantities))
 
-    def _prefetch_to_device(self, data_loader):
+    def _predict_streams(self):
+        """[current stream, second stream] for predict()'s batch pipelining on CUDA, else None
+        (CODES_B200_PREDICT_STREAMS=1 keeps everything on the current stream)."""
+        dev = self.device
+        if dev is None or "cuda" not in str(dev) or not torch.cuda.is_available():
+            return None
+        if os.environ.get("CODES_B200_PREDICT_STREAMS", "2") == "1":
+            return None
+        device = torch.device(dev)
+        alt = self.__dict__.get("_alt_stream")
+        if alt is None or alt.device != device:
+            alt = self.__dict__["_alt_stream"] = torch.cuda.Stream(device)
+        return [torch.cuda.current_stream(device), alt]
+
+    def _prefetch_to_device(self, data_loader, streams=None):
         """Yield the loader's batches with their tensors already on ``self.device``.
 
         On CUDA the host->device copy of batch i+1 is issued on a side stream while batch i is
@@ -168,6 +194,13 @@ class AbstractSurrogateModel(ABC, nn.Module):
             copy_stream = self.__dict__["_copy_stream"] = torch.cuda.Stream(device)
         copy_stream.wait_stream(torch.cuda.current_stream(device))
         pending = None
+        count = [0]
+
+        def consumer():
+            """the stream the next yielded batch will be used on"""
+            s = streams[count[0] % len(streams)] if streams else torch.cuda.current_stream(device)
+            count[0] += 1
+            return s
         ds = getattr(data_loader, "dataset", None)
         compact = (getattr(data_loader, "num_workers", 1) == 0 and hasattr(ds, "compact_ok") and ds.compact_ok())
         if compact:
@@ -184,26 +217,29 @@ class AbstractSurrogateModel(ABC, nn.Module):
                     ready = copy_stream.record_event()
                 self.__dict__["_h2d_bytes"] = self.__dict__.get("_h2d_bytes", 0) + nbytes
                 if pending is not None:
-                    yield self._await_batch(*pending, device)
+                    yield self._await_batch(*pending, consumer())
                 pending = (moved, ready)
             if pending is not None:
-                yield self._await_batch(*pending, device)
+                yield self._await_batch(*pending, consumer())
             return
         for batch in data_loader:
+            if any(isinstance(x, Tensor) and x.is_cuda for x in batch):
+                # device-resident loader: the batch was gathered on the current stream, and the consumer may be the
+                # other stream -- chain the "ready" event behind that work
+                copy_stream.wait_stream(torch.cuda.current_stream(device))
             with torch.cuda.stream(copy_stream):
                 moved = tuple(x.to(device, non_blocking=True) if isinstance(x, Tensor) else x for x in batch)
                 ready = copy_stream.record_event()
             self.__dict__["_h2d_bytes"] = self.__dict__.get("_h2d_bytes", 0) + sum(
                 x.numel() * x.element_size() for x in batch if isinstance(x, Tensor))
             if pending is not None:
-                yield self._await_batch(*pending, device)
+                yield self._await_batch(*pending, consumer())
             pending = (moved, ready)
         if pending is not None:
-            yield self._await_batch(*pending, device)
+            yield self._await_batch(*pending, consumer())
 
     @staticmethod
-    def _await_batch(batch, ready, device):
-        cur = torch.cuda.current_stream(device)
+    def _await_batch(batch, ready, cur):
         cur.wait_event(ready)
         for x in batch:
             if isinstance(x, Tensor) and x.is_cuda:

@@ -120,20 +120,26 @@ def multionet_forward(model, branch_input, trunk_input, phase_ms=None):
                   "tc_multionet_set_weights")
             plan.versions = versions
         need = int(lib().cb_tc_multionet_workspace_bytes(plan.handle, rows))
-        if plan.workspace is None or plan.workspace.numel() < need or plan.workspace.device != dev:
-            plan.workspace = torch.empty(need, device=dev, dtype=torch.uint8)
+        # one workspace (the bf16 hidden activations between the chain kernels and the final kernel) per CUDA stream:
+        # predict() pipelines consecutive batches on two streams
+        if plan.workspace is None:
+            plan.workspace = {}
+        skey = torch.cuda.current_stream(dev).cuda_stream
+        ws = plan.workspace.get(skey)
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = plan.workspace[skey] = torch.empty(need, device=dev, dtype=torch.uint8)
         y = torch.empty((rows, q), device=dev, dtype=torch.float32)
         if phase_ms is None:
             check(lib().cb_tc_multionet_forward(plan.handle, C.c_void_p(b2.data_ptr()), C.c_void_p(t2.data_ptr()),
                                                 rows, C.c_void_p(y.data_ptr()),
-                                                C.c_void_p(plan.workspace.data_ptr()), plan.workspace.numel(),
+                                                C.c_void_p(ws.data_ptr()), ws.numel(),
                                                 _stream(dev)), "tc_multionet_forward")
         else:
             ms = (C.c_float * 3)()
             check(lib().cb_tc_multionet_forward_timed(plan.handle, C.c_void_p(b2.data_ptr()),
                                                       C.c_void_p(t2.data_ptr()), rows, C.c_void_p(y.data_ptr()),
-                                                      C.c_void_p(plan.workspace.data_ptr()),
-                                                      plan.workspace.numel(), _stream(dev), ms),
+                                                      C.c_void_p(ws.data_ptr()),
+                                                      ws.numel(), _stream(dev), ms),
                   "tc_multionet_forward_timed")
             phase_ms[:] = [float(v) for v in ms]
     return y
@@ -182,12 +188,16 @@ def gemm_chain_forward(spec, x, weights, biases):
         y = torch.empty((rows, spec.dims[-1]), device=dev, dtype=torch.float32)
         if rows:
             nbytes = int(L.cb_tc_train_infer_bytes(plan.handle, rows))
-            if plan.scratch is None or plan.scratch.numel() < nbytes:
-                plan.scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            # activations between the per-layer GEMMs: one buffer per CUDA stream (predict() pipelines on two)
+            infer = plan.__dict__.setdefault("infer_scratch", {})
+            skey = torch.cuda.current_stream(dev).cuda_stream
+            sc = infer.get(skey)
+            if sc is None or sc.numel() < nbytes:
+                sc = infer[skey] = torch.empty(nbytes, device=dev, dtype=torch.uint8)
             wl, bl = _f32(weights), _f32(biases)
             check(L.cb_tc_train_infer(plan.handle, ptr_array(wl), ptr_array(bl), C.c_void_p(x2.data_ptr()), rows,
-                                      C.c_void_p(y.data_ptr()), C.c_void_p(plan.scratch.data_ptr()),
-                                      plan.scratch.numel(), _stream(dev)), "tc_train_infer")
+                                      C.c_void_p(y.data_ptr()), C.c_void_p(sc.data_ptr()),
+                                      sc.numel(), _stream(dev)), "tc_train_infer")
     return y.reshape(*x.shape[:-1], spec.dims[-1])
 
 
