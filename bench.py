@@ -67,10 +67,12 @@ class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.samples, self.proc = index, [], None
+    def __init__(self, index: int, enabled: bool = True):
+        self.index, self.samples, self.proc, self.enabled = index, [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:     # one sampler per job (rank 0): eight concurrent nvidia-smi loops stall each other
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
@@ -246,7 +248,7 @@ def run_ours(args):
         barrier()
         _lib.reset_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clocks:
+        with ClockSampler(local_rank, enabled=(rank == 0)) as clocks:
             e0.record()
             streams[1].wait_stream(cur)
             for i in range(args.steps):
@@ -297,9 +299,9 @@ def run_ours(args):
     de = synthetic_x0(n_e2e, seed=4321 + rank)
     _, _, val_loader = model.prepare_data(de, None, de, np.linspace(0, 1, T), ROWS_PER_STEP, shuffle=False)
     steps_per_pass = len(val_loader)
-    passes = max(12, int(round(args.steps / steps_per_pass)))
-    for _ in range(8):                        # warm-up passes: the side-stream allocator pool of the H2D prefetch
-                                              # needs a few passes to stop growing (pass_ms_rank0 shows the steady state)
+    passes = max(40, int(round(args.steps / steps_per_pass)))
+    for _ in range(16):                       # warm-up passes: the per-stream allocator pools (copy stream + the two
+                                              # compute streams) need a few passes to stop growing (pass_ms_rank0)
         p, t = model.predict(val_loader)
         model._l1(p, t)
     barrier()

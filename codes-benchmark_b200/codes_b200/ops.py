@@ -355,12 +355,14 @@ def gather_rows(src: Tensor, idx: Tensor) -> Tensor:
 
 
 # --------------------------------------------------------------------------- denormalise
-def denormalize(x: Tensor, mode: int, dmin: Tensor | None, dmax: Tensor | None, pow10: bool) -> Tensor:
+def denormalize(x: Tensor, mode: int, dmin: Tensor | None, dmax: Tensor | None, pow10: bool,
+                inplace: bool = False) -> Tensor:
+    """``inplace``: overwrite ``x`` (element-wise kernel; used by predict() on its own fp32 result buffers)."""
     _require_cuda(x)
     x2 = _f32c(x)
     q = x2.shape[-1]
     rows = x2.numel() // q
-    out = torch.empty_like(x2)
+    out = x2 if (inplace and x2 is x) else torch.empty_like(x2)
     with torch.cuda.device(x2.device):
         check(lib().cb_denormalize(_p(x2), rows, q, mode, _p(dmin), _p(dmax), int(pow10), _p(out), _stream(x2)),
               "denormalize")
