@@ -165,3 +165,39 @@ def test_predict_with_deduplicated_h2d_equals_full_batches(n, T, bs, monkeypatch
     p2, t2 = m.predict(val)
     assert torch.equal(p1, p2) and torch.equal(t1, t2)
     np.testing.assert_array_equal(t1.cpu().numpy(), d)
+
+
+@pytest.mark.parametrize("name", ["FullyConnected", "MultiONet", "LatentNeuralODE", "LatentPoly"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_predict_on_two_streams_equals_one_stream(name, precision, monkeypatch):
+    """predict() pipelines consecutive batches on two CUDA streams (per-stream workspaces, events from the copy
+    stream): the result must be bit-identical to the single-stream loop, repeatedly (a cross-stream race would show
+    up as a run-to-run difference), for host loaders and for the device-resident shuffled training loader."""
+    import codes_b200 as cb
+    Q, T, n = 5, 24, 300
+    rng = np.random.default_rng(11)
+    d = rng.uniform(-1, 1, size=(n, T, Q)).astype(np.float32)
+    cb.set_precision(precision)
+    try:
+        torch.manual_seed(5)
+        m = getattr(cb, name)("cuda:0", Q, T, 0, None, {})
+        m.normalisation = {"mode": "minmax", "min": [-10.0] * Q, "max": [0.0] * Q, "log10_transform": True}
+        bs = 1024 if name in ("FullyConnected", "MultiONet") else 37
+        tr, _, val = m.prepare_data(d, None, d, np.linspace(0, 1, T), bs, shuffle=True)
+        monkeypatch.setenv("CODES_B200_PREDICT_STREAMS", "1")
+        ref_p, ref_t = m.predict(val)
+        monkeypatch.delenv("CODES_B200_PREDICT_STREAMS")
+        for _ in range(4):
+            p, t = m.predict(val)
+            assert torch.equal(p, ref_p) and torch.equal(t, ref_t)
+        # shuffled (device-resident) loader: same permutation -> same rows
+        torch.manual_seed(9)
+        monkeypatch.setenv("CODES_B200_PREDICT_STREAMS", "1")
+        sp, st_ = m.predict(tr)
+        monkeypatch.delenv("CODES_B200_PREDICT_STREAMS")
+        for _ in range(3):
+            torch.manual_seed(9)
+            p, t = m.predict(tr)
+            assert torch.equal(p, sp) and torch.equal(t, st_)
+    finally:
+        cb.set_precision("fp32")
