@@ -295,12 +295,12 @@ def run_ours(args):
 
     # ---- e2e leg (ALL ranks, weak scaling): public API with HOST batches (pinned), H2D + metric D2H inside
     # the timed region; aggregate = trajectories of all ranks / slowest rank's wall time between barriers
-    n_e2e = 16384
+    n_e2e = 65536                              # N_test = 65536 trajectories = 100 loader batches per pass
     de = synthetic_x0(n_e2e, seed=4321 + rank)
     _, _, val_loader = model.prepare_data(de, None, de, np.linspace(0, 1, T), ROWS_PER_STEP, shuffle=False)
     steps_per_pass = len(val_loader)
-    passes = max(40, int(round(args.steps / steps_per_pass)))
-    for _ in range(16):                       # warm-up passes: the per-stream allocator pools (copy stream + the two
+    passes = max(10, int(round(args.steps / steps_per_pass)))
+    for _ in range(5):                        # warm-up passes: the per-stream allocator pools (copy stream + the two
                                               # compute streams) need a few passes to stop growing (pass_ms_rank0)
         p, t = model.predict(val_loader)
         model._l1(p, t)

@@ -349,8 +349,11 @@ def gather_rows(src: Tensor, idx: Tensor) -> Tensor:
     out = torch.empty((idx.shape[0], *src.shape[1:]), device=src.device, dtype=torch.float32)
     if idx.shape[0] == 0 or row == 0:
         return out
-    with torch.cuda.device(src.device):
+    if torch.cuda.current_device() == src.device.index:      # (per-batch host path of predict(): skip the context manager)
         check(lib().cb_gather_rows(_p(src), _p(idx), idx.shape[0], n_src, row, _p(out), _stream(src)), "gather_rows")
+    else:
+        with torch.cuda.device(src.device):
+            check(lib().cb_gather_rows(_p(src), _p(idx), idx.shape[0], n_src, row, _p(out), _stream(src)), "gather_rows")
     return out
 
 

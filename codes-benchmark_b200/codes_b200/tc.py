@@ -4,6 +4,7 @@ device and refreshed when the fp32 parameters change (optimizer step, load_state
 from __future__ import annotations
 
 import ctypes as C
+import contextlib
 import weakref
 
 import torch
@@ -91,55 +92,67 @@ _MULTIONET_PLANS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 def multionet_forward(model, branch_input, trunk_input, phase_ms=None):
     """Fused MultiONet forward; returns None when the shape is not supported by the fused kernels.
-    ``phase_ms``: optional list that receives the per-kernel durations (bench.py roofline leg)."""
+    ``phase_ms``: optional list that receives the per-kernel durations (bench.py roofline leg).
+    This is the per-batch host path of predict(): everything that does not change between calls (chain specs,
+    parameter lists, the "supported" verdict) is cached on the plan."""
     if not available():
-        return None
-    bspec, tspec = model.branch_net.chain(), model.trunk_net.chain()
-    q = model.N
-    if not lib().cb_tc_multionet_supported(C.byref(bspec.desc), C.byref(tspec.desc), q):
         return None
     dev = branch_input.device
     per_model = _MULTIONET_PLANS.setdefault(model, {})
+    bspec, tspec = model.branch_net.chain(), model.trunk_net.chain()
     key = (dev.index, id(bspec), id(tspec))
     plan = per_model.get(key)
+    q = model.N
     if plan is None:
+        if not lib().cb_tc_multionet_supported(C.byref(bspec.desc), C.byref(tspec.desc), q):
+            return None
         per_model.clear()
         plan = per_model[key] = _MultiONetPlan(bspec, tspec, q, dev)
-    bw, bb = ops.sequential_params(model.branch_net.network)
-    tw, tb = ops.sequential_params(model.trunk_net.network)
-    b2 = branch_input.reshape(-1, bspec.dims[0]).float().contiguous()
-    t2 = trunk_input.reshape(-1, tspec.dims[0]).float().contiguous()
+        # the nn.Linear members are looked up once; their .weight / .bias are read on every call (a caller may
+        # replace parameter objects)
+        plan.linears = ([m for m in model.branch_net.network if isinstance(m, torch.nn.Linear)],
+                        [m for m in model.trunk_net.network if isinstance(m, torch.nn.Linear)])
+    bw = [m.weight for m in plan.linears[0]]; bb = [m.bias for m in plan.linears[0]]
+    tw = [m.weight for m in plan.linears[1]]; tb = [m.bias for m in plan.linears[1]]
+    b2 = branch_input.reshape(-1, bspec.dims[0])
+    t2 = trunk_input.reshape(-1, tspec.dims[0])
+    if b2.dtype != torch.float32 or not b2.is_contiguous():
+        b2 = b2.float().contiguous()
+    if t2.dtype != torch.float32 or not t2.is_contiguous():
+        t2 = t2.float().contiguous()
     rows = b2.shape[0]
     if t2.shape[0] != rows:
         raise ValueError("branch and trunk inputs must have the same number of rows")
-    with torch.cuda.device(dev):
+    ctx = torch.cuda.device(dev) if torch.cuda.current_device() != dev.index else contextlib.nullcontext()
+    with ctx:
+        stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+        stream = C.c_void_p(stream_ptr)
         versions = _versions(bw) + _versions(bb) + _versions(tw) + _versions(tb)
         if versions != plan.versions:
             check(lib().cb_tc_multionet_set_weights(plan.handle, ptr_array(_f32(bw)), ptr_array(_f32(bb)),
-                                                    ptr_array(_f32(tw)), ptr_array(_f32(tb)), _stream(dev)),
+                                                    ptr_array(_f32(tw)), ptr_array(_f32(tb)), stream),
                   "tc_multionet_set_weights")
             plan.versions = versions
-        need = int(lib().cb_tc_multionet_workspace_bytes(plan.handle, rows))
         # one workspace (the bf16 hidden activations between the chain kernels and the final kernel) per CUDA stream:
         # predict() pipelines consecutive batches on two streams
         if plan.workspace is None:
             plan.workspace = {}
-        skey = torch.cuda.current_stream(dev).cuda_stream
-        ws = plan.workspace.get(skey)
-        if ws is None or ws.numel() < need or ws.device != dev:
-            ws = plan.workspace[skey] = torch.empty(need, device=dev, dtype=torch.uint8)
+        ws = plan.workspace.get(stream_ptr)
+        if ws is None or ws.device != dev or ws.numel() < int(lib().cb_tc_multionet_workspace_bytes(plan.handle, rows)):
+            need = int(lib().cb_tc_multionet_workspace_bytes(plan.handle, rows))
+            ws = plan.workspace[stream_ptr] = torch.empty(need, device=dev, dtype=torch.uint8)
         y = torch.empty((rows, q), device=dev, dtype=torch.float32)
         if phase_ms is None:
             check(lib().cb_tc_multionet_forward(plan.handle, C.c_void_p(b2.data_ptr()), C.c_void_p(t2.data_ptr()),
                                                 rows, C.c_void_p(y.data_ptr()),
                                                 C.c_void_p(ws.data_ptr()), ws.numel(),
-                                                _stream(dev)), "tc_multionet_forward")
+                                                stream), "tc_multionet_forward")
         else:
             ms = (C.c_float * 3)()
             check(lib().cb_tc_multionet_forward_timed(plan.handle, C.c_void_p(b2.data_ptr()),
                                                       C.c_void_p(t2.data_ptr()), rows, C.c_void_p(y.data_ptr()),
                                                       C.c_void_p(ws.data_ptr()),
-                                                      ws.numel(), _stream(dev), ms),
+                                                      ws.numel(), stream, ms),
                   "tc_multionet_forward_timed")
             phase_ms[:] = [float(v) for v in ms]
     return y
