@@ -310,6 +310,7 @@ def run_ours(args):
     pass_ms = []
     for _ in range(passes):
         tp = time.perf_counter()
+        p = t = None                          # (as in validate(): the previous pass's results are dead before the next call)
         p, t = model.predict(val_loader)
         metric = model._l1(p, t)              # .item(): 4-byte D2H, like validate()
         pass_ms.append(round((time.perf_counter() - tp) * 1e3, 2))
