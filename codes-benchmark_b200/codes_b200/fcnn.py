@@ -100,7 +100,10 @@ class FullyConnected(AbstractSurrogateModel):
         inputs = torch.from_numpy(np.concatenate(cols, axis=2).reshape(n * T, -1)).float()
         targets = torch.from_numpy(np.ascontiguousarray(data).reshape(n * T, Q)).float()
         pin = pin_memory and self.device is not None and "cuda" in self.device and torch.cuda.is_available()
-        ds = RowBatchIterable([inputs, targets], batch_size, shuffle, pin=pin, device=self.device)
+        # rows r = n*T + t: the x0 and params columns depend on n only, the time column on t only
+        blocks = [("repeat", Q), ("tile", 1)] + ([("repeat", dataset_params.shape[1])] if dataset_params is not None else [])
+        ds = RowBatchIterable([inputs, targets], batch_size, shuffle, pin=pin, device=self.device,
+                              row_structure=[blocks, "full"], period=T)
         return make_loader(ds, self.device, num_workers)
 
     def prepare_data(self, dataset_train, dataset_test, dataset_val, timesteps, batch_size, shuffle=True,

@@ -48,10 +48,23 @@ class RowBatchIterable(IterableDataset):
         self.row_structure = list(row_structure) if row_structure is not None else None
         self._compact = None
         if self.row_structure is not None and self.period > 0 and not shuffle:
-            self._compact = [None if t is None else
-                             _maybe_pin(t[::self.period].contiguous(), pin) if kind == "repeat" else
-                             _maybe_pin(t[:self.period].contiguous(), pin) if kind == "tile" else None
-                             for t, kind in zip(self.tensors, self.row_structure)]
+            def compact(t, kind):
+                if t is None:
+                    return None
+                if kind == "repeat":
+                    return _maybe_pin(t[::self.period].contiguous(), pin)
+                if kind == "tile":
+                    return _maybe_pin(t[:self.period].contiguous(), pin)
+                if isinstance(kind, (list, tuple)):
+                    # column blocks of one tensor, e.g. FullyConnected's [x0 | t | params] rows:
+                    # (("repeat", Q), ("tile", 1), ("repeat", P)) -> one compact tensor per block
+                    parts, c0 = [], 0
+                    for sub, width in kind:
+                        parts.append(compact(t[:, c0:c0 + width], sub))
+                        c0 += width
+                    return parts
+                return None
+            self._compact = [compact(t, kind) for t, kind in zip(self.tensors, self.row_structure)]
         self._tile_dev = {}
         self._idx_cache = {}
         self.constants = [_maybe_pin(c, pin) for c in constants]
@@ -103,20 +116,27 @@ class RowBatchIterable(IterableDataset):
             n_lo, n_hi = start // T, (stop - 1) // T + 1
             nbytes = 0
             batch = []
+            def expand(comp, kind, tag):
+                """device rows [start, stop) of a "repeat" / "tile" tensor from its compact form"""
+                nonlocal nbytes
+                if kind == "repeat":
+                    src = comp[n_lo:n_hi]
+                    nbytes += src.numel() * src.element_size()
+                    return ops.gather_rows(src.to(device, non_blocking=True), idx[0])
+                res = self._tile_dev.get((device, tag))
+                if res is None:
+                    nbytes += comp.numel() * comp.element_size()
+                    res = self._tile_dev[(device, tag)] = comp.to(device, non_blocking=True)
+                return ops.gather_rows(res, idx[1])
+
             for i, (t, kind) in enumerate(zip(self.tensors, self.row_structure)):
                 if t is None:
                     batch.append(None)
-                elif kind == "repeat":
-                    src = self._compact[i][n_lo:n_hi]
-                    nbytes += src.numel() * src.element_size()
-                    batch.append(ops.gather_rows(src.to(device, non_blocking=True), idx[0]))
-                elif kind == "tile":
-                    res = self._tile_dev.get((device, i))
-                    if res is None:
-                        src = self._compact[i]
-                        nbytes += src.numel() * src.element_size()
-                        res = self._tile_dev[(device, i)] = src.to(device, non_blocking=True)
-                    batch.append(ops.gather_rows(res, idx[1]))
+                elif kind in ("repeat", "tile"):
+                    batch.append(expand(self._compact[i], kind, i))
+                elif isinstance(kind, (list, tuple)):
+                    cols = [expand(comp, sub, (i, j)) for j, (comp, (sub, _)) in enumerate(zip(self._compact[i], kind))]
+                    batch.append(torch.cat(cols, dim=1))
                 else:
                     src = t[start:stop]
                     nbytes += src.numel() * src.element_size()

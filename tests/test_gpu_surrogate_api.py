@@ -201,3 +201,31 @@ def test_predict_on_two_streams_equals_one_stream(name, precision, monkeypatch):
             assert torch.equal(p, sp) and torch.equal(t, st_)
     finally:
         cb.set_precision("fp32")
+
+
+@pytest.mark.parametrize("n,T,bs,P", [(37, 20, 256, 0), (50, 100, 1000, 3), (8, 7, 1024, 2)])
+def test_fcnn_predict_with_deduplicated_h2d_equals_full_batches(n, T, bs, P, monkeypatch):
+    """FullyConnected rows are [x0 | t | params]: predict() copies the x0 / params blocks once per trajectory and the
+    time column once, and rebuilds the loader's rows on the device (gather + concat) -- bit-identical results."""
+    import codes_b200 as cb
+    Q = 6
+    rng = np.random.default_rng(n + T + P)
+    d = rng.uniform(-1, 1, size=(n, T, Q)).astype(np.float32)
+    prm = rng.uniform(-1, 1, size=(n, P)).astype(np.float32) if P else None
+    torch.manual_seed(3)
+    m = cb.FullyConnected("cuda:0", Q, T, P, None, {"hidden_size": 48, "num_hidden_layers": 2})
+    _, _, val = m.prepare_data(d, None, d, np.linspace(0, 1, T), bs, shuffle=False, dataset_train_params=prm,
+                               dataset_val_params=prm)
+    assert val.dataset.compact_ok()
+    h0 = m.__dict__.get("_h2d_bytes", 0)
+    p1, t1 = m.predict(val)
+    moved = m.__dict__["_h2d_bytes"] - h0
+    assert moved < 4 * (n * T * Q + (n + len(val)) * (Q + P) + T) + 64
+    # the rebuilt rows equal the loader's own batches
+    first = next(iter(val))
+    dev_first, _ = next(val.dataset.compact_batches(torch.device("cuda:0")))
+    assert torch.equal(dev_first[0].cpu(), first[0]) and torch.equal(dev_first[1].cpu(), first[1])
+    monkeypatch.setenv("CODES_B200_DEDUP_H2D", "0")
+    p2, t2 = m.predict(val)
+    assert torch.equal(p1, p2) and torch.equal(t1, t2)
+    np.testing.assert_array_equal(t1.cpu().numpy(), d)

@@ -222,3 +222,34 @@ def test_activation_mapping_and_unsupported_modules():
     assert "model.coefficient_net.2.0.weight" in m.state_dict() and m.model.encoder.mlp[0].in_features == 3
     m = cb.LatentNeuralODE("cpu", 3, 5, 2, None, {})
     assert "model.ode.base_ode.mlp.0.weight" in m.state_dict() and m.model.ode.base_ode.mlp[0].in_features == 5 + 2
+
+
+@pytest.mark.parametrize("model_name,P", [("MultiONet", 0), ("MultiONet", 2), ("FullyConnected", 0), ("FullyConnected", 3)])
+@pytest.mark.parametrize("n,T,bs", [(37, 20, 256), (9, 7, 1024), (50, 10, 64)])
+def test_compact_batches_rebuild_the_loader_batches(model_name, P, n, T, bs, monkeypatch):
+    """The de-duplicated H2D path of predict() (loaders.compact_batches) must rebuild exactly the batches the loader
+    yields.  Host logic only: cb_gather_rows is replaced by torch indexing so this runs without a GPU."""
+    import codes_b200 as cb
+    from codes_b200 import ops
+    monkeypatch.setattr(ops, "gather_rows", lambda src, idx: src[idx])
+    Q = 4
+    rng = np.random.default_rng(n * T + P)
+    d = rng.uniform(-1, 1, size=(n, T, Q)).astype(np.float32)
+    prm = rng.uniform(-1, 1, size=(n, P)).astype(np.float32) if P else None
+    cfg = ({"hidden_size": 8, "branch_hidden_layers": 1, "trunk_hidden_layers": 1, "output_factor": 2}
+           if model_name == "MultiONet" else {"hidden_size": 8, "num_hidden_layers": 1})
+    m = getattr(cb, model_name)("cpu", Q, T, P, None, cfg)
+    _, _, val = m.prepare_data(d, None, d, np.linspace(0, 1, T), bs, shuffle=False, dataset_train_params=prm,
+                               dataset_val_params=prm)
+    ds = val.dataset
+    assert ds._compact is not None
+    full = list(iter(val))
+    rebuilt = list(ds.compact_batches(torch.device("cpu")))
+    assert len(full) == len(rebuilt) == len(val)
+    total = 0
+    for fb, (rb, nbytes) in zip(full, rebuilt):
+        assert len(fb) == len(rb)
+        for a, b in zip(fb, rb):
+            assert torch.equal(a, b)
+        total += nbytes
+    assert total < sum(t.numel() * 4 for t in ds.tensors if t is not None)   # fewer bytes than the full batches
