@@ -117,8 +117,8 @@ class ClockSampler:
 
 def synthetic_x0(n_traj: int, seed: int) -> np.ndarray:
     """Initial states of the SURVEY 8d generator (only x0 and the time grid feed MultiONet)."""
-    import oracle as O
-    return O.synthetic_dataset(n_traj, T, Q, seed=seed)
+    from codes_b200.synthetic import synthetic_dataset
+    return synthetic_dataset(n_traj, T, Q, seed=seed)
 
 
 def build_model(device: str):

@@ -33,8 +33,8 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 from torch import nn  # noqa: E402
 
-import codes_b200 as cb  # noqa: E402
-import oracle as O  # noqa: E402
+import codes_b200 as cb
+from codes_b200.synthetic import synthetic_dataset  # noqa: E402
 from codes_b200 import train as T  # noqa: E402
 
 PRIMORDIAL = {  # datasets/primordial/surrogates_config.py (active blocks)
@@ -83,8 +83,8 @@ def main():
     }
     tasks = [t for s in surrogates for t in T.create_task_list_for_surrogate(config, s)]
     mine = T.assign_tasks(tasks, world, args.n_train, Tn)[rank]
-    train = O.synthetic_dataset(args.n_train, Tn, Q, 1234)
-    test = O.synthetic_dataset(args.n_test, Tn, Q, 4321)
+    train = synthetic_dataset(args.n_train, Tn, Q, 1234)
+    test = synthetic_dataset(args.n_test, Tn, Q, 4321)
     ts = np.linspace(0, 1, Tn)
     info = {"mode": "minmax", "min": [-10.0] * Q, "max": [0.0] * Q, "log10_transform": True}
     os.environ.setdefault("TQDM_DISABLE", "1")

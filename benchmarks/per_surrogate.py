@@ -27,8 +27,8 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from torch import nn  # noqa: E402
 
-import codes_b200 as cb  # noqa: E402
-import oracle as O  # noqa: E402
+import codes_b200 as cb
+from codes_b200.synthetic import synthetic_dataset  # noqa: E402
 
 DEV = "cuda:0"
 
@@ -68,7 +68,7 @@ def bench_flat(name, cls, cfg, Q, T, n_train, n_test, batch_rows, dims_list, ext
     torch.manual_seed(42)
     m = cls(DEV, Q, T, 0, None, cfg)
     m.normalisation = {"mode": "minmax", "min": [-10.0] * Q, "max": [0.0] * Q, "log10_transform": True}
-    dtr, dte = O.synthetic_dataset(n_train, T, Q, 1234), O.synthetic_dataset(n_test, T, Q, 4321)
+    dtr, dte = synthetic_dataset(n_train, T, Q, 1234), synthetic_dataset(n_test, T, Q, 4321)
     tr, _, va = m.prepare_data(dtr, None, dte, np.linspace(0, 1, T), batch_rows, shuffle=True)
     flop_row = 2 * sum(mac(d) for d in dims_list) + extra_flop_row
     res = {"config": name, "params": sum(p.numel() for p in m.parameters()), "flop_per_row_fwd": flop_row}
@@ -107,7 +107,7 @@ def bench_latent(name, cls, cfg, Q, T, n_train, n_test, batch, flop_traj):
     torch.manual_seed(42)
     m = cls(DEV, Q, T, 0, None, cfg)
     m.normalisation = {"mode": "minmax", "min": [-10.0] * Q, "max": [0.0] * Q, "log10_transform": True}
-    dtr, dte = O.synthetic_dataset(n_train, T, Q, 1234), O.synthetic_dataset(n_test, T, Q, 4321)
+    dtr, dte = synthetic_dataset(n_train, T, Q, 1234), synthetic_dataset(n_test, T, Q, 4321)
     tr, _, _ = m.prepare_data(dtr, None, None, np.linspace(0, 1, T), batch, shuffle=True)
     _, _, va = m.prepare_data(dtr, None, dte, np.linspace(0, 1, T), 8192, shuffle=False)   # whole-set style inference
     res = {"config": name, "params": sum(p.numel() for p in m.parameters())}
@@ -144,7 +144,7 @@ def cpu_reference_flat(kind, m, Q, T, rows):
     from oracle import torch_port as TP
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     torch.set_num_threads(os.cpu_count() or 1)
-    d = O.synthetic_dataset((rows + T - 1) // T, T, Q, 7)
+    d = synthetic_dataset((rows + T - 1) // T, T, Q, 7)
     x0 = torch.from_numpy(np.repeat(d[:, 0, :], T, axis=0)[:rows].copy())
     tt = torch.from_numpy(np.tile(np.linspace(0, 1, T, dtype=np.float32), (rows + T - 1) // T).reshape(-1, 1)[:rows].copy())
     if kind == "fcnn":

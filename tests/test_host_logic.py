@@ -282,3 +282,12 @@ def test_bench_gpu_arm_fails_loudly_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                          timeout=300, cwd=root)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_product_synthetic_generator_equals_the_oracles():
+    """bench.py's GPU arm draws its inputs from codes_b200.synthetic (the product never imports oracle/); the tests'
+    copy in the oracle must stay the same generator."""
+    import oracle as O
+    from codes_b200.synthetic import synthetic_dataset
+    for n, T, Q, seed in [(7, 11, 5, 3), (64, 100, 29, 1234)]:
+        np.testing.assert_array_equal(synthetic_dataset(n, T, Q, seed), O.synthetic_dataset(n, T, Q, seed))
