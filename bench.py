@@ -62,6 +62,15 @@ def peaks():
         return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel: str) -> dict:
+    """dram bytes per launch of `kernel` from the tracked ncu summary profiles/roofline_traffic.json ({} if absent)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+            return json.load(fh).get(kernel, {})
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     """nvidia-smi SM clock + throttle reasons sampled during the timed region."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -133,9 +142,10 @@ def build_model(device: str):
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_forward_rate(rows: int, repeats: int, threads: int, seed: int = 1234):
-    """The reference's CPU algorithm for this forward (torch CPU ops, oracle/torch_port.py) on
-    `threads` host threads with the GPU model's weights; returns (traj/s, seconds)."""
+def port_forward_rate(rows: int, repeats: int, threads: int, seed: int = 1234):
+    """Fallback when oracle/_ref is absent: the reference's CPU algorithm for this forward restated with
+    torch CPU ops (oracle/torch_port.py, pinned to the live-reference goldens by tests/test_oracle_golden.py)
+    on `threads` host threads with the GPU model's weights; returns (traj/s, seconds)."""
     import torch
     from oracle import torch_port as TP
     m = build_model("cpu")
@@ -164,22 +174,94 @@ def cpu_forward_rate(rows: int, repeats: int, threads: int, seed: int = 1234):
     return repeats * rows / T / dt, dt
 
 
+def reference_surrogates():
+    """The reference's own ``codes.surrogates`` (vendored, unmodified, in the git-ignored oracle/_ref; see
+    oracle/make_ref.py), or None when it is not there."""
+    try:
+        from oracle import ref_shim
+        return ref_shim.import_reference()
+    except Exception:
+        return None
+
+
+def build_reference_model(S, device: str, state_dict=None):
+    """The reference's MultiONet class with the cfg2 configuration; seed 42 gives the same initial weights as
+    ``build_model`` (bit-identical initialisation, tests/test_gpu_parity.py), or ``state_dict`` is loaded."""
+    import torch
+    from torch import nn
+    torch.manual_seed(42)
+    m = S.MultiONet(device, Q, T, 0, None, dict(CFG, activation=nn.LeakyReLU()))
+    if state_dict is not None:
+        m.load_state_dict(state_dict, strict=True)
+    m.normalisation = dict(NORM)
+    m.eval()
+    return m
+
+
+def reference_predict_rate(S, device: str, n_batches: int, passes: int, warm_passes: int, threads: int | None,
+                           state_dict=None, seed: int = 1234):
+    """Time the UNMODIFIED reference: ``MultiONet.predict(val_loader)`` (abstract_surrogate.py:217-275) on a loader of
+    ``n_batches`` full 65 536-row batches built by its own ``prepare_data``.  Returns (traj/s, seconds, n_traj)."""
+    import torch
+    if threads:
+        torch.set_num_threads(threads)
+    m = build_reference_model(S, device, state_dict)
+    n_traj = n_batches * ROWS_PER_STEP // T       # the last batch is 36..99 rows short of 65 536
+    d = synthetic_x0(n_traj, seed)
+    _, _, val = m.prepare_data(d, None, d, np.linspace(0, 1, T), ROWS_PER_STEP, shuffle=False)
+    assert len(val) == n_batches, (len(val), n_batches)
+    cuda = "cuda" in device
+
+    def one():
+        p, t = m.predict(val)
+        if cuda:
+            torch.cuda.synchronize()
+        return p
+
+    for _ in range(warm_passes):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        one()
+    dt = time.perf_counter() - t0
+    return passes * n_traj / dt, dt, n_traj
+
+
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    rows = 8192   # bounded sample of one 65536-row step
-    for _ in range(max(0, min(args.warmup, 2))):
-        cpu_forward_rate(rows, 1, cores)
-    rate, dt = cpu_forward_rate(rows, args.steps, cores)
+    S = reference_surrogates()
+    if S is not None:
+        # one step = one full 65 536-row loader batch (same config as the GPU arm); `steps` batches per predict pass,
+        # at most 50 per pass (host memory), so exactly `steps` batches are timed
+        chunks = [50] * (args.steps // 50) + ([args.steps % 50] if args.steps % 50 else [])
+        if args.warmup > 0:
+            reference_predict_rate(S, "cpu", min(args.warmup, 2), 1, 0, cores)
+        traj = dt = 0.0
+        for nb in chunks:
+            r, d_, n_ = reference_predict_rate(S, "cpu", nb, 1, 0, cores)
+            traj += n_
+            dt += d_
+        rate = traj / dt
+        kind, rows = "reference", ROWS_PER_STEP
+        sample = (f"{args.steps} steps x {rows} rows: the unmodified reference MultiONet.predict(val_loader) "
+                  f"(oracle/_ref, torch {'.'.join(__import__('torch').__version__.split('.')[:2])} CPU fp32, {cores} threads)")
+    else:
+        rows = 8192   # bounded sample of one 65536-row step
+        for _ in range(max(0, min(args.warmup, 2))):
+            port_forward_rate(rows, 1, cores)
+        rate, dt = port_forward_rate(rows, args.steps, cores)
+        kind = "port"
+        sample = f"{args.steps} steps x {rows} rows of the cfg2 forward, torch-CPU fp32 port of the reference forward (oracle/_ref absent)"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "trajectories/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{rows} rows per step ({rows / T:.2f} trajectories)"},
-        "cpu_baseline": {"value": rate, "unit": "trajectories/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {rows} rows of the cfg2 forward, torch-CPU fp32 port of the reference forward"},
+        "config": {"workload": WORKLOAD, "rows_per_step": rows, "trajectories_per_step": rows / T},
+        "cpu_baseline": {"value": rate, "unit": "trajectories/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -283,11 +365,13 @@ def run_ours(args):
         final_ms = float(ph[2])
         achieved = FLOP_PER_ROW_FINAL * ROWS_PER_STEP / (final_ms * 1e-3) / 1e12
         step_tf = FLOP_PER_ROW * ROWS_PER_STEP / (elapsed_ms / args.steps * 1e-3) / 1e12
+        traffic = ncu_traffic("don_final_kernel")
         roofline = {
             "bound": "tensor", "kernel": "don_final_kernel (both last Linears 275->2842 + split scalar product)",
             "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full`, profiles/r1_don_final_pair_ncu_full.md
-            "traffic": 99332352, "traffic_unit": "bytes/launch (ncu r1, CTA-pair kernel: 95.24 MB read + 4.09 MB written, profiles/r1_tc_kernels_ncu_full.md)", "peak_source": peak_src,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the tracked ncu summary
+            "traffic": traffic.get("traffic"), "traffic_unit": "bytes/launch; " + traffic.get("source", "no ncu capture"),
+            "peak_source": peak_src,
             "kernel_ms": {"branch_chain": float(ph[0]), "trunk_chain": float(ph[1]), "final": final_ms},
             "flops_per_launch": FLOP_PER_ROW_FINAL * ROWS_PER_STEP,
             "step_achieved": step_tf, "step_frac": step_tf / peak_tf,
@@ -377,13 +461,32 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         sample_rows = ROWS_PER_STEP
         reps = 40
+        reference_gpu = None
         if args.no_cpu_baseline:
             cpu_baseline = None
         else:
-            rate, dt = cpu_forward_rate(sample_rows, reps, cores)
-            cpu_baseline = {"value": rate, "unit": "trajectories/s", "cores": cores, "kind": "port",
-                            "sample": f"{reps} x {sample_rows} rows ({dt:.1f} s) of the same cfg2 forward, "
-                                      "torch-CPU fp32 port of the reference forward"}
+            S = reference_surrogates()
+            if S is not None:
+                nb = 20                                     # bounded sample: 20 full loader batches (~10-30 s of host work)
+                rate, dt, n_ = reference_predict_rate(S, "cpu", nb, 1, 0, cores)
+                cpu_baseline = {"value": rate, "unit": "trajectories/s", "cores": cores, "kind": "reference",
+                                "sample": f"{nb} x {ROWS_PER_STEP} rows ({dt:.1f} s): the unmodified reference "
+                                          "MultiONet.predict(val_loader) from oracle/_ref, torch CPU fp32"}
+                # second comparator: the same unmodified reference class in PyTorch eager on this GPU,
+                # fp32 cuBLAS, host loader batches, synchronised wall clock around predict()
+                try:
+                    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+                    rate_g, dt_g, n_g = reference_predict_rate(S, device, 25, 2, 1, None, state_dict=sd)
+                    reference_gpu = {"value": rate_g, "unit": "trajectories/s",
+                                     "what": "unmodified reference MultiONet.predict(val_loader) on this GPU (PyTorch eager, "
+                                             f"fp32 cuBLAS, TF32 off), 2 passes x {n_g} trajectories in {dt_g:.2f} s"}
+                except Exception as exc:   # the comparator must never take the bench line down
+                    reference_gpu = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+            else:
+                rate, dt = port_forward_rate(sample_rows, reps, cores)
+                cpu_baseline = {"value": rate, "unit": "trajectories/s", "cores": cores, "kind": "port",
+                                "sample": f"{reps} x {sample_rows} rows ({dt:.1f} s) of the same cfg2 forward, "
+                                          "torch-CPU fp32 port of the reference forward (oracle/_ref absent)"}
         line = {
             "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -393,7 +496,7 @@ def run_ours(args):
                        "streams": "batches alternate between two CUDA streams (as in predict()); timed from the first launch to the join of both",
                        "precision": "bf16 operands, fp32 accumulate (tcgen05)", "parallelism": f"trajectory-sharded x{world}"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "train": train,
+            "cpu_baseline": cpu_baseline, "reference_gpu": reference_gpu, "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
