@@ -63,6 +63,8 @@ _SIGNATURES = {
     "cb_mlp_workspace_floats": (_I64, [C.POINTER(MlpDesc), _I64, _I32]),
     "cb_mlp_forward_f32": (_I32, [C.POINTER(MlpDesc), _PP, _PP, _P, _I64, _P, _P, _P, _I64, _P]),
     "cb_mlp_backward_f32": (_I32, [C.POINTER(MlpDesc), _PP, _P, _P, _P, _I64, _PP, _PP, _P, _P, _I64, _P]),
+    "cb_mlp_forward_f32_p": (_I32, [C.POINTER(MlpDesc), _PP, _PP, _P, _I64, _P, _P, _P, _I64, _P, _P]),
+    "cb_mlp_backward_f32_p": (_I32, [C.POINTER(MlpDesc), _PP, _P, _P, _P, _I64, _PP, _PP, _P, _P, _I64, _P, _P, _P]),
     "cb_deeponet_combine_fwd": (_I32, [_P, _P, _I64, _I32, _I32, _P, _P]),
     "cb_deeponet_combine_bwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "cb_poly_eval_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _P]),

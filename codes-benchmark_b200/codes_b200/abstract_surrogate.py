@@ -38,6 +38,34 @@ except Exception:  # pragma: no cover - optuna absent in the build image
         """Stand-in for optuna.TrialPruned when optuna is not installed."""
 
 
+class _RefCompatUnpickler(__import__("pickle").Unpickler):
+    """Unpickler for reference-written ``.pth`` files (abstract_surrogate.py:277-363 pickles ``self.__dict__``, which
+    holds the reference's config dataclass instance, e.g. ``codes.surrogates.FCNN.fcnn_config.FCNNBaseConfig``).
+    When the reference package is importable its classes are used; otherwise a ``codes.*`` class is mapped to the
+    class of the same name in ``codes_b200.configs`` (same fields)."""
+
+    def find_class(self, module, name):
+        if module == "codes" or module.startswith("codes."):
+            try:
+                return super().find_class(module, name)
+            except (ImportError, AttributeError):
+                from . import configs
+                if hasattr(configs, name):
+                    return getattr(configs, name)
+                raise
+        return super().find_class(module, name)
+
+
+def _compat_pickle_module():
+    import pickle
+    import types
+    mod = types.ModuleType("codes_b200_compat_pickle")
+    mod.__dict__.update({k: getattr(pickle, k) for k in dir(pickle) if not k.startswith("__")})
+    mod.Unpickler = _RefCompatUnpickler
+    mod.load = lambda f, **kw: _RefCompatUnpickler(f, **kw).load()
+    return mod
+
+
 class _NoOpScheduler:
     """scheduler.step() placeholder for schedule-free optimizers (abstract_surrogate.py:762-770)."""
 
@@ -130,9 +158,15 @@ class AbstractSurrogateModel(ABC, nn.Module):
         Semantics of abstract_surrogate.py:217-275 (buffers sized first_batch_rows x
         len(loader), loader order preserved, denormalise, reshape).  The reference's extra
         "dummy" forward on the first batch is not repeated: the first
-        batch's output is kept and used to size the buffers.
+        batch's output is kept and used to size the buffers.  Its side effect on the CPU RNG is: the dummy
+        ``next(iter(loader))`` of a SHUFFLING loader draws one ``torch.randperm(N)`` (abstract_surrogate.py:233-239),
+        so the same draw is consumed here and every later training batch order matches the reference for a seed
+        (``validate`` calls predict on the shuffled train loader; tests/golden/predict_rng.npz).
         """
         n_batches = len(data_loader)
+        ds = getattr(data_loader, "dataset", None)
+        if getattr(ds, "shuffle", False) and hasattr(ds, "N"):
+            torch.randperm(ds.N)
         preds = targs = None
         done = 0
         # consecutive batches are independent: on CUDA they alternate between the current stream and a second one, so
@@ -351,7 +385,7 @@ class AbstractSurrogateModel(ABC, nn.Module):
         """Inverse of ``save`` (abstract_surrogate.py:365-406); also loads reference-written .pth files."""
         root = os.path.join(os.getcwd(), "trained") if model_dir is None else model_dir
         path = os.path.join(root, training_id, surr_name, f"{model_identifier}.pth")
-        blob = torch.load(path, map_location=self.device, weights_only=False)
+        blob = torch.load(path, map_location=self.device, weights_only=False, pickle_module=_compat_pickle_module())
         self.load_state_dict(blob["state_dict"])
         for key, val in blob["attributes"].items():
             if key != "device":

@@ -42,10 +42,12 @@ class FullyConnectedNet(nn.Module):
 
 
 def _cached_chain(owner, seq, activation, final_act):
-    """ChainSpec of an nn.Sequential, rebuilt when the PReLU slope changes."""
-    name, param = ops.activation_spec(activation)
+    """ChainSpec of an nn.Sequential.  For a learnable PReLU slope the host snapshot inside the spec (used by the
+    tensor-core inference plans only) is refreshed -- one device read -- when the slope has changed and no gradient
+    is being recorded, i.e. once per validate()/predict() after training steps, never inside a training step."""
     spec = owner.__dict__.get("_chain")
-    if spec is None or spec.act_param != param:
+    if spec is None or spec.slope is not ops.prelu_slope(activation) or \
+            (spec.slope_stale() and not torch.is_grad_enabled()):
         spec = ops.sequential_spec(seq, activation, final_act)
         owner.__dict__["_chain"] = spec
     return spec

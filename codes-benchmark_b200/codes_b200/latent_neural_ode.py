@@ -132,7 +132,8 @@ class ModelWrapper(LatentLossMixin, nn.Module):
         b = list(b[:-1]) + [torch.cat([b[-1], b[-1].new_zeros(P)], dim=0)]
         spec0 = base.chain()
         if self._aug_chain is None or self._aug_chain.act_param != spec0.act_param:
-            self._aug_chain = ops.ChainSpec(spec0.dims[:-1] + [L + P], spec0.act, "identity", spec0.act_param)
+            self._aug_chain = ops.ChainSpec(spec0.dims[:-1] + [L + P], spec0.act, "identity", spec0.act_param,
+                                            slope=spec0.slope)
         y0 = torch.cat([z0, params.to(z0.device, z0.dtype)], dim=1)
         traj = ops.lnode_integrate(self, self._aug_chain, w, b, y0, t_range, reg_factor=base.reg_factor, n_err=L)
         return traj[:, :, :L].contiguous()

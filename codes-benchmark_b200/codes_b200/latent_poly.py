@@ -77,10 +77,11 @@ class PolynomialModelWrapper(LatentLossMixin, nn.Module):
     def coefficients(self, params: Tensor) -> Tensor:
         """(B, P) -> (B, L, deg): the coefficient network as one fused dense chain."""
         w, b = self._coef_params()
-        name, ap = ops.activation_spec(self.config.activation)
-        if self._coef_chain is None or self._coef_chain.act_param != ap:
+        spec = self._coef_chain
+        if spec is None or (spec.slope_stale() and not torch.is_grad_enabled()):
+            name, ap = ops.activation_spec(self.config.activation)
             dims = [w[0].shape[1]] + [x.shape[0] for x in w]
-            self._coef_chain = ops.ChainSpec(dims, name, "identity", ap)
+            self._coef_chain = ops.ChainSpec(dims, name, "identity", ap, slope=ops.prelu_slope(self.config.activation))
         out = ops.run_chain(self._coef_chain, params, w, b, tc_train=False)
         return out.reshape(params.shape[0], self.config.latent_features, self.config.degree)
 

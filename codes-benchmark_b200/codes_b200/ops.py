@@ -44,8 +44,15 @@ def activation_spec(module: nn.Module) -> tuple[str, float]:
     elif name == "prelu":
         if module.weight.numel() != 1:
             raise NotImplementedError("PReLU with per-channel slopes is not supported")
+        # host copy of the learnable slope (one device read): only the tensor-core INFERENCE plans consume it; the
+        # fp32 kernels -- and therefore every training step -- read the slope from device memory (ChainSpec.slope)
         param = float(module.weight.detach().reshape(-1)[0])
     return name, param
+
+
+def prelu_slope(module: nn.Module):
+    """The shared learnable slope parameter of an nn.PReLU() activation, else None."""
+    return module.weight if type(module) is nn.PReLU else None
 
 
 def _stream(t: Tensor) -> C.c_void_p:
@@ -73,10 +80,19 @@ def _p(t) -> C.c_void_p:
 class ChainSpec:
     """Static description of an nn.Sequential of Linear(+activation) layers."""
 
-    def __init__(self, dims: Sequence[int], act: str, final_act: str = "identity", act_param: float = 0.01):
+    def __init__(self, dims: Sequence[int], act: str, final_act: str = "identity", act_param: float = 0.01,
+                 slope: Tensor | None = None):
         self.dims = [int(d) for d in dims]
         self.act, self.final_act, self.act_param = act, final_act, float(act_param)
         self.desc = make_desc(self.dims, act, final_act, act_param)
+        # learnable PReLU slope (1-element nn.Parameter shared by all layers): the fp32 kernels read it from device
+        # memory and return its gradient; ``act_param`` is the host snapshot taken at ``slope_key`` for the
+        # tensor-core inference plans
+        self.slope = slope
+        self.slope_key = None if slope is None else (slope.data_ptr(), slope._version)
+
+    def slope_stale(self) -> bool:
+        return self.slope is not None and self.slope_key != (self.slope.data_ptr(), self.slope._version)
 
     @property
     def n_layers(self) -> int:
@@ -88,10 +104,11 @@ class ChainSpec:
 
 class _MlpChainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, spec: ChainSpec, x: Tensor, *params: Tensor):
+    def forward(ctx, spec: ChainSpec, x: Tensor, slope, *params: Tensor):
         n = spec.n_layers
         weights, biases = params[:n], params[n:]
         _require_cuda(x, *weights)
+        sl = None if slope is None else _f32c(slope.detach()).reshape(-1)
         x2 = _f32c(x.reshape(-1, spec.dims[0]))
         rows = x2.shape[0]
         y = torch.empty((rows, spec.dims[-1]), device=x.device, dtype=torch.float32)
@@ -109,12 +126,13 @@ class _MlpChainFn(torch.autograd.Function):
             ws = torch.empty(max(wsf, 1), device=x.device, dtype=torch.float32)
             wl = [_f32c(w) for w in weights]
             bl = [None if b is None else _f32c(b) for b in biases]
-            check(L.cb_mlp_forward_f32(C.byref(spec.desc), ptr_array(wl), ptr_array(bl), _p(x2), rows,
-                                       _p(y), _p(saved), _p(ws), wsf, _stream(x)), "mlp_forward_f32")
+            check(L.cb_mlp_forward_f32_p(C.byref(spec.desc), ptr_array(wl), ptr_array(bl), _p(x2), rows,
+                                         _p(y), _p(saved), _p(ws), wsf, _p(sl), _stream(x)), "mlp_forward_f32")
         if need_grad:
             ctx.spec = spec
             ctx.x_shape = x.shape
-            ctx.save_for_backward(x2, saved, *wl)
+            ctx.has_slope = sl is not None
+            ctx.save_for_backward(x2, saved, *(() if sl is None else (sl,)), *wl)
             ctx.has_bias = [b is not None for b in biases]
         return y.reshape(*x.shape[:-1], spec.dims[-1])
 
@@ -123,28 +141,33 @@ class _MlpChainFn(torch.autograd.Function):
         spec = ctx.spec
         n = spec.n_layers
         x2, saved, *wl = ctx.saved_tensors
+        sl = wl.pop(0) if ctx.has_slope else None
         rows = x2.shape[0]
         dy2 = _f32c(dy.reshape(rows, spec.dims[-1]))
         dev = x2.device
         L = lib()
         need_dx = ctx.needs_input_grad[1]
+        dsl = None
         with torch.cuda.device(dev):
+            if sl is not None and ctx.needs_input_grad[2]:
+                dsl = torch.empty(1, device=dev, dtype=torch.float32)
             dW = [torch.empty_like(w) for w in wl]
             db = [torch.empty(w.shape[0], device=dev, dtype=torch.float32) if hb else None
                   for w, hb in zip(wl, ctx.has_bias)]
             dx = torch.empty_like(x2) if need_dx else None
             wsf = int(L.cb_mlp_workspace_floats(C.byref(spec.desc), rows, 1))
             ws = torch.empty(wsf, device=dev, dtype=torch.float32)
-            check(L.cb_mlp_backward_f32(C.byref(spec.desc), ptr_array(wl), _p(x2), _p(saved), _p(dy2), rows,
-                                        ptr_array(dW), ptr_array(db), _p(dx), _p(ws), wsf, _stream(x2)),
-                  "mlp_backward_f32")
+            check(L.cb_mlp_backward_f32_p(C.byref(spec.desc), ptr_array(wl), _p(x2), _p(saved), _p(dy2), rows,
+                                          ptr_array(dW), ptr_array(db), _p(dx), _p(ws), wsf, _p(sl), _p(dsl),
+                                          _stream(x2)), "mlp_backward_f32")
         gx = dx.reshape(ctx.x_shape) if need_dx else None
-        return (None, gx, *dW, *db)
+        return (None, gx, dsl, *dW, *db)
 
 
 def mlp_chain(spec: ChainSpec, x: Tensor, weights: Sequence[Tensor], biases: Sequence[Tensor | None]) -> Tensor:
-    """y = chain(x) on the last dimension of ``x`` (fp32 FFMA path, exact mode)."""
-    return _MlpChainFn.apply(spec, x, *weights, *biases)
+    """y = chain(x) on the last dimension of ``x`` (fp32 FFMA path, exact mode).  A PReLU chain reads its learnable
+    slope from ``spec.slope`` (device memory) and returns the slope gradient through autograd."""
+    return _MlpChainFn.apply(spec, x, spec.slope, *weights, *biases)
 
 
 def sequential_params(seq: nn.Sequential):
@@ -157,7 +180,7 @@ def sequential_spec(seq: nn.Sequential, activation: nn.Module, final_act: str = 
     lin = [m for m in seq if isinstance(m, nn.Linear)]
     dims = [lin[0].in_features] + [m.out_features for m in lin]
     name, param = activation_spec(activation)
-    return ChainSpec(dims, name, final_act, param)
+    return ChainSpec(dims, name, final_act, param, slope=prelu_slope(activation))
 
 
 # --------------------------------------------------------------------------- MultiONet combine
@@ -508,8 +531,9 @@ def run_chain(spec: ChainSpec, x: Tensor, weights, biases, tc_train: bool = True
     fp32 FFMA path otherwise.  ``tc_train=False`` pins the differentiable path to fp32 (the latent
     models' coders: their outputs feed finite-difference loss terms that amplify bf16 rounding by
     1/h^2 = n_timesteps^2, latent_neural_ode.py:560-604)."""
-    needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in weights))
-    if not needs_grad and precision_mode() == "bf16":
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in weights)
+                                              or (spec.slope is not None and spec.slope.requires_grad))
+    if not needs_grad and precision_mode() == "bf16" and not spec.slope_stale():
         from . import tc
         if tc.supported(spec):
             return tc.chain_forward(spec, x, weights, biases)
@@ -609,4 +633,8 @@ def lnode_integrate(wrapper, spec: ChainSpec, weights, biases, z0: Tensor, t_eva
     """Differentiable adaptive solve; ``n_err`` > 0 restricts the controller's error norm to the leading
     state features (fixed parameters carried as constant extra features)."""
     reg = wrapper.ode.reg_factor if reg_factor is None else reg_factor
+    if spec.slope is not None and torch.is_grad_enabled() and spec.slope.requires_grad:
+        raise NotImplementedError(
+            "LatentNeuralODE with a learnable nn.PReLU() activation cannot be trained: the persistent adjoint kernel "
+            "does not return the slope gradient of the ODE net (use a stateless activation, or freeze the slope)")
     return _LnodeSolveFn.apply(wrapper, spec, int(n_err), z0, t_eval, reg, *weights, *biases)

@@ -183,8 +183,9 @@ def _train_plan(spec, dev, out_bf16):
 
 
 def train_supported(spec) -> bool:
-    """Tensor-core training handles identity / tanh final activations on a tcgen05 device."""
-    return available() and spec.final_act in ("identity", "tanh")
+    """Tensor-core training handles identity / tanh final activations on a tcgen05 device.  PReLU chains train on
+    the fp32 kernels: those return the gradient of the learnable slope (cb_mlp_backward_f32_p)."""
+    return available() and spec.final_act in ("identity", "tanh") and spec.slope is None
 
 
 def gemm_chain_forward(spec, x, weights, biases):

@@ -27,7 +27,22 @@ struct GemmArgs {
   float* out_z;                       // EPI_FWD: pre-activation (nullable)
   const float* zprev;                 // EPI_DGRAD: pre-activation of previous layer (nullable)
   int act; float act_param;
+  const float* act_param_dev;         // nullable: learnable PReLU slope read from device memory (overrides act_param)
+  float* slope_part;                  // EPI_DGRAD + PReLU: per-CTA partial of d(slope) = sum dH * min(z,0) (nullable)
 };
+
+// deterministic block sum (fixed shuffle tree + fixed warp order); result valid in thread 0
+template <int NT>
+__device__ __forceinline__ float block_sum_fixed(float v, float* scratch /* >= NT/32 floats of shared memory */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < NT / 32; ++w) t += scratch[w];
+  return t;
+}
 
 template <int BM, int BN, int BK, int TM, int TN, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
@@ -121,6 +136,8 @@ sgemm_kernel(const GemmArgs g) {
   }
 
   // ------------------------------------------------------------ epilogue
+  const float ap = g.act_param_dev ? __ldg(g.act_param_dev) : g.act_param;
+  float slope_acc = 0.f;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int64_t m = m0 + ty * TM + i;
@@ -133,15 +150,32 @@ sgemm_kernel(const GemmArgs g) {
       if (g.epi == EPI_FWD) {
         if (g.bias) v += __ldg(g.bias + n);
         if (g.out_z) g.out_z[m * g.ldo + n] = v;
-        g.out[m * g.ldo + n] = act_fwd(g.act, v, g.act_param);
+        g.out[m * g.ldo + n] = act_fwd(g.act, v, ap);
       } else if (g.epi == EPI_DGRAD) {
-        if (g.zprev) v *= act_bwd(g.act, __ldg(g.zprev + m * g.ldo + n), g.act_param);
+        if (g.zprev) {
+          const float z = __ldg(g.zprev + m * g.ldo + n);
+          slope_acc = fmaf(v, fminf(z, 0.f), slope_acc);     // PReLU: d(slope) += dH * min(z, 0)
+          v *= act_bwd(g.act, z, ap);
+        }
         g.out[m * g.ldo + n] = v;
       } else {
         g.out[((int64_t)blockIdx.z * g.M + m) * g.N + n] = v;
       }
     }
   }
+  if (g.epi == EPI_DGRAD && g.slope_part) {      // uniform branch; the tile buffers are free after the main loop
+    const float t = block_sum_fixed<NT>(slope_acc, &As[0][0][0]);
+    if (tid == 0) g.slope_part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// out[0] = sum of `count` partials in a fixed order (one CTA) -> deterministic d(slope)
+__global__ void reduce_slope_kernel(const float* __restrict__ part, int64_t count, float* __restrict__ out) {
+  __shared__ float sm[8];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < count; i += 256) s += part[i];
+  const float t = block_sum_fixed<256>(s, sm);
+  if (threadIdx.x == 0) out[0] = t;
 }
 
 // sum of `splits` partial slabs of `count` floats, fixed order -> deterministic
@@ -275,6 +309,8 @@ struct NarrowParams {
   const float* dy;                     // backward input
   float* dx;                           // backward: gradient w.r.t. x (nullable)
   float* slabs;                        // backward: [n_cta][n][WP*WP + WP]
+  const float* ap_dev;                 // nullable: learnable PReLU slope in device memory (overrides ap)
+  float* slope_part;                   // backward + PReLU: [n_cta] partials of d(slope) (nullable)
   long long rows;
   int num_tiles;
 };
@@ -313,6 +349,7 @@ __global__ void __launch_bounds__(kNarrowThreads) narrow_fwd_kernel(const Narrow
   float* bs = Wt + P.n * WP * WP;                    // [n][WP]
   float* A0 = bs + P.n * WP;                         // [2][64][LD]
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  const float ap = P.ap_dev ? __ldg(P.ap_dev) : P.ap;
   // transpose on the way in: global reads run along k (coalesced), the strided shared-memory writes are cheap
 #pragma unroll 8
   for (int idx = tid; idx < P.n * WP * WP; idx += kNarrowThreads) {
@@ -355,7 +392,7 @@ __global__ void __launch_bounds__(kNarrowThreads) narrow_fwd_kernel(const Narrow
         for (int c = 0; c < TC; ++c) {
           const int col = tx * TC + c;
           const float z = acc[i][c];
-          const float h = act_fwd(act, z, P.ap);
+          const float h = act_fwd(act, z, ap);
           if (col < Nl && rg < P.rows) {
             if (P.pre[l]) P.pre[l][rg * Nl + col] = z;
             if (last) P.y[rg * Nl + col] = h;
@@ -381,6 +418,8 @@ __global__ void __launch_bounds__(kNarrowThreads) narrow_bwd_kernel(const Narrow
   float* Gp = G + kNarrowRows * LD;
   float* Hs = Gp + kNarrowRows * LD;                 // layer input tile
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  const float ap = P.ap_dev ? __ldg(P.ap_dev) : P.ap;
+  float slope_acc = 0.f;
 #pragma unroll 8
   for (int idx = tid; idx < P.n * WP * WP; idx += kNarrowThreads) {
     const int l = idx / (WP * WP), rem = idx - l * WP * WP, j = rem / WP, k = rem - j * WP;
@@ -398,7 +437,7 @@ __global__ void __launch_bounds__(kNarrowThreads) narrow_bwd_kernel(const Narrow
         float g = 0.f;
         if (j < Nl && r0 + r < P.rows) {
           g = __ldg(P.dy + (r0 + r) * Nl + j);
-          if (P.final_act != CB_ACT_IDENTITY) g *= act_bwd(P.final_act, __ldg(P.pre[l] + (r0 + r) * Nl + j), P.ap);
+          if (P.final_act != CB_ACT_IDENTITY) g *= act_bwd(P.final_act, __ldg(P.pre[l] + (r0 + r) * Nl + j), ap);
         }
         G[r * LD + j] = g;
       }
@@ -460,8 +499,11 @@ __global__ void __launch_bounds__(kNarrowThreads) narrow_bwd_kernel(const Narrow
             const int k = tx * TC + c;
             float v = acc[i][c];
             if (l > 0) {
-              if (k < Kl && rg < P.rows) v *= act_bwd(P.act, __ldg(P.pre[l - 1] + rg * Kl + k), P.ap);
-              else v = 0.f;
+              if (k < Kl && rg < P.rows) {
+                const float z = __ldg(P.pre[l - 1] + rg * Kl + k);
+                slope_acc = fmaf(v, fminf(z, 0.f), slope_acc);
+                v *= act_bwd(P.act, z, ap);
+              } else v = 0.f;
               g_nxt[r * LD + k] = v;
             } else if (k < Kl && rg < P.rows) {
               P.dx[rg * Kl + k] = v;
@@ -482,6 +524,11 @@ __global__ void __launch_bounds__(kNarrowThreads) narrow_bwd_kernel(const Narrow
   for (int idx = tid; idx < P.n * WP; idx += kNarrowThreads) {
     const int l = idx / WP;
     slab[(size_t)l * (WP * WP + WP) + WP * WP + (idx - l * WP)] = dba[idx];
+  }
+  if (P.slope_part) {
+    __syncthreads();
+    const float t = block_sum_fixed<kNarrowThreads>(slope_acc, G);
+    if (tid == 0) P.slope_part[blockIdx.x] = t;
   }
 }
 
@@ -531,6 +578,15 @@ static int64_t narrow_slab_floats(const cb_mlp_desc* d, int64_t rows) {
   return (int64_t)narrow_ctas(rows, wp) * d->n_layers * ((int64_t)wp * wp + wp);
 }
 
+// floats for the per-CTA d(slope) partials of a PReLU chain's backward (0 for other activations): one per dgrad
+// CTA of every hidden layer (both SGEMM tile shapes bounded by 128 x 32 tiles), or one per narrow-chain CTA
+static int64_t slope_part_floats(const cb_mlp_desc* d, int64_t rows) {
+  if (d->act != CB_ACT_PRELU) return 0;
+  int64_t total = num_sms() * 2;
+  for (int i = 1; i < d->n_layers; ++i) total += ((rows + 127) / 128) * ((d->dims[i] + 31) / 32);
+  return total;
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -559,6 +615,7 @@ extern "C" int64_t cb_mlp_workspace_floats(const cb_mlp_desc* desc, int64_t rows
     (void)maxw;
     const int64_t slabs = narrow_slab_floats(desc, rows);
     w += part > slabs ? part : slabs;
+    w += slope_part_floats(desc, rows);
   }
   return w;
 }
@@ -567,6 +624,13 @@ extern "C" int32_t cb_mlp_forward_f32(const cb_mlp_desc* desc, const float* cons
                                       const float* const* d_b, const float* d_x, int64_t rows,
                                       float* d_y, float* d_saved, float* d_ws, int64_t ws_floats,
                                       void* stream) {
+  return cb_mlp_forward_f32_p(desc, d_W, d_b, d_x, rows, d_y, d_saved, d_ws, ws_floats, nullptr, stream);
+}
+
+extern "C" int32_t cb_mlp_forward_f32_p(const cb_mlp_desc* desc, const float* const* d_W,
+                                        const float* const* d_b, const float* d_x, int64_t rows,
+                                        float* d_y, float* d_saved, float* d_ws, int64_t ws_floats,
+                                        const float* d_act_param, void* stream) {
   if (int32_t e = check_desc(desc)) return e;
   CB_CHECK_ARG(rows >= 0, "rows < 0");
   if (rows == 0) return CB_OK;  // empty batch: nothing to do
@@ -592,7 +656,7 @@ extern "C" int32_t cb_mlp_forward_f32(const cb_mlp_desc* desc, const float* cons
       P.post[i] = (d_saved && L.post[i] >= 0) ? d_saved + L.post[i] : nullptr;
       P.pre[i] = (d_saved && L.pre[i] >= 0) ? d_saved + L.pre[i] : nullptr;
     }
-    P.x = d_x; P.y = d_y; P.rows = rows;
+    P.x = d_x; P.y = d_y; P.rows = rows; P.ap_dev = d_act_param;
     P.num_tiles = (int)((rows + kNarrowRows - 1) / kNarrowRows);
     const size_t smem = narrow_fwd_smem(n, wp);
     if (wp == 32) {
@@ -613,7 +677,7 @@ extern "C" int32_t cb_mlp_forward_f32(const cb_mlp_desc* desc, const float* cons
     g.B = d_W[i]; g.sBn = desc->dims[i]; g.sBk = 1;
     g.M = rows; g.N = desc->dims[i + 1]; g.K = desc->dims[i]; g.k_per_split = g.K;
     g.epi = EPI_FWD; g.bias = d_b[i]; g.ldo = g.N;
-    g.act = last ? desc->final_act : desc->act; g.act_param = desc->act_param;
+    g.act = last ? desc->final_act : desc->act; g.act_param = desc->act_param; g.act_param_dev = d_act_param;
     if (last) {
       g.out = d_y;
       g.out_z = (d_saved && L.pre[i] >= 0) ? d_saved + L.pre[i] : nullptr;
@@ -634,7 +698,17 @@ extern "C" int32_t cb_mlp_backward_f32(const cb_mlp_desc* desc, const float* con
                                        const float* d_x, const float* d_saved, const float* d_dy,
                                        int64_t rows, float* const* d_dW, float* const* d_db,
                                        float* d_dx, float* d_ws, int64_t ws_floats, void* stream) {
+  return cb_mlp_backward_f32_p(desc, d_W, d_x, d_saved, d_dy, rows, d_dW, d_db, d_dx, d_ws, ws_floats, nullptr,
+                               nullptr, stream);
+}
+
+extern "C" int32_t cb_mlp_backward_f32_p(const cb_mlp_desc* desc, const float* const* d_W,
+                                         const float* d_x, const float* d_saved, const float* d_dy,
+                                         int64_t rows, float* const* d_dW, float* const* d_db,
+                                         float* d_dx, float* d_ws, int64_t ws_floats,
+                                         const float* d_act_param, float* d_dact_param, void* stream) {
   if (int32_t e = check_desc(desc)) return e;
+  CB_CHECK_ARG(d_dact_param == nullptr || desc->act == CB_ACT_PRELU, "d_dact_param is only defined for PReLU chains");
   CB_CHECK_ARG(d_W && d_x && d_dy && d_dW && d_db && d_ws, "NULL pointer argument");
   CB_CHECK_ARG(rows > 0, "rows must be > 0");
   const int n = desc->n_layers;
@@ -650,6 +724,8 @@ extern "C" int32_t cb_mlp_backward_f32(const cb_mlp_desc* desc, const float* con
   SavedLayout L = saved_layout(desc, rows);
   float* gbuf[2] = {d_ws, d_ws + rows * md};
   float* part = d_ws + 2 * rows * md;
+  float* slope_part = d_dact_param ? d_ws + need - slope_part_floats(desc, rows) : nullptr;
+  int64_t slope_count = 0;
   if (const int wp = narrow_width(desc)) {
     NarrowParams P{};
     P.n = n; P.act = desc->act; P.final_act = desc->final_act; P.ap = desc->act_param;
@@ -661,6 +737,7 @@ extern "C" int32_t cb_mlp_backward_f32(const cb_mlp_desc* desc, const float* con
       CB_CHECK_ARG(d_dW[i] != nullptr, "dW[%d] is NULL", i);
     }
     P.x = d_x; P.dy = d_dy; P.dx = d_dx; P.rows = rows; P.slabs = part;
+    P.ap_dev = d_act_param; P.slope_part = slope_part;
     P.num_tiles = (int)((rows + kNarrowRows - 1) / kNarrowRows);
     const int ctas = narrow_ctas(rows, wp);
     const size_t smem = narrow_bwd_smem(n, wp);
@@ -677,6 +754,10 @@ extern "C" int32_t cb_mlp_backward_f32(const cb_mlp_desc* desc, const float* con
     for (int i = 0; i < n; ++i) { R.N[i] = P.N[i]; R.K[i] = P.K[i]; R.dW[i] = d_dW[i]; R.db[i] = d_db[i]; }
     narrow_reduce_kernel<<<dim3((wp * wp + wp + 255) / 256, n), 256, 0, st>>>(part, R);
     CB_LAUNCH_CHECK();
+    if (slope_part) {
+      reduce_slope_kernel<<<1, 256, 0, st>>>(slope_part, ctas, d_dact_param);
+      CB_LAUNCH_CHECK();
+    }
     return CB_OK;
   }
 
@@ -685,7 +766,7 @@ extern "C" int32_t cb_mlp_backward_f32(const cb_mlp_desc* desc, const float* con
   if (desc->final_act != CB_ACT_IDENTITY) {
     const int64_t cnt = rows * desc->dims[n];
     act_bwd_mul_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(
-        d_dy, d_saved + L.pre[n - 1], cnt, desc->final_act, desc->act_param, gbuf[which]);
+        d_dy, d_saved + L.pre[n - 1], cnt, desc->final_act, desc->act_param, gbuf[which]);   // (never PReLU)
     CB_LAUNCH_CHECK();
     g_cur = gbuf[which];
     which ^= 1;
@@ -724,11 +805,20 @@ extern "C" int32_t cb_mlp_backward_f32(const cb_mlp_desc* desc, const float* con
       g.epi = EPI_DGRAD; g.ldo = K;
       g.out = (i == 0) ? d_dx : gbuf[which];
       g.zprev = (i == 0) ? nullptr : d_saved + L.pre[i - 1];
-      g.act = desc->act; g.act_param = desc->act_param;
+      g.act = desc->act; g.act_param = desc->act_param; g.act_param_dev = d_act_param;
+      if (slope_part && i > 0) {
+        g.slope_part = slope_part + slope_count;
+        const int bn = g.N > kSmallTileMaxN ? 128 : 32;
+        slope_count += ((g.M + 127) / 128) * ((g.N + bn - 1) / bn);
+      }
       if (int32_t e = launch_gemm<true, false>(g, 1, st)) return e;
       g_cur = g.out;
       which ^= 1;
     }
+  }
+  if (slope_part) {
+    reduce_slope_kernel<<<1, 256, 0, st>>>(slope_part, slope_count, d_dact_param);
+    CB_LAUNCH_CHECK();
   }
   return CB_OK;
 }

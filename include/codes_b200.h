@@ -98,6 +98,21 @@ CB_API int32_t cb_mlp_backward_f32(const cb_mlp_desc* desc, const float* const* 
                             float* d_dx, float* d_workspace, int64_t workspace_floats,
                             void* stream);
 
+/* Learnable-PReLU variants of the two calls above (nn.PReLU() shared by every layer of a net, SURVEY Q8;
+ * datasets/cloud/surrogates_config.py:55, datasets/primordial_parametric/surrogates_config.py:14):
+ * d_act_param (nullable) is the 1-element slope in DEVICE memory and overrides desc->act_param, so a
+ * training step needs no host read of the slope; d_dact_param (nullable, PReLU chains only) receives
+ * d(loss)/d(slope) = sum over hidden layers and elements of dH * min(z, 0), reduced in a fixed order. */
+CB_API int32_t cb_mlp_forward_f32_p(const cb_mlp_desc* desc, const float* const* d_W,
+                             const float* const* d_b, const float* d_x, int64_t rows,
+                             float* d_y, float* d_saved, float* d_workspace,
+                             int64_t workspace_floats, const float* d_act_param, void* stream);
+CB_API int32_t cb_mlp_backward_f32_p(const cb_mlp_desc* desc, const float* const* d_W,
+                              const float* d_x, const float* d_saved, const float* d_dy,
+                              int64_t rows, float* const* d_dW, float* const* d_db,
+                              float* d_dx, float* d_workspace, int64_t workspace_floats,
+                              const float* d_act_param, float* d_dact_param, void* stream);
+
 /* ------------------------------------------------------- MultiONet combine */
 /* y[r,q] = sum_{k in split_q} branch[r,k]*trunk[r,k]; split sizes follow
  * OperatorNetwork._calculate_split_sizes (deeponet.py:130-137, :245-253). */

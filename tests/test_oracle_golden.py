@@ -223,3 +223,30 @@ def test_tsit5_against_dop853():
                         atol=1e-12, t_eval=te).y.T
         assert np.all(np.abs(ys[i] - ref) <= 50 * (1e-6 + 1e-6 * np.abs(ref)))
     assert (na <= ns).all() and (ns < 200).all()
+
+
+# ---------------------------------------------------------------- torch-CPU port (bench.py's fallback CPU arm)
+def test_torch_port_matches_live_reference_goldens(golden):
+    """oracle/torch_port.py (the CPU arm bench.py falls back to when oracle/_ref is absent) against the outputs of
+    the live reference classes: MultiONet forward and FullyConnected predict incl. de-normalisation."""
+    import torch
+    from oracle import torch_port as TP
+    g = golden("multionet")
+    tt = lambda a: torch.from_numpy(np.asarray(a))  # noqa: E731
+    bw, bb = chain(g, "init.branch_net.network.", [0, 2, 4])
+    tw, tb = chain(g, "init.trunk_net.network.", [0, 2, 4, 6])
+    n = g["y0"].shape[0]
+    y = TP.multionet_forward(tt(g["branch_in"][:n]), tt(g["trunk_in"][:n]), [tt(w) for w in bw], [tt(b) for b in bb],
+                             [tt(w) for w in tw], [tt(b) for b in tb], 5, "leakyrelu")
+    np.testing.assert_allclose(y.numpy(), g["y0"], rtol=1e-5, atol=1e-6)
+    g = golden("fcnn_predict")
+    w, b = chain(g, "model.network.", [0, 2, 4])
+    d = g["data"]
+    n_, T_, Q_ = d.shape
+    x = np.concatenate([np.repeat(d[:, :1, :], T_, axis=1), np.broadcast_to(np.linspace(0, 1, T_)[None, :, None], (n_, T_, 1))],
+                       axis=2).reshape(n_ * T_, Q_ + 1).astype(np.float32)
+    act = "tanh"
+    yraw = TP.mlp_chain(tt(x), [tt(v) for v in w], [tt(v) for v in b], act)
+    np.testing.assert_allclose(yraw.numpy().reshape(n_, T_, Q_), g["p_raw"], rtol=1e-5, atol=1e-6)
+    ylin = TP.denormalize_minmax_log(yraw, tt(g["norm_min"]), tt(g["norm_max"]))
+    np.testing.assert_allclose(ylin.numpy().reshape(n_, T_, Q_), g["p_lin"], rtol=2e-5)
