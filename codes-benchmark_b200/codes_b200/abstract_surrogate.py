@@ -158,15 +158,22 @@ class AbstractSurrogateModel(ABC, nn.Module):
         Semantics of abstract_surrogate.py:217-275 (buffers sized first_batch_rows x
         len(loader), loader order preserved, denormalise, reshape).  The reference's extra
         "dummy" forward on the first batch is not repeated: the first
-        batch's output is kept and used to size the buffers.  Its side effect on the CPU RNG is: the dummy
-        ``next(iter(loader))`` of a SHUFFLING loader draws one ``torch.randperm(N)`` (abstract_surrogate.py:233-239),
-        so the same draw is consumed here and every later training batch order matches the reference for a seed
-        (``validate`` calls predict on the shuffled train loader; tests/golden/predict_rng.npz).
+        batch's output is kept and used to size the buffers.  Its side effects on the CPU RNG are kept: the dummy
+        ``next(iter(loader))`` (abstract_surrogate.py:233-239) draws the DataLoader iterator's base seed (one int64)
+        and, for a SHUFFLING dataset, one ``torch.randperm(N)``; the same draws are consumed here, so every later
+        training batch order matches the reference for a seed (``validate`` calls predict on the shuffled train
+        loader 3x per 10 epochs; tests/golden/predict_rng.npz).
         """
         n_batches = len(data_loader)
         ds = getattr(data_loader, "dataset", None)
+        self._draw_loader_seed(data_loader)
         if getattr(ds, "shuffle", False) and hasattr(ds, "N"):
             torch.randperm(ds.N)
+        grid_hook = getattr(self, "_predict_on_grid", None)   # de-duplicated whole-loader path of a concrete class
+        if grid_hook is not None:
+            res = grid_hook(data_loader, leave_log, leave_norm)
+            if res is not None:
+                return res
         preds = targs = None
         done = 0
         # consecutive batches are independent: on CUDA they alternate between the current stream and a second one, so
@@ -198,6 +205,12 @@ class AbstractSurrogateModel(ABC, nn.Module):
             targs = self.denormalize(targs[:done], leave_log, leave_norm, _inplace=True)
         return (preds.reshape(-1, self.n_timesteps, self.n_quantities),
                 targs.reshape(-1, self.n_timesteps, self.n_quantities))
+
+    @staticmethod
+    def _draw_loader_seed(data_loader) -> None:
+        """Consume what creating a DataLoader iterator consumes from the default CPU generator (its base seed)."""
+        if isinstance(data_loader, DataLoader):
+            torch.empty((), dtype=torch.int64).random_(generator=data_loader.generator)
 
     def _predict_streams(self):
         """[current stream, second stream] for predict()'s batch pipelining on CUDA, else None
@@ -241,6 +254,7 @@ class AbstractSurrogateModel(ABC, nn.Module):
         if compact:
             # loaders built by prepare_data for the flat-row models: every distinct row crosses PCIe once (x0 per
             # trajectory, the time grid once), the T-fold repetition is rebuilt on the device (cb_gather_rows)
+            self._draw_loader_seed(data_loader)      # (this path never creates the DataLoader iterator)
             with torch.cuda.stream(copy_stream):
                 gen = ds.compact_batches(device)
             while True:

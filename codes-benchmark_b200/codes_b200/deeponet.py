@@ -110,6 +110,61 @@ class MultiONet(OperatorNetwork):
         t = self.trunk_net(trunk_input)
         return ops.deeponet_combine(b, t, self.N), targets
 
+    # ------------------------------------------------------------------ de-duplicated predict
+    def _predict_on_grid(self, data_loader, leave_log: bool, leave_norm: bool):
+        """predict() for an un-shuffled loader built by ``prepare_data``: its rows r = n*T + t repeat x0[n] T times
+        and tile the time grid N times (deeponet.py:371-374), so the branch net is evaluated once per trajectory,
+        the trunk net once per grid point and one contraction kernel writes the de-normalised (N, T, Q) predictions
+        (SURVEY 8d F_traj,dedup; ``cb_tc_multionet_grid_forward``).  Same values as the row path up to the bf16
+        rounding of the branch / trunk features (tests/test_gpu_grid_predict.py); returns None whenever the loader
+        or the configuration does not have that structure, and the generic per-batch path runs instead."""
+        from . import tc
+        from .loaders import grid_predict_enabled
+        ds = getattr(data_loader, "dataset", None)
+        dev = self.device
+        if (dev is None or "cuda" not in str(dev) or not isinstance(ds, RowBatchIterable) or ds.shuffle
+                or ds.row_structure != ["repeat", "tile", "full"] or ds._compact is None
+                or getattr(data_loader, "num_workers", 0) != 0 or not grid_predict_enabled()
+                or ops.precision_mode() != "bf16" or ds.N % ds.period != 0):
+            return None
+        norm = self.normalisation
+        mode, do_pow = 0, False
+        if norm is not None:
+            if (not leave_norm) and norm["mode"] == "standardize":
+                return None
+            mode = 1 if ((not leave_norm) and norm["mode"] == "minmax") else 0
+            do_pow = bool(norm["log10_transform"]) and not leave_log
+        if not tc.multionet_grid_supported(self):
+            return None
+        device = torch.device(dev)
+        self._draw_loader_seed(data_loader)                 # the iterator the per-batch loop would have created
+        x0_h, t_h, targ_h = ds._compact[0], ds._compact[1], ds.tensors[2]
+        Q = self.N
+        with torch.inference_mode():
+            copy_stream = self.__dict__.get("_copy_stream")
+            if copy_stream is None or copy_stream.device != device:
+                copy_stream = self.__dict__["_copy_stream"] = torch.cuda.Stream(device)
+            cur = torch.cuda.current_stream(device)
+            copy_stream.wait_stream(cur)
+            with torch.cuda.stream(copy_stream):            # the targets cross PCIe while the predictions are computed
+                targs = targ_h.to(device, non_blocking=True)
+                ready = copy_stream.record_event()
+            x0 = x0_h.to(device, non_blocking=True)
+            tg = t_h.to(device, non_blocking=True)
+            self.__dict__["_h2d_bytes"] = self.__dict__.get("_h2d_bytes", 0) + sum(
+                t.numel() * t.element_size() for t in (x0_h, t_h, targ_h))
+            preds = torch.empty((ds.N, Q), dtype=torch.float32, device=device)
+            dmin = dmax = None
+            if mode == 1:
+                dmin = self._norm_vector(norm["min"], Q, device)
+                dmax = self._norm_vector(norm["max"], Q, device)
+            tc.multionet_grid_forward(self, x0, tg, preds, mode, dmin, dmax, do_pow)
+            cur.wait_event(ready)
+            targs.record_stream(cur)
+            targs = self.denormalize(targs, leave_log, leave_norm, _inplace=True)
+        return (preds.reshape(-1, self.n_timesteps, self.n_quantities),
+                targs.reshape(-1, self.n_timesteps, self.n_quantities))
+
     # ------------------------------------------------------------------ data
     def create_dataloader(self, data: np.ndarray, timesteps: np.ndarray, batch_size: int, shuffle: bool,
                           dataset_params: np.ndarray | None, params_in_branch: bool, num_workers: int = 0,

@@ -170,6 +170,13 @@ def dedup_h2d_enabled() -> bool:
     return os.environ.get("CODES_B200_DEDUP_H2D", "1") != "0"
 
 
+def grid_predict_enabled() -> bool:
+    """CODES_B200_GRID_PREDICT=0: MultiONet.predict keeps the per-batch row path (branch / trunk evaluated per row)
+    even for loaders whose rows are a (trajectory x time) grid."""
+    import os
+    return os.environ.get("CODES_B200_GRID_PREDICT", "1") != "0"
+
+
 def make_loader(dataset: IterableDataset, device: str | None, num_workers: int = 0) -> DataLoader:
     """``DataLoader(batch_size=None)``: the dataset already yields whole batches."""
     pin = device is not None and "cuda" in str(device) and torch.cuda.is_available()

@@ -158,6 +158,65 @@ def multionet_forward(model, branch_input, trunk_input, phase_ms=None):
     return y
 
 
+# --------------------------------------------------------------------------- MultiONet on the (trajectory x time) grid
+class _GridPlan:
+    def __init__(self, bspec, q, device):
+        self.handle = C.c_void_p()
+        with torch.cuda.device(device):
+            check(lib().cb_tc_multionet_grid_create(C.byref(bspec.desc), q, device.index or 0, C.byref(self.handle)),
+                  "tc_multionet_grid_create")
+        self.versions = None
+        self.workspace = None
+        self._fin = weakref.finalize(self, lib().cb_tc_multionet_grid_destroy, self.handle)
+
+
+_GRID_PLANS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def multionet_grid_supported(model) -> bool:
+    """Whether the de-duplicated grid kernels handle this MultiONet (shape only; the caller checks the loader)."""
+    if not available():
+        return False
+    return bool(lib().cb_tc_multionet_grid_supported(C.byref(model.branch_net.chain().desc), model.N))
+
+
+def multionet_grid_forward(model, x0, trunk_rows, out, mode: int, dmin, dmax, pow10: bool):
+    """out[n*T + t, q] = denorm(sum_k branch(x0[n])[k] * trunk(trunk_rows[t])[k]) for every trajectory n and grid
+    point t: branch once per trajectory (bf16 tensor cores), trunk once per grid point (fp32 chain), then the
+    per-quantity contraction kernel writes the (N, T, Q) buffer ``out`` (fp32, contiguous) in one pass.
+    x0: (N, branch_in) fp32 on the device, trunk_rows: (T, trunk_in)."""
+    dev = x0.device
+    bspec, tspec = model.branch_net.chain(), model.trunk_net.chain()
+    per_model = _GRID_PLANS.setdefault(model, {})
+    key = (dev.index, id(bspec))
+    plan = per_model.get(key)
+    if plan is None:
+        per_model.clear()
+        plan = per_model[key] = _GridPlan(bspec, model.N, dev)
+    bw, bb = ops.sequential_params(model.branch_net.network)
+    tw, tb = ops.sequential_params(model.trunk_net.network)
+    n_traj, n_t = x0.shape[0], trunk_rows.shape[0]
+    x0 = x0.float().contiguous()
+    with torch.cuda.device(dev), torch.no_grad():
+        stream = _stream(dev)
+        versions = _versions(bw) + _versions(bb)
+        if versions != plan.versions:
+            check(lib().cb_tc_multionet_grid_set_weights(plan.handle, ptr_array(_f32(bw)), ptr_array(_f32(bb)), stream),
+                  "tc_multionet_grid_set_weights")
+            plan.versions = versions
+        trunk_out = ops.mlp_chain(tspec, trunk_rows.float().contiguous(), [w.detach() for w in tw],
+                                  [b.detach() for b in tb])                    # (T, Q*f) fp32, exact path
+        need = int(lib().cb_tc_multionet_grid_workspace_bytes(plan.handle, n_traj, n_t))
+        if plan.workspace is None or plan.workspace.numel() < need or plan.workspace.device != dev:
+            plan.workspace = torch.empty(need, device=dev, dtype=torch.uint8)
+        check(lib().cb_tc_multionet_grid_forward(
+            plan.handle, C.c_void_p(x0.data_ptr()), n_traj, C.c_void_p(trunk_out.data_ptr()), n_t,
+            C.c_void_p(out.data_ptr()), int(mode), C.c_void_p(None if dmin is None else dmin.data_ptr()),
+            C.c_void_p(None if dmax is None else dmax.data_ptr()), int(bool(pow10)),
+            C.c_void_p(plan.workspace.data_ptr()), plan.workspace.numel(), stream), "tc_multionet_grid_forward")
+    return out
+
+
 # --------------------------------------------------------------------------- tensor-core training path
 class _TrainPlan:
     def __init__(self, spec, device, out_bf16):

@@ -34,6 +34,7 @@
 
 #include "cb_common.cuh"
 #include "cb_tc_ptx.cuh"
+#include "cb_tc_internal.cuh"
 
 namespace cb {
 namespace tc {
@@ -1703,6 +1704,30 @@ extern "C" int32_t cb_tc_chain_forward(cb_tc_chain* plan, const float* d_x, int6
   CB_CHECK_ARG(rows <= (int64_t)kTileM * 0x3fffffff, "too many rows");
   return chain_launch(plan, d_x, nullptr, rows, d_y, nullptr, (cudaStream_t)stream);
 }
+
+// ---------------------------------------------------------------------- internal entry points (cb_tc_internal.cuh)
+namespace cb { namespace tc {
+bool hidden_chain_supported(const cb_mlp_desc* full) {
+  if (check_desc(full) != CB_OK || full->n_layers < 2) return false;
+  cb_mlp_desc h = *full;
+  h.n_layers = full->n_layers - 1;
+  return chain_geometry(&h, OUT_BF16_TMA).ok;
+}
+int32_t hidden_chain_create(const cb_mlp_desc* full, int device, cb_tc_chain** out) {
+  CB_CHECK_ARG(full && full->n_layers >= 2, "hidden chain needs at least two Linear layers");
+  cb_mlp_desc h = *full;
+  h.n_layers = full->n_layers - 1;
+  h.final_act = h.act;     // the last layer of the hidden chain is an ordinary hidden layer
+  return chain_create(&h, device, OUT_BF16_TMA, out);
+}
+int hidden_chain_ld(const cb_tc_chain* plan) { return plan ? plan->ld_out : -1; }
+int32_t hidden_chain_launch(cb_tc_chain* plan, const float* d_x, int64_t rows, __nv_bfloat16* d_yb, cudaStream_t st) {
+  CB_CHECK_ARG(plan && plan->weights_set, "hidden chain: weights not set");
+  CUtensorMap omap;
+  CB_CHECK_ARG(encode_bf16_map(&omap, d_yb, rows, plan->ld_out), "tensor map of the hidden activations failed");
+  return chain_launch(plan, d_x, nullptr, rows, nullptr, &omap, st, d_yb, plan->ld_out);
+}
+}}
 
 // ---------------------------------------------------------------------- MultiONet pipeline
 struct cb_tc_multionet {

@@ -29,6 +29,7 @@
 
 #include "cb_common.cuh"
 #include "cb_tc_ptx.cuh"
+#include "cb_tc_internal.cuh"
 
 namespace cb {
 namespace tcg {
@@ -726,6 +727,21 @@ static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
+
+namespace cb { namespace tcg {
+int32_t gemm_fwd_bf16(const __nv_bfloat16* A, long long rows, int a_ld, int k_total, const __nv_bfloat16* Bp,
+                      int b_rows, int n_true, int n_out_ld, __nv_bfloat16* out, cudaStream_t st) {
+  GemmCall c;
+  memset(&c, 0, sizeof(c));
+  c.mode = EPI_FWD_BF16;
+  c.A = A; c.a_rows = rows; c.a_cols = a_ld; c.a_ld = a_ld;
+  c.B = Bp; c.b_rows = b_rows; c.b_cols = a_ld; c.b_ld = a_ld;
+  c.m_out = rows; c.k_total = k_total; c.n_true = n_true; c.n_out_ld = n_out_ld;
+  c.out_bf16 = out; c.out_rows = rows; c.out_ld = n_out_ld;
+  c.act = CB_ACT_IDENTITY; c.ones_col = -1;
+  return ::launch_gemm(c, st);
+}
+}}
 
 // ---------------------------------------------------------------------------- training plan
 static bool act_needs_z(int act, float p) {

@@ -130,6 +130,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr));
+}
 // registers -> TMEM: lane (row) i of the warp's quarter writes its 16 / 8 values to columns [c, c+16) / [c, c+8)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
   asm volatile(

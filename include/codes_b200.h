@@ -305,6 +305,29 @@ CB_API int32_t cb_tc_multionet_forward_timed(cb_tc_multionet* plan, const float*
                                              void* d_workspace, int64_t workspace_bytes, void* stream,
                                              float* phase_ms);
 
+/* MultiONet on the (trajectory x time) grid: de-duplicated inference for loaders built by
+ * MultiONet.prepare_data, whose rows r = n*T + t repeat x0[n] T times and tile the time grid N times
+ * (deeponet.py:371-374), so that forward (deeponet.py:241-253) recomputes the branch net per grid point and
+ * the trunk net per trajectory.  Here the branch net runs once per trajectory, the trunk outputs
+ * (T, Q*f) are supplied by the caller (one fp32 chain call over the T grid points) and
+ *   y[n,t,q] = sum_{k in split_q} branch(x0[n])[k] * trunk_out[t][k]      (split rule deeponet.py:130-137)
+ * is written straight into the (n_traj, T, Q) prediction buffer of AbstractSurrogateModel.predict
+ * (abstract_surrogate.py:217-275) with its de-normalisation (:435-487; mode / d_min / d_max / pow10 as in
+ * cb_denormalize) fused.  Only valid when the branch input depends on the trajectory alone and the trunk
+ * input on the grid point alone (no parameters, or params_branch=True).  bf16 operands, fp32 accumulate. */
+typedef struct cb_tc_grid cb_tc_grid;
+CB_API int32_t cb_tc_multionet_grid_supported(const cb_mlp_desc* branch, int32_t n_quantities);
+CB_API int32_t cb_tc_multionet_grid_create(const cb_mlp_desc* branch, int32_t n_quantities, int32_t device,
+                                           cb_tc_grid** out);
+CB_API void cb_tc_multionet_grid_destroy(cb_tc_grid* plan);
+CB_API int32_t cb_tc_multionet_grid_set_weights(cb_tc_grid* plan, const float* const* d_Wb,
+                                                const float* const* d_bb, void* stream);
+CB_API int64_t cb_tc_multionet_grid_workspace_bytes(const cb_tc_grid* plan, int64_t n_traj, int32_t n_t);
+CB_API int32_t cb_tc_multionet_grid_forward(cb_tc_grid* plan, const float* d_x0, int64_t n_traj,
+                                            const float* d_trunk_out, int32_t n_t, float* d_y, int32_t mode,
+                                            const float* d_min, const float* d_max, int32_t pow10,
+                                            void* d_workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------- tensor-core (bf16) TRAINING path */
 /* Forward + backward of a dense chain on tcgen05 (bf16 operands, fp32 accumulate), one GEMM launch per
  * layer and direction: replaces loss.backward() through nn.Linear / activations (fcnn.py:291,
