@@ -377,6 +377,57 @@ def run_ours(args):
             "step_achieved": step_tf, "step_frac": step_tf / peak_tf,
         }
 
+    # ---- de-duplicated leg (ALL ranks, weak scaling; SURVEY 8d "F_traj,dedup" -- reported separately from `value`,
+    # never mixed with the row-semantics figures): the fixed 65 536-trajectory cfg2 test set on the (trajectory x
+    # time) grid, x0 resident in HBM, de-normalised (N, T, Q) predictions written to HBM.  HBM-bound: 4*(Q + T*Q)
+    # algorithmic bytes per trajectory; 760 MB written per pass >> 126 MB L2.
+    n_grid = 65536
+    dg = synthetic_x0(n_grid, seed=777 + rank)
+    x0_grid = torch.from_numpy(np.ascontiguousarray(dg[:, 0, :])).to(device)
+    t_grid = torch.linspace(0, 1, T, device=device).reshape(-1, 1).contiguous()
+    out_grid = torch.empty((n_grid * T, Q), device=device, dtype=torch.float32)
+    del dg
+    with torch.inference_mode():
+        for _ in range(3):
+            tc.multionet_grid_forward(model, x0_grid, t_grid, out_grid, 1, dmin, dmax, True)
+        barrier()
+        grid_passes = 10
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(grid_passes):
+            tc.multionet_grid_forward(model, x0_grid, t_grid, out_grid, 1, dmin, dmax, True)
+        g1.record()
+        barrier()
+        grid_ms = torch.tensor([g0.elapsed_time(g1) / grid_passes], device=device)
+        if world > 1:
+            dist.all_reduce(grid_ms, op=dist.ReduceOp.MAX)
+        grid_ms = float(grid_ms.item())
+        grid_phases = []
+        if rank == 0:
+            for _ in range(3):
+                ms = []
+                tc.multionet_grid_forward(model, x0_grid, t_grid, out_grid, 1, dmin, dmax, True, phase_ms=ms)
+                grid_phases.append(ms)
+    bytes_traj = 4 * (Q + T * Q)
+    flop_traj_dedup = 2 * (MAC_BRANCH + T * 2842)
+    dedup = {"value": world * n_grid / (grid_ms * 1e-3), "unit": "trajectories/s", "ms_per_pass": grid_ms,
+             "trajectories_per_pass": n_grid,
+             "what": "cb_tc_multionet_grid_forward: branch once per trajectory (tcgen05 chain + GEMM), trunk once per grid "
+                     "point (fp32 chain), per-quantity contraction kernel writing de-normalised (N,T,Q); x0 resident in HBM",
+             "algorithmic_bytes_per_trajectory": bytes_traj, "algorithmic_flop_per_trajectory": flop_traj_dedup}
+    if rank == 0:
+        peak_tf, peak_gbs, peak_src = peaks()
+        ph = np.mean(np.array(grid_phases), axis=0)
+        gbs = bytes_traj * n_grid / (grid_ms * 1e-3) / 1e9
+        kern_gbs = bytes_traj * n_grid / (float(ph[3]) * 1e-3) / 1e9
+        dedup["roofline"] = {"bound": "hbm", "kernel": "don_grid_kernel (per-quantity contraction + de-normalise + (N,T,Q) store)",
+                             "achieved": kern_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": kern_gbs / peak_gbs,
+                             "pass_achieved": gbs, "pass_frac": gbs / peak_gbs, "peak_source": peak_src,
+                             "traffic": ncu_traffic("don_grid_kernel").get("traffic"),
+                             "kernel_ms": {"trunk_pack": float(ph[0]), "branch_hidden_chain": float(ph[1]),
+                                           "feature_gemm": float(ph[2]), "grid_kernel": float(ph[3])}}
+    del x0_grid, out_grid
+
     # ---- e2e leg (ALL ranks, weak scaling): public API with HOST batches (pinned), H2D + metric D2H inside
     # the timed region; aggregate = trajectories of all ranks / slowest rank's wall time between barriers
     n_e2e = 65536                              # N_test = 65536 trajectories = 100 loader batches per pass
@@ -405,10 +456,29 @@ def run_ours(args):
     e2e = {"value": world * passes * n_e2e / float(dt_e2e.item()), "unit": "trajectories/s",
            "h2d_bytes_per_step": (model.__dict__.get("_h2d_bytes", 0) - h2d_0) / (passes * steps_per_pass),
            "d2h_bytes_per_step": 4.0 / steps_per_pass,
-           "api": "MultiONet.predict(val_loader) + L1 metric .item(), every rank on its own shard; host batches are "
-                  "pinned; x0 crosses PCIe once per trajectory and the time grid once (the loader's T-fold repeated "
-                  "rows are rebuilt on the device), targets in full",
+           "api": "MultiONet.predict(val_loader) + L1 metric .item(), every rank on its own shard; the loader's host "
+                  "tensors are pinned; predict() recognises the (trajectory x time) grid of a prepare_data loader: x0 "
+                  "crosses PCIe once per trajectory, the time grid once, the targets in full (one async copy overlapping "
+                  "the compute), predictions by the de-duplicated grid kernels",
            "passes": passes, "steps_per_pass": steps_per_pass, "pass_ms_rank0": pass_ms, "l1_metric": metric}
+    del p, t
+    # the same call with the grid path switched off (per-batch row path of round 1), 2 passes, for continuity
+    os.environ["CODES_B200_GRID_PREDICT"] = "0"
+    for _ in range(2):
+        p, t = model.predict(val_loader)
+        model._l1(p, t)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        p = t = None
+        p, t = model.predict(val_loader)
+        model._l1(p, t)
+    torch.cuda.synchronize()
+    dt_rows = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt_rows, op=dist.ReduceOp.MAX)
+    os.environ.pop("CODES_B200_GRID_PREDICT", None)
+    e2e["row_path_value"] = world * 2 * n_e2e / float(dt_rows.item())
     del p, t
 
     # ---- training leg (ALL ranks, independent models = the benchmark's task parallelism): steady-state fit
@@ -495,7 +565,7 @@ def run_ours(args):
                        "resident_batches": n_batches, "l2_policy": "inputs larger than L2 (rotating batches)",
                        "streams": "batches alternate between two CUDA streams (as in predict()); timed from the first launch to the join of both",
                        "precision": "bf16 operands, fp32 accumulate (tcgen05)", "parallelism": f"trajectory-sharded x{world}"},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": clocks.summary(), "e2e": e2e, "dedup": dedup, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "reference_gpu": reference_gpu, "train": train,
         }
         print(json.dumps(line), flush=True)

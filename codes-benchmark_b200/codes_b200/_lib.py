@@ -108,6 +108,8 @@ _SIGNATURES = {
     "cb_tc_multionet_grid_set_weights": (_I32, [_P, _PP, _PP, _P]),
     "cb_tc_multionet_grid_workspace_bytes": (_I64, [_P, _I64, _I32]),
     "cb_tc_multionet_grid_forward": (_I32, [_P, _P, _I64, _P, _I32, _P, _I32, _P, _P, _I32, _P, _I64, _P]),
+    "cb_tc_multionet_grid_forward_timed": (_I32, [_P, _P, _I64, _P, _I32, _P, _I32, _P, _P, _I32, _P, _I64, _P,
+                                                  C.POINTER(C.c_float)]),
     "cb_tc_train_create": (_I32, [C.POINTER(MlpDesc), _I32, _I32, C.POINTER(_P)]),
     "cb_tc_train_destroy": (None, [_P]),
     "cb_tc_train_ld": (_I32, [_P, _I32]),

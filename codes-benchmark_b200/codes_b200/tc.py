@@ -180,7 +180,7 @@ def multionet_grid_supported(model) -> bool:
     return bool(lib().cb_tc_multionet_grid_supported(C.byref(model.branch_net.chain().desc), model.N))
 
 
-def multionet_grid_forward(model, x0, trunk_rows, out, mode: int, dmin, dmax, pow10: bool):
+def multionet_grid_forward(model, x0, trunk_rows, out, mode: int, dmin, dmax, pow10: bool, phase_ms=None):
     """out[n*T + t, q] = denorm(sum_k branch(x0[n])[k] * trunk(trunk_rows[t])[k]) for every trajectory n and grid
     point t: branch once per trajectory (bf16 tensor cores), trunk once per grid point (fp32 chain), then the
     per-quantity contraction kernel writes the (N, T, Q) buffer ``out`` (fp32, contiguous) in one pass.
@@ -209,11 +209,16 @@ def multionet_grid_forward(model, x0, trunk_rows, out, mode: int, dmin, dmax, po
         need = int(lib().cb_tc_multionet_grid_workspace_bytes(plan.handle, n_traj, n_t))
         if plan.workspace is None or plan.workspace.numel() < need or plan.workspace.device != dev:
             plan.workspace = torch.empty(need, device=dev, dtype=torch.uint8)
-        check(lib().cb_tc_multionet_grid_forward(
-            plan.handle, C.c_void_p(x0.data_ptr()), n_traj, C.c_void_p(trunk_out.data_ptr()), n_t,
-            C.c_void_p(out.data_ptr()), int(mode), C.c_void_p(None if dmin is None else dmin.data_ptr()),
-            C.c_void_p(None if dmax is None else dmax.data_ptr()), int(bool(pow10)),
-            C.c_void_p(plan.workspace.data_ptr()), plan.workspace.numel(), stream), "tc_multionet_grid_forward")
+        args = (plan.handle, C.c_void_p(x0.data_ptr()), n_traj, C.c_void_p(trunk_out.data_ptr()), n_t,
+                C.c_void_p(out.data_ptr()), int(mode), C.c_void_p(None if dmin is None else dmin.data_ptr()),
+                C.c_void_p(None if dmax is None else dmax.data_ptr()), int(bool(pow10)),
+                C.c_void_p(plan.workspace.data_ptr()), plan.workspace.numel(), stream)
+        if phase_ms is None:
+            check(lib().cb_tc_multionet_grid_forward(*args), "tc_multionet_grid_forward")
+        else:   # bench.py roofline leg: per-kernel CUDA-event durations {pack, hidden chain, feature GEMM, grid kernel}
+            ms = (C.c_float * 4)()
+            check(lib().cb_tc_multionet_grid_forward_timed(*args, ms), "tc_multionet_grid_forward_timed")
+            phase_ms[:] = [float(v) for v in ms]
     return out
 
 

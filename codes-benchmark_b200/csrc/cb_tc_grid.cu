@@ -386,10 +386,33 @@ extern "C" int64_t cb_tc_multionet_grid_workspace_bytes(const cb_tc_grid* g, int
   return (int64_t)n_tchunks * g->Q * g->nkb * kTrTile + rows * (long long)(g->ld_h + g->ldF) * 2 + 4096;
 }
 
+static int32_t grid_forward_impl(cb_tc_grid* g, const float* d_x0, int64_t n_traj, const float* d_trunk_out, int32_t T,
+                                 float* d_y, int32_t mode, const float* d_min, const float* d_max, int32_t pow10,
+                                 void* d_workspace, int64_t workspace_bytes, void* stream, float* phase_ms);
+
 extern "C" int32_t cb_tc_multionet_grid_forward(cb_tc_grid* g, const float* d_x0, int64_t n_traj,
                                                 const float* d_trunk_out, int32_t T, float* d_y, int32_t mode,
                                                 const float* d_min, const float* d_max, int32_t pow10,
                                                 void* d_workspace, int64_t workspace_bytes, void* stream) {
+  return grid_forward_impl(g, d_x0, n_traj, d_trunk_out, T, d_y, mode, d_min, d_max, pow10, d_workspace, workspace_bytes,
+                           stream, nullptr);
+}
+
+// Measurement aid for bench.py: same launches with CUDA events recorded on `stream` around every kernel; synchronises
+// and returns the summed durations {trunk-tile pack, branch hidden chain, feature GEMM, grid kernel} in ms.
+extern "C" int32_t cb_tc_multionet_grid_forward_timed(cb_tc_grid* g, const float* d_x0, int64_t n_traj,
+                                                      const float* d_trunk_out, int32_t T, float* d_y, int32_t mode,
+                                                      const float* d_min, const float* d_max, int32_t pow10,
+                                                      void* d_workspace, int64_t workspace_bytes, void* stream,
+                                                      float* phase_ms) {
+  CB_CHECK_ARG(phase_ms != nullptr, "phase_ms is NULL");
+  return grid_forward_impl(g, d_x0, n_traj, d_trunk_out, T, d_y, mode, d_min, d_max, pow10, d_workspace, workspace_bytes,
+                           stream, phase_ms);
+}
+
+static int32_t grid_forward_impl(cb_tc_grid* g, const float* d_x0, int64_t n_traj, const float* d_trunk_out, int32_t T,
+                                 float* d_y, int32_t mode, const float* d_min, const float* d_max, int32_t pow10,
+                                 void* d_workspace, int64_t workspace_bytes, void* stream, float* phase_ms) {
   CB_CHECK_ARG(g != nullptr && g->weights_set, "grid plan: weights not set");
   CB_CHECK_ARG(n_traj >= 0 && T >= 1, "bad shape");
   if (n_traj == 0) return CB_OK;
@@ -403,6 +426,12 @@ extern "C" int32_t cb_tc_multionet_grid_forward(cb_tc_grid* g, const float* d_x0
   cudaStream_t st = (cudaStream_t)stream;
   const int n_tchunks = (T + kTChunk - 1) / kTChunk;
   const long long chunk = (long long)grid_chunk_tiles(n_tchunks) * kTileM;
+  // timed variant: one event before the first kernel and one after every kernel
+  constexpr int kMaxEv = 1 + 1 + 3 * 64;
+  cudaEvent_t ev[kMaxEv];
+  int n_ev = 0;
+  auto mark = [&]() { if (phase_ms && n_ev < kMaxEv) { cudaEventCreate(&ev[n_ev]); cudaEventRecord(ev[n_ev], st); ++n_ev; } };
+  mark();
   uintptr_t wsp = ((uintptr_t)d_workspace + 1023) & ~(uintptr_t)1023;
   __nv_bfloat16* trp = reinterpret_cast<__nv_bfloat16*>(wsp);
   const size_t trp_total = (size_t)n_tchunks * g->Q * g->nkb * kTrTile;
@@ -415,13 +444,16 @@ extern "C" int32_t cb_tc_multionet_grid_forward(cb_tc_grid* g, const float* d_x0
     if (blocks > 1184) blocks = 1184;
     pack_trunk_tiles_kernel<<<blocks, 256, 0, st>>>(d_trunk_out, T, g->n_out, g->Q, g->nkb, n_tchunks, trp);
     CB_LAUNCH_CHECK();
+    mark();
   }
   GridKernelFn fn = pick<1>(g->Q);
   const int d0 = g->branch.dims[0];
   for (long long n0 = 0; n0 < n_traj; n0 += chunk) {
     const long long n = (n_traj - n0) < chunk ? (n_traj - n0) : chunk;
     if (int32_t e = hidden_chain_launch(g->hidden, d_x0 + n0 * d0, n, hb, st)) return e;
+    mark();
     if (int32_t e = tcg::gemm_fwd_bf16(hb, n, g->ld_h, g->K + 1, g->d_wlast, g->wp_rows, g->Q * g->KQ, g->ldF, F, st)) return e;
+    mark();
     GridParams P;
     memset(&P, 0, sizeof(P));
     CB_CHECK_ARG(encode_bf16_box(&P.tmF, F, n, g->ldF, g->ldF, 64, kTileM), "tensor map of the features failed");
@@ -435,6 +467,17 @@ extern "C" int32_t cb_tc_multionet_grid_forward(cb_tc_grid* g, const float* d_x0
     const int grid = (int)(items < num_sms() ? items : num_sms());
     fn<<<grid, kGThreads, g->smem, st>>>(P);
     CB_LAUNCH_CHECK();
+    mark();
+  }
+  if (phase_ms) {
+    phase_ms[0] = phase_ms[1] = phase_ms[2] = phase_ms[3] = 0.f;
+    if (n_ev > 0) cudaEventSynchronize(ev[n_ev - 1]);
+    for (int i = 1; i < n_ev; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      phase_ms[i == 1 ? 0 : 1 + (i - 2) % 3] += ms;
+    }
+    for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
   }
   return CB_OK;
 }

@@ -328,6 +328,14 @@ CB_API int32_t cb_tc_multionet_grid_forward(cb_tc_grid* plan, const float* d_x0,
                                             const float* d_min, const float* d_max, int32_t pow10,
                                             void* d_workspace, int64_t workspace_bytes, void* stream);
 
+/* Measurement aid for bench.py: the same launches with CUDA events on `stream` around every kernel; synchronises
+ * and returns the summed durations {trunk-tile pack, branch hidden chain, feature GEMM, grid kernel} in ms. */
+CB_API int32_t cb_tc_multionet_grid_forward_timed(cb_tc_grid* plan, const float* d_x0, int64_t n_traj,
+                                                  const float* d_trunk_out, int32_t n_t, float* d_y, int32_t mode,
+                                                  const float* d_min, const float* d_max, int32_t pow10,
+                                                  void* d_workspace, int64_t workspace_bytes, void* stream,
+                                                  float* phase_ms);
+
 /* ------------------------------------------- tensor-core (bf16) TRAINING path */
 /* Forward + backward of a dense chain on tcgen05 (bf16 operands, fp32 accumulate), one GEMM launch per
  * layer and direction: replaces loss.backward() through nn.Linear / activations (fcnn.py:291,
