@@ -389,13 +389,13 @@ def run_ours(args):
     del dg
     with torch.inference_mode():
         for _ in range(3):
-            tc.multionet_grid_forward(model, x0_grid, t_grid, out_grid, 1, dmin, dmax, True)
+            tc.multionet_grid_forward(model, x0_grid, t_grid, out_grid, 1, dmin, dmax, True, trunk_tag="cfg2-grid")
         barrier()
         grid_passes = 10
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(grid_passes):
-            tc.multionet_grid_forward(model, x0_grid, t_grid, out_grid, 1, dmin, dmax, True)
+            tc.multionet_grid_forward(model, x0_grid, t_grid, out_grid, 1, dmin, dmax, True, trunk_tag="cfg2-grid")
         g1.record()
         barrier()
         grid_ms = torch.tensor([g0.elapsed_time(g1) / grid_passes], device=device)
@@ -406,7 +406,7 @@ def run_ours(args):
         if rank == 0:
             for _ in range(3):
                 ms = []
-                tc.multionet_grid_forward(model, x0_grid, t_grid, out_grid, 1, dmin, dmax, True, phase_ms=ms)
+                tc.multionet_grid_forward(model, x0_grid, t_grid, out_grid, 1, dmin, dmax, True, phase_ms=ms, trunk_tag="cfg2-grid")
                 grid_phases.append(ms)
     bytes_traj = 4 * (Q + T * Q)
     flop_traj_dedup = 2 * (MAC_BRANCH + T * 2842)

@@ -180,7 +180,8 @@ def multionet_grid_supported(model) -> bool:
     return bool(lib().cb_tc_multionet_grid_supported(C.byref(model.branch_net.chain().desc), model.N))
 
 
-def multionet_grid_forward(model, x0, trunk_rows, out, mode: int, dmin, dmax, pow10: bool, phase_ms=None):
+def multionet_grid_forward(model, x0, trunk_rows, out, mode: int, dmin, dmax, pow10: bool, phase_ms=None,
+                           trunk_tag=None):
     """out[n*T + t, q] = denorm(sum_k branch(x0[n])[k] * trunk(trunk_rows[t])[k]) for every trajectory n and grid
     point t: branch once per trajectory (bf16 tensor cores), trunk once per grid point (fp32 chain), then the
     per-quantity contraction kernel writes the (N, T, Q) buffer ``out`` (fp32, contiguous) in one pass.
@@ -204,8 +205,15 @@ def multionet_grid_forward(model, x0, trunk_rows, out, mode: int, dmin, dmax, po
             check(lib().cb_tc_multionet_grid_set_weights(plan.handle, ptr_array(_f32(bw)), ptr_array(_f32(bb)), stream),
                   "tc_multionet_grid_set_weights")
             plan.versions = versions
-        trunk_out = ops.mlp_chain(tspec, trunk_rows.float().contiguous(), [w.detach() for w in tw],
-                                  [b.detach() for b in tb])                    # (T, Q*f) fp32, exact path
+        # trunk outputs (T, Q*f), fp32 exact path: a function of the trunk weights and the time grid only, so they are
+        # kept until either changes (validate() / run_eval call predict() many times per set of weights)
+        # (``trunk_tag``: a hashable fingerprint of the grid's CONTENT supplied by the caller; None disables the cache)
+        tkey = None if trunk_tag is None else (_versions(tw) + _versions(tb), trunk_tag, tuple(trunk_rows.shape))
+        if tkey is None or getattr(plan, "trunk_key", None) != tkey:
+            plan.trunk_out = ops.mlp_chain(tspec, trunk_rows.float().contiguous(), [w.detach() for w in tw],
+                                           [b.detach() for b in tb])
+            plan.trunk_key = tkey
+        trunk_out = plan.trunk_out
         need = int(lib().cb_tc_multionet_grid_workspace_bytes(plan.handle, n_traj, n_t))
         if plan.workspace is None or plan.workspace.numel() < need or plan.workspace.device != dev:
             plan.workspace = torch.empty(need, device=dev, dtype=torch.uint8)

@@ -56,7 +56,16 @@ struct GridParams {
   int mode, pow10;             // de-normalisation: mode 1 = minmax
   const float* dmin; const float* dmax;
   int vec_ok;                  // (T*Q) % 4 == 0: every thread's 4*Q-float run is 16-byte aligned
+  long long* dbg;              // -DCB_GRID_DBG: cycle counters of CTA 0 (see grid_forward_impl)
 };
+
+#ifdef CB_GRID_DBG
+#define GCLK() clock64()
+#define GACC(slot, t0) do { if (P.dbg && blockIdx.x == 0 && lane == 0) atomicAdd((unsigned long long*)&P.dbg[slot], (unsigned long long)(clock64() - (t0))); } while (0)
+#else
+#define GCLK() 0ll
+#define GACC(slot, t0) do { (void)(t0); } while (0)
+#endif
 
 template <int Q>
 __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_constant__ GridParams P) {
@@ -64,7 +73,8 @@ __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_con
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t trp_s = base;                                           // trunk tiles of the current item
   const uint32_t a_s = base + ((P.trp_bytes + 1023) & ~1023);            // feature stages
-  const uint32_t ctrl = a_s + P.stages * kKBlockBytes;
+  const uint32_t stage_bytes = (uint32_t)P.nkb * kKBlockBytes;             // one stage = all k-blocks of one quantity
+  const uint32_t ctrl = a_s + P.stages * stage_bytes;
   const uint32_t bar_full = ctrl, bar_empty = ctrl + 8 * kGMaxStages;
   const uint32_t bar_trp = ctrl + 16 * kGMaxStages, bar_acc_full = bar_trp + 8, bar_acc_empty = bar_trp + 16;
   const uint32_t tmem_slot = bar_trp + 24;
@@ -79,7 +89,7 @@ __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_con
   }
   if (threadIdx.x < 2 * Q) {
     const int q = threadIdx.x % Q;
-    dn[threadIdx.x] = P.mode == 1 ? (threadIdx.x < Q ? __ldg(P.dmin + q) : __ldg(P.dmax + q)) : 0.f;
+    dn[threadIdx.x] = P.mode == 1 ? (threadIdx.x < Q ? __ldg(P.dmin + q) : __ldg(P.dmax + q) - __ldg(P.dmin + q)) : 0.f;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
@@ -97,13 +107,14 @@ __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_con
       int s = 0; uint32_t ph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int tile = item / P.n_tchunks;
-        for (int q = 0; q < Q; ++q)
-          for (int kb = 0; kb < P.nkb; ++kb) {
-            mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            mbar_arrive_expect_tx(bar_full + 8 * s, kKBlockBytes);
-            tma_load_2d(a_s + s * kKBlockBytes, &P.tmF, q * P.KQ + kb * kBlockK, tile * kTileM, bar_full + 8 * s);
-            if (++s == P.stages) { s = 0; ph ^= 1; }
-          }
+        for (int q = 0; q < Q; ++q) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
+          for (int kb = 0; kb < P.nkb; ++kb)
+            tma_load_2d(a_s + s * stage_bytes + kb * kKBlockBytes, &P.tmF, q * P.KQ + kb * kBlockK, tile * kTileM,
+                        bar_full + 8 * s);
+          if (++s == P.stages) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 2) {
@@ -125,40 +136,53 @@ __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_con
     // ---------------------------------------------------------------- MMA issuer
     const uint32_t idesc = make_idesc(kTChunk);
     int s = 0; uint32_t ph = 0; int it = 0;
+    const long long t_all = GCLK();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      long long tq = GCLK();
       mbar_wait(bar_trp, it & 1);
+      GACC(1, tq); tq = GCLK();
       if (it > 0) mbar_wait(bar_acc_empty, (it - 1) & 1);
+      GACC(2, tq);
       tcgen05_fence_after();
       for (int q = 0; q < Q; ++q) {
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(bar_full + 8 * s, ph);
-          tcgen05_fence_after();
-          if (elect_one()) {
+        tq = GCLK();
+        mbar_wait(bar_full + 8 * s, ph);
+        GACC(3, tq);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc0 = make_smem_desc(a_s + s * stage_bytes);
+          const uint64_t bdesc0 = make_smem_desc(trp_s + q * P.nkb * kTrTile);
+          const uint32_t d_tmem = tmem_base + q * kTChunk;
+          for (int kb = 0; kb < P.nkb; ++kb) {
             const int nks = (kb == P.nkb - 1) ? P.last_nks : 4;
-            const uint64_t adesc = make_smem_desc(a_s + s * kKBlockBytes);
-            const uint64_t bdesc = make_smem_desc(trp_s + (q * P.nkb + kb) * kTrTile);
+            const uint64_t adesc = adesc0 + (uint64_t)(kb * (kKBlockBytes >> 4));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(kb * (kTrTile >> 4));
+#pragma unroll 4
             for (int ks = 0; ks < nks; ++ks)
-              umma_bf16(tmem_base + q * kTChunk, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc,
-                        (kb | ks) != 0 ? 1u : 0u);
-            umma_commit(bar_empty + 8 * s);
+              umma_bf16(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
           }
-          __syncwarp();
-          if (++s == P.stages) { s = 0; ph ^= 1; }
+          umma_commit(bar_empty + 8 * s);
         }
+        __syncwarp();
+        if (++s == P.stages) { s = 0; ph ^= 1; }
       }
       if (elect_one()) umma_commit(bar_acc_full);
       __syncwarp();
     }
+    GACC(0, t_all);
+    if (P.dbg && blockIdx.x == 0 && lane == 0) P.dbg[7] = it;
   } else {
     // ---------------------------------------------------------------- epilogue: TMEM -> de-normalise -> (n, T, Q)
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = (warp - 3) >> 2;             // grid points [8*half, 8*half + 8) of the item's 16
     const float LOG2_10 = 3.3219280948873623f;
-    (void)LOG2_10;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int tile = item / P.n_tchunks, c = item % P.n_tchunks;
+      long long tq = GCLK();
       mbar_wait(bar_acc_full, it & 1);
+      if (warp == 3) GACC(4, tq);
+      tq = GCLK();
       tcgen05_fence_after();
       const long long n = (long long)tile * kTileM + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -179,12 +203,12 @@ __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_con
         if (P.mode == 1 || P.pow10) {
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
-            const float lo = dn[q], hi = dn[Q + q];
+            const float lo = dn[q], span = dn[Q + q];
 #pragma unroll
             for (int tt = 0; tt < 4; ++tt) {
               float x = v[tt * Q + q];
-              if (P.mode == 1) x = (x + 1.f) * (hi - lo) / 2.f + lo;      // abstract_surrogate.py:468 op order
-              if (P.pow10) x = exp10f(x);
+              if (P.mode == 1) x = (x + 1.f) * span / 2.f + lo;           // abstract_surrogate.py:468 op order
+              if (P.pow10) x = exp2f(x * LOG2_10);                          // 10**x; rel. error <= 2e-6 for |x| <= 38
               v[tt * Q + q] = x;
             }
           }
@@ -205,6 +229,7 @@ __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_con
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty);
+      if (warp == 3) GACC(5, tq);
     }
   }
   tcgen05_fence_before();
@@ -297,10 +322,11 @@ static bool grid_shape(const cb_mlp_desc* b, int Q, int* KQ, int* nkb, int* last
 
 static bool grid_smem(int Q, int nkb, int* stages, size_t* smem) {
   const long long trp = ((long long)Q * nkb * kTrTile + 1023) / 1024 * 1024;
-  long long st = ((long long)kMaxSmem - 1024 - trp - kGCtrl - 2 * kGMaxQ * 4) / kKBlockBytes;
+  const long long stage = (long long)nkb * kKBlockBytes;
+  long long st = ((long long)kMaxSmem - 1024 - trp - kGCtrl - 2 * kGMaxQ * 4) / stage;
   if (st > kGMaxStages) st = kGMaxStages;
   *stages = (int)st;
-  *smem = (size_t)(1024 + trp + (st > 0 ? st : 0) * kKBlockBytes + kGCtrl + 2 * kGMaxQ * 4);
+  *smem = (size_t)(1024 + trp + (st > 0 ? st : 0) * stage + kGCtrl + 2 * kGMaxQ * 4);
   return st >= 2;
 }
 
@@ -465,8 +491,23 @@ static int32_t grid_forward_impl(cb_tc_grid* g, const float* d_x0, int64_t n_tra
     P.vec_ok = (((long long)T * g->Q) % 4 == 0) && (((uintptr_t)P.y & 15) == 0);
     const long long items = (long long)P.n_tiles * n_tchunks;
     const int grid = (int)(items < num_sms() ? items : num_sms());
+#ifdef CB_GRID_DBG
+    P.dbg = nullptr;
+    if (getenv("CB_GRID_DBG")) { CB_CUDA(cudaMalloc(&P.dbg, 64)); CB_CUDA(cudaMemsetAsync(P.dbg, 0, 64, st)); }
+#endif
     fn<<<grid, kGThreads, g->smem, st>>>(P);
     CB_LAUNCH_CHECK();
+#ifdef CB_GRID_DBG
+    if (P.dbg) {
+      long long h[8];
+      CB_CUDA(cudaStreamSynchronize(st));
+      CB_CUDA(cudaMemcpy(h, P.dbg, 64, cudaMemcpyDeviceToHost));
+      cudaFree(P.dbg);
+      fprintf(stderr, "[grid dbg] CTA 0, %lld items: MMA warp total %lld cycles: wait trunk tiles %lld, wait TMEM drained %lld, "
+                      "wait feature stage %lld | epilogue warp 3: wait accumulators %lld, work %lld\n",
+              h[7], h[0], h[1], h[2], h[3], h[4], h[5]);
+    }
+#endif
     mark();
   }
   if (phase_ms) {
