@@ -396,7 +396,8 @@ def denormalize(x: Tensor, mode: int, dmin: Tensor | None, dmax: Tensor | None, 
 
 
 # --------------------------------------------------------------------------- latent ODE solve
-TAPE_CAP = 96   # accepted steps recorded per trajectory for the backward sweep
+TAPE_CAP = 96        # initial capacity (accepted steps per trajectory) of the tape the backward sweep consumes
+TAPE_CAP_MAX = 16384  # the forward re-runs with a doubled tape until every trajectory fits, up to this many steps
 
 
 def _lnode_desc(spec: ChainSpec, tanh_reg: bool, reg_factor: float, rtol: float, atol: float, max_steps: int,
@@ -412,7 +413,7 @@ def _lnode_desc(spec: ChainSpec, tanh_reg: bool, reg_factor: float, rtol: float,
 
 def lnode_solve(spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor, tanh_reg: bool, reg_factor: float,
                 rtol: float, atol: float, max_steps: int = 100000, return_stats: bool = False, record_tape: bool = False,
-                n_err: int = 0):
+                n_err: int = 0, tape_cap: int | None = None):
     """Adaptive Tsit5 solve of dz/dt = ODE-net(z); z0:(B,L) -> (B,T,L) fp32.
     ``record_tape`` additionally returns the accepted-step record the backward sweep consumes."""
     _require_cuda(z0, t_eval)
@@ -432,7 +433,7 @@ def lnode_solve(spec: ChainSpec, weights, biases, z0: Tensor, t_eval: Tensor, ta
     bl = [_f32c(b.detach()) for b in biases]
     tape = tape_bufs = None
     if record_tape:
-        cap = TAPE_CAP
+        cap = int(tape_cap or TAPE_CAP)
         tape_bufs = (torch.empty(B, device=dev, dtype=torch.int32),
                      torch.empty((B, cap), device=dev, dtype=torch.float64),
                      torch.empty((B, cap), device=dev, dtype=torch.float64),
@@ -587,8 +588,22 @@ class _LnodeSolveFn(torch.autograd.Function):
         cfg = wrapper.config
         reg = float(reg_factor.detach()) if cfg.ode_tanh_reg else 1.0
         need_grad = any(ctx.needs_input_grad)
-        res = lnode_solve(spec, weights, biases, z0.detach(), t_eval, cfg.ode_tanh_reg, reg, cfg.rtol, cfg.atol,
-                          return_stats=True, record_tape=need_grad, n_err=n_err)
+        # torchode's AutoDiffAdjoint has no step limit (latent_neural_ode.py:469): the tape of accepted steps grows on
+        # demand -- when a trajectory needed more than `cap` accepted steps the forward is re-run with twice the
+        # capacity, and the capacity found is remembered on the wrapper for the following training steps
+        cap = max(TAPE_CAP, int(wrapper.__dict__.get("_tape_cap", TAPE_CAP)))
+        while True:
+            res = lnode_solve(spec, weights, biases, z0.detach(), t_eval, cfg.ode_tanh_reg, reg, cfg.rtol, cfg.atol,
+                              return_stats=True, record_tape=need_grad, n_err=n_err, tape_cap=cap)
+            if not need_grad or int(res[2][0].min()) >= 0:      # (one host read per training step, as before)
+                break
+            if int(res[1][:, 0].min()) < 0:
+                raise RuntimeError("latent ODE solve: a trajectory did not reach t_end within max_steps Runge-Kutta "
+                                   "steps (step-size collapse); no gradient can be formed")
+            if cap >= TAPE_CAP_MAX:
+                raise RuntimeError(f"latent ODE backward: a trajectory needed more than {TAPE_CAP_MAX} accepted steps")
+            cap *= 2
+        wrapper.__dict__["_tape_cap"] = cap
         out, stats = res[0], res[1]
         wrapper.last_solver_stats = stats
         if need_grad:
@@ -602,9 +617,6 @@ class _LnodeSolveFn(torch.autograd.Function):
         t_eval, *rest = ctx.saved_tensors
         tape, params = rest[:5], rest[5:]
         n, cfg = ctx.n, ctx.cfg
-        if int(tape[0].min()) < 0:
-            raise RuntimeError(f"latent ODE backward: a trajectory needed more than {TAPE_CAP} accepted steps "
-                               "(tape overflow) or did not finish")
         d = _lnode_desc(ctx.spec, cfg.ode_tanh_reg, ctx.reg, cfg.rtol, cfg.atol, 1, ctx.n_err)
         if not FORCE_WIDE_LNODE_BACKWARD and lib().cb_lnode_bwd_supported(C.byref(d), int(t_eval.shape[0])):
             dz0, dW, db, dreg = lnode_solve_backward(ctx.spec, params[:n], params[n:], t_eval, tape, dz,

@@ -351,3 +351,28 @@ def test_best_checkpoint_is_reloaded(tmp_path, monkeypatch):
     for k, v in m.state_dict().items():
         assert torch.equal(v, good[k]), k
     assert m.best_epoch == 5
+
+
+# --------------------------------------------------------------------------------------- LNODE tape growth
+def test_lnode_tape_grows_on_overflow(monkeypatch):
+    """The accepted-step tape has no fixed limit (torchode's AutoDiffAdjoint has none): with an initial capacity of
+    2 steps the forward re-runs with a doubled tape until every trajectory fits; gradients equal the large-tape run."""
+    import codes_b200 as cb
+    from codes_b200 import ops
+    d = np.random.default_rng(3).uniform(-1, 1, (16, 12, 5)).astype(np.float32)
+
+    def grads(cap):
+        monkeypatch.setattr(ops, "TAPE_CAP", cap)
+        torch.manual_seed(11)
+        m = cb.LatentNeuralODE(DEV, 5, 12, 0, None, {"coder_width": 16, "ode_width": 16, "rtol": 1e-7, "atol": 1e-7})
+        loader, _, _ = m.prepare_data(d, None, None, np.linspace(0, 1, 12), 16, shuffle=False)
+        batch = next(iter(loader))
+        pred, x = m(batch)
+        m.model.total_loss(x, pred, None, nn.MSELoss()).backward()
+        steps = int(m.model.last_solver_stats[:, 1].max())
+        return torch.cat([p.grad.flatten() for p in m.parameters()]), steps, m.model._tape_cap
+
+    g_small, steps, cap_found = grads(2)
+    g_big, _, cap_big = grads(256)
+    assert steps > 2 and cap_found >= steps and cap_big == 256
+    assert torch.equal(g_small, g_big)
