@@ -240,13 +240,25 @@ __global__ void latent_loss_kernel(const float* __restrict__ xhat, const float* 
 
 // --------------------------------------------------------------- optimizers
 constexpr int kMaxTensors = 48;
+constexpr int kOptChunk = 2048;          // elements per CTA: 8 independent elements per thread (32 loads in flight)
 struct TensorList {
   float* p[kMaxTensors];
   const float* g[kMaxTensors];
   float* s1[kMaxTensors];
   float* s2[kMaxTensors];
   int64_t n[kMaxTensors];
+  int chunk0[kMaxTensors + 1];           // first chunk (= blockIdx.x) of tensor t; the grid is the total chunk count,
+  int count;                             // so every CTA has work however unequal the tensors are
 };
+
+// tensor and element range of this CTA's chunk
+__device__ __forceinline__ int locate_chunk(const TensorList& tl, int64_t& i0, int64_t& i1) {
+  int t = 0;
+  while (t + 1 < tl.count && (int)blockIdx.x >= tl.chunk0[t + 1]) ++t;
+  i0 = (int64_t)((int)blockIdx.x - tl.chunk0[t]) * kOptChunk;
+  i1 = min(tl.n[t], i0 + kOptChunk);
+  return t;
+}
 
 // Every optimizer kernel can take its scalars from DEVICE memory (`dev`, same field order as the by-value
 // struct): a training step captured in a CUDA graph keeps replaying while the host only rewrites those
@@ -255,14 +267,16 @@ struct AdamArgs { float lr, b1, b2, eps, wd, bc1, bc2_sqrt; };
 __global__ void adamw_kernel(const TensorList tl, const AdamArgs a0, const float* __restrict__ dev) {
   AdamArgs a = a0;
   if (dev) { a.lr = dev[0]; a.b1 = dev[1]; a.b2 = dev[2]; a.eps = dev[3]; a.wd = dev[4]; a.bc1 = dev[5]; a.bc2_sqrt = dev[6]; }
-  const int t = blockIdx.y;
-  const int64_t n = tl.n[t];
+  int64_t i0, i1;
+  const int t = locate_chunk(tl, i0, i1);
   float* __restrict__ p = tl.p[t];
   const float* __restrict__ g = tl.g[t];
   float* __restrict__ m = tl.s1[t];
   float* __restrict__ v = tl.s2[t];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+  for (int j = 0; j < kOptChunk / kThreads; ++j) {
+    const int64_t i = i0 + j * kThreads + threadIdx.x;
+    if (i >= i1) break;
     // torch.optim.AdamW (single-tensor formulation)
     float pv = p[i] * (1.f - a.lr * a.wd);
     const float gv = g[i];
@@ -278,13 +292,15 @@ struct SgdArgs { float lr, momentum, wd; int first; };
 __global__ void sgd_kernel(const TensorList tl, const SgdArgs a0, const float* __restrict__ dev) {
   SgdArgs a = a0;
   if (dev) { a.lr = dev[0]; a.momentum = dev[1]; a.wd = dev[2]; a.first = dev[3] != 0.f; }
-  const int t = blockIdx.y;
-  const int64_t n = tl.n[t];
+  int64_t i0, i1;
+  const int t = locate_chunk(tl, i0, i1);
   float* __restrict__ p = tl.p[t];
   const float* __restrict__ g = tl.g[t];
   float* __restrict__ buf = tl.s1[t];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+  for (int j = 0; j < kOptChunk / kThreads; ++j) {
+    const int64_t i = i0 + j * kThreads + threadIdx.x;
+    if (i >= i1) break;
     float gv = g[i] + a.wd * p[i];
     if (a.momentum != 0.f) {
       gv = a.first ? gv : a.momentum * buf[i] + gv;
@@ -298,14 +314,16 @@ struct SfArgs { float lr, beta1, b2, eps, wd, ckp1, bc2; int adam; };
 __global__ void schedulefree_kernel(const TensorList tl, const SfArgs a0, const float* __restrict__ dev) {
   SfArgs a = a0;
   if (dev) { a.lr = dev[0]; a.beta1 = dev[1]; a.b2 = dev[2]; a.eps = dev[3]; a.wd = dev[4]; a.ckp1 = dev[5]; a.bc2 = dev[6]; }
-  const int t = blockIdx.y;
-  const int64_t n = tl.n[t];
+  int64_t i0, i1;
+  const int t = locate_chunk(tl, i0, i1);
   float* __restrict__ y = tl.p[t];
   const float* __restrict__ g = tl.g[t];
   float* __restrict__ z = tl.s1[t];
   float* __restrict__ v = tl.s2[t];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+  for (int j = 0; j < kOptChunk / kThreads; ++j) {
+    const int64_t i = i0 + j * kThreads + threadIdx.x;
+    if (i >= i1) break;
     float yv = y[i], zv = z[i], gn = g[i];
     if (a.adam) {
       const float vv = a.b2 * v[i] + (1.f - a.b2) * gn * gn;
@@ -321,25 +339,17 @@ __global__ void schedulefree_kernel(const TensorList tl, const SfArgs a0, const 
 }
 
 __global__ void lerp_kernel(const TensorList tl, float w) {
-  const int t = blockIdx.y;
-  const int64_t n = tl.n[t];
+  int64_t i0, i1;
+  const int t = locate_chunk(tl, i0, i1);
   float* __restrict__ p = tl.p[t];
   const float* __restrict__ z = tl.s1[t];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+  for (int j = 0; j < kOptChunk / kThreads; ++j) {
+    const int64_t i = i0 + j * kThreads + threadIdx.x;
+    if (i >= i1) break;
     const float pv = p[i];
     p[i] = pv + w * (z[i] - pv);  // torch.lerp(p, z, w)
   }
-}
-
-static int tensor_grid_x(const int64_t* sizes, int n) {
-  int64_t mx = 1;
-  for (int i = 0; i < n; ++i) mx = sizes[i] > mx ? sizes[i] : mx;
-  int64_t b = (mx + kThreads * 4 - 1) / (kThreads * 4);
-  const int64_t cap = (int64_t)num_sms() * 4 / (n > 0 ? (n < 8 ? n : 8) : 1) + 1;   // ~4 CTAs per SM over the big tensors
-  if (b > cap) b = cap;
-  if (b < 1) b = 1;
-  return (int)b;
 }
 
 // --------------------------------------------------------------- batch gather (device-resident loaders)
@@ -590,7 +600,15 @@ static int32_t for_tensor_chunks(float* const* p, const float* const* g, float* 
       tl.n[i] = sizes[c0 + i];
       CB_CHECK_ARG(tl.p[i] != nullptr && tl.n[i] >= 0, "bad tensor %d", c0 + i);
     }
-    dim3 grid(tensor_grid_x(sizes + c0, cnt), cnt);
+    int chunks = 0;
+    for (int i = 0; i < cnt; ++i) {
+      tl.chunk0[i] = chunks;
+      chunks += (int)((tl.n[i] + kOptChunk - 1) / kOptChunk);
+    }
+    tl.chunk0[cnt] = chunks;
+    tl.count = cnt;
+    if (chunks == 0) continue;
+    dim3 grid(chunks);
     launch(tl, grid);
     CB_LAUNCH_CHECK();
   }
