@@ -282,6 +282,17 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
     if world > 1:
+        # one process per GPU on one host: give every rank its own slice of the host cores (the launch loops, the
+        # pinned-memory copies and torch's intra-op pool of eight ranks otherwise share -- and oversubscribe -- the
+        # same cores; round 1's N=8 end-to-end leg lost 15 % to that)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+            torch.set_num_threads(max(1, len(mine)))
+        except (AttributeError, OSError):
+            pass
         dist.init_process_group("nccl", device_id=torch.device(device))
     cb.set_precision("bf16")
     model = build_model(device)
@@ -481,6 +492,49 @@ def run_ours(args):
     e2e["row_path_value"] = world * 2 * n_e2e / float(dt_rows.item())
     del p, t
 
+    # ---- strong-scaling leg (ALL ranks): the FIXED 65 536-trajectory cfg2 test set split by trajectory over the
+    # ranks (codes_b200/parallel.py): every rank runs predict() on its block, then ONE all_reduce of the error sums
+    # (+ one of the maximum) gives the global metrics -- the design's only data-path collective; the
+    # gather variant moves the (N,T,Q) prediction and target blocks with all_gather_into_tensor over NVLink.
+    from codes_b200 import parallel
+    strong = None
+    if not args.no_strong:
+        n_strong = 65536
+        ds_full = synthetic_x0(n_strong, seed=555)              # identical on every rank
+        tgrid = np.linspace(0, 1, T)
+        sh_loader = parallel.shard_loader(model, ds_full, tgrid, ROWS_PER_STEP)
+        for _ in range(3):
+            p, t, _ = parallel.sharded_predict(model, ds_full, tgrid, ROWS_PER_STEP, gather=False, loader=sh_loader)
+            parallel.sharded_error_metrics(p, t)
+        barrier()
+        n_rep = 5
+        t0 = time.perf_counter()
+        for _ in range(n_rep):
+            p = t = None
+            p, t, _ = parallel.sharded_predict(model, ds_full, tgrid, ROWS_PER_STEP, gather=False, loader=sh_loader)
+            metrics = parallel.sharded_error_metrics(p, t)
+        torch.cuda.synchronize()
+        dt_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_s, op=dist.ReduceOp.MAX)
+        p = t = None
+        barrier()
+        g0 = time.perf_counter()
+        pg, tg_ = parallel.sharded_predict(model, ds_full, tgrid, ROWS_PER_STEP, gather=True, loader=sh_loader)
+        torch.cuda.synchronize()
+        dt_g = torch.tensor([time.perf_counter() - g0], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_g, op=dist.ReduceOp.MAX)
+        strong = {"value": n_rep * n_strong / float(dt_s.item()), "unit": "trajectories/s", "scaling": "strong",
+                  "trajectories": n_strong, "ms_per_pass": float(dt_s.item()) / n_rep * 1e3,
+                  "collective": "all_reduce of 4 error sums + all_reduce(max) per pass (NCCL)" if world > 1 else "none (1 rank)",
+                  "metrics": metrics, "gather_pass_ms": float(dt_g.item()) * 1e3,
+                  "gather_bytes": int(2 * n_strong * T * Q * 4),
+                  "what": "parallel.sharded_predict(gather=False) + sharded_error_metrics on the fixed 65536-trajectory "
+                          "test set, host loader, H2D inside; gather_pass_ms: one pass with all_gather_into_tensor of "
+                          "predictions and targets to every rank"}
+        del pg, tg_, ds_full, sh_loader
+
     # ---- training leg (ALL ranks, independent models = the benchmark's task parallelism): steady-state fit
     # step (forward, loss, backward, AdamW) of the same MultiONet config, bf16 tensor-core training mode
     train = None
@@ -565,7 +619,7 @@ def run_ours(args):
                        "resident_batches": n_batches, "l2_policy": "inputs larger than L2 (rotating batches)",
                        "streams": "batches alternate between two CUDA streams (as in predict()); timed from the first launch to the join of both",
                        "precision": "bf16 operands, fp32 accumulate (tcgen05)", "parallelism": f"trajectory-sharded x{world}"},
-            "clocks": clocks.summary(), "e2e": e2e, "dedup": dedup, "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": clocks.summary(), "e2e": e2e, "dedup": dedup, "strong": strong, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "reference_gpu": reference_gpu, "train": train,
         }
         print(json.dumps(line), flush=True)
@@ -580,6 +634,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (sharded predict + collective) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true",
                     help="skip the host-side cpu_baseline leg (profiling runs under ncu only)")
     args = ap.parse_args()

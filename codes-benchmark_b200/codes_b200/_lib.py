@@ -72,6 +72,8 @@ _SIGNATURES = {
     "cb_poly_eval_batched_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _P]),
     "cb_poly_eval_batched_bwd": (_I32, [_P, _P, _I64, _I32, _I32, _I32, _P, _P, _P]),
     "cb_pointwise_loss": (_I32, [_P, _P, _I64, _I32, _F, _P, _P, _P, _I64, _P]),
+    "cb_error_sums_workspace_doubles": (_I64, []),
+    "cb_error_sums": (_I32, [_P, _P, _I64, _P, _P, _I64, _P]),
     "cb_latent_loss_fwd_bwd": (_I32, [_P, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _F, _P, _P, _P, _I64, _P]),
     "cb_adamw_step": (_I32, [_PP, _PP, _PP, _PP, C.POINTER(_I64), _I32, _F, _F, _F, _F, _F, _I64, _P]),
     "cb_sgd_step": (_I32, [_PP, _PP, _PP, C.POINTER(_I64), _I32, _F, _F, _F, _I64, _P]),

@@ -363,6 +363,19 @@ def latent_traj_loss(x_hat: Tensor, x: Tensor, n_timesteps_h: int, kind: str, w0
                             False)[0]
 
 
+def error_sums(pred: Tensor, target: Tensor) -> Tensor:
+    """(4,) float64 on the device: {sum |e|, sum e^2, sum |e|/|t|, max |e|}, e = pred - target (one fused pass)."""
+    _require_cuda(pred, target)
+    p, t = _f32c(pred), _f32c(target)
+    dev = p.device
+    out = torch.empty(4, device=dev, dtype=torch.float64)
+    wsd = int(lib().cb_error_sums_workspace_doubles())
+    ws = torch.empty(wsd, device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        check(lib().cb_error_sums(_p(p), _p(t), p.numel(), _p(out), _p(ws), wsd, _stream(p)), "error_sums")
+    return out
+
+
 # --------------------------------------------------------------------------- batch gather
 def gather_rows(src: Tensor, idx: Tensor) -> Tensor:
     """src[idx] along dim 0 for a device-resident fp32 dataset (idx: int64 on the same device)."""

@@ -26,19 +26,30 @@ def _world(group=None) -> tuple[int, int]:
     return 0, 1
 
 
+def shard_loader(model, dataset: np.ndarray, timesteps: np.ndarray, batch_size: int, group=None):
+    """This rank's un-shuffled loader over its contiguous block of trajectories (None if the block is empty)."""
+    rank, world = _world(group)
+    lo, hi = shard_bounds(dataset.shape[0], rank, world)
+    if hi <= lo:
+        return None
+    return model.prepare_data(dataset[lo:hi], None, dataset[lo:hi], timesteps, batch_size, shuffle=False)[2]
+
+
 def sharded_predict(model, dataset: np.ndarray, timesteps: np.ndarray, batch_size: int, leave_log: bool = False,
-                    leave_norm: bool = False, gather: bool = True, group=None):
+                    leave_norm: bool = False, gather: bool = True, group=None, loader=None):
     """predict() of ``dataset`` (N,T,Q) split by trajectory over the ranks of ``group``.
 
     Returns (predictions, targets): the full (N,T,Q) tensors on every rank when ``gather`` is
     True (one all_gather of the padded blocks), else this rank's block and its [lo, hi) bounds.
+    ``loader``: this rank's loader from ``shard_loader`` (evaluation loops call predict many times on one test set).
     """
     rank, world = _world(group)
     n = dataset.shape[0]
     lo, hi = shard_bounds(n, rank, world)
     block = max(hi - lo, 0)
     if block > 0:
-        _, _, loader = model.prepare_data(dataset[lo:hi], None, dataset[lo:hi], timesteps, batch_size, shuffle=False)
+        if loader is None:
+            loader = shard_loader(model, dataset, timesteps, batch_size, group)
         preds, targs = model.predict(loader, leave_log=leave_log, leave_norm=leave_norm)
     else:  # more ranks than trajectories
         t, q = dataset.shape[1], dataset.shape[2]
@@ -64,15 +75,26 @@ def sharded_error_metrics(preds: torch.Tensor, targs: torch.Tensor, group=None) 
     """Global error metrics from per-rank blocks with ONE all_reduce of a small tensor
     (sum |e|, sum e^2, sum |e|/|t|, count): the metric math of bench_fcts.py:243-271 without moving
     the (N,T,Q) predictions off the rank that produced them."""
-    err = (preds - targs).double()
-    stats = torch.stack([err.abs().sum(), (err * err).sum(),
-                         (err.abs() / targs.double().abs().clamp_min(1e-300)).sum(),
-                         torch.tensor(float(err.numel()), dtype=torch.float64, device=err.device)])
+    if preds.is_cuda:
+        # one fused pass on the device (cb_error_sums: fp64 accumulation, deterministic) instead of four eager
+        # reductions over temporaries of the size of the predictions
+        from . import ops
+        sums = ops.error_sums(preds, targs)
+        stats = torch.cat([sums[:3], torch.tensor([float(preds.numel())], dtype=torch.float64, device=preds.device)])
+        emax = sums[3:4].clone()
+    else:   # CPU tensors: only the gloo tests of the host logic come here
+        err = (preds - targs).double()
+        stats = torch.stack([err.abs().sum(), (err * err).sum(),
+                             (err.abs() / targs.double().abs().clamp_min(1e-300)).sum(),
+                             torch.tensor(float(err.numel()), dtype=torch.float64)])
+        emax = err.abs().max().reshape(1) if err.numel() else torch.zeros(1, dtype=torch.float64)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(emax, op=dist.ReduceOp.MAX, group=group)
     s_abs, s_sq, s_rel, cnt = (float(v) for v in stats.cpu())
     cnt = max(cnt, 1.0)
-    return {"MAE": s_abs / cnt, "RMSE": (s_sq / cnt) ** 0.5, "MRE": s_rel / cnt, "count": int(cnt)}
+    return {"MAE": s_abs / cnt, "RMSE": (s_sq / cnt) ** 0.5, "MRE": s_rel / cnt, "max_abs": float(emax.cpu()[0]),
+            "count": int(cnt)}
 
 
 def ensemble_mean_std(member_preds: list[torch.Tensor]) -> tuple[torch.Tensor, torch.Tensor]:

@@ -372,6 +372,50 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int64_t*
   }
 }
 
+// --------------------------------------------------------------- error metrics (evaluation)
+// part[b][0..3] = {sum |e|, sum e^2, sum |e|/max(|t|, tiny), max |e|} over this CTA's elements, e = pred - target,
+// accumulated in fp64 per thread, fixed shuffle tree per CTA; error_sums_final_kernel adds the CTAs in index order.
+__global__ void error_sums_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, int64_t n,
+                                  double* __restrict__ part) {
+  double s_abs = 0.0, s_sq = 0.0, s_rel = 0.0, s_max = 0.0;
+  const int64_t n4 = (((uintptr_t)pred | (uintptr_t)tgt) & 15) == 0 ? n / 4 : 0;
+  const float4* p4 = reinterpret_cast<const float4*>(pred);
+  const float4* t4 = reinterpret_cast<const float4*>(tgt);
+  auto acc = [&](float p, float t) {
+    const double e = fabs((double)p - (double)t);
+    s_abs += e; s_sq += e * e; s_rel += e / fmax(fabs((double)t), 1e-300); s_max = fmax(s_max, e);
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(p4 + i), b = __ldg(t4 + i);
+    acc(a.x, b.x); acc(a.y, b.y); acc(a.z, b.z); acc(a.w, b.w);
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc(__ldg(pred + i), __ldg(tgt + i));
+  __shared__ double sm[4][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s_abs += __shfl_down_sync(0xffffffffu, s_abs, o);
+    s_sq += __shfl_down_sync(0xffffffffu, s_sq, o);
+    s_rel += __shfl_down_sync(0xffffffffu, s_rel, o);
+    s_max = fmax(s_max, __shfl_down_sync(0xffffffffu, s_max, o));
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sm[0][w] = s_abs; sm[1][w] = s_sq; sm[2][w] = s_rel; sm[3][w] = s_max; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double r = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r = threadIdx.x == 3 ? fmax(r, sm[3][i]) : r + sm[threadIdx.x][i];
+    part[(size_t)blockIdx.x * 4 + threadIdx.x] = r;
+  }
+}
+__global__ void error_sums_final_kernel(const double* __restrict__ part, int blocks, double* __restrict__ out) {
+  if (threadIdx.x < 4) {
+    double r = 0.0;
+    for (int b = 0; b < blocks; ++b) r = threadIdx.x == 3 ? fmax(r, part[(size_t)b * 4 + 3]) : r + part[(size_t)b * 4 + threadIdx.x];
+    out[threadIdx.x] = r;
+  }
+}
+
 // --------------------------------------------------------------- denormalise
 __global__ void denorm_kernel(const float* __restrict__ x, int64_t total, int Q, int mode,
                               const float* __restrict__ dmin, const float* __restrict__ dmax,
@@ -548,6 +592,25 @@ extern "C" int32_t cb_pointwise_loss(const float* d_pred, const float* d_target,
   pointwise_loss_kernel<<<blocks, kThreads, 0, st>>>(d_pred, d_target, n, kind, scale * inv_n, d_ws, d_dpred);
   CB_LAUNCH_CHECK();
   final_sum_kernel<<<1, 256, 0, st>>>(d_ws, blocks, scale * inv_n, d_loss);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int64_t cb_error_sums_workspace_doubles(void) { return (int64_t)num_sms() * 8 * 4; }
+
+extern "C" int32_t cb_error_sums(const float* d_pred, const float* d_target, int64_t n, double* d_out4,
+                                 double* d_ws, int64_t ws_doubles, void* stream) {
+  CB_CHECK_ARG(d_pred && d_target && d_out4 && d_ws, "NULL pointer argument");
+  CB_CHECK_ARG(n >= 0, "n < 0");
+  const int blocks = grid_for(n > 0 ? n : 1, 16);
+  if (ws_doubles < (int64_t)blocks * 4) {
+    set_error("workspace too small: need %d doubles", blocks * 4);
+    return CB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  error_sums_kernel<<<blocks, kThreads, 0, st>>>(d_pred, d_target, n, d_ws);
+  CB_LAUNCH_CHECK();
+  error_sums_final_kernel<<<1, 32, 0, st>>>(d_ws, blocks, d_out4);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

@@ -161,6 +161,15 @@ CB_API int32_t cb_latent_loss_fwd_bwd(const float* d_xhat, const float* d_x, int
                                float w3, float* d_loss, float* d_dxhat, float* d_workspace,
                                int64_t workspace_floats, void* stream);
 
+/* Evaluation error sums on the device (the metric math of bench_fcts.py:243-271 and the L1 of
+ * abstract_surrogate.py:704-709 without moving (N,T,Q) tensors to the host): d_out4 = {sum |e|, sum e^2,
+ * sum |e|/|t|, max |e|} with e = pred - target over n elements, fp64 accumulation, fixed-order reduction
+ * (deterministic).  With several GPUs each rank reduces its own shard and ONE all_reduce of these four numbers
+ * gives the global MAE / RMSE / MRE (codes_b200/parallel.py). */
+CB_API int64_t cb_error_sums_workspace_doubles(void);
+CB_API int32_t cb_error_sums(const float* d_pred, const float* d_target, int64_t n, double* d_out4,
+                             double* d_workspace, int64_t workspace_doubles, void* stream);
+
 /* --------------------------------------------------------------- optimizers */
 /* Multi-tensor updates over a flat list (abstract_surrogate.py:773-811).
  * d_p/d_g/... are host arrays of device pointers, sizes[] element counts. */
