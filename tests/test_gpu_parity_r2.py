@@ -376,3 +376,20 @@ def test_lnode_tape_grows_on_overflow(monkeypatch):
     g_big, _, cap_big = grads(256)
     assert steps > 2 and cap_found >= steps and cap_big == 256
     assert torch.equal(g_small, g_big)
+
+
+# --------------------------------------------------------------------------------------- evaluation metrics on device
+@pytest.mark.parametrize("n", [1, 5, 1023, 65536 * 29 + 3])
+def test_error_sums_kernel_and_sharded_metrics(n):
+    from codes_b200 import ops, parallel
+    g = torch.Generator(device=DEV).manual_seed(n)
+    p = torch.randn(n + 1, device=DEV, generator=g)[1:]          # (odd offset: exercises the unaligned scalar path)
+    t = torch.randn(n + 1, device=DEV, generator=g)[1:] * 3
+    s = ops.error_sums(p, t).cpu().numpy()
+    e = (p.double() - t.double()).abs()
+    ref = np.array([float(e.sum()), float((e * e).sum()), float((e / t.double().abs().clamp_min(1e-300)).sum()), float(e.max())])
+    np.testing.assert_allclose(s, ref, rtol=1e-11)
+    assert np.array_equal(s, ops.error_sums(p, t).cpu().numpy())          # deterministic
+    m = parallel.sharded_error_metrics(p.reshape(1, -1, 1), t.reshape(1, -1, 1))
+    np.testing.assert_allclose([m["MAE"], m["RMSE"], m["max_abs"]], [ref[0] / n, (ref[1] / n) ** 0.5, ref[3]], rtol=1e-11)
+    assert m["count"] == n
