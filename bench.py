@@ -633,6 +633,9 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"],
+                    help="cfg2 (default) = the headline MultiONet configuration; cfg1 / cfg3 / cfg4 = the other single-GPU "
+                         "configurations of BASELINE.json (benchmarks/workloads.py); cfg5 = benchmarks/full_benchmark.py")
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (sharded predict + collective) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true",
@@ -642,6 +645,10 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "cfg2":
+        sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+        import workloads
+        workloads.run(args, sys.modules[__name__])
     else:
         run_ours(args)
 
