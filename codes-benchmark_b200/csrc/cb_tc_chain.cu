@@ -1352,6 +1352,8 @@ struct cb_tc_chain {
   int dual;                     // shared-memory kernel in dual-tile mode (CB_TC_CHAIN_DUAL=1)
   int ts;                       // this plan runs the TMEM-resident kernel (its weights are packed for it)
   int ts_slots; size_t smem_ts;
+  int mt;                       // this plan runs the multi-tile TMEM-resident kernel (cb_tc_chain_mt.cu; own weight packing)
+  cb::tcmt::MtParams M;
   int ld_out;                   // OUT_BF16_TMA: columns of the bf16 output (multiple of 64)
   size_t smem_bytes;
   int weights_set;
@@ -1515,7 +1517,9 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
   const char* pair_env = getenv("CB_TC_CHAIN_PAIR");   // opt-in: CTA pairs (cta_group::2), see DESIGN.md 4.1
   const char* dual_env = getenv("CB_TC_CHAIN_DUAL");   // opt-in: two interleaved tiles per CTA in the shared-memory kernel
   pl->dual = g.dual_ok && g.ok && dual_env && atoi(dual_env) != 0;
-  pl->ts = !pl->dual && g.ts_ok && !(ts_env && atoi(ts_env) == 0);
+  memset(&pl->M, 0, sizeof(pl->M));
+  pl->mt = !pl->dual && cb::tcmt::mt_supported(desc, out_mode == OUT_BF16_TMA, &pl->M);
+  pl->ts = !pl->dual && !pl->mt && g.ts_ok && !(ts_env && atoi(ts_env) == 0);
   if (pl->dual) {
     P.dual = 1; P.inplace = 1; P.ostage_in_x = 0; P.stage_ld = g.stage_ld_dual ? g.stage_ld_dual : P.stage_ld;
     P.stages = g.stages_dual;
@@ -1552,7 +1556,7 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
     }
     P.n_chunks[i] = chunks;
     pl->Kp[i] = P.nkb[i] * kBlockK;
-    pl->rows_alloc[i] = pl->ts ? Np : round_up(N, chunk);
+    pl->rows_alloc[i] = (pl->ts || pl->mt) ? Np : round_up(N, chunk);
   }
   P.n_jobs = nj;
   {
@@ -1570,7 +1574,9 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
     for (int i = 0; i < desc->n_layers; ++i) {
       pl->d_w[i] = pl->d_wall + (size_t)P.w_row0[i] * kBlockK;
       P.w[i] = pl->d_w[i];
+      pl->M.w[i] = pl->d_w[i];
     }
+    if (pl->mt && cb::tcmt::mt_prepare(desc->act) != CB_OK) { cb_tc_chain_destroy(pl); return CB_ERR_CUDA; }
     const char* e = pair_env;
     pl->cg2 = !pl->ts && !pl->dual && g.cg2_ok && (e && atoi(e) != 0) && encode_bf16_rows64(&P.tmap_w64, pl->d_wall, rows64, 64) &&
               encode_bf16_rows64(&P.tmap_w8, pl->d_wall, rows64, 8);
@@ -1617,6 +1623,10 @@ extern "C" int32_t cb_tc_chain_set_weights(cb_tc_chain* plan, const float* const
     const long long total = (long long)plan->rows_alloc[i] * plan->Kp[i];
     int blocks = (int)((total + 255) / 256);
     if (blocks > 1184) blocks = 1184;
+    if (plan->mt) {
+      if (int32_t e = cb::tcmt::mt_pack_weights(d_W[i], d_b[i], plan->P.N[i], plan->P.K[i], plan->d_w[i], st)) return e;
+      continue;
+    }
     if (plan->ts)
       pack_weights_ts_kernel<<<blocks, 256, 0, st>>>(d_W[i], d_b[i], plan->P.N[i], plan->P.K[i], plan->rows_alloc[i],
                                                     plan->Kp[i], ts_split(plan->rows_alloc[i]), plan->d_w[i]);
@@ -1649,6 +1659,12 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
   P.dbg = nullptr;
   const char* dbg_env = getenv("CB_TC_CHAIN_DBG");
   if (dbg_env) { CB_CUDA(cudaMalloc(&P.dbg, 128)); CB_CUDA(cudaMemsetAsync(P.dbg, 0, 128, st)); }
+  if (plan->mt) {
+    CB_CHECK_ARG(!in_map && (plan->out_mode == OUT_F32 || d_yb != nullptr), "multi-tile chain: unsupported launch mode");
+    cb::tcmt::MtParams M = plan->M;
+    M.x = d_x; M.y = d_y; M.yb = d_yb; M.ld_yb = ld_yb; M.rows = rows; M.num_tiles = P.num_tiles;
+    return cb::tcmt::mt_launch(M, plan->desc.act, st);
+  }
   const bool ts = plan->ts != 0;   // (its weights are packed for the TS kernel: no other kernel may run this plan)
   if (ts) CB_CHECK_ARG(!in_map && (plan->out_mode == OUT_F32 || d_yb != nullptr), "TS chain: unsupported launch mode");
   if (ts) {

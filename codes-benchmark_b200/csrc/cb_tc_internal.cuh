@@ -17,6 +17,31 @@ int32_t hidden_chain_create(const cb_mlp_desc* full, int device, cb_tc_chain** o
 int hidden_chain_ld(const cb_tc_chain* plan);
 int32_t hidden_chain_launch(cb_tc_chain* plan, const float* d_x, int64_t rows, __nv_bfloat16* d_yb, cudaStream_t st);
 }  // namespace tc
+namespace tcmt {
+// Multi-tile TMEM-resident chain kernel (cb_tc_chain_mt.cu): NT 128-row tiles in flight per CTA, interleaved chunk by
+// chunk, so one tile's epilogue (tcgen05.ld -> activation -> tcgen05.st) runs under the other tiles' MMAs and every
+// weight chunk streamed from L2 is used NT times.
+constexpr int kMtChunk = 96;          // output columns per chunk (one 32-column group per epilogue warp class)
+constexpr int kMtMaxChunks = 3;       // layers up to 288 padded columns
+struct MtParams {
+  const __nv_bfloat16* w[CB_MAX_LAYERS];   // packed weights, see mt_pack_weights
+  int K[CB_MAX_LAYERS], N[CB_MAX_LAYERS], ksteps[CB_MAX_LAYERS], nkb[CB_MAX_LAYERS], nch[CB_MAX_LAYERS];
+  int n_layers, final_act;
+  float act_param;
+  int out_bf16;                // 1: every layer is hidden-like, the last one leaves as bf16 (rows, ld_yb) incl. the ones column
+  const float* x; float* y; __nv_bfloat16* yb; int ld_yb;
+  long long rows; int num_tiles;
+  int nt;                      // tiles in flight (2 when a layer has several chunks, else up to 4)
+  int aw;                      // TMEM columns of one tile's packed activations
+  int slots, slot_bytes;       // weight slots in shared memory (one chunk of one layer each)
+  long long* dbg;              // -DCB_MT_DBG: cycle counters of CTA 0's MMA warp
+};
+bool mt_supported(const cb_mlp_desc* d, int out_bf16, MtParams* geom /* nullable: nt, aw, slots, slot_bytes, nch.. */);
+size_t mt_packed_elems(int N, int K);
+int32_t mt_pack_weights(const float* d_W, const float* d_b, int N, int K, __nv_bfloat16* d_out, cudaStream_t st);
+int32_t mt_prepare(int act);   // cudaFuncSetAttribute for the instantiations of this activation
+int32_t mt_launch(const MtParams& P, int act, cudaStream_t st);
+}  // namespace tcmt
 namespace tcg {
 // out (rows, n_out_ld) bf16 = A (rows, a_ld) . Bp^T, Bp = packed K-major weights (b_rows >= round_up(n_out_ld, 256), a_ld)
 // with the bias in column k_total-1; columns >= n_true of `out` are written as zero.  No activation.
