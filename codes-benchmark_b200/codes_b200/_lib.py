@@ -97,6 +97,9 @@ _SIGNATURES = {
     "cb_tc_chain_destroy": (None, [_P]),
     "cb_tc_chain_set_weights": (_I32, [_P, _PP, _PP, _P]),
     "cb_tc_chain_forward": (_I32, [_P, _P, _I64, _P, _P]),
+    "cb_tc_chain_create_grouped": (_I32, [C.POINTER(MlpDesc), _I32, _I32, C.POINTER(_P)]),
+    "cb_tc_chain_set_weights_group": (_I32, [_P, _I32, _PP, _PP, _P]),
+    "cb_tc_chain_forward_grouped": (_I32, [_P, _P, _I64, _I64, _P, _P]),
     "cb_tc_multionet_supported": (_I32, [C.POINTER(MlpDesc), C.POINTER(MlpDesc), _I32]),
     "cb_tc_multionet_create": (_I32, [C.POINTER(MlpDesc), C.POINTER(MlpDesc), _I32, _I32, C.POINTER(_P)]),
     "cb_tc_multionet_destroy": (None, [_P]),

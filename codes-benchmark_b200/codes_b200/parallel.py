@@ -104,18 +104,51 @@ def ensemble_mean_std(member_preds: list[torch.Tensor]) -> tuple[torch.Tensor, t
     return stack.mean(dim=0), stack.std(dim=0, unbiased=True)
 
 
+def _grouped_members(models):
+    """batch -> [(pred_g, targets)] with ALL members in one grouped launch (cb_tc_chain_forward_grouped), or None when
+    the members are not FullyConnected surrogates of one architecture in bf16 inference mode."""
+    from . import ops, tc
+    from .fcnn import FullyConnected
+    if len(models) < 2 or not all(type(m) is FullyConnected for m in models) or ops.precision_mode() != "bf16":
+        return None
+    specs = [m.model.chain() for m in models]
+    s0 = specs[0]
+    if any((s.dims, s.act, s.final_act, s.act_param) != (s0.dims, s0.act, s0.final_act, s0.act_param) or s.slope is not None
+           for s in specs) or not tc.supported(s0):
+        return None
+    params = [ops.sequential_params(m.model.network) for m in models]
+    state = {"ok": True}
+
+    def run(inputs):
+        if not state["ok"]:
+            return None
+        x, targets = (v.to(models[0].device, non_blocking=True) if isinstance(v, torch.Tensor) else v for v in inputs)
+        try:
+            y = tc.grouped_chain_forward(s0, x, [p[0] for p in params], [p[1] for p in params])
+        except RuntimeError:          # architecture outside the multi-tile kernel: per-member launches
+            state["ok"] = False
+            return None
+        return [(y[g], targets) for g in range(len(models))]
+    return run
+
+
 def ensemble_predict(models, data_loader, leave_log: bool = True):
     """DeepEnsemble evaluation (bench_fcts.py:1058-1074) with every batch copied to the device ONCE and
-    pushed through all members back to back, instead of one full load + predict pass per member.
+    pushed through all members -- as ONE grouped launch per batch when the members are FullyConnected surrogates of
+    one architecture (work unit = (member, row tiles), cb_tc_chain_forward_grouped), else back to back -- instead of
+    one full load + predict pass per member.
     Returns (member predictions list of (N,T,Q), targets (N,T,Q), mean, std(ddof=1)) on the device."""
     first = models[0]
     n_batches = len(data_loader)
     bufs = None
     targs = None
     done = 0
+    grouped = _grouped_members(models)
     with torch.inference_mode():
         for inputs in first._prefetch_to_device(data_loader):
-            outs = [m(inputs) for m in models]
+            outs = grouped(inputs) if grouped is not None else None
+            if outs is None:
+                outs = [m(inputs) for m in models]
             p0, t0 = outs[0]
             if bufs is None:
                 shape = (p0.shape[0] * n_batches, *p0.shape[1:])

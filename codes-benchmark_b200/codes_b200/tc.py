@@ -76,6 +76,46 @@ def chain_forward(spec, x, weights, biases):
     return y.reshape(*x.shape[:-1], spec.dims[-1])
 
 
+class _GroupedChainPlan:
+    def __init__(self, spec, n_groups, device):
+        self.handle = C.c_void_p()
+        with torch.cuda.device(device):
+            check(lib().cb_tc_chain_create_grouped(C.byref(spec.desc), device.index or 0, n_groups, C.byref(self.handle)),
+                  "tc_chain_create_grouped")
+        self.versions = [None] * n_groups
+        self._fin = weakref.finalize(self, lib().cb_tc_chain_destroy, self.handle)
+
+
+_GROUPED_PLANS: dict = {}
+
+
+def grouped_chain_forward(spec, x, weights_per_group, biases_per_group):
+    """y[g] = chain_g(x) for G weight sets of one architecture in ONE launch (DeepEnsemble members on a shared batch):
+    x (rows, dims[0]) fp32 -> (G, rows, dims[-1]) fp32.  Per group bitwise identical to ``chain_forward``.
+    Raises RuntimeError when the architecture is outside the multi-tile kernel's range (caller falls back)."""
+    dev = x.device
+    G = len(weights_per_group)
+    key = (tuple(spec.dims), spec.act, spec.final_act, spec.act_param, G, dev.index)
+    plan = _GROUPED_PLANS.get(key)
+    if plan is None:
+        plan = _GROUPED_PLANS[key] = _GroupedChainPlan(spec, G, dev)
+    x2 = x.reshape(-1, spec.dims[0])
+    if x2.dtype != torch.float32 or not x2.is_contiguous():
+        x2 = x2.float().contiguous()
+    rows = x2.shape[0]
+    with torch.cuda.device(dev):
+        for g, (ws, bs) in enumerate(zip(weights_per_group, biases_per_group)):
+            versions = _versions(ws) + _versions(bs)
+            if versions != plan.versions[g]:
+                check(lib().cb_tc_chain_set_weights_group(plan.handle, g, ptr_array(_f32(ws)), ptr_array(_f32(bs)),
+                                                          _stream(dev)), "tc_chain_set_weights_group")
+                plan.versions[g] = versions
+        y = torch.empty((G, rows, spec.dims[-1]), device=dev, dtype=torch.float32)
+        check(lib().cb_tc_chain_forward_grouped(plan.handle, C.c_void_p(x2.data_ptr()), 0, rows,
+                                                C.c_void_p(y.data_ptr()), _stream(dev)), "tc_chain_forward_grouped")
+    return y
+
+
 class _MultiONetPlan:
     def __init__(self, bspec, tspec, q, device):
         self.handle = C.c_void_p()

@@ -1354,6 +1354,8 @@ struct cb_tc_chain {
   int ts_slots; size_t smem_ts;
   int mt;                       // this plan runs the multi-tile TMEM-resident kernel (cb_tc_chain_mt.cu; own weight packing)
   cb::tcmt::MtParams M;
+  int n_groups;                 // grouped plan: this many weight sets of the same architecture, group-major in d_wall
+  size_t group_elems;           // bf16 elements of one group's packed weights
   int ld_out;                   // OUT_BF16_TMA: columns of the bf16 output (multiple of 64)
   size_t smem_bytes;
   int weights_set;
@@ -1494,8 +1496,9 @@ extern "C" void cb_tc_chain_destroy(cb_tc_chain* plan) {
   delete plan;
 }
 
-static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mode, cb_tc_chain** out) {
+static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mode, cb_tc_chain** out, int n_groups = 1) {
   if (int32_t e = check_desc(desc)) return e;
+  CB_CHECK_ARG(n_groups >= 1 && n_groups <= 64, "n_groups out of range [1, 64]");
   CB_CHECK_ARG(out != nullptr, "out is NULL");
   const ChainGeom g = chain_geometry(desc, out_mode);
   CB_CHECK_ARG(g.ok, "chain not supported by the fused tcgen05 kernel (activations + weight stages exceed "
@@ -1566,7 +1569,9 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
       P.w_row0[i] = (int)rows64;
       rows64 += (long long)pl->rows_alloc[i] * (pl->Kp[i] / kBlockK);
     }
-    if (cudaMalloc(&pl->d_wall, (size_t)rows64 * kBlockK * sizeof(__nv_bfloat16)) != cudaSuccess) {
+    pl->n_groups = n_groups;
+    pl->group_elems = (size_t)rows64 * kBlockK;
+    if (cudaMalloc(&pl->d_wall, (size_t)rows64 * kBlockK * sizeof(__nv_bfloat16) * n_groups) != cudaSuccess) {
       cb_tc_chain_destroy(pl);
       set_error("cudaMalloc of the bf16 weight cache failed");
       return CB_ERR_CUDA;
@@ -1575,6 +1580,12 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
       pl->d_w[i] = pl->d_wall + (size_t)P.w_row0[i] * kBlockK;
       P.w[i] = pl->d_w[i];
       pl->M.w[i] = pl->d_w[i];
+      pl->M.w_gstride[i] = (long long)pl->group_elems;
+    }
+    if (n_groups > 1 && !pl->mt) {
+      cb_tc_chain_destroy(pl);
+      set_error("grouped execution needs the multi-tile chain kernel (layers up to 288 wide)");
+      return CB_ERR_ARG;
     }
     if (pl->mt && cb::tcmt::mt_prepare(desc->act) != CB_OK) { cb_tc_chain_destroy(pl); return CB_ERR_CUDA; }
     const char* e = pair_env;
@@ -1612,6 +1623,38 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
 
 extern "C" int32_t cb_tc_chain_create(const cb_mlp_desc* desc, int32_t device, cb_tc_chain** out) {
   return chain_create(desc, device, OUT_F32, out);
+}
+
+extern "C" int32_t cb_tc_chain_create_grouped(const cb_mlp_desc* desc, int32_t device, int32_t n_groups, cb_tc_chain** out) {
+  return chain_create(desc, device, OUT_F32, out, n_groups);
+}
+
+extern "C" int32_t cb_tc_chain_set_weights_group(cb_tc_chain* plan, int32_t group, const float* const* d_W,
+                                                 const float* const* d_b, void* stream) {
+  CB_CHECK_ARG(plan && d_W && d_b, "NULL pointer argument");
+  CB_CHECK_ARG(plan->mt && group >= 0 && group < plan->n_groups, "bad group index %d", group);
+  for (int i = 0; i < plan->P.n_layers; ++i) {
+    CB_CHECK_ARG(d_W[i] != nullptr, "weight %d is NULL", i);
+    if (int32_t e = cb::tcmt::mt_pack_weights(d_W[i], d_b[i], plan->P.N[i], plan->P.K[i],
+                                              plan->d_w[i] + (size_t)group * plan->group_elems, (cudaStream_t)stream)) return e;
+  }
+  plan->weights_set |= 1;
+  return CB_OK;
+}
+
+extern "C" int32_t cb_tc_chain_forward_grouped(cb_tc_chain* plan, const float* d_x, int64_t x_group_stride, int64_t rows,
+                                               float* d_y, void* stream) {
+  CB_CHECK_ARG(plan != nullptr && plan->mt && plan->out_mode == OUT_F32, "not a grouped fp32-output chain plan");
+  CB_CHECK_ARG(plan->weights_set, "cb_tc_chain_set_weights_group must be called for every group first");
+  CB_CHECK_ARG(rows >= 0 && x_group_stride >= 0, "bad shape");
+  if (rows == 0) return CB_OK;
+  CB_CHECK_ARG(d_x && d_y, "NULL pointer argument");
+  cb::tcmt::MtParams M = plan->M;
+  M.x = d_x; M.y = d_y; M.yb = nullptr; M.ld_yb = 0; M.rows = rows;
+  M.num_tiles = (int)((rows + kTileM - 1) / kTileM);
+  M.n_groups = plan->n_groups; M.x_gstride = x_group_stride;
+  M.y_gstride = (long long)rows * plan->desc.dims[plan->desc.n_layers];
+  return cb::tcmt::mt_launch(M, plan->desc.act, (cudaStream_t)stream);
 }
 
 extern "C" int32_t cb_tc_chain_set_weights(cb_tc_chain* plan, const float* const* d_W, const float* const* d_b,
@@ -1663,6 +1706,7 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
     CB_CHECK_ARG(!in_map && (plan->out_mode == OUT_F32 || d_yb != nullptr), "multi-tile chain: unsupported launch mode");
     cb::tcmt::MtParams M = plan->M;
     M.x = d_x; M.y = d_y; M.yb = d_yb; M.ld_yb = ld_yb; M.rows = rows; M.num_tiles = P.num_tiles;
+    M.n_groups = 1; M.x_gstride = 0; M.y_gstride = 0;
     return cb::tcmt::mt_launch(M, plan->desc.act, st);
   }
   const bool ts = plan->ts != 0;   // (its weights are packed for the TS kernel: no other kernel may run this plan)

@@ -87,13 +87,15 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
   const int accw = NCH > 1 ? kMtChunk : (512 / NT - P.aw) / 32 * 32 < kMtChunk ? (512 / NT - P.aw) / 32 * 32 : kMtChunk;
   const uint32_t tile_cols = (uint32_t)(accw + P.aw);
-  const int n_units = (P.num_tiles + NT - 1) / NT;
+  const int units_g = (P.num_tiles + NT - 1) / NT;                       // units per group
+  const int n_units = units_g * (P.n_groups > 0 ? P.n_groups : 1);
   const int n_my = (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
     // ============================================================ weight producer: one slot per (layer, chunk)
     int slot = 0; uint32_t phase = 0;
-    for (int it = 0; it < n_my; ++it)
+    for (int it = 0; it < n_my; ++it) {
+      const int grp = ((int)blockIdx.x + it * (int)gridDim.x) / units_g;
       for (int l = 0; l < P.n_layers; ++l) {
         const int Np = (P.N[l] + 15) & ~15, nkb = P.nkb[l];
         for (int c = 0; c < P.nch[l]; ++c) {
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
           mbar_wait(bar_wempty + 8 * slot, phase ^ 1);
           if (elect_one()) {
             const uint32_t bytes = (uint32_t)(nkb * rows_c * 128);
-            const __nv_bfloat16* src = P.w[l] + (size_t)n0 * nkb * kBlockK;
+            const __nv_bfloat16* src = P.w[l] + (size_t)grp * P.w_gstride[l] + (size_t)n0 * nkb * kBlockK;
             mbar_arrive_expect_tx(bar_wfull + 8 * slot, bytes);
             for (uint32_t off = 0; off < bytes; off += 32768u)
               bulk_load(W0 + (uint32_t)slot * slot_bytes + off, reinterpret_cast<const uint8_t*>(src) + off,
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
           if (++slot == P.slots) { slot = 0; phase ^= 1; }
         }
       }
+    }
   } else if (warp < kMtFirstEpi) {
     // ============================================================ MMA issuers: one tcgen05.mma instruction stream per
     // tile parity -- issuing an MMA blocks the issuing thread for ~60 cycles whatever its shape (a 128x96x16 MMA is 48
@@ -183,13 +186,17 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
       if (lane == 0) mbar_arrive(bar);
     };
     for (int it = 0; it < n_my; ++it) {
-      const int unit = (int)blockIdx.x + it * (int)gridDim.x;
+      const int gunit = (int)blockIdx.x + it * (int)gridDim.x;
+      const int grp = gunit / units_g, unit = gunit - grp * units_g;
+      const float* xg = P.x + (long long)grp * P.x_gstride;
+      float* yg = P.y + (long long)grp * P.y_gstride;
+      __nv_bfloat16* ybg = P.yb + (long long)grp * P.y_gstride;
       // ---- layer 0's A operand of every tile: [x, 1, 0...], 16 elements (8 packed columns) per unit
 #pragma unroll
       for (int s = 0; s < NT; ++s) {
         const long long row_g = ((long long)unit * NT + s) * kTileM + r;
         const bool row_ok = row_g < P.rows;
-        const float* xr = P.x + row_g * K0;
+        const float* xr = xg + row_g * K0;
         const uint32_t a_tmem = tmem_base + lane_off + (uint32_t)s * tile_cols + (uint32_t)accw;
         for (int u = h; u < P.ksteps[0]; u += kMtEpiWarps / 4) {
           uint32_t pk[8];
@@ -209,9 +216,10 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
         // pull the next unit's input rows into L2 now: their staging sits on the critical path of the unit's first layer
 #pragma unroll
         for (int s = 0; s < NT; ++s) {
-          const long long row_n = ((long long)(unit + (int)gridDim.x) * NT + s) * kTileM + r;
+          const int gnext = gunit + (int)gridDim.x, grp_n = gnext / units_g;
+          const long long row_n = ((long long)(gnext - grp_n * units_g) * NT + s) * kTileM + r;
           if (row_n < P.rows && h == 0) {
-            const char* pn = reinterpret_cast<const char*>(P.x + row_n * K0);
+            const char* pn = reinterpret_cast<const char*>(P.x + (long long)grp_n * P.x_gstride + row_n * K0);
             for (int b = 0; b < K0 * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + b));
           }
         }
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
                   }
                 } else if (row_ok) {
                   const bool tanh_out = (P.final_act == CB_ACT_TANH);
-                  float* yp = P.y + row_g * N;
+                  float* yp = yg + row_g * N;
 #pragma unroll
                   for (int i = 0; i < 32; ++i) {
                     const int n = nb + i;
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
                     if (!last) {
                       if (ww == 32) tmem_st16(a_tmem + (uint32_t)(nbb >> 1), Rs); else tmem_st8(a_tmem + (uint32_t)(nbb >> 1), Rs);
                     } else if (row_ok) {
-                      uint4* dst = reinterpret_cast<uint4*>(P.yb + row_g * P.ld_yb + nbb);
+                      uint4* dst = reinterpret_cast<uint4*>(ybg + row_g * P.ld_yb + nbb);
                       dst[0] = make_uint4(Rs[0], Rs[1], Rs[2], Rs[3]);
                       dst[1] = make_uint4(Rs[4], Rs[5], Rs[6], Rs[7]);
                       if (ww == 32) {
@@ -324,7 +332,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
                   uint32_t ones[8] = {pack_bf16(1.f, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
                   if (!last) tmem_st8(a_tmem + (uint32_t)(N >> 1), ones);
                   else if (row_ok) {
-                    uint4* dst = reinterpret_cast<uint4*>(P.yb + row_g * P.ld_yb + N);
+                    uint4* dst = reinterpret_cast<uint4*>(ybg + row_g * P.ld_yb + N);
                     dst[0] = make_uint4(ones[0], 0u, 0u, 0u);
                     dst[1] = make_uint4(0u, 0u, 0u, 0u);
                   }
@@ -464,7 +472,7 @@ int32_t mt_launch(const MtParams& P, int act, cudaStream_t st) {
   bool multi = false;
   for (int i = 0; i < P.n_layers; ++i) multi = multi || P.nch[i] > 1;
   MtKernelFn fn = mt_pick(act, P.nt, multi);
-  const int units = (P.num_tiles + P.nt - 1) / P.nt;
+  const int units = (P.num_tiles + P.nt - 1) / P.nt * (P.n_groups > 0 ? P.n_groups : 1);
   const int grid = units < num_sms() ? units : num_sms();
   const size_t smem = 1024 + (size_t)P.slots * P.slot_bytes + kMtCtrl +
                       (multi ? (size_t)2 * (kMtMaxChunks - 1) * 4 * kMtEpiWarps * 32 * 16 : 0);

@@ -409,7 +409,8 @@ extern "C" int64_t cb_tc_multionet_grid_workspace_bytes(const cb_tc_grid* g, int
   const int n_tchunks = (T + kTChunk - 1) / kTChunk;
   const long long chunk = (long long)grid_chunk_tiles(n_tchunks) * kTileM;
   const long long rows = n_traj < chunk ? (n_traj + kTileM - 1) / kTileM * kTileM : chunk;
-  return (int64_t)n_tchunks * g->Q * g->nkb * kTrTile + rows * (long long)(g->ld_h + g->ldF) * 2 + 4096;
+  const long long rows_all = (n_traj + kTileM - 1) / kTileM * kTileM;
+  return (int64_t)n_tchunks * g->Q * g->nkb * kTrTile + rows_all * (long long)g->ld_h * 2 + rows * (long long)g->ldF * 2 + 4096;
 }
 
 static int32_t grid_forward_impl(cb_tc_grid* g, const float* d_x0, int64_t n_traj, const float* d_trunk_out, int32_t T,
@@ -453,7 +454,7 @@ static int32_t grid_forward_impl(cb_tc_grid* g, const float* d_x0, int64_t n_tra
   const int n_tchunks = (T + kTChunk - 1) / kTChunk;
   const long long chunk = (long long)grid_chunk_tiles(n_tchunks) * kTileM;
   // timed variant: one event before the first kernel and one after every kernel
-  constexpr int kMaxEv = 1 + 1 + 3 * 64;
+  constexpr int kMaxEv = 1 + 2 + 2 * 96;
   cudaEvent_t ev[kMaxEv];
   int n_ev = 0;
   auto mark = [&]() { if (phase_ms && n_ev < kMaxEv) { cudaEventCreate(&ev[n_ev]); cudaEventRecord(ev[n_ev], st); ++n_ev; } };
@@ -462,8 +463,10 @@ static int32_t grid_forward_impl(cb_tc_grid* g, const float* d_x0, int64_t n_tra
   __nv_bfloat16* trp = reinterpret_cast<__nv_bfloat16*>(wsp);
   const size_t trp_total = (size_t)n_tchunks * g->Q * g->nkb * kTrTile;
   __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(wsp + ((trp_total + 1023) & ~(size_t)1023));
-  const long long rows_alloc = n_traj < chunk ? (n_traj + kTileM - 1) / kTileM * kTileM : chunk;
-  __nv_bfloat16* F = hb + rows_alloc * g->ld_h;
+  // the branch hidden chain runs over ALL trajectories in one launch (a chunk of ~16 k rows would fill less than half
+  // of the SMs of the persistent chain kernel); only the feature GEMM + grid kernel pair is chunked for L2 residency
+  const long long rows_all = (n_traj + kTileM - 1) / kTileM * kTileM;
+  __nv_bfloat16* F = hb + rows_all * g->ld_h;
   {
     const long long total = (long long)trp_total / 2;
     int blocks = (int)((total + 255) / 256);
@@ -473,12 +476,11 @@ static int32_t grid_forward_impl(cb_tc_grid* g, const float* d_x0, int64_t n_tra
     mark();
   }
   GridKernelFn fn = pick<1>(g->Q);
-  const int d0 = g->branch.dims[0];
+  if (int32_t e = hidden_chain_launch(g->hidden, d_x0, n_traj, hb, st)) return e;
+  mark();
   for (long long n0 = 0; n0 < n_traj; n0 += chunk) {
     const long long n = (n_traj - n0) < chunk ? (n_traj - n0) : chunk;
-    if (int32_t e = hidden_chain_launch(g->hidden, d_x0 + n0 * d0, n, hb, st)) return e;
-    mark();
-    if (int32_t e = tcg::gemm_fwd_bf16(hb, n, g->ld_h, g->K + 1, g->d_wlast, g->wp_rows, g->Q * g->KQ, g->ldF, F, st)) return e;
+    if (int32_t e = tcg::gemm_fwd_bf16(hb + n0 * g->ld_h, n, g->ld_h, g->K + 1, g->d_wlast, g->wp_rows, g->Q * g->KQ, g->ldF, F, st)) return e;
     mark();
     GridParams P;
     memset(&P, 0, sizeof(P));
@@ -516,7 +518,7 @@ static int32_t grid_forward_impl(cb_tc_grid* g, const float* d_x0, int64_t n_tra
     for (int i = 1; i < n_ev; ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-      phase_ms[i == 1 ? 0 : 1 + (i - 2) % 3] += ms;
+      phase_ms[i == 1 ? 0 : (i == 2 ? 1 : 2 + (i - 3) % 2)] += ms;
     }
     for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
   }

@@ -35,6 +35,11 @@ struct MtParams {
   int aw;                      // TMEM columns of one tile's packed activations
   int slots, slot_bytes;       // weight slots in shared memory (one chunk of one layer each)
   long long* dbg;              // -DCB_MT_DBG: cycle counters of CTA 0's MMA warp
+  // grouped execution (DeepEnsemble / sweep members of one architecture in ONE launch): work unit = (group, tile
+  // block); group g reads the weights at w[l] + g * w_gstride[l], the input rows at x + g * x_gstride (0: all groups
+  // share the input) and writes y + g * y_gstride / yb + g * y_gstride
+  int n_groups;
+  long long w_gstride[CB_MAX_LAYERS], x_gstride, y_gstride;
 };
 bool mt_supported(const cb_mlp_desc* d, int out_bf16, MtParams* geom /* nullable: nt, aw, slots, slot_bytes, nch.. */);
 size_t mt_packed_elems(int N, int K);

@@ -291,6 +291,17 @@ CB_API int32_t cb_tc_chain_set_weights(cb_tc_chain* plan, const float* const* d_
 CB_API int32_t cb_tc_chain_forward(cb_tc_chain* plan, const float* d_x, int64_t rows, float* d_y,
                             void* stream);
 
+/* Grouped chains: G weight sets of ONE architecture run as ONE launch (work unit = (group, block of row tiles)).
+ * This is how the DeepEnsemble members (created by train_fcts.py:184-187, evaluated one after the other by
+ * bench_fcts.py:1058-1074) and equal-architecture sweep members are batched.  Groups either share the input rows
+ * (x_group_stride = 0: an ensemble on one test set) or read rows at d_x + g * x_group_stride floats.
+ * d_y: (n_groups, rows, dims[n]) fp32.  Same arithmetic per group as cb_tc_chain_forward (bitwise identical). */
+CB_API int32_t cb_tc_chain_create_grouped(const cb_mlp_desc* desc, int32_t device, int32_t n_groups, cb_tc_chain** out);
+CB_API int32_t cb_tc_chain_set_weights_group(cb_tc_chain* plan, int32_t group, const float* const* d_W,
+                                             const float* const* d_b, void* stream);
+CB_API int32_t cb_tc_chain_forward_grouped(cb_tc_chain* plan, const float* d_x, int64_t x_group_stride, int64_t rows,
+                                           float* d_y, void* stream);
+
 /* Fused MultiONet forward on tensor cores (deeponet.py:226-253): hidden layers of the branch
  * and trunk nets as two fused chains (bf16 activations handed over through `d_workspace`), then
  * ONE kernel for both last Linears + the per-quantity split scalar product.
