@@ -16,7 +16,8 @@ from .latent_common import Decoder, Encoder
 from .latent_neural_ode import ODE, LatentNeuralODE, ModelWrapper
 from .latent_poly import LatentPoly, Polynomial, PolynomialModelWrapper
 from .loaders import RowBatchIterable
-from .ops import precision_mode, set_precision, set_train_precision, train_precision_mode
+from .ops import (metric_precision_mode, precision_mode, precision_scope, set_metric_precision, set_precision,
+                  set_train_precision, train_precision_mode)
 from . import parallel, train  # noqa: E402,F401  (host-side sharding / task orchestration)
 
 surrogate_classes = [MultiONet, FullyConnected, LatentNeuralODE, LatentPoly]
@@ -27,6 +28,7 @@ __all__ = [
     "Encoder", "Decoder", "LatentPoly", "Polynomial", "PolynomialModelWrapper", "RowBatchIterable",
     "AbstractSurrogateBaseConfig", "FCNNBaseConfig", "MultiONetBaseConfig", "LatentNeuralODEBaseConfig",
     "LatentPolynomialBaseConfig", "precision_mode", "set_precision", "set_train_precision",
+    "metric_precision_mode", "set_metric_precision", "precision_scope",
     "train_precision_mode",
 ]
 

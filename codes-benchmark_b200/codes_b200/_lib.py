@@ -67,6 +67,7 @@ _SIGNATURES = {
     "cb_mlp_backward_f32_p": (_I32, [C.POINTER(MlpDesc), _PP, _P, _P, _P, _I64, _PP, _PP, _P, _P, _I64, _P, _P, _P]),
     "cb_deeponet_combine_fwd": (_I32, [_P, _P, _I64, _I32, _I32, _P, _P]),
     "cb_deeponet_combine_bwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
+    "cb_deeponet_grid_combine_f32": (_I32, [_P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _P, _P]),
     "cb_poly_eval_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _P]),
     "cb_poly_eval_bwd": (_I32, [_P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _I64, _P]),
     "cb_poly_eval_batched_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _P]),
@@ -123,6 +124,11 @@ _SIGNATURES = {
     "cb_tc_train_forward": (_I32, [_P, _PP, _PP, _P, _I64, _P, _P, _I64, _P]),
     "cb_tc_train_infer_bytes": (_I64, [_P, _I64]),
     "cb_tc_train_infer": (_I32, [_P, _PP, _PP, _P, _I64, _P, _P, _I64, _P]),
+    "cb_tc_x3_create": (_I32, [C.POINTER(MlpDesc), _I32, C.POINTER(_P)]),
+    "cb_tc_x3_destroy": (None, [_P]),
+    "cb_tc_x3_set_weights": (_I32, [_P, _PP, _PP, _P]),
+    "cb_tc_x3_workspace_bytes": (_I64, [_P, _I64]),
+    "cb_tc_x3_forward": (_I32, [_P, _P, _I64, _P, _P, _I64, _P]),
     "cb_tc_train_backward": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _PP, _PP, _P, _P]),
     "cb_tc_combine_fwd": (_I32, [_P, _P, _I64, _I32, _I32, _I32, _P, _P]),
     "cb_tc_combine_bwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P]),

@@ -152,7 +152,7 @@ class AbstractSurrogateModel(ABC, nn.Module):
 
     # ------------------------------------------------------------------ inference
     def predict(self, data_loader: DataLoader, leave_log: bool = False,
-                leave_norm: bool = False) -> tuple[Tensor, Tensor]:
+                leave_norm: bool = False, _any_order: bool = False) -> tuple[Tensor, Tensor]:
         """Run the model over a loader; returns (predictions, targets) as (N, T, Q) device tensors.
 
         Semantics of abstract_surrogate.py:217-275 (buffers sized first_batch_rows x
@@ -163,6 +163,8 @@ class AbstractSurrogateModel(ABC, nn.Module):
         and, for a SHUFFLING dataset, one ``torch.randperm(N)``; the same draws are consumed here, so every later
         training batch order matches the reference for a seed (``validate`` calls predict on the shuffled train
         loader 3x per 10 epochs; tests/golden/predict_rng.npz).
+        ``_any_order`` (private; validate()'s permutation-invariant L1 over the shuffled training loader): the rows
+        may come back in the dataset's natural order instead of the epoch's permutation.
         """
         n_batches = len(data_loader)
         ds = getattr(data_loader, "dataset", None)
@@ -171,7 +173,7 @@ class AbstractSurrogateModel(ABC, nn.Module):
             torch.randperm(ds.N)
         grid_hook = getattr(self, "_predict_on_grid", None)   # de-duplicated whole-loader path of a concrete class
         if grid_hook is not None:
-            res = grid_hook(data_loader, leave_log, leave_norm)
+            res = grid_hook(data_loader, leave_log, leave_norm, _any_order)
             if res is not None:
                 return res
         preds = targs = None
@@ -462,7 +464,7 @@ class AbstractSurrogateModel(ABC, nn.Module):
             self.best_epoch, self.best_test_loss = -1, None
             return
         self.eval()
-        with torch.inference_mode():
+        with torch.inference_mode(), ops.precision_scope(ops.metric_precision_mode()):
             preds, targets = self.predict(test_loader)
             final_loss = self._criterion_value(criterion, preds, targets)
         if final_loss < self.best_test_loss:
@@ -497,11 +499,13 @@ class AbstractSurrogateModel(ABC, nn.Module):
         if epoch % self.update_epochs != 0:
             return
         index = epoch // self.update_epochs
-        with torch.inference_mode():
+        # recorded numbers (and the checkpoint / pruning decisions taken on them) come from fp32-grade predictions:
+        # ops.metric_precision_mode(), 'bf16x3' unless configured otherwise
+        with torch.inference_mode(), ops.precision_scope(ops.metric_precision_mode()):
             self.eval()
             if hasattr(optimizer, "eval"):
                 optimizer.eval()
-            p, t = self.predict(train_loader, leave_log=True)
+            p, t = self.predict(train_loader, leave_log=True, _any_order=True)   # a mean over all rows
             self.train_loss[index] = self._l1(p, t)
             p, t = self.predict(test_loader, leave_log=True)
             self.test_loss[index] = self._l1(p, t)

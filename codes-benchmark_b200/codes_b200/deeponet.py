@@ -111,22 +111,28 @@ class MultiONet(OperatorNetwork):
         return ops.deeponet_combine(b, t, self.N), targets
 
     # ------------------------------------------------------------------ de-duplicated predict
-    def _predict_on_grid(self, data_loader, leave_log: bool, leave_norm: bool):
+    def _predict_on_grid(self, data_loader, leave_log: bool, leave_norm: bool, any_order: bool = False):
         """predict() for an un-shuffled loader built by ``prepare_data``: its rows r = n*T + t repeat x0[n] T times
         and tile the time grid N times (deeponet.py:371-374), so the branch net is evaluated once per trajectory,
         the trunk net once per grid point and one contraction kernel writes the de-normalised (N, T, Q) predictions
         (SURVEY 8d F_traj,dedup; ``cb_tc_multionet_grid_forward``).  Same values as the row path up to the bf16
         rounding of the branch / trunk features (tests/test_gpu_grid_predict.py); returns None whenever the loader
-        or the configuration does not have that structure, and the generic per-batch path runs instead."""
+        or the configuration does not have that structure, and the generic per-batch path runs instead.
+        ``any_order`` (validate()'s order-free L1 on the SHUFFLED training loader): a device-resident shuffling dataset
+        is evaluated on its own grid in natural row order -- no H2D copy at all, its targets already live in HBM."""
         from . import tc
         from .loaders import grid_predict_enabled
         ds = getattr(data_loader, "dataset", None)
         dev = self.device
-        if (dev is None or "cuda" not in str(dev) or not isinstance(ds, RowBatchIterable) or ds.shuffle
-                or ds.row_structure != ["repeat", "tile", "full"] or ds._compact is None
+        if (dev is None or "cuda" not in str(dev) or not isinstance(ds, RowBatchIterable)
+                or ds.row_structure != ["repeat", "tile", "full"] or ds.period <= 0
                 or getattr(data_loader, "num_workers", 0) != 0 or not grid_predict_enabled()
-                or ops.precision_mode() != "bf16" or ds.N % ds.period != 0):
+                or ds.N % ds.period != 0):
             return None
+        resident = ds.shuffle
+        if (resident and not (any_order and ds.device is not None)) or (not resident and ds._compact is None):
+            return None
+        prec = ops.precision_mode()
         norm = self.normalisation
         mode, do_pow = 0, False
         if norm is not None:
@@ -134,12 +140,32 @@ class MultiONet(OperatorNetwork):
                 return None
             mode = 1 if ((not leave_norm) and norm["mode"] == "minmax") else 0
             do_pow = bool(norm["log10_transform"]) and not leave_log
-        if not tc.multionet_grid_supported(self):
+        if prec == "bf16" and not tc.multionet_grid_supported(self):
             return None
         device = torch.device(dev)
         self._draw_loader_seed(data_loader)                 # the iterator the per-batch loop would have created
-        x0_h, t_h, targ_h = ds._compact[0], ds._compact[1], ds.tensors[2]
         Q = self.N
+        if resident:
+            torch.randperm(ds.N)          # the permutation the per-batch loop's iterator would have drawn (RNG parity)
+            with torch.inference_mode():
+                if ds._resident is None:
+                    ds._resident = ([None if t is None else t.to(ds.device, non_blocking=True) for t in ds.tensors],
+                                    [c.to(ds.device, non_blocking=True) for c in ds.constants])
+                br, tr, tg_all = ds._resident[0]
+                x0, tg = br[::ds.period].contiguous(), tr[:ds.period].contiguous()
+                preds = torch.empty((ds.N, Q), dtype=torch.float32, device=device)
+                dmin = dmax = None
+                if mode == 1:
+                    dmin = self._norm_vector(norm["min"], Q, device)
+                    dmax = self._norm_vector(norm["max"], Q, device)
+                if prec == "bf16":
+                    tc.multionet_grid_forward(self, x0, tg, preds, mode, dmin, dmax, do_pow, trunk_tag=None)
+                else:
+                    self._grid_forward_f32(x0, tg, preds, mode, dmin, dmax, do_pow)
+                targs = self.denormalize(tg_all.clone(), leave_log, leave_norm, _inplace=True)
+            return (preds.reshape(-1, self.n_timesteps, self.n_quantities),
+                    targs.reshape(-1, self.n_timesteps, self.n_quantities))
+        x0_h, t_h, targ_h = ds._compact[0], ds._compact[1], ds.tensors[2]
         with torch.inference_mode():
             copy_stream = self.__dict__.get("_copy_stream")
             if copy_stream is None or copy_stream.device != device:
@@ -164,12 +190,29 @@ class MultiONet(OperatorNetwork):
             tag = ds.__dict__.get("_grid_tag")
             if tag is None:                                  # content fingerprint of the (T, trunk_in) time grid
                 tag = ds.__dict__["_grid_tag"] = t_h.numpy().tobytes()
-            tc.multionet_grid_forward(self, x0, tg, preds, mode, dmin, dmax, do_pow, trunk_tag=tag)
+            if prec == "bf16":
+                tc.multionet_grid_forward(self, x0, tg, preds, mode, dmin, dmax, do_pow, trunk_tag=tag)
+            else:
+                self._grid_forward_f32(x0, tg, preds, mode, dmin, dmax, do_pow)
             cur.wait_event(ready)
             targs.record_stream(cur)
             targs = self.denormalize(targs, leave_log, leave_norm, _inplace=True)
         return (preds.reshape(-1, self.n_timesteps, self.n_quantities),
                 targs.reshape(-1, self.n_timesteps, self.n_quantities))
+
+    def _grid_forward_f32(self, x0, tg, preds, mode, dmin, dmax, do_pow, chunk: int = 16384):
+        """fp32-grade grid path ('fp32' and 'bf16x3' modes): the branch net once per trajectory through ``run_chain``
+        (FFMA kernels or the split-precision tensor-core GEMMs), the trunk net once per grid point on the fp32 kernels,
+        then the fp32 contraction ``cb_deeponet_grid_combine_f32`` writes the de-normalised (N, T, Q) block.  Chunked
+        over trajectories: the (chunk, Q*f) branch outputs stay at ~190 MB."""
+        tw, tb = ops.sequential_params(self.trunk_net.network)
+        trunk_out = ops.mlp_chain(self.trunk_net.chain(), tg.float().contiguous(), [w.detach() for w in tw],
+                                  [b.detach() for b in tb])
+        T, Q = tg.shape[0], self.N
+        out = preds.view(-1, T, Q)
+        for n0 in range(0, x0.shape[0], chunk):
+            b = self.branch_net(x0[n0:n0 + chunk])
+            ops.deeponet_grid_combine(b, trunk_out, Q, out[n0:n0 + chunk], mode, dmin, dmax, do_pow)
 
     # ------------------------------------------------------------------ data
     def create_dataloader(self, data: np.ndarray, timesteps: np.ndarray, batch_size: int, shuffle: bool,

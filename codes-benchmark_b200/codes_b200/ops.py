@@ -6,7 +6,9 @@ bookkeeping) only; there is no torch compute on these paths and no CPU fallback.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import threading
 from typing import Sequence
 
 import torch
@@ -487,27 +489,89 @@ def lnode_solve_backward(spec: ChainSpec, weights, biases, t_eval: Tensor, tape_
     return dz0, dW, db, dreg
 
 
+def deeponet_grid_combine(branch_out: Tensor, trunk_out: Tensor, n_quantities: int, out: Tensor, mode: int,
+                          dmin: Tensor | None, dmax: Tensor | None, pow10: bool) -> Tensor:
+    """out[n, t, q] = denorm(sum_{k in split_q} branch_out[n, k] * trunk_out[t, k]) in fp32 (gradient-free):
+    MultiONet's split scalar product (deeponet.py:241-253) on per-trajectory / per-grid-point operands."""
+    _require_cuda(branch_out, trunk_out, out)
+    b, t = _f32c(branch_out), _f32c(trunk_out)
+    n, n_out = b.shape
+    with torch.cuda.device(b.device):
+        check(lib().cb_deeponet_grid_combine_f32(_p(b), _p(t), n, t.shape[0], n_out, n_quantities, int(mode), _p(dmin),
+                                                 _p(dmax), int(bool(pow10)), _p(out), _stream(b)),
+              "deeponet_grid_combine_f32")
+    return out
+
+
 # --------------------------------------------------------------------------- precision dispatch
 _PRECISION = {"mode": None}
+_PRECISION_TLS = threading.local()          # precision_scope(): per-thread override (worker threads share the module)
+PRECISION_MODES = ("fp32", "bf16", "bf16x3")
+X3_MIN_ROWS = 1024     # below this (or for chains narrower than X3_MIN_WIDTH) the FFMA kernels are as fast
+X3_MIN_WIDTH = 128
 
 
 def precision_mode() -> str:
-    """'fp32' (FFMA, exact mode) or 'bf16' (tcgen05 tensor cores, fp32 accumulate).
+    """Arithmetic of gradient-free dense chains (``predict`` / ``forward`` under ``no_grad``):
 
-    Selected by ``set_precision`` or the ``CODES_B200_PRECISION`` environment variable;
-    the default is 'bf16' for inference-only dense chains and always 'fp32' for anything
-    that needs gradients or feeds the ODE step-size controller.
-    """
+    * ``'bf16'``   -- tcgen05 tensor cores, bf16 operands, fp32 accumulate (default; rel-L2 <= 1e-2);
+    * ``'bf16x3'`` -- tcgen05 tensor cores at fp32-grade accuracy: every fp32 operand is carried as three bf16
+      pieces and each Linear runs the six significant piece products (``cb_tc_x3_forward``), ~1e-6 of the fp32 mode;
+    * ``'fp32'``   -- FFMA kernels, the exactness mode (also forces fp32 training).
+
+    Selected by ``set_precision`` / ``CODES_B200_PRECISION``, temporarily by ``precision_scope``.  Anything that
+    needs gradients or feeds the ODE step-size controller never uses the bf16 modes."""
     import os
+    ov = getattr(_PRECISION_TLS, "mode", None)
+    if ov is not None:
+        return ov
     if _PRECISION["mode"] is None:
         _PRECISION["mode"] = os.environ.get("CODES_B200_PRECISION", "bf16").lower()
     return _PRECISION["mode"]
 
 
 def set_precision(mode: str) -> None:
-    if mode not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if mode not in PRECISION_MODES:
+        raise ValueError("precision must be 'fp32', 'bf16' or 'bf16x3'")
     _PRECISION["mode"] = mode
+
+
+@contextlib.contextmanager
+def precision_scope(mode: str | None):
+    """Run the enclosed gradient-free calls of THIS thread in ``mode`` (None: no change)."""
+    if mode is None:
+        yield
+        return
+    if mode not in PRECISION_MODES:
+        raise ValueError("precision must be 'fp32', 'bf16' or 'bf16x3'")
+    prev = getattr(_PRECISION_TLS, "mode", None)
+    _PRECISION_TLS.mode = mode
+    try:
+        yield
+    finally:
+        _PRECISION_TLS.mode = prev
+
+
+_METRIC_PRECISION = {"mode": None}
+
+
+def metric_precision_mode() -> str:
+    """Arithmetic of the predictions behind RECORDED numbers -- ``validate()``'s train/test losses and MAE, the
+    best-checkpoint choice, ``get_checkpoint()``: ``'bf16x3'`` by default, so that what a run logs and which weights
+    it keeps agree with the fp32 reference to ~1e-6 instead of the bf16 mode's 1e-2 (``set_metric_precision`` /
+    ``CODES_B200_METRIC_PRECISION``; ``'bf16'`` restores the fastest path).  ``set_precision('fp32')`` always wins."""
+    import os
+    if precision_mode() == "fp32":
+        return "fp32"
+    if _METRIC_PRECISION["mode"] is None:
+        _METRIC_PRECISION["mode"] = os.environ.get("CODES_B200_METRIC_PRECISION", "bf16x3").lower()
+    return _METRIC_PRECISION["mode"]
+
+
+def set_metric_precision(mode: str) -> None:
+    if mode not in PRECISION_MODES:
+        raise ValueError("metric precision must be 'fp32', 'bf16' or 'bf16x3'")
+    _METRIC_PRECISION["mode"] = mode
 
 
 _TRAIN_PRECISION = {"mode": None}
@@ -547,12 +611,18 @@ def run_chain(spec: ChainSpec, x: Tensor, weights, biases, tc_train: bool = True
     1/h^2 = n_timesteps^2, latent_neural_ode.py:560-604)."""
     needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in weights)
                                               or (spec.slope is not None and spec.slope.requires_grad))
-    if not needs_grad and precision_mode() == "bf16" and not spec.slope_stale():
+    mode = precision_mode()
+    if not needs_grad and mode == "bf16" and not spec.slope_stale():
         from . import tc
         if tc.supported(spec):
             return tc.chain_forward(spec, x, weights, biases)
         if tc.train_supported(spec) and x.numel() // max(spec.dims[0], 1) >= TC_TRAIN_MIN_ROWS:
             return tc.gemm_chain_forward(spec, x, weights, biases)    # too wide for the fused kernel: GEMM per layer
+    if not needs_grad and mode == "bf16x3" and not spec.slope_stale():
+        from . import tc
+        if (tc.x3_supported(spec) and x.numel() // max(spec.dims[0], 1) >= X3_MIN_ROWS
+                and max(spec.dims[1:-1], default=0) >= X3_MIN_WIDTH):
+            return tc.x3_chain_forward(spec, x, weights, biases)      # fp32-grade on the tensor cores
     if needs_grad and tc_train and _use_tc_training(spec, x):
         from . import tc
         return tc.train_chain(spec, x, weights, biases)
@@ -581,7 +651,7 @@ def try_fused_multionet(model, branch_input: Tensor, trunk_input: Tensor):
     if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
         return None
     if precision_mode() != "bf16":
-        return None
+        return None          # fp32 / bf16x3: the two nets go through run_chain, then the fp32 combine kernel
     from . import tc
     if not hasattr(tc, "multionet_forward"):
         return None

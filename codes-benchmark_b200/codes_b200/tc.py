@@ -76,6 +76,56 @@ def chain_forward(spec, x, weights, biases):
     return y.reshape(*x.shape[:-1], spec.dims[-1])
 
 
+# --------------------------------------------------------------------------- split precision (bf16x3)
+class _X3Plan:
+    def __init__(self, spec, device):
+        self.handle = C.c_void_p()
+        with torch.cuda.device(device):
+            check(lib().cb_tc_x3_create(C.byref(spec.desc), device.index or 0, C.byref(self.handle)), "tc_x3_create")
+        self.versions = None
+        self.workspace = {}
+        self._fin = weakref.finalize(self, lib().cb_tc_x3_destroy, self.handle)
+
+
+_X3_PLANS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def x3_supported(spec) -> bool:
+    """fp32-grade tensor-core chains: any chain with an identity / tanh final activation and a fixed slope."""
+    return available() and spec.final_act in ("identity", "tanh")
+
+
+def x3_chain_forward(spec, x, weights, biases):
+    """Gradient-free y = chain(x) at fp32-grade accuracy on the tensor cores (three bf16 pieces per fp32 operand, six
+    piece products per Linear, ``cb_tc_x3_forward``); x:(..., dims[0]) fp32 -> (..., dims[-1]) fp32."""
+    dev = x.device
+    per_spec = _X3_PLANS.setdefault(spec, {})
+    plan = per_spec.get(dev.index)
+    if plan is None:
+        plan = per_spec[dev.index] = _X3Plan(spec, dev)
+    x2 = x.reshape(-1, spec.dims[0])
+    if x2.dtype != torch.float32 or not x2.is_contiguous():
+        x2 = x2.float().contiguous()
+    rows = x2.shape[0]
+    L = lib()
+    with torch.cuda.device(dev):
+        versions = _versions(weights) + _versions(biases)
+        if versions != plan.versions:
+            check(L.cb_tc_x3_set_weights(plan.handle, ptr_array(_f32(weights)), ptr_array(_f32(biases)), _stream(dev)),
+                  "tc_x3_set_weights")
+            plan.versions = versions
+        y = torch.empty((rows, spec.dims[-1]), device=dev, dtype=torch.float32)
+        if rows:
+            nbytes = int(L.cb_tc_x3_workspace_bytes(plan.handle, rows))
+            skey = torch.cuda.current_stream(dev).cuda_stream       # predict() pipelines batches on two streams
+            ws = plan.workspace.get(skey)
+            if ws is None or ws.numel() < nbytes:
+                ws = plan.workspace[skey] = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            check(L.cb_tc_x3_forward(plan.handle, C.c_void_p(x2.data_ptr()), rows, C.c_void_p(y.data_ptr()),
+                                     C.c_void_p(ws.data_ptr()), ws.numel(), _stream(dev)), "tc_x3_forward")
+    return y.reshape(*x.shape[:-1], spec.dims[-1])
+
+
 class _GroupedChainPlan:
     def __init__(self, spec, n_groups, device):
         self.handle = C.c_void_p()

@@ -433,6 +433,81 @@ __global__ void denorm_kernel(const float* __restrict__ x, int64_t total, int Q,
   }
 }
 
+// --------------------------------------------------------------- MultiONet on the (trajectory x time) grid, fp32
+// y[n, t, q] = denorm(sum_{k in split_q} B[n, k] * Tr[t, k])  -- the split scalar product of MultiONet.forward
+// (deeponet.py:241-253) on de-duplicated operands: B = branch net output per TRAJECTORY (n, n_out), Tr = trunk net
+// output per GRID POINT (T, n_out); fp32 FFMA, the contraction of the fp32-grade inference mode (the bf16 mode uses the
+// tcgen05 kernel of cb_tc_grid.cu).  One block = 64 trajectories x 112 grid points, loop over the quantities; per
+// quantity a register-tiled (64 x len_q) . (len_q x 112) product, thread = 4 trajectories x 7 grid points, operands
+// staged k-major in shared memory in chunks of 32 features.  De-normalisation as cb_denormalize.
+constexpr int kGcN = 64, kGcT = 112, kGcK = 32, kGcLdB = kGcN + 4, kGcLdT = kGcT;
+__global__ void __launch_bounds__(256) grid_combine_f32_kernel(const float* __restrict__ B, const float* __restrict__ Tr,
+                                                               int64_t n_traj, int T, int n_out, int Q, int mode,
+                                                               const float* __restrict__ dmin,
+                                                               const float* __restrict__ dmax, int pow10,
+                                                               float* __restrict__ y) {
+  __shared__ __align__(16) float Bs[kGcK][kGcLdB];
+  __shared__ __align__(16) float Ts[kGcK][kGcLdT];
+  const int tid = threadIdx.x;
+  const int tn = tid >> 4, tt = tid & 15;                 // trajectories [4 tn, 4 tn + 4), grid points tt + 16 j
+  const int64_t n0 = (int64_t)blockIdx.x * kGcN;
+  const int t0 = blockIdx.y * kGcT;
+  const int base = n_out / Q, rem = n_out % Q;
+  for (int q = 0; q < Q; ++q) {
+    const int len = base + (q < rem ? 1 : 0), off = q * base + (q < rem ? q : rem);
+    float acc[4][7];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 7; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < len; k0 += kGcK) {
+      __syncthreads();
+      // stage B (64 x 32) and Tr (112 x 32) chunk, transposed to k-major; coalesced along k
+      for (int e = tid; e < kGcN * kGcK; e += 256) {
+        const int r = e >> 5, k = e & 31;
+        const int64_t n = n0 + r;
+        Bs[k][r] = (n < n_traj && k0 + k < len) ? __ldg(B + n * n_out + off + k0 + k) : 0.f;
+      }
+      for (int e = tid; e < kGcT * kGcK; e += 256) {
+        const int r = e >> 5, k = e & 31;
+        const int t = t0 + r;
+        Ts[k][r] = (t < T && k0 + k < len) ? __ldg(Tr + (int64_t)t * n_out + off + k0 + k) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < kGcK; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&Bs[k][tn * 4]);
+        float b[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) b[j] = Ts[k][tt + 16 * j];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
+          acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
+          acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
+          acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+        }
+      }
+    }
+    float lo = 0.f, span = 0.f;
+    if (mode == 1) { lo = __ldg(dmin + q); span = __ldg(dmax + q) - lo; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t n = n0 + tn * 4 + i;
+      if (n >= n_traj) continue;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int t = t0 + tt + 16 * j;
+        if (t >= T) continue;
+        float v = acc[i][j];
+        if (mode == 1) v = (v + 1.f) * span / 2.f + lo;   // abstract_surrogate.py:468 op order
+        if (pow10) v = exp10f(v);
+        y[(n * T + t) * Q + q] = v;
+      }
+    }
+  }
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -795,6 +870,22 @@ extern "C" int32_t cb_denormalize(const float* d_x, int64_t n_rows, int32_t n_q,
   if (n_rows == 0) return CB_OK;
   denorm_kernel<<<grid_for(n_rows * n_q), kThreads, 0, (cudaStream_t)stream>>>(
       d_x, n_rows * n_q, n_q, mode, d_min, d_max, pow10, d_out);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+extern "C" int32_t cb_deeponet_grid_combine_f32(const float* d_branch_out, const float* d_trunk_out, int64_t n_traj,
+                                                int32_t n_t, int32_t n_outputs, int32_t n_quantities, int32_t mode,
+                                                const float* d_min, const float* d_max, int32_t pow10, float* d_y,
+                                                void* stream) {
+  CB_CHECK_ARG(n_traj >= 0 && n_t >= 1 && n_quantities >= 1 && n_outputs >= n_quantities, "bad grid-combine shape");
+  CB_CHECK_ARG(mode == 0 || (mode == 1 && d_min && d_max), "bad normalisation mode %d", mode);
+  if (n_traj == 0) return CB_OK;
+  CB_CHECK_ARG(d_branch_out && d_trunk_out && d_y, "NULL pointer argument");
+  CB_CHECK_ARG(n_traj <= (int64_t)kGcN * 0x7fffffff, "too many trajectories");
+  dim3 grid((unsigned)((n_traj + kGcN - 1) / kGcN), (unsigned)((n_t + kGcT - 1) / kGcT));
+  grid_combine_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_branch_out, d_trunk_out, n_traj, n_t, n_outputs,
+                                                                  n_quantities, mode, d_min, d_max, pow10, d_y);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

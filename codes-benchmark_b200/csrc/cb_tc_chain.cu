@@ -15,10 +15,11 @@
 // the same time and the epilogue multiplies them and segment-sums over each quantity's f columns,
 // so the two (rows x Q*f) fp32 tensors of the reference (deeponet.py:241-253) never exist.
 //
-// Warp roles (320 threads):   warp 0     TMA producer (1 elected thread)
-//                             warp 1     tcgen05.mma issuer (1 elected thread) + TMEM alloc/dealloc
-//                             warps 2-9  epilogue: two warps per TMEM lane quarter (32 rows), each
-//                                        taking every other 32-column group of a chunk
+// Warp roles of don_final_kernel (352 threads; the chain kernels use 12 epilogue warps, see kCThreads):
+//                             warp 0      TMA producer (1 elected thread)
+//                             warps 1-2   tcgen05.mma issuers (1 elected thread each; warp 1 also TMEM alloc/dealloc)
+//                             warps 3-10  epilogue: two warps per TMEM lane quarter (32 rows), each
+//                                         taking every other 32-column group of a chunk
 // Work items ("jobs") are (layer, 128-column output chunk); MMA of job j+1 overlaps the epilogue of
 // job j through the TMEM slot ring, and layer l+1 starts on the k-blocks whose producing chunks of
 // layer l are already written (fine-grained dependency through the `epi_done` counter).
@@ -45,7 +46,14 @@ constexpr int kMaxJobs = 96;
 constexpr int kMaxGroups = 128;      // 32-column groups of the MultiONet output layer (<= 4096 columns)
 constexpr int kMaxStages = 12;
 constexpr int kEpiThreads = 256;   // 8 epilogue warps: two per TMEM lane quarter, splitting the columns
-constexpr int kThreads = 64 + kEpiThreads;
+// MultiONet final kernel: TWO tcgen05.mma issuing warps (warp 1 drives the branch accumulators, warp 2 the trunk
+// accumulators): issuing one MMA occupies the issuing thread for ~45 cycles while a 128-column instruction is 64 tensor
+// cycles, and the per-stage barrier / descriptor work comes on top -- one instruction stream kept the tensor pipe 51 %
+// busy (profiles/r1_don_final_pair_ncu_full.md); two independent streams on disjoint TMEM slots and weight stages do not
+// change a single operand or the order of any accumulation.
+constexpr int kFIssuers = 2;
+constexpr int kFFirstEpi = 1 + kFIssuers;
+constexpr int kFThreads = 32 * kFFirstEpi + kEpiThreads;
 // chain kernels: EW/4 epilogue warps per TMEM lane quarter ("column classes"), each taking every (EW/4)-th 32-column
 // group.  12 warps = 3 classes: a 288-column layer (the 275-wide MultiONet nets) is 9 groups = 3 per warp, and 448
 // threads leave 146 registers per thread (the TS kernel keeps up to 4 packed groups + one raw group in registers)
@@ -933,7 +941,7 @@ chain_ts_kernel(const __grid_constant__ ChainParams P) {
 // (own activation tiles, own half of every weight stage; transaction bytes credited to the leader's
 // barriers) and their own epilogue (own 128 TMEM lanes); tcgen05.commit multicasts to both CTAs.
 template <bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFThreads, 1)
 don_final_kernel(const __grid_constant__ FinalParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -1027,14 +1035,19 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
         }
       }
     }
-  } else if (warp == 1) {
-    // MMA issuer: warp-converged control flow, one elected lane issues (PAIR: leader CTA only)
+  } else if (warp < kFFirstEpi) {
+    // MMA issuers: warp-converged control flow, one elected lane issues (PAIR: leader CTA only).  Issuer `net` owns the
+    // jobs (chunk j, net): TMEM slots gs = 2 * job + net and the weight stages the producer filled for them
+    // ([net * nkb, net * nkb + nkb) of every run of 2 * nkb stages).
     if (leader) {
-      int stage = 0; uint32_t phase = 0;
-      int gs = 0;   // global slot-use counter (2 per job)
+      const int net = warp - 1;
       const int nkb = P.nkb;
+      int stage = net * nkb; uint32_t phase = 0;
+      while (stage >= P.stages) { stage -= P.stages; phase ^= 1; }
+      int gs = net;   // global slot-use counter (2 per job)
       const int last_nks = P.ksteps - (nkb - 1) * 4;
       const uint64_t bdesc0 = make_smem_desc(ST0);
+      const uint64_t adesc0 = make_smem_desc(net ? XT : XB);
       long long c_in = 0, c_tempty = 0, c_full = 0, c_issue = 0;
       const long long c_start = CB_CLK();
       for (int it = 0; it < n_my_tiles; ++it) {
@@ -1042,64 +1055,61 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
         mbar_wait(C.bar_in, it & 1);
         tcgen05_fence_after();
         c_in += CB_CLK() - c0;
-        for (int j = 0; j < P.n_jobs; ++j) {
+        for (int j = 0; j < P.n_jobs; ++j, gs += 2) {
           const int ncols = min(kChunkN, P.n_out - j * kChunkN);
           const uint32_t idesc = PAIR ? make_idesc_pair(ncols) : make_idesc(ncols);
-          for (int net = 0; net < 2; ++net, ++gs) {
-            const int slot = gs & (kSlots - 1);
-            const uint32_t use = (uint32_t)(gs / kSlots);
+          const int slot = gs & (kSlots - 1);
+          const uint32_t use = (uint32_t)(gs / kSlots);
+          c0 = CB_CLK();
+          mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
+          tcgen05_fence_after();
+          c_tempty += CB_CLK() - c0;
+          const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
+          for (int kb = 0; kb < nkb; ++kb) {
             c0 = CB_CLK();
-            mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
+            mbar_wait(C.bar_full + 8 * stage, phase);
             tcgen05_fence_after();
-            c_tempty += CB_CLK() - c0;
-            const uint64_t adesc0 = make_smem_desc(net ? XT : XB);
-            const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
-            for (int kb = 0; kb < nkb; ++kb) {
-              c0 = CB_CLK();
-              mbar_wait(C.bar_full + 8 * stage, phase);
-              tcgen05_fence_after();
-              const long long c1 = CB_CLK();
-              c_full += c1 - c0;
-              const int nks = (kb == nkb - 1) ? last_nks : 4;
-              const uint64_t adesc = adesc0 + (uint64_t)(kb * (kKBlockBytes >> 4));
-              const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kStageBytes >> 4));
-              if (elect_one()) {
-                if constexpr (PAIR) {
-                  umma_bf16_pair(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
-#pragma unroll
-                  for (int ks = 1; ks < 4; ++ks)
-                    if (ks < nks) umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
-                  umma_commit_pair(C.bar_empty + 8 * stage);
-                } else {
-                  umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
-#pragma unroll
-                  for (int ks = 1; ks < 4; ++ks)
-                    if (ks < nks) umma_bf16(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
-                  umma_commit(C.bar_empty + 8 * stage);
-                }
-              }
-              __syncwarp();
-              c_issue += CB_CLK() - c1;
-              if (++stage == P.stages) { stage = 0; phase ^= 1; }
-            }
+            const long long c1 = CB_CLK();
+            c_full += c1 - c0;
+            const int nks = (kb == nkb - 1) ? last_nks : 4;
+            const uint64_t adesc = adesc0 + (uint64_t)(kb * (kKBlockBytes >> 4));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kStageBytes >> 4));
             if (elect_one()) {
-              if constexpr (PAIR) umma_commit_pair(C.bar_tfull + 8 * slot);
-              else umma_commit(C.bar_tfull + 8 * slot);
+              if constexpr (PAIR) {
+                umma_bf16_pair(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+#pragma unroll
+                for (int ks = 1; ks < 4; ++ks)
+                  if (ks < nks) umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
+                umma_commit_pair(C.bar_empty + 8 * stage);
+                if (kb == nkb - 1) umma_commit_pair(C.bar_tfull + 8 * slot);
+              } else {
+                umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+#pragma unroll
+                for (int ks = 1; ks < 4; ++ks)
+                  if (ks < nks) umma_bf16(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
+                umma_commit(C.bar_empty + 8 * stage);
+                if (kb == nkb - 1) umma_commit(C.bar_tfull + 8 * slot);
+              }
             }
             __syncwarp();
+            c_issue += CB_CLK() - c1;
+            if (++stage == P.stages) { stage = 0; phase ^= 1; }
           }
+          // the other net's stages of this chunk
+          stage += nkb;
+          while (stage >= P.stages) { stage -= P.stages; phase ^= 1; }
         }
       }
       if (P.dbg && blockIdx.x == 0 && lane == 0) {
-        P.dbg[0] = CB_CLK() - c_start; P.dbg[1] = c_in; P.dbg[2] = c_tempty; P.dbg[3] = c_full; P.dbg[4] = c_issue;
-        P.dbg[5] = n_my_tiles;
+        long long* o = P.dbg + 8 * net;
+        o[0] = CB_CLK() - c_start; o[1] = c_in; o[2] = c_tempty; o[3] = c_full; o[4] = c_issue; o[5] = n_my_tiles;
       }
     }
   } else {
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
-    const int h = (warp - 2) >> 2;          // this warp takes the 32-column groups with (group & 1) == h
-    const int et = threadIdx.x - 64;        // 0..255
+    const int h = (warp - kFFirstEpi) >> 2;   // this warp takes the 32-column groups with (group & 1) == h
+    const int et = threadIdx.x - 32 * kFFirstEpi;   // 0..255
     // Each of the two column-half warps of a row keeps ONE running partial per quantity in a register
     // and adds it to y exactly once (red.global.add on the pre-zeroed output): every y[r,q] is
     // 0 + a + b with a, b the two halves' partials -> commutative, hence bitwise deterministic.
@@ -1116,6 +1126,8 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
       cur_acc += s;
     };
     int gs = 0;
+    long long e_wait = 0;
+    const long long e_start = CB_CLK();
     for (int it = 0; it < n_my_tiles; ++it) {
       const int tile = PAIR ? (my0 + it * stride) * 2 + (int)rank : my0 + it * stride;
       const long long row_g = (long long)tile * kTileM + r;
@@ -1123,8 +1135,10 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
       for (int j = 0; j < P.n_jobs; ++j, gs += 2) {
         const int ncols = min(kChunkN, P.n_out - j * kChunkN);
         const int slot_b = gs & (kSlots - 1), slot_t = (gs + 1) & (kSlots - 1);
+        const long long e0 = CB_CLK();
         mbar_wait(C.bar_tfull + 8 * slot_b, (uint32_t)(gs / kSlots) & 1);
         mbar_wait(C.bar_tfull + 8 * slot_t, (uint32_t)((gs + 1) / kSlots) & 1);
+        e_wait += CB_CLK() - e0;
         tcgen05_fence_after();
         const uint32_t ta_b = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)slot_b * kChunkN;
         const uint32_t ta_t = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)slot_t * kChunkN;
@@ -1194,6 +1208,7 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
       epi_bar_sync();    // every epilogue warp has released its TMEM slots and consumed the tile
       if (et == 0) red_release_inc(C.epi_done);
     }
+    if (P.dbg && blockIdx.x == 0 && et == 0) { P.dbg[16] = CB_CLK() - e_start; P.dbg[17] = e_wait; }
   }
   if constexpr (PAIR) {
     tcgen05_fence_before();
@@ -2023,7 +2038,7 @@ static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_
   const int grid = F.num_tiles < grid_cap() ? F.num_tiles : grid_cap();
   F.dbg = nullptr;
   const char* dbg_env = getenv("CB_TC_FINAL_DBG");
-  if (dbg_env) { CB_CUDA(cudaMalloc(&F.dbg, 64)); CB_CUDA(cudaMemsetAsync(F.dbg, 0, 64, st)); }
+  if (dbg_env) { CB_CUDA(cudaMalloc(&F.dbg, 192)); CB_CUDA(cudaMemsetAsync(F.dbg, 0, 192, st)); }
   if (m->pair) {
     // one cluster of two CTAs per pair of 128-row tiles, persistent over the pairs
     const int pairs = (F.num_tiles + 1) / 2;
@@ -2032,7 +2047,7 @@ static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kFThreads);
     cfg.dynamicSmemBytes = m->smem_pair;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -2041,16 +2056,19 @@ static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_
     cfg.attrs = attr; cfg.numAttrs = 1;
     CB_CUDA(cudaLaunchKernelEx(&cfg, don_final_kernel<true>, F));
   } else {
-    don_final_kernel<false><<<grid, kThreads, m->smem_final, st>>>(F);
+    don_final_kernel<false><<<grid, kFThreads, m->smem_final, st>>>(F);
   }
   CB_LAUNCH_CHECK();
   if (dbg_env) {
-    long long h[8];
+    long long h[24];
     CB_CUDA(cudaStreamSynchronize(st));
-    CB_CUDA(cudaMemcpy(h, F.dbg, 64, cudaMemcpyDeviceToHost));
+    CB_CUDA(cudaMemcpy(h, F.dbg, 192, cudaMemcpyDeviceToHost));
     cudaFree(F.dbg);
-    fprintf(stderr, "[final dbg] MMA warp of CTA 0: total %lld cycles over %lld tiles: wait A tiles %lld, wait TMEM slot %lld, "
-                    "wait weight stage %lld, issue %lld\n", h[0], h[5], h[1], h[2], h[3], h[4]);
+    for (int net = 0; net < 2; ++net)
+      fprintf(stderr, "[final dbg] MMA warp %d of CTA 0: total %lld cycles over %lld tiles: wait A tiles %lld, wait TMEM slot %lld, "
+                      "wait weight stage %lld, issue %lld\n", net, h[8 * net], h[8 * net + 5], h[8 * net + 1], h[8 * net + 2],
+              h[8 * net + 3], h[8 * net + 4]);
+    fprintf(stderr, "[final dbg] epilogue thread 0 of CTA 0: total %lld cycles, waiting for accumulators %lld\n", h[16], h[17]);
   }
   if (ev) cudaEventRecord(ev[3], st);
   return CB_OK;

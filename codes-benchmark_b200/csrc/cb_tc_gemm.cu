@@ -64,6 +64,13 @@ struct GemmParams {
   long long m_bound;           // valid output rows
   float* out_f32;              // fp32 outputs (EPI_*_F32: (m_bound, n_true) dense; EPI_WGRAD: partials)
   long long ld_out_f32, partial_stride;
+  // split-precision ("bf16x3") forward GEMMs: both operands are stored as three bf16 segments [hi | mid | lo] of their
+  // fp32 values along K (segment s at columns [s * seg_cols, s * seg_cols + seg_cols)); the reduction runs over
+  // n_terms (A segment, B segment) pairs, smallest products first, into ONE fp32 accumulator.  n_terms = 1: plain bf16.
+  int n_terms, kk_total;       // kk_total = n_terms * kblocks
+  int a_seg_cols, b_seg_cols;
+  int8_t term_a[8], term_b[8];
+  int out_segs, out_seg_cols;  // EPI_FWD_BF16: the activation leaves as out_segs segments out_seg_cols columns apart
 };
 
 struct Item { int m_tile, n_blk0, n_nblk, kb0, kb1, split; };
@@ -79,7 +86,7 @@ __device__ __forceinline__ Item decode_item(const GemmParams& P, int item) {
   it.n_nblk = base + (nt < rem ? 1 : 0);
   it.n_blk0 = nt * base + (nt < rem ? nt : rem);
   it.kb0 = it.split * P.kb_per_split;
-  it.kb1 = min(P.kblocks, it.kb0 + P.kb_per_split);
+  it.kb1 = min(P.kk_total, it.kb0 + P.kb_per_split);
   return it;
 }
 
@@ -212,24 +219,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode_item(P, item);
       const uint32_t bytes = (uint32_t)kStageA + (P.b_mn ? (uint32_t)it.n_nblk * kBoxBytes : (uint32_t)P.b_box_rows * 128u);
-      for (int kb = it.kb0; kb < it.kb1; ++kb) {
+      int term = it.kb0 / P.kblocks, kb = it.kb0 - term * P.kblocks;
+      for (int kk = it.kb0; kk < it.kb1; ++kk) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         if (elect_one()) {
           const uint32_t sa = base + stage * P.stage_bytes, sb = sa + kStageA, full = bar_full + 8 * stage;
           mbar_arrive_expect_tx(full, bytes);
+          const int ka = P.term_a[term] * P.a_seg_cols + kb * kBlockK, kbb = P.term_b[term] * P.b_seg_cols + kb * kBlockK;
           if (P.a_mn) {
-            tma_load_2d(sa, &P.tmA, it.m_tile * kTileM, kb * kBlockK, full);
-            tma_load_2d(sa + kBoxBytes, &P.tmA, it.m_tile * kTileM + 64, kb * kBlockK, full);
+            tma_load_2d(sa, &P.tmA, it.m_tile * kTileM, ka, full);
+            tma_load_2d(sa + kBoxBytes, &P.tmA, it.m_tile * kTileM + 64, ka, full);
           } else {
-            tma_load_2d(sa, &P.tmA, kb * kBlockK, it.m_tile * kTileM, full);
+            tma_load_2d(sa, &P.tmA, ka, it.m_tile * kTileM, full);
           }
           if (P.b_mn) {
             for (int g = 0; g < it.n_nblk; ++g)
-              tma_load_2d(sb + g * kBoxBytes, &P.tmB, (it.n_blk0 + g) * 64, kb * kBlockK, full);
+              tma_load_2d(sb + g * kBoxBytes, &P.tmB, (it.n_blk0 + g) * 64, kbb, full);
           } else {
-            tma_load_2d(sb, &P.tmB, kb * kBlockK, it.n_blk0 * 64, full);
+            tma_load_2d(sb, &P.tmB, kbb, it.n_blk0 * 64, full);
           }
         }
+        if (++kb == P.kblocks) { kb = 0; ++term; }
         __syncwarp();
         if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
@@ -247,15 +257,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)slot * kAccCols;
       const uint32_t idesc = make_idesc_mn(it.n_nblk * 64, P.a_mn, P.b_mn);
-      for (int kb = it.kb0; kb < it.kb1; ++kb) {
+      int kb = it.kb0 % P.kblocks;
+      for (int kk = it.kb0; kk < it.kb1; ++kk) {
         mbar_wait(bar_full + 8 * stage, phase);
         tcgen05_fence_after();
         const uint32_t sa = base + stage * P.stage_bytes, sb = sa + kStageA;
         const uint64_t adesc = P.a_mn ? make_smem_desc_mn(sa) : make_smem_desc(sa);
         const uint64_t bdesc = P.b_mn ? make_smem_desc_mn(sb) : make_smem_desc(sb);
         const int nks = (kb == P.kblocks - 1) ? P.last_nks : 4;
+        if (++kb == P.kblocks) kb = 0;
         if (elect_one()) {
-          umma_bf16(d_tmem, adesc, bdesc, idesc, kb != it.kb0 ? 1u : 0u);
+          umma_bf16(d_tmem, adesc, bdesc, idesc, kk != it.kb0 ? 1u : 0u);
 #pragma unroll
           for (int ks = 1; ks < 4; ++ks)
             if (ks < nks) umma_bf16(d_tmem, adesc + a_step * ks, bdesc + b_step * ks, idesc, 1u);
@@ -336,13 +348,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             }
           } else {
             tmem_ld_wait();
-            act_block_rt(P.act, v, f, P.act_param);
+            if (P.out_segs > 1) {
+              // split precision: the accurate activations of the fp32 path (cb_common.cuh), not the MUFU approximations
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = act_fwd(P.act, __uint_as_float(v[i]), P.act_param);
+            } else {
+              act_block_rt(P.act, v, f, P.act_param);
+            }
           }
-          const int n_pass = (MODE == EPI_FWD_BF16 && P.save_z) ? 2 : 1;
+          // passes: the activation [, its pre-activation (save_z)] -- or, split precision, the hi / mid / lo bf16
+          // segments of the fp32 activation: f <- f - bf16(f) after every pass
+          const bool split_out = MODE == EPI_FWD_BF16 && P.out_segs > 1;
+          const int n_pass = split_out ? P.out_segs : ((MODE == EPI_FWD_BF16 && P.save_z) ? 2 : 1);
           for (int pass = 0; pass < n_pass; ++pass) {
             const int pbuf = (gb + pass) % kNumStaging;
             const uint32_t pst = OST + pbuf * kStaging;
-            if (pass == 1) {
+            if (pass >= 1) {
               if (leader) tma_store_wait_read_le(1);
               asm volatile("bar.sync 1, 256;" ::: "memory");
             }
@@ -352,12 +373,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
               float o[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                float val = pass == 0 ? f[g * 8 + i] : __uint_as_float(v[g * 8 + i]);
+                float val = (pass == 0 || split_out) ? f[g * 8 + i] : __uint_as_float(v[g * 8 + i]);
                 if (edge) {
                   const int col = col0 + g * 8 + i;
                   if (col >= P.n_true) val = (pass == 0 && col == P.ones_col) ? 1.f : 0.f;
                 }
                 o[i] = val;
+                if (split_out) f[g * 8 + i] = val - __bfloat162float(__float2bfloat16_rn(val));
               }
               const int c8 = h * 4 + g;
               st_shared_v4(pst + (uint32_t)(r * 128 + ((c8 ^ (r & 7)) << 4)), pack_bf16(o[0], o[1]),
@@ -366,7 +388,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             fence_proxy_async();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (leader) {
-              tma_store_2d(pass == 0 ? &P.tmOut : &P.tmOut2, pst, col_blk, it.m_tile * kTileM);
+              if (split_out) tma_store_2d(&P.tmOut, pst, col_blk + pass * P.out_seg_cols, it.m_tile * kTileM);
+              else tma_store_2d(pass == 0 ? &P.tmOut : &P.tmOut2, pst, col_blk, it.m_tile * kTileM);
               tma_store_commit();
             }
           }
@@ -627,6 +650,53 @@ __global__ void combine_bf16_bwd_kernel(const __nv_bfloat16* __restrict__ B, con
   }
 }
 
+
+// ---------------------------------------------------------------------------- split precision ("bf16x3") packing
+// v = hi + mid + lo with hi = bf16(v), mid = bf16(v - hi), lo = bf16(v - hi - mid): 24 significant bits, exact for every
+// fp32 value whose three pieces stay normal.  Segment s of a row lives at columns [s * ld, s * ld + ld).
+__device__ __forceinline__ void split3(float v, float& hi, float& mid, float& lo) {
+  hi = __bfloat162float(__float2bfloat16_rn(v));
+  const float r1 = v - hi;
+  mid = __bfloat162float(__float2bfloat16_rn(r1));
+  lo = __bfloat162float(__float2bfloat16_rn(r1 - mid));
+}
+// fp32 (rows, K) -> bf16 (rows, 3 * ld): segments of [x, 1, 0...]
+__global__ void pack_rows_x3_kernel(const float* __restrict__ x, long long rows, int K, int ld,
+                                    __nv_bfloat16* __restrict__ out) {
+  const long long total = rows * (ld / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (ld / 8);
+    const int c0 = (int)(i % (ld / 8)) * 8;
+    float h[8], m[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float v = c < K ? x[r * K + c] : (c == K ? 1.f : 0.f);
+      split3(v, h[j], m[j], l[j]);
+    }
+    __nv_bfloat16* o = out + r * 3 * ld + c0;
+    *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+    *reinterpret_cast<uint4*>(o + ld) = make_uint4(pack_bf16(m[0], m[1]), pack_bf16(m[2], m[3]), pack_bf16(m[4], m[5]), pack_bf16(m[6], m[7]));
+    *reinterpret_cast<uint4*>(o + 2 * ld) = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
+  }
+}
+// fp32 nn.Linear weight (N,K) + bias -> bf16 (wp_rows, 3 * ld): segments of [W | b | 0]
+__global__ void pack_weight_x3_kernel(const float* __restrict__ W, const float* __restrict__ b, int N, int K,
+                                      int wp_rows, int ld, __nv_bfloat16* __restrict__ Wp) {
+  const long long total = (long long)wp_rows * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ld), k = (int)(i % ld);
+    float v = 0.f;
+    if (n < N) v = k < K ? W[(long long)n * K + k] : (k == K && b ? b[n] : 0.f);
+    float h, m, l;
+    split3(v, h, m, l);
+    __nv_bfloat16* o = Wp + (long long)n * 3 * ld + k;
+    o[0] = __float2bfloat16(h); o[ld] = __float2bfloat16(m); o[2 * ld] = __float2bfloat16(l);
+  }
+}
+
 }  // namespace tcg
 }  // namespace cb
 
@@ -658,6 +728,8 @@ struct GemmCall {
   const __nv_bfloat16* aux; long long ld_aux;
   int splits;              // wgrad only
   long long partial_stride;
+  int x3;                  // split precision: A = (a_rows, 3 * a_ld), B = (b_rows, 3 * b_ld) as [hi | mid | lo] segments;
+                           // EPI_FWD_BF16 output = (out_rows, 3 * out_ld) segments
 };
 
 template <int MODE>
@@ -683,6 +755,20 @@ static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
   P.splits = c.splits > 0 ? c.splits : 1;
   P.kb_per_split = (P.kblocks + P.splits - 1) / P.splits;
   P.splits = (P.kblocks + P.kb_per_split - 1) / P.kb_per_split;
+  P.n_terms = 1; P.kk_total = P.kblocks; P.out_segs = 1;
+  if (c.x3) {
+    // (A segment, B segment) pairs whose products are >= 2^-18 of the leading one, smallest first:
+    // lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi   (0 = hi, 1 = mid, 2 = lo)
+    static const int8_t ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
+    CB_CHECK_ARG(P.splits == 1 && !c.a_mn && !c.b_mn, "split precision: forward GEMMs only");
+    P.n_terms = 6;
+    for (int t = 0; t < 6; ++t) { P.term_a[t] = ta[t]; P.term_b[t] = tb[t]; }
+    P.a_seg_cols = (int)c.a_ld; P.b_seg_cols = (int)c.b_ld;
+    P.kk_total = P.n_terms * P.kblocks;
+    P.kb_per_split = P.kk_total;
+    if (c.mode == EPI_FWD_BF16) { P.out_segs = 3; P.out_seg_cols = (int)c.out_ld; }
+  }
+  const long long seg_mul = c.x3 ? 3 : 1;
   P.a_mn = c.a_mn; P.b_mn = c.b_mn;
   const int widest = (P.n_blocks + P.n_tiles - 1) / P.n_tiles;
   P.b_box_rows = widest * 64;
@@ -698,10 +784,10 @@ static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
   CB_CHECK_ARG(P.kblocks >= 1 && P.m_tiles >= 1 && P.n_blocks >= 1 && P.stages >= 2, "empty GEMM");
   bool ok = true;
   if (c.a_mn) ok = ok && encode_bf16_box(&P.tmA, c.A, c.a_rows, c.a_cols, c.a_ld, 64, 64);
-  else ok = ok && encode_bf16_box(&P.tmA, c.A, c.a_rows, c.a_cols, c.a_ld, 64, kTileM);
+  else ok = ok && encode_bf16_box(&P.tmA, c.A, c.a_rows, c.a_cols * seg_mul, c.a_ld * seg_mul, 64, kTileM);
   if (c.b_mn) ok = ok && encode_bf16_box(&P.tmB, c.B, c.b_rows, c.b_cols, c.b_ld, 64, 64);
-  else ok = ok && encode_bf16_box(&P.tmB, c.B, c.b_rows, c.b_cols, c.b_ld, 64, P.b_box_rows);
-  if (c.out_bf16) ok = ok && encode_bf16_box(&P.tmOut, c.out_bf16, c.out_rows, c.out_ld, c.out_ld, 64, kTileM);
+  else ok = ok && encode_bf16_box(&P.tmB, c.B, c.b_rows, c.b_cols * seg_mul, c.b_ld * seg_mul, 64, P.b_box_rows);
+  if (c.out_bf16) ok = ok && encode_bf16_box(&P.tmOut, c.out_bf16, c.out_rows, c.out_ld * seg_mul, c.out_ld * seg_mul, 64, kTileM);
   if (c.out2_bf16) ok = ok && encode_bf16_box(&P.tmOut2, c.out2_bf16, c.out_rows, c.out_ld, c.out_ld, 64, kTileM);
   if (c.aux_kind != AUX_NONE) ok = ok && encode_bf16_box(&P.tmAux, c.aux, c.out_rows, c.ld_aux, c.ld_aux, 64, kTileM);
   CB_CHECK_ARG(ok, "cuTensorMapEncodeTiled failed for a GEMM operand");
@@ -919,6 +1005,116 @@ extern "C" int32_t cb_tc_train_infer(cb_tc_train* p, const float* const* d_W, co
   CB_CHECK_ARG(((uintptr_t)d_workspace & 255) == 0, "workspace must be 256-byte aligned");
   if (workspace_bytes < cb_tc_train_infer_bytes(p, rows)) { set_error("workspace too small"); return CB_ERR_WORKSPACE; }
   return chain_forward_impl(p, d_W, d_b, d_x, rows, d_y, reinterpret_cast<uint8_t*>(d_workspace), false, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------- split-precision ("bf16x3") inference
+// Gradient-free y = chain(x) at fp32-class accuracy on the tensor cores: every fp32 operand (input rows, weights,
+// biases, hidden activations) is carried as three bf16 segments and every Linear is ONE tcgen05 GEMM over the six
+// (activation segment, weight segment) pairs whose products reach 2^-18 of the leading one (launch_gemm, x3 = 1):
+// 6x the MMA work of the bf16 mode, fp32 accumulation in TMEM throughout.  Replaces the FFMA kernels of the exact mode
+// where only the RESULT has to be fp32-grade (validate(), recorded metrics): same reference code as cb_tc_train_infer
+// (fcnn.py:91-98, deeponet.py:35-48,71-84, latent_neural_ode.py:702-742).
+struct cb_tc_x3 {
+  cb_mlp_desc desc;
+  int device, n;
+  int ld[CB_MAX_LAYERS + 1];
+  __nv_bfloat16* wp[CB_MAX_LAYERS];   // (wp_rows, 3 * ld[i])
+  int wp_rows[CB_MAX_LAYERS];
+  int weights_set;
+};
+
+extern "C" void cb_tc_x3_destroy(cb_tc_x3* p) {
+  if (!p) return;
+  for (int i = 0; i < CB_MAX_LAYERS; ++i) if (p->wp[i]) cudaFree(p->wp[i]);
+  delete p;
+}
+
+extern "C" int32_t cb_tc_x3_create(const cb_mlp_desc* desc, int32_t device, cb_tc_x3** out) {
+  if (int32_t e = check_desc(desc)) return e;
+  CB_CHECK_ARG(out != nullptr, "out is NULL");
+  CB_CHECK_ARG(desc->final_act == CB_ACT_IDENTITY || desc->final_act == CB_ACT_TANH, "final activation must be identity or tanh");
+  CB_CHECK_ARG(tensor_map_encoder() != nullptr, "cuTensorMapEncodeTiled unavailable");
+  CB_CUDA(cudaSetDevice(device));
+  cb_tc_x3* p = new cb_tc_x3();
+  memset(p, 0, sizeof(*p));
+  p->desc = *desc; p->device = device; p->n = desc->n_layers;
+  for (int i = 0; i <= p->n; ++i) p->ld[i] = round_up_i(desc->dims[i] + 1, 64);
+  for (int i = 0; i < p->n; ++i) {
+    p->wp_rows[i] = round_up_i(p->ld[i + 1], 256);
+    if (cudaMalloc(&p->wp[i], (size_t)p->wp_rows[i] * 3 * p->ld[i] * 2) != cudaSuccess) {
+      cb_tc_x3_destroy(p);
+      set_error("cudaMalloc of the split weight copies failed");
+      return CB_ERR_CUDA;
+    }
+  }
+  *out = p;
+  return CB_OK;
+}
+
+extern "C" int32_t cb_tc_x3_set_weights(cb_tc_x3* p, const float* const* d_W, const float* const* d_b, void* stream) {
+  CB_CHECK_ARG(p && d_W && d_b, "NULL pointer argument");
+  for (int i = 0; i < p->n; ++i) {
+    CB_CHECK_ARG(d_W[i] != nullptr, "weight %d is NULL", i);
+    const long long total = (long long)p->wp_rows[i] * p->ld[i];
+    pack_weight_x3_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(d_W[i], d_b[i], p->desc.dims[i + 1],
+                                                                              p->desc.dims[i], p->wp_rows[i], p->ld[i], p->wp[i]);
+    CB_LAUNCH_CHECK();
+  }
+  p->weights_set = 1;
+  return CB_OK;
+}
+
+extern "C" int64_t cb_tc_x3_workspace_bytes(const cb_tc_x3* p, int64_t rows) {
+  if (!p || rows < 0) return -1;
+  int ld_max = 0;
+  for (int i = 0; i < p->n; ++i) ld_max = p->ld[i] > ld_max ? p->ld[i] : ld_max;
+  return 2 * rows_pad(rows) * 3 * ld_max * 2 + 256;
+}
+
+extern "C" int32_t cb_tc_x3_forward(cb_tc_x3* p, const float* d_x, int64_t rows, float* d_y, void* d_workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  CB_CHECK_ARG(p != nullptr && p->weights_set, "cb_tc_x3_set_weights must be called first");
+  CB_CHECK_ARG(rows >= 0, "rows < 0");
+  if (rows == 0) return CB_OK;
+  CB_CHECK_ARG(d_x && d_y && d_workspace, "NULL pointer argument");
+  CB_CHECK_ARG(((uintptr_t)d_workspace & 255) == 0, "workspace must be 256-byte aligned");
+  if (workspace_bytes < cb_tc_x3_workspace_bytes(p, rows)) { set_error("workspace too small"); return CB_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = p->n;
+  const long long rp = rows_pad(rows);
+  int ld_max = 0;
+  for (int i = 0; i < n; ++i) ld_max = p->ld[i] > ld_max ? p->ld[i] : ld_max;
+  __nv_bfloat16* buf[2] = {reinterpret_cast<__nv_bfloat16*>(d_workspace),
+                           reinterpret_cast<__nv_bfloat16*>(d_workspace) + rp * 3 * ld_max};
+  pack_rows_x3_kernel<<<ew_blocks(rows * (p->ld[0] / 8)), 256, 0, st>>>(d_x, rows, p->desc.dims[0], p->ld[0], buf[0]);
+  CB_LAUNCH_CHECK();
+  for (int i = 0; i < n; ++i) {
+    const bool last = i == n - 1;
+    GemmCall c;
+    memset(&c, 0, sizeof(c));
+    c.x3 = 1;
+    c.A = buf[i & 1];
+    c.a_rows = rows; c.a_cols = p->ld[i]; c.a_ld = p->ld[i];
+    c.B = p->wp[i]; c.b_rows = p->wp_rows[i]; c.b_cols = p->ld[i]; c.b_ld = p->ld[i];
+    c.m_out = rows; c.k_total = p->desc.dims[i] + 1;
+    c.n_true = p->desc.dims[i + 1];
+    c.act_param = p->desc.act_param;
+    if (last) {
+      c.mode = EPI_FWD_F32;
+      c.n_out_ld = round_up_i(c.n_true, 64);
+      c.out_f32 = d_y; c.ld_out_f32 = c.n_true;
+      c.act = p->desc.final_act;
+    } else {
+      c.mode = EPI_FWD_BF16;
+      c.n_out_ld = p->ld[i + 1];
+      c.out_bf16 = buf[(i + 1) & 1];
+      c.out_rows = rows; c.out_ld = p->ld[i + 1];
+      c.act = p->desc.act;
+      c.ones_col = c.n_true;
+    }
+    if (int32_t e = launch_gemm(c, st)) return e;
+  }
+  return CB_OK;
 }
 
 // Gradients of the chain.  d_dy: fp32 (rows, dims[n]) (or bf16 (rows, ld[n]) with zero padding when the

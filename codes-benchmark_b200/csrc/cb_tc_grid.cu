@@ -15,8 +15,10 @@
 // The trunk outputs Tr (T, n_out) are computed once per call by the caller (fp32 chain) and packed into the
 // UMMA B-operand image trp[c][q][kb] = 16 grid points x 64 features (SWIZZLE_128B, K-major).
 //
-// don_grid_kernel (352 threads, persistent, one CTA per SM): warp 0 streams the feature tiles A (128 trajectories x
-// 64 features, TMA) through a ring of 16 KiB stages, warp 2 bulk-copies the item's trunk tiles (Q*nkb*2 KiB), warp 1
+// don_grid_kernel (352 threads, persistent, one CTA per SM): warp 0 streams, per quantity, the feature tiles A (128
+// trajectories x 64 features per k-block, TMA) AND the matching trunk tiles (16 grid points x 64 features, bulk copy)
+// through one ring of stages (the trunk tiles used to sit in shared memory per item: 116 KB at Q = 29, which left three
+// feature stages = 96 KB in flight per SM and made the kernel latency-bound on the L2 -> SM stream), warp 1
 // issues tcgen05.mma M=128 N=16: accumulator of quantity q = TMEM columns [16q, 16q+16) (lane = trajectory,
 // column = grid point), warps 3-10 read TMEM (tcgen05.ld 32x32b.x4: 4 grid points of one quantity), apply the
 // de-normalisation of AbstractSurrogateModel.denormalize (abstract_surrogate.py:435-487) and write 4*Q contiguous
@@ -71,9 +73,9 @@ template <int Q>
 __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_constant__ GridParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t trp_s = base;                                           // trunk tiles of the current item
-  const uint32_t a_s = base + ((P.trp_bytes + 1023) & ~1023);            // feature stages
-  const uint32_t stage_bytes = (uint32_t)P.nkb * kKBlockBytes;             // one stage = all k-blocks of one quantity
+  const uint32_t a_s = base;                                               // stages
+  const uint32_t feat_bytes = (uint32_t)P.nkb * kKBlockBytes;              // one stage = all k-blocks of one quantity:
+  const uint32_t stage_bytes = feat_bytes + (uint32_t)P.nkb * kTrTile;     //   feature tiles, then the trunk tiles
   const uint32_t ctrl = a_s + P.stages * stage_bytes;
   const uint32_t bar_full = ctrl, bar_empty = ctrl + 8 * kGMaxStages;
   const uint32_t bar_trp = ctrl + 16 * kGMaxStages, bar_acc_full = bar_trp + 8, bar_acc_empty = bar_trp + 16;
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_trp, 1); mbar_init(bar_acc_full, 1); mbar_init(bar_acc_empty, kGEpiWarps);
+    mbar_init(bar_acc_full, 1); mbar_init(bar_acc_empty, kGEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 2 * Q) {
@@ -106,29 +108,17 @@ __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_con
     if (elect_one()) {
       int s = 0; uint32_t ph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int tile = item / P.n_tchunks;
+        const int tile = item / P.n_tchunks, c = item % P.n_tchunks;
         for (int q = 0; q < Q; ++q) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
           for (int kb = 0; kb < P.nkb; ++kb)
             tma_load_2d(a_s + s * stage_bytes + kb * kKBlockBytes, &P.tmF, q * P.KQ + kb * kBlockK, tile * kTileM,
                         bar_full + 8 * s);
+          bulk_load(a_s + s * stage_bytes + feat_bytes,
+                    reinterpret_cast<const uint8_t*>(P.trp) + ((size_t)c * Q + q) * (size_t)(P.nkb * kTrTile),
+                    (uint32_t)(P.nkb * kTrTile), bar_full + 8 * s);
           if (++s == P.stages) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ---------------------------------------------------------------- trunk-tile loader (one bulk copy per item)
-    if (elect_one()) {
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int c = item % P.n_tchunks;
-        if (it > 0) mbar_wait(bar_acc_full, (it - 1) & 1);     // the previous item's MMAs have read their tiles
-        mbar_arrive_expect_tx(bar_trp, P.trp_bytes);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(P.trp) + (size_t)c * P.trp_bytes;
-        for (int off = 0; off < P.trp_bytes; off += 32768) {
-          const int n = min(32768, P.trp_bytes - off);
-          bulk_load(trp_s + off, src + off, n, bar_trp);
         }
       }
     }
@@ -139,8 +129,6 @@ __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_con
     const long long t_all = GCLK();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       long long tq = GCLK();
-      mbar_wait(bar_trp, it & 1);
-      GACC(1, tq); tq = GCLK();
       if (it > 0) mbar_wait(bar_acc_empty, (it - 1) & 1);
       GACC(2, tq);
       tcgen05_fence_after();
@@ -151,7 +139,7 @@ __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_con
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t adesc0 = make_smem_desc(a_s + s * stage_bytes);
-          const uint64_t bdesc0 = make_smem_desc(trp_s + q * P.nkb * kTrTile);
+          const uint64_t bdesc0 = make_smem_desc(a_s + s * stage_bytes + feat_bytes);
           const uint32_t d_tmem = tmem_base + q * kTChunk;
           for (int kb = 0; kb < P.nkb; ++kb) {
             const int nks = (kb == P.nkb - 1) ? P.last_nks : 4;
@@ -171,7 +159,7 @@ __global__ void __launch_bounds__(kGThreads, 1) don_grid_kernel(const __grid_con
     }
     GACC(0, t_all);
     if (P.dbg && blockIdx.x == 0 && lane == 0) P.dbg[7] = it;
-  } else {
+  } else if (warp >= 3) {
     // ---------------------------------------------------------------- epilogue: TMEM -> de-normalise -> (n, T, Q)
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = (warp - 3) >> 2;             // grid points [8*half, 8*half + 8) of the item's 16
@@ -321,12 +309,13 @@ static bool grid_shape(const cb_mlp_desc* b, int Q, int* KQ, int* nkb, int* last
 }
 
 static bool grid_smem(int Q, int nkb, int* stages, size_t* smem) {
-  const long long trp = ((long long)Q * nkb * kTrTile + 1023) / 1024 * 1024;
-  const long long stage = (long long)nkb * kKBlockBytes;
-  long long st = ((long long)kMaxSmem - 1024 - trp - kGCtrl - 2 * kGMaxQ * 4) / stage;
+  (void)Q;
+  const long long stage = (long long)nkb * (kKBlockBytes + kTrTile);
+  long long st = ((long long)kMaxSmem - 1024 - kGCtrl - 2 * kGMaxQ * 4) / stage;
   if (st > kGMaxStages) st = kGMaxStages;
+  if (const char* e = getenv("CB_GRID_MAX_STAGES")) { const int c = atoi(e); if (c >= 2 && c < st) st = c; }   // experiment knob
   *stages = (int)st;
-  *smem = (size_t)(1024 + trp + (st > 0 ? st : 0) * stage + kGCtrl + 2 * kGMaxQ * 4);
+  *smem = (size_t)(1024 + (st > 0 ? st : 0) * stage + kGCtrl + 2 * kGMaxQ * 4);
   return st >= 2;
 }
 

@@ -123,6 +123,16 @@ CB_API int32_t cb_deeponet_combine_bwd(const float* d_branch, const float* d_tru
                                 int64_t rows, int32_t n_outputs, int32_t n_quantities,
                                 float* d_dbranch, float* d_dtrunk, void* stream);
 
+/* The same split scalar product on DE-DUPLICATED operands (loaders built by MultiONet.prepare_data repeat x0 T times
+ * and tile the time grid N times, deeponet.py:371-374): d_branch_out (n_traj, n_outputs) = branch net per trajectory,
+ * d_trunk_out (n_t, n_outputs) = trunk net per grid point;
+ *   y[n, t, q] = denorm(sum_{k in split_q} branch_out[n,k] * trunk_out[t,k]),  y (n_traj, n_t, n_quantities) fp32,
+ * fp32 FFMA, de-normalisation fused as in cb_denormalize (mode 0: none, 1: minmax with d_min/d_max (Q); pow10). */
+CB_API int32_t cb_deeponet_grid_combine_f32(const float* d_branch_out, const float* d_trunk_out, int64_t n_traj,
+                                     int32_t n_t, int32_t n_outputs, int32_t n_quantities, int32_t mode,
+                                     const float* d_min, const float* d_max, int32_t pow10, float* d_y,
+                                     void* stream);
+
 /* ----------------------------------------------------- LatentPoly polynomial */
 /* z[b,t,l] = z0[b,l] + sum_{i=1..deg} C[l,i-1]*t[t]^i
  * (Polynomial.forward latent_poly.py:489-512 + broadcast add :380). */
@@ -381,6 +391,20 @@ CB_API int64_t cb_tc_train_infer_bytes(const cb_tc_train* plan, int64_t rows);
 CB_API int32_t cb_tc_train_infer(cb_tc_train* plan, const float* const* d_W, const float* const* d_b,
                                  const float* d_x, int64_t rows, void* d_y, void* d_workspace,
                                  int64_t workspace_bytes, void* stream);
+/* ---- split-precision ("bf16x3") inference: fp32-grade results from the tensor cores.
+ * Gradient-free y = chain(x) (same reference code as cb_tc_train_infer: fcnn.py:91-98, deeponet.py:35-48,71-84,
+ * latent_neural_ode.py:702-742) with every fp32 operand -- input rows, weights, biases, hidden activations --
+ * carried as three bf16 segments hi + mid + lo (24 significant bits) and every Linear run as ONE tcgen05 GEMM over
+ * the six segment pairs whose products reach 2^-18 of the leading one (fp32 accumulation in TMEM, accurate
+ * activations).  6x the tensor-core work of the bf16 mode; results agree with the fp32 FFMA mode to ~1e-6
+ * (tests/test_gpu_x3.py).  final_act must be IDENTITY or TANH.  Workspace: 256-byte aligned. */
+typedef struct cb_tc_x3 cb_tc_x3;
+CB_API int32_t cb_tc_x3_create(const cb_mlp_desc* desc, int32_t device, cb_tc_x3** out);
+CB_API void cb_tc_x3_destroy(cb_tc_x3* plan);
+CB_API int32_t cb_tc_x3_set_weights(cb_tc_x3* plan, const float* const* d_W, const float* const* d_b, void* stream);
+CB_API int64_t cb_tc_x3_workspace_bytes(const cb_tc_x3* plan, int64_t rows);
+CB_API int32_t cb_tc_x3_forward(cb_tc_x3* plan, const float* d_x, int64_t rows, float* d_y, void* d_workspace,
+                                int64_t workspace_bytes, void* stream);
 /* d_dW[i] (out,in) / d_db[i] (out) fp32 are OVERWRITTEN (deterministic split reduction); d_dx may be
  * NULL; d_y (the fp32 forward output) is only read for a tanh final activation. */
 CB_API int32_t cb_tc_train_backward(cb_tc_train* plan, const void* d_dy, const float* d_y, int64_t rows,

@@ -130,8 +130,149 @@ __global__ void __launch_bounds__(128, 1) bench2(int N, int n_kb_iters, int nkb,
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+
+// bench3: MMAs (SS, N columns) issued by warp 1 while warp 2 streams `bulk_kb` KiB bulk copies global -> shared memory
+// back to back (the weight ring of the real kernels): does concurrent async-proxy write traffic slow the tensor pipe?
+__global__ void __launch_bounds__(128, 1) bench3(int N, int n_mma, int nkb, const uint8_t* gsrc, int bulk_bytes, int n_bulk,
+                                                 long long* out) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar, bbar[4];
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bbar[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_ptr)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(nkb * 16384 + nkb * 32768) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(raw + (base - smem_u32(raw)))[i] = 0x3c003c00u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_ptr;
+  const uint32_t scratch = base + nkb * 16384 + nkb * 32768;     // 4 x bulk_bytes ring
+  if (threadIdx.x == 32) {
+    const uint32_t A = base, B = base + nkb * 16384;
+    const uint32_t idesc = make_idesc(N);
+    long long t0 = clock64();
+    for (int i = 0; i < n_mma; ++i) {
+      const int ks = i & 3, kb = (i >> 2) % nkb;
+      umma(tmem, make_desc(A + kb * 16384 + ks * 32), make_desc(B + (N > 128 ? kb * 32768 : kb * 16384) + ks * 32), idesc, i > 0);
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    mbar_wait(smem_u32(&bar), 0);
+    out[1] = clock64() - t0;
+  } else if (threadIdx.x == 64 && n_bulk > 0) {
+    long long t0 = clock64();
+    for (int i = 0; i < n_bulk; ++i) {
+      const int s = i & 3;
+      if (i >= 4) mbar_wait(smem_u32(&bbar[s]), ((i >> 2) - 1) & 1);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bbar[s])), "r"(bulk_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(scratch + s * bulk_bytes), "l"(gsrc + (size_t)((i * 7 + blockIdx.x) % 64) * bulk_bytes), "r"(bulk_bytes), "r"(smem_u32(&bbar[s])) : "memory");
+    }
+    for (int i = n_bulk < 4 ? 0 : n_bulk - 4; i < n_bulk; ++i) mbar_wait(smem_u32(&bbar[i & 3]), (i >> 2) & 1);
+    out[0] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+
+// bench4: CTA pairs (cluster of 2, tcgen05.mma.cta_group::2, M = 256): the leader issues n_mma instructions of N
+// columns; each CTA holds its 128 A rows and HALF of the B rows (N/2 x 64).  n_issuers = 2: two warps of the leader
+// alternate accumulators (columns [0,N) and [N,2N) when they fit).
+__device__ __forceinline__ uint32_t idesc_pair(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) bench4(int N, int n_mma, int nkb, int n_issuers, long long* out) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_ptr)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(nkb * 16384 * 2) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(raw + (base - smem_u32(raw)))[i] = 0x3c003c00u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_ptr;
+  const int iss = (threadIdx.x >> 5) - 1;
+  if (rank == 0 && (threadIdx.x & 31) == 0 && iss >= 0 && iss < n_issuers) {
+    const uint32_t A = base, B = base + nkb * 16384;
+    const uint32_t idesc = idesc_pair(N);
+    const uint32_t d = tmem + (2 * N <= 512 ? iss * N : 0);
+    long long t0 = clock64();
+    const int mine = n_mma / n_issuers;
+    for (int i = 0; i < mine; ++i) {
+      const int ks = i & 3, kb = (i >> 2) % nkb;
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                   ::"r"(d), "l"(make_desc(A + kb * 16384 + ks * 32)), "l"(make_desc(B + kb * 16384 + ks * 32)), "r"(idesc), "r"((uint32_t)(i > 0)) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(&bar[iss])), "h"((uint16_t)3) : "memory");
+    long long t1 = clock64();
+    mbar_wait(smem_u32(&bar[iss]), 0);
+    if (blockIdx.x == 0) { out[2 * iss] = t1 - t0; out[2 * iss + 1] = clock64() - t0; }
+  } else if (rank == 1 && threadIdx.x == 32) {
+    for (int i = 0; i < n_issuers; ++i) mbar_wait(smem_u32(&bar[i]), 0);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 int main() {
-  long long* d; cudaMalloc(&d, 16);
+  long long* d; cudaMalloc(&d, 64);
+  {
+    cudaFuncSetAttribute(bench4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int ctas : {2, 148})
+      for (int N : {64, 128, 256})
+        for (int ni : {1, 2}) {
+          const int n_mma = 1024;
+          for (int rep = 0; rep < 2; ++rep) bench4<<<ctas, 128, 200 * 1024>>>(N, n_mma, 2, ni, d);
+          long long h[4]; cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
+          cudaError_t e = cudaGetLastError();
+          const long long done = ni == 2 ? (h[1] > h[3] ? h[1] : h[3]) : h[1];
+          printf("bench4 pair ctas=%3d N=%3d issuers=%d: issue %.1f, complete %.1f cyc per M=256 mma (ideal %d) %s\n", ctas, N, ni,
+                 (double)h[0] / (n_mma / ni), (double)done / n_mma, 128 * N / 256, e == cudaSuccess ? "" : cudaGetErrorString(e));
+        }
+  }
+  {
+    uint8_t* g; cudaMalloc(&g, 64 * 32768); cudaMemset(g, 0, 64 * 32768);
+    cudaFuncSetAttribute(bench3, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    for (int ctas : {1, 148})
+      for (int N : {128, 256})
+        for (int bulk : {0, 8192, 16384}) {
+          const int n_mma = 1024;
+          const int n_bulk = bulk ? (int)((long long)n_mma * (128 * N / 256) * 48 / bulk) : 0;   // ~48 B/clk if it kept up
+          for (int rep = 0; rep < 2; ++rep) bench3<<<ctas, 128, 220 * 1024>>>(N, n_mma, 2, g, bulk ? bulk : 8192, n_bulk, d);
+          long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+          cudaError_t e = cudaGetLastError();
+          printf("bench3 ctas=%3d N=%3d bulk=%5d x %4d: mma %.1f cyc each (ideal %d); copies %.1f B/clk %s\n", ctas, N, bulk, n_bulk,
+                 (double)h[1] / n_mma, 128 * N / 256, n_bulk ? (double)n_bulk * bulk / (double)h[0] : 0.0,
+                 e == cudaSuccess ? "" : cudaGetErrorString(e));
+        }
+  }
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int n_mma = 512;
   for (int mode = 0; mode < 2; ++mode)
