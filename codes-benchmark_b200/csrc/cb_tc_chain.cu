@@ -53,7 +53,14 @@ constexpr int kEpiThreads = 256;   // 8 epilogue warps: two per TMEM lane quarte
 // change a single operand or the order of any accumulation.
 constexpr int kFIssuers = 2;
 constexpr int kFFirstEpi = 1 + kFIssuers;
-constexpr int kFThreads = 32 * kFFirstEpi + kEpiThreads;
+#ifndef CB_FINAL_EPI_WARPS
+#define CB_FINAL_EPI_WARPS 8
+#endif
+constexpr int kFEpiWarps = CB_FINAL_EPI_WARPS;          // 8: two column classes per TMEM lane quarter; 16: four
+constexpr int kFEpiThreads = 32 * kFEpiWarps;
+constexpr int kFColStride = 32 * (kFEpiWarps / 4);
+constexpr int kFThreads = 32 * kFFirstEpi + kFEpiThreads;
+__device__ __forceinline__ void final_epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kFEpiThreads) : "memory"); }
 // chain kernels: EW/4 epilogue warps per TMEM lane quarter ("column classes"), each taking every (EW/4)-th 32-column
 // group.  12 warps = 3 classes: a 288-column layer (the 275-wide MultiONet nets) is 9 groups = 3 per warp, and 448
 // threads leave 146 registers per thread (the TS kernel keeps up to 4 packed groups + one raw group in registers)
@@ -961,7 +968,7 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
     if (threadIdx.x == 0) {
       for (int s = 0; s < P.stages; ++s) { mbar_init(C.bar_full + 8 * s, 1); mbar_init(C.bar_empty + 8 * s, 1); }
       // tempty: one arrival per epilogue warp of BOTH CTAs (on the leader's barrier)
-      for (int s = 0; s < kSlots; ++s) { mbar_init(C.bar_tfull + 8 * s, 1); mbar_init(C.bar_tempty + 8 * s, 2 * (kEpiThreads / 32)); }
+      for (int s = 0; s < kSlots; ++s) { mbar_init(C.bar_tfull + 8 * s, 1); mbar_init(C.bar_tempty + 8 * s, 2 * kFEpiWarps); }
       mbar_init(C.bar_in, 1);
       *C.epi_done = 0;
       *C.in_staged = 0;
@@ -977,7 +984,7 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
     tcgen05_fence_after();
     tmem_base = *reinterpret_cast<volatile uint32_t*>(C.tmem_ptr);
   } else {
-    tmem_base = setup_cta(C, P.stages, warp);
+    tmem_base = setup_cta(C, P.stages, warp, kFEpiThreads);
   }
   const int units = PAIR ? (P.num_tiles + 1) / 2 : P.num_tiles;            // tile pairs / tiles
   const int my0 = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
@@ -1142,7 +1149,7 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
         tcgen05_fence_after();
         const uint32_t ta_b = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)slot_b * kChunkN;
         const uint32_t ta_t = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)slot_t * kChunkN;
-        for (int c0 = h * 32; c0 < ncols; c0 += 64) {
+        for (int c0 = h * 32; c0 < ncols; c0 += kFColStride) {
           uint32_t vb[32], vt[32];
           const int w = min(32, ncols - c0);
           if (w == 32) { tmem_ld32(ta_b + c0, vb); tmem_ld32(ta_t + c0, vt); }
@@ -1196,8 +1203,8 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
         if constexpr (PAIR) {
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive_cluster(L_bar_tempty + 8 * slot_b);
-            mbar_arrive_cluster(L_bar_tempty + 8 * slot_t);
+            mbar_arrive_cluster_relaxed(L_bar_tempty + 8 * slot_b);
+            mbar_arrive_cluster_relaxed(L_bar_tempty + 8 * slot_t);
           }
         } else {
           mbar_arrive(C.bar_tempty + 8 * slot_b);
@@ -1205,7 +1212,7 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
         }
       }
       add_to(-1, 0.f);   // flush the last running partial
-      epi_bar_sync();    // every epilogue warp has released its TMEM slots and consumed the tile
+      final_epi_bar_sync();    // every epilogue warp has released its TMEM slots and consumed the tile
       if (et == 0) red_release_inc(C.epi_done);
     }
     if (P.dbg && blockIdx.x == 0 && et == 0) { P.dbg[16] = CB_CLK() - e_start; P.dbg[17] = e_wait; }
@@ -1700,7 +1707,7 @@ extern "C" int32_t cb_tc_chain_set_weights(cb_tc_chain* plan, const float* const
 // launch helper shared by the public forward and the MultiONet pipeline
 static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorMap* in_map, int64_t rows,
                             float* d_y, const CUtensorMap* out_map, cudaStream_t st, __nv_bfloat16* d_yb = nullptr,
-                            int ld_yb = 0) {
+                            int ld_yb = 0, __nv_bfloat16* const* save = nullptr, const int* save_ld = nullptr) {
   ChainParams P = plan->P;
   P.x = d_x; P.y = d_y; P.rows = rows;
   if (in_map) { P.in_mode = IN_BF16_TMA; P.tmap_in = *in_map; }
@@ -1722,8 +1729,13 @@ static int32_t chain_launch(cb_tc_chain* plan, const float* d_x, const CUtensorM
     cb::tcmt::MtParams M = plan->M;
     M.x = d_x; M.y = d_y; M.yb = d_yb; M.ld_yb = ld_yb; M.rows = rows; M.num_tiles = P.num_tiles;
     M.n_groups = 1; M.x_gstride = 0; M.y_gstride = 0;
+    for (int l = 0; l < CB_MAX_LAYERS; ++l) {
+      M.save[l] = (save && l < plan->desc.n_layers - 1) ? save[l] : nullptr;
+      M.save_ld[l] = (save_ld && l < plan->desc.n_layers - 1) ? save_ld[l] : 0;
+    }
     return cb::tcmt::mt_launch(M, plan->desc.act, st);
   }
+  CB_CHECK_ARG(save == nullptr, "saving the intermediate activations needs the multi-tile chain kernel");
   const bool ts = plan->ts != 0;   // (its weights are packed for the TS kernel: no other kernel may run this plan)
   if (ts) CB_CHECK_ARG(!in_map && (plan->out_mode == OUT_F32 || d_yb != nullptr), "TS chain: unsupported launch mode");
   if (ts) {
@@ -1801,6 +1813,22 @@ int32_t hidden_chain_launch(cb_tc_chain* plan, const float* d_x, int64_t rows, _
   CUtensorMap omap;
   CB_CHECK_ARG(encode_bf16_map(&omap, d_yb, rows, plan->ld_out), "tensor map of the hidden activations failed");
   return chain_launch(plan, d_x, nullptr, rows, nullptr, &omap, st, d_yb, plan->ld_out);
+}
+bool hidden_chain_saves_ok(const cb_tc_chain* plan) { return plan && plan->mt && plan->n_groups <= 1; }
+int32_t hidden_chain_launch_saving(cb_tc_chain* plan, const float* d_x, int64_t rows, __nv_bfloat16* d_yb,
+                                   __nv_bfloat16* const* save, const int* save_ld, cudaStream_t st) {
+  CB_CHECK_ARG(plan && plan->weights_set, "hidden chain: weights not set");
+  CB_CHECK_ARG(hidden_chain_saves_ok(plan), "hidden chain: this plan cannot save its intermediate activations");
+  for (int l = 0; l + 1 < plan->desc.n_layers; ++l) {
+    // every row holds the layer's Np = round_up(width, 16) columns (+ a 16-column k-step for the ones column when
+    // the width is a multiple of 16) written with 16-byte stores
+    const int need = ((plan->desc.dims[l + 1] + 15) & ~15) + ((plan->desc.dims[l + 1] & 15) == 0 ? 16 : 0);
+    CB_CHECK_ARG(save && save_ld && save[l] && save_ld[l] >= need && save_ld[l] % 8 == 0 && ((uintptr_t)save[l] & 15) == 0,
+                 "hidden chain: bad save buffer for layer %d", l);
+  }
+  CUtensorMap omap;
+  CB_CHECK_ARG(encode_bf16_map(&omap, d_yb, rows, plan->ld_out), "tensor map of the hidden activations failed");
+  return chain_launch(plan, d_x, nullptr, rows, nullptr, &omap, st, d_yb, plan->ld_out, save, save_ld);
 }
 }}
 

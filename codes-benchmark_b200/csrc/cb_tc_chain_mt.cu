@@ -49,6 +49,44 @@ constexpr int kMtCtrl = 256;
 #define MCLK() 0ll
 #endif
 
+
+// Row-contiguous global store of one 32-column bf16 group (64 bytes per row, one row per lane): the four lanes of a
+// quad exchange their 16-byte pieces (4 x 4 transpose, two shfl.xor stages) so that store i of the quad writes the 64
+// contiguous bytes of row (quad base + i).  A warp-wide store then touches 8 rows x 64 B instead of 32 rows x 16 B:
+// a quarter of the LSU wavefronts of the direct per-lane stores (which made the saved-activation stores of a training
+// forward more expensive than the layer's MMAs).
+__device__ __forceinline__ void store_group_rows(__nv_bfloat16* base, long long row0, long long n_rows, long long ld,
+                                                 const uint32_t (&R)[16], int lane) {
+  uint32_t p[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) p[i] = R[i];
+  const bool odd = lane & 1, upper = lane & 2;
+#pragma unroll
+  for (int k = 0; k < 4; k += 2) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t send = odd ? p[4 * k + e] : p[4 * (k + 1) + e];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+      if (odd) p[4 * k + e] = recv; else p[4 * (k + 1) + e] = recv;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t send = upper ? p[4 * k + e] : p[4 * (k + 2) + e];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 2);
+      if (upper) p[4 * k + e] = recv; else p[4 * (k + 2) + e] = recv;
+    }
+  }
+  const int j = lane & 3;
+  const long long rbase = row0 + (lane & ~3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (rbase + i < n_rows)
+      *reinterpret_cast<uint4*>(base + (rbase + i) * ld + 8 * j) = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+}
+
 template <int ACT, int NT, int NCH>
 __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_constant__ MtParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -316,14 +354,12 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
                     }
                     if (!last) {
                       if (ww == 32) tmem_st16(a_tmem + (uint32_t)(nbb >> 1), Rs); else tmem_st8(a_tmem + (uint32_t)(nbb >> 1), Rs);
+                    } else if (ww == 32) {
+                      store_group_rows(ybg + nbb, row_g - lane, P.rows, P.ld_yb, Rs, lane);
                     } else if (row_ok) {
                       uint4* dst = reinterpret_cast<uint4*>(ybg + row_g * P.ld_yb + nbb);
                       dst[0] = make_uint4(Rs[0], Rs[1], Rs[2], Rs[3]);
                       dst[1] = make_uint4(Rs[4], Rs[5], Rs[6], Rs[7]);
-                      if (ww == 32) {
-                        dst[2] = make_uint4(Rs[8], Rs[9], Rs[10], Rs[11]);
-                        dst[3] = make_uint4(Rs[12], Rs[13], Rs[14], Rs[15]);
-                      }
                     }
                   }
                 }
@@ -340,6 +376,44 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
                 if (!last) {
                   tmem_st_wait();
                   arrive(bar_aready + 8 * s);
+                  if (P.save[l] != nullptr) {
+                    // training forward: keep the activation for the backward pass.  AFTER the hand-off (the tile's next
+                    // layer is already being issued); chunks 0..nch-2 are re-read from the park area, which this thread
+                    // itself overwrites next
+                    __nv_bfloat16* sv = P.save[l];
+                    const long long sld = P.save_ld[l];
+#pragma unroll
+                    for (int cc = 0; cc < NCH; ++cc) {
+                      const int nbb = cc * kMtChunk + h * 32;
+                      const int ww = min(32, Np - nbb);
+                      if (cc < nch && ww > 0) {
+                        uint32_t Rs[16];
+                        if (cc == c) {
+#pragma unroll
+                          for (int i = 0; i < 16; ++i) Rs[i] = Rc[i];
+                        } else {
+                          const uint32_t pa = park + ((uint32_t)((s * (NCH - 1) + cc) * 4) * (kMtEpiWarps * 32) + et) * 16u;
+#pragma unroll
+                          for (int j = 0; j < 4; ++j)
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(Rs[4 * j]), "=r"(Rs[4 * j + 1]), "=r"(Rs[4 * j + 2]), "=r"(Rs[4 * j + 3])
+                                         : "r"(pa + (uint32_t)j * (kMtEpiWarps * 32 * 16)));
+                        }
+                        if (ww == 32) {
+                          store_group_rows(sv + nbb, row_g - lane, P.rows, sld, Rs, lane);
+                        } else if (row_ok) {
+                          uint4* dst = reinterpret_cast<uint4*>(sv + row_g * sld + nbb);
+                          dst[0] = make_uint4(Rs[0], Rs[1], Rs[2], Rs[3]);
+                          dst[1] = make_uint4(Rs[4], Rs[5], Rs[6], Rs[7]);
+                        }
+                      }
+                    }
+                    if ((N & 15) == 0 && h == 0 && row_ok) {
+                      uint4* dst = reinterpret_cast<uint4*>(sv + row_g * sld + N);
+                      dst[0] = make_uint4(pack_bf16(1.f, 0.f), 0u, 0u, 0u);
+                      dst[1] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                  }
                 }
               }
             }

@@ -845,10 +845,15 @@ struct cb_tc_train {
   __nv_bfloat16* wp[CB_MAX_LAYERS];   // (wp_rows, ld[i])    [W | b | 0]
   __nv_bfloat16* wt[CB_MAX_LAYERS];   // (wt_rows, ld[i+1])  W^T
   int wp_rows[CB_MAX_LAYERS], wt_rows[CB_MAX_LAYERS];
+  // fused forward of the hidden layers (multi-tile TMEM chain kernel of cb_tc_chain_mt.cu writing every activation the
+  // backward pass needs) instead of one GEMM launch per layer; NULL when the chain is outside that kernel's range or the
+  // activation needs its pre-activation saved (GELU / SiLU / Mish)
+  cb_tc_chain* fused_hidden;
 };
 
 extern "C" void cb_tc_train_destroy(cb_tc_train* p) {
   if (!p) return;
+  if (p->fused_hidden) cb_tc_chain_destroy(p->fused_hidden);
   for (int i = 0; i < CB_MAX_LAYERS; ++i) {
     if (p->wp[i]) cudaFree(p->wp[i]);
     if (p->wt[i]) cudaFree(p->wt[i]);
@@ -877,6 +882,16 @@ extern "C" int32_t cb_tc_train_create(const cb_mlp_desc* desc, int32_t device, i
       cb_tc_train_destroy(p);
       set_error("cudaMalloc of the bf16 weight copies failed");
       return CB_ERR_CUDA;
+    }
+  }
+  {
+    // CB_TC_TRAIN_FUSED_FWD=0: one GEMM launch per hidden layer (the pre-fusion path, for comparison)
+    const char* e = getenv("CB_TC_TRAIN_FUSED_FWD");
+    if (!(e && atoi(e) == 0) && p->n >= 3 && !p->needs_z && hidden_chain_supported(desc)) {
+      cb_tc_chain* h = nullptr;
+      if (hidden_chain_create(desc, device, &h) == CB_OK && hidden_chain_saves_ok(h) && hidden_chain_ld(h) == p->ld[p->n - 1])
+        p->fused_hidden = h;
+      else if (h) cb_tc_chain_destroy(h);
     }
   }
   *out = p;
@@ -945,7 +960,17 @@ static int32_t chain_forward_impl(cb_tc_train* p, const float* const* d_W, const
   pack_rows_kernel<<<ew_blocks(rows * (p->ld[0] / 8)), 256, 0, st>>>(d_x, rows, p->desc.dims[0], p->ld[0],
                                                                    p->desc.dims[0], act_ptr(0));
   CB_LAUNCH_CHECK();
-  for (int i = 0; i < n; ++i) {
+  int first = 0;
+  if (keep && p->fused_hidden) {
+    // hidden layers 0 .. n-2 in ONE launch: H_1 .. H_{n-1} written where the per-layer GEMMs would have put them
+    if (int32_t e = cb_tc_chain_set_weights(p->fused_hidden, d_W, d_b, st)) return e;
+    __nv_bfloat16* save[CB_MAX_LAYERS];
+    int save_ld[CB_MAX_LAYERS];
+    for (int l = 0; l + 2 < n; ++l) { save[l] = act_ptr(l + 1); save_ld[l] = p->ld[l + 1]; }
+    if (int32_t e = hidden_chain_launch_saving(p->fused_hidden, d_x, rows, act_ptr(n - 1), save, save_ld, st)) return e;
+    first = n - 1;
+  }
+  for (int i = first; i < n; ++i) {
     const bool last = i == n - 1;
     GemmCall c;
     memset(&c, 0, sizeof(c));

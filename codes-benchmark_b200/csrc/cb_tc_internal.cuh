@@ -16,6 +16,11 @@ bool hidden_chain_supported(const cb_mlp_desc* full);
 int32_t hidden_chain_create(const cb_mlp_desc* full, int device, cb_tc_chain** out);
 int hidden_chain_ld(const cb_tc_chain* plan);
 int32_t hidden_chain_launch(cb_tc_chain* plan, const float* d_x, int64_t rows, __nv_bfloat16* d_yb, cudaStream_t st);
+// Multi-tile plans only (hidden_chain_saves_ok): the same launch that also writes every intermediate activation
+// H_1 .. H_{n-2} as bf16 (rows, save_ld[l]) -- the fused FORWARD of a training step.
+bool hidden_chain_saves_ok(const cb_tc_chain* plan);
+int32_t hidden_chain_launch_saving(cb_tc_chain* plan, const float* d_x, int64_t rows, __nv_bfloat16* d_yb,
+                                   __nv_bfloat16* const* save, const int* save_ld, cudaStream_t st);
 }  // namespace tc
 namespace tcmt {
 // Multi-tile TMEM-resident chain kernel (cb_tc_chain_mt.cu): NT 128-row tiles in flight per CTA, interleaved chunk by
@@ -40,6 +45,11 @@ struct MtParams {
   // share the input) and writes y + g * y_gstride / yb + g * y_gstride
   int n_groups;
   long long w_gstride[CB_MAX_LAYERS], x_gstride, y_gstride;
+  // training forward: the bf16 activation of layer l (incl. the ones column, as the next GEMM's A operand) is ALSO
+  // written to save[l] (rows, save_ld[l]) when non-NULL -- the tensors cb_tc_train_backward needs (l < n_layers - 1;
+  // the last layer's activation is `yb`)
+  __nv_bfloat16* save[CB_MAX_LAYERS];
+  int save_ld[CB_MAX_LAYERS];
 };
 bool mt_supported(const cb_mlp_desc* d, int out_bf16, MtParams* geom /* nullable: nt, aw, slots, slot_bytes, nch.. */);
 size_t mt_packed_elems(int N, int K);

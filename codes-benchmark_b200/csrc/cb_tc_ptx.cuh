@@ -278,6 +278,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The same arrival WITHOUT release semantics.  `.release.cluster` compiles to MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR +
+// CGAERRBAR in front of the SYNCS.ARRIVE, i.e. the warp waits for every memory operation it has in flight (in the
+// MultiONet final kernel: the red.global.add of the running partial sums, an L2 round trip) -- ncu attributed 3.5 of 9
+// stalled warps per issue slot to `membar` and the epilogue, not the tensor pipe, set the kernel's pace.  Use only where
+// the arrival publishes NO generic-proxy memory: a TMEM slot whose tcgen05.ld reads have been waited for
+// (tcgen05.wait::ld) and fenced (tcgen05.fence::before_thread_sync) needs execution ordering only.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // dependency counters that live in the leader CTA's shared memory and are bumped by either CTA of a pair
 __device__ __forceinline__ void red_release_inc_cluster(uint32_t cluster_addr) {
   asm volatile("red.release.cluster.shared::cluster.add.s32 [%0], 1;" ::"r"(cluster_addr) : "memory");

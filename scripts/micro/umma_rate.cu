@@ -241,8 +241,91 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) bench4(int N
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+
+// bench5: TMEM read throughput (tcgen05.ld.32x32b.x32, n_rd_warps warps, each its own lane quarter / column window) with
+// and without a concurrent tcgen05.mma stream (N = 256, SS) on the same SM.
+__global__ void __launch_bounds__(640, 1) bench5(int n_mma, int n_ld, int n_rd_warps, long long* out) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_ptr)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(2 * 16384 + 2 * 32768) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(raw + (base - smem_u32(raw)))[i] = 0x3c003c00u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_ptr;
+  if (threadIdx.x == 32 && n_mma > 0) {
+    const uint32_t A = base, B = base + 2 * 16384;
+    const uint32_t idesc = make_idesc(256);
+    long long t0 = clock64();
+    for (int i = 0; i < n_mma; ++i) {
+      const int ks = i & 3, kb = (i >> 2) & 1;
+      umma(tmem, make_desc(A + kb * 16384 + ks * 32), make_desc(B + kb * 32768 + ks * 32), idesc, i > 0);   // columns [0, 256)
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    mbar_wait(smem_u32(&bar), 0);
+    out[0] = clock64() - t0;
+  } else if (warp >= 4 && warp < 4 + n_rd_warps && n_ld > 0) {
+    const int q = warp & 3, cls = (warp - 4) >> 2;
+    const uint32_t addr = tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(cls % 8) * 32u;   // columns [256, 512): not the MMA's
+    uint32_t acc = 0;
+    long long t0 = clock64();
+    for (int i = 0; i < n_ld; ++i) {
+      uint32_t v[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(addr));
+      if ((i & 3) == 3) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc ^= v[j];
+      }
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const long long dt = clock64() - t0;
+    if (warp == 4 && (threadIdx.x & 31) == 0) { out[1] = dt; out[2] = acc; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 int main() {
   long long* d; cudaMalloc(&d, 64);
+  {
+    cudaFuncSetAttribute(bench5, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int rdw : {4, 8, 16})
+      for (int with_mma : {0, 1})
+        for (int with_ld : {0, 1}) {
+          if (!with_mma && !with_ld) continue;
+          if (!with_ld && rdw != 4) continue;
+          const int n_mma = with_mma ? 16384 : 0, n_ld = with_ld ? 16384 / rdw : 0;   // loads end while the MMAs still run
+          cudaMemset(d, 0, 64);
+          for (int rep = 0; rep < 2; ++rep) bench5<<<148, 640, 200 * 1024>>>(n_mma, n_ld, rdw, d);
+          long long h[3]; cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
+          cudaError_t e = cudaGetLastError();
+          printf("bench5 read warps=%2d mma=%d ld=%d: mma %.1f cyc each (ideal 128); TMEM read %.1f B/clk/SM %s\n", rdw, with_mma, with_ld,
+                 n_mma ? (double)h[0] / n_mma : 0.0, n_ld ? (double)n_ld * rdw * 4096.0 / (double)h[1] : 0.0,
+                 e == cudaSuccess ? "" : cudaGetErrorString(e));
+        }
+  }
   {
     cudaFuncSetAttribute(bench4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     for (int ctas : {2, 148})
