@@ -577,6 +577,33 @@ def run_ours(args):
                  "what": "MultiONet cfg2 fit step (forward + MSE + backward + AdamW), host batches, one model per rank"}
         del tr_model, opt, batches
 
+    # ---- the three inference precisions on the same 65 536-row batches (rank 0; device-resident rows, row path):
+    # 'bf16' is `value`; 'bf16x3' is what validate() / get_checkpoint() run by default (fp32-grade, six bf16 piece
+    # products per Linear on the tensor cores); 'fp32' is the FFMA exactness mode
+    precision_modes = None
+    if rank == 0:
+        precision_modes = {}
+        tg_dummy = preds[:ROWS_PER_STEP]
+        with torch.inference_mode():
+            for mode, reps in (("bf16x3", 10), ("fp32", 3)):
+                with cb.precision_scope(mode):
+                    for i in range(2):
+                        model((branch_all[:ROWS_PER_STEP], trunk_all[:ROWS_PER_STEP], tg_dummy))
+                    torch.cuda.synchronize()
+                    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    p0.record()
+                    for i in range(reps):
+                        lo = ((i + 1) % n_batches) * ROWS_PER_STEP
+                        model((branch_all[lo:lo + ROWS_PER_STEP], trunk_all[lo:lo + ROWS_PER_STEP], tg_dummy))
+                    p1.record()
+                    torch.cuda.synchronize()
+                ms = p0.elapsed_time(p1) / reps
+                precision_modes[mode] = {"value": TRAJ_PER_STEP / (ms * 1e-3), "unit": "trajectories/s", "ms_per_step": ms,
+                                         "algorithmic_tflops": FLOP_PER_ROW * ROWS_PER_STEP / (ms * 1e-3) / 1e12}
+        precision_modes["what"] = ("MultiONet.forward on 65536 device-resident rows under codes_b200.precision_scope(mode): "
+                                   "bf16x3 = fp32-grade results from the tensor cores (three bf16 pieces per fp32 operand, "
+                                   "six piece products per Linear, fp32 combine), the default of validate(); fp32 = FFMA kernels")
+
     if world > 1:
         # every rank must reach the end together (rank 0 also ran the extra legs)
         dist.barrier()
@@ -621,6 +648,7 @@ def run_ours(args):
                        "precision": "bf16 operands, fp32 accumulate (tcgen05)", "parallelism": f"trajectory-sharded x{world}"},
             "clocks": clocks.summary(), "e2e": e2e, "dedup": dedup, "strong": strong, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "reference_gpu": reference_gpu, "train": train,
+            "precision_modes": precision_modes,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

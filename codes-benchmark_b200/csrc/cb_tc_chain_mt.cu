@@ -269,10 +269,13 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
         const int Np = (N + 15) & ~15;
         const int nch = P.nch[l];
         const uint32_t et = threadIdx.x - 32 * kMtFirstEpi;  // epilogue thread index 0..383
-#pragma unroll
+        // (real loops over the chunks and the tiles: the register arrays below are indexed by the fully unrolled inner
+        // loops only; unrolling c and s as well made the kernel 18 k instructions = 290 KB of code, far beyond the
+        // instruction caches -- ncu's top stall reason was `no_instruction`)
+#pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
           if (c < nch) {
-#pragma unroll
+#pragma unroll 1
             for (int s = 0; s < NT; ++s) {
               const long long row_g = ((long long)unit * NT + s) * kTileM + r;
               const bool row_ok = row_g < P.rows;
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
               if (c == nch - 1 && hidden_like) {
                 // every MMA of (tile s, layer l) has retired: overwrite the tile's A operand / write the bf16 output
                 const uint32_t a_tmem = acc + (uint32_t)accw;
-#pragma unroll
+#pragma unroll 1
                 for (int cc = 0; cc < NCH; ++cc) {
                   const int nbb = cc * kMtChunk + h * 32;
                   const int ww = min(32, Np - nbb);
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
                     // itself overwrites next
                     __nv_bfloat16* sv = P.save[l];
                     const long long sld = P.save_ld[l];
-#pragma unroll
+#pragma unroll 1
                     for (int cc = 0; cc < NCH; ++cc) {
                       const int nbb = cc * kMtChunk + h * 32;
                       const int ww = min(32, Np - nbb);
