@@ -48,7 +48,8 @@ class LnodeTape(C.Structure):
 
 _LIB = None
 _LOCK = threading.Lock()
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libcodes_b200.so")
+LIB_PATH = os.environ.get("CODES_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                           "libcodes_b200.so")   # (override: kernel-variant experiments)
 
 _P = C.c_void_p
 _PP = C.POINTER(C.c_void_p)

@@ -133,6 +133,8 @@ class MultiONet(OperatorNetwork):
         if (resident and not (any_order and ds.device is not None)) or (not resident and ds._compact is None):
             return None
         prec = ops.precision_mode()
+        if prec == "fp32":
+            return None          # the exactness mode keeps the reference's row semantics (and its summation order)
         norm = self.normalisation
         mode, do_pow = 0, False
         if norm is not None:
@@ -201,7 +203,7 @@ class MultiONet(OperatorNetwork):
                 targs.reshape(-1, self.n_timesteps, self.n_quantities))
 
     def _grid_forward_f32(self, x0, tg, preds, mode, dmin, dmax, do_pow, chunk: int = 16384):
-        """fp32-grade grid path ('fp32' and 'bf16x3' modes): the branch net once per trajectory through ``run_chain``
+        """fp32-grade grid path ('bf16x3' mode): the branch net once per trajectory through ``run_chain``
         (FFMA kernels or the split-precision tensor-core GEMMs), the trunk net once per grid point on the fp32 kernels,
         then the fp32 contraction ``cb_deeponet_grid_combine_f32`` writes the de-normalised (N, T, Q) block.  Chunked
         over trajectories: the (chunk, Q*f) branch outputs stay at ~190 MB."""

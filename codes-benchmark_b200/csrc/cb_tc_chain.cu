@@ -46,11 +46,11 @@ constexpr int kMaxJobs = 96;
 constexpr int kMaxGroups = 128;      // 32-column groups of the MultiONet output layer (<= 4096 columns)
 constexpr int kMaxStages = 12;
 constexpr int kEpiThreads = 256;   // 8 epilogue warps: two per TMEM lane quarter, splitting the columns
-// MultiONet final kernel: TWO tcgen05.mma issuing warps (warp 1 drives the branch accumulators, warp 2 the trunk
-// accumulators): issuing one MMA occupies the issuing thread for ~45 cycles while a 128-column instruction is 64 tensor
-// cycles, and the per-stage barrier / descriptor work comes on top -- one instruction stream kept the tensor pipe 51 %
-// busy (profiles/r1_don_final_pair_ncu_full.md); two independent streams on disjoint TMEM slots and weight stages do not
-// change a single operand or the order of any accumulation.
+// MultiONet final kernel: room for TWO tcgen05.mma issuing warps (warp 1: branch accumulators, warp 2: trunk
+// accumulators; disjoint TMEM slots and weight stages, no operand or accumulation order changes).  Measured
+// (scripts/micro/umma_rate.cu): one thread issues a cta_group::2 128-column MMA every 88.9 cycles (64 tensor cycles),
+// two threads reach 64.7.  The kernel itself did not get faster -- its pace was set by the epilogue (see
+// mbar_arrive_cluster_relaxed) -- and the second issuer is OFF by default, see multionet_forward_impl.
 constexpr int kFIssuers = 2;
 constexpr int kFFirstEpi = 1 + kFIssuers;
 #ifndef CB_FINAL_EPI_WARPS
@@ -122,6 +122,7 @@ struct FinalParams {
   CUtensorMap tmap_w[2];       // the same buffers as (rows, 64) tensors, 64-row boxes (CTA-pair kernel)
   long long* dbg;              // CB_TC_FINAL_DBG: per-role cycle counters of CTA 0 (debug), else NULL
   int K, ksteps, nkb, n_jobs, n_out, Q, stages;
+  int one_issuer;              // CB_TC_FINAL_ISSUERS=1 (debug / comparison): warp 1 issues the MMAs of both nets
   int seg_base, seg_rem;       // split sizes: seg_base + (q < seg_rem)   (deeponet.py:130-137)
   int16_t grp_q[kMaxGroups];   // quantity whose split contains the first column of 32-column group g
   int16_t grp_end[kMaxGroups]; // end column (exclusive) of that split
@@ -1046,15 +1047,14 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
     // MMA issuers: warp-converged control flow, one elected lane issues (PAIR: leader CTA only).  Issuer `net` owns the
     // jobs (chunk j, net): TMEM slots gs = 2 * job + net and the weight stages the producer filled for them
     // ([net * nkb, net * nkb + nkb) of every run of 2 * nkb stages).
-    if (leader) {
-      const int net = warp - 1;
+    if (leader && !(P.one_issuer && warp == 2)) {
+      const int net0 = P.one_issuer ? 0 : warp - 1, net1 = P.one_issuer ? 2 : warp;   // the nets this warp issues
+      const int net = net0;
       const int nkb = P.nkb;
-      int stage = net * nkb; uint32_t phase = 0;
+      int stage = net0 * nkb; uint32_t phase = 0;
       while (stage >= P.stages) { stage -= P.stages; phase ^= 1; }
-      int gs = net;   // global slot-use counter (2 per job)
       const int last_nks = P.ksteps - (nkb - 1) * 4;
       const uint64_t bdesc0 = make_smem_desc(ST0);
-      const uint64_t adesc0 = make_smem_desc(net ? XT : XB);
       long long c_in = 0, c_tempty = 0, c_full = 0, c_issue = 0;
       const long long c_start = CB_CLK();
       for (int it = 0; it < n_my_tiles; ++it) {
@@ -1062,49 +1062,55 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
         mbar_wait(C.bar_in, it & 1);
         tcgen05_fence_after();
         c_in += CB_CLK() - c0;
-        for (int j = 0; j < P.n_jobs; ++j, gs += 2) {
+        for (int j = 0; j < P.n_jobs; ++j) {
           const int ncols = min(kChunkN, P.n_out - j * kChunkN);
           const uint32_t idesc = PAIR ? make_idesc_pair(ncols) : make_idesc(ncols);
-          const int slot = gs & (kSlots - 1);
-          const uint32_t use = (uint32_t)(gs / kSlots);
-          c0 = CB_CLK();
-          mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
-          tcgen05_fence_after();
-          c_tempty += CB_CLK() - c0;
-          const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
-          for (int kb = 0; kb < nkb; ++kb) {
+          for (int nn = net0; nn < net1; ++nn) {
+            const int gs = 2 * (it * P.n_jobs + j) + nn;   // global slot-use counter (2 per job)
+            const uint64_t adesc0 = make_smem_desc(nn ? XT : XB);
+            const int slot = gs & (kSlots - 1);
+            const uint32_t use = (uint32_t)(gs / kSlots);
             c0 = CB_CLK();
-            mbar_wait(C.bar_full + 8 * stage, phase);
+            mbar_wait(C.bar_tempty + 8 * slot, (use & 1) ^ 1);
             tcgen05_fence_after();
-            const long long c1 = CB_CLK();
-            c_full += c1 - c0;
-            const int nks = (kb == nkb - 1) ? last_nks : 4;
-            const uint64_t adesc = adesc0 + (uint64_t)(kb * (kKBlockBytes >> 4));
-            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kStageBytes >> 4));
-            if (elect_one()) {
-              if constexpr (PAIR) {
-                umma_bf16_pair(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+            c_tempty += CB_CLK() - c0;
+            const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
+            for (int kb = 0; kb < nkb; ++kb) {
+              c0 = CB_CLK();
+              mbar_wait(C.bar_full + 8 * stage, phase);
+              tcgen05_fence_after();
+              const long long c1 = CB_CLK();
+              c_full += c1 - c0;
+              const int nks = (kb == nkb - 1) ? last_nks : 4;
+              const uint64_t adesc = adesc0 + (uint64_t)(kb * (kKBlockBytes >> 4));
+              const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kStageBytes >> 4));
+              if (elect_one()) {
+                if constexpr (PAIR) {
+                  umma_bf16_pair(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
 #pragma unroll
-                for (int ks = 1; ks < 4; ++ks)
-                  if (ks < nks) umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
-                umma_commit_pair(C.bar_empty + 8 * stage);
-                if (kb == nkb - 1) umma_commit_pair(C.bar_tfull + 8 * slot);
-              } else {
-                umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+                  for (int ks = 1; ks < 4; ++ks)
+                    if (ks < nks) umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
+                  umma_commit_pair(C.bar_empty + 8 * stage);
+                  if (kb == nkb - 1) umma_commit_pair(C.bar_tfull + 8 * slot);
+                } else {
+                  umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
 #pragma unroll
-                for (int ks = 1; ks < 4; ++ks)
-                  if (ks < nks) umma_bf16(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
-                umma_commit(C.bar_empty + 8 * stage);
-                if (kb == nkb - 1) umma_commit(C.bar_tfull + 8 * slot);
+                  for (int ks = 1; ks < 4; ++ks)
+                    if (ks < nks) umma_bf16(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, 1u);
+                  umma_commit(C.bar_empty + 8 * stage);
+                  if (kb == nkb - 1) umma_commit(C.bar_tfull + 8 * slot);
+                }
               }
+              __syncwarp();
+              c_issue += CB_CLK() - c1;
+              if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
-            __syncwarp();
-            c_issue += CB_CLK() - c1;
-            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            if (!P.one_issuer) {
+              // the other net's stages of this chunk
+              stage += nkb;
+              while (stage >= P.stages) { stage -= P.stages; phase ^= 1; }
+            }
           }
-          // the other net's stages of this chunk
-          stage += nkb;
-          while (stage >= P.stages) { stage -= P.stages; phase ^= 1; }
         }
       }
       if (P.dbg && blockIdx.x == 0 && lane == 0) {
@@ -1203,8 +1209,13 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
         if constexpr (PAIR) {
           __syncwarp();
           if (lane == 0) {
+#ifdef CB_FINAL_RELEASE_ARRIVE      // experiment: the release.cluster arrival (MEMBAR.ALL.GPU behind the global reductions)
+            mbar_arrive_cluster(L_bar_tempty + 8 * slot_b);
+            mbar_arrive_cluster(L_bar_tempty + 8 * slot_t);
+#else
             mbar_arrive_cluster_relaxed(L_bar_tempty + 8 * slot_b);
             mbar_arrive_cluster_relaxed(L_bar_tempty + 8 * slot_t);
+#endif
           }
         } else {
           mbar_arrive(C.bar_tempty + 8 * slot_b);
@@ -2065,6 +2076,11 @@ static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_
   F.num_tiles = (int)((rows + kTileM - 1) / kTileM);
   const int grid = F.num_tiles < grid_cap() ? F.num_tiles : grid_cap();
   F.dbg = nullptr;
+  // Default: ONE issuing warp.  CB_TC_FINAL_ISSUERS=2 lets warp 2 issue the trunk accumulators' MMAs: correct and
+  // equally fast when the kernel runs alone, but with a second stream's kernels in flight (predict()'s batch
+  // pipelining) it produced sporadic wrong accumulators and launch failures that we could not explain from the barrier
+  // protocol -- kept as an experiment switch only (scripts/dbg_rowpath.py reproduces it).
+  { const char* e = getenv("CB_TC_FINAL_ISSUERS"); F.one_issuer = (e && atoi(e) == 2) ? 0 : 1; }
   const char* dbg_env = getenv("CB_TC_FINAL_DBG");
   if (dbg_env) { CB_CUDA(cudaMalloc(&F.dbg, 192)); CB_CUDA(cudaMemsetAsync(F.dbg, 0, 192, st)); }
   if (m->pair) {

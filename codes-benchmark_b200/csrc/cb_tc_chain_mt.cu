@@ -43,6 +43,11 @@ constexpr int kMtMaxSlots = 8;
 constexpr int kMtMaxTiles = 4;
 constexpr int kMtCtrl = 256;
 
+#ifdef CB_MT_UNROLL_EPI          // experiment: fully unrolled chunk / tile loops in the epilogue (18 k instructions)
+#define CB_MT_EPI_PRAGMA _Pragma("unroll")
+#else
+#define CB_MT_EPI_PRAGMA _Pragma("unroll 1")
+#endif
 #ifdef CB_MT_DBG
 #define MCLK() clock64()
 #else
@@ -272,10 +277,10 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
         // (real loops over the chunks and the tiles: the register arrays below are indexed by the fully unrolled inner
         // loops only; unrolling c and s as well made the kernel 18 k instructions = 290 KB of code, far beyond the
         // instruction caches -- ncu's top stall reason was `no_instruction`)
-#pragma unroll 1
+        CB_MT_EPI_PRAGMA
         for (int c = 0; c < NCH; ++c) {
           if (c < nch) {
-#pragma unroll 1
+            CB_MT_EPI_PRAGMA
             for (int s = 0; s < NT; ++s) {
               const long long row_g = ((long long)unit * NT + s) * kTileM + r;
               const bool row_ok = row_g < P.rows;
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
               if (c == nch - 1 && hidden_like) {
                 // every MMA of (tile s, layer l) has retired: overwrite the tile's A operand / write the bf16 output
                 const uint32_t a_tmem = acc + (uint32_t)accw;
-#pragma unroll 1
+                CB_MT_EPI_PRAGMA
                 for (int cc = 0; cc < NCH; ++cc) {
                   const int nbb = cc * kMtChunk + h * 32;
                   const int ww = min(32, Np - nbb);
@@ -357,12 +362,16 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
                     }
                     if (!last) {
                       if (ww == 32) tmem_st16(a_tmem + (uint32_t)(nbb >> 1), Rs); else tmem_st8(a_tmem + (uint32_t)(nbb >> 1), Rs);
-                    } else if (ww == 32) {
+                    } else if (ww == 32 && !P.direct_stores) {
                       store_group_rows(ybg + nbb, row_g - lane, P.rows, P.ld_yb, Rs, lane);
                     } else if (row_ok) {
                       uint4* dst = reinterpret_cast<uint4*>(ybg + row_g * P.ld_yb + nbb);
                       dst[0] = make_uint4(Rs[0], Rs[1], Rs[2], Rs[3]);
                       dst[1] = make_uint4(Rs[4], Rs[5], Rs[6], Rs[7]);
+                      if (ww == 32) {
+                        dst[2] = make_uint4(Rs[8], Rs[9], Rs[10], Rs[11]);
+                        dst[3] = make_uint4(Rs[12], Rs[13], Rs[14], Rs[15]);
+                      }
                     }
                   }
                 }
@@ -385,7 +394,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
                     // itself overwrites next
                     __nv_bfloat16* sv = P.save[l];
                     const long long sld = P.save_ld[l];
-#pragma unroll 1
+                    CB_MT_EPI_PRAGMA
                     for (int cc = 0; cc < NCH; ++cc) {
                       const int nbb = cc * kMtChunk + h * 32;
                       const int ww = min(32, Np - nbb);
@@ -545,7 +554,9 @@ int32_t mt_prepare(int act) {
   return CB_OK;
 }
 
-int32_t mt_launch(const MtParams& P, int act, cudaStream_t st) {
+int32_t mt_launch(const MtParams& P_in, int act, cudaStream_t st) {
+  MtParams P = P_in;
+  { const char* e = getenv("CB_MT_DIRECT_STORES"); P.direct_stores = (e && atoi(e) != 0) ? 1 : 0; }
   bool multi = false;
   for (int i = 0; i < P.n_layers; ++i) multi = multi || P.nch[i] > 1;
   MtKernelFn fn = mt_pick(act, P.nt, multi);

@@ -50,6 +50,7 @@ struct MtParams {
   // the last layer's activation is `yb`)
   __nv_bfloat16* save[CB_MAX_LAYERS];
   int save_ld[CB_MAX_LAYERS];
+  int direct_stores;           // CB_MT_DIRECT_STORES=1 (debug / comparison): one 16-byte store per lane and piece
 };
 bool mt_supported(const cb_mlp_desc* d, int out_bf16, MtParams* geom /* nullable: nt, aw, slots, slot_bytes, nch.. */);
 size_t mt_packed_elems(int N, int K);

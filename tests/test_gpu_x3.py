@@ -146,19 +146,28 @@ def test_multionet_predict_bf16x3_equals_fp32_mode(grid, monkeypatch):
     assert eb > 20 * e3                                  # the bf16 mode is what the 1e-2 tolerance is for
 
 
-def test_fp32_grid_path_equals_fp32_row_path(monkeypatch):
+def test_bf16x3_grid_path_equals_row_path_and_fp32_mode_keeps_rows(monkeypatch):
+    """A narrow net (FFMA chains in both paths, rows below the tensor-core threshold): the fp32 grid contraction against
+    the per-row combine kernel -- only the summation order differs.  The 'fp32' exactness mode never takes the grid
+    path: its predict() is the reference's row semantics, bit for bit."""
     import codes_b200 as cb
-    cb.set_precision("fp32")
     Q, T, N = 6, 101, 300
     m = _multionet(Q, T, seed=3, f=10, H=64)
     d = O.synthetic_dataset(N, T, Q, seed=5)
     m.normalisation = {"mode": "minmax", "log10_transform": True, "min": -3.0, "max": 1.5}
     _, _, val = m.prepare_data(d, None, d, np.linspace(0, 1, T), 4096, shuffle=False)
+    cb.set_precision("bf16x3")
     pg, tg = m.predict(val)
     monkeypatch.setenv("CODES_B200_GRID_PREDICT", "0")
     pr, tr = m.predict(val)
     assert torch.equal(tg, tr)
     assert torch.allclose(pg, pr, rtol=2e-5, atol=1e-7)
+    cb.set_precision("fp32")
+    p32r, _ = m.predict(val)
+    monkeypatch.delenv("CODES_B200_GRID_PREDICT")
+    p32, _ = m.predict(val)
+    assert torch.equal(p32, p32r)
+    assert torch.allclose(pg, p32, rtol=2e-5, atol=1e-7)
 
 
 def test_validate_records_fp32_grade_metrics():
@@ -206,7 +215,7 @@ def test_order_free_grid_predict_on_the_resident_training_loader():
     """validate()'s train-loss pass: the shuffled, device-resident loader is evaluated on its own grid (no H2D); the
     L1 equals the per-batch path's, and the CPU RNG stream advances exactly as the per-batch path advances it."""
     import codes_b200 as cb
-    cb.set_precision("fp32")
+    cb.set_precision("bf16x3")
     Q, T, N = 6, 50, 200
     m = _multionet(Q, T, seed=1, f=8, H=64)
     d = O.synthetic_dataset(N, T, Q, seed=9)
