@@ -71,6 +71,8 @@ struct GemmParams {
   int a_seg_cols, b_seg_cols;
   int8_t term_a[8], term_b[8];
   int out_segs, out_seg_cols;  // EPI_FWD_BF16: the activation leaves as out_segs segments out_seg_cols columns apart
+  __nv_bfloat16* out_seg_ptr;  //   ... written with direct (quad-transposed, row-contiguous) stores to (m_bound, out_seg_ld)
+  long long out_seg_ld;
 };
 
 struct Item { int m_tile, n_blk0, n_nblk, kb0, kb1, split; };
@@ -307,7 +309,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         const int col0 = col_blk + h * 32;                  // first column owned by this thread
         uint32_t v[32];
         tmem_ld32(taddr + cb * 64 + h * 32, v);
-        if constexpr (kStaged) {
+        if (MODE == EPI_FWD_BF16 && P.out_segs > 1) {
+          // split precision: hi / mid / lo bf16 segments of the fp32 activation, f <- f - bf16(f) between the passes,
+          // written straight from registers with row-contiguous stores (8 rows x 64 B per instruction).  The staged
+          // TMA-store path below costs a shared-memory round trip, a proxy fence, two CTA barriers and a wait on the
+          // previous store per segment: with three segments per block it, not the MMAs, set the pace of the hidden
+          // layers (tensor pipe 22 % active, profiles/r2_tc_kernels_ncu_full.md).
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = act_fwd(P.act, __uint_as_float(v[i]), P.act_param);
+          const bool edge = col0 + 32 > P.n_true;
+          for (int pass = 0; pass < P.out_segs; ++pass) {
+            uint32_t R[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float a = f[2 * i], b = f[2 * i + 1];
+              if (edge) {
+                const int col = col0 + 2 * i;
+                if (col >= P.n_true) a = (pass == 0 && col == P.ones_col) ? 1.f : 0.f;
+                if (col + 1 >= P.n_true) b = (pass == 0 && col + 1 == P.ones_col) ? 1.f : 0.f;
+              }
+              R[i] = pack_bf16(a, b);
+              f[2 * i] = a - __bfloat162float(__float2bfloat16_rn(a));
+              f[2 * i + 1] = b - __bfloat162float(__float2bfloat16_rn(b));
+            }
+            store_group_rows(P.out_seg_ptr + (long long)pass * P.out_seg_cols + col0, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
+          }
+        } else if constexpr (kStaged) {
           const int buf = gb % kNumStaging;
           const uint32_t ost = OST + buf * kStaging;
           if (leader) {
@@ -766,7 +795,10 @@ static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
     P.a_seg_cols = (int)c.a_ld; P.b_seg_cols = (int)c.b_ld;
     P.kk_total = P.n_terms * P.kblocks;
     P.kb_per_split = P.kk_total;
-    if (c.mode == EPI_FWD_BF16) { P.out_segs = 3; P.out_seg_cols = (int)c.out_ld; }
+    if (c.mode == EPI_FWD_BF16) {
+      P.out_segs = 3; P.out_seg_cols = (int)c.out_ld;
+      P.out_seg_ptr = c.out_bf16; P.out_seg_ld = 3 * c.out_ld;
+    }
   }
   const long long seg_mul = c.x3 ? 3 : 1;
   P.a_mn = c.a_mn; P.b_mn = c.b_mn;

@@ -250,6 +250,49 @@ __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
 }
 
 
+// Row-contiguous global store of one 32-column bf16 group (64 bytes per row, one row per lane): the four lanes of a
+// quad exchange their 16-byte pieces (4 x 4 transpose, two shfl.xor stages) so that store i of the quad writes the 64
+// contiguous bytes of row (quad base + i).  A warp-wide store then touches 8 rows x 64 B instead of 32 rows x 16 B:
+// a quarter of the LSU wavefronts of the direct per-lane stores (which made the saved-activation stores of a training
+// forward more expensive than the layer's MMAs).
+// 4 x 4 transpose of 16-byte pieces inside a lane quad (two shfl.xor stages): in: p[4k..4k+3] = piece k of THIS lane's
+// row; out: p[4i..4i+3] = piece (lane & 3) of the row of quad lane i.  All 32 lanes must call it.
+__device__ __forceinline__ void quad_transpose16(uint32_t (&p)[16], int lane) {
+  const bool odd = lane & 1, upper = lane & 2;
+#pragma unroll
+  for (int k = 0; k < 4; k += 2) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t send = odd ? p[4 * k + e] : p[4 * (k + 1) + e];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+      if (odd) p[4 * k + e] = recv; else p[4 * (k + 1) + e] = recv;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t send = upper ? p[4 * k + e] : p[4 * (k + 2) + e];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 2);
+      if (upper) p[4 * k + e] = recv; else p[4 * (k + 2) + e] = recv;
+    }
+  }
+}
+__device__ __forceinline__ void store_group_rows(__nv_bfloat16* base, long long row0, long long n_rows, long long ld,
+                                                 const uint32_t (&R)[16], int lane) {
+  uint32_t p[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) p[i] = R[i];
+  quad_transpose16(p, lane);
+  const int j = lane & 3;
+  const long long rbase = row0 + (lane & ~3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (rbase + i < n_rows)
+      *reinterpret_cast<uint4*>(base + (rbase + i) * ld + 8 * j) = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+}
+
+
 // ------------------------------------------------------------------ CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
