@@ -46,11 +46,10 @@ constexpr int kMaxJobs = 96;
 constexpr int kMaxGroups = 128;      // 32-column groups of the MultiONet output layer (<= 4096 columns)
 constexpr int kMaxStages = 12;
 constexpr int kEpiThreads = 256;   // 8 epilogue warps: two per TMEM lane quarter, splitting the columns
-// MultiONet final kernel: room for TWO tcgen05.mma issuing warps (warp 1: branch accumulators, warp 2: trunk
-// accumulators; disjoint TMEM slots and weight stages, no operand or accumulation order changes).  Measured
+// MultiONet final kernel: TWO tcgen05.mma issuing warps (warp 1: branch accumulators, warp 2: trunk accumulators;
+// disjoint TMEM slots and weight-stage rings, no operand or accumulation order changes).  Measured
 // (scripts/micro/umma_rate.cu): one thread issues a cta_group::2 128-column MMA every 88.9 cycles (64 tensor cycles),
-// two threads reach 64.7.  The kernel itself did not get faster -- its pace was set by the epilogue (see
-// mbar_arrive_cluster_relaxed) -- and the second issuer is OFF by default, see multionet_forward_impl.
+// two threads reach 64.7.
 constexpr int kFIssuers = 2;
 constexpr int kFFirstEpi = 1 + kFIssuers;
 #ifndef CB_FINAL_EPI_WARPS
@@ -997,8 +996,16 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
   const uint32_t L_bar_tempty = PAIR ? mapa_shared(C.bar_tempty, 0) : C.bar_tempty;
 
   if (warp == 0) {
-    // TMA producer: warp-converged, one elected lane issues
-    int stage = 0; uint32_t phase = 0;
+    // TMA producer: warp-converged, one elected lane issues.
+    // The weight stages are TWO rings of `half` stages, one per net: ring `net` is filled in order and drained in order
+    // by exactly one MMA-issuing warp.  (One shared ring with the nets' k-blocks interleaved is correct for ONE issuer
+    // only: an mbarrier parity wait succeeds whenever the barrier's current phase parity differs from the one asked
+    // for, so a consumer that waits for fill k of a stage before fill k-1 -- the OTHER issuer's k-block -- has landed
+    // passes at once.  The producer issues the loads in order but they complete out of order under memory contention,
+    // e.g. a second stream's kernels: sporadic wrong accumulators, extra arrivals on the `empty` barriers, launch
+    // failures.  scripts/dbg_rowpath.py reproduced it.)
+    const int half = P.stages / 2;
+    int rs0 = 0, rs1 = 0; uint32_t rp0 = 0u, rp1 = 0u;   // ring position / phase of net 0 / net 1
     int seen_epi = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
       wait_counter(C.epi_done, it, seen_epi);              // previous tile fully consumed (this CTA)
@@ -1024,6 +1031,8 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
         for (int net = 0; net < 2; ++net) {
           const __nv_bfloat16* src = P.w[net] + (size_t)j * P.nkb * (kKBlockBytes / 2);
           for (int kb = 0; kb < P.nkb; ++kb) {
+            const int stage = net ? half + rs1 : rs0;
+            const uint32_t phase = net ? rp1 : rp0;
             mbar_wait(C.bar_empty + 8 * stage, phase ^ 1);
             if (elect_one()) {
               if constexpr (PAIR) {
@@ -1038,7 +1047,8 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
               }
             }
             __syncwarp();
-            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            if (net) { if (++rs1 == half) { rs1 = 0; rp1 ^= 1; } }
+            else { if (++rs0 == half) { rs0 = 0; rp0 ^= 1; } }
           }
         }
       }
@@ -1051,8 +1061,8 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
       const int net0 = P.one_issuer ? 0 : warp - 1, net1 = P.one_issuer ? 2 : warp;   // the nets this warp issues
       const int net = net0;
       const int nkb = P.nkb;
-      int stage = net0 * nkb; uint32_t phase = 0;
-      while (stage >= P.stages) { stage -= P.stages; phase ^= 1; }
+      const int half = P.stages / 2;
+      int rs0 = 0, rs1 = 0; uint32_t rp0 = 0u, rp1 = 0u;   // ring position / phase per net (see the producer)
       const int last_nks = P.ksteps - (nkb - 1) * 4;
       const uint64_t bdesc0 = make_smem_desc(ST0);
       long long c_in = 0, c_tempty = 0, c_full = 0, c_issue = 0;
@@ -1076,8 +1086,9 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
             c_tempty += CB_CLK() - c0;
             const uint32_t d_tmem = tmem_base + (uint32_t)slot * kChunkN;
             for (int kb = 0; kb < nkb; ++kb) {
+              const int stage = nn ? half + rs1 : rs0;
               c0 = CB_CLK();
-              mbar_wait(C.bar_full + 8 * stage, phase);
+              mbar_wait(C.bar_full + 8 * stage, nn ? rp1 : rp0);
               tcgen05_fence_after();
               const long long c1 = CB_CLK();
               c_full += c1 - c0;
@@ -1103,12 +1114,8 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
               }
               __syncwarp();
               c_issue += CB_CLK() - c1;
-              if (++stage == P.stages) { stage = 0; phase ^= 1; }
-            }
-            if (!P.one_issuer) {
-              // the other net's stages of this chunk
-              stage += nkb;
-              while (stage >= P.stages) { stage -= P.stages; phase ^= 1; }
+              if (nn) { if (++rs1 == half) { rs1 = 0; rp1 ^= 1; } }
+              else { if (++rs0 == half) { rs0 = 0; rp0 ^= 1; } }
             }
           }
         }
@@ -1882,10 +1889,11 @@ static bool final_geometry(int K, int Q, int* nkb_out, int* stages_out, size_t* 
   long long stages = ((long long)kMaxSmem - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (const char* e = getenv("CB_TC_MAX_STAGES")) { const int c = atoi(e); if (c >= 2 && c < stages) stages = c; }  // experiment knob
+  stages &= ~1ll;                      // two rings of stages / 2 (one per net)
   if (nkb_out) *nkb_out = nkb;
   if (stages_out) *stages_out = (int)stages;
   if (smem_out) *smem_out = (size_t)(fixed + (stages > 0 ? stages : 0) * stage_bytes);
-  return stages >= 2;
+  return stages >= 4;
 }
 
 extern "C" int32_t cb_tc_multionet_supported(const cb_mlp_desc* branch, const cb_mlp_desc* trunk, int32_t Q) {
@@ -2076,11 +2084,8 @@ static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_
   F.num_tiles = (int)((rows + kTileM - 1) / kTileM);
   const int grid = F.num_tiles < grid_cap() ? F.num_tiles : grid_cap();
   F.dbg = nullptr;
-  // Default: ONE issuing warp.  CB_TC_FINAL_ISSUERS=2 lets warp 2 issue the trunk accumulators' MMAs: correct and
-  // equally fast when the kernel runs alone, but with a second stream's kernels in flight (predict()'s batch
-  // pipelining) it produced sporadic wrong accumulators and launch failures that we could not explain from the barrier
-  // protocol -- kept as an experiment switch only (scripts/dbg_rowpath.py reproduces it).
-  { const char* e = getenv("CB_TC_FINAL_ISSUERS"); F.one_issuer = (e && atoi(e) == 2) ? 0 : 1; }
+  // Two MMA-issuing warps (branch / trunk accumulators) by default; CB_TC_FINAL_ISSUERS=1: warp 1 issues both nets.
+  { const char* e = getenv("CB_TC_FINAL_ISSUERS"); F.one_issuer = (e && atoi(e) == 1) ? 1 : 0; }
   const char* dbg_env = getenv("CB_TC_FINAL_DBG");
   if (dbg_env) { CB_CUDA(cudaMalloc(&F.dbg, 192)); CB_CUDA(cudaMemsetAsync(F.dbg, 0, 192, st)); }
   if (m->pair) {
