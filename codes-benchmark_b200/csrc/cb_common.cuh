@@ -54,6 +54,20 @@ inline int num_sms() {
   return cached;
 }
 
+// Opt the kernel in to the LARGEST dynamic shared-memory size the device allows for it (device opt-in limit minus the
+// kernel's static shared memory).  The attribute is per-kernel, process-wide state: setting it to the exact size of
+// each launch let one host thread LOWER it between another thread's set and launch ("invalid argument" launch failures
+// with several worker threads per GPU, benchmarks/full_benchmark.py) and let a second plan with a smaller tile shrink
+// the limit of an existing one.  Always the same maximal value => idempotent and race-free.
+inline cudaError_t allow_max_dynamic_smem(const void* kernel) {
+  int dev = 0, max_smem = 232448;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) max_smem -= (int)fa.sharedSizeBytes;
+  else cudaGetLastError();
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+}
+
 // ---------------------------------------------------------------- activations
 // torch.nn default semantics, fp32.  Accurate variants (erff/tanhf/expf, not the
 // fast-math intrinsics) because the fp32 path is the exactness mode.

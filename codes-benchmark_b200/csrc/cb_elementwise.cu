@@ -742,7 +742,7 @@ extern "C" int32_t cb_latent_loss_fwd_bwd(const float* d_xhat, const float* d_x,
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (smem > 48 * 1024)
-    CB_CUDA(cudaFuncSetAttribute(latent_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CUDA(allow_max_dynamic_smem((const void*)latent_loss_kernel));
   latent_loss_kernel<<<(unsigned)blocks, nt, smem, st>>>(d_xhat, d_x, batch, n_t, n_q,
                                                         1.f / (float)n_timesteps_h, kind, w0, w2, w3,
                                                         d_ws, d_dxhat);

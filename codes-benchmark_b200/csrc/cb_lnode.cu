@@ -461,12 +461,12 @@ extern "C" int32_t cb_lnode_solve_fwd(const cb_lnode_desc* desc, const float* co
   if (use64) {
     const size_t smem = lnode_smem_bytes<64>(P);
     // 256 threads with 4-output thread tiles: 8 warps per SM keep the FFMA pipe busier than 4
-    CB_CUDA(cudaFuncSetAttribute(lnode_solve_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CUDA(allow_max_dynamic_smem((const void*)lnode_solve_kernel<64, 4>));
     lnode_solve_kernel<64, 4><<<(unsigned)((batch + 63) / 64), 256, smem, st>>>(
         P, gW, gB, d_z0, d_t_eval, batch, d_z_out, d_stats, tp);
   } else {
     const size_t smem = lnode_smem_bytes<32>(P);
-    CB_CUDA(cudaFuncSetAttribute(lnode_solve_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CUDA(allow_max_dynamic_smem((const void*)lnode_solve_kernel<32, 8>));
     lnode_solve_kernel<32, 8><<<(unsigned)((batch + 31) / 32), 256, smem, st>>>(
         P, gW, gB, d_z0, d_t_eval, batch, d_z_out, d_stats, tp);
   }
@@ -863,7 +863,7 @@ extern "C" int32_t cb_lnode_solve_bwd(const cb_lnode_desc* desc, const float* co
   if (small) {
     n_cta = (int)((batch + 15) / 16);
     const size_t smem = lnode_bwd_smem_bytes(P, 16);
-    CB_CUDA(cudaFuncSetAttribute(lnode_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CUDA(allow_max_dynamic_smem((const void*)lnode_bwd_kernel<16>));
     lnode_bwd_kernel<16><<<n_cta, kBThreads, smem, st>>>(P, gW, gB, d_t_eval, batch, tp, d_g, d_dz0, slabs, slab_floats);
   } else {
     n_cta = (int)((batch + kBT - 1) / kBT);
@@ -873,7 +873,7 @@ extern "C" int32_t cb_lnode_solve_bwd(const cb_lnode_desc* desc, const float* co
     if (lnode_bwd_smem_bytes(P) > (size_t)max_smem) P.weights_in_smem = 0;
     const size_t smem = lnode_bwd_smem_bytes(P);
     CB_CHECK_ARG(smem <= (size_t)max_smem, "ODE net too wide for the backward sweep kernel (%zu bytes of shared memory)", smem);
-    CB_CUDA(cudaFuncSetAttribute(lnode_bwd_kernel<kBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CUDA(allow_max_dynamic_smem((const void*)lnode_bwd_kernel<kBT>));
     lnode_bwd_kernel<kBT><<<n_cta, kBThreads, smem, st>>>(P, gW, gB, d_t_eval, batch, tp, d_g, d_dz0, slabs, slab_floats);
   }
   CB_LAUNCH_CHECK();

@@ -660,10 +660,10 @@ extern "C" int32_t cb_mlp_forward_f32_p(const cb_mlp_desc* desc, const float* co
     P.num_tiles = (int)((rows + kNarrowRows - 1) / kNarrowRows);
     const size_t smem = narrow_fwd_smem(n, wp);
     if (wp == 32) {
-      CB_CUDA(cudaFuncSetAttribute(narrow_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CUDA(allow_max_dynamic_smem((const void*)narrow_fwd_kernel<32>));
       narrow_fwd_kernel<32><<<narrow_ctas(rows, 32), kNarrowThreads, smem, st>>>(P);
     } else {
-      CB_CUDA(cudaFuncSetAttribute(narrow_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CUDA(allow_max_dynamic_smem((const void*)narrow_fwd_kernel<64>));
       narrow_fwd_kernel<64><<<narrow_ctas(rows), kNarrowThreads, smem, st>>>(P);
     }
     CB_LAUNCH_CHECK();
@@ -742,10 +742,10 @@ extern "C" int32_t cb_mlp_backward_f32_p(const cb_mlp_desc* desc, const float* c
     const int ctas = narrow_ctas(rows, wp);
     const size_t smem = narrow_bwd_smem(n, wp);
     if (wp == 32) {
-      CB_CUDA(cudaFuncSetAttribute(narrow_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CUDA(allow_max_dynamic_smem((const void*)narrow_bwd_kernel<32>));
       narrow_bwd_kernel<32><<<ctas, kNarrowThreads, smem, st>>>(P);
     } else {
-      CB_CUDA(cudaFuncSetAttribute(narrow_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CUDA(allow_max_dynamic_smem((const void*)narrow_bwd_kernel<64>));
       narrow_bwd_kernel<64><<<ctas, kNarrowThreads, smem, st>>>(P);
     }
     CB_LAUNCH_CHECK();

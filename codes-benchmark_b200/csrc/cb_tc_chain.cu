@@ -1636,22 +1636,19 @@ static int32_t chain_create(const cb_mlp_desc* desc, int32_t device, int out_mod
     {
       P.ts_acol = g.ts_acol; P.ts_slot_bytes = g.ts_slot_bytes; P.ts_kbs = g.ts_kbs;
       pl->ts_slots = g.ts_slots; pl->smem_ts = g.smem_ts;
-      if (pl->ts && cudaFuncSetAttribute(chain_ts_kernel_for(desc->act), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)pl->smem_ts) != cudaSuccess) {
+      if (pl->ts && allow_max_dynamic_smem((const void*)chain_ts_kernel_for(desc->act)) != cudaSuccess) {
         cb_tc_chain_destroy(pl);
         set_error("cannot reserve %zu bytes of shared memory for the TMEM-resident chain kernel", g.smem_ts);
         return CB_ERR_CUDA;
       }
     }
-    if (pl->cg2 && cudaFuncSetAttribute(chain_pair_kernel_for(desc->act), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)pl->smem_cg2) != cudaSuccess) {
+    if (pl->cg2 && allow_max_dynamic_smem((const void*)chain_pair_kernel_for(desc->act)) != cudaSuccess) {
       cudaGetLastError();
       pl->cg2 = 0;
     }
   }
   pl->smem_bytes = pl->dual ? g.smem_dual : g.smem;
-  if (cudaFuncSetAttribute(chain_kernel_for(desc->act, pl->dual ? g.stages_dual : g.stages), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)pl->smem_bytes) != cudaSuccess) {
+  if (allow_max_dynamic_smem((const void*)chain_kernel_for(desc->act, pl->dual ? g.stages_dual : g.stages)) != cudaSuccess) {
     cb_tc_chain_destroy(pl);
     set_error("cannot reserve %zu bytes of shared memory for the chain kernel: %s", g.smem,
               cudaGetErrorString(cudaGetLastError()));
@@ -1962,13 +1959,11 @@ extern "C" int32_t cb_tc_multionet_create(const cb_mlp_desc* branch, const cb_ml
   }
   for (int i = 0; i < 2 && m->pair; ++i)
     if (!encode_bf16_rows64(&F.tmap_w[i], m->d_wlast[i], (long long)m->rows_alloc * (m->Kp / kBlockK), 64)) m->pair = 0;
-  if (m->pair && cudaFuncSetAttribute(don_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)m->smem_pair) != cudaSuccess) {
+  if (m->pair && allow_max_dynamic_smem((const void*)don_final_kernel<true>) != cudaSuccess) {
     cudaGetLastError();
     m->pair = 0;
   }
-  if (cudaFuncSetAttribute(don_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_final) !=
-      cudaSuccess) {
+  if (allow_max_dynamic_smem((const void*)don_final_kernel<false>) != cudaSuccess) {
     cb_tc_multionet_destroy(m);
     set_error("cannot reserve shared memory for the MultiONet final kernel");
     return CB_ERR_CUDA;

@@ -373,7 +373,7 @@ extern "C" int32_t cb_tc_multionet_grid_create(const cb_mlp_desc* branch, int32_
     return CB_ERR_CUDA;
   }
   GridKernelFn fn = pick<1>(Q);
-  if (!fn || cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem) != cudaSuccess) {
+  if (!fn || allow_max_dynamic_smem((const void*)fn) != cudaSuccess) {
     cb_tc_multionet_grid_destroy(g);
     set_error("cannot reserve %zu bytes of shared memory for the grid kernel", g->smem);
     return CB_ERR_CUDA;

@@ -378,6 +378,41 @@ def test_lnode_tape_grows_on_overflow(monkeypatch):
     assert torch.equal(g_small, g_big)
 
 
+# --------------------------------------------------------------------------------------- worker threads sharing a GPU
+def test_worker_threads_with_different_shapes_do_not_shrink_each_others_smem_limit():
+    """benchmarks/full_benchmark.py runs several host threads per GPU; tasks with different time grids need different
+    dynamic shared-memory sizes for the same kernel.  The opt-in limit is per-kernel, process-wide state: setting it
+    to each launch's exact size let one thread lower it between another thread's set and launch ("invalid argument",
+    1 of 112 tasks in a 2-GPU run).  Every kernel now opts in to the device maximum (allow_max_dynamic_smem)."""
+    import threading
+    import codes_b200 as cb
+    errors = []
+
+    def worker(T, seed):
+        try:
+            torch.manual_seed(seed)
+            rng = np.random.default_rng(seed)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for rep in range(6):
+                    m = cb.LatentNeuralODE(DEV, 5, T, 0, None, {"coder_width": 32, "ode_width": 64})
+                    d = rng.uniform(-1, 1, (64, T, 5)).astype(np.float32)
+                    loader, _, val = m.prepare_data(d, None, d, np.linspace(0, 1, T), 64, shuffle=False)
+                    pred, x = m(next(iter(loader)))
+                    m.model.total_loss(x, pred, None, nn.MSELoss()).backward()
+                    p, _ = m.predict(val)
+                    assert torch.isfinite(p).all()
+        except Exception as exc:      # noqa: BLE001 -- the test reports whatever a worker hit
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=worker, args=(T, i)) for i, T in enumerate((7, 100, 15, 51))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+
+
 # --------------------------------------------------------------------------------------- evaluation metrics on device
 @pytest.mark.parametrize("n", [1, 5, 1023, 65536 * 29 + 3])
 def test_error_sums_kernel_and_sharded_metrics(n):
