@@ -442,6 +442,9 @@ def run_ours(args):
     # ---- e2e leg (ALL ranks, weak scaling): public API with HOST batches (pinned), H2D + metric D2H inside
     # the timed region; aggregate = trajectories of all ranks / slowest rank's wall time between barriers
     n_e2e = 65536                              # N_test = 65536 trajectories = 100 loader batches per pass
+    # the headline e2e number copies EVERYTHING predict() reads from the host on every pass: the device cache of
+    # un-shuffled loader tensors (loaders.device_copy) is switched off here and measured separately below
+    os.environ["CODES_B200_DEVICE_CACHE_MB"] = "0"
     de = synthetic_x0(n_e2e, seed=4321 + rank)
     _, _, val_loader = model.prepare_data(de, None, de, np.linspace(0, 1, T), ROWS_PER_STEP, shuffle=False)
     steps_per_pass = len(val_loader)
@@ -490,6 +493,31 @@ def run_ours(args):
         dist.all_reduce(dt_rows, op=dist.ReduceOp.MAX)
     os.environ.pop("CODES_B200_GRID_PREDICT", None)
     e2e["row_path_value"] = world * 2 * n_e2e / float(dt_rows.item())
+    del p, t
+    # the same loader read AGAIN and again (validate() every update_epochs, the evaluation's 3-35 predict() calls per
+    # model): with the device cache on (the default) the targets cross PCIe on the first pass only; x0 still crosses
+    # every pass.  Reported beside the headline, never instead of it.
+    os.environ.pop("CODES_B200_DEVICE_CACHE_MB", None)
+    h2d_c0 = model.__dict__.get("_h2d_bytes", 0)
+    p, t = model.predict(val_loader)
+    model._l1(p, t)
+    h2d_first = model.__dict__.get("_h2d_bytes", 0) - h2d_c0
+    barrier()
+    h2d_c1 = model.__dict__.get("_h2d_bytes", 0)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        p = t = None
+        p, t = model.predict(val_loader)
+        model._l1(p, t)
+    torch.cuda.synchronize()
+    dt_c = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt_c, op=dist.ReduceOp.MAX)
+    e2e["repeat_passes"] = {"value": world * 5 * n_e2e / float(dt_c.item()), "unit": "trajectories/s",
+                            "h2d_bytes_first_pass": h2d_first,
+                            "h2d_bytes_per_later_pass": (model.__dict__.get("_h2d_bytes", 0) - h2d_c1) / 5,
+                            "what": "second and later predict() calls on the SAME loader: its targets stay in HBM after the "
+                                    "first call (CODES_B200_DEVICE_CACHE_MB, default 4 GiB per loader); x0 is copied every pass"}
     del p, t
 
     # ---- strong-scaling leg (ALL ranks): the FIXED 65 536-trajectory cfg2 test set split by trajectory over the

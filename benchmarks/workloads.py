@@ -74,6 +74,8 @@ def _events_ms(fn, reps, streams=None):
 
 def _time_e2e(model, loader, n_traj, passes):
     import torch
+    # every pass copies everything predict() reads from the host (the device cache of un-shuffled loader tensors off)
+    os.environ["CODES_B200_DEVICE_CACHE_MB"] = "0"
     for _ in range(3):
         p, t = model.predict(loader)
         model._l1(p, t)

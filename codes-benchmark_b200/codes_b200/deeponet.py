@@ -174,12 +174,20 @@ class MultiONet(OperatorNetwork):
                 copy_stream = self.__dict__["_copy_stream"] = torch.cuda.Stream(device)
             cur = torch.cuda.current_stream(device)
             copy_stream.wait_stream(cur)
+            nbytes = x0_h.numel() * x0_h.element_size()
+            was_resident = (device, "base", 2) in ds._tile_dev
             with torch.cuda.stream(copy_stream):            # the targets cross PCIe while the predictions are computed
-                targs = targ_h.to(device, non_blocking=True)
+                res = ds.device_copy(2, device)              # ... once: resident afterwards (loaders.device_copy)
+                if res is not None:
+                    targs = res.clone()                      # predict() de-normalises its own buffer in place
+                    if not was_resident:
+                        nbytes += targ_h.numel() * targ_h.element_size()
+                else:
+                    targs = targ_h.to(device, non_blocking=True)
+                    nbytes += targ_h.numel() * targ_h.element_size()
                 ready = copy_stream.record_event()
             x0 = x0_h.to(device, non_blocking=True)
             tg = ds._tile_dev.get((device, "grid"))          # the time grid stays resident after the first call
-            nbytes = x0_h.numel() * x0_h.element_size() + targ_h.numel() * targ_h.element_size()
             if tg is None:
                 tg = ds._tile_dev[(device, "grid")] = t_h.to(device, non_blocking=True)
                 nbytes += t_h.numel() * t_h.element_size()

@@ -96,6 +96,34 @@ class RowBatchIterable(IterableDataset):
             batch = [None if t is None else ops.gather_rows(t, idx) for t in tensors]
             yield tuple(batch[i] if kind == "t" else constants[i] for kind, i in self.layout)
 
+    def device_copy(self, i: int, device: torch.device):
+        """Device-resident copy of base tensor ``i`` of an un-shuffled loader, or None when caching is off
+        or the tensor is too large.  validate() and the evaluation re-read the same test loader 3-35 times; its targets
+        (the one tensor of a flat-row loader that is not de-duplicated) then cross PCIe once instead of once per pass.
+        ``CODES_B200_DEVICE_CACHE_MB`` (default 4096, 0 disables) caps the bytes kept per loader."""
+        cap = device_cache_bytes()
+        t = self.tensors[i]
+        if cap <= 0 or t is None or self.shuffle:
+            return None
+        key = (device, "base", i)
+        hit = self._tile_dev.get(key)
+        if hit is not None:
+            return hit
+        nbytes = t.numel() * t.element_size()
+        held = sum(v.numel() * v.element_size() for k, v in self._tile_dev.items()
+                   if isinstance(k, tuple) and len(k) == 3 and k[1] == "base")
+        if held + nbytes > cap:
+            return None
+        try:
+            free, _ = torch.cuda.mem_get_info(device)
+        except Exception:      # noqa: BLE001
+            return None
+        if nbytes * 4 > free:
+            return None
+        hit = self._tile_dev[key] = t.to(device, non_blocking=True)
+        self.__dict__["_cache_fill_bytes"] = self.__dict__.get("_cache_fill_bytes", 0) + nbytes
+        return hit
+
     def compact_ok(self) -> bool:
         return self._compact is not None and dedup_h2d_enabled()
 
@@ -138,9 +166,16 @@ class RowBatchIterable(IterableDataset):
                     cols = [expand(comp, sub, (i, j)) for j, (comp, (sub, _)) in enumerate(zip(self._compact[i], kind))]
                     batch.append(torch.cat(cols, dim=1))
                 else:
-                    src = t[start:stop]
-                    nbytes += src.numel() * src.element_size()
-                    batch.append(src.to(device, non_blocking=True))
+                    had = (device, "base", i) in self._tile_dev
+                    res = self.device_copy(i, device)
+                    if res is not None:                      # resident after the first pass: no per-batch copy
+                        if not had:
+                            nbytes += t.numel() * t.element_size()
+                        batch.append(res[start:stop])
+                    else:
+                        src = t[start:stop]
+                        nbytes += src.numel() * src.element_size()
+                        batch.append(src.to(device, non_blocking=True))
             consts = [c.to(device, non_blocking=True) for c in self.constants]
             yield tuple(batch[i] if kind == "t" else consts[i] for kind, i in self.layout), nbytes
 
@@ -168,6 +203,15 @@ def dedup_h2d_enabled() -> bool:
     """CODES_B200_DEDUP_H2D=0: ``predict`` copies the loader's full (T-fold repeated) batches as the reference does."""
     import os
     return os.environ.get("CODES_B200_DEDUP_H2D", "1") != "0"
+
+
+def device_cache_bytes() -> int:
+    """CODES_B200_DEVICE_CACHE_MB: bytes of un-shuffled loader tensors ``predict`` may keep on the device (default 4 GiB)."""
+    import os
+    try:
+        return int(float(os.environ.get("CODES_B200_DEVICE_CACHE_MB", "4096")) * (1 << 20))
+    except ValueError:
+        return 0
 
 
 def grid_predict_enabled() -> bool:

@@ -284,16 +284,41 @@ __global__ void __launch_bounds__(kMtThreads, 1) chain_mt_kernel(const __grid_co
                       }
                     }
                   }
-                } else if (row_ok) {
-                  const bool tanh_out = (P.final_act == CB_ACT_TANH);
-                  float* yp = yg + row_g * N;
+                } else if (P.direct_stores || N <= 8) {
+                  // narrow outputs (LatentPoly's 6 quantities): N stores of 32 rows x 4 B whose rows are N * 4 B apart are
+                  // already dense in memory; the transpose below would cost 160 shuffles for them (cfg4: 0.45 -> 0.51 ms)
+                  if (row_ok) {
+                    const bool tanh_out = (P.final_act == CB_ACT_TANH);
+                    float* yp = yg + row_g * N;
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) {
-                    const int n = nb + i;
-                    if (i < w && n < N) {
-                      const float z = __uint_as_float(v[i]);
-                      yp[n] = tanh_out ? tanhf(z) : z;
+                    for (int i = 0; i < 32; ++i) {
+                      const int n = nb + i;
+                      if (i < w && n < N) {
+                        const float z = __uint_as_float(v[i]);
+                        yp[n] = tanh_out ? tanhf(z) : z;
+                      }
                     }
+                  }
+                } else {
+                  // fp32 output rows (N floats each, not 16-byte aligned in general): transpose the warp's 32 rows x 32
+                  // columns through shuffles so that every store instruction writes one row's consecutive floats --
+                  // the per-lane scalar stores (32 rows x 4 B per instruction) made the decoders of the latent models
+                  // store-bound (29 x 32 LSU wavefronts per warp and tile)
+                  if (P.final_act == CB_ACT_TANH) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(tanhf(__uint_as_float(v[i])));
+                  }
+                  if (w < 32) {
+#pragma unroll
+                    for (int i = 16; i < 32; ++i) v[i] = 0u;      // (tcgen05.ld.x16 filled 16 columns only)
+                  }
+                  warp_transpose32(v, lane);
+                  const int n = nb + lane;
+                  const long long r0 = row_g - lane;              // first row of this warp's lane quarter
+                  if (lane < w && n < N) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                      if (r0 + i < P.rows) yg[(r0 + i) * N + n] = __uint_as_float(v[i]);
                   }
                 }
               }

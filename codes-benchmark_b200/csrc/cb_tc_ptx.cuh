@@ -255,6 +255,22 @@ __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
 // contiguous bytes of row (quad base + i).  A warp-wide store then touches 8 rows x 64 B instead of 32 rows x 16 B:
 // a quarter of the LSU wavefronts of the direct per-lane stores (which made the saved-activation stores of a training
 // forward more expensive than the layer's MMAs).
+// 32 x 32 transpose of one register per lane and column across a warp (five shfl.xor stages): in: v[i] = element
+// (row = this lane, column i); out: v[i] = element (row i, column = this lane).  All 32 lanes must call it.
+__device__ __forceinline__ void warp_transpose32(uint32_t (&v)[32], int lane) {
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const bool up = (lane & j) != 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if ((i & j) == 0) {
+        const uint32_t send = up ? v[i] : v[i + j];
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, j);
+        if (up) v[i] = recv; else v[i + j] = recv;
+      }
+    }
+  }
+}
 // 4 x 4 transpose of 16-byte pieces inside a lane quad (two shfl.xor stages): in: p[4k..4k+3] = piece k of THIS lane's
 // row; out: p[4i..4i+3] = piece (lane & 3) of the row of quad lane i.  All 32 lanes must call it.
 __device__ __forceinline__ void quad_transpose16(uint32_t (&p)[16], int lane) {
