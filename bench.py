@@ -528,6 +528,7 @@ def run_ours(args):
     strong = None
     if not args.no_strong:
         n_strong = 65536
+        os.environ["CODES_B200_DEVICE_CACHE_MB"] = "0"         # every pass copies its targets (as the headline e2e leg)
         ds_full = synthetic_x0(n_strong, seed=555)              # identical on every rank
         tgrid = np.linspace(0, 1, T)
         sh_loader = parallel.shard_loader(model, ds_full, tgrid, ROWS_PER_STEP)
@@ -562,6 +563,7 @@ def run_ours(args):
                           "test set, host loader, H2D inside; gather_pass_ms: one pass with all_gather_into_tensor of "
                           "predictions and targets to every rank"}
         del pg, tg_, ds_full, sh_loader
+        os.environ.pop("CODES_B200_DEVICE_CACHE_MB", None)
 
     # ---- training leg (ALL ranks, independent models = the benchmark's task parallelism): steady-state fit
     # step (forward, loss, backward, AdamW) of the same MultiONet config, bf16 tensor-core training mode

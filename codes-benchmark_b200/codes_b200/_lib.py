@@ -109,6 +109,7 @@ _SIGNATURES = {
     "cb_tc_multionet_set_weights": (_I32, [_P, _PP, _PP, _PP, _PP, _P]),
     "cb_tc_multionet_forward": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _P]),
     "cb_tc_multionet_forward_timed": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _P, C.POINTER(C.c_float)]),
+    "cb_tc_multionet_final_train": (_I32, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _I64, _P]),
     "cb_tc_multionet_grid_supported": (_I32, [C.POINTER(MlpDesc), _I32]),
     "cb_tc_multionet_grid_create": (_I32, [C.POINTER(MlpDesc), _I32, _I32, C.POINTER(_P)]),
     "cb_tc_multionet_grid_destroy": (None, [_P]),
@@ -123,6 +124,8 @@ _SIGNATURES = {
     "cb_tc_train_saved_bytes": (_I64, [_P, _I64]),
     "cb_tc_train_scratch_bytes": (_I64, [_P, _I64]),
     "cb_tc_train_forward": (_I32, [_P, _PP, _PP, _P, _I64, _P, _P, _I64, _P]),
+    "cb_tc_train_forward_hidden": (_I32, [_P, _PP, _PP, _P, _I64, _P, _I64, _P]),
+    "cb_tc_train_saved_offset": (_I64, [_P, _I64, _I32]),
     "cb_tc_train_infer_bytes": (_I64, [_P, _I64]),
     "cb_tc_train_infer": (_I32, [_P, _PP, _PP, _P, _I64, _P, _P, _I64, _P]),
     "cb_tc_x3_create": (_I32, [C.POINTER(MlpDesc), _I32, C.POINTER(_P)]),

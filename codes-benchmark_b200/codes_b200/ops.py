@@ -638,6 +638,9 @@ def try_tc_multionet_training(model, branch_input: Tensor, trunk_input: Tensor):
     if not (_use_tc_training(bspec, branch_input) and _use_tc_training(tspec, trunk_input)):
         return None
     from . import tc
+    y = tc.multionet_train_forward(model, branch_input, trunk_input)   # last Linears + combine as one launch
+    if y is not None:
+        return y
     bw, bb = sequential_params(model.branch_net.network)
     tw, tb = sequential_params(model.trunk_net.network)
     b = tc.train_chain(bspec, branch_input, bw, bb, out_bf16=True)

@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import ctypes as C
 import contextlib
+import os
 import weakref
 
 import torch
@@ -188,20 +189,11 @@ def multionet_forward(model, branch_input, trunk_input, phase_ms=None):
     if not available():
         return None
     dev = branch_input.device
-    per_model = _MULTIONET_PLANS.setdefault(model, {})
     bspec, tspec = model.branch_net.chain(), model.trunk_net.chain()
-    key = (dev.index, id(bspec), id(tspec))
-    plan = per_model.get(key)
     q = model.N
+    plan = _multionet_plan(model, bspec, tspec, dev)
     if plan is None:
-        if not lib().cb_tc_multionet_supported(C.byref(bspec.desc), C.byref(tspec.desc), q):
-            return None
-        per_model.clear()
-        plan = per_model[key] = _MultiONetPlan(bspec, tspec, q, dev)
-        # the nn.Linear members are looked up once; their .weight / .bias are read on every call (a caller may
-        # replace parameter objects)
-        plan.linears = ([m for m in model.branch_net.network if isinstance(m, torch.nn.Linear)],
-                        [m for m in model.trunk_net.network if isinstance(m, torch.nn.Linear)])
+        return None
     bw = [m.weight for m in plan.linears[0]]; bb = [m.bias for m in plan.linears[0]]
     tw = [m.weight for m in plan.linears[1]]; tb = [m.bias for m in plan.linears[1]]
     b2 = branch_input.reshape(-1, bspec.dims[0])
@@ -414,12 +406,8 @@ class _TcTrainChainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        spec, plan, rows = ctx.spec, ctx.plan, ctx.rows
-        n = spec.n_layers
+        spec, rows = ctx.spec, ctx.rows
         saved, y = ctx.saved_tensors
-        dev = saved.device
-        L = lib()
-        need_dx = ctx.needs_input_grad[2]
         if ctx.out_bf16:
             dy2 = dy.contiguous()
             if dy2.dtype != torch.bfloat16:
@@ -428,22 +416,31 @@ class _TcTrainChainFn(torch.autograd.Function):
             dy2 = dy.reshape(rows, spec.dims[-1])
             if dy2.dtype != torch.float32 or not dy2.is_contiguous():
                 dy2 = dy2.float().contiguous()
-        with torch.cuda.device(dev):
-            dW = [torch.empty(s, device=dev, dtype=torch.float32) for s in ctx.w_shapes]
-            db = [torch.empty(s[0], device=dev, dtype=torch.float32) if hb else None
-                  for s, hb in zip(ctx.w_shapes, ctx.has_bias)]
-            dx = torch.empty((rows, spec.dims[0]), device=dev, dtype=torch.float32) if need_dx else None
-            nbytes = int(L.cb_tc_train_scratch_bytes(plan.handle, rows))
-            if plan.scratch is None or plan.scratch.numel() < nbytes:
-                plan.scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-            check(L.cb_tc_train_backward(plan.handle, C.c_void_p(dy2.data_ptr()),
-                                         C.c_void_p(None if ctx.out_bf16 else y.data_ptr()), rows,
-                                         C.c_void_p(saved.data_ptr()), C.c_void_p(plan.scratch.data_ptr()),
-                                         plan.scratch.numel(), ptr_array(dW), ptr_array(db),
-                                         C.c_void_p(None if dx is None else dx.data_ptr()), _stream(dev)),
-                  "tc_train_backward")
-        gx = dx.reshape(ctx.x_shape) if need_dx else None
+        dW, db, dx = _chain_backward(spec, ctx.plan, rows, saved, dy2, None if ctx.out_bf16 else y, ctx.w_shapes,
+                                     ctx.has_bias, ctx.needs_input_grad[2])
+        gx = dx.reshape(ctx.x_shape) if dx is not None else None
         return (None, None, gx, *dW, *db)
+
+
+def _chain_backward(spec, plan, rows, saved, dy2, y, w_shapes, has_bias, need_dx):
+    """cb_tc_train_backward of one chain: (dW list, db list, dx or None) from the saved activations and the gradient
+    of the chain's output (bf16 (rows, ld_n) for out_bf16 plans, else fp32 (rows, dims[-1]))."""
+    dev = saved.device
+    L = lib()
+    with torch.cuda.device(dev):
+        dW = [torch.empty(s, device=dev, dtype=torch.float32) for s in w_shapes]
+        db = [torch.empty(s[0], device=dev, dtype=torch.float32) if hb else None for s, hb in zip(w_shapes, has_bias)]
+        dx = torch.empty((rows, spec.dims[0]), device=dev, dtype=torch.float32) if need_dx else None
+        nbytes = int(L.cb_tc_train_scratch_bytes(plan.handle, rows))
+        if plan.scratch is None or plan.scratch.numel() < nbytes:
+            plan.scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        check(L.cb_tc_train_backward(plan.handle, C.c_void_p(dy2.data_ptr()),
+                                     C.c_void_p(None if y is None else y.data_ptr()), rows,
+                                     C.c_void_p(saved.data_ptr()), C.c_void_p(plan.scratch.data_ptr()),
+                                     plan.scratch.numel(), ptr_array(dW), ptr_array(db),
+                                     C.c_void_p(None if dx is None else dx.data_ptr()), _stream(dev)),
+              "tc_train_backward")
+    return dW, db, dx
 
 
 def train_chain(spec, x, weights, biases, out_bf16: bool = False):
@@ -481,3 +478,121 @@ class _TcCombineFn(torch.autograd.Function):
 
 def combine_bf16(b, t, n_out: int, q: int):
     return _TcCombineFn.apply(b, t, n_out, q)
+
+
+# --------------------------------------------------------------------------- MultiONet training step, fused last layers
+def fused_final_train_enabled() -> bool:
+    """CB_TC_TRAIN_FUSED_FINAL=0: the training forward of MultiONet goes back to two last-layer GEMMs + the bf16 combine
+    kernel (comparison switch)."""
+    return os.environ.get("CB_TC_TRAIN_FUSED_FINAL", "1") != "0"
+
+
+def _multionet_plan(model, bspec, tspec, dev):
+    """The model's cb_tc_multionet plan (shared with multionet_forward), or None when the shape is not supported."""
+    per_model = _MULTIONET_PLANS.setdefault(model, {})
+    key = (dev.index, id(bspec), id(tspec))
+    plan = per_model.get(key)
+    if plan is None:
+        if not lib().cb_tc_multionet_supported(C.byref(bspec.desc), C.byref(tspec.desc), model.N):
+            return None
+        per_model.clear()
+        plan = per_model[key] = _MultiONetPlan(bspec, tspec, model.N, dev)
+        # the nn.Linear members are looked up once; their .weight / .bias are read on every call (a caller may
+        # replace parameter objects)
+        plan.linears = ([m for m in model.branch_net.network if isinstance(m, torch.nn.Linear)],
+                        [m for m in model.trunk_net.network if isinstance(m, torch.nn.Linear)])
+    return plan
+
+
+class _TcMultiONetTrainFn(torch.autograd.Function):
+    """y = MultiONet(branch_input, trunk_input) for training (deeponet.py:226-253, loop 340-351): the hidden layers of
+    both nets as in _TcTrainChainFn, then ONE launch of the final kernel for both last Linears and the split scalar
+    product, which also leaves the two last-layer outputs as bf16 for the backward pass.  Backward: bf16 combine
+    gradient, then cb_tc_train_backward of each chain."""
+
+    @staticmethod
+    def forward(ctx, mplan, bspec, tspec, q, xb, xt, *params):
+        nb, nt = bspec.n_layers, tspec.n_layers
+        bw, bb = params[:nb], params[nb:2 * nb]
+        tw, tb = params[2 * nb:2 * nb + nt], params[2 * nb + nt:]
+        dev = xb.device
+        L = lib()
+        plans = (_train_plan(bspec, dev, True), _train_plan(tspec, dev, True))
+        xs = []
+        for x, spec in ((xb, bspec), (xt, tspec)):
+            x2 = x.reshape(-1, spec.dims[0])
+            if x2.dtype != torch.float32 or not x2.is_contiguous():
+                x2 = x2.float().contiguous()
+            xs.append(x2)
+        rows = xs[0].shape[0]
+        if xs[1].shape[0] != rows:
+            raise ValueError("branch and trunk inputs must have the same number of rows")
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
+            y = torch.empty((rows, q), device=dev, dtype=torch.float32)
+            ld_out = plans[0].ld_out
+            yb = torch.empty((rows, ld_out), device=dev, dtype=torch.bfloat16)
+            yt = torch.empty((rows, ld_out), device=dev, dtype=torch.bfloat16)
+            saved, h_ptr, lasts = [], [], []
+            for plan, spec, x2, ws, bs in ((plans[0], bspec, xs[0], bw, bb), (plans[1], tspec, xs[1], tw, tb)):
+                n = spec.n_layers
+                nbytes = int(L.cb_tc_train_saved_bytes(plan.handle, rows))
+                sv = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+                wl, bl = _f32(ws), _f32(bs)
+                check(L.cb_tc_train_forward_hidden(plan.handle, ptr_array(wl), ptr_array(bl), C.c_void_p(x2.data_ptr()),
+                                                   rows, C.c_void_p(sv.data_ptr()), nbytes, stream),
+                      "tc_train_forward_hidden")
+                saved.append(sv)
+                h_ptr.append(sv.data_ptr() + int(L.cb_tc_train_saved_offset(plan.handle, rows, n - 1)))
+                lasts.append((wl[-1], bl[-1]))
+            ld_h = int(L.cb_tc_train_ld(plans[0].handle, nb - 1))
+            if int(L.cb_tc_train_ld(plans[1].handle, nt - 1)) != ld_h:
+                raise RuntimeError("branch and trunk hidden widths differ")
+            check(L.cb_tc_multionet_final_train(mplan.handle, C.c_void_p(lasts[0][0].data_ptr()),
+                                                C.c_void_p(None if lasts[0][1] is None else lasts[0][1].data_ptr()),
+                                                C.c_void_p(lasts[1][0].data_ptr()),
+                                                C.c_void_p(None if lasts[1][1] is None else lasts[1][1].data_ptr()),
+                                                C.c_void_p(h_ptr[0]), C.c_void_p(h_ptr[1]), ld_h, rows,
+                                                C.c_void_p(y.data_ptr()), C.c_void_p(yb.data_ptr()),
+                                                C.c_void_p(yt.data_ptr()), ld_out, stream), "tc_multionet_final_train")
+            mplan.versions = None          # the plan's packed last-layer weights were replaced: inference re-packs
+        ctx.specs, ctx.plans, ctx.rows, ctx.q = (bspec, tspec), plans, rows, q
+        ctx.shapes = [([tuple(w.shape) for w in ws], [b is not None for b in bs]) for ws, bs in ((bw, bb), (tw, tb))]
+        ctx.x_shapes = (xb.shape, xt.shape)
+        ctx.save_for_backward(saved[0], saved[1], yb, yt)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        sb, st, yb, yt = ctx.saved_tensors
+        rows = ctx.rows
+        dev = yb.device
+        dy = dy.float().contiguous()
+        dyb, dyt = torch.empty_like(yb), torch.empty_like(yt)
+        with torch.cuda.device(dev):
+            check(lib().cb_tc_combine_bwd(C.c_void_p(yb.data_ptr()), C.c_void_p(yt.data_ptr()), C.c_void_p(dy.data_ptr()),
+                                          rows, ctx.specs[0].dims[-1], ctx.q, yb.shape[1], C.c_void_p(dyb.data_ptr()),
+                                          C.c_void_p(dyt.data_ptr()), _stream(dev)), "tc_combine_bwd")
+        grads, gxs = [], []
+        for k, (saved, dyk) in enumerate(((sb, dyb), (st, dyt))):
+            w_shapes, has_bias = ctx.shapes[k]
+            dW, db, dx = _chain_backward(ctx.specs[k], ctx.plans[k], rows, saved, dyk, None, w_shapes, has_bias,
+                                         ctx.needs_input_grad[4 + k])
+            gxs.append(None if dx is None else dx.reshape(ctx.x_shapes[k]))
+            grads += [*dW, *db]
+        return (None, None, None, None, gxs[0], gxs[1], *grads)
+
+
+def multionet_train_forward(model, branch_input, trunk_input):
+    """Differentiable MultiONet forward with the fused last layers, or None (unsupported shape / switched off)."""
+    if not fused_final_train_enabled():
+        return None
+    bspec, tspec = model.branch_net.chain(), model.trunk_net.chain()
+    if bspec.n_layers < 2 or tspec.n_layers < 2:
+        return None
+    mplan = _multionet_plan(model, bspec, tspec, branch_input.device)
+    if mplan is None:
+        return None
+    bw = [m.weight for m in mplan.linears[0]]; bb = [m.bias for m in mplan.linears[0]]
+    tw = [m.weight for m in mplan.linears[1]]; tb = [m.bias for m in mplan.linears[1]]
+    return _TcMultiONetTrainFn.apply(mplan, bspec, tspec, model.N, branch_input, trunk_input, *bw, *bb, *tw, *tb)

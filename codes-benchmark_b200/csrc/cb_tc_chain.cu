@@ -128,6 +128,10 @@ struct FinalParams {
   float* y;                    // (rows, Q) fp32
   long long rows;
   int num_tiles;
+  // training forward (cb_tc_multionet_final_train): both last-layer outputs also leave as bf16 (rows, ld_yb) -- the
+  // backward pass needs them (d branch_out = dy * trunk_out and vice versa); NULL in inference
+  __nv_bfloat16* yb[2];
+  long long ld_yb;
 };
 
 // activation + bf16 pack of `w` (16 or 32) accumulator columns -> next layer's A operand.
@@ -1169,6 +1173,18 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
           else { tmem_ld16(ta_b + c0, vb); tmem_ld16(ta_t + c0, vt); }
           tmem_ld_wait();
           const int nb = j * kChunkN + c0;
+          if (P.yb[0]) {
+            // training: this thread's 32 columns of both products as bf16, row-contiguous stores (8 rows x 64 B each)
+            uint32_t R[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              R[i] = (2 * i < w) ? pack_bf16(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1])) : 0u;
+            store_group_rows(P.yb[0] + nb, row_g - lane, P.rows, P.ld_yb, R, lane);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              R[i] = (2 * i < w) ? pack_bf16(__uint_as_float(vt[2 * i]), __uint_as_float(vt[2 * i + 1])) : 0u;
+            store_group_rows(P.yb[1] + nb, row_g - lane, P.rows, P.ld_yb, R, lane);
+          }
           const int g = nb >> 5;
           int qi = P.grp_q[g];
           int seg_end = P.grp_end[g];
@@ -2035,6 +2051,75 @@ extern "C" int32_t cb_tc_multionet_forward_timed(cb_tc_multionet* m, const float
   return e;
 }
 
+static int32_t launch_final(cb_tc_multionet* m, FinalParams& F, cudaStream_t st);
+
+// Training forward of the two last Linears + the split scalar product (deeponet.py:241-253) in ONE launch of the final
+// kernel: y (rows, Q) fp32 as in inference, plus both last-layer outputs as bf16 (rows, ld_out) for the backward pass
+// (cb_tc_combine_bwd, cb_tc_train_backward).  d_hb / d_ht: the last hidden activations, bf16 (rows, ld_h) with the
+// constant-one column at index K (what cb_tc_train_forward_hidden saves).  Replaces two forward GEMMs that wrote
+// (rows, ld_out) bf16 each and the bf16 combine kernel that read both back.  The last-layer weights are packed here,
+// every call (they change every step): a later cb_tc_multionet_forward needs cb_tc_multionet_set_weights again.
+extern "C" int32_t cb_tc_multionet_final_train(cb_tc_multionet* m, const float* d_Wb_last, const float* d_bb_last,
+                                               const float* d_Wt_last, const float* d_bt_last, const void* d_hb,
+                                               const void* d_ht, int64_t ld_h, int64_t rows, float* d_y, void* d_yb,
+                                               void* d_yt, int64_t ld_out, void* stream) {
+  CB_CHECK_ARG(m != nullptr, "plan is NULL");
+  CB_CHECK_ARG(rows >= 0, "rows < 0");
+  if (rows == 0) return CB_OK;
+  CB_CHECK_ARG(d_Wb_last && d_Wt_last && d_hb && d_ht && d_y && d_yb && d_yt, "NULL pointer argument");
+  CB_CHECK_ARG(rows <= (int64_t)kTileM * 0x3fffffff, "too many rows");
+  CB_CHECK_ARG(ld_h >= m->Kp && (ld_h & 7) == 0, "ld_h must cover the padded reduction length and be a multiple of 8");
+  CB_CHECK_ARG(ld_out >= (int64_t)round_up(m->F.n_out, 32) && (ld_out & 7) == 0, "ld_out too small for the padded outputs");
+  CB_CHECK_ARG((((uintptr_t)d_hb | (uintptr_t)d_ht | (uintptr_t)d_yb | (uintptr_t)d_yt) & 15) == 0, "bf16 buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* Ws[2] = {d_Wb_last, d_Wt_last};
+  const float* bs[2] = {d_bb_last, d_bt_last};
+  for (int i = 0; i < 2; ++i) {
+    const long long total = (long long)m->rows_alloc * m->Kp;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    pack_weights_kernel<<<blocks, 256, 0, st>>>(Ws[i], bs[i], m->n_out, m->K, m->rows_alloc, m->Kp, m->d_wlast[i], kChunkN);
+    CB_LAUNCH_CHECK();
+  }
+  m->weights_set = 0;      // the hidden chains of this plan do not hold these weights
+  FinalParams F = m->F;
+  CB_CHECK_ARG(encode_bf16_map(&F.tmap_in[0], d_hb, rows, ld_h) && encode_bf16_map(&F.tmap_in[1], d_ht, rows, ld_h),
+               "tensor map of the hidden activations failed");
+  CB_CUDA(cudaMemsetAsync(d_y, 0, (size_t)rows * m->Q * sizeof(float), st));   // the final kernel accumulates into y
+  F.y = d_y; F.rows = rows;
+  F.num_tiles = (int)((rows + kTileM - 1) / kTileM);
+  F.yb[0] = reinterpret_cast<__nv_bfloat16*>(d_yb); F.yb[1] = reinterpret_cast<__nv_bfloat16*>(d_yt);
+  F.ld_yb = ld_out;
+  F.dbg = nullptr;
+  { const char* e = getenv("CB_TC_FINAL_ISSUERS"); F.one_issuer = (e && atoi(e) == 1) ? 1 : 0; }
+  return launch_final(m, F, st);
+}
+
+static int32_t launch_final(cb_tc_multionet* m, FinalParams& F, cudaStream_t st) {
+  const int grid = F.num_tiles < grid_cap() ? F.num_tiles : grid_cap();
+  if (m->pair) {
+    // one cluster of two CTAs per pair of 128-row tiles, persistent over the pairs
+    const int pairs = (F.num_tiles + 1) / 2;
+    const int clusters = pairs < grid_cap() / 2 ? pairs : grid_cap() / 2;
+    F.stages = m->stages_pair;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kFThreads);
+    cfg.dynamicSmemBytes = m->smem_pair;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CB_CUDA(cudaLaunchKernelEx(&cfg, don_final_kernel<true>, F));
+  } else {
+    don_final_kernel<false><<<grid, kFThreads, m->smem_final, st>>>(F);
+  }
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
 static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_in, const float* d_trunk_in,
                                       int64_t rows, float* d_y, void* d_workspace, int64_t workspace_bytes,
                                       void* stream, cudaEvent_t* ev) {
@@ -2077,32 +2162,12 @@ static int32_t multionet_forward_impl(cb_tc_multionet* m, const float* d_branch_
   F.tmap_in[0] = hmap[0]; F.tmap_in[1] = hmap[1];
   F.y = d_y; F.rows = rows;
   F.num_tiles = (int)((rows + kTileM - 1) / kTileM);
-  const int grid = F.num_tiles < grid_cap() ? F.num_tiles : grid_cap();
   F.dbg = nullptr;
   // Two MMA-issuing warps (branch / trunk accumulators) by default; CB_TC_FINAL_ISSUERS=1: warp 1 issues both nets.
   { const char* e = getenv("CB_TC_FINAL_ISSUERS"); F.one_issuer = (e && atoi(e) == 1) ? 1 : 0; }
   const char* dbg_env = getenv("CB_TC_FINAL_DBG");
   if (dbg_env) { CB_CUDA(cudaMalloc(&F.dbg, 192)); CB_CUDA(cudaMemsetAsync(F.dbg, 0, 192, st)); }
-  if (m->pair) {
-    // one cluster of two CTAs per pair of 128-row tiles, persistent over the pairs
-    const int pairs = (F.num_tiles + 1) / 2;
-    const int clusters = pairs < grid_cap() / 2 ? pairs : grid_cap() / 2;
-    F.stages = m->stages_pair;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kFThreads);
-    cfg.dynamicSmemBytes = m->smem_pair;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    CB_CUDA(cudaLaunchKernelEx(&cfg, don_final_kernel<true>, F));
-  } else {
-    don_final_kernel<false><<<grid, kFThreads, m->smem_final, st>>>(F);
-  }
-  CB_LAUNCH_CHECK();
+  if (int32_t e = launch_final(m, F, st)) return e;
   if (dbg_env) {
     long long h[24];
     CB_CUDA(cudaStreamSynchronize(st));

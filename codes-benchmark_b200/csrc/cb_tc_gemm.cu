@@ -41,6 +41,7 @@ constexpr int kBoxBytes = 8192;                // one 64 x 64 bf16 TMA box = 64 
 constexpr int kMaxStages = 6;
 constexpr int kStaging = 16384;                // one 128 x 64 bf16 output block
 constexpr int kNumStaging = 3;                 // ring of output blocks: aux prefetch / compute in place / store drain
+constexpr int kMaxAuxSlots = 8;                // direct-store data-gradient epilogue: ring of prefetched h / z blocks
 constexpr int kThreads = 320;
 constexpr int kEpiThreads = 256;
 constexpr int kAccCols = 256;                  // TMEM columns per accumulator slot
@@ -48,6 +49,8 @@ constexpr int kCtrl = 256;
 
 enum { EPI_FWD_BF16 = 0, EPI_FWD_F32 = 1, EPI_DGRAD_BF16 = 2, EPI_DGRAD_F32 = 3, EPI_WGRAD = 4 };
 enum { AUX_NONE = 0, AUX_H = 1, AUX_Z = 2 };
+
+static_assert(16 * kMaxStages + 32 + 8 * kMaxAuxSlots + 8 <= kCtrl, "control block too small");
 
 struct GemmParams {
   CUtensorMap tmA, tmB;        // operand loads
@@ -73,6 +76,11 @@ struct GemmParams {
   int out_segs, out_seg_cols;  // EPI_FWD_BF16: the activation leaves as out_segs segments out_seg_cols columns apart
   __nv_bfloat16* out_seg_ptr;  //   ... written with direct (quad-transposed, row-contiguous) stores to (m_bound, out_seg_ld)
   long long out_seg_ld;
+  // direct_out (plain bf16 EPI_FWD_BF16 / EPI_DGRAD_BF16): the epilogue stores its 32-column groups straight from
+  // registers to out_seg_ptr (and the pre-activation to out2_ptr) instead of staging 64-column blocks for TMA stores
+  int direct_out;
+  __nv_bfloat16* out2_ptr;
+  int aux_slots;               // direct data-gradient epilogue: slots of the aux ring, prefetch distance aux_slots - 1
 };
 
 struct Item { int m_tile, n_blk0, n_nblk, kb0, kb1, split; };
@@ -195,13 +203,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   const uint32_t ctrl = OST + P.staging_bytes;
   const uint32_t bar_full = ctrl, bar_empty = ctrl + 8 * kMaxStages, bar_tfull = ctrl + 16 * kMaxStages,
                  bar_tempty = bar_tfull + 16, bar_aux = bar_tfull + 32;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(gbase + (ctrl - base) + 16 * kMaxStages + 64);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(gbase + (ctrl - base) + 16 * kMaxStages + 32 + 8 * kMaxAuxSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, kEpiThreads); }
-    for (int s = 0; s < kNumStaging; ++s) mbar_init(bar_aux + 8 * s, 1);
+    for (int s = 0; s < kMaxAuxSlots; ++s) mbar_init(bar_aux + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -292,10 +300,31 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     const bool has_aux = MODE == EPI_DGRAD_BF16 && P.aux_kind != AUX_NONE;
     int gb = 0;                              // staging-ring position (one per bf16 block stored)
     int li = 0;
-    if (has_aux && leader && (int)blockIdx.x < n_items) {
-      const Item it0 = decode_item(P, blockIdx.x);
-      mbar_arrive_expect_tx(bar_aux, kStaging);
-      tma_load_2d(OST, &P.tmAux, it0.n_blk0 * 64, it0.m_tile * kTileM, bar_aux);
+    // direct-store data gradient: the leader's prefetch cursor walks the CTA's (item, block) sequence aux_slots - 1
+    // blocks ahead of the epilogue (the saved activations come from HBM: one block ahead left every block waiting
+    // for a full memory latency)
+    int pf_item = blockIdx.x, pf_cb = 0, pf_gb = 0;
+    Item pf_it = decode_item(P, pf_item < n_items ? pf_item : 0);
+    auto prefetch_aux = [&]() {
+      if (pf_item >= n_items) return;
+      const int slot = pf_gb % P.aux_slots;
+      mbar_arrive_expect_tx(bar_aux + 8 * slot, kStaging);
+      tma_load_2d(OST + slot * kStaging, &P.tmAux, (pf_it.n_blk0 + pf_cb) * 64, pf_it.m_tile * kTileM, bar_aux + 8 * slot);
+      ++pf_gb;
+      if (++pf_cb == pf_it.n_nblk) {
+        pf_cb = 0;
+        pf_item += gridDim.x;
+        if (pf_item < n_items) pf_it = decode_item(P, pf_item);
+      }
+    };
+    if (has_aux && leader) {
+      if (MODE == EPI_DGRAD_BF16 && P.direct_out) {
+        for (int i = 0; i + 1 < P.aux_slots; ++i) prefetch_aux();
+      } else if ((int)blockIdx.x < n_items) {
+        const Item it0 = decode_item(P, blockIdx.x);
+        mbar_arrive_expect_tx(bar_aux, kStaging);
+        tma_load_2d(OST, &P.tmAux, it0.n_blk0 * 64, it0.m_tile * kTileM, bar_aux);
+      }
     }
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
       const Item it = decode_item(P, item);
@@ -336,6 +365,78 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             }
             store_group_rows(P.out_seg_ptr + (long long)pass * P.out_seg_cols + col0, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
           }
+        } else if (MODE == EPI_FWD_BF16 && P.direct_out) {
+          // plain bf16 forward, direct stores: no shared-memory round trip, proxy fence, CTA barrier or store wait per
+          // 64-column block -- with K = 288 (the 275-wide MultiONet layers) a tile's MMAs take 3.3 k cycles, the staged
+          // epilogue of its four blocks took twice that (gemm_kernel<0> 490 TFLOP/s on the last Linears)
+          tmem_ld_wait();
+          float f[32];
+          act_block_rt(P.act, v, f, P.act_param);
+          const bool edge = col0 + 32 > P.n_true;
+          uint32_t R[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = f[2 * i], b = f[2 * i + 1];
+            if (edge) {
+              const int col = col0 + 2 * i;
+              if (col >= P.n_true) a = (col == P.ones_col) ? 1.f : 0.f;
+              if (col + 1 >= P.n_true) b = (col + 1 == P.ones_col) ? 1.f : 0.f;
+            }
+            R[i] = pack_bf16(a, b);
+          }
+          store_group_rows(P.out_seg_ptr + col0, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
+          if (P.save_z) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
+              if (edge) {
+                const int col = col0 + 2 * i;
+                if (col >= P.n_true) a = 0.f;
+                if (col + 1 >= P.n_true) b = 0.f;
+              }
+              R[i] = pack_bf16(a, b);
+            }
+            store_group_rows(P.out2_ptr + col0, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
+          }
+        } else if (MODE == EPI_DGRAD_BF16 && P.direct_out) {
+          // data gradient, direct stores; the saved h / z block still arrives by TMA in the 3-slot ring one block ahead
+          const int buf = gb % P.aux_slots;
+          const uint32_t ost = OST + buf * kStaging;
+          float f[32];
+          if (has_aux) {
+            // the block fetched now goes to the slot read during block gb-1: behind this barrier every thread has
+            // finished block gb-1
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (leader) prefetch_aux();
+            uint32_t aw[16];
+            mbar_wait(bar_aux + 8 * buf, (uint32_t)(gb / P.aux_slots) & 1);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int c8 = h * 4 + g;
+              ld_shared_v4(ost + (uint32_t)(r * 128 + ((c8 ^ (r & 7)) << 4)), aw[g * 4], aw[g * 4 + 1], aw[g * 4 + 2],
+                           aw[g * 4 + 3]);
+            }
+            tmem_ld_wait();
+            dact_block_rt(P.act, P.aux_kind, v, aw, f, P.act_param);
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          }
+          const bool edge = col0 + 32 > P.n_true;
+          uint32_t R[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = f[2 * i], b = f[2 * i + 1];
+            if (edge) {
+              const int col = col0 + 2 * i;
+              if (col >= P.n_true) a = (col == P.ones_col) ? 1.f : 0.f;
+              if (col + 1 >= P.n_true) b = (col + 1 == P.ones_col) ? 1.f : 0.f;
+            }
+            R[i] = pack_bf16(a, b);
+          }
+          store_group_rows(P.out_seg_ptr + col0, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
+          gb += 1;
         } else if constexpr (kStaged) {
           const int buf = gb % kNumStaging;
           const uint32_t ost = OST + buf * kStaging;
@@ -772,6 +873,12 @@ static cudaError_t set_smem_attr() {
   return e;
 }
 
+// CB_TC_GEMM_DIRECT=0: the plain bf16 forward / data-gradient epilogues go back to staged TMA stores (comparison switch)
+static bool gemm_direct_out() {
+  static const int v = [] { const char* e = getenv("CB_TC_GEMM_DIRECT"); return (e && atoi(e) == 0) ? 0 : 1; }();
+  return v != 0;
+}
+
 static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
   GemmParams P;
   memset(&P, 0, sizeof(P));
@@ -800,12 +907,27 @@ static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
       P.out_seg_ptr = c.out_bf16; P.out_seg_ld = 3 * c.out_ld;
     }
   }
+  if (!c.x3 && (c.mode == EPI_FWD_BF16 || c.mode == EPI_DGRAD_BF16) && gemm_direct_out()) {
+    P.direct_out = 1;
+    P.out_seg_ptr = c.out_bf16; P.out_seg_ld = c.out_ld; P.out2_ptr = c.out2_bf16;
+  }
   const long long seg_mul = c.x3 ? 3 : 1;
   P.a_mn = c.a_mn; P.b_mn = c.b_mn;
   const int widest = (P.n_blocks + P.n_tiles - 1) / P.n_tiles;
   P.b_box_rows = widest * 64;
   P.stage_bytes = kStageA + widest * kBoxBytes;
   P.staging_bytes = c.mode == EPI_WGRAD ? 0 : kNumStaging * kStaging;
+  P.aux_slots = kNumStaging;
+  if (P.direct_out && c.mode == EPI_FWD_BF16) P.staging_bytes = 0;     // nothing staged: the space goes to operand stages
+  if (P.direct_out && c.mode == EPI_DGRAD_BF16 && c.aux_kind != AUX_NONE) {
+    // all slots prefetch (nothing is staged for stores): as many as leave three operand stages -- four when the
+    // reduction is long (there the epilogue is rare and the operand pipeline sets the pace)
+    const int keep_stages = P.kblocks > 8 ? 4 : 3;
+    int slots = (kMaxSmem - 1024 - kCtrl - keep_stages * P.stage_bytes) / kStaging;
+    slots = slots > kMaxAuxSlots ? kMaxAuxSlots : slots;
+    if (const char* e = getenv("CB_TC_GEMM_AUX_SLOTS")) { const int v = atoi(e); if (v >= 2 && v <= kMaxAuxSlots) slots = v; }
+    if (slots >= 2) { P.aux_slots = slots; P.staging_bytes = slots * kStaging; }
+  }
   P.stages = (kMaxSmem - 1024 - P.staging_bytes - kCtrl) / P.stage_bytes;
   if (P.stages > kMaxStages) P.stages = kMaxStages;
   const size_t smem = 1024 + (size_t)P.stages * P.stage_bytes + P.staging_bytes + kCtrl;
@@ -973,7 +1095,8 @@ extern "C" int64_t cb_tc_train_scratch_bytes(const cb_tc_train* p, int64_t rows)
 // shared by the training forward (activations saved per layer) and the gradient-free forward
 // (two ping-pong activation buffers, no pre-activation stores)
 static int32_t chain_forward_impl(cb_tc_train* p, const float* const* d_W, const float* const* d_b, const float* d_x,
-                                  int64_t rows, void* d_y, uint8_t* buf, bool keep, cudaStream_t st) {
+                                  int64_t rows, void* d_y, uint8_t* buf, bool keep, cudaStream_t st,
+                                  bool skip_last = false) {
   const int n = p->n;
   const long long rp = rows_pad(rows);
   int ld_max = 0;
@@ -1002,7 +1125,7 @@ static int32_t chain_forward_impl(cb_tc_train* p, const float* const* d_W, const
     if (int32_t e = hidden_chain_launch_saving(p->fused_hidden, d_x, rows, act_ptr(n - 1), save, save_ld, st)) return e;
     first = n - 1;
   }
-  for (int i = first; i < n; ++i) {
+  for (int i = first; i < (skip_last ? n - 1 : n); ++i) {
     const bool last = i == n - 1;
     GemmCall c;
     memset(&c, 0, sizeof(c));
@@ -1042,6 +1165,29 @@ extern "C" int32_t cb_tc_train_forward(cb_tc_train* p, const float* const* d_W, 
   CB_CHECK_ARG(((uintptr_t)d_saved & 255) == 0, "saved buffer must be 256-byte aligned");
   if (saved_bytes < cb_tc_train_saved_bytes(p, rows)) { set_error("saved buffer too small"); return CB_ERR_WORKSPACE; }
   return chain_forward_impl(p, d_W, d_b, d_x, rows, d_y, reinterpret_cast<uint8_t*>(d_saved), true, (cudaStream_t)stream);
+}
+
+// The same without the last Linear: packs every layer's weights (the backward pass reads the transposed packs),
+// runs and saves H_0 .. H_{n-1}.  For MultiONet, whose two last Linears and split scalar product are one launch of the
+// final kernel (cb_tc_multionet_final_train) reading H_{n-1} of both nets at cb_tc_train_saved_offset(plan, rows, n-1).
+extern "C" int32_t cb_tc_train_forward_hidden(cb_tc_train* p, const float* const* d_W, const float* const* d_b,
+                                              const float* d_x, int64_t rows, void* d_saved, int64_t saved_bytes,
+                                              void* stream) {
+  CB_CHECK_ARG(p && d_W && d_b, "NULL pointer argument");
+  CB_CHECK_ARG(rows >= 0, "rows < 0");
+  CB_CHECK_ARG(p->n >= 2, "a chain of one Linear has no hidden part");
+  if (rows == 0) return CB_OK;
+  CB_CHECK_ARG(d_x && d_saved, "NULL pointer argument");
+  CB_CHECK_ARG(((uintptr_t)d_saved & 255) == 0, "saved buffer must be 256-byte aligned");
+  if (saved_bytes < cb_tc_train_saved_bytes(p, rows)) { set_error("saved buffer too small"); return CB_ERR_WORKSPACE; }
+  return chain_forward_impl(p, d_W, d_b, d_x, rows, nullptr, reinterpret_cast<uint8_t*>(d_saved), true,
+                            (cudaStream_t)stream, true);
+}
+
+// Byte offset of the saved bf16 activation H_layer (rows, cb_tc_train_ld(plan, layer)) inside the saved buffer.
+extern "C" int64_t cb_tc_train_saved_offset(const cb_tc_train* p, int64_t rows, int32_t layer) {
+  if (!p || rows < 0 || layer < 0 || layer >= p->n) return -1;
+  return saved_offset(p, rows, layer, 0);
 }
 
 // Gradient-free y = chain(x) with one tensor-core GEMM per layer (chains too wide for the fused single-launch

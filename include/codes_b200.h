@@ -334,6 +334,16 @@ CB_API int32_t cb_tc_multionet_forward_timed(cb_tc_multionet* plan, const float*
                                              const float* d_trunk_in, int64_t rows, float* d_y,
                                              void* d_workspace, int64_t workspace_bytes, void* stream,
                                              float* phase_ms);
+/* TRAINING forward of the two last Linears + the split scalar product (deeponet.py:241-253; the training loop
+ * deeponet.py:340-351) in one launch of the same final kernel: y (rows, Q) fp32, plus both last-layer outputs as bf16
+ * (rows, ld_out) for the backward pass (cb_tc_combine_bwd, cb_tc_train_backward).  d_hb / d_ht: the last hidden
+ * activations of the branch / trunk net, bf16 (rows, ld_h) with the constant-one column at index K (what
+ * cb_tc_train_forward_hidden saves).  The last-layer weights (fp32, (n_out, K) and (n_out)) are packed by every call;
+ * a later cb_tc_multionet_forward on the same plan needs cb_tc_multionet_set_weights again. */
+CB_API int32_t cb_tc_multionet_final_train(cb_tc_multionet* plan, const float* d_Wb_last, const float* d_bb_last,
+                                           const float* d_Wt_last, const float* d_bt_last, const void* d_hb,
+                                           const void* d_ht, int64_t ld_h, int64_t rows, float* d_y, void* d_yb,
+                                           void* d_yt, int64_t ld_out, void* stream);
 
 /* MultiONet on the (trajectory x time) grid: de-duplicated inference for loaders built by
  * MultiONet.prepare_data, whose rows r = n*T + t repeat x0[n] T times and tile the time grid N times
@@ -385,6 +395,15 @@ CB_API int64_t cb_tc_train_scratch_bytes(const cb_tc_train* plan, int64_t rows);
 CB_API int32_t cb_tc_train_forward(cb_tc_train* plan, const float* const* d_W, const float* const* d_b,
                                    const float* d_x, int64_t rows, void* d_y, void* d_saved,
                                    int64_t saved_bytes, void* stream);
+/* The same without the last Linear: H_0 .. H_{n-1} are computed and saved, every layer's weights are packed for the
+ * backward pass.  For MultiONet (deeponet.py:241-253), whose two last Linears and split scalar product run as ONE
+ * launch (cb_tc_multionet_final_train) on H_{n-1} of both nets.  cb_tc_train_saved_offset: byte offset of the bf16
+ * activation H_layer, (rows, cb_tc_train_ld(plan, layer)) with the constant-one column at index dims[layer], inside
+ * the saved buffer (layer < n). */
+CB_API int32_t cb_tc_train_forward_hidden(cb_tc_train* plan, const float* const* d_W, const float* const* d_b,
+                                          const float* d_x, int64_t rows, void* d_saved, int64_t saved_bytes,
+                                          void* stream);
+CB_API int64_t cb_tc_train_saved_offset(const cb_tc_train* plan, int64_t rows, int32_t layer);
 /* gradient-free y = chain(x), one tensor-core GEMM per layer, for chains too wide for the fused
  * single-launch kernel (cb_tc_chain_supported == 0), e.g. FullyConnected 6 -> 800 x 8 -> 5. */
 CB_API int64_t cb_tc_train_infer_bytes(const cb_tc_train* plan, int64_t rows);

@@ -138,6 +138,45 @@ def test_multionet_training_step_matches_fp32_path(Q, T, hid, nb, nt, f, n):
         assert rel(a, b) <= 3e-2
 
 
+@pytest.mark.parametrize("Q,T,hid,nb,nt,f,n", [(29, 100, 275, 5, 9, 98, 41), (7, 50, 96, 2, 3, 13, 90)])
+def test_multionet_fused_last_layers_match_gemm_plus_combine(Q, T, hid, nb, nt, f, n, monkeypatch):
+    """Training forward with both last Linears + the split scalar product in one launch of the final kernel
+    (cb_tc_multionet_final_train) vs two last-layer GEMMs + the bf16 combine kernel: same saved bf16 outputs up to the
+    rounding of the product (fp32 accumulators here, bf16-rounded factors there), same gradients."""
+    _tc()
+    import codes_b200 as cb
+    torch.manual_seed(Q)
+    m = cb.MultiONet(DEV, Q, T, 0, None, {"hidden_size": hid, "branch_hidden_layers": nb, "trunk_hidden_layers": nt,
+                                          "output_factor": f, "activation": nn.LeakyReLU()})
+    d = O.synthetic_dataset(n, T, Q, seed=5)
+    tr, _, _ = m.prepare_data(d, None, None, np.linspace(0, 1, T), n * T, shuffle=False)
+    batch = next(iter(tr))
+    res = {}
+    try:
+        cb.set_precision("bf16"); cb.set_train_precision("bf16")
+        for fused in ("1", "0"):
+            monkeypatch.setenv("CB_TC_TRAIN_FUSED_FINAL", fused)
+            m.zero_grad()
+            out, tgt = m(batch)
+            loss = cb.ops.pointwise_loss(out, tgt, "mse")
+            loss.backward()
+            res[fused] = (out.detach().clone(), [p.grad.clone() for p in m.parameters()])
+    finally:
+        cb.set_precision("fp32")
+    assert rel(res["1"][0], res["0"][0]) <= 1e-2
+    for a, b in zip(res["1"][1], res["0"][1]):
+        assert torch.isfinite(a).all()
+        assert rel(a, b) <= 1e-2
+    # the fused forward leaves the model's inference plan without packed weights: predict-side forward re-packs
+    with torch.no_grad():
+        cb.set_precision("bf16")
+        try:
+            y_inf = m(batch)[0]
+        finally:
+            cb.set_precision("fp32")
+    assert rel(y_inf, res["1"][0]) <= 1e-2
+
+
 @pytest.mark.parametrize("which", ["fcnn", "multionet"])
 def test_fit_loss_curve_tracks_fp32_mode(which):
     """same seed, same data, same schedule: the validation losses recorded by fit() in the bf16 training
