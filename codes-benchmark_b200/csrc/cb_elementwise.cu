@@ -87,24 +87,76 @@ __global__ void combine_bwd_kernel(const float* __restrict__ br, const float* __
 }
 
 // --------------------------------------------------------------- LatentPoly
-// One thread per (b, t) point writes the L latent values of that point (contiguous): no per-element 64-bit div / mod
-// (the element-per-thread version spent its time in index arithmetic: 566 GB/s = 9 % of HBM on a write-only kernel).
+// z[b,t,l] = z0[b,l] + t * Horner_l(t): the polynomial part depends on (t,l) only, so a thread owns ONE element j =
+// t*L + l of the (T*L)-float trajectory row, evaluates Horner once and then walks the trajectories b = blockIdx.y,
+// + gridDim.y, ...: one fma, one cached z0 load and one fully coalesced store per element, no per-element index
+// arithmetic.  (Round 1: element per thread with 64-bit div / mod, 0.57 TB/s; point per thread with L strided 4-byte
+// stores, 1.3 TB/s -- on a write-only kernel.)
 __global__ void poly_fwd_kernel(const float* __restrict__ C, const float* __restrict__ z0,
                                 const float* __restrict__ t, int64_t B, int T, int L, int deg,
                                 float* __restrict__ z) {
-  const int64_t points = B * T;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < points; i += stride) {
-    const int64_t b = i / T;
-    const int ti = (int)(i - b * T);
+  const int TL = T * L;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= TL) return;
+  const int ti = j / L, l = j - ti * L;
+  const float tv = __ldg(t + ti);
+  float p = 0.f;
+  for (int d = deg - 1; d >= 0; --d) p = fmaf(p, tv, __ldg(C + l * deg + d));  // Horner
+  const int64_t nb = gridDim.y;
+  int64_t b = blockIdx.y;
+  for (; b + 3 * nb < B; b += 4 * nb) {
+    const float a0 = __ldg(z0 + b * L + l), a1 = __ldg(z0 + (b + nb) * L + l), a2 = __ldg(z0 + (b + 2 * nb) * L + l),
+                a3 = __ldg(z0 + (b + 3 * nb) * L + l);
+    z[b * TL + j] = fmaf(p, tv, a0);
+    z[(b + nb) * TL + j] = fmaf(p, tv, a1);
+    z[(b + 2 * nb) * TL + j] = fmaf(p, tv, a2);
+    z[(b + 3 * nb) * TL + j] = fmaf(p, tv, a3);
+  }
+  for (; b < B; b += nb) z[b * TL + j] = fmaf(p, tv, __ldg(z0 + b * L + l));
+}
+
+// The same values through 16-byte stores over the FLAT (B*T*L) array (trajectory rows of T*L floats start at arbitrary
+// 4-byte offsets, so the row kernel's warp stores straddle lines): the per-(t,l) Horner value, its t and l sit in
+// shared-memory tables, a thread owns float4 number i4, i4 + stride, ... and keeps (b, j) of its first element by
+// increments (one 64-bit division per thread).  Used when the tables fit (T*L <= 4096) and z is 16-byte aligned.
+__global__ void poly_fwd_flat_kernel(const float* __restrict__ C, const float* __restrict__ z0,
+                                     const float* __restrict__ t, int64_t B, int T, int L, int deg,
+                                     float* __restrict__ z) {
+  extern __shared__ float psm[];
+  const int TL = T * L;
+  float* P = psm;
+  float* TV = psm + TL;
+  int* LL = reinterpret_cast<int*>(psm + 2 * TL);
+  for (int j = threadIdx.x; j < TL; j += blockDim.x) {
+    const int ti = j / L, l = j - ti * L;
     const float tv = __ldg(t + ti);
-    const float* z0b = z0 + b * L;
-    float* out = z + i * L;
-    for (int l = 0; l < L; ++l) {
-      float p = 0.f;
-      for (int d = deg - 1; d >= 0; --d) p = fmaf(p, tv, __ldg(C + l * deg + d));  // Horner
-      out[l] = fmaf(p, tv, __ldg(z0b + l));
-    }
+    float p = 0.f;
+    for (int d = deg - 1; d >= 0; --d) p = fmaf(p, tv, __ldg(C + l * deg + d));  // Horner
+    P[j] = p; TV[j] = tv; LL[j] = l;
+  }
+  __syncthreads();
+  const int64_t total = B * TL, n4 = total / 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t b = (i4 * 4) / TL;
+  int j = (int)(i4 * 4 - b * TL);
+  const int64_t db = (stride * 4) / TL;
+  const int dj = (int)(stride * 4 - db * TL);
+  auto value = [&](int64_t bb, int jj) {
+    if (jj >= TL) { jj -= TL; ++bb; }
+    return fmaf(P[jj], TV[jj], __ldg(z0 + bb * L + LL[jj]));
+  };
+  for (; i4 < n4; i4 += stride) {
+    float4 o;
+    o.x = value(b, j); o.y = value(b, j + 1); o.z = value(b, j + 2); o.w = value(b, j + 3);
+    reinterpret_cast<float4*>(z)[i4] = o;
+    b += db; j += dj;
+    if (j >= TL) { j -= TL; ++b; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(total - n4 * 4)) {      // at most 3 tail elements
+    const int64_t e = n4 * 4 + threadIdx.x;
+    const int64_t bb = e / TL;
+    z[e] = value(bb, (int)(e - bb * TL));
   }
 }
 
@@ -177,67 +229,77 @@ __global__ void pointwise_loss_kernel(const float* __restrict__ pred, const floa
   if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
 
-// trajectory + derivative terms of ModelWrapper.total_loss; one thread per (b,q) column.
-// smem: d[T][blockDim], g[T][blockDim]
-__global__ void latent_loss_kernel(const float* __restrict__ xhat, const float* __restrict__ x,
-                                   int64_t B, int T, int Q, float h, int kind, float w0, float w2,
-                                   float w3, float* __restrict__ part, float* __restrict__ dxhat) {
-  extern __shared__ float sm[];
-  const int nt = blockDim.x;
-  float* d = sm;
-  float* g = sm + (size_t)T * nt;
+// trajectory + derivative terms of ModelWrapper.total_loss (latent_neural_ode.py:522-604 = latent_poly.py:383-467).
+// A CTA owns 32 consecutive (b,q) columns: lane = column, warp = one of kLossSegs time segments.  Pass 1 loads the
+// segment's rows of both tensors (independent loads, 32 consecutive floats per warp and row), keeps d = x_hat - x
+// for the whole column tile in shared memory ([T][32] floats) and sums the trajectory term.  Pass 2 walks the
+// segment with d[t-2 .. t+2] in registers: the finite-difference residuals e1 (latent_neural_ode.py:554-563) and e2
+// (565-582) of row t for the loss value, and the gradient in GATHER form -- dL/dd[j] collects row j-1 / j / j+1 of
+// the central stencils plus the one-sided boundary rows 0 and T-1 -- so nothing is accumulated in shared memory and
+// 8 CTAs of 256 threads fit an SM (the round-1 kernel scattered into a second [T][64] array: 4 CTAs x 64 threads per
+// SM, 0.6 TB/s).  Reads 8 B, writes 4 B per element.
+constexpr int kLossCols = 32, kLossSegs = 8;
+__global__ void __launch_bounds__(kLossCols * kLossSegs)
+latent_loss_kernel(const float* __restrict__ xhat, const float* __restrict__ x, int64_t B, int T, int Q, float h,
+                   int kind, float w0, float w2, float w3, float* __restrict__ part, float* __restrict__ dxhat) {
+  extern __shared__ float dsm[];                      // d[t][lane]
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
   const int64_t cols = B * Q;
-  const int64_t c = (int64_t)blockIdx.x * nt + threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * kLossCols + lane;
+  const bool valid = c < cols;
+  const int64_t b = valid ? c / Q : 0;
+  const int64_t base = b * T * Q + (valid ? c - b * Q : 0);
+  const int t0 = (int)((long long)seg * T / kLossSegs), t1 = (int)((long long)(seg + 1) * T / kLossSegs);
   const float inv_n = 1.f / (float)((double)B * T * Q);
   const float ih = 1.f / h, ih2 = 1.f / (h * h);
-  float s = 0.f;
-  if (c < cols) {
-    const int64_t b = c / Q;
-    const int q = (int)(c - b * Q);
-    const int64_t base = b * T * Q + q;
-    float traj = 0.f;
-    for (int t = 0; t < T; ++t) {
-      const float dv = xhat[base + (int64_t)t * Q] - __ldg(x + base + (int64_t)t * Q);
-      d[t * nt + threadIdx.x] = dv;
-      float v, gr;
-      loss_terms(kind, dv, v, gr);
-      traj += v;
-      g[t * nt + threadIdx.x] = w0 * gr * inv_n;
-    }
-#define D_(t) d[(t) * nt + threadIdx.x]
-#define G_(t) g[(t) * nt + threadIdx.x]
-    float s1 = 0.f, s2 = 0.f;
-    const float c1 = 2.f * w2 * inv_n, c2 = 2.f * w3 * inv_n;
-    for (int t = 0; t < T; ++t) {
-      // first derivative row t (latent_neural_ode.py:554-563)
-      float e1;
-      if (t == 0) { e1 = (D_(1) - D_(0)) * ih; G_(1) += c1 * e1 * ih; G_(0) -= c1 * e1 * ih; }
-      else if (t == T - 1) { e1 = (D_(T - 1) - D_(T - 2)) * ih; G_(T - 1) += c1 * e1 * ih; G_(T - 2) -= c1 * e1 * ih; }
-      else { e1 = (D_(t + 1) - D_(t - 1)) * (0.5f * ih); G_(t + 1) += c1 * e1 * 0.5f * ih; G_(t - 1) -= c1 * e1 * 0.5f * ih; }
-      s1 += e1 * e1;
-      // second derivative row t (latent_neural_ode.py:565-582)
-      float e2;
-      if (t == 0) {
-        e2 = (2.f * D_(0) - 5.f * D_(1) + 4.f * D_(2) - D_(3)) * ih2;
-        const float k = c2 * e2 * ih2;
-        G_(0) += 2.f * k; G_(1) -= 5.f * k; G_(2) += 4.f * k; G_(3) -= k;
-      } else if (t == T - 1) {
-        e2 = (2.f * D_(T - 1) - 5.f * D_(T - 2) + 4.f * D_(T - 3) - D_(T - 4)) * ih2;
-        const float k = c2 * e2 * ih2;
-        G_(T - 1) += 2.f * k; G_(T - 2) -= 5.f * k; G_(T - 3) += 4.f * k; G_(T - 4) -= k;
-      } else {
-        e2 = (D_(t + 1) - 2.f * D_(t) + D_(t - 1)) * ih2;
-        const float k = c2 * e2 * ih2;
-        G_(t + 1) += k; G_(t) -= 2.f * k; G_(t - 1) += k;
-      }
-      s2 += e2 * e2;
-    }
-    s = (w0 * traj + w2 * s1 + w3 * s2) * inv_n;
-    if (dxhat)
-      for (int t = 0; t < T; ++t) dxhat[base + (int64_t)t * Q] = G_(t);
-#undef D_
-#undef G_
+  float traj = 0.f;
+#pragma unroll 4
+  for (int t = t0; t < t1; ++t) {
+    const float dv = valid ? xhat[base + (int64_t)t * Q] - __ldg(x + base + (int64_t)t * Q) : 0.f;
+    dsm[t * kLossCols + lane] = dv;
+    float v, gr;
+    loss_terms(kind, dv, v, gr);
+    traj += v;
   }
+  __syncthreads();
+#define D_(t) dsm[(t) * kLossCols + lane]
+  // one-sided boundary rows (T >= 4)
+  const float e1_0 = (D_(1) - D_(0)) * ih, e1_L = (D_(T - 1) - D_(T - 2)) * ih;
+  const float e2_0 = (2.f * D_(0) - 5.f * D_(1) + 4.f * D_(2) - D_(3)) * ih2;
+  const float e2_L = (2.f * D_(T - 1) - 5.f * D_(T - 2) + 4.f * D_(T - 3) - D_(T - 4)) * ih2;
+  const float c1 = 2.f * w2 * inv_n, c2 = 2.f * w3 * inv_n;
+  float s1 = 0.f, s2 = 0.f;
+  // window d[t-2 .. t+2] (indices clamped; clamped entries are never used)
+  float dm2 = D_(max(t0 - 2, 0)), dm1 = D_(max(t0 - 1, 0)), d0 = D_(min(t0, T - 1)), dp1 = D_(min(t0 + 1, T - 1)),
+        dp2 = D_(min(t0 + 2, T - 1));
+  for (int t = t0; t < t1; ++t) {
+    // central residuals of rows t-1, t, t+1 (meaningful where the row is interior: 1 <= row <= T-2)
+    const float e1m = (d0 - dm2) * (0.5f * ih), e1p = (dp2 - d0) * (0.5f * ih);
+    const float e2m = (d0 - 2.f * dm1 + dm2) * ih2, e2c = (dp1 - 2.f * d0 + dm1) * ih2, e2p = (dp2 - 2.f * dp1 + d0) * ih2;
+    const float e1 = t == 0 ? e1_0 : (t == T - 1 ? e1_L : (dp1 - dm1) * (0.5f * ih));
+    const float e2 = t == 0 ? e2_0 : (t == T - 1 ? e2_L : e2c);
+    s1 += e1 * e1;
+    s2 += e2 * e2;
+    if (dxhat && valid) {
+      float v, gr;
+      loss_terms(kind, d0, v, gr);
+      float g1 = 0.f, g2 = 0.f;
+      if (t >= 1) g1 += (t - 1 == 0) ? ih * e1_0 : 0.5f * ih * e1m;            // row t-1 adds to column entry t
+      if (t <= T - 2) g1 -= (t + 1 == T - 1) ? ih * e1_L : 0.5f * ih * e1p;    // row t+1 subtracts
+      if (t == 0) g1 -= ih * e1_0;
+      if (t == T - 1) g1 += ih * e1_L;
+      if (t - 1 >= 1 && t - 1 <= T - 2) g2 += e2m;
+      if (t >= 1 && t <= T - 2) g2 -= 2.f * e2c;
+      if (t + 1 >= 1 && t + 1 <= T - 2) g2 += e2p;
+      if (t <= 3) g2 += (t == 0 ? 2.f : t == 1 ? -5.f : t == 2 ? 4.f : -1.f) * e2_0;
+      if (t >= T - 4) { const int k = T - 1 - t; g2 += (k == 0 ? 2.f : k == 1 ? -5.f : k == 2 ? 4.f : -1.f) * e2_L; }
+      dxhat[base + (int64_t)t * Q] = w0 * gr * inv_n + c1 * g1 + c2 * ih2 * g2;
+    }
+    dm2 = dm1; dm1 = d0; d0 = dp1; dp1 = dp2;
+    dp2 = D_(min(t + 3, T - 1));
+  }
+#undef D_
+  float s = valid ? (w0 * traj + w2 * s1 + w3 * s2) * inv_n : 0.f;
   s = block_sum(s);
   if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
@@ -389,6 +451,7 @@ __global__ void error_sums_kernel(const float* __restrict__ pred, const float* _
     const double e = fabs((double)p - (double)t);
     s_abs += e; s_sq += e * e; s_rel += e / fmax(fabs((double)t), 1e-300); s_max = fmax(s_max, e);
   };
+
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 a = __ldg(p4 + i), b = __ldg(t4 + i);
     acc(a.x, b.x); acc(a.y, b.y); acc(a.z, b.z); acc(a.w, b.w);
@@ -577,7 +640,19 @@ extern "C" int32_t cb_poly_eval_fwd(const float* d_coef, const float* d_z0, cons
   CB_CHECK_ARG(d_coef && d_z0 && d_t && d_z, "NULL pointer argument");
   CB_CHECK_ARG(batch >= 0 && n_t >= 1 && latent >= 1 && degree >= 1, "bad polynomial shape");
   if (batch == 0) return CB_OK;
-  poly_fwd_kernel<<<grid_for(batch * n_t, 1), kThreads, 0, (cudaStream_t)stream>>>(
+  CB_CHECK_ARG((int64_t)n_t * latent < (1ll << 30), "trajectory row too long");
+  const int tl = n_t * latent;
+  if (tl >= 4 && tl <= 4096 && ((uintptr_t)d_z & 15) == 0) {
+    poly_fwd_flat_kernel<<<grid_for(batch * tl / 4, 4), kThreads, (size_t)tl * 12, (cudaStream_t)stream>>>(
+        d_coef, d_z0, d_t, batch, n_t, latent, degree, d_z);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
+  const int bx = (tl + kThreads - 1) / kThreads;
+  int64_t by = ((int64_t)num_sms() * 8 + bx - 1) / bx;        // ~8 CTAs per SM
+  if (by > batch) by = batch;
+  if (by > 65535) by = 65535;
+  poly_fwd_kernel<<<dim3(bx, (unsigned)by), kThreads, 0, (cudaStream_t)stream>>>(
       d_coef, d_z0, d_t, batch, n_t, latent, degree, d_z);
   CB_LAUNCH_CHECK();
   return CB_OK;
@@ -729,12 +804,10 @@ extern "C" int32_t cb_latent_loss_fwd_bwd(const float* d_xhat, const float* d_x,
   CB_CHECK_ARG(n_t >= 4, "latent loss needs >= 4 time points (4-point one-sided stencil), got %d", n_t);
   CB_CHECK_ARG(n_timesteps_h >= 1, "n_timesteps_h must be >= 1");
   CB_CHECK_ARG(kind == CB_LOSS_MSE || kind == CB_LOSS_SMOOTHL1, "unknown loss kind %d", kind);
-  int nt = 64;
-  size_t smem = (size_t)2 * n_t * nt * sizeof(float);
-  while (smem > 200 * 1024 && nt > 32) { nt /= 2; smem = (size_t)2 * n_t * nt * sizeof(float); }
+  const size_t smem = (size_t)n_t * kLossCols * sizeof(float);
   CB_CHECK_ARG(smem <= 200 * 1024, "n_t=%d too large for the fused loss kernel", n_t);
   const int64_t cols = batch * n_q;
-  const int64_t blocks = (cols + nt - 1) / nt;
+  const int64_t blocks = (cols + kLossCols - 1) / kLossCols;
   CB_CHECK_ARG(blocks < (1ll << 31), "too many columns");
   if (ws_floats < blocks) {
     set_error("workspace too small: need %lld floats", (long long)blocks);
@@ -743,9 +816,9 @@ extern "C" int32_t cb_latent_loss_fwd_bwd(const float* d_xhat, const float* d_x,
   cudaStream_t st = (cudaStream_t)stream;
   if (smem > 48 * 1024)
     CB_CUDA(allow_max_dynamic_smem((const void*)latent_loss_kernel));
-  latent_loss_kernel<<<(unsigned)blocks, nt, smem, st>>>(d_xhat, d_x, batch, n_t, n_q,
-                                                        1.f / (float)n_timesteps_h, kind, w0, w2, w3,
-                                                        d_ws, d_dxhat);
+  latent_loss_kernel<<<(unsigned)blocks, kLossCols * kLossSegs, smem, st>>>(d_xhat, d_x, batch, n_t, n_q,
+                                                                           1.f / (float)n_timesteps_h, kind, w0, w2, w3,
+                                                                           d_ws, d_dxhat);
   CB_LAUNCH_CHECK();
   final_sum_kernel<<<1, 256, 0, st>>>(d_ws, (int)blocks, 1.f, d_loss);
   CB_LAUNCH_CHECK();
