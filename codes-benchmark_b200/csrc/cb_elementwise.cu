@@ -91,7 +91,8 @@ __global__ void combine_bwd_kernel(const float* __restrict__ br, const float* __
 // t*L + l of the (T*L)-float trajectory row, evaluates Horner once and then walks the trajectories b = blockIdx.y,
 // + gridDim.y, ...: one fma, one cached z0 load and one fully coalesced store per element, no per-element index
 // arithmetic.  (Round 1: element per thread with 64-bit div / mod, 0.57 TB/s; point per thread with L strided 4-byte
-// stores, 1.3 TB/s -- on a write-only kernel.)
+// stores, 1.3 TB/s -- on a write-only kernel; this one 3.2 TB/s.  A variant with 16-byte stores over the flat array
+// and the per-(t,l) values in shared-memory tables measured slower, 2.6 TB/s: three table reads per element.)
 __global__ void poly_fwd_kernel(const float* __restrict__ C, const float* __restrict__ z0,
                                 const float* __restrict__ t, int64_t B, int T, int L, int deg,
                                 float* __restrict__ z) {
@@ -113,51 +114,6 @@ __global__ void poly_fwd_kernel(const float* __restrict__ C, const float* __rest
     z[(b + 3 * nb) * TL + j] = fmaf(p, tv, a3);
   }
   for (; b < B; b += nb) z[b * TL + j] = fmaf(p, tv, __ldg(z0 + b * L + l));
-}
-
-// The same values through 16-byte stores over the FLAT (B*T*L) array (trajectory rows of T*L floats start at arbitrary
-// 4-byte offsets, so the row kernel's warp stores straddle lines): the per-(t,l) Horner value, its t and l sit in
-// shared-memory tables, a thread owns float4 number i4, i4 + stride, ... and keeps (b, j) of its first element by
-// increments (one 64-bit division per thread).  Used when the tables fit (T*L <= 4096) and z is 16-byte aligned.
-__global__ void poly_fwd_flat_kernel(const float* __restrict__ C, const float* __restrict__ z0,
-                                     const float* __restrict__ t, int64_t B, int T, int L, int deg,
-                                     float* __restrict__ z) {
-  extern __shared__ float psm[];
-  const int TL = T * L;
-  float* P = psm;
-  float* TV = psm + TL;
-  int* LL = reinterpret_cast<int*>(psm + 2 * TL);
-  for (int j = threadIdx.x; j < TL; j += blockDim.x) {
-    const int ti = j / L, l = j - ti * L;
-    const float tv = __ldg(t + ti);
-    float p = 0.f;
-    for (int d = deg - 1; d >= 0; --d) p = fmaf(p, tv, __ldg(C + l * deg + d));  // Horner
-    P[j] = p; TV[j] = tv; LL[j] = l;
-  }
-  __syncthreads();
-  const int64_t total = B * TL, n4 = total / 4;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t b = (i4 * 4) / TL;
-  int j = (int)(i4 * 4 - b * TL);
-  const int64_t db = (stride * 4) / TL;
-  const int dj = (int)(stride * 4 - db * TL);
-  auto value = [&](int64_t bb, int jj) {
-    if (jj >= TL) { jj -= TL; ++bb; }
-    return fmaf(P[jj], TV[jj], __ldg(z0 + bb * L + LL[jj]));
-  };
-  for (; i4 < n4; i4 += stride) {
-    float4 o;
-    o.x = value(b, j); o.y = value(b, j + 1); o.z = value(b, j + 2); o.w = value(b, j + 3);
-    reinterpret_cast<float4*>(z)[i4] = o;
-    b += db; j += dj;
-    if (j >= TL) { j -= TL; ++b; }
-  }
-  if (blockIdx.x == 0 && threadIdx.x < (int)(total - n4 * 4)) {      // at most 3 tail elements
-    const int64_t e = n4 * 4 + threadIdx.x;
-    const int64_t bb = e / TL;
-    z[e] = value(bb, (int)(e - bb * TL));
-  }
 }
 
 // dz0[b,l] = sum_t dz[b,t,l]
@@ -642,12 +598,6 @@ extern "C" int32_t cb_poly_eval_fwd(const float* d_coef, const float* d_z0, cons
   if (batch == 0) return CB_OK;
   CB_CHECK_ARG((int64_t)n_t * latent < (1ll << 30), "trajectory row too long");
   const int tl = n_t * latent;
-  if (tl >= 4 && tl <= 4096 && ((uintptr_t)d_z & 15) == 0) {
-    poly_fwd_flat_kernel<<<grid_for(batch * tl / 4, 4), kThreads, (size_t)tl * 12, (cudaStream_t)stream>>>(
-        d_coef, d_z0, d_t, batch, n_t, latent, degree, d_z);
-    CB_LAUNCH_CHECK();
-    return CB_OK;
-  }
   const int bx = (tl + kThreads - 1) / kThreads;
   int64_t by = ((int64_t)num_sms() * 8 + bx - 1) / bx;        // ~8 CTAs per SM
   if (by > batch) by = batch;

@@ -951,7 +951,9 @@ chain_ts_kernel(const __grid_constant__ ChainParams P) {
 // traffic per row halves.  The leader CTA (rank 0) issues all MMAs; both CTAs run their own TMA producer
 // (own activation tiles, own half of every weight stage; transaction bytes credited to the leader's
 // barriers) and their own epilogue (own 128 TMEM lanes); tcgen05.commit multicasts to both CTAs.
-template <bool PAIR>
+// TRAIN = true: the epilogue additionally stores both products as bf16 (FinalParams::yb) -- a separate instantiation, so
+// the inference kernel's epilogue is exactly the one measured in profiles/r2_final_kernel.md.
+template <bool PAIR, bool TRAIN>
 __global__ void __launch_bounds__(kFThreads, 1)
 don_final_kernel(const __grid_constant__ FinalParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -1173,7 +1175,7 @@ don_final_kernel(const __grid_constant__ FinalParams P) {
           else { tmem_ld16(ta_b + c0, vb); tmem_ld16(ta_t + c0, vt); }
           tmem_ld_wait();
           const int nb = j * kChunkN + c0;
-          if (P.yb[0]) {
+          if constexpr (TRAIN) {
             // training: this thread's 32 columns of both products as bf16, row-contiguous stores (8 rows x 64 B each)
             uint32_t R[16];
 #pragma unroll
@@ -1975,11 +1977,13 @@ extern "C" int32_t cb_tc_multionet_create(const cb_mlp_desc* branch, const cb_ml
   }
   for (int i = 0; i < 2 && m->pair; ++i)
     if (!encode_bf16_rows64(&F.tmap_w[i], m->d_wlast[i], (long long)m->rows_alloc * (m->Kp / kBlockK), 64)) m->pair = 0;
-  if (m->pair && allow_max_dynamic_smem((const void*)don_final_kernel<true>) != cudaSuccess) {
+  if (m->pair && (allow_max_dynamic_smem((const void*)don_final_kernel<true, false>) != cudaSuccess ||
+                  allow_max_dynamic_smem((const void*)don_final_kernel<true, true>) != cudaSuccess)) {
     cudaGetLastError();
     m->pair = 0;
   }
-  if (allow_max_dynamic_smem((const void*)don_final_kernel<false>) != cudaSuccess) {
+  if (allow_max_dynamic_smem((const void*)don_final_kernel<false, false>) != cudaSuccess ||
+      allow_max_dynamic_smem((const void*)don_final_kernel<false, true>) != cudaSuccess) {
     cb_tc_multionet_destroy(m);
     set_error("cannot reserve shared memory for the MultiONet final kernel");
     return CB_ERR_CUDA;
@@ -2112,9 +2116,12 @@ static int32_t launch_final(cb_tc_multionet* m, FinalParams& F, cudaStream_t st)
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CB_CUDA(cudaLaunchKernelEx(&cfg, don_final_kernel<true>, F));
+    if (F.yb[0]) CB_CUDA(cudaLaunchKernelEx(&cfg, don_final_kernel<true, true>, F));
+    else CB_CUDA(cudaLaunchKernelEx(&cfg, don_final_kernel<true, false>, F));
+  } else if (F.yb[0]) {
+    don_final_kernel<false, true><<<grid, kFThreads, m->smem_final, st>>>(F);
   } else {
-    don_final_kernel<false><<<grid, kFThreads, m->smem_final, st>>>(F);
+    don_final_kernel<false, false><<<grid, kFThreads, m->smem_final, st>>>(F);
   }
   CB_LAUNCH_CHECK();
   return CB_OK;

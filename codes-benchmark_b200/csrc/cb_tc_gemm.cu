@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -44,6 +45,11 @@ constexpr int kNumStaging = 3;                 // ring of output blocks: aux pre
 constexpr int kMaxAuxSlots = 8;                // direct-store data-gradient epilogue: ring of prefetched h / z blocks
 constexpr int kThreads = 320;
 constexpr int kEpiThreads = 256;
+// The bf16 data-gradient epilogue (act' from the saved activation, pack, store) is a ~400-instruction dependent chain
+// per 64-column block that two warps per scheduler cannot hide (profiles/r2_train_gemm275_ncu.md): that mode runs
+// SIXTEEN epilogue warps, four per TMEM lane quarter, 16 columns of every 64-column block each.
+constexpr int kEpiWarpsDgrad = 16;
+constexpr int kThreadsDgrad = 64 + 32 * kEpiWarpsDgrad;
 constexpr int kAccCols = 256;                  // TMEM columns per accumulator slot
 constexpr int kCtrl = 256;
 
@@ -51,6 +57,14 @@ enum { EPI_FWD_BF16 = 0, EPI_FWD_F32 = 1, EPI_DGRAD_BF16 = 2, EPI_DGRAD_F32 = 3,
 enum { AUX_NONE = 0, AUX_H = 1, AUX_Z = 2 };
 
 static_assert(16 * kMaxStages + 32 + 8 * kMaxAuxSlots + 8 <= kCtrl, "control block too small");
+
+// cycle counters per role and wait reason of CTA 0 (compile with CB_EXTRA_NVCC_FLAGS=-DCB_TC_GEMM_DBG, run with
+// CB_TC_GEMM_DBG=<mode> to print them after every launch of that epilogue mode)
+#ifdef CB_TC_GEMM_DBG
+#define GCLK() clock64()
+#else
+#define GCLK() 0ll
+#endif
 
 struct GemmParams {
   CUtensorMap tmA, tmB;        // operand loads
@@ -81,6 +95,7 @@ struct GemmParams {
   int direct_out;
   __nv_bfloat16* out2_ptr;
   int aux_slots;               // direct data-gradient epilogue: slots of the aux ring, prefetch distance aux_slots - 1
+  long long* dbg;              // CB_TC_GEMM_DBG: cycle counters of CTA 0, else NULL
 };
 
 struct Item { int m_tile, n_blk0, n_nblk, kb0, kb1, split; };
@@ -164,6 +179,33 @@ __device__ __forceinline__ void dact_block(const uint32_t (&v)[32], const uint32
     f[2 * i + 1] = __uint_as_float(v[2 * i + 1]) * dact<ACT, FROM_Z>(bf16_hi(aw[i]), p);
   }
 }
+template <int ACT, bool FROM_Z>
+__device__ __forceinline__ void dact_block16(const uint32_t (&v)[16], const uint32_t (&aw)[8], float (&f)[16], float p) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    f[2 * i] = __uint_as_float(v[2 * i]) * dact<ACT, FROM_Z>(bf16_lo(aw[i]), p);
+    f[2 * i + 1] = __uint_as_float(v[2 * i + 1]) * dact<ACT, FROM_Z>(bf16_hi(aw[i]), p);
+  }
+}
+__device__ __forceinline__ void dact_block16_rt(int act, int aux_kind, const uint32_t (&v)[16], const uint32_t (&aw)[8],
+                                                float (&f)[16], float p) {
+  switch (act) {
+    case CB_ACT_RELU: dact_block16<CB_ACT_RELU, false>(v, aw, f, p); break;
+    case CB_ACT_LEAKYRELU:
+    case CB_ACT_PRELU:
+      if (aux_kind == AUX_Z) dact_block16<CB_ACT_LEAKYRELU, true>(v, aw, f, p);
+      else dact_block16<CB_ACT_LEAKYRELU, false>(v, aw, f, p);
+      break;
+    case CB_ACT_TANH: dact_block16<CB_ACT_TANH, false>(v, aw, f, p); break;
+    case CB_ACT_GELU: dact_block16<CB_ACT_GELU, true>(v, aw, f, p); break;
+    case CB_ACT_ELU: dact_block16<CB_ACT_ELU, false>(v, aw, f, p); break;
+    case CB_ACT_SILU: dact_block16<CB_ACT_SILU, true>(v, aw, f, p); break;
+    case CB_ACT_SOFTPLUS: dact_block16<CB_ACT_SOFTPLUS, false>(v, aw, f, p); break;
+    case CB_ACT_MISH: dact_block16<CB_ACT_MISH, true>(v, aw, f, p); break;
+    case CB_ACT_SIGMOID: dact_block16<CB_ACT_SIGMOID, false>(v, aw, f, p); break;
+    default: dact_block16<CB_ACT_IDENTITY, false>(v, aw, f, p); break;
+  }
+}
 __device__ __forceinline__ void dact_block_rt(int act, int aux_kind, const uint32_t (&v)[32], const uint32_t (&aw)[16],
                                               float (&f)[32], float p) {
   switch (act) {
@@ -194,7 +236,9 @@ __device__ __forceinline__ void tma_store_wait_read_le(int n) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmParams P) {
+__global__ void __launch_bounds__(MODE == EPI_DGRAD_BF16 ? kThreadsDgrad : kThreads, 1)
+gemm_kernel(const __grid_constant__ GemmParams P) {
+  constexpr int kEpiThreadsM = MODE == EPI_DGRAD_BF16 ? 32 * kEpiWarpsDgrad : kEpiThreads;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -208,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, kEpiThreads); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, kEpiThreadsM); }
     for (int s = 0; s < kMaxAuxSlots; ++s) mbar_init(bar_aux + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -226,12 +270,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   if (warp == 0) {
     // ============================================================ TMA producer
     int stage = 0; uint32_t phase = 0;
+    long long g_empty = 0;
+    const long long g_start = GCLK();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode_item(P, item);
       const uint32_t bytes = (uint32_t)kStageA + (P.b_mn ? (uint32_t)it.n_nblk * kBoxBytes : (uint32_t)P.b_box_rows * 128u);
       int term = it.kb0 / P.kblocks, kb = it.kb0 - term * P.kblocks;
       for (int kk = it.kb0; kk < it.kb1; ++kk) {
+        const long long g0 = GCLK();
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        g_empty += GCLK() - g0;
         if (elect_one()) {
           const uint32_t sa = base + stage * P.stage_bytes, sb = sa + kStageA, full = bar_full + 8 * stage;
           mbar_arrive_expect_tx(full, bytes);
@@ -254,23 +302,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
     }
+    if (P.dbg && blockIdx.x == 0 && lane == 0) { P.dbg[0] = GCLK() - g_start; P.dbg[1] = g_empty; }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
     int stage = 0; uint32_t phase = 0;
     int li = 0;
+    long long g_tempty = 0, g_full = 0;
+    const long long g_start = GCLK();
     // descriptor increments per 16-element k-step, in 16-byte units: K-major +32 B, MN-major +16 rows x 128 B
     const uint64_t a_step = P.a_mn ? 128u : 2u, b_step = P.b_mn ? 128u : 2u;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
       const Item it = decode_item(P, item);
       const int slot = li & 1;
+      long long g0 = GCLK();
       mbar_wait(bar_tempty + 8 * slot, ((uint32_t)(li >> 1) & 1) ^ 1);
       tcgen05_fence_after();
+      g_tempty += GCLK() - g0;
       const uint32_t d_tmem = tmem_base + (uint32_t)slot * kAccCols;
       const uint32_t idesc = make_idesc_mn(it.n_nblk * 64, P.a_mn, P.b_mn);
       int kb = it.kb0 % P.kblocks;
       for (int kk = it.kb0; kk < it.kb1; ++kk) {
+        g0 = GCLK();
         mbar_wait(bar_full + 8 * stage, phase);
         tcgen05_fence_after();
+        g_full += GCLK() - g0;
         const uint32_t sa = base + stage * P.stage_bytes, sb = sa + kStageA;
         const uint64_t adesc = P.a_mn ? make_smem_desc_mn(sa) : make_smem_desc(sa);
         const uint64_t bdesc = P.b_mn ? make_smem_desc_mn(sb) : make_smem_desc(sb);
@@ -289,6 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       if (elect_one()) umma_commit(bar_tfull + 8 * slot);
       __syncwarp();
     }
+    if (P.dbg && blockIdx.x == 0 && lane == 0) { P.dbg[2] = GCLK() - g_start; P.dbg[3] = g_tempty; P.dbg[4] = g_full; P.dbg[5] = li; }
   } else {
     // ============================================================ epilogue warps (2..9)
     const int q = warp & 3;                 // TMEM lane quarter
@@ -303,14 +359,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     // direct-store data gradient: the leader's prefetch cursor walks the CTA's (item, block) sequence aux_slots - 1
     // blocks ahead of the epilogue (the saved activations come from HBM: one block ahead left every block waiting
     // for a full memory latency)
-    int pf_item = blockIdx.x, pf_cb = 0, pf_gb = 0;
+    // (ring positions and phases are kept by increments: a runtime % or / per block sits on the epilogue's critical path)
+    int pf_item = blockIdx.x, pf_cb = 0, pf_slot = 0;
+    int aux_buf = 0; uint32_t aux_phase = 0;       // consumer side of the ring (every epilogue thread)
     Item pf_it = decode_item(P, pf_item < n_items ? pf_item : 0);
     auto prefetch_aux = [&]() {
       if (pf_item >= n_items) return;
-      const int slot = pf_gb % P.aux_slots;
+      const int slot = pf_slot;
       mbar_arrive_expect_tx(bar_aux + 8 * slot, kStaging);
       tma_load_2d(OST + slot * kStaging, &P.tmAux, (pf_it.n_blk0 + pf_cb) * 64, pf_it.m_tile * kTileM, bar_aux + 8 * slot);
-      ++pf_gb;
+      if (++pf_slot == P.aux_slots) pf_slot = 0;
       if (++pf_cb == pf_it.n_nblk) {
         pf_cb = 0;
         pf_item += gridDim.x;
@@ -318,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       }
     };
     if (has_aux && leader) {
-      if (MODE == EPI_DGRAD_BF16 && P.direct_out) {
+      if (MODE == EPI_DGRAD_BF16) {
         for (int i = 0; i + 1 < P.aux_slots; ++i) prefetch_aux();
       } else if ((int)blockIdx.x < n_items) {
         const Item it0 = decode_item(P, blockIdx.x);
@@ -326,15 +384,71 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         tma_load_2d(OST, &P.tmAux, it0.n_blk0 * 64, it0.m_tile * kTileM, bar_aux);
       }
     }
+    long long g_tfull = 0, g_aux = 0, g_bar = 0, g_ld = 0, g_st = 0, g_pf = 0;
+    const long long g_start = GCLK();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
       const Item it = decode_item(P, item);
       const int slot = li & 1;
+      const long long g0 = GCLK();
       mbar_wait(bar_tfull + 8 * slot, (uint32_t)(li >> 1) & 1);
       tcgen05_fence_after();
+      g_tfull += GCLK() - g0;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * kAccCols;
       const long long row_g = (long long)it.m_tile * kTileM + r;
       for (int cb = 0; cb < it.n_nblk; ++cb) {
         const int col_blk = (it.n_blk0 + cb) * 64;          // first global output column of this block
+        if constexpr (MODE == EPI_DGRAD_BF16) {
+          // sixteen warps: h = 0..3 is the 16-column quarter of the block; direct row-contiguous stores; the saved
+          // h / z block arrives by TMA in a ring of P.aux_slots blocks, aux_slots - 1 blocks ahead
+          const int c16 = col_blk + h * 16;
+          uint32_t v[16];
+          tmem_ld16x(taddr + cb * 64 + h * 16, v);
+          float f[16];
+          if (has_aux) {
+            const int buf = aux_buf;
+            const uint32_t ost = OST + buf * kStaging;
+            // the block fetched now goes to the slot read during block gb-1: behind this barrier every thread has
+            // finished block gb-1
+            long long g1 = GCLK();
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            g_bar += GCLK() - g1;
+            if (leader) { const long long g3 = GCLK(); prefetch_aux(); g_pf += GCLK() - g3; }
+            uint32_t aw[8];
+            g1 = GCLK();
+            mbar_wait(bar_aux + 8 * buf, aux_phase);
+            g_aux += GCLK() - g1;
+            if (++aux_buf == P.aux_slots) { aux_buf = 0; aux_phase ^= 1; }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int c8 = h * 2 + g;
+              ld_shared_v4(ost + (uint32_t)(r * 128 + ((c8 ^ (r & 7)) << 4)), aw[g * 4], aw[g * 4 + 1], aw[g * 4 + 2],
+                           aw[g * 4 + 3]);
+            }
+            g1 = GCLK();
+            tmem_ld_wait();
+            g_ld += GCLK() - g1;
+            dact_block16_rt(P.act, P.aux_kind, v, aw, f, P.act_param);
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          }
+          if (c16 + 16 > P.n_true) {           // (one warp-uniform branch: padding columns are zero, the bias column one)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = c16 + i;
+              f[i] = col < P.n_true ? f[i] : (col == P.ones_col ? 1.f : 0.f);
+            }
+          }
+          uint32_t R[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) R[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+          const long long g2 = GCLK();
+          store_group_rows16(P.out_seg_ptr + c16, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
+          g_st += GCLK() - g2;
+          gb += 1;
+          continue;
+        }
         const int col0 = col_blk + h * 32;                  // first column owned by this thread
         uint32_t v[32];
         tmem_ld32(taddr + cb * 64 + h * 32, v);
@@ -398,45 +512,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             }
             store_group_rows(P.out2_ptr + col0, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
           }
-        } else if (MODE == EPI_DGRAD_BF16 && P.direct_out) {
-          // data gradient, direct stores; the saved h / z block still arrives by TMA in the 3-slot ring one block ahead
-          const int buf = gb % P.aux_slots;
-          const uint32_t ost = OST + buf * kStaging;
-          float f[32];
-          if (has_aux) {
-            // the block fetched now goes to the slot read during block gb-1: behind this barrier every thread has
-            // finished block gb-1
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (leader) prefetch_aux();
-            uint32_t aw[16];
-            mbar_wait(bar_aux + 8 * buf, (uint32_t)(gb / P.aux_slots) & 1);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int c8 = h * 4 + g;
-              ld_shared_v4(ost + (uint32_t)(r * 128 + ((c8 ^ (r & 7)) << 4)), aw[g * 4], aw[g * 4 + 1], aw[g * 4 + 2],
-                           aw[g * 4 + 3]);
-            }
-            tmem_ld_wait();
-            dact_block_rt(P.act, P.aux_kind, v, aw, f, P.act_param);
-          } else {
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          }
-          const bool edge = col0 + 32 > P.n_true;
-          uint32_t R[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = f[2 * i], b = f[2 * i + 1];
-            if (edge) {
-              const int col = col0 + 2 * i;
-              if (col >= P.n_true) a = (col == P.ones_col) ? 1.f : 0.f;
-              if (col + 1 >= P.n_true) b = (col + 1 == P.ones_col) ? 1.f : 0.f;
-            }
-            R[i] = pack_bf16(a, b);
-          }
-          store_group_rows(P.out_seg_ptr + col0, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
-          gb += 1;
         } else if constexpr (kStaged) {
           const int buf = gb % kNumStaging;
           const uint32_t ost = OST + buf * kStaging;
@@ -556,6 +631,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       tcgen05_fence_before();
       mbar_arrive(bar_tempty + 8 * slot);
     }
+    if (P.dbg && blockIdx.x == 0 && et == 0) { P.dbg[6] = GCLK() - g_start; P.dbg[7] = g_tfull; P.dbg[8] = g_aux; P.dbg[9] = g_bar; P.dbg[10] = g_ld; P.dbg[11] = g_st; P.dbg[12] = g_pf; }
     if constexpr (kStaged) {
       // the bulk stores must be complete before the kernel's writes are consumed / shared memory is released
       if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -873,7 +949,7 @@ static cudaError_t set_smem_attr() {
   return e;
 }
 
-// CB_TC_GEMM_DIRECT=0: the plain bf16 forward / data-gradient epilogues go back to staged TMA stores (comparison switch)
+// CB_TC_GEMM_DIRECT=0: the plain bf16 forward epilogue goes back to staged TMA stores (comparison switch)
 static bool gemm_direct_out() {
   static const int v = [] { const char* e = getenv("CB_TC_GEMM_DIRECT"); return (e && atoi(e) == 0) ? 0 : 1; }();
   return v != 0;
@@ -907,7 +983,8 @@ static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
       P.out_seg_ptr = c.out_bf16; P.out_seg_ld = 3 * c.out_ld;
     }
   }
-  if (!c.x3 && (c.mode == EPI_FWD_BF16 || c.mode == EPI_DGRAD_BF16) && gemm_direct_out()) {
+  CB_CHECK_ARG(!(c.x3 && c.mode == EPI_DGRAD_BF16), "split precision: forward GEMMs only");
+  if (c.mode == EPI_DGRAD_BF16 || (!c.x3 && c.mode == EPI_FWD_BF16 && gemm_direct_out())) {
     P.direct_out = 1;
     P.out_seg_ptr = c.out_bf16; P.out_seg_ld = c.out_ld; P.out2_ptr = c.out2_bf16;
   }
@@ -947,6 +1024,11 @@ static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
   CB_CHECK_ARG(ok, "cuTensorMapEncodeTiled failed for a GEMM operand");
   const long long items = (long long)P.m_tiles * P.n_tiles * P.splits;
   const int grid = (int)(items < num_sms() ? items : num_sms());
+#ifdef CB_TC_GEMM_DBG
+  if (const char* e = getenv("CB_TC_GEMM_DBG")) {
+    if (atoi(e) == c.mode) { CB_CUDA(cudaMalloc(&P.dbg, 104)); CB_CUDA(cudaMemsetAsync(P.dbg, 0, 104, st)); }
+  }
+#endif
   switch (c.mode) {
     case EPI_FWD_BF16:
       CB_CUDA(set_smem_attr<EPI_FWD_BF16>());
@@ -956,7 +1038,7 @@ static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
       gemm_kernel<EPI_FWD_F32><<<grid, kThreads, smem, st>>>(P); break;
     case EPI_DGRAD_BF16:
       CB_CUDA(set_smem_attr<EPI_DGRAD_BF16>());
-      gemm_kernel<EPI_DGRAD_BF16><<<grid, kThreads, smem, st>>>(P); break;
+      gemm_kernel<EPI_DGRAD_BF16><<<grid, kThreadsDgrad, smem, st>>>(P); break;
     case EPI_DGRAD_F32:
       CB_CUDA(set_smem_attr<EPI_DGRAD_F32>());
       gemm_kernel<EPI_DGRAD_F32><<<grid, kThreads, smem, st>>>(P); break;
@@ -965,6 +1047,18 @@ static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
       gemm_kernel<EPI_WGRAD><<<grid, kThreads, smem, st>>>(P); break;
   }
   CB_LAUNCH_CHECK();
+#ifdef CB_TC_GEMM_DBG
+  if (P.dbg) {
+    long long h[13];
+    CB_CUDA(cudaStreamSynchronize(st));
+    CB_CUDA(cudaMemcpy(h, P.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(P.dbg);
+    fprintf(stderr, "[gemm dbg] mode %d  m_tiles %d n_tiles %d kblocks %d stages %d aux_slots %d | producer: total %lld, wait empty %lld | "
+                    "MMA: total %lld over %lld items, wait TMEM slot %lld, wait operands %lld | epilogue t0: total %lld, wait accumulator "
+                    "%lld, wait aux %lld, block barrier %lld, wait tcgen05.ld %lld, stores %lld, leader prefetch %lld\n", c.mode, P.m_tiles, P.n_tiles, P.kblocks, P.stages, P.aux_slots,
+            h[0], h[1], h[2], h[5], h[3], h[4], h[6], h[7], h[8], h[9], h[10], h[11], h[12]);
+  }
+#endif
   return CB_OK;
 }
 

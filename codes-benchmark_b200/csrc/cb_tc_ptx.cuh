@@ -130,6 +130,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16x(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
@@ -308,6 +316,25 @@ __device__ __forceinline__ void store_group_rows(__nv_bfloat16* base, long long 
       *reinterpret_cast<uint4*>(base + (rbase + i) * ld + 8 * j) = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
 }
 
+// The 16-column version (R = this lane's 16 bf16 = two 16-byte pieces of its own row): after one exchange inside a lane
+// pair, lane 2i + p holds piece p of rows 2i and 2i + 1; each of the two stores writes 16 rows x 32 contiguous bytes.
+__device__ __forceinline__ void store_group_rows16(__nv_bfloat16* base, long long row0, long long n_rows, long long ld,
+                                                   const uint32_t (&R)[8], int lane) {
+  const bool odd = lane & 1;
+  uint32_t keep[4], recv[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const uint32_t send = odd ? R[e] : R[4 + e];
+    recv[e] = __shfl_xor_sync(0xffffffffu, send, 1);
+    keep[e] = odd ? R[4 + e] : R[e];
+  }
+  const long long rbase = row0 + (lane & ~1);
+  __nv_bfloat16* dst = base + rbase * ld + (odd ? 8 : 0);
+  if (rbase < n_rows)
+    *reinterpret_cast<uint4*>(dst) = odd ? make_uint4(recv[0], recv[1], recv[2], recv[3]) : make_uint4(keep[0], keep[1], keep[2], keep[3]);
+  if (rbase + 1 < n_rows)
+    *reinterpret_cast<uint4*>(dst + ld) = odd ? make_uint4(keep[0], keep[1], keep[2], keep[3]) : make_uint4(recv[0], recv[1], recv[2], recv[3]);
+}
 
 // ------------------------------------------------------------------ CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
