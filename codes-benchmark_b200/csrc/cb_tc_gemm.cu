@@ -45,15 +45,19 @@ constexpr int kNumStaging = 3;                 // ring of output blocks: aux pre
 constexpr int kMaxAuxSlots = 8;                // direct-store data-gradient epilogue: ring of prefetched h / z blocks
 constexpr int kThreads = 320;
 constexpr int kEpiThreads = 256;
-// The bf16 data-gradient epilogue (act' from the saved activation, pack, store) is a ~400-instruction dependent chain
-// per 64-column block that two warps per scheduler cannot hide (profiles/r2_train_gemm275_ncu.md): that mode runs
-// SIXTEEN epilogue warps, four per TMEM lane quarter, 16 columns of every 64-column block each.
-constexpr int kEpiWarpsDgrad = 16;
-constexpr int kThreadsDgrad = 64 + 32 * kEpiWarpsDgrad;
+// The bf16 epilogues (activation or act' from the saved activation, pack, store) are a ~400-instruction dependent chain
+// per 64-column block that two warps per scheduler cannot hide (profiles/r2_train_gemm275_ncu.md): the plain bf16
+// forward and data-gradient modes run SIXTEEN epilogue warps, four per TMEM lane quarter, 16 columns of every
+// 64-column block each.
+constexpr int kEpiWarpsWide = 16;
+constexpr int kThreadsWide = 64 + 32 * kEpiWarpsWide;
+__host__ __device__ constexpr bool wide_epilogue(int mode) { return mode == 0 /* EPI_FWD_BF16 */ || mode == 2 /* EPI_DGRAD_BF16 */; }
 constexpr int kAccCols = 256;                  // TMEM columns per accumulator slot
 constexpr int kCtrl = 256;
 
-enum { EPI_FWD_BF16 = 0, EPI_FWD_F32 = 1, EPI_DGRAD_BF16 = 2, EPI_DGRAD_F32 = 3, EPI_WGRAD = 4 };
+// EPI_FWD_X3: the split-precision ("bf16x3") forward -- three bf16 output segments per block, eight epilogue warps of 32
+// columns; the plain bf16 forward and data-gradient modes run sixteen epilogue warps of 16 columns
+enum { EPI_FWD_BF16 = 0, EPI_FWD_F32 = 1, EPI_DGRAD_BF16 = 2, EPI_DGRAD_F32 = 3, EPI_WGRAD = 4, EPI_FWD_X3 = 5 };
 enum { AUX_NONE = 0, AUX_H = 1, AUX_Z = 2 };
 
 static_assert(16 * kMaxStages + 32 + 8 * kMaxAuxSlots + 8 <= kCtrl, "control block too small");
@@ -68,7 +72,6 @@ static_assert(16 * kMaxStages + 32 + 8 * kMaxAuxSlots + 8 <= kCtrl, "control blo
 
 struct GemmParams {
   CUtensorMap tmA, tmB;        // operand loads
-  CUtensorMap tmOut, tmOut2;   // bf16 stores: activation (or gradient) / pre-activation
   CUtensorMap tmAux;           // dgrad: h (AUX_H) or z (AUX_Z) of the layer whose pre-activation gradient is produced
   int m_tiles, n_tiles, n_blocks, splits;
   int kblocks, kb_per_split, last_nks;
@@ -87,13 +90,10 @@ struct GemmParams {
   int n_terms, kk_total;       // kk_total = n_terms * kblocks
   int a_seg_cols, b_seg_cols;
   int8_t term_a[8], term_b[8];
-  int out_segs, out_seg_cols;  // EPI_FWD_BF16: the activation leaves as out_segs segments out_seg_cols columns apart
+  int out_segs, out_seg_cols;  // EPI_FWD_X3: the activation leaves as out_segs segments out_seg_cols columns apart; 1 otherwise
   __nv_bfloat16* out_seg_ptr;  //   ... written with direct (quad-transposed, row-contiguous) stores to (m_bound, out_seg_ld)
   long long out_seg_ld;
-  // direct_out (plain bf16 EPI_FWD_BF16 / EPI_DGRAD_BF16): the epilogue stores its 32-column groups straight from
-  // registers to out_seg_ptr (and the pre-activation to out2_ptr) instead of staging 64-column blocks for TMA stores
-  int direct_out;
-  __nv_bfloat16* out2_ptr;
+  __nv_bfloat16* out2_ptr;     // EPI_FWD_BF16 with save_z: the bf16 pre-activation, same layout as out_seg_ptr
   int aux_slots;               // direct data-gradient epilogue: slots of the aux ring, prefetch distance aux_slots - 1
   long long* dbg;              // CB_TC_GEMM_DBG: cycle counters of CTA 0, else NULL
 };
@@ -147,6 +147,26 @@ __device__ __forceinline__ void act_block_rt(int act, const uint32_t (&v)[32], f
     case CB_ACT_MISH: act_block<CB_ACT_MISH>(v, f, p); break;
     case CB_ACT_SIGMOID: act_block<CB_ACT_SIGMOID>(v, f, p); break;
     default: act_block<CB_ACT_IDENTITY>(v, f, p); break;
+  }
+}
+template <int ACT>
+__device__ __forceinline__ void act_block16(const uint32_t (&v)[16], float (&f)[16], float p) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = act_fast<ACT>(__uint_as_float(v[i]), p);
+}
+__device__ __forceinline__ void act_block16_rt(int act, const uint32_t (&v)[16], float (&f)[16], float p) {
+  switch (act) {
+    case CB_ACT_RELU: act_block16<CB_ACT_RELU>(v, f, p); break;
+    case CB_ACT_LEAKYRELU:
+    case CB_ACT_PRELU: act_block16<CB_ACT_LEAKYRELU>(v, f, p); break;
+    case CB_ACT_TANH: act_block16<CB_ACT_TANH>(v, f, p); break;
+    case CB_ACT_GELU: act_block16<CB_ACT_GELU>(v, f, p); break;
+    case CB_ACT_ELU: act_block16<CB_ACT_ELU>(v, f, p); break;
+    case CB_ACT_SILU: act_block16<CB_ACT_SILU>(v, f, p); break;
+    case CB_ACT_SOFTPLUS: act_block16<CB_ACT_SOFTPLUS>(v, f, p); break;
+    case CB_ACT_MISH: act_block16<CB_ACT_MISH>(v, f, p); break;
+    case CB_ACT_SIGMOID: act_block16<CB_ACT_SIGMOID>(v, f, p); break;
+    default: act_block16<CB_ACT_IDENTITY>(v, f, p); break;
   }
 }
 // act'(.) from the saved activation h = act(z) (FROM_Z = false) or from the saved pre-activation z
@@ -229,16 +249,11 @@ __device__ __forceinline__ void dact_block_rt(int act, int aux_kind, const uint3
 __device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
 }
-__device__ __forceinline__ void tma_store_wait_read_le(int n) {
-  if (n == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  else if (n == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-  else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-}
 
 template <int MODE>
-__global__ void __launch_bounds__(MODE == EPI_DGRAD_BF16 ? kThreadsDgrad : kThreads, 1)
+__global__ void __launch_bounds__(wide_epilogue(MODE) ? kThreadsWide : kThreads, 1)
 gemm_kernel(const __grid_constant__ GemmParams P) {
-  constexpr int kEpiThreadsM = MODE == EPI_DGRAD_BF16 ? 32 * kEpiWarpsDgrad : kEpiThreads;
+  constexpr int kEpiThreadsM = wide_epilogue(MODE) ? 32 * kEpiWarpsWide : kEpiThreads;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -352,9 +367,7 @@ gemm_kernel(const __grid_constant__ GemmParams P) {
     const int h = (warp - 2) >> 2;          // column half: columns [32h, 32h+32) of every 64-column block
     const int et = threadIdx.x - 64;        // 0..255
     const bool leader = et == 0;
-    constexpr bool kStaged = MODE == EPI_FWD_BF16 || MODE == EPI_DGRAD_BF16;
     const bool has_aux = MODE == EPI_DGRAD_BF16 && P.aux_kind != AUX_NONE;
-    int gb = 0;                              // staging-ring position (one per bf16 block stored)
     int li = 0;
     // direct-store data gradient: the leader's prefetch cursor walks the CTA's (item, block) sequence aux_slots - 1
     // blocks ahead of the epilogue (the saved activations come from HBM: one block ahead left every block waiting
@@ -375,15 +388,8 @@ gemm_kernel(const __grid_constant__ GemmParams P) {
         if (pf_item < n_items) pf_it = decode_item(P, pf_item);
       }
     };
-    if (has_aux && leader) {
-      if (MODE == EPI_DGRAD_BF16) {
-        for (int i = 0; i + 1 < P.aux_slots; ++i) prefetch_aux();
-      } else if ((int)blockIdx.x < n_items) {
-        const Item it0 = decode_item(P, blockIdx.x);
-        mbar_arrive_expect_tx(bar_aux, kStaging);
-        tma_load_2d(OST, &P.tmAux, it0.n_blk0 * 64, it0.m_tile * kTileM, bar_aux);
-      }
-    }
+    if (has_aux && leader)
+      for (int i = 0; i + 1 < P.aux_slots; ++i) prefetch_aux();
     long long g_tfull = 0, g_aux = 0, g_bar = 0, g_ld = 0, g_st = 0, g_pf = 0;
     const long long g_start = GCLK();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
@@ -446,18 +452,48 @@ gemm_kernel(const __grid_constant__ GemmParams P) {
           const long long g2 = GCLK();
           store_group_rows16(P.out_seg_ptr + c16, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
           g_st += GCLK() - g2;
-          gb += 1;
+          continue;
+        }
+        if constexpr (MODE == EPI_FWD_BF16) {
+          // sixteen warps, 16 columns each: activation, bf16, row-contiguous stores straight from registers (no
+          // shared-memory round trip, proxy fence, CTA barrier or store wait per block); GELU / SiLU / Mish nets also
+          // keep the pre-activation for the backward pass
+          const int c16 = col_blk + h * 16;
+          uint32_t v[16];
+          tmem_ld16x(taddr + cb * 64 + h * 16, v);
+          tmem_ld_wait();
+          float f[16];
+          act_block16_rt(P.act, v, f, P.act_param);
+          const bool edge = c16 + 16 > P.n_true;
+          if (edge) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = c16 + i;
+              f[i] = col < P.n_true ? f[i] : (col == P.ones_col ? 1.f : 0.f);
+            }
+          }
+          uint32_t R[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) R[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+          store_group_rows16(P.out_seg_ptr + c16, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
+          if (P.save_z) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = (!edge || c16 + i < P.n_true) ? __uint_as_float(v[i]) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) R[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+            store_group_rows16(P.out2_ptr + c16, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
+          }
           continue;
         }
         const int col0 = col_blk + h * 32;                  // first column owned by this thread
         uint32_t v[32];
         tmem_ld32(taddr + cb * 64 + h * 32, v);
-        if (MODE == EPI_FWD_BF16 && P.out_segs > 1) {
+        if constexpr (MODE == EPI_FWD_X3) {
           // split precision: hi / mid / lo bf16 segments of the fp32 activation, f <- f - bf16(f) between the passes,
-          // written straight from registers with row-contiguous stores (8 rows x 64 B per instruction).  The staged
-          // TMA-store path below costs a shared-memory round trip, a proxy fence, two CTA barriers and a wait on the
-          // previous store per segment: with three segments per block it, not the MMAs, set the pace of the hidden
-          // layers (tensor pipe 22 % active, profiles/r2_tc_kernels_ncu_full.md).
+          // written straight from registers with row-contiguous stores (8 rows x 64 B per instruction).  (Staging the
+          // blocks in shared memory for TMA stores cost a round trip, a proxy fence, two CTA barriers and a wait on the
+          // previous store per segment: with three segments per block that, not the MMAs, set the pace of the hidden
+          // layers -- tensor pipe 22 % active, profiles/r2_tc_kernels_ncu_full.md.)
           tmem_ld_wait();
           float f[32];
 #pragma unroll
@@ -479,126 +515,6 @@ gemm_kernel(const __grid_constant__ GemmParams P) {
             }
             store_group_rows(P.out_seg_ptr + (long long)pass * P.out_seg_cols + col0, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
           }
-        } else if (MODE == EPI_FWD_BF16 && P.direct_out) {
-          // plain bf16 forward, direct stores: no shared-memory round trip, proxy fence, CTA barrier or store wait per
-          // 64-column block -- with K = 288 (the 275-wide MultiONet layers) a tile's MMAs take 3.3 k cycles, the staged
-          // epilogue of its four blocks took twice that (gemm_kernel<0> 490 TFLOP/s on the last Linears)
-          tmem_ld_wait();
-          float f[32];
-          act_block_rt(P.act, v, f, P.act_param);
-          const bool edge = col0 + 32 > P.n_true;
-          uint32_t R[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = f[2 * i], b = f[2 * i + 1];
-            if (edge) {
-              const int col = col0 + 2 * i;
-              if (col >= P.n_true) a = (col == P.ones_col) ? 1.f : 0.f;
-              if (col + 1 >= P.n_true) b = (col + 1 == P.ones_col) ? 1.f : 0.f;
-            }
-            R[i] = pack_bf16(a, b);
-          }
-          store_group_rows(P.out_seg_ptr + col0, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
-          if (P.save_z) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
-              if (edge) {
-                const int col = col0 + 2 * i;
-                if (col >= P.n_true) a = 0.f;
-                if (col + 1 >= P.n_true) b = 0.f;
-              }
-              R[i] = pack_bf16(a, b);
-            }
-            store_group_rows(P.out2_ptr + col0, row_g - lane, P.m_bound, P.out_seg_ld, R, lane);
-          }
-        } else if constexpr (kStaged) {
-          const int buf = gb % kNumStaging;
-          const uint32_t ost = OST + buf * kStaging;
-          if (leader) {
-            // ring slot (gb+1) was last read by the store issued two blocks ago
-            tma_store_wait_read_le(1);
-            if (has_aux) {
-              // prefetch the aux block of the NEXT output block into the next ring slot
-              int nm = it.m_tile, nc = col_blk + 64;
-              bool more = true;
-              if (cb + 1 == it.n_nblk) {
-                more = item + (int)gridDim.x < n_items;
-                if (more) { const Item nx = decode_item(P, item + gridDim.x); nm = nx.m_tile; nc = nx.n_blk0 * 64; }
-              }
-              if (more) {
-                const int nb = (gb + 1) % kNumStaging;
-                mbar_arrive_expect_tx(bar_aux + 8 * nb, kStaging);
-                tma_load_2d(OST + nb * kStaging, &P.tmAux, nc, nm * kTileM, bar_aux + 8 * nb);
-              }
-            }
-          }
-          float f[32];
-          if constexpr (MODE == EPI_DGRAD_BF16) {
-            if (has_aux) {
-              uint32_t aw[16];
-              mbar_wait(bar_aux + 8 * buf, (uint32_t)(gb / kNumStaging) & 1);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int c8 = h * 4 + g;
-                ld_shared_v4(ost + (uint32_t)(r * 128 + ((c8 ^ (r & 7)) << 4)), aw[g * 4], aw[g * 4 + 1], aw[g * 4 + 2],
-                             aw[g * 4 + 3]);
-              }
-              tmem_ld_wait();
-              dact_block_rt(P.act, P.aux_kind, v, aw, f, P.act_param);
-            } else {
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-            }
-          } else {
-            tmem_ld_wait();
-            if (P.out_segs > 1) {
-              // split precision: the accurate activations of the fp32 path (cb_common.cuh), not the MUFU approximations
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = act_fwd(P.act, __uint_as_float(v[i]), P.act_param);
-            } else {
-              act_block_rt(P.act, v, f, P.act_param);
-            }
-          }
-          // passes: the activation [, its pre-activation (save_z)] -- or, split precision, the hi / mid / lo bf16
-          // segments of the fp32 activation: f <- f - bf16(f) after every pass
-          const bool split_out = MODE == EPI_FWD_BF16 && P.out_segs > 1;
-          const int n_pass = split_out ? P.out_segs : ((MODE == EPI_FWD_BF16 && P.save_z) ? 2 : 1);
-          for (int pass = 0; pass < n_pass; ++pass) {
-            const int pbuf = (gb + pass) % kNumStaging;
-            const uint32_t pst = OST + pbuf * kStaging;
-            if (pass >= 1) {
-              if (leader) tma_store_wait_read_le(1);
-              asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
-            const bool edge = col0 + 32 > P.n_true;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float o[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float val = (pass == 0 || split_out) ? f[g * 8 + i] : __uint_as_float(v[g * 8 + i]);
-                if (edge) {
-                  const int col = col0 + g * 8 + i;
-                  if (col >= P.n_true) val = (pass == 0 && col == P.ones_col) ? 1.f : 0.f;
-                }
-                o[i] = val;
-                if (split_out) f[g * 8 + i] = val - __bfloat162float(__float2bfloat16_rn(val));
-              }
-              const int c8 = h * 4 + g;
-              st_shared_v4(pst + (uint32_t)(r * 128 + ((c8 ^ (r & 7)) << 4)), pack_bf16(o[0], o[1]),
-                           pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-            }
-            fence_proxy_async();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (leader) {
-              if (split_out) tma_store_2d(&P.tmOut, pst, col_blk + pass * P.out_seg_cols, it.m_tile * kTileM);
-              else tma_store_2d(pass == 0 ? &P.tmOut : &P.tmOut2, pst, col_blk, it.m_tile * kTileM);
-              tma_store_commit();
-            }
-          }
-          gb += n_pass;
         } else if constexpr (MODE == EPI_WGRAD) {
           tmem_ld_wait();
           if (row_g < P.m_bound) {
@@ -632,10 +548,6 @@ gemm_kernel(const __grid_constant__ GemmParams P) {
       mbar_arrive(bar_tempty + 8 * slot);
     }
     if (P.dbg && blockIdx.x == 0 && et == 0) { P.dbg[6] = GCLK() - g_start; P.dbg[7] = g_tfull; P.dbg[8] = g_aux; P.dbg[9] = g_bar; P.dbg[10] = g_ld; P.dbg[11] = g_st; P.dbg[12] = g_pf; }
-    if constexpr (kStaged) {
-      // the bulk stores must be complete before the kernel's writes are consumed / shared memory is released
-      if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -949,15 +861,10 @@ static cudaError_t set_smem_attr() {
   return e;
 }
 
-// CB_TC_GEMM_DIRECT=0: the plain bf16 forward epilogue goes back to staged TMA stores (comparison switch)
-static bool gemm_direct_out() {
-  static const int v = [] { const char* e = getenv("CB_TC_GEMM_DIRECT"); return (e && atoi(e) == 0) ? 0 : 1; }();
-  return v != 0;
-}
-
 static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
   GemmParams P;
   memset(&P, 0, sizeof(P));
+  const int mode = (c.x3 && c.mode == EPI_FWD_BF16) ? EPI_FWD_X3 : c.mode;     // kernel instantiation
   P.n_blocks = c.n_out_ld / 64;
   P.n_tiles = (P.n_blocks + 3) / 4;
   P.m_tiles = (int)((c.m_out + kTileM - 1) / kTileM);
@@ -978,32 +885,31 @@ static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
     P.a_seg_cols = (int)c.a_ld; P.b_seg_cols = (int)c.b_ld;
     P.kk_total = P.n_terms * P.kblocks;
     P.kb_per_split = P.kk_total;
-    if (c.mode == EPI_FWD_BF16) {
+    if (mode == EPI_FWD_X3) {
       P.out_segs = 3; P.out_seg_cols = (int)c.out_ld;
       P.out_seg_ptr = c.out_bf16; P.out_seg_ld = 3 * c.out_ld;
     }
   }
   CB_CHECK_ARG(!(c.x3 && c.mode == EPI_DGRAD_BF16), "split precision: forward GEMMs only");
-  if (c.mode == EPI_DGRAD_BF16 || (!c.x3 && c.mode == EPI_FWD_BF16 && gemm_direct_out())) {
-    P.direct_out = 1;
-    P.out_seg_ptr = c.out_bf16; P.out_seg_ld = c.out_ld; P.out2_ptr = c.out2_bf16;
-  }
+  if (wide_epilogue(mode)) { P.out_seg_ptr = c.out_bf16; P.out_seg_ld = c.out_ld; P.out2_ptr = c.out2_bf16; }
   const long long seg_mul = c.x3 ? 3 : 1;
   P.a_mn = c.a_mn; P.b_mn = c.b_mn;
   const int widest = (P.n_blocks + P.n_tiles - 1) / P.n_tiles;
   P.b_box_rows = widest * 64;
   P.stage_bytes = kStageA + widest * kBoxBytes;
-  P.staging_bytes = c.mode == EPI_WGRAD ? 0 : kNumStaging * kStaging;
+  // shared memory besides the operand stages: the fp32-output modes transpose 128 x 64 floats through it, the data
+  // gradient keeps its ring of prefetched saved-activation blocks there, the other modes store from registers
+  P.staging_bytes = (mode == EPI_FWD_F32 || mode == EPI_DGRAD_F32) ? kNumStaging * kStaging : 0;
   P.aux_slots = kNumStaging;
-  if (P.direct_out && c.mode == EPI_FWD_BF16) P.staging_bytes = 0;     // nothing staged: the space goes to operand stages
-  if (P.direct_out && c.mode == EPI_DGRAD_BF16 && c.aux_kind != AUX_NONE) {
-    // all slots prefetch (nothing is staged for stores): as many as leave three operand stages -- four when the
-    // reduction is long (there the epilogue is rare and the operand pipeline sets the pace)
+  if (mode == EPI_DGRAD_BF16 && c.aux_kind != AUX_NONE) {
+    // as many slots as leave three operand stages -- four when the reduction is long (there the epilogue is rare and
+    // the operand pipeline sets the pace)
     const int keep_stages = P.kblocks > 8 ? 4 : 3;
     int slots = (kMaxSmem - 1024 - kCtrl - keep_stages * P.stage_bytes) / kStaging;
     slots = slots > kMaxAuxSlots ? kMaxAuxSlots : slots;
     if (const char* e = getenv("CB_TC_GEMM_AUX_SLOTS")) { const int v = atoi(e); if (v >= 2 && v <= kMaxAuxSlots) slots = v; }
-    if (slots >= 2) { P.aux_slots = slots; P.staging_bytes = slots * kStaging; }
+    if (slots < 2) slots = 2;
+    P.aux_slots = slots; P.staging_bytes = slots * kStaging;
   }
   P.stages = (kMaxSmem - 1024 - P.staging_bytes - kCtrl) / P.stage_bytes;
   if (P.stages > kMaxStages) P.stages = kMaxStages;
@@ -1018,27 +924,28 @@ static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
   else ok = ok && encode_bf16_box(&P.tmA, c.A, c.a_rows, c.a_cols * seg_mul, c.a_ld * seg_mul, 64, kTileM);
   if (c.b_mn) ok = ok && encode_bf16_box(&P.tmB, c.B, c.b_rows, c.b_cols, c.b_ld, 64, 64);
   else ok = ok && encode_bf16_box(&P.tmB, c.B, c.b_rows, c.b_cols * seg_mul, c.b_ld * seg_mul, 64, P.b_box_rows);
-  if (c.out_bf16) ok = ok && encode_bf16_box(&P.tmOut, c.out_bf16, c.out_rows, c.out_ld * seg_mul, c.out_ld * seg_mul, 64, kTileM);
-  if (c.out2_bf16) ok = ok && encode_bf16_box(&P.tmOut2, c.out2_bf16, c.out_rows, c.out_ld, c.out_ld, 64, kTileM);
   if (c.aux_kind != AUX_NONE) ok = ok && encode_bf16_box(&P.tmAux, c.aux, c.out_rows, c.ld_aux, c.ld_aux, 64, kTileM);
   CB_CHECK_ARG(ok, "cuTensorMapEncodeTiled failed for a GEMM operand");
   const long long items = (long long)P.m_tiles * P.n_tiles * P.splits;
   const int grid = (int)(items < num_sms() ? items : num_sms());
 #ifdef CB_TC_GEMM_DBG
   if (const char* e = getenv("CB_TC_GEMM_DBG")) {
-    if (atoi(e) == c.mode) { CB_CUDA(cudaMalloc(&P.dbg, 104)); CB_CUDA(cudaMemsetAsync(P.dbg, 0, 104, st)); }
+    if (atoi(e) == mode) { CB_CUDA(cudaMalloc(&P.dbg, 104)); CB_CUDA(cudaMemsetAsync(P.dbg, 0, 104, st)); }
   }
 #endif
-  switch (c.mode) {
+  switch (mode) {
     case EPI_FWD_BF16:
       CB_CUDA(set_smem_attr<EPI_FWD_BF16>());
-      gemm_kernel<EPI_FWD_BF16><<<grid, kThreads, smem, st>>>(P); break;
+      gemm_kernel<EPI_FWD_BF16><<<grid, kThreadsWide, smem, st>>>(P); break;
+    case EPI_FWD_X3:
+      CB_CUDA(set_smem_attr<EPI_FWD_X3>());
+      gemm_kernel<EPI_FWD_X3><<<grid, kThreads, smem, st>>>(P); break;
     case EPI_FWD_F32:
       CB_CUDA(set_smem_attr<EPI_FWD_F32>());
       gemm_kernel<EPI_FWD_F32><<<grid, kThreads, smem, st>>>(P); break;
     case EPI_DGRAD_BF16:
       CB_CUDA(set_smem_attr<EPI_DGRAD_BF16>());
-      gemm_kernel<EPI_DGRAD_BF16><<<grid, kThreadsDgrad, smem, st>>>(P); break;
+      gemm_kernel<EPI_DGRAD_BF16><<<grid, kThreadsWide, smem, st>>>(P); break;
     case EPI_DGRAD_F32:
       CB_CUDA(set_smem_attr<EPI_DGRAD_F32>());
       gemm_kernel<EPI_DGRAD_F32><<<grid, kThreads, smem, st>>>(P); break;
@@ -1055,7 +962,7 @@ static int32_t launch_gemm(const GemmCall& c, cudaStream_t st) {
     cudaFree(P.dbg);
     fprintf(stderr, "[gemm dbg] mode %d  m_tiles %d n_tiles %d kblocks %d stages %d aux_slots %d | producer: total %lld, wait empty %lld | "
                     "MMA: total %lld over %lld items, wait TMEM slot %lld, wait operands %lld | epilogue t0: total %lld, wait accumulator "
-                    "%lld, wait aux %lld, block barrier %lld, wait tcgen05.ld %lld, stores %lld, leader prefetch %lld\n", c.mode, P.m_tiles, P.n_tiles, P.kblocks, P.stages, P.aux_slots,
+                    "%lld, wait aux %lld, block barrier %lld, wait tcgen05.ld %lld, stores %lld, leader prefetch %lld\n", mode, P.m_tiles, P.n_tiles, P.kblocks, P.stages, P.aux_slots,
             h[0], h[1], h[2], h[5], h[3], h[4], h[6], h[7], h[8], h[9], h[10], h[11], h[12]);
   }
 #endif
