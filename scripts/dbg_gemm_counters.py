@@ -11,6 +11,19 @@ from codes_b200.synthetic import synthetic_dataset
 
 DEV = "cuda:0"
 torch.manual_seed(0)
+if len(sys.argv) > 1 and sys.argv[1] == "fcnn":
+    # gradient-free forward of FullyConnected cfg1 (6 -> 800 x 8 -> 5): nine per-layer GEMM launches
+    cb.set_precision("bf16")
+    m = cb.FullyConnected(DEV, 5, 101, 0, None, {"hidden_size": 800, "num_hidden_layers": 8, "activation": nn.GELU()})
+    m.eval()
+    x = torch.rand(65536, 6, device=DEV)
+    with torch.no_grad():
+        for i in range(2):
+            if i == 1:
+                print("---- step 2 (warm)", file=sys.stderr, flush=True)
+            m.model(x)
+    torch.cuda.synchronize()
+    sys.exit(0)
 Q, T = 29, 100
 m = cb.MultiONet(DEV, Q, T, 0, None, {"hidden_size": 275, "branch_hidden_layers": 5, "trunk_hidden_layers": 9,
                                       "output_factor": 98, "activation": nn.LeakyReLU(), "learning_rate": 4e-5})
