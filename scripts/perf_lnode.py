@@ -9,7 +9,8 @@ with torch.no_grad():
     for p in m.model.ode.mlp.parameters():
         p.mul_(float(os.environ.get("SCALE", "1")))
 w, b = ops.sequential_params(m.model.ode.mlp)
-z0 = (torch.rand(65536, 5, device="cuda:0") * 2 - 1)
+NB = int(os.environ.get("NB", "65536"))
+z0 = (torch.rand(NB, 5, device="cuda:0") * 2 - 1)
 t = torch.linspace(0, 1, 100, device="cuda:0")
 for _ in range(3):
     zs, st = ops.lnode_solve(m.model.ode.chain(), w, b, z0, t, True, 1.0, 1e-6, 1e-6, return_stats=True)
@@ -21,5 +22,5 @@ for _ in range(5):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 S = st[:, 0].float().mean().item()
-flop = 2 * 17024 * (6 * S + 2) * 65536
-print(f"lnode solve 65536 traj: {ms:.3f} ms, mean steps {S:.2f} max {st[:,0].max().item()}, {65536/ms*1e3/1e6:.2f} M traj/s, {flop/ms/1e9:.2f} TFLOP/s fp32")
+flop = 2 * 17024 * (6 * S + 2) * NB
+print(f"lnode solve {NB} traj (CB_LNODE_TB={os.environ.get('CB_LNODE_TB', 'auto')}): {ms:.3f} ms, mean steps {S:.2f} max {st[:,0].max().item()}, {NB/ms*1e3/1e6:.2f} M traj/s, {flop/ms/1e9:.2f} TFLOP/s fp32")
