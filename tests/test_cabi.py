@@ -54,6 +54,19 @@ def test_host_side_queries_do_not_need_a_gpu():
     assert b"dims" in L.cb_last_error()
 
 
+def test_training_entry_points_reject_bad_arguments_without_a_gpu():
+    """The entry points added for MultiONet's fused training forward validate their arguments before any CUDA call:
+    status != 0 and a message in cb_last_error(), no crash."""
+    from codes_b200 import _lib
+    L = _lib.lib()
+    null = C.c_void_p(None)
+    assert L.cb_tc_multionet_final_train(null, null, null, null, null, null, null, 320, 128, null, null, null, 2880, null) != 0
+    assert b"plan" in L.cb_last_error()
+    assert L.cb_tc_train_forward_hidden(null, None, None, null, 128, null, 0, null) != 0
+    assert b"NULL" in L.cb_last_error()
+    assert L.cb_tc_train_saved_offset(null, 128, 0) == -1
+
+
 def test_missing_cuda_fails_loudly():
     import torch
     import pytest
