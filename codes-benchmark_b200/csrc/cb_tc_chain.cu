@@ -1716,15 +1716,16 @@ extern "C" int32_t cb_tc_chain_set_weights(cb_tc_chain* plan, const float* const
                                            void* stream) {
   CB_CHECK_ARG(plan && d_W && d_b, "NULL pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < plan->P.n_layers; ++i) CB_CHECK_ARG(d_W[i] != nullptr, "weight %d is NULL", i);
+  if (plan->mt) {
+    if (int32_t e = cb::tcmt::mt_pack_weights_all(d_W, d_b, plan->P.N, plan->P.K, plan->P.n_layers, plan->d_w, st)) return e;
+    plan->weights_set = 1;
+    return CB_OK;
+  }
   for (int i = 0; i < plan->P.n_layers; ++i) {
-    CB_CHECK_ARG(d_W[i] != nullptr, "weight %d is NULL", i);
     const long long total = (long long)plan->rows_alloc[i] * plan->Kp[i];
     int blocks = (int)((total + 255) / 256);
     if (blocks > 1184) blocks = 1184;
-    if (plan->mt) {
-      if (int32_t e = cb::tcmt::mt_pack_weights(d_W[i], d_b[i], plan->P.N[i], plan->P.K[i], plan->d_w[i], st)) return e;
-      continue;
-    }
     if (plan->ts)
       pack_weights_ts_kernel<<<blocks, 256, 0, st>>>(d_W[i], d_b[i], plan->P.N[i], plan->P.K[i], plan->rows_alloc[i],
                                                     plan->Kp[i], ts_split(plan->rows_alloc[i]), plan->d_w[i]);

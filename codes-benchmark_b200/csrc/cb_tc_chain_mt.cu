@@ -455,6 +455,57 @@ __global__ void mt_pack_kernel(const float* __restrict__ W, const float* __restr
 static int rup(int v, int m) { return (v + m - 1) / m * m; }
 static int kp_of(int K) { return ((K + 1 + kUmmaK - 1) / kUmmaK + 3) / 4 * kBlockK; }
 
+// Every layer of a chain in ONE launch (a training step re-packs all of them: the per-layer launches were 14 of the
+// ~95 sub-10-us launches of a MultiONet step): element i of the concatenated index space belongs to layer t with
+// start[t] <= i < start[t+1].
+struct MtPackList {
+  const float* W[CB_MAX_LAYERS]; const float* b[CB_MAX_LAYERS];
+  __nv_bfloat16* Wp[CB_MAX_LAYERS];
+  int N[CB_MAX_LAYERS], K[CB_MAX_LAYERS], Np[CB_MAX_LAYERS], Kp[CB_MAX_LAYERS];
+  long long start[CB_MAX_LAYERS + 1];
+  int count;
+};
+__global__ void mt_pack_multi_kernel(const MtPackList L) {
+  const long long total = L.start[L.count];
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    int t = 0;
+    while (g >= L.start[t + 1]) ++t;
+    const long long i = g - L.start[t];
+    const int N = L.N[t], K = L.K[t], Np = L.Np[t], Kp = L.Kp[t];
+    const int nkb = Kp / kBlockK;
+    const int n = (int)(i / Kp), k = (int)(i % Kp);
+    float v = 0.f;
+    if (n < N) {
+      if (k < K) v = L.W[t][(long long)n * K + k];
+      else if (k == K && L.b[t]) v = L.b[t][n];
+    }
+    const int n0 = n / kMtChunk * kMtChunk;
+    const int rows = min(kMtChunk, Np - n0);
+    const int r = n - n0, kb = k / kBlockK, kk = k % kBlockK;
+    const size_t off = ((size_t)n0 * nkb + (size_t)kb * rows + r) * kBlockK + (size_t)(((kk >> 3) ^ (r & 7)) << 3) + (kk & 7);
+    L.Wp[t][off] = __float2bfloat16(v);
+  }
+}
+
+int32_t mt_pack_weights_all(const float* const* d_W, const float* const* d_b, const int* N, const int* K, int n_layers,
+                            __nv_bfloat16* const* d_out, cudaStream_t st) {
+  MtPackList L;
+  memset(&L, 0, sizeof(L));
+  long long total = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    L.W[i] = d_W[i]; L.b[i] = d_b[i]; L.Wp[i] = d_out[i];
+    L.N[i] = N[i]; L.K[i] = K[i]; L.Np[i] = rup(N[i], 16); L.Kp[i] = kp_of(K[i]);
+    L.start[i] = total;
+    total += (long long)L.Np[i] * L.Kp[i];
+  }
+  L.start[n_layers] = total; L.count = n_layers;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  mt_pack_multi_kernel<<<blocks, 256, 0, st>>>(L);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
 size_t mt_packed_elems(int N, int K) { return (size_t)rup(N, 16) * kp_of(K); }
 
 int32_t mt_pack_weights(const float* d_W, const float* d_b, int N, int K, __nv_bfloat16* d_out, cudaStream_t st) {

@@ -14,7 +14,7 @@
 // holds the constant 1.0 that multiplies the bias column of the packed weights, so the bias add is part
 // of the forward GEMM and db is column `K` of the weight-gradient GEMM.  The weight gradient is
 // split over the batch rows (one (tile, split) work item per CTA); the fp32 partial tiles are reduced in
-// a fixed order by wgrad_reduce_kernel -> deterministic gradients (cf. run_training.py:35).
+// a fixed order by wgrad_reduce_multi_kernel -> deterministic gradients (cf. run_training.py:35).
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 tcgen05.mma issuer (+ TMEM alloc), warps 2-9
 // epilogue (two warps per TMEM lane quarter, alternating 64-column blocks).  Tile = 128 rows x up to 256
@@ -603,37 +603,61 @@ __global__ void pack_dy_kernel(const float* __restrict__ dy, const float* __rest
 
 // fp32 nn.Linear weight (N,K) + bias -> bf16 Wp (rows_alloc, ldK) = [W | b | 0] and its transpose
 // Wt (ldK_rows, ldN) = W^T (no bias row: the ones column carries no gradient).
-__global__ void pack_weight_pair_kernel(const float* __restrict__ W, const float* __restrict__ b, int N, int K,
-                                        int wp_rows, int ldK, int wt_rows, int ldN,
-                                        __nv_bfloat16* __restrict__ Wp, __nv_bfloat16* __restrict__ Wt) {
-  const long long n_wp = (long long)wp_rows * ldK, n_wt = (long long)wt_rows * ldN;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_wp + n_wt;
-       i += (long long)gridDim.x * blockDim.x) {
+// Every layer of a chain in ONE launch (the per-layer launches were a third of the ~95 sub-10-us launches of a
+// MultiONet training step): element g of the concatenated index space belongs to layer t, start[t] <= g < start[t+1].
+struct PackPairList {
+  const float* W[CB_MAX_LAYERS]; const float* b[CB_MAX_LAYERS];
+  __nv_bfloat16* Wp[CB_MAX_LAYERS]; __nv_bfloat16* Wt[CB_MAX_LAYERS];
+  int N[CB_MAX_LAYERS], K[CB_MAX_LAYERS], wp_rows[CB_MAX_LAYERS], ldK[CB_MAX_LAYERS], ldN[CB_MAX_LAYERS];
+  long long start[CB_MAX_LAYERS + 1];     // start[t+1] - start[t] = wp_rows * ldK + wt_rows * ldN
+  int count;
+};
+__global__ void pack_weight_pair_multi_kernel(const PackPairList L) {
+  const long long total = L.start[L.count];
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    int t = 0;
+    while (g >= L.start[t + 1]) ++t;
+    const long long i = g - L.start[t];
+    const int N = L.N[t], K = L.K[t], ldK = L.ldK[t], ldN = L.ldN[t];
+    const long long n_wp = (long long)L.wp_rows[t] * ldK;
+    const float* W = L.W[t];
     if (i < n_wp) {
       const int n = (int)(i / ldK), k = (int)(i % ldK);
       float v = 0.f;
-      if (n < N) v = k < K ? W[(long long)n * K + k] : (k == K && b ? b[n] : 0.f);
-      Wp[i] = __float2bfloat16(v);
+      if (n < N) v = k < K ? W[(long long)n * K + k] : (k == K && L.b[t] ? L.b[t][n] : 0.f);
+      L.Wp[t][i] = __float2bfloat16(v);
     } else {
       const long long j = i - n_wp;
       const int k = (int)(j / ldN), n = (int)(j % ldN);
-      Wt[j] = __float2bfloat16((k < K && n < N) ? W[(long long)n * K + k] : 0.f);
+      L.Wt[t][j] = __float2bfloat16((k < K && n < N) ? W[(long long)n * K + k] : 0.f);
     }
   }
 }
 
-// dW[n,k] = sum_s partial[s][n][k] (k < K), db[n] = sum_s partial[s][n][K]; fixed summation order.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, long long stride, int N, int K,
-                                    int ld, float* __restrict__ dW, float* __restrict__ db) {
-  const long long total = (long long)N * (K + 1);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+// The split reductions of every layer's weight gradient in ONE launch at the end of the backward pass (every layer
+// keeps its own partial region): dW[n,k] = sum_s partial[s][n][k] (k < K), db[n] = sum_s partial[s][n][K], fixed
+// summation order -> deterministic.
+struct WgradReduceList {
+  const float* part[CB_MAX_LAYERS]; float* dW[CB_MAX_LAYERS]; float* db[CB_MAX_LAYERS];
+  long long stride[CB_MAX_LAYERS];
+  int splits[CB_MAX_LAYERS], N[CB_MAX_LAYERS], K[CB_MAX_LAYERS], ld[CB_MAX_LAYERS];
+  long long start[CB_MAX_LAYERS + 1];     // start[t+1] - start[t] = N * (K + 1)
+  int count;
+};
+__global__ void wgrad_reduce_multi_kernel(const WgradReduceList L) {
+  const long long total = L.start[L.count];
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    int t = 0;
+    while (g >= L.start[t + 1]) ++t;
+    const long long i = g - L.start[t];
+    const int K = L.K[t], splits = L.splits[t];
+    const long long stride = L.stride[t];
     const int n = (int)(i / (K + 1)), k = (int)(i % (K + 1));
-    const float* p = part + (long long)n * ld + k;
+    const float* p = L.part[t] + (long long)n * L.ld[t] + k;
     float acc = 0.f;
     for (int s = 0; s < splits; ++s) acc += p[s * stride];
-    if (k < K) dW[(long long)n * K + k] = acc;
-    else if (db) db[n] = acc;
+    if (k < K) L.dW[t][(long long)n * K + k] = acc;
+    else if (L.db[t]) L.db[t][n] = acc;
   }
 }
 
@@ -1080,16 +1104,17 @@ static int wgrad_splits(const cb_tc_train* p, int i, long long rows) {
   return s;
 }
 
+static long long wgrad_part_bytes(const cb_tc_train* p, int i, long long rows) {
+  return round_up_ll((long long)wgrad_splits(p, i, rows) * p->desc.dims[i + 1] * p->ld[i] * 4, 256);
+}
+
 extern "C" int64_t cb_tc_train_scratch_bytes(const cb_tc_train* p, int64_t rows) {
   if (!p || rows < 0) return -1;
   const long long rp = rows_pad(rows);
   int ld_max = 0;
   long long part = 0;
   for (int i = 0; i <= p->n; ++i) ld_max = p->ld[i] > ld_max ? p->ld[i] : ld_max;
-  for (int i = 0; i < p->n; ++i) {
-    const long long b = (long long)wgrad_splits(p, i, rows) * p->desc.dims[i + 1] * p->ld[i] * 4;
-    part = b > part ? b : part;
-  }
+  for (int i = 0; i < p->n; ++i) part += wgrad_part_bytes(p, i, rows);     // one region per layer: ONE reduce launch at the end
   return 2 * rp * ld_max * 2 + part + 512;
 }
 
@@ -1105,12 +1130,20 @@ static int32_t chain_forward_impl(cb_tc_train* p, const float* const* d_W, const
   auto act_ptr = [&](int i) -> __nv_bfloat16* {
     return reinterpret_cast<__nv_bfloat16*>(keep ? buf + saved_offset(p, rows, i, 0) : buf + (size_t)(i & 1) * rp * ld_max * 2);
   };
-  for (int i = 0; i < n; ++i) {
-    CB_CHECK_ARG(d_W[i] != nullptr, "weight %d is NULL", i);
-    const long long total = (long long)p->wp_rows[i] * p->ld[i] + (long long)p->wt_rows[i] * p->ld[i + 1];
-    pack_weight_pair_kernel<<<ew_blocks(total), 256, 0, st>>>(d_W[i], d_b[i], p->desc.dims[i + 1], p->desc.dims[i],
-                                                           p->wp_rows[i], p->ld[i], p->wt_rows[i], p->ld[i + 1],
-                                                           p->wp[i], p->wt[i]);
+  {
+    PackPairList L;
+    memset(&L, 0, sizeof(L));
+    long long total = 0;
+    for (int i = 0; i < n; ++i) {
+      CB_CHECK_ARG(d_W[i] != nullptr, "weight %d is NULL", i);
+      L.W[i] = d_W[i]; L.b[i] = d_b[i]; L.Wp[i] = p->wp[i]; L.Wt[i] = p->wt[i];
+      L.N[i] = p->desc.dims[i + 1]; L.K[i] = p->desc.dims[i];
+      L.wp_rows[i] = p->wp_rows[i]; L.ldK[i] = p->ld[i]; L.ldN[i] = p->ld[i + 1];
+      L.start[i] = total;
+      total += (long long)p->wp_rows[i] * p->ld[i] + (long long)p->wt_rows[i] * p->ld[i + 1];
+    }
+    L.start[n] = total; L.count = n;
+    pack_weight_pair_multi_kernel<<<ew_blocks(total), 256, 0, st>>>(L);
     CB_LAUNCH_CHECK();
   }
   pack_rows_kernel<<<ew_blocks(rows * (p->ld[0] / 8)), 256, 0, st>>>(d_x, rows, p->desc.dims[0], p->ld[0],
@@ -1341,7 +1374,9 @@ extern "C" int32_t cb_tc_train_backward(cb_tc_train* p, const void* d_dy, const 
   const uint8_t* sv = reinterpret_cast<const uint8_t*>(d_saved);
   __nv_bfloat16* dz[2] = {reinterpret_cast<__nv_bfloat16*>(d_scratch),
                           reinterpret_cast<__nv_bfloat16*>(d_scratch) + rp * ld_max};
-  float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d_scratch) + 2 * rp * ld_max * 2 + 256);
+  uint8_t* part_base = reinterpret_cast<uint8_t*>(d_scratch) + 2 * rp * ld_max * 2 + 256;
+  WgradReduceList RL;
+  memset(&RL, 0, sizeof(RL));
   const __nv_bfloat16* cur;
   int pp = 0;
   if (p->out_bf16) {
@@ -1366,15 +1401,15 @@ extern "C" int32_t cb_tc_train_backward(cb_tc_train* p, const void* d_dy, const 
       c.B = hin; c.b_rows = rows; c.b_cols = p->ld[i]; c.b_ld = p->ld[i]; c.b_mn = 1;
       c.m_out = N; c.n_out_ld = p->ld[i]; c.n_true = K + 1; c.k_total = rows;
       c.splits = wgrad_splits(p, i, rows);
+      float* part = reinterpret_cast<float*>(part_base);
+      part_base += wgrad_part_bytes(p, i, rows);
       c.out_f32 = part; c.ld_out_f32 = p->ld[i]; c.partial_stride = (long long)N * p->ld[i];
       if (int32_t e = launch_gemm(c, st)) return e;
       const int kb = (int)((rows + kBlockK - 1) / kBlockK);
       const int per = (kb + c.splits - 1) / c.splits;
-      const int splits = (kb + per - 1) / per;
       CB_CHECK_ARG(d_dW[i] != nullptr, "dW[%d] is NULL", i);
-      wgrad_reduce_kernel<<<ew_blocks((long long)N * (K + 1)), 256, 0, st>>>(part, splits, c.partial_stride, N, K,
-                                                                            p->ld[i], d_dW[i], d_db[i]);
-      CB_LAUNCH_CHECK();
+      RL.part[i] = part; RL.dW[i] = d_dW[i]; RL.db[i] = d_db[i]; RL.stride[i] = c.partial_stride;
+      RL.splits[i] = (kb + per - 1) / per; RL.N[i] = N; RL.K[i] = K; RL.ld[i] = p->ld[i];
     }
     if (i == 0 && !d_dx) break;
     {
@@ -1401,6 +1436,14 @@ extern "C" int32_t cb_tc_train_backward(cb_tc_train* p, const void* d_dy, const 
       cur = dz[pp];
       pp ^= 1;
     }
+  }
+  {
+    // the split reductions of all layers: one launch
+    long long total = 0;
+    for (int i = 0; i < n; ++i) { RL.start[i] = total; total += (long long)RL.N[i] * (RL.K[i] + 1); }
+    RL.start[n] = total; RL.count = n;
+    wgrad_reduce_multi_kernel<<<ew_blocks(total), 256, 0, st>>>(RL);
+    CB_LAUNCH_CHECK();
   }
   return CB_OK;
 }

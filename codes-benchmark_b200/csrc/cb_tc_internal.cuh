@@ -55,6 +55,9 @@ struct MtParams {
 bool mt_supported(const cb_mlp_desc* d, int out_bf16, MtParams* geom /* nullable: nt, aw, slots, slot_bytes, nch.. */);
 size_t mt_packed_elems(int N, int K);
 int32_t mt_pack_weights(const float* d_W, const float* d_b, int N, int K, __nv_bfloat16* d_out, cudaStream_t st);
+// all layers of a chain in one launch
+int32_t mt_pack_weights_all(const float* const* d_W, const float* const* d_b, const int* N, const int* K, int n_layers,
+                            __nv_bfloat16* const* d_out, cudaStream_t st);
 int32_t mt_prepare(int act);   // cudaFuncSetAttribute for the instantiations of this activation
 int32_t mt_launch(const MtParams& P, int act, cudaStream_t st);
 }  // namespace tcmt
