@@ -1,5 +1,5 @@
 // Tensor-core TRAINING path of the dense chains (tcgen05 + TMEM + TMA, sm_100a): one persistent,
-// warp-specialised bf16 GEMM kernel with four epilogues serves the forward layer, the data gradient and
+// warp-specialised bf16 GEMM kernel with six epilogues serves the forward layer, the data gradient and
 // the weight gradient of every nn.Linear of
 //   FullyConnectedNet (fcnn.py:81-98), BranchNet/TrunkNet (deeponet.py:15-84),
 //   Encoder/Decoder (latent_neural_ode.py:687-742)
@@ -16,11 +16,14 @@
 // split over the batch rows (one (tile, split) work item per CTA); the fp32 partial tiles are reduced in
 // a fixed order by wgrad_reduce_multi_kernel -> deterministic gradients (cf. run_training.py:35).
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 tcgen05.mma issuer (+ TMEM alloc), warps 2-9
-// epilogue (two warps per TMEM lane quarter, alternating 64-column blocks).  Tile = 128 rows x up to 256
-// columns (one tcgen05.mma N), k-block = 64; 4 stages of (16 KiB A + 32 KiB B); two 256-column fp32
-// accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.  bf16 outputs leave
-// through a swizzled staging buffer + TMA store, fp32 outputs are stored directly.
+// Warp roles: warp 0 TMA producer, warp 1 tcgen05.mma issuer (+ TMEM alloc), then the epilogue warps -- SIXTEEN for
+// the plain bf16 forward and data-gradient modes (576 threads; four warps per TMEM lane quarter, 16 columns of every
+// 64-column block each), eight for the fp32-output, weight-gradient and split-precision modes (320 threads; 32 columns
+// each).  Tile = 128 rows x up to 256 columns (one tcgen05.mma N), k-block = 64; 3-6 stages of (16 KiB A + <= 32 KiB B);
+// two 256-column fp32 accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.  bf16 outputs are
+// stored straight from registers (pair- / quad-transposed, row-contiguous 16-byte pieces); the fp32 (rows, N) outputs
+// are transposed through shared memory; the data gradient reads the saved activation through a ring of TMA-prefetched
+// 16 KiB blocks.  What bounds which shape: profiles/r2_train_gemm275_ncu.md.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -41,7 +44,7 @@ constexpr int kStageA = 16384;                 // 128 x 64 bf16
 constexpr int kBoxBytes = 8192;                // one 64 x 64 bf16 TMA box = 64 rows of the B operand per k-block
 constexpr int kMaxStages = 6;
 constexpr int kStaging = 16384;                // one 128 x 64 bf16 output block
-constexpr int kNumStaging = 3;                 // ring of output blocks: aux prefetch / compute in place / store drain
+constexpr int kNumStaging = 3;                 // 16 KiB blocks of shared memory behind the operand stages (fp32-output transposes)
 constexpr int kMaxAuxSlots = 8;                // direct-store data-gradient epilogue: ring of prefetched h / z blocks
 constexpr int kThreads = 320;
 constexpr int kEpiThreads = 256;
@@ -258,7 +261,7 @@ gemm_kernel(const __grid_constant__ GemmParams P) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  const uint32_t OST = base + P.stages * P.stage_bytes;       // staging ring (48 KiB; absent for EPI_WGRAD)
+  const uint32_t OST = base + P.stages * P.stage_bytes;       // fp32 transpose scratch / ring of saved-activation blocks
   const uint32_t ctrl = OST + P.staging_bytes;
   const uint32_t bar_full = ctrl, bar_empty = ctrl + 8 * kMaxStages, bar_tfull = ctrl + 16 * kMaxStages,
                  bar_tempty = bar_tfull + 16, bar_aux = bar_tfull + 32;

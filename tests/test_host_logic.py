@@ -311,3 +311,18 @@ def test_reference_written_pth_loads_without_the_reference_package(golden):
     assert m.n_epochs == 1 and m.normalisation["log10_transform"] is True
     assert type(m.config).__name__ == "MultiONetBaseConfig" and m.config.hidden_size == 10
     assert not m.training
+
+
+def test_normalisation_vectors_stay_cached_when_min_and_max_alternate():
+    """denormalize() asks for the `min` and the `max` vector on every call: a cache that holds one entry makes every
+    request a miss, and on CUDA every miss is a synchronous pageable H2D copy (it queued behind the 760 MB target copy
+    of a cfg2 predict() pass and blocked the host for its 13.7 ms)."""
+    m = cb.FullyConnected("cpu", 3, 5, 0, None, {})
+    lo, hi = np.array([-1.0, -2.0, -3.0], dtype=np.float32), np.array([1.0, 2.0, 3.0], dtype=np.float32)
+    a0, b0 = m._norm_vector(lo, 3, "cpu"), m._norm_vector(hi, 3, "cpu")
+    for _ in range(3):
+        assert m._norm_vector(lo, 3, "cpu") is a0
+        assert m._norm_vector(hi, 3, "cpu") is b0
+    assert torch.equal(m._norm_vector(2.5, 3, "cpu"), torch.full((3,), 2.5))          # scalars are broadcast
+    with pytest.raises(ValueError):
+        m._norm_vector(np.zeros(4, dtype=np.float32), 3, "cpu")
